@@ -1,0 +1,19 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a real B200 (run on the GPU box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def kat():
+    import json
+    with open(os.path.join(ROOT, 'tests', 'golden', 'kat_quantizer.json')) as f:
+        return json.load(f)
