@@ -1,0 +1,121 @@
+/*
+ * lbt.h — C ABI of liblbt_b200.so: the B200 (sm_100a) kernels behind the dynamic-fixed-point
+ * (DFXP) training hot path of freudh/lbt.
+ *
+ * The reference has no FFI layer (it is pure Python on TensorFlow 1.x); the "interface each entry
+ * point replaces" is therefore the reference Python function / the TF op it dispatched to
+ * (file:line under /root/reference).  Conventions:
+ *   - plain C types only; every buffer is owned by the caller (device memory unless stated);
+ *   - the library never allocates or frees device memory and never synchronises with the host:
+ *     all scalar state (ranges, overflow counters, the step counter) lives on the device, so a
+ *     whole training step is CUDA-graph capturable;
+ *   - `stream` is a cudaStream_t passed as void*; NULL = the legacy default stream;
+ *   - return 0 on success, a negative LBT_E* code otherwise (lbt_strerror() names it); nothing
+ *     throws or aborts across the ABI;
+ *   - 16-byte aligned base pointers take the vectorised paths; anything else falls back to a
+ *     scalar kernel with identical results.
+ */
+#ifndef LBT_H_
+#define LBT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBT_VERSION 100 /* 0.1.0 */
+
+enum lbt_status {
+  LBT_OK = 0,
+  LBT_EINVAL = -1,       /* bad argument (null pointer, bits out of range, ...) */
+  LBT_EUNSUPPORTED = -2, /* shape / alignment / kind not supported by this build */
+  LBT_EARCH = -3,        /* device is not sm_100 (B200) */
+  LBT_ECUDA = -4,        /* a CUDA runtime / driver call failed (see lbt_last_cuda_error) */
+  LBT_EWORKSPACE = -5    /* workspace too small */
+};
+
+/* Rounding of lbt_quantize. */
+enum lbt_round_mode {
+  LBT_ROUND_NEAREST = 0,           /* `identity`,            dynamic_fixed_point.py:25-30 */
+  LBT_ROUND_STOCHASTIC_NOISE = 1,  /* `stochastic_identity`, dynamic_fixed_point.py:32-38, noise from `noise[n_inner]` */
+  LBT_ROUND_STOCHASTIC_PHILOX = 2  /* same, noise generated in-kernel (identical to lbt_noise_fill) */
+};
+
+/* Integer mantissa output of lbt_quantize (mantissa k = q * 2^(bits-integer_bits-1)). */
+enum lbt_mant_kind {
+  LBT_MANT_NONE = 0,
+  LBT_MANT_S8 = 1,  /* bits <= 8 */
+  LBT_MANT_U8 = 2,  /* bits <= 9 and input known non-negative (post-ReLU conv activations, F7) */
+  LBT_MANT_S16 = 3  /* bits <= 16 */
+};
+
+/* Per-quantiser overflow statistics block: uint64_t[4] on the device. */
+#define LBT_CNT_OVER 0      /* #{x*m >= L} + #{x*m < -L}        dynamic_fixed_point.py:63-64 */
+#define LBT_CNT_OVER_HALF 1 /* #{x*m >= L/2} + #{x*m < -L/2}    dynamic_fixed_point.py:65-66 */
+#define LBT_CNT_NUMEL 2     /* elements seen (denominator of reduce_mean, :67) */
+#define LBT_CNT_TICKET 3    /* internal: CTA arrival ticket, always 0 between launches */
+#define LBT_CNT_WORDS 4
+
+int lbt_version(void);
+const char* lbt_strerror(int status);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* lbt_last_cuda_error(void);
+/* Number of kernels this library has launched from the calling process (for bench accounting). */
+uint64_t lbt_launch_count(void);
+
+/*
+ * Fused DFXP quantiser: replaces weight_quantization() + overflow_rate() + update_range()
+ * (dynamic_fixed_point.py:4-45, 48-67, 70-94), i.e. ~25 TF elementwise/reduce launches, with ONE
+ * pass over x.  x is viewed as [n_outer, n_inner] = [dim0, prod(rest)]; stochastic noise has
+ * n_inner values and is shared by all n_outer rows (tf.random_uniform(X.shape[1:]), :36).
+ *
+ *   m = 2^(bits - *integer_bits - 1), L = 2^(bits-1)
+ *   nearest:     k = rint (min(max(x*m,     -L), L-1))          (ties to even)
+ *   stochastic:  k = floor(min(max(x*m + u, -L), L-1))
+ *   out_fp32 = k / m   (may be -0.0);   out_mant = (mant_kind) k
+ *   counters += {#over, #over_half, n} measured on x*m (un-noised, un-clipped)
+ *   update_range != 0: the last CTA applies  ib <- min(bits-1, ib + delta)  and zeroes counters,
+ *     delta = +1 if over/n > t, else -1 if over_half/n <= t, else 0  (read-then-update: every
+ *     element of this launch is quantised with the value *integer_bits had at launch).
+ *   update_range == 0: counters are left accumulated for lbt_update_ranges() (data-parallel:
+ *     all-reduce them first).
+ *
+ * bits in [2, 24]; bits == 32 must be handled by the caller (pass-through, :22-23).
+ * out_fp32 and out_mant may each be NULL; with both NULL and counters given the launch is a
+ * statistics-only pass (overflow_rate / update_range on their own, dynamic_fixed_point.py:48,70).
+ * counters may be NULL only when update_range == 0 (no statistics are gathered).  dev_step (device uint64, may be NULL) is added
+ * to the high word of `offset` so a captured CUDA graph draws fresh noise every replay.
+ * out_fp32 may alias x (in-place).
+ */
+int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int bits, int32_t* integer_bits,
+                 float target_overflow_rate, int mode, const float* noise, uint64_t seed,
+                 uint64_t offset, const uint64_t* dev_step, float* out_fp32, void* out_mant,
+                 int mant_kind, uint64_t* counters, int update_range, void* stream);
+
+/*
+ * u[j] for j < n_inner of the Philox4x32-10 stream lbt_quantize(mode=2) uses:
+ *   r = philox4x32_10(counter = {g_lo, g_hi, off_lo, off_hi}, key = {seed_lo, seed_hi}), g = j / 4
+ *   u[j] = (r[j % 4] >> 8) * 2^-24,  off = offset + (dev_step ? *dev_step << 32 : 0)
+ * Stands in for tf.random_uniform (dynamic_fixed_point.py:36) so a run stays checkable on the CPU.
+ */
+int lbt_noise_fill(float* u, size_t n_inner, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                   void* stream);
+
+/*
+ * The range controller (update_range, dynamic_fixed_point.py:84-94) for n quantisers at once:
+ *   ranges[i] <- min(bits[i]-1, ranges[i] + delta(counters[i], target[i])); counters[i] <- 0.
+ * All arrays on the device; counters is uint64_t[n][LBT_CNT_WORDS].  Replaces the reference's
+ * host-scheduled tf.cond/tf.assign per quantiser (trainer.py:63,157).
+ */
+int lbt_update_ranges(int32_t* ranges, uint64_t* counters, const int32_t* bits, const float* target,
+                      size_t n, void* stream);
+
+/* *dev_step += 1 (one thread); keeps the step counter on the device for graph replay. */
+int lbt_step_advance(uint64_t* dev_step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBT_H_ */

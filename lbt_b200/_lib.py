@@ -1,0 +1,82 @@
+"""ctypes binding of liblbt_b200.so (the C ABI declared in include/lbt.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this raises.  PyTorch is
+used only for device memory and streams; tensors cross the ABI as raw pointers + sizes.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblbt_b200.so')
+
+c_void_p, c_int, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+c_u64, c_char_p = ctypes.c_uint64, ctypes.c_char_p
+
+# name -> (restype, argtypes); mirrors include/lbt.h one to one (tests/test_abi.py checks both ways)
+SIGNATURES = {
+    'lbt_version': (c_int, []),
+    'lbt_strerror': (c_char_p, [c_int]),
+    'lbt_last_cuda_error': (c_char_p, []),
+    'lbt_launch_count': (c_u64, []),
+    'lbt_quantize': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_float, c_int, c_void_p, c_u64, c_u64,
+                             c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    'lbt_noise_fill': (c_int, [c_void_p, c_size_t, c_u64, c_u64, c_void_p, c_void_p]),
+    'lbt_update_ranges': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'lbt_step_advance': (c_int, [c_void_p, c_void_p]),
+}
+
+# not part of the public header: tuning knobs used by bench sweeps
+_INTERNAL = {
+    'lbt_quantize_tune': (c_int, [c_int, c_int]),
+}
+
+
+class LbtError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises LbtError if the .so is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LbtError('%s not found — build it with `python -m lbt_b200.build` (needs nvcc); '
+                           'there is no CPU or PyTorch fallback for the DFXP hot path' % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for table in (SIGNATURES, _INTERNAL):
+            for name, (res, args) in table.items():
+                fn = getattr(h, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        h = lib()
+        msg = h.lbt_strerror(status).decode()
+        if status == -4:
+            msg += ': ' + h.lbt_last_cuda_error().decode()
+        raise LbtError('liblbt_b200: %s (status %d)' % (msg, status))
+
+
+def ptr(t):
+    """Raw device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LbtError('lbt_b200 operates on CUDA tensors only (no CPU fallback); got a %s tensor' % t.device)
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count():
+    return int(lib().lbt_launch_count())

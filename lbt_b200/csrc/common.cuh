@@ -1,0 +1,89 @@
+// Shared host/device helpers for liblbt_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/lbt.h"
+
+namespace lbt {
+
+// ---- host-side bookkeeping -------------------------------------------------------------------
+extern std::atomic<uint64_t> g_launches;
+void set_cuda_error(cudaError_t e, const char* where);
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool ok = false;
+};
+// Immutable per-device cache (SM count, arch check).  Thread-safe.
+const DeviceInfo& device_info();
+
+inline int check_launch(const char* where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_cuda_error(e, where);
+    return LBT_ECUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return LBT_OK;
+}
+
+#define LBT_REQUIRE_ARCH()                        \
+  do {                                            \
+    const ::lbt::DeviceInfo& _di = ::lbt::device_info(); \
+    if (!_di.ok) return _di.device < 0 ? LBT_ECUDA : LBT_EARCH; \
+  } while (0)
+
+// ---- device helpers --------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// u in [0, 1 - 2^-24]: the top 24 bits of a 32-bit draw.
+__device__ __forceinline__ float u01(uint32_t r) { return __uint2float_rn(r >> 8) * 5.9604644775390625e-08f; }
+
+// Noise for inner indices 4g .. 4g+3.
+__device__ __forceinline__ float4 philox_noise4(uint64_t g, uint64_t seed, uint64_t off) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)off, (uint32_t)(off >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  return make_float4(u01(r.x), u01(r.y), u01(r.z), u01(r.w));
+}
+
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 2^e as an exact fp32 (e clamped to the normal range).
+__device__ __forceinline__ float exp2i(int e) {
+  e = max(-126, min(127, e));
+  return __int_as_float((e + 127) << 23);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lbt
