@@ -115,6 +115,37 @@ int lbt_update_ranges(int32_t* ranges, uint64_t* counters, const int32_t* bits, 
 /* *dev_step += 1 (one thread); keeps the step counter on the device for graph replay. */
 int lbt_step_advance(uint64_t* dev_step, void* stream);
 
+/* Epilogue of lbt_gemm_i8. */
+enum lbt_gemm_epilogue {
+  LBT_EPI_F32 = 0,  /* out_f32[m*ldc+n] = fp32(acc) * 2^e (+ bias[n]),  e = exp_const + *ibA + *ibB */
+  LBT_EPI_ACC64 = 1 /* acc64[m*ldc+n] += alpha * acc  (64-bit integer atomics; split-K, exact) */
+};
+
+/*
+ * D[M,N] = A[M,K] * B[N,K]^T on DFXP integer mantissas with exact int32 accumulation in tensor memory
+ * (tcgen05.mma.kind::i8, TMA-fed).  Replaces the fp32 GEMMs the reference runs on fake-quantised
+ * floats: tf.matmul (dynamic_fixed_point.py:388), tf.nn.conv2d after im2col (:196, :291) and their
+ * tf.gradients (:207-210, :302-305, :457-460).
+ *   A, B: K-major byte matrices (row pitch lda/ldb bytes, multiples of 16; 16-byte aligned bases);
+ *         a_kind/b_kind = LBT_MANT_S8 or LBT_MANT_U8.
+ *   LBT_EPI_F32: the value of a mantissa with `bits` total bits is k * 2^-(bits-1-ib), so pass
+ *         exp_const = -(bitsA-1) - (bitsB-1) and the two device range pointers (either may be NULL = 0).
+ *         Result == RN_fp32(exact_dot * 2^e) bit for bit.  K <= 65536.
+ *   LBT_EPI_ACC64: K is cut into k_splits chunks (each <= 65536) spread over the SMs; partial sums are
+ *         added to acc64 (caller zeroes it) scaled by the integer alpha.  Finish with lbt_acc64_finalize.
+ */
+int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M,
+                size_t N, size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const,
+                const float* bias, float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits,
+                void* stream);
+
+/*
+ * out[i] = fp32(acc64[i]) * 2^(exp_const + *ibA + *ibB) (+ add_scale * add[i]) — the wgrad tail
+ * `tf.gradients(y, W, gradq) + 2 * weight_decay * W` (dynamic_fixed_point.py:207, 302, 457).
+ */
+int lbt_acc64_finalize(const int64_t* acc64, size_t n, const int32_t* ibA, const int32_t* ibB, int exp_const,
+                       const float* add, float add_scale, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,11 +25,16 @@ SIGNATURES = {
     'lbt_noise_fill': (c_int, [c_void_p, c_size_t, c_u64, c_u64, c_void_p, c_void_p]),
     'lbt_update_ranges': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'lbt_step_advance': (c_int, [c_void_p, c_void_p]),
+    'lbt_gemm_i8': (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_int,
+                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    'lbt_acc64_finalize': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p,
+                                   c_void_p]),
 }
 
 # not part of the public header: tuning knobs used by bench sweeps
 _INTERNAL = {
     'lbt_quantize_tune': (c_int, [c_int, c_int]),
+    'lbt_gemm_debug_error': (c_int, []),
 }
 
 

@@ -1,0 +1,484 @@
+// Integer-mantissa GEMM on the 5th-gen tensor cores of B200 (sm_100a only):
+//
+//     D[M,N] (s32, in TMEM)  =  A[M,K] (u8|s8, K-major)  x  B[N,K]^T (u8|s8, K-major)
+//
+// TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma.kind::i8 (M128 x BN x K32,
+// issued by one thread) -> s32 accumulators in tensor memory (double buffered) -> tcgen05.ld epilogue.
+// Replaces the fp32 cuBLAS/cuDNN GEMMs the reference runs on fake-quantised floats
+// (tf.matmul dynamic_fixed_point.py:388, tf.nn.conv2d :291 and their tf.gradients :302-305, :457-460):
+// the products of DFXP mantissas are accumulated EXACTLY in int32, and the epilogue applies the
+// power-of-two rescale 2^(ibA + ibB + const) read from the layers' range variables on the device.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).  Persistent CTAs over (m-tile, n-tile, k-split).
+//
+// Epilogues:
+//   LBT_EPI_F32   out[m, n] = fp32(acc) * 2^e (+ bias[n])            (fprop / dgrad / dense)
+//   LBT_EPI_ACC64 acc64[m, n] += alpha * acc   (64-bit atomics)       (wgrad split-K: order-independent,
+//                 bit-reproducible; per-split K <= 65536 keeps the s32 partial exact)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace lbt {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 128;  // bytes == int8 elements == one 128B swizzle row
+constexpr int kUmmaK = 32;    // kind::i8: 32 bytes of K per instruction
+constexpr int kThreads = 192;
+constexpr long long kWatchdogCycles = 4000000000ll;
+
+__device__ int g_gemm_error = 0;
+
+struct GemmParams {
+  uint32_t M, N, K;
+  uint32_t m_tiles, n_tiles, k_blocks, k_blocks_per_split, k_splits;
+  int epilogue;
+  const int32_t* ibA;
+  const int32_t* ibB;
+  int exp_const;
+  const float* bias;
+  float* out;
+  size_t ldc;
+  long long* acc64;
+  int alpha;
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3f) == 0) {
+      if (*abort_flag) return false;
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > kWatchdogCycles) {  // ~2 s: something is wrong with the pipeline protocol
+        *abort_flag = 1;
+        atomicExch(&g_gemm_error, 1);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::i8, s32 accumulate.
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All previously issued MMAs of this thread arrive on `bar` when they complete.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor: K-major operand tile, 128-byte swizzle (rows of 128 B, 8-row
+// atoms 1024 B apart).  Fields (PTX ISA "tcgen05 matrix descriptor"): [0,14) address>>4,
+// [16,30) leading byte offset>>4 (unused for swizzled K-major: 1), [32,46) stride byte offset>>4
+// (1024>>4), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageA = kBlockM * kBlockK;
+  static constexpr int kStageB = BN * kBlockK;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    s_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  volatile int* abort_flag = &s_abort;
+
+  const uint32_t total_items = p.m_tiles * p.n_tiles * p.k_splits;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+        const uint32_t m_tile = item % p.m_tiles, rest = item / p.m_tiles;
+        const uint32_t n_tile = rest % p.n_tiles, ks = rest / p.n_tiles;
+        const uint32_t kb0 = ks * p.k_blocks_per_split;
+        const uint32_t kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag))) break;
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+          tma_load_2d(&tmA, &full_bar[stage], sa, (int)(kb * kBlockK), (int)(m_tile * kBlockM));
+          tma_load_2d(&tmB, &full_bar[stage], sa + C::kStageA, (int)(kb * kBlockK), (int)(n_tile * BN));
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+        const uint32_t ks = (item / p.m_tiles) / p.n_tiles;
+        const uint32_t kb0 = ks * p.k_blocks_per_split;
+        const uint32_t kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag))) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (uint32_t kb = kb0; kb < kb1; ++kb) {
+          if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag))) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + C::kStageA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance the descriptor start address by k*32 bytes inside the 128B swizzle row
+            umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), p.idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (!ok) break;
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM -> registers -> global =====
+    const uint32_t quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    int e = p.exp_const;
+    if (p.ibA) e += *p.ibA;
+    if (p.ibB) e += *p.ibB;
+    const float scale = exp2i(e);
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+      const uint32_t m_tile = item % p.m_tiles, rest = item / p.m_tiles;
+      const uint32_t n_tile = rest % p.n_tiles;
+      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
+      const uint32_t col0 = n_tile * BN;
+      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (row < p.M && col0 + c < p.N) {
+          const uint32_t ncol = min(16u, p.N - (col0 + c));
+          if (p.epilogue == LBT_EPI_F32) {
+            float* o = p.out + (size_t)row * p.ldc + col0 + c;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[j] = __int2float_rn((int)v[j]) * scale;
+              if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+            }
+            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) o[j] = f[j];
+            }
+          } else {
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(p.acc64) + (size_t)row * p.ldc + col0 + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < (int)ncol) {
+                const long long a = (long long)(int)v[j] * (long long)p.alpha;
+                if (a != 0) atomicAdd(o + j, (unsigned long long)a);
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// out[i] = fp32(acc64[i]) * 2^e (+ add_scale * add[i])   — wgrad finalize: scale + weight-decay term
+// (dynamic_fixed_point.py:302 `+ 2 * weight_decay * W`: a separate fp32 multiply then add).
+__global__ void acc64_finalize_kernel(const long long* acc, size_t n, const int32_t* ibA, const int32_t* ibB, int exp_const,
+                                      const float* add, float add_scale, float* out) {
+  int e = exp_const;
+  if (ibA) e += *ibA;
+  if (ibB) e += *ibB;
+  const float scale = exp2i(e);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = __ll2float_rn(acc[i]) * scale;
+    if (add) v = __fadd_rn(v, __fmul_rn(add_scale, add[i]));
+    out[i] = v;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 2-D K-major operand [rows, K] of bytes, row pitch `ld`; box = 128 bytes of K x `box_rows` rows.
+int make_operand_map(CUtensorMap* map, const void* base, size_t rows, size_t K, size_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return LBT_ECUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    return LBT_ECUDA;
+  }
+  return LBT_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, unsigned grid, cudaStream_t st) {
+  static bool attr_done[16] = {};
+  const int dev = device_info().device;
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(gemm_i8_kernel)");
+      return LBT_ECUDA;
+    }
+    attr_done[dev] = true;
+  }
+  gemm_i8_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  return check_launch("lbt_gemm_i8");
+}
+
+}  // namespace
+}  // namespace lbt
+
+using namespace lbt;
+
+extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M, size_t N,
+                           size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
+                           float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits, void* stream) {
+  if (!A || !B) return LBT_EINVAL;
+  if ((a_kind != LBT_MANT_S8 && a_kind != LBT_MANT_U8) || (b_kind != LBT_MANT_S8 && b_kind != LBT_MANT_U8)) return LBT_EINVAL;
+  if (epilogue == LBT_EPI_F32 ? !out_f32 : (epilogue == LBT_EPI_ACC64 ? !acc64 : true)) return LBT_EINVAL;
+  if (M == 0 || N == 0) return LBT_OK;
+  if (K == 0) return LBT_EINVAL;
+  if (ldc < N) return LBT_EINVAL;
+  if (lda < K || ldb < K || (lda & 15) || (ldb & 15)) return LBT_EUNSUPPORTED;  // TMA: 16-byte row pitch
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return LBT_EUNSUPPORTED;
+  if (M >= (1ull << 31) || N >= (1ull << 31) || K >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+
+  int bn = 256;
+  for (int c : {16, 32, 64, 128, 256})
+    if ((size_t)c >= N) {
+      bn = c;
+      break;
+    }
+
+  GemmParams p{};
+  p.M = (uint32_t)M;
+  p.N = (uint32_t)N;
+  p.K = (uint32_t)K;
+  p.m_tiles = (uint32_t)((M + kBlockM - 1) / kBlockM);
+  p.n_tiles = (uint32_t)((N + bn - 1) / bn);
+  p.k_blocks = (uint32_t)((K + kBlockK - 1) / kBlockK);
+  uint32_t splits = k_splits < 1 ? 1u : (uint32_t)k_splits;
+  if (epilogue == LBT_EPI_F32) splits = 1;
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  p.k_blocks_per_split = (p.k_blocks + splits - 1) / splits;
+  // s32 accumulator: |u8*s8| <= 255*128, so one CTA may sum at most 65536 products exactly
+  const uint32_t max_kb = 65536 / kBlockK;
+  if (p.k_blocks_per_split > max_kb) {
+    if (epilogue == LBT_EPI_F32) return LBT_EUNSUPPORTED;  // caller must use the split-K epilogue
+    p.k_blocks_per_split = max_kb;
+  }
+  p.k_splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  p.epilogue = epilogue;
+  p.ibA = ibA;
+  p.ibB = ibB;
+  p.exp_const = exp_const;
+  p.bias = bias;
+  p.out = out_f32;
+  p.ldc = ldc;
+  p.acc64 = reinterpret_cast<long long*>(acc64);
+  p.alpha = alpha;
+  // instruction descriptor: c_format s32 (2) @4, a_format @7, b_format @10 (0 = u8, 1 = s8), K-major A and B,
+  // N>>3 @17, M>>4 @24
+  p.idesc = (2u << 4) | ((a_kind == LBT_MANT_S8 ? 1u : 0u) << 7) | ((b_kind == LBT_MANT_S8 ? 1u : 0u) << 10) |
+            ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+
+  CUtensorMap ta, tb;
+  int rc = make_operand_map(&ta, A, M, K, lda, kBlockM);
+  if (rc) return rc;
+  rc = make_operand_map(&tb, B, N, K, ldb, (uint32_t)bn);
+  if (rc) return rc;
+
+  const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
+  const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 16: return launch<16>(ta, tb, p, grid, st);
+    case 32: return launch<32>(ta, tb, p, grid, st);
+    case 64: return launch<64>(ta, tb, p, grid, st);
+    case 128: return launch<128>(ta, tb, p, grid, st);
+    default: return launch<256>(ta, tb, p, grid, st);
+  }
+}
+
+extern "C" int lbt_acc64_finalize(const int64_t* acc64, size_t n, const int32_t* ibA, const int32_t* ibB, int exp_const,
+                                  const float* add, float add_scale, float* out, void* stream) {
+  if (!acc64 || !out) return LBT_EINVAL;
+  if (n == 0) return LBT_OK;
+  LBT_REQUIRE_ARCH();
+  const size_t blocks = (n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 4096 ? blocks : 4096);
+  acc64_finalize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(acc64), n, ibA, ibB, exp_const, add, add_scale, out);
+  return check_launch("lbt_acc64_finalize");
+}
+
+// Test hook: 1 if any GEMM CTA hit the bounded-wait watchdog since the last call (synchronises).
+extern "C" int lbt_gemm_debug_error(void) {
+  int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, g_gemm_error, sizeof(int)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_gemm_error, &zero, sizeof(int));
+  return v;
+}

@@ -17,8 +17,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRowsUnroll = 8;
 
-int g_blocks_per_sm = 6;
-int g_rows_per_group = 8;
+// Defaults from the round-1 sweep on B200 (benchmarks/quantize_bench.py --tune, 2^26 elements).
+int g_blocks_per_sm = 8;
+int g_rows_per_group = 32;
 
 struct QParams {
   const float* x;

@@ -1,0 +1,65 @@
+"""Host wrappers of the tcgen05 int8 GEMM (csrc/gemm_i8.cu) — raw pointers across the C ABI."""
+import torch
+
+from . import _lib
+from .quantizer import MANT_S8, MANT_U8
+
+EPI_F32, EPI_ACC64 = 0, 1
+
+
+def _kind(t):
+    if t.dtype == torch.int8:
+        return MANT_S8
+    if t.dtype == torch.uint8:
+        return MANT_U8
+    raise _lib.LbtError('GEMM operands must be int8/uint8 mantissas, got %s' % t.dtype)
+
+
+def _check_operand(t, K):
+    if t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != K:
+        raise _lib.LbtError('GEMM operand must be a K-major [rows, K] matrix with unit inner stride')
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), K)
+
+
+def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None):
+    """fp32 out[M,N] = (A[M,K] @ B[N,K]^T) * 2^(exp_const + ibA + ibB) (+ bias)."""
+    M, K = A.shape
+    N = B.shape[0]
+    lda, ldb = _check_operand(A, K), _check_operand(B, K)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.check(_lib.lib().lbt_gemm_i8(_lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
+                                      _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), _lib.ptr(out), None,
+                                      out.stride(0), 1, 1, _lib.stream()))
+    return out
+
+
+def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
+    """acc64[M,N] += alpha * (A[M,K] @ B[N,K]^T), exact, K split across the SMs."""
+    M, K = A.shape
+    N = B.shape[0]
+    lda, ldb = _check_operand(A, K), _check_operand(B, K)
+    if acc64.dtype != torch.int64 or acc64.shape != (M, N) or not acc64.is_contiguous():
+        raise _lib.LbtError('acc64 must be a contiguous int64 [M, N] tensor')
+    if k_splits <= 0:
+        tiles = -(-M // 128) * -(-N // min(256, max(16, 1 << (max(N, 1) - 1).bit_length())))
+        sms = torch.cuda.get_device_properties(A.device).multi_processor_count
+        k_splits = max(1, sms // max(1, tiles))
+    _lib.check(_lib.lib().lbt_gemm_i8(_lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
+                                      None, None, 0, None, None, _lib.ptr(acc64), N, int(alpha), int(k_splits),
+                                      _lib.stream()))
+    return acc64
+
+
+def acc64_finalize(acc64, *, ibA=None, ibB=None, exp_const=0, add=None, add_scale=0.0, out=None):
+    """fp32 out = acc64 * 2^(exp_const + ibA + ibB) + add_scale * add."""
+    if out is None:
+        out = torch.empty(acc64.shape, dtype=torch.float32, device=acc64.device)
+    _lib.check(_lib.lib().lbt_acc64_finalize(_lib.ptr(acc64), acc64.numel(), _lib.ptr(ibA), _lib.ptr(ibB),
+                                             int(exp_const), _lib.ptr(add), float(add_scale), _lib.ptr(out),
+                                             _lib.stream()))
+    return out
+
+
+def debug_error():
+    return int(_lib.lib().lbt_gemm_debug_error())

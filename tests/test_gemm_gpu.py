@@ -1,0 +1,86 @@
+"""tcgen05 int8 GEMM vs an exact int64 reference: bit-for-bit (SURVEY.md §7.4 self-check)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lbt_b200 import gemm as G  # noqa: E402
+
+
+def _operand(rng, rows, K, signed, ld=None):
+    ld = ld or -(-K // 16) * 16
+    buf = torch.zeros(rows, ld, dtype=torch.int8 if signed else torch.uint8)
+    lo, hi = (-128, 128) if signed else (0, 256)
+    vals = torch.from_numpy(rng.integers(lo, hi, size=(rows, K)).astype(np.int8 if signed else np.uint8))
+    buf[:, :K] = vals
+    buf[:, K:] = 77 if signed else 200          # pitch padding must never be read
+    return buf.cuda()[:, :K], vals.to(torch.int64)
+
+
+def _exact(a64, b64):
+    return a64.double().cuda() @ b64.double().cuda().T          # |sum| < 2^53: exact in fp64
+
+
+SHAPES = [(128, 16, 128), (128, 128, 128), (256, 256, 512), (1, 1, 1), (5, 3, 7), (130, 10, 64), (257, 33, 130),
+          (1000, 100, 1000), (4096, 16, 144), (2048, 64, 576), (512, 1000, 512), (300, 400, 2048), (128, 256, 4608),
+          (8192, 128, 1600)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+@pytest.mark.parametrize('kinds', ['ss', 'us', 'su', 'uu'])
+def test_gemm_f32_bit_exact(M, N, K, kinds):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A, a64 = _operand(rng, M, K, kinds[0] == 's')
+    B, b64 = _operand(rng, N, K, kinds[1] == 's')
+    out = G.gemm_i8(A, B, exp_const=0)
+    torch.cuda.synchronize()
+    assert G.debug_error() == 0, 'GEMM pipeline watchdog fired'
+    ref = _exact(a64, b64)
+    assert torch.equal(out.double(), ref.float().double()), (out.double() - ref).abs().max()
+
+
+def test_gemm_scale_and_bias_from_device_ranges():
+    rng = np.random.default_rng(1)
+    M, N, K = 384, 48, 300
+    A, a64 = _operand(rng, M, K, False)
+    B, b64 = _operand(rng, N, K, True)
+    ibA = torch.tensor(1, dtype=torch.int32, device='cuda')
+    ibB = torch.tensor(-2, dtype=torch.int32, device='cuda')
+    bias = torch.randn(N, device='cuda')
+    out = G.gemm_i8(A, B, ibA=ibA, ibB=ibB, exp_const=-(9 - 1) - (8 - 1), bias=bias)
+    scale = 2.0 ** (1 - 2 - 8 - 7)
+    ref = (_exact(a64, b64).float() * scale) + bias            # RN(exact * 2^e) then one rounded add
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize('M,N,K,splits', [(144, 16, 262144, 0), (27, 16, 65536 * 3 + 5, 0), (576, 64, 16384, 7),
+                                          (4608, 512, 12544, 0), (128, 16, 128, 4)])
+def test_gemm_split_k_acc64_exact(M, N, K, splits):
+    rng = np.random.default_rng(K)
+    A, a64 = _operand(rng, M, K, False)
+    B, b64 = _operand(rng, N, K, True)
+    acc = torch.zeros(M, N, dtype=torch.int64, device='cuda')
+    G.gemm_i8_acc64(A, B, acc, alpha=1, k_splits=splits)
+    G.gemm_i8_acc64(A, B, acc, alpha=2, k_splits=splits)       # hi/lo recombination uses alpha
+    torch.cuda.synchronize()
+    assert G.debug_error() == 0
+    ref = _exact(a64, b64).to(torch.int64)
+    assert torch.equal(acc, 3 * ref)
+    W = torch.randn(M, N, device='cuda')
+    ib = torch.tensor(3, dtype=torch.int32, device='cuda')
+    out = G.acc64_finalize(acc, ibA=ib, exp_const=-20, add=W, add_scale=4e-4)
+    ref32 = (3 * ref).float() * 2.0 ** -17 + torch.tensor(4e-4, device='cuda') * W
+    assert torch.equal(out, ref32)
+
+
+def test_gemm_worst_case_magnitudes_do_not_overflow():
+    """All operands at the extreme values and K at the exactness bound of a single s32 accumulator."""
+    K = 65536
+    A = torch.full((128, K), 255, dtype=torch.uint8, device='cuda')
+    B = torch.full((16, K), -128, dtype=torch.int8, device='cuda')
+    out = G.gemm_i8(A, B)
+    assert torch.all(out == float(-255 * 128 * K))
+    with pytest.raises(Exception):
+        G.gemm_i8(torch.zeros(128, K + 128, dtype=torch.uint8, device='cuda'),
+                  torch.zeros(16, K + 128, dtype=torch.int8, device='cuda'))
