@@ -146,6 +146,40 @@ int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind
 int lbt_acc64_finalize(const int64_t* acc64, size_t n, const int32_t* ibA, const int32_t* ibB, int exp_const,
                        const float* add, float add_scale, float* out, void* stream);
 
+/*
+ * im2col gather of an NHWC mantissa tensor src[N,H,W,C] into the K-major GEMM operand
+ * out[M = N*OH*OW, K = kh*kw*C] (row pitch ld bytes), k = (r*kw + s)*C + c — the A operand of the
+ * implicit GEMMs behind tf.nn.conv2d / Conv2DBackpropInput (dynamic_fixed_point.py:291, 305).
+ *   transposed == 0 (fprop): row (n,oh,ow) reads src[n, oh*sh - pad_top + r, ow*sw - pad_left + s, c]
+ *   transposed == 1 (dgrad): src is the output-gradient map; row (n,oh,ow) iterates the conv INPUT
+ *     grid and reads src[n, (oh + pad_top - r)/sh, (ow + pad_left - s)/sw, c] where divisible.
+ * Out-of-range taps are 0 (TF 'SAME' zero padding).  src_kind S8/U8 copies bytes; S16 (signed
+ * mantissas wider than 8 bits, e.g. the 9-bit first-layer activations) writes K*3 bytes per row:
+ * [hi | hi | lo] with k = 2*hi + lo, to be multiplied against [W | W | W].
+ */
+int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W, int C, int OH, int OW, int kh, int kw,
+                  int sh, int sw, int pad_top, int pad_left, int transposed, void* out, size_t ld,
+                  void* stream);
+
+/* out[c*ld_out + r] = in[r*ld_in + c] for an R x C byte matrix (operand re-majoring for wgrad). */
+int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in, void* out, size_t ld_out,
+                     void* stream);
+
+/*
+ * acc64[c] += sum_r in[r*C + c] over an R x C matrix of s8 / s16 mantissas (exact).  The bias gradient
+ * tf.gradients(y, b, gradq) (dynamic_fixed_point.py:209, 304, 459); finish with lbt_acc64_finalize.
+ */
+int lbt_colsum_i(const void* in, int kind, size_t R, size_t C, int64_t* acc64, void* stream);
+
+/*
+ * Momentum SGD on flat fp32 buffers (tf.train.MomentumOptimizer.apply_gradients, trainer.py:81-82,
+ * non-Nesterov):  accum <- momentum*accum + grad_scale*grad ;  w <- w - lr*accum.
+ * dev_lr (device float, may be NULL) overrides lr so a captured graph can follow an LR schedule;
+ * grad_scale = 1/world_size turns the all-reduced gradient sum into the data-parallel mean.
+ */
+int lbt_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float lr, const float* dev_lr,
+                     float momentum, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,11 @@ SIGNATURES = {
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     'lbt_acc64_finalize': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p,
                                    c_void_p]),
+    'lbt_im2col_i8': (c_int, [c_void_p, c_int] + [c_int] * 13 + [c_void_p, c_size_t, c_void_p]),
+    'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
+    'lbt_colsum_i': (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
+    'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
+                                 c_void_p]),
 }
 
 # not part of the public header: tuning knobs used by bench sweeps

@@ -1,0 +1,639 @@
+"""Quantised layers of the DFXP training path — PyTorch host side over liblbt_b200's C ABI.
+
+Mirrors the reference's layer set (``dfxp:N`` = /root/reference/dynamic_fixed_point.py:N) with the
+PyTorch-style constructors the reference's orphan ``custom.py`` expects (custom.py:5, 11-12, 29-30):
+
+    Conv2d_q(bits, in_channels, out_channels, kernel_size, stride=1, padding='SAME', bias=True)   dfxp:224-316
+    Linear_q(bits, in_features, out_features, bias=True)           (= Dense_q)                    dfxp:319-470
+    BatchNorm2d_q(bits, num_features)    (= Normalization_q + Rescale_q, BatchNorm_q)             dfxp:539-743
+    ResidualBlock_q / ResidualBottleneck_q                                                        dfxp:746-980
+
+Semantics follow the TensorFlow classes: NHWC/HWIO arithmetic (tensors are logical NCHW stored
+channels_last, conv weights are stored HWIO, dense weights [in, out]) so the rounding noise
+broadcasts over dim 0 exactly as ``tf.random_uniform(X.shape[1:])`` does; conv activations use
+``bits+1`` (dfxp:287); every quantiser is stochastic (dfxp:192-206 hard-code it); the backward
+pass quantises the incoming gradient, is straight-through for the forward quantisers, and carries
+the weight decay inside the gradient (``+ 2*wd*W``, dfxp:302).
+
+All arithmetic on tensors runs in the library's kernels (quantiser, im2col, tcgen05 int8 GEMM);
+there is no PyTorch/CPU fallback for them.  Range variables stay constant during a step and are
+advanced once per step by ``Runtime.update_ranges()`` (read-then-update).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, gemm as G, quantizer as Q
+
+
+# ------------------------------------------------------------------------------------------------
+# Runtime: shared per-model state (quantiser ids, Philox seed, device step counter, flat range state)
+# ------------------------------------------------------------------------------------------------
+
+
+class Runtime:
+    """What the TF graph + session held implicitly: the list of quantisers ('update_range'
+    collection, dfxp:40-41), the RNG stream and the per-step range update (trainer.py:63, 157)."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+        self.sites = []
+        self.dev_step = None         # int64[1] on the device once finalised
+        self.noise_fn = None         # tests: callable(site, n_inner, device) -> explicit noise tensor
+        self.flat = None
+        self.timer = None            # bench: callable(name) -> context manager timing a kernel class
+
+    def register(self, site):
+        site.qid = len(self.sites)
+        self.sites.append(site)
+
+    def finalize(self, device):
+        """Flatten every quantiser's range/counters into contiguous device arrays (one
+        lbt_update_ranges launch per step; one all-reduce of the counters under data parallelism)."""
+        n = len(self.sites)
+        ranges = torch.empty(n, dtype=torch.int32, device=device)
+        counters = torch.zeros(n, Q.CNT_WORDS, dtype=torch.int64, device=device)
+        bits = torch.tensor([s.bits for s in self.sites], dtype=torch.int32, device=device)
+        target = torch.tensor([s.target for s in self.sites], dtype=torch.float32, device=device)
+        for i, s in enumerate(self.sites):
+            ranges[i] = int(s.range)
+            s._buffers['range'] = ranges[i]
+            s._buffers['counters'] = counters[i]
+        self.flat = dict(ranges=ranges, counters=counters, bits=bits, target=target)
+        self.dev_step = torch.zeros(1, dtype=torch.int64, device=device)
+        return self
+
+    def update_ranges(self):
+        """The ``update_range_op`` fetch of trainer.py:157 for all quantisers, then step += 1."""
+        f = self.flat
+        h = _lib.lib()
+        _lib.check(h.lbt_update_ranges(_lib.ptr(f['ranges']), _lib.ptr(f['counters']), _lib.ptr(f['bits']),
+                                       _lib.ptr(f['target']), len(self.sites), _lib.stream()))
+        _lib.check(h.lbt_step_advance(_lib.ptr(self.dev_step), _lib.stream()))
+
+    def ranges(self):
+        """{quantiser name: integer_bits} — the cheap parity probe (tf.summary of *_range, dfxp:180-190)."""
+        vals = self.flat['ranges'].cpu().tolist() if self.flat is not None else [int(s.range) for s in self.sites]
+        return {s.name: v for s, v in zip(self.sites, vals)}
+
+
+_default_runtime = Runtime()
+
+
+def default_runtime():
+    return _default_runtime
+
+
+class QuantSite(nn.Module):
+    """One ``weight_quantization`` call site and its ``*_range`` variable (dfxp:161-171)."""
+
+    def __init__(self, runtime, name, bits, init_range=2, target_overflow_rate=0.0):
+        super().__init__()
+        assert 1 <= bits <= 32, 'invalid value for bits: %d' % bits          # dfxp:21
+        self.runtime = runtime
+        self.name = name
+        self.bits = int(bits)
+        self.target = float(target_overflow_rate)
+        self.register_buffer('range', torch.tensor(int(init_range), dtype=torch.int32))
+        self.register_buffer('counters', torch.zeros(Q.CNT_WORDS, dtype=torch.int64))
+        runtime.register(self)
+
+    def quantize(self, x, want_fp32=True, mant_kind=Q.MANT_NONE):
+        """Stochastic DFXP quantisation of ``x`` (memory order = TF layout).  Gathers the overflow
+        counters; the range itself moves in Runtime.update_ranges()."""
+        rt = self.runtime
+        kw = dict(target_overflow_rate=self.target, want_fp32=want_fp32, mant_kind=mant_kind, counters=self.counters,
+                  update_range=False)
+        if rt.noise_fn is not None:
+            n_inner = Q.rows_view(x)[1]
+            kw.update(mode=Q.ROUND_NOISE, noise=rt.noise_fn(self, n_inner, x.device))
+        else:
+            kw.update(mode=Q.ROUND_PHILOX, seed=rt.seed, offset=Q.make_offset(self.qid, 0), dev_step=rt.dev_step)
+        return Q.quantize(x, self.bits, self.range, **kw)
+
+    def extra_repr(self):
+        return '%s bits=%d' % (self.name, self.bits)
+
+
+class _QuantSTE(torch.autograd.Function):
+    """Forward: fake-quantise through the site.  Backward: identity (dfxp:30, 38)."""
+
+    @staticmethod
+    def forward(ctx, x, site):
+        q, _ = site.quantize(x)
+        return q
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None
+
+
+class _GradQuant(torch.autograd.Function):
+    """Identity in forward; quantises the incoming gradient in backward (``gradq``, dfxp:300, 621, 687)."""
+
+    @staticmethod
+    def forward(ctx, y, site):
+        ctx.site = site
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _mem_contig(dy)
+        q, _ = ctx.site.quantize(dy)
+        return q, None
+
+
+def _mem_contig(x):
+    """Contiguous in memory in the TF order: channels_last for 4-D (NHWC), plain otherwise."""
+    if x.dim() == 4:
+        return x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous(memory_format=torch.channels_last)
+    return x.contiguous()
+
+
+def same_pad(in_size, k, s):
+    """TF 'SAME': (out, pad_before, pad_after) — pad_total = max((out-1)*s + k - in, 0), before = total//2."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    return out, total // 2, total - total // 2
+
+
+def _pitch16(k):
+    return -(-k // 16) * 16
+
+
+def _as_operand(t):
+    """[rows, K] byte matrix with a 16-byte row pitch (TMA requirement); copies only when needed."""
+    rows, K = t.shape
+    if t.stride(1) == 1 and t.stride(0) % 16 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    buf = torch.zeros(rows, _pitch16(K), dtype=t.dtype, device=t.device)
+    buf[:, :K] = t
+    return buf[:, :K]
+
+
+def _transpose_bytes(t):
+    """[R, C] -> [C, R] byte matrix with a 16-byte pitch (lbt_transpose_i8)."""
+    R, C = t.shape
+    assert t.stride(1) == 1
+    out = torch.empty(C, _pitch16(R), dtype=t.dtype, device=t.device)
+    _lib.check(_lib.lib().lbt_transpose_i8(_lib.ptr(t), R, C, t.stride(0), _lib.ptr(out), out.stride(0), _lib.stream()))
+    return out[:, :R]
+
+
+def _im2col(src_nhwc, src_kind, OH, OW, kh, kw, sh, sw, pt, pl, transposed):
+    N, H, W, C = src_nhwc.shape
+    segs = 3 if src_kind == Q.MANT_S16 else 1
+    K = kh * kw * C * segs
+    M = N * OH * OW
+    out = torch.empty(M, _pitch16(K), dtype=torch.int8 if src_kind != Q.MANT_U8 else torch.uint8, device=src_nhwc.device)
+    _lib.check(_lib.lib().lbt_im2col_i8(_lib.ptr(src_nhwc), src_kind, N, H, W, C, OH, OW, kh, kw, sh, sw, pt, pl,
+                                        1 if transposed else 0, _lib.ptr(out), out.stride(0), _lib.stream()))
+    return out[:, :K]
+
+
+def _colsum(mant2d, kind):
+    acc = torch.zeros(mant2d.shape[1], dtype=torch.int64, device=mant2d.device)
+    _lib.check(_lib.lib().lbt_colsum_i(_lib.ptr(mant2d), kind, mant2d.shape[0], mant2d.shape[1], _lib.ptr(acc),
+                                       _lib.stream()))
+    return acc
+
+
+# ------------------------------------------------------------------------------------------------
+# Conv2d_q
+# ------------------------------------------------------------------------------------------------
+
+
+class _QConv2dFn(torch.autograd.Function):
+    """dfxp:272-305 on integer mantissas: quantise X (bits+1), W, [b]; implicit GEMM fprop; in backward
+    quantise the gradient, then wgrad (+2*wd*W), bias grad, dgrad — all through lbt_gemm_i8."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer):
+        x = _mem_contig(x)
+        N, Cin, H, W = x.shape
+        kh, kw, _, Cout = weight.shape
+        sh, sw = layer.stride
+        if layer.padding == 'SAME':
+            OH, pt, _ = same_pad(H, kh, sh)
+            OW, pl, _ = same_pad(W, kw, sw)
+        else:
+            pt = pl = layer.pad_int
+            OH = (H + 2 * pt - kh) // sh + 1
+            OW = (W + 2 * pl - kw) // sw + 1
+        xb = layer.qX.bits
+        # F7/H2: 9-bit activations are u8 when the input is known non-negative, else s16 split hi|hi|lo
+        if xb <= 8:
+            xkind = Q.MANT_S8
+        elif xb <= 9 and not layer.input_signed:
+            xkind = Q.MANT_U8
+        else:
+            xkind = Q.MANT_S16
+        if layer.qW.bits > 8 or xb > 16:
+            raise _lib.LbtError('Conv2d_q: weights wider than 8 bits need the hi/lo GEMM split (not built yet)')
+        x_nhwc = x.permute(0, 2, 3, 1)
+        _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)                   # dfxp:287
+        _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)               # dfxp:289
+        segs = 3 if xkind == Q.MANT_S16 else 1
+        Kf = kh * kw * Cin
+        # B operand [Cout, Kf]: transpose of the HWIO mantissas (tiny)
+        wt = _transpose_bytes(wm.view(Kf, Cout))
+        if segs == 3:
+            wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
+        if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
+            A = xm.reshape(N * H * W, Cin)                                                     # 1x1: no gather
+        else:
+            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+        bq = None
+        if bias is not None:
+            bq, _ = layer.qb.quantize(bias)                                                    # dfxp:294
+        y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
+        G.gemm_i8(A, wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=-(xb - 1) - (layer.qW.bits - 1),
+                  bias=bq, out=y.view(N * OH * OW, Cout))                                      # dfxp:291, 296
+        ctx.layer = layer
+        ctx.geom = (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind)
+        ctx.save_for_backward(xm, wm, weight)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        xm, wm, weight = ctx.saved_tensors
+        N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind = ctx.geom
+        xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
+        if gb > 8:
+            raise _lib.LbtError('Conv2d_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
+        dy = _mem_contig(dy).permute(0, 2, 3, 1)
+        _, gm = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S8)                    # dfxp:300
+        M = N * OH * OW
+        g2 = gm.view(M, Cout)
+        Kf = kh * kw * Cin
+        dW = db = dX = None
+        # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
+        if ctx.needs_input_grad[1]:
+            gt = _transpose_bytes(g2)                                                           # [Cout, M]
+            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+            at = _transpose_bytes(A)                                                            # [Kf*segs, M]
+            acc = torch.zeros(Kf, Cout, dtype=torch.int64, device=dy.device)
+            if xkind == Q.MANT_S16:
+                G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
+                G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
+            else:
+                G.gemm_i8_acc64(at, gt, acc, alpha=1)
+            dW = G.acc64_finalize(acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                                  add=weight.detach().view(Kf, Cout), add_scale=2 * layer.weight_decay
+                                  ).view(kh, kw, Cin, Cout)                                     # dfxp:302
+        if layer.qb is not None and ctx.needs_input_grad[2]:
+            db = G.acc64_finalize(_colsum(g2, Q.MANT_S8), ibA=layer.qG.range, exp_const=-(gb - 1))   # dfxp:304
+        # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
+        if ctx.needs_input_grad[0]:
+            K2 = kh * kw * Cout
+            w2 = _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+            if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
+                A2 = g2
+            else:
+                A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
+            dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dy.device)
+            G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=-(gb - 1) - (wb - 1),
+                      out=dx.view(N * H * W, Cin))                                             # dfxp:305
+            dX = dx.permute(0, 3, 1, 2)
+        return dX, dW, db, None
+
+
+class Conv2d_q(nn.Module):
+    """Quantised 2-d convolution, dfxp:224-316 (``Conv2d_pq`` dfxp:129-221 is an identical copy).
+
+    ``weight`` is stored HWIO like the reference's ``tf.Variable(ksize)``; ``padding`` is an int or
+    'SAME' | 'VALID' with TensorFlow semantics.  ``input_signed=False`` declares a non-negative input
+    (anything fed by a ReLU) so the bits+1 = 9-bit activation mantissas fit the u8 tensor-core type."""
+
+    def __init__(self, bits, in_channels, out_channels, kernel_size, stride=1, padding='SAME', bias=True, *,
+                 weight_decay=0.0, target_overflow_rate=0.0, input_range=2, weight_range=2, bias_range=2, grad_range=2,
+                 grad_bits=None, input_signed=True, name='conv', runtime=None):
+        super().__init__()
+        rt = runtime or default_runtime()
+        kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
+        self.stride = (stride, stride) if isinstance(stride, int) else tuple(stride)
+        if isinstance(padding, str):
+            assert padding in ('SAME', 'VALID')
+            self.padding, self.pad_int = ('SAME', 0) if padding == 'SAME' else ('INT', 0)
+        else:
+            self.padding, self.pad_int = 'INT', int(padding)
+        self.bits, self.weight_decay, self.input_signed, self.name = bits, float(weight_decay), input_signed, name
+        limit = (3 / (kh * kw * in_channels)) ** 0.5                                           # dfxp:247-254
+        self.weight = nn.Parameter(torch.empty(kh, kw, in_channels, out_channels).uniform_(-limit, limit))
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None                  # dfxp:264
+        # creation order = quantiser id order = the oracle's: X, W, [b], grad
+        self.qX = QuantSite(rt, name + '/X', bits + 1, input_range, target_overflow_rate)      # dfxp:287 bits+1
+        self.qW = QuantSite(rt, name + '/W', bits, weight_range, target_overflow_rate)
+        self.qb = QuantSite(rt, name + '/b', bits, bias_range, target_overflow_rate) if bias else None
+        self.qG = QuantSite(rt, name + '/grad', grad_bits or bits, grad_range, target_overflow_rate)
+
+    def forward(self, x):
+        return _QConv2dFn.apply(x, self.weight, self.bias, self)
+
+    def info(self):
+        return '%d bits conv2d: %dx%dx%d stride %dx%d pad %s weight_decay %f' % (
+            self.bits, self.weight.shape[0], self.weight.shape[1], self.weight.shape[3], self.stride[0], self.stride[1],
+            self.padding, self.weight_decay)
+
+
+Conv2d_pq = Conv2d_q
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear_q / Dense_q
+# ------------------------------------------------------------------------------------------------
+
+
+class _QLinearFn(torch.autograd.Function):
+    """dfxp:384-393, 453-460: y = Q(X) @ Q(W) [+ Q(b)]; all three GEMMs on int8 mantissas."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, layer):
+        x = x.contiguous()
+        Bsz, In = x.shape
+        Out = weight.shape[1]
+        if layer.qX.bits > 8 or layer.qW.bits > 8:
+            raise _lib.LbtError('Linear_q: operands wider than 8 bits need the hi/lo GEMM split (not built yet)')
+        _, xm = layer.qX.quantize(x, want_fp32=False, mant_kind=Q.MANT_S8)                     # dfxp:384 (bits)
+        _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)                # dfxp:386
+        bq = None
+        if bias is not None:
+            bq, _ = layer.qb.quantize(bias)
+        wt = _transpose_bytes(wm)                                                               # [Out, In]
+        y = G.gemm_i8(_as_operand(xm), wt, ibA=layer.qX.range, ibB=layer.qW.range,
+                      exp_const=-(layer.qX.bits - 1) - (layer.qW.bits - 1), bias=bq)           # dfxp:388, 393
+        ctx.layer = layer
+        ctx.save_for_backward(xm, wm, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        xm, wm, weight = ctx.saved_tensors
+        xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
+        if gb > 8:
+            raise _lib.LbtError('Linear_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
+        _, gm = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S8)       # dfxp:453
+        In, Out = wm.shape
+        dX = dW = db = None
+        if ctx.needs_input_grad[1]:
+            acc = torch.zeros(In, Out, dtype=torch.int64, device=dy.device)
+            G.gemm_i8_acc64(_transpose_bytes(xm), _transpose_bytes(gm), acc, alpha=1, k_splits=1)
+            dW = G.acc64_finalize(acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                                  add=weight.detach(), add_scale=2 * layer.weight_decay)       # dfxp:457
+        if layer.qb is not None and ctx.needs_input_grad[2]:
+            db = G.acc64_finalize(_colsum(gm, Q.MANT_S8), ibA=layer.qG.range, exp_const=-(gb - 1))   # dfxp:459
+        if ctx.needs_input_grad[0]:
+            dX = G.gemm_i8(_as_operand(gm), _as_operand(wm), ibA=layer.qG.range, ibB=layer.qW.range,
+                           exp_const=-(gb - 1) - (wb - 1))                                     # dfxp:460
+        return dX, dW, db, None
+
+
+class Linear_q(nn.Module):
+    """Quantised fully connected layer, dfxp:319-470 (``Dense_q``).  ``weight`` is [in, out]."""
+
+    def __init__(self, bits, in_features, out_features, bias=True, *, weight_decay=0.0, target_overflow_rate=0.0,
+                 input_range=2, weight_range=2, bias_range=2, grad_range=2, grad_bits=None, name='dense', runtime=None):
+        super().__init__()
+        rt = runtime or default_runtime()
+        self.bits, self.weight_decay, self.name = bits, float(weight_decay), name
+        limit = (6 / (in_features + out_features)) ** 0.5                                      # dfxp:338
+        self.weight = nn.Parameter(torch.empty(in_features, out_features).uniform_(-limit, limit))
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        self.qX = QuantSite(rt, name + '/X', bits, input_range, target_overflow_rate)          # dfxp:384: bits
+        self.qW = QuantSite(rt, name + '/W', bits, weight_range, target_overflow_rate)
+        self.qb = QuantSite(rt, name + '/b', bits, bias_range, target_overflow_rate) if bias else None
+        self.qG = QuantSite(rt, name + '/grad', grad_bits or bits, grad_range, target_overflow_rate)
+
+    def forward(self, x):
+        return _QLinearFn.apply(x, self.weight, self.bias, self)
+
+    def info(self):
+        return '%d bits dense: %dx%d weight_decay %f' % (self.bits, self.weight.shape[0], self.weight.shape[1],
+                                                        self.weight_decay)
+
+
+Dense_q = Linear_q
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm: Normalization_q + Rescale_q
+# ------------------------------------------------------------------------------------------------
+
+
+class _WeightDecayGrad(torch.autograd.Function):
+    """Adds 2*wd*p to the gradient of p (the reference keeps weight decay inside the layer's grad)."""
+
+    @staticmethod
+    def forward(ctx, p, wd):
+        ctx.wd = wd
+        ctx.save_for_backward(p)
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        return g + (2 * ctx.wd) * p.detach(), None
+
+
+class Normalization_q(nn.Module):
+    """dfxp:539-623: quantise, batch moments of the QUANTISED input (biased variance), normalise;
+    running statistics with momentum 0.999; backward quantises the gradient then applies the
+    batch-norm VJP."""
+
+    def __init__(self, bits, num_features, momentum=0.999, eps=1e-5, *, target_overflow_rate=0.0, input_range=2,
+                 grad_range=2, grad_bits=None, name='norm', runtime=None):
+        super().__init__()
+        rt = runtime or default_runtime()
+        self.bits, self.momentum, self.eps, self.name = bits, momentum, eps, name
+        self.register_buffer('X_mean_running', torch.zeros(num_features))                     # dfxp:565-568
+        self.register_buffer('X_var_running', torch.ones(num_features))
+        self.qX = QuantSite(rt, name + '/X', bits, input_range, target_overflow_rate)          # dfxp:584
+        self.qG = QuantSite(rt, name + '/grad', grad_bits or bits, grad_range, target_overflow_rate)   # dfxp:621
+
+    def forward(self, x):
+        x = _mem_contig(x)
+        xq = _QuantSTE.apply(x, self.qX)
+        axes = (0, 2, 3) if x.dim() == 4 else (0,)
+        shape = (1, -1, 1, 1) if x.dim() == 4 else (1, -1)
+        if self.training:
+            mean = xq.mean(dim=axes)                                                           # dfxp:588
+            var = ((xq - mean.view(shape)) ** 2).mean(dim=axes)
+            with torch.no_grad():                                                              # dfxp:602-612
+                self.X_mean_running.mul_(self.momentum).add_((1 - self.momentum) * mean)
+                self.X_var_running.mul_(self.momentum).add_((1 - self.momentum) * var)
+        else:
+            mean, var = self.X_mean_running, self.X_var_running
+        y = (xq - mean.view(shape)) / ((var.view(shape) + self.eps) ** 0.5)                    # dfxp:616
+        return _GradQuant.apply(y, self.qG)
+
+
+class Rescale_q(nn.Module):
+    """dfxp:626-694: y = Q(X) * Q(gamma) + Q(beta); weight decay on gamma (dfxp:689)."""
+
+    def __init__(self, bits, num_features, *, weight_decay=0.0, target_overflow_rate=0.0, input_range=2, gamma_range=2,
+                 beta_range=2, grad_range=2, grad_bits=None, name='rescale', runtime=None):
+        super().__init__()
+        rt = runtime or default_runtime()
+        self.bits, self.weight_decay, self.name = bits, float(weight_decay), name
+        self.gamma = nn.Parameter(torch.ones(num_features))
+        self.beta = nn.Parameter(torch.zeros(num_features))
+        self.qX = QuantSite(rt, name + '/X', bits, input_range, target_overflow_rate)          # dfxp:677
+        self.qg = QuantSite(rt, name + '/g', bits, gamma_range, target_overflow_rate)          # dfxp:679
+        self.qb = QuantSite(rt, name + '/b', bits, beta_range, target_overflow_rate)           # dfxp:681
+        self.qG = QuantSite(rt, name + '/grad', grad_bits or bits, grad_range, target_overflow_rate)   # dfxp:687
+
+    def forward(self, x):
+        x = _mem_contig(x)
+        shape = (1, -1, 1, 1) if x.dim() == 4 else (1, -1)
+        xq = _QuantSTE.apply(x, self.qX)
+        gq = _QuantSTE.apply(_WeightDecayGrad.apply(self.gamma, self.weight_decay), self.qg)
+        bq = _QuantSTE.apply(self.beta, self.qb)
+        y = xq * gq.view(shape) + bq.view(shape)                                               # dfxp:683
+        return _GradQuant.apply(y, self.qG)
+
+
+class BatchNorm2d_q(nn.Sequential):
+    """dfxp:697-743: Normalization_q then Rescale_q (whose input range is hard-coded to 2, dfxp:735)."""
+
+    def __init__(self, bits, num_features, momentum=0.999, eps=1e-5, *, weight_decay=0.0, target_overflow_rate=0.0,
+                 input_range=2, gamma_range=2, beta_range=2, grad_range=2, grad_bits=None, name='bn', runtime=None):
+        super().__init__(
+            Normalization_q(bits, num_features, momentum, eps, target_overflow_rate=target_overflow_rate,
+                            input_range=input_range, grad_range=grad_range, grad_bits=grad_bits, name=name + '-norm',
+                            runtime=runtime),
+            Rescale_q(bits, num_features, weight_decay=weight_decay, target_overflow_rate=target_overflow_rate,
+                      input_range=2, gamma_range=gamma_range, beta_range=beta_range, grad_range=grad_range,
+                      grad_bits=grad_bits, name=name + '-rescale', runtime=runtime))
+
+    def info(self):
+        return 'BatchNorm'
+
+
+BatchNorm_q = BatchNorm2d_q
+
+
+# ------------------------------------------------------------------------------------------------
+# Plumbing layers (dfxp:983-1053) with TF semantics
+# ------------------------------------------------------------------------------------------------
+
+
+class ReLU_q(nn.ReLU):
+    def info(self):
+        return 'ReLU'
+
+
+class MaxPool_q(nn.Module):
+    """tf.nn.max_pool with 'SAME' (padding ignored in the max) or 'VALID' (dfxp:993-1006)."""
+
+    def __init__(self, kernel_size, stride, padding='SAME'):
+        super().__init__()
+        self.k, self.s, self.padding = kernel_size, stride, padding
+
+    def forward(self, x):
+        if self.padding == 'SAME':
+            _, pt, pb = same_pad(x.shape[2], self.k, self.s)
+            _, pl, pr = same_pad(x.shape[3], self.k, self.s)
+            if pt or pb or pl or pr:
+                x = F.pad(x, (pl, pr, pt, pb), value=float('-inf'))
+        return F.max_pool2d(x, self.k, self.s)
+
+
+class AvgPool_q(nn.Module):
+    """tf.nn.avg_pool 'VALID' (dfxp:1009-1022)."""
+
+    def __init__(self, kernel_size, stride=1):
+        super().__init__()
+        self.k, self.s = kernel_size, stride
+
+    def forward(self, x):
+        return F.avg_pool2d(x, self.k, self.s)
+
+
+class Dropout_q(nn.Module):
+    """tf.nn.dropout(x, keep_prob) = x / keep * floor(keep + u) (dfxp:1025-1040); keep_prob is KEEP."""
+
+    def __init__(self, keep_prob):
+        super().__init__()
+        self.keep_prob = keep_prob
+        self.uniform_fn = None      # tests: callable(shape, device) -> the reference's uniform tensor
+
+    def forward(self, x):
+        if not self.training or self.keep_prob >= 1.0:
+            return x
+        u = self.uniform_fn(x) if self.uniform_fn is not None else torch.rand_like(x)
+        return x / self.keep_prob * torch.floor(self.keep_prob + u)
+
+
+class Flatten_q(nn.Module):
+    """tf.reshape(X, [-1, dim]) of the NHWC tensor (dfxp:1043-1053)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        if x.dim() == 4:
+            x = x.permute(0, 2, 3, 1)
+        return x.reshape(-1, self.dim)
+
+
+class Sequential_q(nn.Sequential):
+    """dfxp:512-536."""
+
+
+# ------------------------------------------------------------------------------------------------
+# Residual blocks (dfxp:746-980)
+# ------------------------------------------------------------------------------------------------
+
+
+class ResidualBlock_q(nn.Module):
+    expansion = 1
+
+    def __init__(self, bits, in_channels, channels, stride, batch_norm=True, *, weight_decay=0.0, target_overflow_rate=0.0,
+                 input_range=2, weight_range=2, bias_range=2, grad_range=2, grad_bits=None, name='block', runtime=None):
+        super().__init__()
+        ckw = dict(bias=not batch_norm, weight_decay=weight_decay, input_range=input_range, weight_range=weight_range,
+                   bias_range=bias_range, grad_range=grad_range, grad_bits=grad_bits, input_signed=False, runtime=runtime)
+        self._bn = lambda n, c: (BatchNorm2d_q(bits, c, weight_decay=weight_decay, target_overflow_rate=target_overflow_rate,
+                                               input_range=input_range, grad_range=grad_range, grad_bits=grad_bits, name=n,
+                                               runtime=runtime) if batch_norm else nn.Identity())
+        self.residual = self._build_residual(bits, in_channels, channels, stride, name, ckw)
+        if stride == 1 and in_channels == self.expansion * channels:                           # dfxp:828-829
+            self.shortcut = nn.Sequential()
+        else:
+            self.shortcut = nn.Sequential(
+                Conv2d_q(bits, in_channels, self.expansion * channels, 1, stride, 'SAME', name=name + '-shortcut',
+                         target_overflow_rate=target_overflow_rate, **ckw),
+                self._bn(name + '-shortcut-bn', self.expansion * channels))
+        del self._bn
+
+    def _build_residual(self, bits, in_channels, channels, stride, name, ckw):
+        return nn.Sequential(
+            Conv2d_q(bits, in_channels, channels, 3, stride, 'SAME', name=name + '-1', **ckw),
+            self._bn(name + '-bn1', channels), ReLU_q(),
+            Conv2d_q(bits, channels, channels, 3, 1, 'SAME', name=name + '-2', **ckw),
+            self._bn(name + '-bn2', channels))
+
+    def forward(self, x):
+        # block inputs come from a ReLU (or max-pool of one) in every reference model: non-negative
+        return F.relu(self.residual(x) + self.shortcut(x))                                     # dfxp:858-863
+
+    def info(self):
+        return 'Residual block'
+
+
+class ResidualBottleneck_q(ResidualBlock_q):
+    expansion = 4
+
+    def _build_residual(self, bits, in_channels, channels, stride, name, ckw):
+        return nn.Sequential(
+            Conv2d_q(bits, in_channels, channels, 1, 1, 'SAME', name=name + '-1', **ckw),
+            self._bn(name + '-bn1', channels), ReLU_q(),
+            Conv2d_q(bits, channels, channels, 3, stride, 'SAME', name=name + '-2', **ckw),      # stride on the 3x3
+            self._bn(name + '-bn2', channels), ReLU_q(),
+            Conv2d_q(bits, channels, 4 * channels, 1, 1, 'SAME', name=name + '-3', **ckw),
+            self._bn(name + '-bn3', 4 * channels))

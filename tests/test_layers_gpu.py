@@ -1,0 +1,193 @@
+"""Layer-level parity of lbt_b200.dfxp with the CPU oracle on the same inputs and the same Philox noise.
+
+Quantiser outputs are compared bit-exactly (through the exact-GEMM identity); GEMM/conv outputs must
+equal RN_fp32(exact integer dot * 2^-f) bit for bit (computed here in fp64 from the oracle's fake-quant
+operands) and sit within the fp32-accumulation tolerance of the oracle's own fp32 conv/matmul
+(|y - y_ref| <= K * 2^-24 * sum|a||b|).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dfxp as O
+
+pytestmark = pytest.mark.gpu
+
+from lbt_b200 import dfxp as D  # noqa: E402
+
+SEED = 77
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).cuda()
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().cpu()
+
+
+def conv64(xq, wq, strides, padding):
+    return O.tf_conv2d(xq.double(), wq.double(), strides, padding)
+
+
+CONV_CASES = [
+    # Cin, Cout, k, stride, H, batch, bias, signed input
+    (16, 16, 3, 1, 8, 4, False, False),
+    (16, 32, 3, 2, 8, 4, False, False),
+    (16, 32, 1, 2, 8, 4, False, False),
+    (32, 64, 1, 1, 6, 3, False, False),
+    (3, 16, 3, 1, 10, 4, False, True),
+    (3, 64, 5, 1, 9, 2, True, True),
+    (64, 128, 5, 1, 7, 2, True, False),
+    (3, 64, 7, 2, 17, 2, False, True),
+    (24, 40, 3, 2, 7, 3, True, False),       # Cin not a multiple of 16 -> scalar gather path
+    (16, 16, 3, 1, 5, 2, False, True),       # signed 9-bit on a 16-channel input (hi|hi|lo split)
+]
+
+
+@pytest.mark.parametrize('Cin,Cout,k,s,H,B,bias,signed', CONV_CASES)
+def test_conv2d_q_forward_backward(Cin, Cout, k, s, H, B, bias, signed):
+    rng = np.random.default_rng(Cin * 100 + Cout + k + s)
+    ctx = O.Context(O.PhiloxNoise(SEED))
+    wd = 2e-4
+    ol = O.Conv2d_q(ctx, 'c', 8, [k, k, Cin, Cout], [1, s, s, 1], 'SAME', use_bias=bias, weight_decay=wd, rng=rng)
+    rt = D.Runtime(SEED)
+    pl = D.Conv2d_q(8, Cin, Cout, k, s, 'SAME', bias=bias, weight_decay=wd, input_signed=signed, runtime=rt).cuda()
+    rt.finalize('cuda')
+    pl.weight.data.copy_(ol.W.detach())
+    x = torch.from_numpy(rng.standard_normal((B, H, H, Cin)).astype(np.float32) * 1.5)
+    if not signed:
+        x = x.abs()
+    if bias:
+        b0 = torch.from_numpy(rng.standard_normal(Cout).astype(np.float32) * 0.1)
+        ol.b.data.copy_(b0)
+        pl.bias.data.copy_(b0)
+
+    y_o = ol.forward(x)
+    xg = nchw(x).requires_grad_(True)
+    y_p = pl(xg)
+    # exact identity: y == RN(conv64(Xq, Wq)) (+ bq)
+    y64 = conv64(ol.Xq.detach(), ol.Wq.detach(), ol.strides, 'SAME').float()
+    if bias:
+        y64 = y64 + ol.bq.detach()
+    assert torch.equal(nhwc(y_p.detach()), y64), 'fprop is not the exactly-rounded integer result'
+    tol = (k * k * Cin) * 2.0 ** -24 * float(O.tf_conv2d(ol.Xq.detach().abs(), ol.Wq.detach().abs(), ol.strides, 'SAME').max())
+    assert float((nhwc(y_p.detach()) - y_o).abs().max()) <= tol + 1e-12
+
+    g = torch.from_numpy(rng.standard_normal(tuple(y_o.shape)).astype(np.float32) * 0.7)
+    dx_o = ol.backward(g)
+    y_p.backward(nchw(g))
+    gq = ol.gradq
+    # dgrad / wgrad exact references in fp64 through autograd on the fp64 conv
+    X64 = ol.Xq.detach().double().requires_grad_(True)
+    W64 = ol.Wq.detach().double().requires_grad_(True)
+    y2 = O.tf_conv2d(X64, W64, ol.strides, 'SAME')
+    dX64, dW64 = torch.autograd.grad(y2, [X64, W64], gq.double())
+    assert torch.equal(nhwc(xg.grad), dX64.float()), 'dgrad is not the exactly-rounded integer result'
+    dW_ref = dW64.float() + (2 * wd) * ol.W.detach()
+    assert torch.equal(pl.weight.grad.cpu(), dW_ref), 'wgrad (+2*wd*W) is not the exactly-rounded result'
+    assert torch.allclose(pl.weight.grad.cpu(), ol.dW, rtol=1e-4, atol=1e-4 * float(ol.dW.abs().max()))
+    assert torch.allclose(nhwc(xg.grad), dx_o, rtol=1e-4, atol=1e-5 * float(dx_o.abs().max()) + 1e-12)
+    if bias:
+        db64 = gq.double().sum(dim=(0, 1, 2)).float()
+        assert torch.equal(pl.bias.grad.cpu(), db64)
+    # controller: apply and compare every range
+    rt.update_ranges()
+    want = [int(q.range) for q in ol.quantizers()]
+    assert list(rt.ranges().values()) == want
+
+
+@pytest.mark.parametrize('B,In,Out,bias', [(128, 2048, 400, True), (128, 400, 10, True), (256, 64, 10, False), (7, 20, 5, True)])
+def test_linear_q_forward_backward(B, In, Out, bias):
+    rng = np.random.default_rng(B + In + Out)
+    ctx = O.Context(O.PhiloxNoise(SEED))
+    wd = 2e-4
+    ol = O.Dense_q(ctx, 'd', 8, In, Out, use_bias=bias, weight_decay=wd, rng=rng)
+    rt = D.Runtime(SEED)
+    pl = D.Linear_q(8, In, Out, bias=bias, weight_decay=wd, runtime=rt).cuda()
+    rt.finalize('cuda')
+    pl.weight.data.copy_(ol.W.detach())
+    x = torch.from_numpy(rng.standard_normal((B, In)).astype(np.float32))
+    y_o = ol.forward(x)
+    xg = x.cuda().requires_grad_(True)
+    y_p = pl(xg)
+    y64 = (ol.Xq.detach().double() @ ol.Wq.detach().double()).float()
+    if bias:
+        y64 = y64 + ol.bq.detach()
+    assert torch.equal(y_p.detach().cpu(), y64)
+    assert torch.allclose(y_p.detach().cpu(), y_o, rtol=1e-5, atol=1e-5)
+    g = torch.from_numpy(rng.standard_normal((B, Out)).astype(np.float32) * 0.3)
+    dx_o = ol.backward(g)
+    y_p.backward(g.cuda())
+    gq = ol.gradq.double()
+    assert torch.equal(xg.grad.cpu(), (gq @ ol.Wq.detach().double().T).float())
+    assert torch.equal(pl.weight.grad.cpu(), (ol.Xq.detach().double().T @ gq).float() + (2 * wd) * ol.W.detach())
+    if bias:
+        assert torch.equal(pl.bias.grad.cpu(), gq.sum(0).float())
+    assert torch.allclose(xg.grad.cpu(), dx_o, rtol=1e-4, atol=1e-6)
+    rt.update_ranges()
+    assert list(rt.ranges().values()) == [int(q.range) for q in ol.quantizers()]
+
+
+@pytest.mark.parametrize('C,H,B', [(16, 8, 8), (64, 4, 16), (10, 3, 5)])
+def test_batchnorm_q_forward_backward(C, H, B):
+    rng = np.random.default_rng(C + H + B)
+    ctx = O.Context(O.PhiloxNoise(SEED))
+    wd = 2e-4
+    ol = O.BatchNorm_q(ctx, 'bn', 8, C, True, weight_decay=wd)
+    rt = D.Runtime(SEED)
+    pl = D.BatchNorm2d_q(8, C, weight_decay=wd, runtime=rt).cuda()
+    rt.finalize('cuda')
+    g0 = torch.from_numpy((1 + 0.3 * rng.standard_normal(C)).astype(np.float32))
+    b0 = torch.from_numpy((0.2 * rng.standard_normal(C)).astype(np.float32))
+    ol.layers[1].gamma.data.copy_(g0)
+    ol.layers[1].beta.data.copy_(b0)
+    pl[1].gamma.data.copy_(g0)
+    pl[1].beta.data.copy_(b0)
+    x = torch.from_numpy((rng.standard_normal((B, H, H, C)) * 1.2 + 0.3).astype(np.float32))
+    y_o = ol.forward(x)
+    xg = nchw(x).requires_grad_(True)
+    y_p = pl(xg)
+    # the rescale quantiser sees a normalised value that may differ in the last ulp between reduction orders:
+    # allow a handful of one-step mantissa differences
+    step = 2.0 ** -(8 - 2 - 1) * float(g0.abs().max())
+    diff = (nhwc(y_p.detach()) - y_o).abs()
+    assert float(diff.max()) <= step + 1e-6
+    assert float((diff > 1e-6).float().mean()) < 0.01
+    assert torch.allclose(pl[0].X_mean_running.cpu(), ol.layers[0].X_mean_running, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(pl[0].X_var_running.cpu(), ol.layers[0].X_var_running, rtol=1e-5, atol=1e-7)
+    g = torch.from_numpy(rng.standard_normal(tuple(y_o.shape)).astype(np.float32) * 0.5)
+    dx_o = ol.backward(g)
+    y_p.backward(nchw(g))
+    dgam_o, dbeta_o = ol.layers[1].dgamma, ol.layers[1].dbeta
+    assert torch.allclose(pl[1].beta.grad.cpu(), dbeta_o, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(pl[1].gamma.grad.cpu(), dgam_o, rtol=1e-3, atol=step * B * H * H * 0.02 + 1e-4)
+    ddiff = (nhwc(xg.grad) - dx_o).abs()
+    assert float((ddiff > 1e-4 * float(dx_o.abs().max())).float().mean()) < 0.02
+    rt.update_ranges()
+    assert list(rt.ranges().values()) == [int(q.range) for q in ol.quantizers()]
+
+
+def test_plumbing_layers_match_tf_semantics():
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.standard_normal((2, 7, 7, 5)).astype(np.float32))
+    # max-pool 3x3/2 SAME on 7 -> 4 (pad 1 before, 1 after); on 8 -> 4 (pad 0 before, 1 after)
+    for H in (7, 8, 32):
+        xx = torch.from_numpy(rng.standard_normal((2, H, H, 5)).astype(np.float32))
+        want = O.tf_max_pool(xx, [1, 3, 3, 1], [1, 2, 2, 1], 'SAME')
+        got = nhwc(D.MaxPool_q(3, 2, 'SAME')(nchw(xx)))
+        assert torch.equal(got, want)
+    want = O.tf_avg_pool(x, [1, 7, 7, 1], [1, 1, 1, 1], 'VALID')
+    got = nhwc(D.AvgPool_q(7, 1)(nchw(x)))
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+    # flatten follows NHWC order
+    assert torch.equal(D.Flatten_q(7 * 7 * 5)(nchw(x)).cpu(), x.reshape(2, -1))
+    # dropout: keep-prob semantics, x / keep * floor(keep + u)
+    d = D.Dropout_q(0.5)
+    u = torch.rand(2, 5, 7, 7, device='cuda')
+    d.uniform_fn = lambda t: u
+    xg = nchw(x)
+    assert torch.equal(d(xg), xg / 0.5 * torch.floor(0.5 + u))
+    d.eval()
+    assert d(xg) is xg
