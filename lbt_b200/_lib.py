@@ -75,6 +75,43 @@ def check(status):
         raise LbtError('liblbt_b200: %s (status %d)' % (msg, status))
 
 
+class Profiler:
+    """Brackets every C-ABI launch with CUDA events on the launching stream (bench.py's live roofline
+    measurement).  ``meta`` carries the algorithmic bytes / ops of the launch."""
+
+    def __init__(self):
+        self.records = []          # (name, start_event, end_event, meta)
+
+    def summary(self):
+        """{name: dict(launches, ms, bytes, ops)} after a synchronize."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, meta in self.records:
+            d = out.setdefault(name, dict(launches=0, ms=0.0, bytes=0, ops=0))
+            d['launches'] += 1
+            d['ms'] += a.elapsed_time(b)
+            d['bytes'] += (meta or {}).get('bytes', 0)
+            d['ops'] += (meta or {}).get('ops', 0)
+        return out
+
+
+profiler = None     # set to a Profiler instance to time each launch (never during CUDA-graph capture)
+
+
+def call(name, *args, meta=None):
+    """Invoke one C-ABI entry point and raise on a non-zero status."""
+    fn = getattr(lib(), name)
+    if profiler is None:
+        check(fn(*args))
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = fn(*args)
+    b.record()
+    profiler.records.append((name, a, b, meta))
+    check(rc)
+
+
 def ptr(t):
     """Raw device pointer of a CUDA tensor (None -> NULL)."""
     if t is None:

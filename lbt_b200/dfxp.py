@@ -68,10 +68,9 @@ class Runtime:
     def update_ranges(self):
         """The ``update_range_op`` fetch of trainer.py:157 for all quantisers, then step += 1."""
         f = self.flat
-        h = _lib.lib()
-        _lib.check(h.lbt_update_ranges(_lib.ptr(f['ranges']), _lib.ptr(f['counters']), _lib.ptr(f['bits']),
-                                       _lib.ptr(f['target']), len(self.sites), _lib.stream()))
-        _lib.check(h.lbt_step_advance(_lib.ptr(self.dev_step), _lib.stream()))
+        _lib.call('lbt_update_ranges', _lib.ptr(f['ranges']), _lib.ptr(f['counters']), _lib.ptr(f['bits']),
+                                       _lib.ptr(f['target']), len(self.sites), _lib.stream())
+        _lib.call('lbt_step_advance', _lib.ptr(self.dev_step), _lib.stream())
 
     def ranges(self):
         """{quantiser name: integer_bits} — the cheap parity probe (tf.summary of *_range, dfxp:180-190)."""
@@ -178,7 +177,7 @@ def _transpose_bytes(t):
     R, C = t.shape
     assert t.stride(1) == 1
     out = torch.empty(C, _pitch16(R), dtype=t.dtype, device=t.device)
-    _lib.check(_lib.lib().lbt_transpose_i8(_lib.ptr(t), R, C, t.stride(0), _lib.ptr(out), out.stride(0), _lib.stream()))
+    _lib.call('lbt_transpose_i8', _lib.ptr(t), R, C, t.stride(0), _lib.ptr(out), out.stride(0), _lib.stream())
     return out[:, :R]
 
 
@@ -188,15 +187,15 @@ def _im2col(src_nhwc, src_kind, OH, OW, kh, kw, sh, sw, pt, pl, transposed):
     K = kh * kw * C * segs
     M = N * OH * OW
     out = torch.empty(M, _pitch16(K), dtype=torch.int8 if src_kind != Q.MANT_U8 else torch.uint8, device=src_nhwc.device)
-    _lib.check(_lib.lib().lbt_im2col_i8(_lib.ptr(src_nhwc), src_kind, N, H, W, C, OH, OW, kh, kw, sh, sw, pt, pl,
-                                        1 if transposed else 0, _lib.ptr(out), out.stride(0), _lib.stream()))
+    _lib.call('lbt_im2col_i8', _lib.ptr(src_nhwc), src_kind, N, H, W, C, OH, OW, kh, kw, sh, sw, pt, pl,
+                                        1 if transposed else 0, _lib.ptr(out), out.stride(0), _lib.stream())
     return out[:, :K]
 
 
 def _colsum(mant2d, kind):
     acc = torch.zeros(mant2d.shape[1], dtype=torch.int64, device=mant2d.device)
-    _lib.check(_lib.lib().lbt_colsum_i(_lib.ptr(mant2d), kind, mant2d.shape[0], mant2d.shape[1], _lib.ptr(acc),
-                                       _lib.stream()))
+    _lib.call('lbt_colsum_i', _lib.ptr(mant2d), kind, mant2d.shape[0], mant2d.shape[1], _lib.ptr(acc),
+                                       _lib.stream())
     return acc
 
 

@@ -28,9 +28,9 @@ def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None):
     lda, ldb = _check_operand(A, K), _check_operand(B, K)
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
-    _lib.check(_lib.lib().lbt_gemm_i8(_lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
+    _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                                       _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), _lib.ptr(out), None,
-                                      out.stride(0), 1, 1, _lib.stream()))
+                                      out.stride(0), 1, 1, _lib.stream(), meta=dict(ops=2 * M * N * K))
     return out
 
 
@@ -45,9 +45,9 @@ def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
         tiles = -(-M // 128) * -(-N // min(256, max(16, 1 << (max(N, 1) - 1).bit_length())))
         sms = torch.cuda.get_device_properties(A.device).multi_processor_count
         k_splits = max(1, sms // max(1, tiles))
-    _lib.check(_lib.lib().lbt_gemm_i8(_lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
+    _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
                                       None, None, 0, None, None, _lib.ptr(acc64), N, int(alpha), int(k_splits),
-                                      _lib.stream()))
+                                      _lib.stream(), meta=dict(ops=2 * M * N * K))
     return acc64
 
 
@@ -55,9 +55,9 @@ def acc64_finalize(acc64, *, ibA=None, ibB=None, exp_const=0, add=None, add_scal
     """fp32 out = acc64 * 2^(exp_const + ibA + ibB) + add_scale * add."""
     if out is None:
         out = torch.empty(acc64.shape, dtype=torch.float32, device=acc64.device)
-    _lib.check(_lib.lib().lbt_acc64_finalize(_lib.ptr(acc64), acc64.numel(), _lib.ptr(ibA), _lib.ptr(ibB),
+    _lib.call('lbt_acc64_finalize', _lib.ptr(acc64), acc64.numel(), _lib.ptr(ibA), _lib.ptr(ibB),
                                              int(exp_const), _lib.ptr(add), float(add_scale), _lib.ptr(out),
-                                             _lib.stream()))
+                                             _lib.stream())
     return out
 
 

@@ -57,11 +57,11 @@ def quantize(x, bits, integer_bits, *, target_overflow_rate=0.0, mode=ROUND_NEAR
         if noise.numel() != n_inner or noise.dtype != torch.float32:
             raise _lib.LbtError('noise must be fp32 with X.shape[1:] elements (%d), got %d' % (n_inner, noise.numel()))
         noise = noise.contiguous()
-    h = _lib.lib()
-    _lib.check(h.lbt_quantize(_lib.ptr(x), n_outer, n_inner, int(bits), _lib.ptr(integer_bits),
+    _lib.call('lbt_quantize', _lib.ptr(x), n_outer, n_inner, int(bits), _lib.ptr(integer_bits),
                               float(target_overflow_rate), int(mode), _lib.ptr(noise), int(seed), int(offset),
                               _lib.ptr(dev_step), _lib.ptr(out) if want_fp32 else None, _lib.ptr(out_mant),
-                              int(mant_kind), _lib.ptr(counters), 1 if update_range else 0, _lib.stream()))
+                              int(mant_kind), _lib.ptr(counters), 1 if update_range else 0, _lib.stream(),
+              meta=dict(bytes=n_outer * n_inner * (4 + (4 if want_fp32 else 0) + {0: 0, 1: 1, 2: 1, 3: 2}[int(mant_kind)])))
     return (out if want_fp32 else None), out_mant
 
 
@@ -117,8 +117,8 @@ def update_range(X, target_overflow_rate, bits, integer_bits):
 def noise_fill(n_inner, seed, offset, device='cuda', dev_step=None):
     """The Philox noise vector ``lbt_quantize(mode=ROUND_PHILOX)`` uses for (seed, offset)."""
     u = torch.empty(int(n_inner), dtype=torch.float32, device=device)
-    _lib.check(_lib.lib().lbt_noise_fill(_lib.ptr(u), int(n_inner), int(seed), int(offset), _lib.ptr(dev_step),
-                                         _lib.stream()))
+    _lib.call('lbt_noise_fill', _lib.ptr(u), int(n_inner), int(seed), int(offset), _lib.ptr(dev_step),
+                                         _lib.stream())
     return u
 
 

@@ -63,9 +63,9 @@ class Trainer:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
             if self.sync_counters:
                 dist.all_reduce(rt.flat['counters'], op=dist.ReduceOp.SUM, group=self.group)
-        _lib.check(_lib.lib().lbt_sgd_momentum(_lib.ptr(self.flat_w), _lib.ptr(self.flat_a), _lib.ptr(self.flat_g),
+        _lib.call('lbt_sgd_momentum', _lib.ptr(self.flat_w), _lib.ptr(self.flat_a), _lib.ptr(self.flat_g),
                                                self.flat_w.numel(), self.lr, _lib.ptr(self.dev_lr), self.momentum,
-                                               1.0 / self.world, _lib.stream()))
+                                               1.0 / self.world, _lib.stream())
         rt.update_ranges()
 
     def step(self, X, y):

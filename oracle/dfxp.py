@@ -307,6 +307,10 @@ class Layer_q:
     def grads_and_vars(self):
         return []
 
+    def variables(self):
+        """Trainable variables in grads_and_vars() order (available before any backward)."""
+        return []
+
     def quantizers(self):
         return []
 
@@ -362,6 +366,9 @@ class Conv2d_q(Layer_q):
             r.append((self.db, self.b))
         return r
 
+    def variables(self):
+        return [self.W] + ([self.b] if self.use_bias else [])
+
     def quantizers(self):
         return [self.qX, self.qW] + ([self.qb] if self.use_bias else []) + [self.qG]
 
@@ -412,6 +419,9 @@ class Dense_q(Layer_q):
             r.append((self.db, self.b))
         return r
 
+    def variables(self):
+        return [self.W] + ([self.b] if self.use_bias else [])
+
     def quantizers(self):
         return [self.qX, self.qW] + ([self.qb] if self.use_bias else []) + [self.qG]
 
@@ -442,6 +452,12 @@ class Sequential_q(Layer_q):
         r = []
         for layer in self.layers:
             r += layer.quantizers()
+        return r
+
+    def variables(self):
+        r = []
+        for layer in self.layers:
+            r += layer.variables()
         return r
 
 
@@ -511,6 +527,9 @@ class Rescale_q(Layer_q):
 
     def grads_and_vars(self):
         return [(self.dgamma, self.gamma), (self.dbeta, self.beta)]
+
+    def variables(self):
+        return [self.gamma, self.beta]
 
     def quantizers(self):
         return [self.qX, self.qg, self.qb, self.qG]
@@ -638,6 +657,9 @@ class ResidualBlock_q(Layer_q):
     def grads_and_vars(self):
         return self.residual.grads_and_vars() + self.shortcut.grads_and_vars()
 
+    def variables(self):
+        return self.residual.variables() + self.shortcut.variables()
+
     def quantizers(self):
         return self.residual.quantizers() + self.shortcut.quantizers()
 
@@ -714,6 +736,12 @@ class Model:
         r = []
         for layer in self.layers:
             r += layer.quantizers()
+        return r
+
+    def variables(self):
+        r = []
+        for layer in self.layers:
+            r += layer.variables()
         return r
 
     def ranges(self):
