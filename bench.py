@@ -190,7 +190,7 @@ def run_native(a):
     if name.startswith('Resnet'):
         kw.update(image=image, num_classes=classes)
     torch.manual_seed(0)
-    model = getattr(M, name)(bits, **kw).to(dev).to(memory_format=torch.channels_last)
+    model = getattr(M, name)(bits, **kw).to(dev)
     trainer = Trainer(model, lr=1e-2, momentum=0.9)
 
     # synthetic data: a small pool of pinned host batches (NHWC fp32, like the reference's feed_dict)

@@ -180,6 +180,50 @@ int lbt_colsum_i(const void* in, int kind, size_t R, size_t C, int64_t* acc64, v
 int lbt_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float lr, const float* dev_lr,
                      float momentum, float grad_scale, void* stream);
 
+/*
+ * Fused quantised batch-norm = Normalization_q + Rescale_q (dynamic_fixed_point.py:539-743), training mode,
+ * NHWC tensors viewed as [n_outer = N, n_inner = H*W*C] with C % 4 == 0, all quantisers <= 8 bits and
+ * stochastic (noise pointer [n_inner] or NULL = in-kernel Philox keyed by (seed, offset_*, dev_step)).
+ * Statistics are exact integer sums of mantissas: `sums` buffers are int64, zeroed by the caller.
+ *
+ * fwd 1: k1 = Q_norm(x) (dfxp:584) ; sums[0..C) = sum k1, sums[C..2C) = sum k1^2 over N,H,W ; counters += stats.
+ */
+int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_inner, int C, int bits, const int32_t* ib,
+                           const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                           int8_t* k1, int64_t* sums, uint64_t* counters, void* stream);
+/*
+ * fwd 2: mean/var (biased, dfxp:588) from `sums`; y1 = (xq - mean) / sqrt(var + eps) (dfxp:616);
+ * k2 = Q_rescale(y1) (dfxp:677); out = xq2 * gamma_q + beta_q (dfxp:683) [+ add] [ReLU, dfxp:986].
+ * Optionally writes the batch moments and updates the running averages (momentum*avg + (1-momentum)*batch,
+ * dfxp:602-612).  gamma_q / beta_q are the fake-quantised vectors (lbt_quantize, dfxp:679-682).
+ */
+int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                     const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                     uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                     const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                     float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                     float momentum, void* stream);
+/*
+ * bwd 1: g (w.r.t. the module output) -> ReLU mask (relu: 0 none, 1 recomputed from k2, 2 from `out`)
+ * [-> d_add = masked g] -> kg2 = Q(g) (dfxp:687) -> sums[0..C) = sum kg2 (dbeta, :690),
+ * sums[C..2C) = sum kg2*k2 (dgamma, :689) -> dx2 = gq2 * gamma_q (:691) -> kg1 = Q(dx2) (dfxp:621)
+ * -> sums[2C..3C) = sum kg1, sums[3C..4C) = sum kg1*k1.
+ */
+int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
+                           size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                           const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                           const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                           const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                           uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
+                           int8_t* kg1, int64_t* sums, void* stream);
+/*
+ * bwd 2: dx = (gq1 - mean(gq1) - xhat * mean(gq1 * xhat)) / sqrt(var + eps), the batch-norm VJP that
+ * tf.gradients(y, X, gradq) yields for dfxp:616 (dfxp:623), from kg1, k1 and the two sum buffers.
+ */
+int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
+                     const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
+                     const int64_t* bwd_sums, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

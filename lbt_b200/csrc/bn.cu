@@ -1,0 +1,700 @@
+// Fused quantised batch-norm for B200 (sm_100a): Normalization_q + Rescale_q of
+// /root/reference/dynamic_fixed_point.py:539-743 in two HBM-bound passes forward and two backward,
+// instead of ~4 quantiser calls + ~25 TF elementwise/reduce kernels over activation-sized fp32 tensors.
+//
+//   fwd 1  lbt_bn_fwd_quant_stats : x (fp32) -> k1 = Q_norm(x) (s8) + exact per-channel sum(k1), sum(k1^2)
+//   fwd 2  lbt_bn_fwd_apply       : k1 -> y1 = (xq - mean)/sqrt(var+eps) -> k2 = Q_rescale(y1) (s8)
+//                                   -> out = relu?(xq2*gq + bq (+ add))   (fp32)
+//   bwd 1  lbt_bn_bwd_quant_stats : g -> relu mask -> kg2 = Q(g) -> sums for dgamma/dbeta -> dx2 = gq2*gq
+//                                   -> kg1 = Q(dx2) (s8) + sums for the batch-norm VJP (+ d_add)
+//   bwd 2  lbt_bn_bwd_apply       : kg1, k1 -> dx = (gq1 - mean(gq1) - xhat*mean(gq1*xhat)) / sqrt(var+eps)
+//
+// Batch statistics are taken over the QUANTISED input (dfxp:588) and are computed exactly: integer
+// sums of mantissas (int64), finished in fp64, rounded once to fp32.  Tensors are NHWC: [n_outer = N,
+// n_inner = H*W*C]; the rounding noise is indexed by the inner position and shared over N (dfxp:36).
+// A thread owns 4 consecutive channels of one inner position and walks down N, so its Philox draw and
+// its per-channel partial sums live in registers.
+#include "common.cuh"
+
+namespace lbt {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRows = 4;  // rows (batch entries) in flight per thread
+
+struct Tiling {
+  size_t n_outer, n_inner;
+  int C;
+  uint32_t n_vec, chunks, rows_per_group;
+  uint64_t total_tiles;
+  int fixed_channels;  // 1: a thread sees the same 4 channels in every tile (256 % (C/4) == 0)
+};
+
+struct QSite {
+  int bits;
+  const int32_t* ib;
+  const float* noise;  // explicit noise [n_inner] or NULL -> Philox
+  uint64_t seed, offset;
+  const uint64_t* dev_step;
+  unsigned long long* counters;
+};
+
+struct QC {
+  float m, inv_m, L, hi, half;
+};
+
+__device__ __forceinline__ QC make_qc(int bits, int ib) {
+  QC c;
+  int f = bits - ib - 1;
+  f = max(-126, min(126, f));
+  c.m = exp2i(f);
+  c.inv_m = exp2i(-f);
+  c.L = exp2i(bits - 1);
+  c.hi = c.L - 1.0f;
+  c.half = c.L * 0.5f;
+  return c;
+}
+
+// stochastic_identity (dfxp:34-37) + overflow counters (dfxp:60-66); returns the integral mantissa as float
+__device__ __forceinline__ float squant(float x, float u, const QC& c, uint32_t& n1, uint32_t& n2) {
+  const float y = __fmul_rn(x, c.m);
+  n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
+  n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
+  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+
+__device__ __forceinline__ float4 site_noise(const QSite& s, uint32_t v, uint64_t off) {
+  if (s.noise) return __ldg(reinterpret_cast<const float4*>(s.noise) + v);
+  return philox_noise4(v, s.seed, off);
+}
+__device__ __forceinline__ uint64_t site_offset(const QSite& s) {
+  uint64_t off = s.offset;
+  if (s.dev_step) off += (*s.dev_step) << 32;
+  return off;
+}
+
+__device__ __forceinline__ void publish_counters(unsigned long long* counters, uint32_t n1, uint32_t n2, size_t numel,
+                                                 uint32_t* s_red) {
+  // block reduce two u32 counters and add them to the site's statistics block; the last CTA (ticket)
+  // adds the element count.  Must be called by all threads.
+  n1 = warp_sum(n1);
+  n2 = warp_sum(n2);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) {
+    s_red[w] = n1;
+    s_red[8 + w] = n2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && counters) {
+    uint32_t b1 = 0, b2 = 0;
+    for (int i = 0; i < kThreads / 32; ++i) {
+      b1 += s_red[i];
+      b2 += s_red[8 + i];
+    }
+    if (b1) atomicAdd(counters + LBT_CNT_OVER, (unsigned long long)b1);
+    if (b2) atomicAdd(counters + LBT_CNT_OVER_HALF, (unsigned long long)b2);
+    __threadfence();
+    const unsigned long long t = atomicAdd(counters + LBT_CNT_TICKET, 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      atomicAdd(counters + LBT_CNT_NUMEL, (unsigned long long)numel);
+      counters[LBT_CNT_TICKET] = 0ull;
+    }
+  }
+}
+
+// Per-channel partial sums: NS sums for each of the thread's 4 channels.
+template <int NS>
+struct Acc {
+  long long s[NS][4];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0;
+  }
+};
+
+// Add the thread's partials for channels c0..c0+3 straight into the global sums (general path).
+template <int NS>
+__device__ __forceinline__ void flush_global(Acc<NS>& a, long long* sums, int C, int c0) {
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (a.s[i][j]) atomicAdd(reinterpret_cast<unsigned long long*>(sums) + (size_t)i * C + c0 + j, (unsigned long long)a.s[i][j]);
+  a.zero();
+}
+
+// Fixed-channel path: every thread kept the same channel group (c0 = 4 * (tid % (C/4))) for the whole
+// kernel.  Reduce across the lanes of a warp that share a group, then across warps through shared memory,
+// then one global atomic per (sum, channel) per CTA.
+template <int NS>
+__device__ __forceinline__ void flush_block(Acc<NS>& a, long long* sums, int C, unsigned long long* s_acc) {
+  const int groups = C >> 2;
+  for (int i = threadIdx.x; i < NS * C; i += kThreads) s_acc[i] = 0ull;
+  __syncthreads();
+  if (groups < 32) {
+    for (int o = 16; o >= groups; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a.s[i][j] += __shfl_xor_sync(0xffffffffu, a.s[i][j], o);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  if (groups >= 32 || lane < groups) {
+    const int c0 = 4 * (threadIdx.x % groups);
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (a.s[i][j]) atomicAdd(s_acc + (size_t)i * C + c0 + j, (unsigned long long)a.s[i][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NS * C; i += kThreads)
+    if (s_acc[i]) atomicAdd(reinterpret_cast<unsigned long long*>(sums) + i, s_acc[i]);
+}
+
+__device__ __forceinline__ void unpack4(uint32_t w, int (&k)[4]) {
+  k[0] = (int)(int8_t)(w & 0xff);
+  k[1] = (int)(int8_t)((w >> 8) & 0xff);
+  k[2] = (int)(int8_t)((w >> 16) & 0xff);
+  k[3] = (int)(int8_t)(w >> 24);
+}
+__device__ __forceinline__ uint32_t pack4(const float (&k)[4]) {
+  const int i0 = __float2int_rn(k[0]), i1 = __float2int_rn(k[1]), i2 = __float2int_rn(k[2]), i3 = __float2int_rn(k[3]);
+  return (uint32_t)(i0 & 0xff) | ((uint32_t)(i1 & 0xff) << 8) | ((uint32_t)(i2 & 0xff) << 16) | ((uint32_t)(i3 & 0xff) << 24);
+}
+
+// Batch moments of the quantised input from the exact integer sums (dfxp:588, biased variance),
+// finished in fp64 and rounded once: mean = 2^-f * S1/n, var = 2^-2f * (S2/n - (S1/n)^2).
+__device__ __forceinline__ void moments(const long long* sums, int C, int c, double n, float inv_m, float& mean, float& var) {
+  const double s1 = (double)sums[c], s2 = (double)sums[C + c];
+  const double mu = s1 / n;
+  double v = s2 / n - mu * mu;
+  if (v < 0.0) v = 0.0;
+  mean = (float)(mu * (double)inv_m);
+  var = (float)(v * (double)inv_m * (double)inv_m);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fwd 1
+// ------------------------------------------------------------------------------------------------
+struct Fwd1Params {
+  Tiling t;
+  const float* x;
+  QSite q;
+  int8_t* k1;
+  long long* sums;  // [2*C]
+};
+
+__global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
+  extern __shared__ unsigned long long s_acc[];
+  __shared__ uint32_t s_red[16];
+  const QC c = make_qc(p.q.bits, *reinterpret_cast<volatile const int32_t*>(p.q.ib));
+  const uint64_t off = site_offset(p.q);
+  uint32_t n1 = 0, n2 = 0;
+  Acc<2> acc;
+  acc.zero();
+  for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), ch = (uint32_t)(tile % p.t.chunks);
+    const uint32_t v = ch * kThreads + threadIdx.x;
+    if (v < p.t.n_vec) {
+      const float4 u = site_noise(p.q, v, off);
+      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      for (size_t r = r0; r < r1; r += kRows) {
+        float4 xv[kRows];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          if (r + i < r1) xv[i] = __ldcs(reinterpret_cast<const float4*>(p.x + (r + i) * p.t.n_inner) + v);
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          if (r + i < r1) {
+            float k[4];
+            k[0] = squant(xv[i].x, u.x, c, n1, n2);
+            k[1] = squant(xv[i].y, u.y, c, n1, n2);
+            k[2] = squant(xv[i].z, u.z, c, n1, n2);
+            k[3] = squant(xv[i].w, u.w, c, n1, n2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const long long ki = (long long)__float2int_rn(k[j]);
+              acc.s[0][j] += ki;
+              acc.s[1][j] += ki * ki;
+            }
+            *reinterpret_cast<uint32_t*>(p.k1 + (r + i) * p.t.n_inner + 4 * (size_t)v) = pack4(k);
+          }
+      }
+      if (!p.t.fixed_channels) flush_global<2>(acc, p.sums, p.t.C, (int)((4ull * v) % (uint64_t)p.t.C));
+    }
+  }
+  if (p.t.fixed_channels) flush_block<2>(acc, p.sums, p.t.C, s_acc);
+  publish_counters(p.q.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fwd 2
+// ------------------------------------------------------------------------------------------------
+struct Fwd2Params {
+  Tiling t;
+  const int8_t* k1;
+  int bits1;
+  const int32_t* ib1;
+  const long long* sums;  // [2*C] from fwd 1
+  float eps;
+  QSite q2;               // Rescale_q's X quantiser
+  const float* gq;        // quantised gamma [C]
+  const float* bq;        // quantised beta  [C]
+  const float* add;       // optional shortcut tensor, same shape
+  int relu;
+  int8_t* k2;
+  float* out;
+  float* batch_mean;      // [C] optional
+  float* batch_var;       // [C] optional
+  float* run_mean;        // [C] optional, updated in place with `momentum` (dfxp:602-612)
+  float* run_var;
+  float momentum;
+};
+
+__global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
+  extern __shared__ float s_par[];  // [4*C]: mean, denom, gq, bq
+  __shared__ uint32_t s_red[16];
+  const int C = p.t.C;
+  const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
+  const QC c2 = make_qc(p.q2.bits, *reinterpret_cast<volatile const int32_t*>(p.q2.ib));
+  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  for (int ch = threadIdx.x; ch < C; ch += kThreads) {
+    float mean, var;
+    moments(p.sums, C, ch, n, c1.inv_m, mean, var);
+    s_par[ch] = mean;
+    s_par[C + ch] = __fsqrt_rn(__fadd_rn(var, p.eps));  // (var + eps) ** 0.5, dfxp:616
+    s_par[2 * C + ch] = p.gq[ch];
+    s_par[3 * C + ch] = p.bq[ch];
+    if (blockIdx.x == 0) {
+      if (p.batch_mean) p.batch_mean[ch] = mean;
+      if (p.batch_var) p.batch_var[ch] = var;
+      if (p.run_mean) {  // momentum * average + (1 - momentum) * variable
+        p.run_mean[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_mean[ch]), __fmul_rn(1.0f - p.momentum, mean));
+        p.run_var[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_var[ch]), __fmul_rn(1.0f - p.momentum, var));
+      }
+    }
+  }
+  __syncthreads();
+  const uint64_t off = site_offset(p.q2);
+  uint32_t n1 = 0, n2 = 0;
+  for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
+    const uint32_t v = chk * kThreads + threadIdx.x;
+    if (v >= p.t.n_vec) continue;
+    const int c0 = (int)((4ull * v) % (uint64_t)C);
+    const float4 u = site_noise(p.q2, v, off);
+    const float un[4] = {u.x, u.y, u.z, u.w};
+    float mean[4], den[4], g[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mean[j] = s_par[c0 + j];
+      den[j] = s_par[C + c0 + j];
+      g[j] = s_par[2 * C + c0 + j];
+      b[j] = s_par[3 * C + c0 + j];
+    }
+    const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+    for (size_t r = r0; r < r1; r += kRows) {
+      uint32_t kw[kRows];
+      float4 av[kRows];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          kw[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
+          if (p.add) av[i] = __ldcs(reinterpret_cast<const float4*>(p.add + idx));
+        }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          int k1[4];
+          unpack4(kw[i], k1);
+          const float a4[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
+          float k2[4], o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float xq = __int2float_rn(k1[j]) * c1.inv_m;
+            const float y1 = __fdiv_rn(__fsub_rn(xq, mean[j]), den[j]);      // dfxp:616
+            k2[j] = squant(y1, un[j], c2, n1, n2);                            // dfxp:677
+            float y2 = __fadd_rn(__fmul_rn(k2[j] * c2.inv_m, g[j]), b[j]);    // dfxp:683
+            if (p.add) y2 = __fadd_rn(y2, a4[j]);                             // residual sum, dfxp:862
+            if (p.relu) y2 = fmaxf(0.0f, y2);                                 // tf.maximum(0.0, X), dfxp:986
+            o[j] = y2;
+          }
+          *reinterpret_cast<uint32_t*>(p.k2 + idx) = pack4(k2);
+          *reinterpret_cast<float4*>(p.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+  }
+  publish_counters(p.q2.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bwd 1
+// ------------------------------------------------------------------------------------------------
+struct Bwd1Params {
+  Tiling t;
+  const float* g;       // gradient w.r.t. the module output
+  const float* out;     // module output (needed for the ReLU mask when `add` was fused), or NULL
+  int relu;             // 0 none, 1 mask recomputed from k2 (no add), 2 mask from `out`
+  const int8_t* k2;
+  const int8_t* k1;
+  int bits2;
+  const int32_t* ib2;
+  const float* gq;
+  const float* bq;
+  QSite qg2;            // Rescale_q's gradient quantiser (dfxp:687)
+  QSite qg1;            // Normalization_q's gradient quantiser (dfxp:621)
+  float* d_add;         // optional: gradient w.r.t. the fused shortcut input (= masked g)
+  int8_t* kg1;
+  long long* sums;      // [4*C]: sum kg2, sum kg2*k2, sum kg1, sum kg1*k1
+};
+
+__global__ void __launch_bounds__(kThreads) bn_bwd1_kernel(const Bwd1Params p) {
+  extern __shared__ unsigned long long s_acc[];
+  __shared__ uint32_t s_red[16];
+  const int C = p.t.C;
+  const QC c2 = make_qc(p.bits2, *reinterpret_cast<volatile const int32_t*>(p.ib2));
+  const QC cg2 = make_qc(p.qg2.bits, *reinterpret_cast<volatile const int32_t*>(p.qg2.ib));
+  const QC cg1 = make_qc(p.qg1.bits, *reinterpret_cast<volatile const int32_t*>(p.qg1.ib));
+  const uint64_t off2 = site_offset(p.qg2), off1 = site_offset(p.qg1);
+  uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  Acc<4> acc;
+  acc.zero();
+  for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
+    const uint32_t v = chk * kThreads + threadIdx.x;
+    if (v < p.t.n_vec) {
+      const int c0 = (int)((4ull * v) % (uint64_t)C);
+      const float4 u2v = site_noise(p.qg2, v, off2), u1v = site_noise(p.qg1, v, off1);
+      const float u2[4] = {u2v.x, u2v.y, u2v.z, u2v.w}, u1[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
+      float g[4], b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        g[j] = __ldg(p.gq + c0 + j);
+        b[j] = __ldg(p.bq + c0 + j);
+      }
+      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      for (size_t r = r0; r < r1; r += kRows) {
+        float4 gv[kRows], ov[kRows];
+        uint32_t w2[kRows], w1[kRows];
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          if (r + i < r1) {
+            const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+            gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
+            w2[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k2 + idx));
+            w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
+            if (p.relu == 2) ov[i] = __ldcs(reinterpret_cast<const float4*>(p.out + idx));
+          }
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          if (r + i < r1) {
+            const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+            int k2[4], k1[4];
+            unpack4(w2[i], k2);
+            unpack4(w1[i], k1);
+            const float gin[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+            const float oin[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+            float gm[4], kq1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float gj = gin[j];
+              if (p.relu == 1) {
+                const float y2 = __fadd_rn(__fmul_rn(__int2float_rn(k2[j]) * c2.inv_m, g[j]), b[j]);
+                if (!(y2 > 0.0f)) gj = 0.0f;
+              } else if (p.relu == 2) {
+                if (!(oin[j] > 0.0f)) gj = 0.0f;
+              }
+              gm[j] = gj;
+              const float kg2 = squant(gj, u2[j], cg2, a1, a2);                    // dfxp:687
+              const long long kg2i = (long long)__float2int_rn(kg2);
+              acc.s[0][j] += kg2i;                                                 // dbeta  (dfxp:690)
+              acc.s[1][j] += kg2i * (long long)k2[j];                              // dgamma (dfxp:689)
+              const float dx2 = __fmul_rn(kg2 * cg2.inv_m, g[j]);                  // dfxp:691
+              kq1[j] = squant(dx2, u1[j], cg1, b1, b2);                            // dfxp:621
+              const long long kg1i = (long long)__float2int_rn(kq1[j]);
+              acc.s[2][j] += kg1i;
+              acc.s[3][j] += kg1i * (long long)k1[j];
+            }
+            if (p.d_add) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+            *reinterpret_cast<uint32_t*>(p.kg1 + idx) = pack4(kq1);
+          }
+      }
+      if (!p.t.fixed_channels) flush_global<4>(acc, p.sums, C, c0);
+    }
+  }
+  if (p.t.fixed_channels) flush_block<4>(acc, p.sums, C, s_acc);
+  const size_t numel = p.t.n_outer * p.t.n_inner;
+  publish_counters(p.qg2.counters, a1, a2, numel, s_red);
+  publish_counters(p.qg1.counters, b1, b2, numel, s_red);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bwd 2
+// ------------------------------------------------------------------------------------------------
+struct Bwd2Params {
+  Tiling t;
+  const int8_t* kg1;
+  const int8_t* k1;
+  int bits1;
+  const int32_t* ib1;
+  const long long* fsums;  // [2*C] forward sums
+  float eps;
+  int bitsg1;
+  const int32_t* ibg1;
+  const long long* bsums;  // [4*C] backward sums (uses [2C..4C))
+  float* dx;
+};
+
+__global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
+  extern __shared__ float s_par[];  // [5*C]: mean, 1/den, mean_g, mean_gxhat, (unused)
+  const int C = p.t.C;
+  const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
+  const QC cg = make_qc(p.bitsg1, *reinterpret_cast<volatile const int32_t*>(p.ibg1));
+  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  for (int ch = threadIdx.x; ch < C; ch += kThreads) {
+    float mean, var;
+    moments(p.fsums, C, ch, n, c1.inv_m, mean, var);
+    const float den = __fsqrt_rn(__fadd_rn(var, p.eps));
+    // mean(gq) and mean(gq * xhat) from the exact integer sums, finished in fp64
+    const double sg = (double)p.bsums[2 * C + ch] * (double)cg.inv_m;                       // sum gq
+    const double sgx = (double)p.bsums[3 * C + ch] * (double)cg.inv_m * (double)c1.inv_m;   // sum gq*xq
+    const double mg = sg / n;
+    const double mgx = ((sgx - (double)mean * sg) / (double)den) / n;                        // mean(gq * xhat)
+    s_par[ch] = mean;
+    s_par[C + ch] = den;
+    s_par[2 * C + ch] = (float)mg;
+    s_par[3 * C + ch] = (float)mgx;
+  }
+  __syncthreads();
+  for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
+    const uint32_t v = chk * kThreads + threadIdx.x;
+    if (v >= p.t.n_vec) continue;
+    const int c0 = (int)((4ull * v) % (uint64_t)C);
+    float mean[4], den[4], mg[4], mgx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mean[j] = s_par[c0 + j];
+      den[j] = s_par[C + c0 + j];
+      mg[j] = s_par[2 * C + c0 + j];
+      mgx[j] = s_par[3 * C + c0 + j];
+    }
+    const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+    for (size_t r = r0; r < r1; r += kRows) {
+      uint32_t wg[kRows], w1[kRows];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          wg[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.kg1 + idx));
+          w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
+        }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          int kg[4], k1[4];
+          unpack4(wg[i], kg);
+          unpack4(w1[i], k1);
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float gq = __int2float_rn(kg[j]) * cg.inv_m;
+            const float xhat = __fdiv_rn(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j]);
+            // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616)
+            o[j] = __fdiv_rn(gq - mg[j] - xhat * mgx[j], den[j]);
+          }
+          *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+  }
+}
+
+// ---- host helpers ----------------------------------------------------------------------------
+int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid) {
+  if (C <= 0 || (C & 3) || n_inner % (size_t)C) return LBT_EUNSUPPORTED;
+  if (n_inner / 4 >= 0xffffffffull) return LBT_EUNSUPPORTED;
+  const DeviceInfo& di = device_info();
+  t.n_outer = n_outer;
+  t.n_inner = n_inner;
+  t.C = C;
+  t.n_vec = (uint32_t)(n_inner / 4);
+  t.chunks = (t.n_vec + kThreads - 1) / kThreads;
+  uint32_t rpg = 32;
+  if (rpg > n_outer) rpg = (uint32_t)n_outer;
+  while (rpg > 1 && (uint64_t)t.chunks * ((n_outer + rpg - 1) / rpg) < 2ull * di.sm_count) rpg = (rpg + 1) / 2;
+  t.rows_per_group = rpg;
+  t.total_tiles = (uint64_t)t.chunks * ((n_outer + rpg - 1) / rpg);
+  const int groups = C >> 2;
+  t.fixed_channels = (groups <= kThreads && (kThreads % groups) == 0) ? 1 : 0;
+  const uint64_t cap = (uint64_t)di.sm_count * 6;
+  grid = (unsigned)(t.total_tiles < cap ? t.total_tiles : cap);
+  return LBT_OK;
+}
+
+QSite make_site(int bits, const int32_t* ib, const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                uint64_t* counters) {
+  QSite s;
+  s.bits = bits;
+  s.ib = ib;
+  s.noise = noise;
+  s.seed = seed;
+  s.offset = offset;
+  s.dev_step = dev_step;
+  s.counters = reinterpret_cast<unsigned long long*>(counters);
+  return s;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(bn)");
+      return LBT_ECUDA;
+    }
+  }
+  return LBT_OK;
+}
+
+}  // namespace
+}  // namespace lbt
+
+using namespace lbt;
+
+extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_inner, int C, int bits, const int32_t* ib,
+                                      const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                                      int8_t* k1, int64_t* sums, uint64_t* counters, void* stream) {
+  if (!x || !ib || !k1 || !sums) return LBT_EINVAL;
+  if (bits < 2 || bits > 8) return LBT_EUNSUPPORTED;
+  if (n_outer == 0 || n_inner == 0) return LBT_OK;
+  if (!al16(x) || !al4(k1) || (noise && !al16(noise))) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  Fwd1Params p{};
+  unsigned grid;
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  if (rc) return rc;
+  p.x = x;
+  p.q = make_site(bits, ib, noise, seed, offset, dev_step, counters);
+  p.k1 = k1;
+  p.sums = reinterpret_cast<long long*>(sums);
+  const size_t smem = (size_t)2 * C * 8;
+  if ((rc = set_smem(bn_fwd1_kernel, smem))) return rc;
+  bn_fwd1_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("lbt_bn_fwd_quant_stats");
+}
+
+extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                                const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                                uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                                const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                                float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                                float momentum, void* stream) {
+  if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2 || !out) return LBT_EINVAL;
+  if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
+  if ((run_mean == nullptr) != (run_var == nullptr)) return LBT_EINVAL;
+  if (n_outer == 0 || n_inner == 0) return LBT_OK;
+  if (!al4(k1) || !al4(k2) || !al16(out) || (add && !al16(add)) || (noise2 && !al16(noise2))) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  Fwd2Params p{};
+  unsigned grid;
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  if (rc) return rc;
+  p.k1 = k1;
+  p.bits1 = bits1;
+  p.ib1 = ib1;
+  p.sums = reinterpret_cast<const long long*>(sums);
+  p.eps = eps;
+  p.q2 = make_site(bits2, ib2, noise2, seed, offset2, dev_step, counters2);
+  p.gq = gamma_q;
+  p.bq = beta_q;
+  p.add = add;
+  p.relu = relu;
+  p.k2 = k2;
+  p.out = out;
+  p.batch_mean = batch_mean;
+  p.batch_var = batch_var;
+  p.run_mean = run_mean;
+  p.run_var = run_var;
+  p.momentum = momentum;
+  const size_t smem = (size_t)4 * C * 4;
+  if ((rc = set_smem(bn_fwd2_kernel, smem))) return rc;
+  bn_fwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("lbt_bn_fwd_apply");
+}
+
+extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
+                                      size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                                      const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                                      const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                                      const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                                      uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
+                                      int8_t* kg1, int64_t* sums, void* stream) {
+  if (!g || !k2 || !k1 || !ib2 || !gamma_q || !beta_q || !ib_g2 || !ib_g1 || !kg1 || !sums) return LBT_EINVAL;
+  if (relu < 0 || relu > 2 || (relu == 2 && !out)) return LBT_EINVAL;
+  if (bits2 < 2 || bits2 > 8 || bits_g2 < 2 || bits_g2 > 8 || bits_g1 < 2 || bits_g1 > 8) return LBT_EUNSUPPORTED;
+  if (n_outer == 0 || n_inner == 0) return LBT_OK;
+  if (!al16(g) || !al4(k2) || !al4(k1) || !al4(kg1) || (out && !al16(out)) || (d_add && !al16(d_add)) ||
+      (noise_g2 && !al16(noise_g2)) || (noise_g1 && !al16(noise_g1)))
+    return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  Bwd1Params p{};
+  unsigned grid;
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  if (rc) return rc;
+  p.g = g;
+  p.out = out;
+  p.relu = relu;
+  p.k2 = k2;
+  p.k1 = k1;
+  p.bits2 = bits2;
+  p.ib2 = ib2;
+  p.gq = gamma_q;
+  p.bq = beta_q;
+  p.qg2 = make_site(bits_g2, ib_g2, noise_g2, seed, offset_g2, dev_step, counters_g2);
+  p.qg1 = make_site(bits_g1, ib_g1, noise_g1, seed, offset_g1, dev_step, counters_g1);
+  p.d_add = d_add;
+  p.kg1 = kg1;
+  p.sums = reinterpret_cast<long long*>(sums);
+  const size_t smem = (size_t)4 * C * 8;
+  if ((rc = set_smem(bn_bwd1_kernel, smem))) return rc;
+  bn_bwd1_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("lbt_bn_bwd_quant_stats");
+}
+
+extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
+                                const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
+                                const int64_t* bwd_sums, float* dx, void* stream) {
+  if (!kg1 || !k1 || !ib1 || !fwd_sums || !ib_g1 || !bwd_sums || !dx) return LBT_EINVAL;
+  if (n_outer == 0 || n_inner == 0) return LBT_OK;
+  if (!al4(kg1) || !al4(k1) || !al16(dx)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  Bwd2Params p{};
+  unsigned grid;
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  if (rc) return rc;
+  p.kg1 = kg1;
+  p.k1 = k1;
+  p.bits1 = bits1;
+  p.ib1 = ib1;
+  p.fsums = reinterpret_cast<const long long*>(fwd_sums);
+  p.eps = eps;
+  p.bitsg1 = bits_g1;
+  p.ibg1 = ib_g1;
+  p.bsums = reinterpret_cast<const long long*>(bwd_sums);
+  p.dx = dx;
+  const size_t smem = (size_t)4 * C * 4;
+  if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
+  bn_bwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("lbt_bn_bwd_apply");
+}

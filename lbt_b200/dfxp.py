@@ -211,6 +211,8 @@ class _QConv2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, layer):
         x = _mem_contig(x)
+        if not weight.is_contiguous():      # HWIO memory order is part of the semantics (noise broadcasts over kh)
+            weight = weight.contiguous()
         N, Cin, H, W = x.shape
         kh, kw, _, Cout = weight.shape
         sh, sw = layer.stride
@@ -495,11 +497,94 @@ class Rescale_q(nn.Module):
         return _GradQuant.apply(y, self.qG)
 
 
+def _site_args(site, x_like):
+    """(noise pointer tensor or None, Philox offset) of a quantiser site for the fused kernels."""
+    rt = site.runtime
+    if rt.noise_fn is not None:
+        return rt.noise_fn(site, Q.rows_view(x_like)[1], x_like.device).contiguous(), 0
+    return None, Q.make_offset(site.qid, 0)
+
+
+class _FusedBNFn(torch.autograd.Function):
+    """Normalization_q + Rescale_q (+ residual add, + ReLU) in 2 forward and 2 backward passes over the
+    activation (csrc/bn.cu), saving only the two s8 mantissa tensors for backward."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, add, bn, relu):
+        norm, resc = bn[0], bn[1]
+        rt = norm.qX.runtime
+        x = _mem_contig(x)
+        N, C = x.shape[0], x.shape[1]
+        n_inner = x.numel() // N
+        dev = x.device
+        sums = torch.zeros(2 * C, dtype=torch.int64, device=dev)
+        k1 = torch.empty_like(x, dtype=torch.int8)
+        nz1, off1 = _site_args(norm.qX, x)
+        _lib.call('lbt_bn_fwd_quant_stats', _lib.ptr(x), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
+                  _lib.ptr(nz1), rt.seed, off1, _lib.ptr(rt.dev_step), _lib.ptr(k1), _lib.ptr(sums),
+                  _lib.ptr(norm.qX.counters), _lib.stream(), meta=dict(bytes=x.numel() * 5))
+        gq, _ = resc.qg.quantize(gamma.detach())                                               # dfxp:679
+        bq, _ = resc.qb.quantize(beta.detach())                                                # dfxp:681
+        k2 = torch.empty_like(k1)
+        out = torch.empty_like(x)
+        if add is not None:
+            add = _mem_contig(add)
+        nz2, off2 = _site_args(resc.qX, x)
+        relu_mode = 0 if not relu else (2 if add is not None else 1)
+        _lib.call('lbt_bn_fwd_apply', _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range), _lib.ptr(sums),
+                  float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
+                  _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add),
+                  1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
+                  _lib.ptr(norm.X_var_running), float(norm.momentum), _lib.stream(),
+                  meta=dict(bytes=x.numel() * (6 + (4 if add is not None else 0))))
+        ctx.bn, ctx.relu_mode, ctx.has_add = bn, relu_mode, add is not None
+        ctx.save_for_backward(k1, k2, sums, gq, bq, gamma, out if relu_mode == 2 else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        bn = ctx.bn
+        norm, resc = bn[0], bn[1]
+        rt = norm.qX.runtime
+        k1, k2, sums, gq, bq, gamma, out = ctx.saved_tensors
+        g = _mem_contig(g)
+        N, C = g.shape[0], g.shape[1]
+        n_inner = g.numel() // N
+        dev = g.device
+        bsums = torch.zeros(4 * C, dtype=torch.int64, device=dev)
+        kg1 = torch.empty_like(k1)
+        d_add = torch.empty_like(g) if ctx.has_add else None
+        nzg2, offg2 = _site_args(resc.qG, g)
+        nzg1, offg1 = _site_args(norm.qG, g)
+        _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g), _lib.ptr(out), ctx.relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
+                  C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
+                  _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
+                  _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
+                  _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums), _lib.stream(),
+                  meta=dict(bytes=g.numel() * (7 + (4 if ctx.relu_mode == 2 else 0) + (4 if ctx.has_add else 0))))
+        dx = torch.empty_like(g)
+        _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
+                  _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
+                  _lib.stream(), meta=dict(bytes=g.numel() * 6))
+        # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
+        dbeta = G.acc64_finalize(bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
+        dgamma = G.acc64_finalize(bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
+                                  exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add=gamma.detach(),
+                                  add_scale=2 * resc.weight_decay)
+        return dx, dgamma, dbeta, d_add, None, None
+
+
 class BatchNorm2d_q(nn.Sequential):
-    """dfxp:697-743: Normalization_q then Rescale_q (whose input range is hard-coded to 2, dfxp:735)."""
+    """dfxp:697-743: Normalization_q then Rescale_q (whose input range is hard-coded to 2, dfxp:735).
+
+    In training mode with <= 8-bit quantisers and C % 4 == 0 the pair runs as the fused kernels of
+    csrc/bn.cu; ``forward(x, add=None, relu=False)`` can additionally fold the residual sum and the ReLU
+    that follow it in the reference's blocks (dfxp:862, 986).  Otherwise the two sub-modules run one
+    after the other."""
 
     def __init__(self, bits, num_features, momentum=0.999, eps=1e-5, *, weight_decay=0.0, target_overflow_rate=0.0,
-                 input_range=2, gamma_range=2, beta_range=2, grad_range=2, grad_bits=None, name='bn', runtime=None):
+                 input_range=2, gamma_range=2, beta_range=2, grad_range=2, grad_bits=None, name='bn', runtime=None,
+                 fused=True, relu=False):
         super().__init__(
             Normalization_q(bits, num_features, momentum, eps, target_overflow_rate=target_overflow_rate,
                             input_range=input_range, grad_range=grad_range, grad_bits=grad_bits, name=name + '-norm',
@@ -507,6 +592,22 @@ class BatchNorm2d_q(nn.Sequential):
             Rescale_q(bits, num_features, weight_decay=weight_decay, target_overflow_rate=target_overflow_rate,
                       input_range=2, gamma_range=gamma_range, beta_range=beta_range, grad_range=grad_range,
                       grad_bits=grad_bits, name=name + '-rescale', runtime=runtime))
+        self.fused = fused
+        self.relu = relu            # apply the ReLU that follows this BN in the reference's layer lists
+
+    def _can_fuse(self, x):
+        norm, resc = self[0], self[1]
+        return (self.fused and self.training and x.dim() in (2, 4) and x.shape[1] % 4 == 0 and
+                max(norm.qX.bits, norm.qG.bits, resc.qX.bits, resc.qG.bits) <= 8 and min(norm.qX.bits, resc.qX.bits) >= 2)
+
+    def forward(self, x, add=None, relu=False):
+        relu = relu or self.relu
+        if self._can_fuse(x):
+            return _FusedBNFn.apply(x, self[1].gamma, self[1].beta, add, self, relu)
+        y = self[1](self[0](x))
+        if add is not None:
+            y = y + add
+        return F.relu(y) if relu else y
 
     def info(self):
         return 'BatchNorm'
@@ -597,9 +698,11 @@ class ResidualBlock_q(nn.Module):
         super().__init__()
         ckw = dict(bias=not batch_norm, weight_decay=weight_decay, input_range=input_range, weight_range=weight_range,
                    bias_range=bias_range, grad_range=grad_range, grad_bits=grad_bits, input_signed=False, runtime=runtime)
-        self._bn = lambda n, c: (BatchNorm2d_q(bits, c, weight_decay=weight_decay, target_overflow_rate=target_overflow_rate,
-                                               input_range=input_range, grad_range=grad_range, grad_bits=grad_bits, name=n,
-                                               runtime=runtime) if batch_norm else nn.Identity())
+        # relu=True folds the ReLU that follows the BN in the reference (dfxp:795, 928) into the BN kernels
+        self._bn = lambda n, c, relu=False: (
+            BatchNorm2d_q(bits, c, weight_decay=weight_decay, target_overflow_rate=target_overflow_rate,
+                          input_range=input_range, grad_range=grad_range, grad_bits=grad_bits, name=n, runtime=runtime,
+                          relu=relu) if batch_norm else (ReLU_q() if relu else nn.Identity()))
         self.residual = self._build_residual(bits, in_channels, channels, stride, name, ckw)
         if stride == 1 and in_channels == self.expansion * channels:                           # dfxp:828-829
             self.shortcut = nn.Sequential()
@@ -613,13 +716,21 @@ class ResidualBlock_q(nn.Module):
     def _build_residual(self, bits, in_channels, channels, stride, name, ckw):
         return nn.Sequential(
             Conv2d_q(bits, in_channels, channels, 3, stride, 'SAME', name=name + '-1', **ckw),
-            self._bn(name + '-bn1', channels), ReLU_q(),
+            self._bn(name + '-bn1', channels, relu=True),
             Conv2d_q(bits, channels, channels, 3, 1, 'SAME', name=name + '-2', **ckw),
             self._bn(name + '-bn2', channels))
 
     def forward(self, x):
-        # block inputs come from a ReLU (or max-pool of one) in every reference model: non-negative
-        return F.relu(self.residual(x) + self.shortcut(x))                                     # dfxp:858-863
+        # y = relu(residual(x) + shortcut(x)) (dfxp:858-863); the sum and the ReLU ride in the last BN's kernels.
+        # Block inputs come from a ReLU (or a max-pool of one) in every reference model: non-negative.
+        r = x
+        for m in list(self.residual)[:-1]:
+            r = m(r)
+        last = self.residual[-1]
+        sc = self.shortcut(x)
+        if isinstance(last, BatchNorm2d_q):
+            return last(r, add=sc, relu=True)
+        return F.relu(last(r) + sc)
 
     def info(self):
         return 'Residual block'
@@ -631,8 +742,8 @@ class ResidualBottleneck_q(ResidualBlock_q):
     def _build_residual(self, bits, in_channels, channels, stride, name, ckw):
         return nn.Sequential(
             Conv2d_q(bits, in_channels, channels, 1, 1, 'SAME', name=name + '-1', **ckw),
-            self._bn(name + '-bn1', channels), ReLU_q(),
+            self._bn(name + '-bn1', channels, relu=True),
             Conv2d_q(bits, channels, channels, 3, stride, 'SAME', name=name + '-2', **ckw),      # stride on the 3x3
-            self._bn(name + '-bn2', channels), ReLU_q(),
+            self._bn(name + '-bn2', channels, relu=True),
             Conv2d_q(bits, channels, 4 * channels, 1, 1, 'SAME', name=name + '-3', **ckw),
             self._bn(name + '-bn3', 4 * channels))

@@ -92,8 +92,7 @@ class CIFAR10_Resnet(Model):
         b = self.bits
         return [
             dfxp.Conv2d_pq(b, 3, 16, 3, 1, 'SAME', bias=False, **self._kw(name='conv1', input_signed=True)),
-            dfxp.BatchNorm2d_q(b, 16, **self._kw(name='conv1-bn')),
-            dfxp.ReLU_q(),
+            dfxp.BatchNorm2d_q(b, 16, relu=True, **self._kw(name='conv1-bn')),      # + ReLU_q (models.py:414)
         ] + self._build_blocks(16, self.num_blocks[0], 1) \
           + self._build_blocks(32, self.num_blocks[1], 2) \
           + self._build_blocks(64, self.num_blocks[2], 2) + [
@@ -137,8 +136,7 @@ class ImageNet_Resnet(Model):
         final = -(-self.image // 32)
         layers = [
             dfxp.Conv2d_q(b, 3, 64, 7, 2, 'SAME', bias=False, **self._kw(name='conv1', input_signed=True)),
-            dfxp.BatchNorm2d_q(b, 64, **self._kw(name='conv1-bn')),
-            dfxp.ReLU_q(),
+            dfxp.BatchNorm2d_q(b, 64, relu=True, **self._kw(name='conv1-bn')),
             dfxp.MaxPool_q(3, 2, 'SAME'),
         ]
         for ch, n, s in zip((64, 128, 256, 512), self.num_blocks, (1, 2, 2, 2)):

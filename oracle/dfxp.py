@@ -77,8 +77,13 @@ class PhiloxNoise:
 class Context:
     """Per-model bookkeeping the TF graph did implicitly: quantiser ids, noise source, step count."""
 
-    def __init__(self, noise=None):
+    def __init__(self, noise=None, exact=False):
         self.noise = noise if noise is not None else NumpyNoise(0)
+        # exact=False: fp32 accumulation everywhere, like the reference's cuDNN/cuBLAS/Eigen kernels.
+        # exact=True : conv/matmul/batch-moment accumulations are carried out in fp64 (exact for DFXP
+        #   mantissa products) and rounded ONCE to fp32 — the arithmetic of the integer tensor-core
+        #   path, which must then match bit for bit.
+        self.exact = exact
         self.n_quant = 0
         self.last_counts = {}       # qid -> (n_over, n_over_half, numel) of the latest call
 
@@ -345,7 +350,10 @@ class Conv2d_q(Layer_q):
         self.X = _leaf(X)
         self.Xq = self.qX(self.X)
         self.Wq = self.qW(self.W)
-        self.y = tf_conv2d(self.Xq, self.Wq, self.strides, self.padding)         # dfxp:291
+        if self.qX.ctx.exact:   # exactly-rounded accumulation (see Context)
+            self.y = tf_conv2d(self.Xq.double(), self.Wq.double(), self.strides, self.padding).float()
+        else:
+            self.y = tf_conv2d(self.Xq, self.Wq, self.strides, self.padding)     # dfxp:291
         if self.use_bias:
             self.bq = self.qb(self.b)
             self.y = self.y + self.bq                                             # dfxp:296
@@ -398,7 +406,10 @@ class Dense_q(Layer_q):
         self.X = _leaf(X)
         self.Xq = self.qX(self.X)
         self.Wq = self.qW(self.W)
-        self.y = self.Xq @ self.Wq                                                # dfxp:388
+        if self.qX.ctx.exact:
+            self.y = (self.Xq.double() @ self.Wq.double()).float()
+        else:
+            self.y = self.Xq @ self.Wq                                            # dfxp:388
         if self.use_bias:
             self.bq = self.qb(self.b)
             self.y = self.y + self.bq
@@ -476,8 +487,13 @@ class Normalization_q(Layer_q):
         self.X = _leaf(X)
         self.Xq = self.qX(self.X)
         axes = list(range(self.Xq.dim() - 1))
-        mean_b = self.Xq.mean(dim=axes)                                           # dfxp:588
-        var_b = ((self.Xq - mean_b) ** 2).mean(dim=axes)
+        if self.qX.ctx.exact:
+            x64 = self.Xq.double()
+            m64 = x64.mean(dim=axes)
+            mean_b, var_b = m64.float(), ((x64 - m64) ** 2).mean(dim=axes).float()
+        else:
+            mean_b = self.Xq.mean(dim=axes)                                       # dfxp:588
+            var_b = ((self.Xq - mean_b) ** 2).mean(dim=axes)
         if self.train:
             mean, var = mean_b, var_b
             with torch.no_grad():                                                 # dfxp:602-612
@@ -553,7 +569,10 @@ class ReLU_q(Layer_q):
 
     def forward(self, X):
         self.X = _leaf(X)
-        self.y = torch.clamp_min(self.X, 0.0)
+        # tf.maximum(0.0, X): TF's _MaximumGrad sends the gradient to X only where NOT (0.0 >= X), i.e.
+        # strictly X > 0 (at X == 0 it goes to the constant).  torch.relu has exactly that backward;
+        # torch.clamp_min would pass the gradient at X == 0, which quantised activations hit often.
+        self.y = torch.relu(self.X)
         return self.y.detach()
 
 
@@ -698,9 +717,9 @@ class ResidualBottleneck_q(ResidualBlock_q):
 class Model:
     """models.py:7-54: forward chain, mean sparse-softmax-xent loss, manual reverse chain."""
 
-    def __init__(self, bits, dropout=0.5, weight_decay=0.0, noise=None, seed=0, grad_bits=None):
+    def __init__(self, bits, dropout=0.5, weight_decay=0.0, noise=None, seed=0, grad_bits=None, exact=False):
         self.bits, self.dropout, self.weight_decay, self.grad_bits = bits, dropout, weight_decay, grad_bits
-        self.ctx = Context(noise)
+        self.ctx = Context(noise, exact=exact)
         self.rng = np.random.default_rng(seed)
         self.layers = self.get_layers()
         self.velocity = None
