@@ -161,6 +161,20 @@ int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W, int C, int
                   int sh, int sw, int pad_top, int pad_left, int transposed, void* out, size_t ld,
                   void* stream);
 
+/*
+ * Implicit-GEMM convolution on mantissas (no im2col matrix in HBM): TMA im2col-mode loads of the NHWC
+ * source + tcgen05.mma.kind::i8.  Replaces tf.nn.conv2d (dynamic_fixed_point.py:196, 291); run on the
+ * output-gradient map with the 180-degree-rotated filter it is tf.gradients(y, X, gradq) of a stride-1
+ * convolution (:210, :305).
+ *   src[N,H,W,C] s8|u8, C in {16, 32, 64} or a multiple of 128;  wp[Cout, kh*kw*C] packed K-major
+ *   (k = (r*kw + s)*C + c, row pitch ldw bytes);  out[N*OH*OW, Cout] fp32 (row pitch ldc floats):
+ *   out = fp32(acc) * 2^(exp_const + *ib_src + *ib_w) (+ bias[co]).  kh*kw*C <= 65536.
+ */
+int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind,
+                      size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
+                      int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
+                      float* out, size_t ldc, void* stream);
+
 /* out[c*ld_out + r] = in[r*ld_in + c] for an R x C byte matrix (operand re-majoring for wgrad). */
 int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in, void* out, size_t ld_out,
                      void* stream);

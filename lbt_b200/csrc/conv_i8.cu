@@ -1,0 +1,393 @@
+// Implicit-GEMM convolution on DFXP integer mantissas for B200 (sm_100a): no im2col matrix ever touches HBM.
+//
+//   out[m, n] = 2^e * sum_{tap=(r,s)} sum_c src[pixel(m) + tap, c] * Wp[n, tap*C + c]   (+ bias[n])
+//
+// A operand: TMA *im2col mode* over the NHWC mantissa tensor (C, W, H, N): one bulk load fetches, for 128
+// consecutive output pixels (wrapping rows and images in hardware, zero-filling TF 'SAME' padding) and one
+// filter tap, a [128 x Cb] block of channels straight into shared memory in the tensor core's K-major layout.
+// B operand: 2-D tiled TMA over the packed weights Wp[N, taps*C] (K-major).  tcgen05.mma.kind::i8 accumulates
+// exactly in s32 in tensor memory; the epilogue applies the power-of-two rescale read from the range variables.
+//
+// Replaces tf.nn.conv2d (dynamic_fixed_point.py:291) and, run on the output-gradient map with the filter
+// rotated by 180 degrees, tf.gradients(y, X, gradq) for stride-1 convolutions (dynamic_fixed_point.py:305).
+//
+// Channel chunk Cb = min(C, 128) in {16, 32, 64, 128} selects the shared-memory layout: 16-byte rows of
+// interleaved 8x16B core matrices, or 32/64/128-byte swizzled rows; a pipeline stage always carries 128 bytes
+// of K per row (128/Cb tap-blocks), i.e. four K=32 MMAs.  Same warp roles and mbarrier protocol as gemm_i8.cu.
+#include "tcgen05.cuh"
+
+namespace lbt {
+namespace {
+
+using namespace tc;
+
+constexpr int kBlockM = 128;
+constexpr int kStageK = 128;  // bytes of K per row per stage
+constexpr int kThreads = 192;
+
+__device__ int g_conv_error = 0;
+
+struct ConvParams {
+  uint32_t M, N;                 // output pixels, output channels
+  uint32_t OW, OHW;              // output width, OH*OW
+  int lower_w, lower_h;          // base-pixel offset of output (0,0): -pad_left, -pad_top
+  int sw, sh;
+  uint32_t kw;                   // filter width (tap -> (r, s))
+  uint32_t taps, cchunks;        // kh*kw, C / Cb
+  uint32_t ksteps;               // taps * cchunks (+1 padding step when Cb == 16 and odd)
+  uint32_t ksteps_real;
+  uint32_t cb;                   // channel chunk bytes
+  uint32_t mode;                 // log2(cb / 16)
+  uint32_t C;                    // source channels
+  uint32_t m_tiles, n_tiles;
+  const int32_t* ibA;
+  const int32_t* ibB;
+  int exp_const;
+  const float* bias;
+  float* out;
+  size_t ldc;
+  uint32_t idesc;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageA = kBlockM * kStageK;
+  static constexpr int kStageB = BN * kStageK;
+  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    s_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  volatile int* abort_flag = &s_abort;
+
+  const uint32_t total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t spb = kStageK / p.cb;                       // tap-blocks per stage
+  const uint32_t a_block = kBlockM * p.cb, b_block = BN * p.cb;
+  const uint32_t nstages_k = (p.ksteps + spb - 1) / spb;     // pipeline stages per tile
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        const uint32_t m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+        const uint32_t m0 = m_tile * kBlockM;
+        const uint32_t img = m0 / p.OHW, rem = m0 % p.OHW;
+        const int oh = (int)(rem / p.OW), ow = (int)(rem % p.OW);
+        const int base_w = p.lower_w + ow * p.sw, base_h = p.lower_h + oh * p.sh;
+        for (uint32_t ks = 0; ks < nstages_k; ++ks) {
+          if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_conv_error))) break;
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kStageA;
+          const uint32_t k0 = ks * spb;
+          const uint32_t nblk = min(spb, p.ksteps - k0);
+          mbar_expect_tx(&full_bar[stage], nblk * (a_block + b_block));
+          for (uint32_t j = 0; j < nblk; ++j) {
+            uint32_t kstep = k0 + j;
+            const bool pad = kstep >= p.ksteps_real;        // Cb == 16 pairing pad: B is OOB-zero, A is any tap
+            const uint32_t ka = pad ? 0u : kstep;
+            const uint32_t tap = ka / p.cchunks, cc = ka % p.cchunks;
+            const uint32_t r = tap / p.kw, s = tap % p.kw;
+            tma_load_im2col_4d(&tmA, &full_bar[stage], sa + j * a_block, (int)(cc * p.cb), base_w, base_h, (int)img,
+                               (uint16_t)s, (uint16_t)r);
+            tma_load_2d(&tmB, &full_bar[stage], sb + j * b_block, (int)(kstep * p.cb), (int)(n_tile * BN));
+          }
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+        if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag, &g_conv_error))) break;
+        fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t first = 1;
+        for (uint32_t ks = 0; ks < nstages_k; ++ks) {
+          if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_conv_error))) break;
+          fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kStageA;
+          const uint32_t nblk = min(spb, p.ksteps - ks * spb);
+          if (p.mode == 0) {
+            // 16-byte rows: one K=32 instruction spans two consecutive tap-blocks (leading byte offset = block size)
+            for (uint32_t j = 0; j < nblk; j += 2) {  // nblk is even: ksteps is padded to an even count
+              umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block, 0, a_block), make_desc_kmajor(sb + j * b_block, 0, b_block),
+                      p.idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          } else {
+            const uint32_t per_block = p.cb / 32;
+            for (uint32_t j = 0; j < nblk; ++j)
+              for (uint32_t kk = 0; kk < per_block; ++kk) {
+                umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block + kk * 32, (int)p.mode, 16),
+                        make_desc_kmajor(sb + j * b_block + kk * 32, (int)p.mode, 16), p.idesc, first ? 0u : 1u);
+                first = 0;
+              }
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (!ok) break;
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const uint32_t quad = warp & 3;
+    int e = p.exp_const;
+    if (p.ibA) e += *p.ibA;
+    if (p.ibB) e += *p.ibB;
+    const float scale = exp2i(e);
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
+      const uint32_t m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_conv_error);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      fence_after();
+      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
+      const uint32_t col0 = n_tile * BN;
+      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (row < p.M && col0 + c < p.N) {
+          const uint32_t ncol = min(16u, p.N - (col0 + c));
+          float* o = p.out + (size_t)row * p.ldc + col0 + c;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __int2float_rn((int)v[j]) * scale;
+            if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+          }
+          if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < (int)ncol) o[j] = f[j];
+          }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---- host ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void* driver_fn(const char* name) {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return f;
+}
+
+CUtensorMapSwizzle swizzle_of(uint32_t mode) {
+  switch (mode) {
+    case 0: return CU_TENSOR_MAP_SWIZZLE_NONE;
+    case 1: return CU_TENSOR_MAP_SWIZZLE_32B;
+    case 2: return CU_TENSOR_MAP_SWIZZLE_64B;
+    default: return CU_TENSOR_MAP_SWIZZLE_128B;
+  }
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, unsigned grid, cudaStream_t st) {
+  static bool attr_done[16] = {};
+  const int dev = device_info().device;
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(conv_fprop_kernel)");
+      return LBT_ECUDA;
+    }
+    attr_done[dev] = true;
+  }
+  conv_fprop_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  return check_launch("lbt_conv_i8_fprop");
+}
+
+}  // namespace
+}  // namespace lbt
+
+using namespace lbt;
+
+extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind,
+                                 size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
+                                 int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
+                                 float* out, size_t ldc, void* stream) {
+  if (!src || !wp || !out) return LBT_EINVAL;
+  if ((src_kind != LBT_MANT_S8 && src_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
+    return LBT_EINVAL;
+  if (C % 16) return LBT_EUNSUPPORTED;
+  const uint32_t cb = C >= 128 ? 128u : (uint32_t)C;
+  if (cb != 16 && cb != 32 && cb != 64 && cb != 128) return LBT_EUNSUPPORTED;
+  if (C % cb) return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15) || (ldw & 15)) return LBT_EUNSUPPORTED;
+  if (ldc < (size_t)Cout) return LBT_EINVAL;
+  const size_t Ktot = (size_t)kh * kw * C;
+  if (ldw < Ktot) return LBT_EINVAL;
+  if (Ktot > 65536) return LBT_EUNSUPPORTED;  // exactness bound of one s32 accumulator
+  if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+  static EncodeTiledFn enc_tiled = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
+  static EncodeIm2colFn enc_im2col = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));
+  if (!enc_tiled || !enc_im2col) return LBT_ECUDA;
+
+  int bn = 256;
+  for (int c : {16, 32, 64, 128, 256})
+    if (c >= Cout) {
+      bn = c;
+      break;
+    }
+  uint32_t mode = 0;
+  while ((16u << mode) < cb) ++mode;
+
+  ConvParams p{};
+  p.M = (uint32_t)((size_t)N * OH * OW);
+  p.N = (uint32_t)Cout;
+  p.OW = (uint32_t)OW;
+  p.OHW = (uint32_t)(OH * OW);
+  p.lower_w = -pad_left;
+  p.lower_h = -pad_top;
+  p.sw = sw;
+  p.sh = sh;
+  p.kw = (uint32_t)kw;
+  p.taps = (uint32_t)(kh * kw);
+  p.cchunks = (uint32_t)C / cb;
+  p.ksteps_real = p.taps * p.cchunks;
+  p.ksteps = p.ksteps_real + ((cb == 16 && (p.ksteps_real & 1)) ? 1 : 0);
+  p.cb = cb;
+  p.mode = mode;
+  p.C = (uint32_t)C;
+  p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  p.n_tiles = ((uint32_t)Cout + bn - 1) / bn;
+  p.ibA = ib_src;
+  p.ibB = ib_w;
+  p.exp_const = exp_const;
+  p.bias = bias;
+  p.out = out;
+  p.ldc = ldc;
+  p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
+
+  // A: im2col map over (C, W, H, N).  The bounding box of base pixels is [lower, dim + upper): with
+  // lower = -pad_before and upper = pad_after - (k - 1) it has exactly (out - 1) * stride + 1 positions.
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
+    // pad_after chosen so that the last output pixel's base position is inside the box
+    const int upper_w = (OW - 1) * sw + 1 - W - pad_left;
+    const int upper_h = (OH - 1) * sh + 1 - H - pad_top;
+    int lower[2] = {-pad_left, -pad_top};
+    int upper[2] = {upper_w, upper_h};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    CUresult r = enc_im2col(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(src), gdim, gstr, lower, upper, cb, kBlockM,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeIm2col");
+      return LBT_ECUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldw};
+    cuuint32_t box[2] = {cb, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc_tiled(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(wp), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(weights)");
+      return LBT_ECUDA;
+    }
+  }
+  const uint64_t tiles = (uint64_t)p.m_tiles * p.n_tiles;
+  const unsigned grid = (unsigned)(tiles < (uint64_t)di.sm_count ? tiles : (uint64_t)di.sm_count);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 16: return launch<16>(ta, tb, p, grid, st);
+    case 32: return launch<32>(ta, tb, p, grid, st);
+    case 64: return launch<64>(ta, tb, p, grid, st);
+    case 128: return launch<128>(ta, tb, p, grid, st);
+    default: return launch<256>(ta, tb, p, grid, st);
+  }
+}
+
+extern "C" int lbt_conv_debug_error(void) {
+  int v = 0, zero = 0;
+  if (cudaMemcpyFromSymbol(&v, g_conv_error, sizeof(int)) != cudaSuccess) return -1;
+  cudaMemcpyToSymbol(g_conv_error, &zero, sizeof(int));
+  return v;
+}

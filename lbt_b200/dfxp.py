@@ -199,6 +199,19 @@ def _colsum(mant2d, kind):
     return acc
 
 
+def _implicit_ok(C, kh, kw):
+    """Shapes the implicit-GEMM kernel takes: C in {16,32,64} or a multiple of 128; kh*kw*C <= 65536."""
+    return (C in (16, 32, 64) or (C >= 128 and C % 128 == 0)) and kh * kw * C <= 65536 and kh <= 255 and kw <= 255
+
+
+def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d):
+    """lbt_conv_i8_fprop: out2d[N*OH*OW, Cout] = conv(src, wp) * 2^(exp_const + ib_src + ib_w) (+ bias)."""
+    N, H, W, C = src_nhwc.shape
+    _lib.call('lbt_conv_i8_fprop', _lib.ptr(src_nhwc), src_kind, N, H, W, C, _lib.ptr(wp), Q.MANT_S8, wp.stride(0), Cout,
+              kh, kw, sh, sw, pt, pl, OH, OW, _lib.ptr(ib_src), _lib.ptr(ib_w), int(exp_const), _lib.ptr(bias),
+              _lib.ptr(out2d), out2d.stride(0), _lib.stream(), meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C))
+
+
 # ------------------------------------------------------------------------------------------------
 # Conv2d_q
 # ------------------------------------------------------------------------------------------------
@@ -242,16 +255,20 @@ class _QConv2dFn(torch.autograd.Function):
         wt = _transpose_bytes(wm.view(Kf, Cout))
         if segs == 3:
             wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
-        if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
-            A = xm.reshape(N * H * W, Cin)                                                     # 1x1: no gather
-        else:
-            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
         bq = None
         if bias is not None:
             bq, _ = layer.qb.quantize(bias)                                                    # dfxp:294
         y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
-        G.gemm_i8(A, wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=-(xb - 1) - (layer.qW.bits - 1),
-                  bias=bq, out=y.view(N * OH * OW, Cout))                                      # dfxp:291, 296
+        e = -(xb - 1) - (layer.qW.bits - 1)
+        if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
+            G.gemm_i8(xm.reshape(N * H * W, Cin), wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=e, bias=bq,
+                      out=y.view(N * OH * OW, Cout))                                           # 1x1: plain GEMM
+        elif layer.implicit and segs == 1 and _implicit_ok(Cin, kh, kw):
+            _conv_implicit(xm, xkind, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, layer.qX.range, layer.qW.range, e, bq,
+                           y.view(N * OH * OW, Cout))                                          # dfxp:291, 296
+        else:
+            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+            G.gemm_i8(A, wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=e, bias=bq, out=y.view(N * OH * OW, Cout))
         ctx.layer = layer
         ctx.geom = (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind)
         ctx.save_for_backward(xm, wm, weight)
@@ -290,14 +307,20 @@ class _QConv2dFn(torch.autograd.Function):
         # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
         if ctx.needs_input_grad[0]:
             K2 = kh * kw * Cout
-            w2 = _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
-            if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
-                A2 = g2
-            else:
-                A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
             dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dy.device)
-            G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=-(gb - 1) - (wb - 1),
-                      out=dx.view(N * H * W, Cin))                                             # dfxp:305
+            e = -(gb - 1) - (wb - 1)
+            if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
+                w2 = _as_operand(wm.view(Cin, Cout))
+                G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+            elif layer.implicit and sh == 1 and sw == 1 and _implicit_ok(Cout, kh, kw):
+                # stride 1: dX = conv(G, rot180(W)) with padding (k - 1 - pad): the same implicit-GEMM kernel
+                w2 = _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
+                _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
+                               layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
+            else:
+                w2 = _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+                A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
+                G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
             dX = dx.permute(0, 3, 1, 2)
         return dX, dW, db, None
 
@@ -311,7 +334,7 @@ class Conv2d_q(nn.Module):
 
     def __init__(self, bits, in_channels, out_channels, kernel_size, stride=1, padding='SAME', bias=True, *,
                  weight_decay=0.0, target_overflow_rate=0.0, input_range=2, weight_range=2, bias_range=2, grad_range=2,
-                 grad_bits=None, input_signed=True, name='conv', runtime=None):
+                 grad_bits=None, input_signed=True, name='conv', runtime=None, implicit=True):
         super().__init__()
         rt = runtime or default_runtime()
         kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
@@ -322,6 +345,7 @@ class Conv2d_q(nn.Module):
         else:
             self.padding, self.pad_int = 'INT', int(padding)
         self.bits, self.weight_decay, self.input_signed, self.name = bits, float(weight_decay), input_signed, name
+        self.implicit = implicit    # implicit-GEMM kernels where the shape allows; False = explicit im2col + GEMM
         limit = (3 / (kh * kw * in_channels)) ** 0.5                                           # dfxp:247-254
         self.weight = nn.Parameter(torch.empty(kh, kw, in_channels, out_channels).uniform_(-limit, limit))
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None                  # dfxp:264

@@ -43,6 +43,17 @@ CONV_CASES = [
     (3, 64, 7, 2, 17, 2, False, True),
     (24, 40, 3, 2, 7, 3, True, False),       # Cin not a multiple of 16 -> scalar gather path
     (16, 16, 3, 1, 5, 2, False, True),       # signed 9-bit on a 16-channel input (hi|hi|lo split)
+    # implicit-GEMM shared-memory layouts: 16B interleaved / 32B / 64B / 128B swizzle, 1 and 2 channel chunks
+    (16, 16, 5, 1, 9, 2, False, False),      # 25 taps (odd -> zero pad step)
+    (16, 48, 3, 1, 33, 5, True, False),      # M = 5445 (ragged last tile), N = 48
+    (32, 32, 3, 1, 8, 4, False, False),
+    (32, 64, 3, 2, 9, 3, False, False),
+    (64, 64, 3, 1, 6, 2, False, False),
+    (64, 128, 3, 2, 9, 2, False, False),
+    (128, 128, 3, 1, 5, 2, False, False),
+    (256, 128, 3, 1, 4, 2, False, False),
+    (128, 256, 3, 2, 7, 3, False, False),
+    (256, 512, 3, 1, 4, 3, False, False),    # two N tiles
 ]
 
 
