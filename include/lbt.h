@@ -175,6 +175,18 @@ int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C,
                       int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
                       float* out, size_t ldc, void* stream);
 
+/*
+ * Implicit-GEMM weight gradient: acc64[(r*kw+s)*C + c, co] += alpha * sum over output pixels m of
+ * src[pixel(m) + (r,s), c] * g[m, co] — tf.gradients(y, W, gradq) (dynamic_fixed_point.py:207, 302) in HWIO
+ * order, exact.  Both operands are consumed MN-major straight from TMA loads (no transposes); the pixel
+ * dimension is split over the SMs (k_splits, 0 = auto; each CTA sums <= 65536 pixels in s32) and reduced
+ * with 64-bit atomics.  src[N,H,W,C] and g[N*OH*OW, Cout] are s8|u8 with C, Cout in {16,32,64} or
+ * multiples of 128.  Caller zeroes acc64[kh*kw*C, Cout]; finish with lbt_acc64_finalize.
+ */
+int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout,
+                      int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
+                      int alpha, int k_splits, void* stream);
+
 /* out[c*ld_out + r] = in[r*ld_in + c] for an R x C byte matrix (operand re-majoring for wgrad). */
 int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in, void* out, size_t ld_out,
                      void* stream);

@@ -235,6 +235,184 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad: dW[(r,s,c), co] = sum over output pixels m of  X[pixel(m) + (r,s), c] * G[m, co]
+// The reduction runs over PIXELS, so both operands are MN-major: the very same "128 pixels x Cb channels"
+// blocks the TMA produces are the tensor core's K x M (K x N) atoms — no transposes, no im2col matrix.
+// M tile = 128 consecutive (tap, channel) rows = 128/Cb tap-blocks; one pipeline stage = one block of 128
+// pixels (four K=32 MMAs).  Pixel blocks are split across CTAs; partial sums go to the int64 buffer with
+// 64-bit atomics (exact, order-independent).
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  uint32_t Mpix, N;              // output pixels (reduction length), output channels
+  uint32_t OW, OHW;
+  int lower_w, lower_h, sw, sh;
+  uint32_t kw, cchunks, ksteps;  // filter width, C / Cb, taps * cchunks
+  uint32_t cb, mode_a;           // channel chunk bytes of X, log2(cb/16)
+  uint32_t cbn, mode_b, nchunks; // channel chunk bytes of G, log2(cbn/16), BN / cbn
+  uint32_t m_tiles, n_tiles;     // over (tap, channel) rows / output channels
+  uint32_t pix_blocks, blocks_per_split, k_splits;
+  uint32_t Kf;                   // taps * C
+  long long* acc64;
+  int alpha;
+  uint32_t idesc;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    s_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmG);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  volatile int* abort_flag = &s_abort;
+
+  const uint32_t total_items = p.m_tiles * p.n_tiles * p.k_splits;
+  const uint32_t spb = kStageK / p.cb;                 // tap-blocks per M tile
+  const uint32_t a_block = kBlockM * p.cb;             // 128 pixels x cb
+  const uint32_t b_block = kBlockM * p.cbn;            // 128 pixels x cbn
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+        const uint32_t m_tile = item % p.m_tiles, rest = item / p.m_tiles;
+        const uint32_t n_tile = rest % p.n_tiles, ks = rest / p.n_tiles;
+        const uint32_t pb0 = ks * p.blocks_per_split, pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
+        const uint32_t k0 = m_tile * spb;
+        const uint32_t nblk = min(spb, p.ksteps - k0);
+        for (uint32_t pb = pb0; pb < pb1; ++pb) {
+          if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_conv_error))) break;
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kStageA;
+          const uint32_t m0 = pb * kBlockM;
+          const uint32_t img = m0 / p.OHW, rem = m0 % p.OHW;
+          const int oh = (int)(rem / p.OW), ow = (int)(rem % p.OW);
+          const int base_w = p.lower_w + ow * p.sw, base_h = p.lower_h + oh * p.sh;
+          mbar_expect_tx(&full_bar[stage], nblk * a_block + p.nchunks * b_block);
+          for (uint32_t j = 0; j < nblk; ++j) {
+            const uint32_t kstep = k0 + j;
+            const uint32_t tap = kstep / p.cchunks, cc = kstep % p.cchunks;
+            tma_load_im2col_4d(&tmX, &full_bar[stage], sa + j * a_block, (int)(cc * p.cb), base_w, base_h, (int)img,
+                               (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
+          }
+          for (uint32_t j = 0; j < p.nchunks; ++j)
+            tma_load_2d(&tmG, &full_bar[stage], sb + j * b_block, (int)(n_tile * BN + j * p.cbn), (int)m0);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+        const uint32_t ks = (item / p.m_tiles) / p.n_tiles;
+        const uint32_t pb0 = ks * p.blocks_per_split, pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
+        if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag, &g_conv_error))) break;
+        fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (uint32_t pb = pb0; pb < pb1; ++pb) {
+          if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_conv_error))) break;
+          fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kStageA;
+#pragma unroll
+          for (uint32_t kk = 0; kk < kBlockM / 32; ++kk) {
+            // 32 pixels (K) per instruction: advance by 32 rows of the block
+            umma_i8(d_tmem, make_desc_mnmajor(sa + kk * 32 * p.cb, (int)p.mode_a, a_block),
+                    make_desc_mnmajor(sb + kk * 32 * p.cbn, (int)p.mode_b, b_block), p.idesc, (pb > pb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (!ok) break;
+        umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const uint32_t quad = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
+      const uint32_t m_tile = item % p.m_tiles, rest = item / p.m_tiles;
+      const uint32_t n_tile = rest % p.n_tiles;
+      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_conv_error);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      fence_after();
+      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;   // (tap, channel) index kf
+      const uint32_t col0 = n_tile * BN;
+      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (row < p.Kf && col0 + c < p.N) {
+          const uint32_t ncol = min(16u, p.N - (col0 + c));
+          unsigned long long* o = reinterpret_cast<unsigned long long*>(p.acc64) + (size_t)row * p.N + col0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < (int)ncol) {
+              const long long a = (long long)(int)v[j] * (long long)p.alpha;
+              if (a != 0) atomicAdd(o + j, (unsigned long long)a);
+            }
+        }
+      }
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
 // ---- host ------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -382,6 +560,127 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
     case 64: return launch<64>(ta, tb, p, grid, st);
     case 128: return launch<128>(ta, tb, p, grid, st);
     default: return launch<256>(ta, tb, p, grid, st);
+  }
+}
+
+namespace lbt {
+namespace {
+template <int BN>
+int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tg, const WgradParams& p, unsigned grid, cudaStream_t st) {
+  static bool attr_done[16] = {};
+  const int dev = device_info().device;
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_kernel)");
+      return LBT_ECUDA;
+    }
+    attr_done[dev] = true;
+  }
+  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(tx, tg, p);
+  return check_launch("lbt_conv_i8_wgrad");
+}
+}  // namespace
+}  // namespace lbt
+
+extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout,
+                                 int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
+                                 int alpha, int k_splits, void* stream) {
+  if (!src || !g || !acc64) return LBT_EINVAL;
+  if ((src_kind != LBT_MANT_S8 && src_kind != LBT_MANT_U8) || (g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8)) return LBT_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
+    return LBT_EINVAL;
+  const uint32_t cb = C >= 128 ? 128u : (uint32_t)C;
+  const uint32_t cbn = Cout >= 128 ? 128u : (uint32_t)Cout;
+  if ((cb != 16 && cb != 32 && cb != 64 && cb != 128) || (C % cb)) return LBT_EUNSUPPORTED;
+  if ((cbn != 16 && cbn != 32 && cbn != 64 && cbn != 128) || (Cout % cbn)) return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return LBT_EUNSUPPORTED;
+  if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+  static EncodeTiledFn enc_tiled = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
+  static EncodeIm2colFn enc_im2col = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));
+  if (!enc_tiled || !enc_im2col) return LBT_ECUDA;
+
+  int bn = Cout >= 256 ? 256 : Cout;  // 16, 32, 64, 128 or 256 (Cout is a multiple of cbn)
+  if (Cout > 128 && Cout % 256) bn = 128;
+  uint32_t mode_a = 0, mode_b = 0;
+  while ((16u << mode_a) < cb) ++mode_a;
+  while ((16u << mode_b) < cbn) ++mode_b;
+
+  WgradParams p{};
+  p.Mpix = (uint32_t)((size_t)N * OH * OW);
+  p.N = (uint32_t)Cout;
+  p.OW = (uint32_t)OW;
+  p.OHW = (uint32_t)(OH * OW);
+  p.lower_w = -pad_left;
+  p.lower_h = -pad_top;
+  p.sw = sw;
+  p.sh = sh;
+  p.kw = (uint32_t)kw;
+  p.cchunks = (uint32_t)C / cb;
+  p.ksteps = (uint32_t)(kh * kw) * p.cchunks;
+  p.cb = cb;
+  p.mode_a = mode_a;
+  p.cbn = cbn;
+  p.mode_b = mode_b;
+  p.nchunks = (uint32_t)bn / cbn;
+  const uint32_t spb = kStageK / cb;
+  p.m_tiles = (p.ksteps + spb - 1) / spb;
+  p.n_tiles = ((uint32_t)Cout + bn - 1) / bn;
+  p.pix_blocks = (p.Mpix + kBlockM - 1) / kBlockM;
+  uint32_t splits = k_splits > 0 ? (uint32_t)k_splits : 0;
+  if (!splits) {
+    const uint32_t tiles = p.m_tiles * p.n_tiles;
+    splits = (uint32_t)di.sm_count / (tiles ? tiles : 1);
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.pix_blocks) splits = p.pix_blocks;
+  p.blocks_per_split = (p.pix_blocks + splits - 1) / splits;
+  if (p.blocks_per_split > 65536 / kBlockM) p.blocks_per_split = 65536 / kBlockM;  // s32 exactness bound per CTA
+  p.k_splits = (p.pix_blocks + p.blocks_per_split - 1) / p.blocks_per_split;
+  p.Kf = (uint32_t)(kh * kw * C);
+  p.acc64 = reinterpret_cast<long long*>(acc64);
+  p.alpha = alpha;
+  p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, g_kind == LBT_MANT_S8, true, true, bn, kBlockM);
+
+  CUtensorMap tx, tg;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
+    int lower[2] = {-pad_left, -pad_top};
+    int upper[2] = {(OW - 1) * sw + 1 - W - pad_left, (OH - 1) * sh + 1 - H - pad_top};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    CUresult r = enc_im2col(&tx, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(src), gdim, gstr, lower, upper, cb, kBlockM,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode_a), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeIm2col(wgrad)");
+      return LBT_ECUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)Cout, (cuuint64_t)p.Mpix};
+    cuuint64_t gstr[1] = {(cuuint64_t)Cout};
+    cuuint32_t box[2] = {cbn, (cuuint32_t)kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc_tiled(&tg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(g), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode_b), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(grad)");
+      return LBT_ECUDA;
+    }
+  }
+  const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
+  const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (bn) {
+    case 16: return launch_wgrad<16>(tx, tg, p, grid, st);
+    case 32: return launch_wgrad<32>(tx, tg, p, grid, st);
+    case 64: return launch_wgrad<64>(tx, tg, p, grid, st);
+    case 128: return launch_wgrad<128>(tx, tg, p, grid, st);
+    default: return launch_wgrad<256>(tx, tg, p, grid, st);
   }
 }
 

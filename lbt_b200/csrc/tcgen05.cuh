@@ -129,6 +129,17 @@ __device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr, int m, 
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
          (desc_layout_bits(m) << 61);
 }
+// MN-major operand: shared memory holds [K rows][16 << m bytes of M (or N)] blocks — exactly what a TMA load of
+// "pixels x channels" produces — and the reduction runs down the rows.  An 8-row K atom is (128 << m) bytes;
+// `group_stride` is the byte distance between consecutive (16 << m)-wide groups along M/N (the next block).
+//   m == 0: SBO = MN-group stride, LBO = K-atom stride;  swizzled: LBO = MN-group stride, SBO = K-atom stride.
+__device__ __forceinline__ uint64_t make_desc_mnmajor(uint32_t smem_addr, int m, uint32_t group_stride) {
+  const uint32_t katom = 128u << m;
+  const uint32_t lbo = m == 0 ? katom : group_stride;
+  const uint32_t sbo = m == 0 ? group_stride : katom;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46) | (desc_layout_bits(m) << 61);
+}
 // 128-byte-swizzled K-major tile (rows of 128 B): the plain GEMM operand.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) { return make_desc_kmajor(smem_addr, 3, 16); }
 

@@ -290,11 +290,20 @@ class _QConv2dFn(torch.autograd.Function):
         dW = db = dX = None
         # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
         if ctx.needs_input_grad[1]:
-            gt = _transpose_bytes(g2)                                                           # [Cout, M]
-            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
-            at = _transpose_bytes(A)                                                            # [Kf*segs, M]
             acc = torch.zeros(Kf, Cout, dtype=torch.int64, device=dy.device)
-            if xkind == Q.MANT_S16:
+            if layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
+                # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
+                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                          sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(),
+                          meta=dict(ops=2 * M * Cout * Kf))
+                gt = at = None
+            else:
+                gt = _transpose_bytes(g2)                                                       # [Cout, M]
+                A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+                at = _transpose_bytes(A)                                                        # [Kf*segs, M]
+            if at is None:
+                pass
+            elif xkind == Q.MANT_S16:
                 G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
                 G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
             else:
