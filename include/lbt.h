@@ -48,7 +48,11 @@ enum lbt_mant_kind {
   LBT_MANT_NONE = 0,
   LBT_MANT_S8 = 1,  /* bits <= 8 */
   LBT_MANT_U8 = 2,  /* bits <= 9 and input known non-negative (post-ReLU conv activations, F7) */
-  LBT_MANT_S16 = 3  /* bits <= 16 */
+  LBT_MANT_S16 = 3, /* bits <= 16 */
+  /* 3-channel signed 9-bit input (the image fed to a first Conv2d_q, bits+1 = 9): every pixel becomes 16
+   * s8 bytes {hi0,hi1,hi2, hi0,hi1,hi2, lo0,lo1,lo2, 0 x 7} with k = 2*hi + lo, i.e. a 16-channel s8 NHWC
+   * tensor the implicit-GEMM kernels consume against weights packed {W, W, W, 0}.  n_inner % 3 == 0. */
+  LBT_MANT_S9C3 = 4
 };
 
 /* Per-quantiser overflow statistics block: uint64_t[4] on the device. */

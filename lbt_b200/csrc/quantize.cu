@@ -203,6 +203,46 @@ __global__ void __launch_bounds__(kThreads) quantize_scalar_kernel(const QParams
   finish_stats(n1, n2, p, ib);
 }
 
+// 3-channel input (an image): one thread per pixel, output 16 s8 bytes {hi x3, hi x3, lo x3, 0 x7} (LBT_MANT_S9C3).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) quantize_c3_kernel(const QParams p) {
+  const int ib = *reinterpret_cast<volatile const int32_t*>(p.ib);
+  const QConst c = make_const(p.bits, ib);
+  uint64_t off = p.offset;
+  if (MODE == LBT_ROUND_STOCHASTIC_PHILOX && p.dev_step) off += (*p.dev_step) << 32;
+  uint32_t n1 = 0, n2 = 0;
+  const size_t ppr = p.n_inner / 3, npix = p.n_outer * ppr;
+  for (size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * kThreads) {
+    const size_t row = pix / ppr, j0 = (pix % ppr) * 3;
+    int k[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const size_t col = j0 + ch;
+      float u = 0.f;
+      if (MODE == LBT_ROUND_STOCHASTIC_NOISE) u = __ldg(p.noise + col);
+      if (MODE == LBT_ROUND_STOCHASTIC_PHILOX) {
+        const float4 u4 = philox_noise4(col >> 2, p.seed, off);
+        const int l = (int)(col & 3);
+        u = l == 0 ? u4.x : (l == 1 ? u4.y : (l == 2 ? u4.z : u4.w));
+      }
+      k[ch] = __float2int_rn(quant1<MODE>(p.x[row * p.n_inner + col], u, c, n1, n2));
+    }
+    uint32_t w[4] = {0, 0, 0, 0};
+    uint8_t b[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) b[i] = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      b[ch] = b[3 + ch] = (uint8_t)((k[ch] >> 1) & 0xff);  // hi = floor(k / 2), in [-128, 127]
+      b[6 + ch] = (uint8_t)(k[ch] & 1);                     // lo in {0, 1}
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i >> 2] |= (uint32_t)b[i] << (8 * (i & 3));
+    reinterpret_cast<uint4*>(p.mant)[pix] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  finish_stats(n1, n2, p, ib);
+}
+
 __global__ void noise_fill_kernel(float* u, size_t n_inner, uint64_t seed, uint64_t offset, const uint64_t* dev_step) {
   uint64_t off = offset;
   if (dev_step) off += (*dev_step) << 32;
@@ -260,7 +300,9 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
   if (mode < 0 || mode > 2) return LBT_EINVAL;
   if (mode == LBT_ROUND_STOCHASTIC_NOISE && !noise) return LBT_EINVAL;
   if (!out_fp32 && !out_mant && !counters) return LBT_EINVAL;  // nothing to produce
-  if (out_mant && (mant_kind < LBT_MANT_S8 || mant_kind > LBT_MANT_S16)) return LBT_EINVAL;
+  if (out_mant && (mant_kind < LBT_MANT_S8 || mant_kind > LBT_MANT_S9C3)) return LBT_EINVAL;
+  if (mant_kind == LBT_MANT_S9C3 && (bits > 9 || n_inner % 3 != 0 || out_fp32 || (reinterpret_cast<uintptr_t>(out_mant) & 15)))
+    return LBT_EINVAL;
   if (!out_mant) mant_kind = LBT_MANT_NONE;
   if (mant_kind == LBT_MANT_S8 && bits > 8) return LBT_EINVAL;
   if (mant_kind == LBT_MANT_U8 && bits > 9) return LBT_EINVAL;
@@ -291,6 +333,17 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
   const bool vec = (n_inner % 4 == 0) && (n_inner / 4 < 0xffffffffull) && aligned16(x) && (!out_fp32 || aligned16(out_fp32)) &&
                    (!out_mant || aligned16(out_mant)) && (mode != LBT_ROUND_STOCHASTIC_NOISE || aligned16(noise));
   const uint64_t cap = (uint64_t)di.sm_count * (uint64_t)g_blocks_per_sm;
+  if (mant_kind == LBT_MANT_S9C3) {
+    const uint64_t npix = (uint64_t)n_outer * (n_inner / 3);
+    const uint64_t blocks = (npix + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    switch (mode) {
+      case LBT_ROUND_NEAREST: quantize_c3_kernel<0><<<grid, kThreads, 0, st>>>(p); break;
+      case LBT_ROUND_STOCHASTIC_NOISE: quantize_c3_kernel<1><<<grid, kThreads, 0, st>>>(p); break;
+      default: quantize_c3_kernel<2><<<grid, kThreads, 0, st>>>(p); break;
+    }
+    return check_launch("lbt_quantize(c3)");
+  }
   if (vec) {
     p.n_vec = (uint32_t)(n_inner / 4);
     p.chunks = (p.n_vec + kThreads - 1) / kThreads;

@@ -99,12 +99,12 @@ class QuantSite(nn.Module):
         self.register_buffer('counters', torch.zeros(Q.CNT_WORDS, dtype=torch.int64))
         runtime.register(self)
 
-    def quantize(self, x, want_fp32=True, mant_kind=Q.MANT_NONE):
+    def quantize(self, x, want_fp32=True, mant_kind=Q.MANT_NONE, out_mant=None):
         """Stochastic DFXP quantisation of ``x`` (memory order = TF layout).  Gathers the overflow
         counters; the range itself moves in Runtime.update_ranges()."""
         rt = self.runtime
         kw = dict(target_overflow_rate=self.target, want_fp32=want_fp32, mant_kind=mant_kind, counters=self.counters,
-                  update_range=False)
+                  update_range=False, out_mant=out_mant)
         if rt.noise_fn is not None:
             n_inner = Q.rows_view(x)[1]
             kw.update(mode=Q.ROUND_NOISE, noise=rt.noise_fn(self, n_inner, x.device))
@@ -247,19 +247,34 @@ class _QConv2dFn(torch.autograd.Function):
         if layer.qW.bits > 8 or xb > 16:
             raise _lib.LbtError('Conv2d_q: weights wider than 8 bits need the hi/lo GEMM split (not built yet)')
         x_nhwc = x.permute(0, 2, 3, 1)
-        _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)                   # dfxp:287
         _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)               # dfxp:289
-        segs = 3 if xkind == Q.MANT_S16 else 1
         Kf = kh * kw * Cin
-        # B operand [Cout, Kf]: transpose of the HWIO mantissas (tiny)
-        wt = _transpose_bytes(wm.view(Kf, Cout))
-        if segs == 3:
-            wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
         bq = None
         if bias is not None:
             bq, _ = layer.qb.quantize(bias)                                                    # dfxp:294
         y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
         e = -(xb - 1) - (layer.qW.bits - 1)
+        if (xkind == Q.MANT_S16 and xb <= 9 and Cin == 3 and layer.implicit and kh * kw * 16 <= 65536 and
+                _implicit_ok(Cout, 1, 1)):
+            # image input: signed 9-bit k = 2*hi + lo as a 16-channel s8 tensor {hi,hi,lo,0} against {W,W,W,0}
+            xkind = Q.MANT_S9C3
+            xm = torch.empty(N, H, W, 16, dtype=torch.int8, device=x.device)
+            layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind, out_mant=xm)           # dfxp:287
+            w3 = wm.view(kh * kw, 3, Cout)
+            w16 = torch.cat([w3, w3, w3, torch.zeros(kh * kw, 7, Cout, dtype=torch.int8, device=x.device)], dim=1)
+            wt = _transpose_bytes(w16.view(kh * kw * 16, Cout))
+            _conv_implicit(xm, Q.MANT_S8, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, layer.qX.range, layer.qW.range, e, bq,
+                           y.view(N * OH * OW, Cout))
+            ctx.layer = layer
+            ctx.geom = (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind)
+            ctx.save_for_backward(xm, wm, weight)
+            return y.permute(0, 3, 1, 2)
+        _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)                   # dfxp:287
+        segs = 3 if xkind == Q.MANT_S16 else 1
+        # B operand [Cout, Kf]: transpose of the HWIO mantissas (tiny)
+        wt = _transpose_bytes(wm.view(Kf, Cout))
+        if segs == 3:
+            wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
         if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
             G.gemm_i8(xm.reshape(N * H * W, Cin), wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=e, bias=bq,
                       out=y.view(N * OH * OW, Cout))                                           # 1x1: plain GEMM
@@ -291,7 +306,17 @@ class _QConv2dFn(torch.autograd.Function):
         # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
         if ctx.needs_input_grad[1]:
             acc = torch.zeros(Kf, Cout, dtype=torch.int64, device=dy.device)
-            if layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
+            if xkind == Q.MANT_S9C3 and _implicit_ok(Cout, 1, 1):
+                # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
+                acc16 = torch.zeros(kh * kw * 16, Cout, dtype=torch.int64, device=dy.device)
+                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                          sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+                a = acc16.view(kh * kw, 16, Cout)
+                acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+                gt = at = None
+            elif xkind == Q.MANT_S9C3:
+                raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
+            elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
                 # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
                           sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(),

@@ -15,8 +15,9 @@ import torch
 from . import _lib
 
 ROUND_NEAREST, ROUND_NOISE, ROUND_PHILOX = 0, 1, 2
-MANT_NONE, MANT_S8, MANT_U8, MANT_S16 = 0, 1, 2, 3
+MANT_NONE, MANT_S8, MANT_U8, MANT_S16, MANT_S9C3 = 0, 1, 2, 3, 4
 _MANT_DTYPE = {MANT_S8: torch.int8, MANT_U8: torch.uint8, MANT_S16: torch.int16}
+_MANT_BYTES = {MANT_NONE: 0, MANT_S8: 1, MANT_U8: 1, MANT_S16: 2, MANT_S9C3: 6}     # per element, for the roofline
 CNT_WORDS = 4
 
 
@@ -61,7 +62,7 @@ def quantize(x, bits, integer_bits, *, target_overflow_rate=0.0, mode=ROUND_NEAR
                               float(target_overflow_rate), int(mode), _lib.ptr(noise), int(seed), int(offset),
                               _lib.ptr(dev_step), _lib.ptr(out) if want_fp32 else None, _lib.ptr(out_mant),
                               int(mant_kind), _lib.ptr(counters), 1 if update_range else 0, _lib.stream(),
-              meta=dict(bytes=n_outer * n_inner * (4 + (4 if want_fp32 else 0) + {0: 0, 1: 1, 2: 1, 3: 2}[int(mant_kind)])))
+              meta=dict(bytes=n_outer * n_inner * (4 + (4 if want_fp32 else 0) + _MANT_BYTES[int(mant_kind)])))
     return (out if want_fp32 else None), out_mant
 
 
