@@ -202,6 +202,54 @@ int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in, void* out
 int lbt_colsum_i(const void* in, int kind, size_t R, size_t C, int64_t* acc64, void* stream);
 
 /*
+ * One launch for every gradient of the step: out[k] = fp32(acc64[k]) * 2^(exp_const + *ibA + *ibB)
+ * (+ add_scale * add[k]) for each job — the tails `tf.gradients(...) + 2*weight_decay*W` of every layer
+ * (dynamic_fixed_point.py:207-209, 302-304, 457-459, 689-690).  The job table lives on the device;
+ * `start` is the running sum of n over the preceding jobs and `total` the sum of all n.
+ */
+typedef struct lbt_finalize_job {
+  const int64_t* acc64;
+  uint64_t n;
+  const int32_t* ibA; /* may be NULL */
+  const int32_t* ibB; /* may be NULL */
+  int32_t exp_const;
+  float add_scale;
+  const float* add; /* may be NULL */
+  float* out;
+  uint64_t start;
+} lbt_finalize_job;
+int lbt_finalize_multi(const lbt_finalize_job* jobs_dev, size_t njobs, uint64_t total, void* stream);
+
+/*
+ * One launch for every PARAMETER quantiser of the step (weights dfxp:289, 386; biases :294, 391; BN gamma /
+ * beta :679-682): stochastic DFXP quantisation with the in-kernel Philox stream (offset = quantiser id,
+ * + *dev_step << 32), overflow counters, and the operands the tensor-core kernels consume:
+ *   out_f32  fake-quantised fp32 copy (vectors), or NULL
+ *   LBT_PREP_CONV  (x is HWIO [kh,kw,Cin,Cout]): out_a[Cout, (r,s,ci)] (fprop B, pitch ld_a; c3pad: 16
+ *                  pseudo-channels {W,W,W,0} per tap for a 3-channel first layer), out_b[Cin, (r',s',co)]
+ *                  (dgrad B, pitch ld_b; rot180: taps reversed for the stride-1 implicit dgrad)
+ *   LBT_PREP_DENSE (x is [in = Cin, out = Cout]): out_a[out, in], out_b[in, out]
+ * Each CTA handles `chunk_elems` consecutive elements of one job: block_job / block_chunk give the mapping.
+ */
+enum lbt_prep_layout { LBT_PREP_VECTOR = 0, LBT_PREP_CONV = 1, LBT_PREP_DENSE = 2 };
+typedef struct lbt_prep_job {
+  const float* x;
+  uint64_t n_outer, n_inner;
+  const int32_t* ib;
+  uint64_t* counters;
+  uint64_t offset;
+  float* out_f32;
+  int8_t* out_a;
+  int8_t* out_b;
+  uint64_t ld_a, ld_b;
+  int32_t bits, layout;
+  uint32_t kh, kw, Cin, Cout;
+  int32_t c3pad, rot180;
+} lbt_prep_job;
+int lbt_param_prep(const lbt_prep_job* jobs_dev, const uint32_t* block_job_dev, const uint32_t* block_chunk_dev,
+                   size_t nblocks, uint32_t chunk_elems, uint64_t seed, const uint64_t* dev_step, void* stream);
+
+/*
  * Momentum SGD on flat fp32 buffers (tf.train.MomentumOptimizer.apply_gradients, trainer.py:81-82,
  * non-Nesterov):  accum <- momentum*accum + grad_scale*grad ;  w <- w - lr*accum.
  * dev_lr (device float, may be NULL) overrides lr so a captured graph can follow an LR schedule;

@@ -38,6 +38,8 @@ SIGNATURES = {
     'lbt_colsum_i': (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
                                  c_void_p]),
+    'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),
+    'lbt_param_prep': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_uint32, c_u64, c_void_p, c_void_p]),
     'lbt_bn_fwd_quant_stats': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_u64, c_u64,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'lbt_bn_fwd_apply': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
@@ -61,6 +63,32 @@ _INTERNAL = {
 
 class LbtError(RuntimeError):
     pass
+
+
+class FinalizeJob(ctypes.Structure):
+    """lbt_finalize_job (include/lbt.h)."""
+    _fields_ = [('acc64', c_void_p), ('n', c_u64), ('ibA', c_void_p), ('ibB', c_void_p), ('exp_const', ctypes.c_int32),
+                ('add_scale', c_float), ('add', c_void_p), ('out', c_void_p), ('start', c_u64)]
+
+
+class PrepJob(ctypes.Structure):
+    """lbt_prep_job (include/lbt.h)."""
+    _fields_ = [('x', c_void_p), ('n_outer', c_u64), ('n_inner', c_u64), ('ib', c_void_p), ('counters', c_void_p),
+                ('offset', c_u64), ('out_f32', c_void_p), ('out_a', c_void_p), ('out_b', c_void_p), ('ld_a', c_u64),
+                ('ld_b', c_u64), ('bits', ctypes.c_int32), ('layout', ctypes.c_int32), ('kh', ctypes.c_uint32),
+                ('kw', ctypes.c_uint32), ('Cin', ctypes.c_uint32), ('Cout', ctypes.c_uint32), ('c3pad', ctypes.c_int32),
+                ('rot180', ctypes.c_int32)]
+
+
+def to_device_table(structs, device, keep=None):
+    """Upload a list of ctypes Structures as one contiguous device byte tensor.  The staging copy is pinned and
+    the transfer asynchronous, so this is legal inside CUDA-graph capture (it becomes a memcpy node; `keep` — a
+    list — receives the pinned tensor, which must outlive the graph)."""
+    arr = (type(structs[0]) * len(structs))(*structs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+    if keep is not None:
+        keep.append(host)
+    return host.to(device, non_blocking=True)
 
 
 _lib = None

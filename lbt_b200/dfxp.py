@@ -43,7 +43,40 @@ class Runtime:
         self.dev_step = None         # int64[1] on the device once finalised
         self.noise_fn = None         # tests: callable(site, n_inner, device) -> explicit noise tensor
         self.flat = None
-        self.timer = None            # bench: callable(name) -> context manager timing a kernel class
+        self.grad_sink = None        # Trainer: collects every integer gradient sum for ONE lbt_finalize_multi launch
+        self.prep = None             # ParamPrep: ONE lbt_param_prep launch quantises + packs every parameter
+        self._arena = None           # int64 workspace (integer sums), zeroed once per step
+        self._arena_off = 0
+        self._arena_used = 0
+        self._arena_on = False
+
+    # ---- per-step workspace: exact integer sums live in one arena that is zeroed with a single launch ----
+    def begin_step(self, device):
+        """Start of a training step: recycle + zero the int64 arena, then quantise and pack all parameters."""
+        need = max(self._arena_off, 1 << 14)
+        if self._arena is None or self._arena.numel() < need or self._arena.device != torch.device(device):
+            self._arena = torch.zeros(need * 5 // 4, dtype=torch.int64, device=device)
+        elif self._arena_used:
+            self._arena[:self._arena_used].zero_()
+        self._arena_off = 0
+        self._arena_used = 0
+        self._arena_on = True
+        self._prep_valid = False
+        if self.prep is not None:
+            self.prep.run()
+            self._prep_valid = True      # until update_ranges() closes the step
+
+    def zeros_i64(self, n, device):
+        """n zeroed int64 slots (16-byte aligned) from the arena; a fresh tensor when the arena is off or full."""
+        if not self._arena_on:
+            return torch.zeros(int(n), dtype=torch.int64, device=device)
+        n_al = (int(n) + 1) & ~1
+        off = self._arena_off
+        self._arena_off += n_al                      # keeps counting so the next begin_step() can grow the arena
+        if self._arena_on and off + n_al <= self._arena.numel():
+            self._arena_used = off + n_al
+            return self._arena[off:off + n]
+        return torch.zeros(int(n), dtype=torch.int64, device=device)
 
     def register(self, site):
         site.qid = len(self.sites)
@@ -71,11 +104,110 @@ class Runtime:
         _lib.call('lbt_update_ranges', _lib.ptr(f['ranges']), _lib.ptr(f['counters']), _lib.ptr(f['bits']),
                                        _lib.ptr(f['target']), len(self.sites), _lib.stream())
         _lib.call('lbt_step_advance', _lib.ptr(self.dev_step), _lib.stream())
+        self._arena_on = False           # the step is closed: prepared operands and arena slices are stale now
+        self._prep_valid = False
 
     def ranges(self):
         """{quantiser name: integer_bits} — the cheap parity probe (tf.summary of *_range, dfxp:180-190)."""
         vals = self.flat['ranges'].cpu().tolist() if self.flat is not None else [int(s.range) for s in self.sites]
         return {s.name: v for s, v in zip(self.sites, vals)}
+
+
+class ParamPrep:
+    """All parameter quantisers of a step in ONE launch (lbt_param_prep): conv / dense weights are quantised
+    (dfxp:289, 386) and written straight into the packed operand layouts the tensor-core kernels read; biases
+    and BN gamma / beta (dfxp:294, 391, 679-682) become fake-quant fp32 vectors.  Same quantiser ids, ranges and
+    Philox stream as the per-layer path, so the results are identical bit for bit."""
+
+    CHUNK = 4096
+
+    def __init__(self, model, runtime, device):
+        self.rt = runtime
+        self.entries = {}            # module -> dict of prepared tensors
+        jobs = []
+
+        def job(site, x, layout=0, **kw):
+            n_outer, n_inner = Q.rows_view(x)
+            j = _lib.PrepJob(x=x.data_ptr(), n_outer=n_outer, n_inner=n_inner, ib=site.range.data_ptr(),
+                             counters=site.counters.data_ptr(), offset=Q.make_offset(site.qid, 0), bits=site.bits,
+                             layout=layout, **kw)
+            jobs.append(j)
+
+        def vec(site, p):
+            out = torch.empty_like(p.data)
+            job(site, p.data, out_f32=out.data_ptr())
+            return out
+
+        for m in model.modules():
+            if isinstance(m, Conv2d_q) and m.qW.bits <= 8:
+                kh, kw, Cin, Cout = m.weight.shape
+                e = {}
+                c3 = bool(m.input_signed and m.qX.bits == 9 and Cin == 3 and m.implicit and _implicit_ok(Cout, 1, 1))
+                Ka = kh * kw * (16 if c3 else Cin)
+                e['c3'] = c3
+                e['wt'] = torch.zeros(Cout, _pitch16(Ka), dtype=torch.int8, device=device)[:, :Ka]
+                rot = bool(m.implicit and m.stride == (1, 1) and _implicit_ok(Cout, kh, kw) and not (kh == 1 and kw == 1))
+                K2 = kh * kw * Cout
+                e['rot180'] = rot
+                e['w2'] = None if c3 else torch.zeros(Cin, _pitch16(K2), dtype=torch.int8, device=device)[:, :K2]
+                job(m.qW, m.weight.data, layout=1, kh=kh, kw=kw, Cin=Cin, Cout=Cout, c3pad=int(c3), rot180=int(rot),
+                    out_a=e['wt'].data_ptr(), ld_a=e['wt'].stride(0),
+                    out_b=0 if e['w2'] is None else e['w2'].data_ptr(), ld_b=0 if e['w2'] is None else e['w2'].stride(0))
+                if m.bias is not None:
+                    e['bq'] = vec(m.qb, m.bias)
+                self.entries[m] = e
+            elif isinstance(m, Linear_q) and m.qW.bits <= 8:
+                In, Out = m.weight.shape
+                e = {}
+                e['wt'] = torch.zeros(Out, _pitch16(In), dtype=torch.int8, device=device)[:, :In]
+                e['w2'] = torch.zeros(In, _pitch16(Out), dtype=torch.int8, device=device)[:, :Out]
+                job(m.qW, m.weight.data, layout=2, Cin=In, Cout=Out, out_a=e['wt'].data_ptr(), ld_a=e['wt'].stride(0),
+                    out_b=e['w2'].data_ptr(), ld_b=e['w2'].stride(0))
+                if m.bias is not None:
+                    e['bq'] = vec(m.qb, m.bias)
+                self.entries[m] = e
+            elif isinstance(m, Rescale_q):
+                self.entries[m] = dict(gq=vec(m.qg, m.gamma), bq=vec(m.qb, m.beta))
+        self.njobs = len(jobs)
+        if not jobs:
+            return
+        bj, bc = [], []
+        for i, j in enumerate(jobs):
+            n = j.n_outer * j.n_inner
+            for c in range(-(-n // self.CHUNK)):
+                bj.append(i)
+                bc.append(c)
+        self.jobs_dev = _lib.to_device_table(jobs, device)
+        self.block_job = torch.tensor(bj, dtype=torch.int32, device=device)
+        self.block_chunk = torch.tensor(bc, dtype=torch.int32, device=device)
+        self._keep = jobs
+
+    def run(self):
+        if not self.njobs:
+            return
+        rt = self.rt
+        _lib.call('lbt_param_prep', _lib.ptr(self.jobs_dev), _lib.ptr(self.block_job), _lib.ptr(self.block_chunk),
+                  self.block_job.numel(), self.CHUNK, rt.seed, _lib.ptr(rt.dev_step), _lib.stream())
+
+
+def _prepared(layer):
+    """The ParamPrep entry of a layer for the current step, or None (per-layer quantisers run instead)."""
+    rt = layer.qX.runtime
+    if rt.prep is None or rt.noise_fn is not None or not getattr(rt, '_prep_valid', False):
+        return None
+    return rt.prep.entries.get(layer)
+
+
+def _emit_grad(rt, param, acc, *, ibA=None, ibB=None, exp_const=0, add_scale=0.0, shape=None):
+    """Gradient of ``param`` from its exact integer sum: handed to the Trainer's sink (one lbt_finalize_multi per
+    step) when there is one, else finalised here.  ``+ 2*wd*param`` rides along (dfxp:302, 457, 689)."""
+    sink = rt.grad_sink
+    if sink is not None and sink.accepts(param):
+        sink.add(param, acc, ibA, ibB, exp_const, add_scale)
+        return None
+    g = G.acc64_finalize(acc, ibA=ibA, ibB=ibB, exp_const=exp_const, add=param.detach().reshape(-1) if add_scale else None,
+                         add_scale=add_scale)
+    return g.view(shape if shape is not None else param.shape)
 
 
 _default_runtime = Runtime()
@@ -192,8 +324,9 @@ def _im2col(src_nhwc, src_kind, OH, OW, kh, kw, sh, sw, pt, pl, transposed):
     return out[:, :K]
 
 
-def _colsum(mant2d, kind):
-    acc = torch.zeros(mant2d.shape[1], dtype=torch.int64, device=mant2d.device)
+def _colsum(mant2d, kind, rt=None):
+    acc = (rt.zeros_i64(mant2d.shape[1], mant2d.device) if rt is not None
+           else torch.zeros(mant2d.shape[1], dtype=torch.int64, device=mant2d.device))
     _lib.call('lbt_colsum_i', _lib.ptr(mant2d), kind, mant2d.shape[0], mant2d.shape[1], _lib.ptr(acc),
                                        _lib.stream())
     return acc
@@ -247,11 +380,16 @@ class _QConv2dFn(torch.autograd.Function):
         if layer.qW.bits > 8 or xb > 16:
             raise _lib.LbtError('Conv2d_q: weights wider than 8 bits need the hi/lo GEMM split (not built yet)')
         x_nhwc = x.permute(0, 2, 3, 1)
-        _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)               # dfxp:289
+        prep = _prepared(layer)      # weights / bias already quantised + packed by this step's lbt_param_prep?
         Kf = kh * kw * Cin
-        bq = None
-        if bias is not None:
-            bq, _ = layer.qb.quantize(bias)                                                    # dfxp:294
+        bq = wm = None
+        if prep is None:
+            _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)           # dfxp:289
+            if bias is not None:
+                bq, _ = layer.qb.quantize(bias)                                                # dfxp:294
+        else:
+            bq = prep.get('bq')
+        ctx.prep = prep
         y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
         e = -(xb - 1) - (layer.qW.bits - 1)
         if (xkind == Q.MANT_S16 and xb <= 9 and Cin == 3 and layer.implicit and kh * kw * 16 <= 65536 and
@@ -260,9 +398,12 @@ class _QConv2dFn(torch.autograd.Function):
             xkind = Q.MANT_S9C3
             xm = torch.empty(N, H, W, 16, dtype=torch.int8, device=x.device)
             layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind, out_mant=xm)           # dfxp:287
-            w3 = wm.view(kh * kw, 3, Cout)
-            w16 = torch.cat([w3, w3, w3, torch.zeros(kh * kw, 7, Cout, dtype=torch.int8, device=x.device)], dim=1)
-            wt = _transpose_bytes(w16.view(kh * kw * 16, Cout))
+            if prep is not None:
+                wt = prep['wt']
+            else:
+                w3 = wm.view(kh * kw, 3, Cout)
+                w16 = torch.cat([w3, w3, w3, torch.zeros(kh * kw, 7, Cout, dtype=torch.int8, device=x.device)], dim=1)
+                wt = _transpose_bytes(w16.view(kh * kw * 16, Cout))
             _conv_implicit(xm, Q.MANT_S8, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, layer.qX.range, layer.qW.range, e, bq,
                            y.view(N * OH * OW, Cout))
             ctx.layer = layer
@@ -272,7 +413,7 @@ class _QConv2dFn(torch.autograd.Function):
         _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)                   # dfxp:287
         segs = 3 if xkind == Q.MANT_S16 else 1
         # B operand [Cout, Kf]: transpose of the HWIO mantissas (tiny)
-        wt = _transpose_bytes(wm.view(Kf, Cout))
+        wt = prep['wt'] if prep is not None else _transpose_bytes(wm.view(Kf, Cout))
         if segs == 3:
             wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
         if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
@@ -304,11 +445,13 @@ class _QConv2dFn(torch.autograd.Function):
         Kf = kh * kw * Cin
         dW = db = dX = None
         # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
+        rt = layer.qX.runtime
+        prep = ctx.prep
         if ctx.needs_input_grad[1]:
-            acc = torch.zeros(Kf, Cout, dtype=torch.int64, device=dy.device)
+            acc = rt.zeros_i64(Kf * Cout, dy.device).view(Kf, Cout)
             if xkind == Q.MANT_S9C3 and _implicit_ok(Cout, 1, 1):
                 # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
-                acc16 = torch.zeros(kh * kw * 16, Cout, dtype=torch.int64, device=dy.device)
+                acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dy.device).view(kh * kw * 16, Cout)
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
                           sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
                 a = acc16.view(kh * kw, 16, Cout)
@@ -333,26 +476,28 @@ class _QConv2dFn(torch.autograd.Function):
                 G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
             else:
                 G.gemm_i8_acc64(at, gt, acc, alpha=1)
-            dW = G.acc64_finalize(acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
-                                  add=weight.detach().view(Kf, Cout), add_scale=2 * layer.weight_decay
-                                  ).view(kh, kw, Cin, Cout)                                     # dfxp:302
+            dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                            add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))         # dfxp:302
         if layer.qb is not None and ctx.needs_input_grad[2]:
-            db = G.acc64_finalize(_colsum(g2, Q.MANT_S8), ibA=layer.qG.range, exp_const=-(gb - 1))   # dfxp:304
+            db = _emit_grad(rt, layer.bias, _colsum(g2, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))  # dfxp:304
         # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
         if ctx.needs_input_grad[0]:
             K2 = kh * kw * Cout
             dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dy.device)
             e = -(gb - 1) - (wb - 1)
+            pw2 = prep['w2'] if prep is not None else None        # packed by lbt_param_prep in the form used below
+            if prep is not None and pw2 is None:
+                raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
             if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
-                w2 = _as_operand(wm.view(Cin, Cout))
+                w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
                 G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
             elif layer.implicit and sh == 1 and sw == 1 and _implicit_ok(Cout, kh, kw):
                 # stride 1: dX = conv(G, rot180(W)) with padding (k - 1 - pad): the same implicit-GEMM kernel
-                w2 = _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
+                w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
                 _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
                                layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
             else:
-                w2 = _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+                w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
                 A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
                 G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
             dX = dx.permute(0, 3, 1, 2)
@@ -417,14 +562,18 @@ class _QLinearFn(torch.autograd.Function):
         if layer.qX.bits > 8 or layer.qW.bits > 8:
             raise _lib.LbtError('Linear_q: operands wider than 8 bits need the hi/lo GEMM split (not built yet)')
         _, xm = layer.qX.quantize(x, want_fp32=False, mant_kind=Q.MANT_S8)                     # dfxp:384 (bits)
-        _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)                # dfxp:386
-        bq = None
-        if bias is not None:
-            bq, _ = layer.qb.quantize(bias)
-        wt = _transpose_bytes(wm)                                                               # [Out, In]
+        prep = _prepared(layer)
+        bq = wm = None
+        if prep is None:
+            _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)            # dfxp:386
+            if bias is not None:
+                bq, _ = layer.qb.quantize(bias)
+            wt = _transpose_bytes(wm)                                                           # [Out, In]
+        else:
+            wt, bq = prep['wt'], prep.get('bq')
         y = G.gemm_i8(_as_operand(xm), wt, ibA=layer.qX.range, ibB=layer.qW.range,
                       exp_const=-(layer.qX.bits - 1) - (layer.qW.bits - 1), bias=bq)           # dfxp:388, 393
-        ctx.layer = layer
+        ctx.layer, ctx.prep = layer, prep
         ctx.save_for_backward(xm, wm, weight)
         return y
 
@@ -436,17 +585,19 @@ class _QLinearFn(torch.autograd.Function):
         if gb > 8:
             raise _lib.LbtError('Linear_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
         _, gm = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S8)       # dfxp:453
-        In, Out = wm.shape
+        In, Out = weight.shape
+        rt = layer.qX.runtime
         dX = dW = db = None
         if ctx.needs_input_grad[1]:
-            acc = torch.zeros(In, Out, dtype=torch.int64, device=dy.device)
+            acc = rt.zeros_i64(In * Out, dy.device).view(In, Out)
             G.gemm_i8_acc64(_transpose_bytes(xm), _transpose_bytes(gm), acc, alpha=1, k_splits=1)
-            dW = G.acc64_finalize(acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
-                                  add=weight.detach(), add_scale=2 * layer.weight_decay)       # dfxp:457
+            dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range,
+                            exp_const=-(xb - 1) - (gb - 1), add_scale=2 * layer.weight_decay)  # dfxp:457
         if layer.qb is not None and ctx.needs_input_grad[2]:
-            db = G.acc64_finalize(_colsum(gm, Q.MANT_S8), ibA=layer.qG.range, exp_const=-(gb - 1))   # dfxp:459
+            db = _emit_grad(rt, layer.bias, _colsum(gm, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))  # dfxp:459
         if ctx.needs_input_grad[0]:
-            dX = G.gemm_i8(_as_operand(gm), _as_operand(wm), ibA=layer.qG.range, ibB=layer.qW.range,
+            w2 = ctx.prep['w2'] if ctx.prep is not None else _as_operand(wm)
+            dX = G.gemm_i8(_as_operand(gm), w2, ibA=layer.qG.range, ibB=layer.qW.range,
                            exp_const=-(gb - 1) - (wb - 1))                                     # dfxp:460
         return dX, dW, db, None
 
@@ -575,14 +726,18 @@ class _FusedBNFn(torch.autograd.Function):
         N, C = x.shape[0], x.shape[1]
         n_inner = x.numel() // N
         dev = x.device
-        sums = torch.zeros(2 * C, dtype=torch.int64, device=dev)
+        sums = rt.zeros_i64(2 * C, dev)
         k1 = torch.empty_like(x, dtype=torch.int8)
         nz1, off1 = _site_args(norm.qX, x)
         _lib.call('lbt_bn_fwd_quant_stats', _lib.ptr(x), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
                   _lib.ptr(nz1), rt.seed, off1, _lib.ptr(rt.dev_step), _lib.ptr(k1), _lib.ptr(sums),
                   _lib.ptr(norm.qX.counters), _lib.stream(), meta=dict(bytes=x.numel() * 5))
-        gq, _ = resc.qg.quantize(gamma.detach())                                               # dfxp:679
-        bq, _ = resc.qb.quantize(beta.detach())                                                # dfxp:681
+        prep = _prepared(resc)
+        if prep is not None:
+            gq, bq = prep['gq'], prep['bq']
+        else:
+            gq, _ = resc.qg.quantize(gamma.detach())                                           # dfxp:679
+            bq, _ = resc.qb.quantize(beta.detach())                                            # dfxp:681
         k2 = torch.empty_like(k1)
         out = torch.empty_like(x)
         if add is not None:
@@ -609,7 +764,7 @@ class _FusedBNFn(torch.autograd.Function):
         N, C = g.shape[0], g.shape[1]
         n_inner = g.numel() // N
         dev = g.device
-        bsums = torch.zeros(4 * C, dtype=torch.int64, device=dev)
+        bsums = rt.zeros_i64(4 * C, dev)
         kg1 = torch.empty_like(k1)
         d_add = torch.empty_like(g) if ctx.has_add else None
         nzg2, offg2 = _site_args(resc.qG, g)
@@ -625,10 +780,9 @@ class _FusedBNFn(torch.autograd.Function):
                   _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
                   _lib.stream(), meta=dict(bytes=g.numel() * 6))
         # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
-        dbeta = G.acc64_finalize(bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
-        dgamma = G.acc64_finalize(bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
-                                  exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add=gamma.detach(),
-                                  add_scale=2 * resc.weight_decay)
+        dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
+        dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
+                            exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add_scale=2 * resc.weight_decay)
         return dx, dgamma, dbeta, d_add, None, None
 
 

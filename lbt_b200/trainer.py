@@ -6,15 +6,69 @@ weights (trainer.py:79-84), then the range controller of every quantiser.  New h
 is single-device): data parallelism over the batch — one process per GPU, the
 flattened gradient all-reduced with NCCL, and the overflow counters all-reduced before the
 controller runs so every replica keeps identical ranges and sees the global-batch overflow rate.
+
+Per step the parameter side costs four launches regardless of depth: lbt_param_prep (quantise + pack
+every parameter), lbt_finalize_multi (every gradient), lbt_sgd_momentum, lbt_update_ranges.
 """
 import torch
 import torch.distributed as dist
 
 from . import _lib
+from .dfxp import ParamPrep
+
+
+def sync_replicas(flat_g, counters, group=None, sync_counters=True):
+    """The data-parallel exchange: sum the flat gradient and the quantisers' overflow counters over
+    the replicas.  Device-agnostic (NCCL on GPUs; the gloo CPU tests drive it too)."""
+    dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
+    if sync_counters:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+
+
+class GradSink:
+    """Collects (integer sum, scale exponents, weight-decay term) of every parameter gradient during backward and
+    converts them all with ONE lbt_finalize_multi launch, writing straight into the flat gradient buffer."""
+
+    def __init__(self, params):
+        self.out = {id(p): p for p in params}
+        self.jobs = []
+        self._key = None
+        self._table = None
+        self._pinned = []            # staging copies of uploaded tables (kept alive for captured CUDA graphs)
+        self.active = False         # only between begin() and flush(): outside a Trainer step layers finalise themselves
+
+    def accepts(self, param):
+        return self.active and id(param) in self.out
+
+    def begin(self):
+        self.jobs = []
+        self.active = True
+
+    def add(self, param, acc, ibA, ibB, exp_const, add_scale):
+        self.jobs.append((param, acc, ibA, ibB, int(exp_const), float(add_scale)))
+
+    def flush(self):
+        self.active = False
+        if not self.jobs:
+            return
+        structs, key, start = [], [], 0
+        for param, acc, ibA, ibB, e, s in self.jobs:
+            n = acc.numel()
+            assert n == param.numel() and acc.is_contiguous()
+            j = _lib.FinalizeJob(acc64=acc.data_ptr(), n=n, ibA=_lib.ptr(ibA) or 0, ibB=_lib.ptr(ibB) or 0, exp_const=e,
+                                 add_scale=s, add=param.data.data_ptr() if s else 0, out=param.grad.data_ptr(), start=start)
+            structs.append(j)
+            key.append((j.acc64, n, j.ibA, j.ibB, e, s, j.add, j.out))
+            start += n
+        key = tuple(key)
+        if key != self._key:                      # pointers are stable from step to step: upload the table once
+            self._table = _lib.to_device_table(structs, self.jobs[0][1].device, keep=self._pinned)
+            self._key = key
+        _lib.call('lbt_finalize_multi', _lib.ptr(self._table), len(structs), start, _lib.stream())
 
 
 class Trainer:
-    def __init__(self, model, lr=1e-2, momentum=0.9, *, process_group=None, sync_counters=True):
+    def __init__(self, model, lr=1e-2, momentum=0.9, *, process_group=None, sync_counters=True, batched=True):
         self.model = model
         self.lr, self.momentum = float(lr), float(momentum)
         self.group = process_group
@@ -24,7 +78,9 @@ class Trainer:
         if not params or not params[0].is_cuda:
             raise _lib.LbtError('Trainer needs the model on a CUDA device (no CPU fallback)')
         dev = params[0].device
-        model.runtime.finalize(dev)
+        self.device = dev
+        rt = model.runtime
+        rt.finalize(dev)
         # flatten parameters / gradients / momentum: one SGD launch and one all-reduce per step
         sizes = [p.numel() for p in params]
         offs, total = [], 0
@@ -42,6 +98,11 @@ class Trainer:
         self.dev_lr = torch.tensor(self.lr, dtype=torch.float32, device=dev)
         if self.world > 1:                               # replicas start from rank 0's weights
             dist.broadcast(self.flat_w, src=0, group=self.group)
+        # batched parameter-side launches (identical arithmetic; batched=False keeps the per-layer launches)
+        self.batched = batched
+        self.sink = GradSink(params) if batched else None
+        rt.grad_sink = self.sink
+        rt.prep = ParamPrep(model, rt, dev) if batched else None
 
     def set_lr(self, lr, reset_momentum=True):
         """LR change; the reference re-creates the optimizer, zeroing momentum (trainer.py:79-84, 118-132)."""
@@ -51,21 +112,24 @@ class Trainer:
             self.flat_a.zero_()
 
     def forward_backward(self, X, y):
+        rt = self.model.runtime
         self.flat_g.zero_()
+        if self.batched:
+            rt.begin_step(self.device)
+            self.sink.begin()
         logits = self.model(X)
         loss = self.model.loss(logits, y)
         loss.backward()
+        if self.batched:
+            self.sink.flush()
         return loss.detach(), logits.detach()
 
     def apply(self):
         rt = self.model.runtime
         if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
-            if self.sync_counters:
-                dist.all_reduce(rt.flat['counters'], op=dist.ReduceOp.SUM, group=self.group)
+            sync_replicas(self.flat_g, rt.flat['counters'], self.group, self.sync_counters)
         _lib.call('lbt_sgd_momentum', _lib.ptr(self.flat_w), _lib.ptr(self.flat_a), _lib.ptr(self.flat_g),
-                                               self.flat_w.numel(), self.lr, _lib.ptr(self.dev_lr), self.momentum,
-                                               1.0 / self.world, _lib.stream())
+                  self.flat_w.numel(), self.lr, _lib.ptr(self.dev_lr), self.momentum, 1.0 / self.world, _lib.stream())
         rt.update_ranges()
 
     def step(self, X, y):

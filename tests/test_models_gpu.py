@@ -225,3 +225,22 @@ def test_cifar10_model_step_bit_exact_vs_exact_oracle():
         assert torch.equal(p.grad.cpu(), go), 'gradient of a %s variable differs' % (tuple(vo.shape),)
     pm.runtime.update_ranges()
     assert list(pm.ranges().values()) == om.ranges()
+
+
+@pytest.mark.parametrize('name', ['CIFAR10_Model', 'CIFAR10_Resnet20'])
+def test_batched_parameter_launches_are_bit_identical(name):
+    """lbt_param_prep + lbt_finalize_multi + the int64 arena (one launch each per step) give exactly the
+    weights, losses and ranges of the per-layer launches."""
+    torch.manual_seed(0)
+    X = (torch.randn(32, 3, 32, 32, device='cuda') * 0.5).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (32,), device='cuda')
+    results = []
+    for batched in (False, True):
+        torch.manual_seed(1)
+        pm = getattr(M, name)(8, weight_decay=2e-4, dropout=1.0, seed=9).cuda()
+        tr = Trainer(pm, lr=1e-2, momentum=0.9, batched=batched)
+        losses = [float(tr.step(X, y)) for _ in range(4)]
+        results.append((losses, tr.flat_w.clone(), list(pm.ranges().values())))
+    assert results[0][0] == results[1][0]
+    assert torch.equal(results[0][1], results[1][1])
+    assert results[0][2] == results[1][2]
