@@ -40,7 +40,11 @@ enum lbt_status {
 enum lbt_round_mode {
   LBT_ROUND_NEAREST = 0,           /* `identity`,            dynamic_fixed_point.py:25-30 */
   LBT_ROUND_STOCHASTIC_NOISE = 1,  /* `stochastic_identity`, dynamic_fixed_point.py:32-38, noise from `noise[n_inner]` */
-  LBT_ROUND_STOCHASTIC_PHILOX = 2  /* same, noise generated in-kernel (identical to lbt_noise_fill) */
+  LBT_ROUND_STOCHASTIC_PHILOX = 2, /* same, noise generated in-kernel (identical to lbt_noise_fill) */
+  /* OR-able flag: gather the overflow statistics by min/max tracking instead of exact counts.  The counters then
+   * hold "number of threads that saw an overflow" — still > 0 iff any element overflowed, which is all the
+   * controller tests when target_overflow_rate == 0 (the reference's only setting); ignored for a non-zero target. */
+  LBT_STATS_MINMAX = 0x100
 };
 
 /* Integer mantissa output of lbt_quantize (mantissa k = q * 2^(bits-integer_bits-1)). */
@@ -268,7 +272,7 @@ int lbt_sgd_momentum(float* w, float* accum, const float* grad, size_t n, float 
  */
 int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_inner, int C, int bits, const int32_t* ib,
                            const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
-                           int8_t* k1, int64_t* sums, uint64_t* counters, void* stream);
+                           int8_t* k1, int64_t* sums, uint64_t* counters, int stats_minmax, void* stream);
 /*
  * fwd 2: mean/var (biased, dfxp:588) from `sums`; y1 = (xq - mean) / sqrt(var + eps) (dfxp:616);
  * k2 = Q_rescale(y1) (dfxp:677); out = xq2 * gamma_q + beta_q (dfxp:683) [+ add] [ReLU, dfxp:986].
@@ -280,7 +284,7 @@ int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, in
                      uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                      const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                      float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                     float momentum, void* stream);
+                     float momentum, int stats_minmax, void* stream);
 /*
  * bwd 1: g (w.r.t. the module output) -> ReLU mask (relu: 0 none, 1 recomputed from k2, 2 from `out`)
  * [-> d_add = masked g] -> kg2 = Q(g) (dfxp:687) -> sums[0..C) = sum kg2 (dbeta, :690),
@@ -293,7 +297,7 @@ int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int
                            const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
                            const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
                            uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
-                           int8_t* kg1, int64_t* sums, void* stream);
+                           int8_t* kg1, int64_t* sums, int stats_minmax, void* stream);
 /*
  * bwd 2: dx = (gq1 - mean(gq1) - xhat * mean(gq1 * xhat)) / sqrt(var + eps), the batch-norm VJP that
  * tf.gradients(y, X, gradq) yields for dfxp:616 (dfxp:623), from kg1, k1 and the two sum buffers.

@@ -41,14 +41,14 @@ SIGNATURES = {
     'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),
     'lbt_param_prep': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_uint32, c_u64, c_void_p, c_void_p]),
     'lbt_bn_fwd_quant_stats': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_u64, c_u64,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'lbt_bn_fwd_apply': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                  c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p]),
     'lbt_bn_bwd_quant_stats': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,
                                        c_void_p, c_void_p, c_u64, c_void_p, c_u64, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_void_p]),
+                                       c_void_p, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

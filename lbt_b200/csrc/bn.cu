@@ -37,6 +37,7 @@ struct QSite {
   uint64_t seed, offset;
   const uint64_t* dev_step;
   unsigned long long* counters;
+  int minmax;  // 1: min/max statistics (target_overflow_rate == 0)
 };
 
 struct QC {
@@ -61,6 +62,18 @@ __device__ __forceinline__ float squant(float x, float u, const QC& c, uint32_t&
   n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
   n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
   return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+
+// min/max variant of the statistics (LBT_STATS_MINMAX): two FMNMX instead of four compares + adds
+__device__ __forceinline__ float squant_mm(float x, float u, const QC& c, float& mx, float& mn) {
+  const float y = __fmul_rn(x, c.m);
+  mx = fmaxf(mx, y);
+  mn = fminf(mn, y);
+  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+__device__ __forceinline__ void mm_to_counts(const QC& c, float mx, float mn, uint32_t& n1, uint32_t& n2) {
+  n1 = (mx >= c.L || mn < -c.L) ? 1u : 0u;
+  n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
 }
 
 __device__ __forceinline__ float4 site_noise(const QSite& s, uint32_t v, uint64_t off) {
@@ -103,10 +116,12 @@ __device__ __forceinline__ void publish_counters(unsigned long long* counters, u
   }
 }
 
-// Per-channel partial sums: NS sums for each of the thread's 4 channels.
-template <int NS>
+// Per-channel partial sums: NS sums for each of the thread's 4 channels.  32-bit per thread (a thread sums at
+// most a few 10^4 products of two 8-bit mantissas; the host rejects tensors where that could overflow),
+// widened to 64 bits when the partials are combined.
+template <int NS, typename T = int>
 struct Acc {
-  long long s[NS][4];
+  T s[NS][4];
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int i = 0; i < NS; ++i)
@@ -122,7 +137,8 @@ __device__ __forceinline__ void flush_global(Acc<NS>& a, long long* sums, int C,
   for (int i = 0; i < NS; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (a.s[i][j]) atomicAdd(reinterpret_cast<unsigned long long*>(sums) + (size_t)i * C + c0 + j, (unsigned long long)a.s[i][j]);
+      if (a.s[i][j])
+        atomicAdd(reinterpret_cast<unsigned long long*>(sums) + (size_t)i * C + c0 + j, (unsigned long long)(long long)a.s[i][j]);
   a.zero();
 }
 
@@ -130,16 +146,21 @@ __device__ __forceinline__ void flush_global(Acc<NS>& a, long long* sums, int C,
 // kernel.  Reduce across the lanes of a warp that share a group, then across warps through shared memory,
 // then one global atomic per (sum, channel) per CTA.
 template <int NS>
-__device__ __forceinline__ void flush_block(Acc<NS>& a, long long* sums, int C, unsigned long long* s_acc) {
+__device__ __forceinline__ void flush_block(Acc<NS>& a32, long long* sums, int C, unsigned long long* s_acc) {
   const int groups = C >> 2;
   for (int i = threadIdx.x; i < NS * C; i += kThreads) s_acc[i] = 0ull;
   __syncthreads();
+  long long v[NS][4];
+#pragma unroll
+  for (int i = 0; i < NS; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = (long long)a32.s[i][j];
   if (groups < 32) {
     for (int o = 16; o >= groups; o >>= 1) {
 #pragma unroll
       for (int i = 0; i < NS; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) a.s[i][j] += __shfl_xor_sync(0xffffffffu, a.s[i][j], o);
+        for (int j = 0; j < 4; ++j) v[i][j] += __shfl_xor_sync(0xffffffffu, v[i][j], o);
     }
   }
   const int lane = threadIdx.x & 31;
@@ -149,7 +170,7 @@ __device__ __forceinline__ void flush_block(Acc<NS>& a, long long* sums, int C, 
     for (int i = 0; i < NS; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (a.s[i][j]) atomicAdd(s_acc + (size_t)i * C + c0 + j, (unsigned long long)a.s[i][j]);
+        if (v[i][j]) atomicAdd(s_acc + (size_t)i * C + c0 + j, (unsigned long long)v[i][j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NS * C; i += kThreads)
@@ -195,6 +216,8 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
   const QC c = make_qc(p.q.bits, *reinterpret_cast<volatile const int32_t*>(p.q.ib));
   const uint64_t off = site_offset(p.q);
   uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  const bool mm = p.q.minmax != 0;
   Acc<2> acc;
   acc.zero();
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
@@ -212,13 +235,20 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
         for (int i = 0; i < kRows; ++i)
           if (r + i < r1) {
             float k[4];
-            k[0] = squant(xv[i].x, u.x, c, n1, n2);
-            k[1] = squant(xv[i].y, u.y, c, n1, n2);
-            k[2] = squant(xv[i].z, u.z, c, n1, n2);
-            k[3] = squant(xv[i].w, u.w, c, n1, n2);
+            if (mm) {
+              k[0] = squant_mm(xv[i].x, u.x, c, mx, mn);
+              k[1] = squant_mm(xv[i].y, u.y, c, mx, mn);
+              k[2] = squant_mm(xv[i].z, u.z, c, mx, mn);
+              k[3] = squant_mm(xv[i].w, u.w, c, mx, mn);
+            } else {
+              k[0] = squant(xv[i].x, u.x, c, n1, n2);
+              k[1] = squant(xv[i].y, u.y, c, n1, n2);
+              k[2] = squant(xv[i].z, u.z, c, n1, n2);
+              k[3] = squant(xv[i].w, u.w, c, n1, n2);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const long long ki = (long long)__float2int_rn(k[j]);
+              const int ki = __float2int_rn(k[j]);
               acc.s[0][j] += ki;
               acc.s[1][j] += ki * ki;
             }
@@ -229,6 +259,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
     }
   }
   if (p.t.fixed_channels) flush_block<2>(acc, p.sums, p.t.C, s_acc);
+  if (mm) mm_to_counts(c, mx, mn, n1, n2);
   publish_counters(p.q.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
 }
 
@@ -282,6 +313,8 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
   __syncthreads();
   const uint64_t off = site_offset(p.q2);
   uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  const bool mm = p.q2.minmax != 0;
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -320,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
           for (int j = 0; j < 4; ++j) {
             const float xq = __int2float_rn(k1[j]) * c1.inv_m;
             const float y1 = __fdiv_rn(__fsub_rn(xq, mean[j]), den[j]);      // dfxp:616
-            k2[j] = squant(y1, un[j], c2, n1, n2);                            // dfxp:677
+            k2[j] = mm ? squant_mm(y1, un[j], c2, mx, mn) : squant(y1, un[j], c2, n1, n2);   // dfxp:677
             float y2 = __fadd_rn(__fmul_rn(k2[j] * c2.inv_m, g[j]), b[j]);    // dfxp:683
             if (p.add) y2 = __fadd_rn(y2, a4[j]);                             // residual sum, dfxp:862
             if (p.relu) y2 = fmaxf(0.0f, y2);                                 // tf.maximum(0.0, X), dfxp:986
@@ -331,6 +364,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
         }
     }
   }
+  if (mm) mm_to_counts(c2, mx, mn, n1, n2);
   publish_counters(p.q2.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
 }
 
@@ -355,7 +389,7 @@ struct Bwd1Params {
   long long* sums;      // [4*C]: sum kg2, sum kg2*k2, sum kg1, sum kg1*k1
 };
 
-__global__ void __launch_bounds__(kThreads) bn_bwd1_kernel(const Bwd1Params p) {
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
   const int C = p.t.C;
@@ -364,6 +398,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd1_kernel(const Bwd1Params p) {
   const QC cg1 = make_qc(p.qg1.bits, *reinterpret_cast<volatile const int32_t*>(p.qg1.ib));
   const uint64_t off2 = site_offset(p.qg2), off1 = site_offset(p.qg1);
   uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  float amx = -INFINITY, amn = INFINITY, bmx = -INFINITY, bmn = INFINITY;
+  const bool mm2 = p.qg2.minmax != 0, mm1 = p.qg1.minmax != 0;
   Acc<4> acc;
   acc.zero();
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
@@ -412,15 +448,15 @@ __global__ void __launch_bounds__(kThreads) bn_bwd1_kernel(const Bwd1Params p) {
                 if (!(oin[j] > 0.0f)) gj = 0.0f;
               }
               gm[j] = gj;
-              const float kg2 = squant(gj, u2[j], cg2, a1, a2);                    // dfxp:687
-              const long long kg2i = (long long)__float2int_rn(kg2);
+              const float kg2 = mm2 ? squant_mm(gj, u2[j], cg2, amx, amn) : squant(gj, u2[j], cg2, a1, a2);   // dfxp:687
+              const int kg2i = __float2int_rn(kg2);
               acc.s[0][j] += kg2i;                                                 // dbeta  (dfxp:690)
-              acc.s[1][j] += kg2i * (long long)k2[j];                              // dgamma (dfxp:689)
+              acc.s[1][j] += kg2i * k2[j];                                         // dgamma (dfxp:689)
               const float dx2 = __fmul_rn(kg2 * cg2.inv_m, g[j]);                  // dfxp:691
-              kq1[j] = squant(dx2, u1[j], cg1, b1, b2);                            // dfxp:621
-              const long long kg1i = (long long)__float2int_rn(kq1[j]);
+              kq1[j] = mm1 ? squant_mm(dx2, u1[j], cg1, bmx, bmn) : squant(dx2, u1[j], cg1, b1, b2);         // dfxp:621
+              const int kg1i = __float2int_rn(kq1[j]);
               acc.s[2][j] += kg1i;
-              acc.s[3][j] += kg1i * (long long)k1[j];
+              acc.s[3][j] += kg1i * k1[j];
             }
             if (p.d_add) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
             *reinterpret_cast<uint32_t*>(p.kg1 + idx) = pack4(kq1);
@@ -431,6 +467,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd1_kernel(const Bwd1Params p) {
   }
   if (p.t.fixed_channels) flush_block<4>(acc, p.sums, C, s_acc);
   const size_t numel = p.t.n_outer * p.t.n_inner;
+  if (mm2) mm_to_counts(cg2, amx, amn, a1, a2);
+  if (mm1) mm_to_counts(cg1, bmx, bmn, b1, b2);
   publish_counters(p.qg2.counters, a1, a2, numel, s_red);
   publish_counters(p.qg1.counters, b1, b2, numel, s_red);
 }
@@ -521,6 +559,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
 int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid) {
   if (C <= 0 || (C & 3) || n_inner % (size_t)C) return LBT_EUNSUPPORTED;
   if (n_inner / 4 >= 0xffffffffull) return LBT_EUNSUPPORTED;
+  if (n_outer * n_inner >= (1ull << 36)) return LBT_EUNSUPPORTED;  // keeps every thread's 32-bit partial sums exact
   const DeviceInfo& di = device_info();
   t.n_outer = n_outer;
   t.n_inner = n_inner;
@@ -540,8 +579,9 @@ int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid
 }
 
 QSite make_site(int bits, const int32_t* ib, const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
-                uint64_t* counters) {
+                uint64_t* counters, int minmax = 0) {
   QSite s;
+  s.minmax = minmax;
   s.bits = bits;
   s.ib = ib;
   s.noise = noise;
@@ -574,7 +614,7 @@ using namespace lbt;
 
 extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_inner, int C, int bits, const int32_t* ib,
                                       const float* noise, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
-                                      int8_t* k1, int64_t* sums, uint64_t* counters, void* stream) {
+                                      int8_t* k1, int64_t* sums, uint64_t* counters, int stats_minmax, void* stream) {
   if (!x || !ib || !k1 || !sums) return LBT_EINVAL;
   if (bits < 2 || bits > 8) return LBT_EUNSUPPORTED;
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
@@ -585,7 +625,7 @@ extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_i
   int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
   if (rc) return rc;
   p.x = x;
-  p.q = make_site(bits, ib, noise, seed, offset, dev_step, counters);
+  p.q = make_site(bits, ib, noise, seed, offset, dev_step, counters, stats_minmax);
   p.k1 = k1;
   p.sums = reinterpret_cast<long long*>(sums);
   const size_t smem = (size_t)2 * C * 8;
@@ -599,7 +639,7 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
                                 uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                                 const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                                 float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                                float momentum, void* stream) {
+                                float momentum, int stats_minmax, void* stream) {
   if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2 || !out) return LBT_EINVAL;
   if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
   if ((run_mean == nullptr) != (run_var == nullptr)) return LBT_EINVAL;
@@ -615,7 +655,7 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.ib1 = ib1;
   p.sums = reinterpret_cast<const long long*>(sums);
   p.eps = eps;
-  p.q2 = make_site(bits2, ib2, noise2, seed, offset2, dev_step, counters2);
+  p.q2 = make_site(bits2, ib2, noise2, seed, offset2, dev_step, counters2, stats_minmax);
   p.gq = gamma_q;
   p.bq = beta_q;
   p.add = add;
@@ -639,7 +679,7 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
                                       const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
                                       const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
                                       uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
-                                      int8_t* kg1, int64_t* sums, void* stream) {
+                                      int8_t* kg1, int64_t* sums, int stats_minmax, void* stream) {
   if (!g || !k2 || !k1 || !ib2 || !gamma_q || !beta_q || !ib_g2 || !ib_g1 || !kg1 || !sums) return LBT_EINVAL;
   if (relu < 0 || relu > 2 || (relu == 2 && !out)) return LBT_EINVAL;
   if (bits2 < 2 || bits2 > 8 || bits_g2 < 2 || bits_g2 > 8 || bits_g1 < 2 || bits_g1 > 8) return LBT_EUNSUPPORTED;
@@ -661,8 +701,8 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   p.ib2 = ib2;
   p.gq = gamma_q;
   p.bq = beta_q;
-  p.qg2 = make_site(bits_g2, ib_g2, noise_g2, seed, offset_g2, dev_step, counters_g2);
-  p.qg1 = make_site(bits_g1, ib_g1, noise_g1, seed, offset_g1, dev_step, counters_g1);
+  p.qg2 = make_site(bits_g2, ib_g2, noise_g2, seed, offset_g2, dev_step, counters_g2, stats_minmax);
+  p.qg1 = make_site(bits_g1, ib_g1, noise_g1, seed, offset_g1, dev_step, counters_g1, stats_minmax);
   p.d_add = d_add;
   p.kg1 = kg1;
   p.sums = reinterpret_cast<long long*>(sums);

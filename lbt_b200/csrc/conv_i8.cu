@@ -54,21 +54,29 @@ struct Cfg {
   static constexpr int kStageA = kBlockM * kStageK;
   static constexpr int kStageB = BN * kStageK;
   static constexpr int kStageBytes = kStageA + kStageB;
-  static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
+  // Narrow tiles do little work per tile, so their time is a chain of latencies (TMA -> MMA -> tcgen05.ld ->
+  // store).  Hide it with several CTAs per SM (small smem rings) and a deep ring of TMEM accumulators.
+  static constexpr int kCtasPerSm = BN <= 16 ? 3 : (BN <= 128 ? 2 : 1);
+  static constexpr int kStages = BN <= 64 ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kAccStages = BN <= 64 ? 4 : 2;
+  static constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
+  static_assert(kCtasPerSm * kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kCtasPerSm * kTmemCols <= 512, "tensor memory budget");
 };
 
+inline int ctas_per_sm(int bn) { return bn <= 16 ? 3 : (bn <= 128 ? 2 : 1); }
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[C::kAccStages];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[C::kAccStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
 
@@ -78,7 +86,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
@@ -172,7 +180,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if (!ok) break;
         umma_commit(&tmem_full_bar[acc]);
-        if (++acc == 2) {
+        if (++acc == C::kAccStages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -222,7 +230,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) {
+      if (++acc == C::kAccStages) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -259,15 +267,15 @@ struct WgradParams {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t empty_bar[C::kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[C::kAccStages];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[C::kAccStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
 
@@ -277,7 +285,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
@@ -361,7 +369,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         if (!ok) break;
         umma_commit(&tmem_full_bar[acc]);
-        if (++acc == 2) {
+        if (++acc == C::kAccStages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -400,7 +408,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) {
+      if (++acc == C::kAccStages) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -552,7 +560,8 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
     }
   }
   const uint64_t tiles = (uint64_t)p.m_tiles * p.n_tiles;
-  const unsigned grid = (unsigned)(tiles < (uint64_t)di.sm_count ? tiles : (uint64_t)di.sm_count);
+  const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm(bn);
+  const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 16: return launch<16>(ta, tb, p, grid, st);
@@ -632,7 +641,7 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   uint32_t splits = k_splits > 0 ? (uint32_t)k_splits : 0;
   if (!splits) {
     const uint32_t tiles = p.m_tiles * p.n_tiles;
-    splits = (uint32_t)di.sm_count / (tiles ? tiles : 1);
+    splits = (uint32_t)(di.sm_count * ctas_per_sm(bn)) / (tiles ? tiles : 1);
     if (splits < 1) splits = 1;
   }
   if (splits > p.pix_blocks) splits = p.pix_blocks;
@@ -673,7 +682,8 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
     }
   }
   const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
-  const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
+  const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm(bn);
+  const unsigned grid = (unsigned)(items < cap ? items : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 16: return launch_wgrad<16>(tx, tg, p, grid, st);

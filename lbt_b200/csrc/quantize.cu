@@ -71,6 +71,18 @@ __device__ __forceinline__ float quant1(float x, float u, const QConst& c, uint3
   return k;
 }
 
+// Same arithmetic with min/max tracking instead of the four comparisons + adds of the exact counters
+// (LBT_STATS_MINMAX): enough for the controller whenever target_overflow_rate == 0, the only value the
+// reference ever uses (n1 > 0 <=> max >= L or min < -L; n2 == 0 <=> max < L/2 and min >= -L/2).
+template <int MODE>
+__device__ __forceinline__ float quant1_mm(float x, float u, const QConst& c, float& mx, float& mn) {
+  const float y = __fmul_rn(x, c.m);
+  mx = fmaxf(mx, y);
+  mn = fminf(mn, y);
+  if (MODE == LBT_ROUND_NEAREST) return rintf(fminf(fmaxf(y, -c.L), c.hi));
+  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+
 // Tail of every quantiser kernel: block-reduce the two counters, publish, ticket, controller.
 __device__ __forceinline__ void finish_stats(uint32_t n1, uint32_t n2, const QParams& p, int ib_at_launch) {
   if (p.counters == nullptr) return;
@@ -131,13 +143,14 @@ __device__ __forceinline__ void store_mant4(void* mant, int kind, size_t idx, fl
   }
 }
 
-template <int MODE>
+template <int MODE, bool MM>
 __global__ void __launch_bounds__(kThreads) quantize_vec_kernel(const QParams p) {
   const int ib = *reinterpret_cast<volatile const int32_t*>(p.ib);
   const QConst c = make_const(p.bits, ib);
   uint64_t off = p.offset;
   if (MODE == LBT_ROUND_STOCHASTIC_PHILOX && p.dev_step) off += (*p.dev_step) << 32;
   uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
 
   for (uint64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.chunks), ch = (uint32_t)(tile % p.chunks);
@@ -156,10 +169,18 @@ __global__ void __launch_bounds__(kThreads) quantize_vec_kernel(const QParams p)
 #pragma unroll
       for (int i = 0; i < kRowsUnroll; ++i) {
         if (r + i < r1) {
-          const float k0 = quant1<MODE>(xv[i].x, u.x, c, n1, n2);
-          const float k1 = quant1<MODE>(xv[i].y, u.y, c, n1, n2);
-          const float k2 = quant1<MODE>(xv[i].z, u.z, c, n1, n2);
-          const float k3 = quant1<MODE>(xv[i].w, u.w, c, n1, n2);
+          float k0, k1, k2, k3;
+          if (MM) {
+            k0 = quant1_mm<MODE>(xv[i].x, u.x, c, mx, mn);
+            k1 = quant1_mm<MODE>(xv[i].y, u.y, c, mx, mn);
+            k2 = quant1_mm<MODE>(xv[i].z, u.z, c, mx, mn);
+            k3 = quant1_mm<MODE>(xv[i].w, u.w, c, mx, mn);
+          } else {
+            k0 = quant1<MODE>(xv[i].x, u.x, c, n1, n2);
+            k1 = quant1<MODE>(xv[i].y, u.y, c, n1, n2);
+            k2 = quant1<MODE>(xv[i].z, u.z, c, n1, n2);
+            k3 = quant1<MODE>(xv[i].w, u.w, c, n1, n2);
+          }
           const size_t idx = (r + i) * p.n_inner + 4 * (size_t)v;
           if (p.out)
             *reinterpret_cast<float4*>(p.out + idx) =
@@ -168,6 +189,10 @@ __global__ void __launch_bounds__(kThreads) quantize_vec_kernel(const QParams p)
         }
       }
     }
+  }
+  if (MM) {  // per-thread indicators: the controller only needs "any" / "none"
+    n1 = (mx >= c.L || mn < -c.L) ? 1u : 0u;
+    n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
   }
   finish_stats(n1, n2, p, ib);
 }
@@ -297,6 +322,9 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
                             uint64_t* counters, int update_range, void* stream) {
   if (!x || !integer_bits) return LBT_EINVAL;
   if (bits < 2 || bits > 24) return LBT_EINVAL;
+  // LBT_STATS_MINMAX: min/max tracking instead of exact overflow counts (valid for target_overflow_rate == 0)
+  const bool minmax = (mode & LBT_STATS_MINMAX) != 0 && target_overflow_rate == 0.0f && counters != nullptr;
+  mode &= ~LBT_STATS_MINMAX;
   if (mode < 0 || mode > 2) return LBT_EINVAL;
   if (mode == LBT_ROUND_STOCHASTIC_NOISE && !noise) return LBT_EINVAL;
   if (!out_fp32 && !out_mant && !counters) return LBT_EINVAL;  // nothing to produce
@@ -355,9 +383,18 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
     p.total_tiles = (uint64_t)p.chunks * ((n_outer + rpg - 1) / rpg);
     const unsigned grid = (unsigned)(p.total_tiles < cap ? p.total_tiles : cap);
     switch (mode) {
-      case LBT_ROUND_NEAREST: quantize_vec_kernel<0><<<grid, kThreads, 0, st>>>(p); break;
-      case LBT_ROUND_STOCHASTIC_NOISE: quantize_vec_kernel<1><<<grid, kThreads, 0, st>>>(p); break;
-      default: quantize_vec_kernel<2><<<grid, kThreads, 0, st>>>(p); break;
+      case LBT_ROUND_NEAREST:
+        if (minmax) quantize_vec_kernel<0, true><<<grid, kThreads, 0, st>>>(p);
+        else quantize_vec_kernel<0, false><<<grid, kThreads, 0, st>>>(p);
+        break;
+      case LBT_ROUND_STOCHASTIC_NOISE:
+        if (minmax) quantize_vec_kernel<1, true><<<grid, kThreads, 0, st>>>(p);
+        else quantize_vec_kernel<1, false><<<grid, kThreads, 0, st>>>(p);
+        break;
+      default:
+        if (minmax) quantize_vec_kernel<2, true><<<grid, kThreads, 0, st>>>(p);
+        else quantize_vec_kernel<2, false><<<grid, kThreads, 0, st>>>(p);
+        break;
     }
   } else {
     const uint64_t n = (uint64_t)n_outer * n_inner;

@@ -242,6 +242,8 @@ class QuantSite(nn.Module):
             kw.update(mode=Q.ROUND_NOISE, noise=rt.noise_fn(self, n_inner, x.device))
         else:
             kw.update(mode=Q.ROUND_PHILOX, seed=rt.seed, offset=Q.make_offset(self.qid, 0), dev_step=rt.dev_step)
+        if self.target == 0.0:      # the controller then only tests "any overflow": min/max statistics suffice
+            kw['mode'] |= Q.STATS_MINMAX
         return Q.quantize(x, self.bits, self.range, **kw)
 
     def extra_repr(self):
@@ -731,7 +733,7 @@ class _FusedBNFn(torch.autograd.Function):
         nz1, off1 = _site_args(norm.qX, x)
         _lib.call('lbt_bn_fwd_quant_stats', _lib.ptr(x), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
                   _lib.ptr(nz1), rt.seed, off1, _lib.ptr(rt.dev_step), _lib.ptr(k1), _lib.ptr(sums),
-                  _lib.ptr(norm.qX.counters), _lib.stream(), meta=dict(bytes=x.numel() * 5))
+                  _lib.ptr(norm.qX.counters), int(norm.qX.target == 0), _lib.stream(), meta=dict(bytes=x.numel() * 5))
         prep = _prepared(resc)
         if prep is not None:
             gq, bq = prep['gq'], prep['bq']
@@ -748,7 +750,7 @@ class _FusedBNFn(torch.autograd.Function):
                   float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
                   _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add),
                   1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
-                  _lib.ptr(norm.X_var_running), float(norm.momentum), _lib.stream(),
+                  _lib.ptr(norm.X_var_running), float(norm.momentum), int(resc.qX.target == 0), _lib.stream(),
                   meta=dict(bytes=x.numel() * (6 + (4 if add is not None else 0))))
         ctx.bn, ctx.relu_mode, ctx.has_add = bn, relu_mode, add is not None
         ctx.save_for_backward(k1, k2, sums, gq, bq, gamma, out if relu_mode == 2 else None)
@@ -773,7 +775,8 @@ class _FusedBNFn(torch.autograd.Function):
                   C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
                   _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
                   _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
-                  _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums), _lib.stream(),
+                  _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
+                  int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
                   meta=dict(bytes=g.numel() * (7 + (4 if ctx.relu_mode == 2 else 0) + (4 if ctx.has_add else 0))))
         dx = torch.empty_like(g)
         _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),

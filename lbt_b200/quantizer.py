@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 ROUND_NEAREST, ROUND_NOISE, ROUND_PHILOX = 0, 1, 2
+STATS_MINMAX = 0x100       # OR into the mode: min/max overflow statistics (exact enough for target_overflow_rate == 0)
 MANT_NONE, MANT_S8, MANT_U8, MANT_S16, MANT_S9C3 = 0, 1, 2, 3, 4
 _MANT_DTYPE = {MANT_S8: torch.int8, MANT_U8: torch.uint8, MANT_S16: torch.int16}
 _MANT_BYTES = {MANT_NONE: 0, MANT_S8: 1, MANT_U8: 1, MANT_S16: 2, MANT_S9C3: 6}     # per element, for the roofline
