@@ -1,0 +1,124 @@
+"""Config-3 GEMM / convolution microbench: TOPS of lbt_gemm_i8 and the implicit-GEMM convolution kernels vs the int8
+dense tensor-core peak (run on the GPU box).
+
+    python benchmarks/gemm_bench.py [--square 4096,8192,16384] [--layers resnet20|resnet18|none] [--out FILE]
+
+Ops = 2*M*N*K per launch.  Every timed launch is preceded by an L2 flush when --flush is given; by
+default launches run back to back (the square GEMMs are compute bound, operands >> L2 at 16384).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lbt_b200 import _lib, dfxp, gemm as G, quantizer as Q  # noqa: E402
+
+INT8_PEAK_TOPS = 4500.0     # B200 dense int8 nominal (B200_PROFILING.md); no measured int8 figure in MEASURED_PEAKS.json
+
+
+def timeit(fn, iters=10, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / iters
+    ts = []
+    for _ in range(iters):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def rand_i8(*shape, unsigned=False):
+    if unsigned:
+        return torch.randint(0, 256, shape, dtype=torch.uint8, device='cuda')
+    return torch.randint(-128, 128, shape, dtype=torch.int8, device='cuda')
+
+
+def bench_square(n, flush):
+    A, B = rand_i8(n, n, unsigned=True), rand_i8(n, n)
+    out = torch.empty(n, n, dtype=torch.float32, device='cuda')
+    t = timeit(lambda: G.gemm_i8(A, B, exp_const=-14, out=out), flush=flush)
+    return dict(kind='gemm', M=n, N=n, K=n, us=t * 1e6, tops=2 * n ** 3 / t / 1e12)
+
+
+def conv_case(N, H, W, Cin, Cout, k, s, flush, name):
+    """fprop / dgrad (stride 1) / wgrad of one Conv2d_q shape through the C ABI."""
+    OH, pt, _ = dfxp.same_pad(H, k, s)
+    OW, pl, _ = dfxp.same_pad(W, k, s)
+    x = rand_i8(N, H, W, Cin, unsigned=True)
+    g = rand_i8(N, OH, OW, Cout)
+    Kf = k * k * Cin
+    wt = torch.zeros(Cout, dfxp._pitch16(Kf), dtype=torch.int8, device='cuda')[:, :Kf]
+    wt.copy_(rand_i8(Cout, Kf))
+    ib = torch.tensor(2, dtype=torch.int32, device='cuda')
+    y = torch.empty(N * OH * OW, Cout, dtype=torch.float32, device='cuda')
+    rows = []
+    ops = 2 * N * OH * OW * Cout * Kf
+    if dfxp._implicit_ok(Cin, k, k):
+        t = timeit(lambda: dfxp._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, s, s, pt, pl, OH, OW, ib, ib, -15, None, y),
+                   flush=flush)
+        byts = x.numel() + y.numel() * 4
+        rows.append(dict(kind='fprop', layer=name, M=N * OH * OW, N=Cout, K=Kf, us=t * 1e6, tops=ops / t / 1e12,
+                         gbs=byts / t / 1e9))
+    if dfxp._implicit_ok(Cin, k, k) and dfxp._implicit_ok(Cout, 1, 1):
+        acc = torch.zeros(Kf, Cout, dtype=torch.int64, device='cuda')
+        t = timeit(lambda: _lib.call('lbt_conv_i8_wgrad', _lib.ptr(x), Q.MANT_U8, N, H, W, Cin, _lib.ptr(g), Q.MANT_S8, Cout,
+                                     k, k, s, s, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream()), flush=flush)
+        rows.append(dict(kind='wgrad', layer=name, M=Kf, N=Cout, K=N * OH * OW, us=t * 1e6, tops=ops / t / 1e12,
+                         gbs=(x.numel() + g.numel()) / t / 1e9))
+    return rows
+
+
+LAYERS = {
+    'resnet20': [(256, 32, 32, 16, 16, 3, 1, 's1 3x3 16->16'), (256, 32, 32, 16, 32, 3, 2, 's2 3x3 16->32 /2'),
+                 (256, 16, 16, 32, 32, 3, 1, 's2 3x3 32->32'), (256, 16, 16, 32, 64, 3, 2, 's3 3x3 32->64 /2'),
+                 (256, 8, 8, 64, 64, 3, 1, 's3 3x3 64->64')],
+    'resnet18': [(256, 56, 56, 64, 64, 3, 1, 'l1 3x3 64->64'), (256, 56, 56, 64, 128, 3, 2, 'l2 3x3 64->128 /2'),
+                 (256, 28, 28, 128, 128, 3, 1, 'l2 3x3 128->128'), (256, 28, 28, 128, 256, 3, 2, 'l3 3x3 128->256 /2'),
+                 (256, 14, 14, 256, 256, 3, 1, 'l3 3x3 256->256'), (256, 14, 14, 256, 512, 3, 2, 'l4 3x3 256->512 /2'),
+                 (256, 7, 7, 512, 512, 3, 1, 'l4 3x3 512->512')],
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--square', default='4096,8192,16384')
+    ap.add_argument('--layers', default='resnet20,resnet18')
+    ap.add_argument('--flush', action='store_true')
+    ap.add_argument('--out', default='gpurun_out/gemm_bench.json')
+    a = ap.parse_args()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda') if a.flush else None
+    rows = []
+    for n in [int(s) for s in a.square.split(',') if s]:
+        rows.append(bench_square(n, flush))
+    for fam in [f for f in a.layers.split(',') if f and f != 'none']:
+        for (N, H, W, Ci, Co, k, s, name) in LAYERS[fam]:
+            rows += conv_case(N, H, W, Ci, Co, k, s, flush, fam + ' ' + name)
+    for r in rows:
+        r['frac_int8_peak'] = r['tops'] / INT8_PEAK_TOPS
+        print('%-6s %-32s M=%-8d N=%-6d K=%-8d %9.1f us %8.1f TOPS (%.3f of %.0f)%s' % (
+            r['kind'], r.get('layer', 'square'), r['M'], r['N'], r['K'], r['us'], r['tops'], r['frac_int8_peak'],
+            INT8_PEAK_TOPS, '  %.0f GB/s' % r['gbs'] if 'gbs' in r else ''))
+    assert G.debug_error() == 0
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(dict(int8_peak_tops=INT8_PEAK_TOPS, flush=a.flush, rows=rows), open(a.out, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()

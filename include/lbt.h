@@ -123,6 +123,22 @@ int lbt_update_ranges(int32_t* ranges, uint64_t* counters, const int32_t* bits, 
 /* *dev_step += 1 (one thread); keeps the step counter on the device for graph replay. */
 int lbt_step_advance(uint64_t* dev_step, void* stream);
 
+/*
+ * One `weight_quantization(..., stochastic=True)` call site (dynamic_fixed_point.py:4-45) as the fused kernels
+ * see it: the quantiser's width, its `*_range` variable, its noise (explicit tensor [n_inner], or NULL = the
+ * in-kernel Philox stream keyed by (seed, offset + (*dev_step << 32)), identical to lbt_noise_fill) and its
+ * statistics block.  Host struct, passed by pointer; every pointer inside is a device pointer.
+ */
+typedef struct lbt_qsite {
+  int32_t bits;          /* total mantissa bits incl. sign */
+  int32_t stats_minmax;  /* 1: LBT_STATS_MINMAX statistics (valid for target_overflow_rate == 0) */
+  const int32_t* ib;     /* integer_bits (read only; the controller runs in lbt_update_ranges) */
+  const float* noise;
+  uint64_t seed, offset;
+  const uint64_t* dev_step; /* may be NULL */
+  uint64_t* counters;       /* uint64[LBT_CNT_WORDS], may be NULL */
+} lbt_qsite;
+
 /* Epilogue of lbt_gemm_i8. */
 enum lbt_gemm_epilogue {
   LBT_EPI_F32 = 0,  /* out_f32[m*ldc+n] = fp32(acc) * 2^e (+ bias[n]),  e = exp_const + *ibA + *ibB */
@@ -141,11 +157,17 @@ enum lbt_gemm_epilogue {
  *         Result == RN_fp32(exact_dot * 2^e) bit for bit.  K <= 65536.
  *   LBT_EPI_ACC64: K is cut into k_splits chunks (each <= 65536) spread over the SMs; partial sums are
  *         added to acc64 (caller zeroes it) scaled by the integer alpha.  Finish with lbt_acc64_finalize.
+ *   q_out != NULL (LBT_EPI_F32 only, N % 4 == 0): the fused re-quantising epilogue.  Instead of storing the
+ *         fp32 result v, the kernel stores k_out[m*N + n] = Q_site(v) (s8, stochastic) and adds the exact
+ *         per-column sums[n] += k, sums[N + n] += k*k (int64, caller-zeroed) plus the site's overflow
+ *         statistics: Normalization_q's input quantiser + batch moments (dfxp:584-588) folded into the GEMM
+ *         that produces its input.  The noise index of element (m, n) is (m % rows_per_image) * N + n.
+ *         out_f32 may be NULL.
  */
 int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M,
                 size_t N, size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const,
                 const float* bias, float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits,
-                void* stream);
+                const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, size_t rows_per_image, void* stream);
 
 /*
  * out[i] = fp32(acc64[i]) * 2^(exp_const + *ibA + *ibB) (+ add_scale * add[i]) — the wgrad tail
@@ -177,11 +199,13 @@ int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W, int C, int
  *   src[N,H,W,C] s8|u8, C in {16, 32, 64} or a multiple of 128;  wp[Cout, kh*kw*C] packed K-major
  *   (k = (r*kw + s)*C + c, row pitch ldw bytes);  out[N*OH*OW, Cout] fp32 (row pitch ldc floats):
  *   out = fp32(acc) * 2^(exp_const + *ib_src + *ib_w) (+ bias[co]).  kh*kw*C <= 65536.
+ *   q_out != NULL (Cout % 4 == 0): fused re-quantising epilogue as in lbt_gemm_i8 — k_out[N*OH*OW, Cout] s8,
+ *   sums[2*Cout], rows_per_image = OH*OW; `out` may then be NULL.
  */
 int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind,
                       size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
                       int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
-                      float* out, size_t ldc, void* stream);
+                      float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, void* stream);
 
 /*
  * Implicit-GEMM weight gradient: acc64[(r*kw+s)*C + c, co] += alpha * sum over output pixels m of
@@ -278,13 +302,18 @@ int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_inner, int C
  * k2 = Q_rescale(y1) (dfxp:677); out = xq2 * gamma_q + beta_q (dfxp:683) [+ add] [ReLU, dfxp:986].
  * Optionally writes the batch moments and updates the running averages (momentum*avg + (1-momentum)*batch,
  * dfxp:602-612).  gamma_q / beta_q are the fake-quantised vectors (lbt_quantize, dfxp:679-682).
+ * q_next != NULL: the module output is additionally quantised with the CONSUMING layer's input quantiser
+ * (Conv2d_q's `Xq`, dfxp:287: bits+1, stochastic) and stored as mantissas next_mant (next_kind LBT_MANT_U8 for a
+ * 9-bit non-negative tensor, LBT_MANT_S8 for <= 8 bits), with that site's overflow statistics; `out` may then
+ * be NULL when no other consumer needs the fp32 tensor.
  */
 int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
                      const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
                      uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                      const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                      float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                     float momentum, int stats_minmax, void* stream);
+                     float momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                     void* stream);
 /*
  * bwd 1: g (w.r.t. the module output) -> ReLU mask (relu: 0 none, 1 recomputed from k2, 2 from `out`)
  * [-> d_add = masked g] -> kg2 = Q(g) (dfxp:687) -> sums[0..C) = sum kg2 (dbeta, :690),
@@ -301,10 +330,12 @@ int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int
 /*
  * bwd 2: dx = (gq1 - mean(gq1) - xhat * mean(gq1 * xhat)) / sqrt(var + eps), the batch-norm VJP that
  * tf.gradients(y, X, gradq) yields for dfxp:616 (dfxp:623), from kg1, k1 and the two sum buffers.
+ * q_grad != NULL: dx is quantised on the spot with the PRODUCING convolution's gradient quantiser (`gradq`,
+ * dfxp:300) into g_mant (s8) with that site's statistics; `dx` may then be NULL.
  */
 int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
                      const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
-                     const int64_t* bwd_sums, float* dx, void* stream);
+                     const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream);
 
 #ifdef __cplusplus
 }

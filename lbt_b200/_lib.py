@@ -26,12 +26,13 @@ SIGNATURES = {
     'lbt_update_ranges': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'lbt_step_advance': (c_int, [c_void_p, c_void_p]),
     'lbt_gemm_i8': (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_int,
-                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+                            c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'lbt_acc64_finalize': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p,
                                    c_void_p]),
     'lbt_im2col_i8': (c_int, [c_void_p, c_int] + [c_int] * 13 + [c_void_p, c_size_t, c_void_p]),
     'lbt_conv_i8_fprop': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_size_t] + [c_int] * 9 +
-                          [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                          [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     'lbt_conv_i8_wgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_int] * 9 +
                           [c_void_p, c_int, c_int, c_void_p]),
     'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
@@ -44,13 +45,14 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'lbt_bn_fwd_apply': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                  c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                                 c_void_p, c_void_p, c_int, c_void_p]),
     'lbt_bn_bwd_quant_stats': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,
                                        c_void_p, c_void_p, c_u64, c_void_p, c_u64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
-                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 # not part of the public header: tuning knobs used by bench sweeps
@@ -69,6 +71,12 @@ class FinalizeJob(ctypes.Structure):
     """lbt_finalize_job (include/lbt.h)."""
     _fields_ = [('acc64', c_void_p), ('n', c_u64), ('ibA', c_void_p), ('ibB', c_void_p), ('exp_const', ctypes.c_int32),
                 ('add_scale', c_float), ('add', c_void_p), ('out', c_void_p), ('start', c_u64)]
+
+
+class QSiteStruct(ctypes.Structure):
+    """lbt_qsite (include/lbt.h): one quantiser call site as the fused kernels see it."""
+    _fields_ = [('bits', ctypes.c_int32), ('stats_minmax', ctypes.c_int32), ('ib', c_void_p), ('noise', c_void_p),
+                ('seed', c_u64), ('offset', c_u64), ('dev_step', c_void_p), ('counters', c_void_p)]
 
 
 class PrepJob(ctypes.Structure):

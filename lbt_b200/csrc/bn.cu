@@ -14,7 +14,7 @@
 // n_inner = H*W*C]; the rounding noise is indexed by the inner position and shared over N (dfxp:36).
 // A thread owns 4 consecutive channels of one inner position and walks down N, so its Philox draw and
 // its per-channel partial sums live in registers.
-#include "common.cuh"
+#include "qsite.cuh"
 
 namespace lbt {
 namespace {
@@ -29,62 +29,6 @@ struct Tiling {
   uint64_t total_tiles;
   int fixed_channels;  // 1: a thread sees the same 4 channels in every tile (256 % (C/4) == 0)
 };
-
-struct QSite {
-  int bits;
-  const int32_t* ib;
-  const float* noise;  // explicit noise [n_inner] or NULL -> Philox
-  uint64_t seed, offset;
-  const uint64_t* dev_step;
-  unsigned long long* counters;
-  int minmax;  // 1: min/max statistics (target_overflow_rate == 0)
-};
-
-struct QC {
-  float m, inv_m, L, hi, half;
-};
-
-__device__ __forceinline__ QC make_qc(int bits, int ib) {
-  QC c;
-  int f = bits - ib - 1;
-  f = max(-126, min(126, f));
-  c.m = exp2i(f);
-  c.inv_m = exp2i(-f);
-  c.L = exp2i(bits - 1);
-  c.hi = c.L - 1.0f;
-  c.half = c.L * 0.5f;
-  return c;
-}
-
-// stochastic_identity (dfxp:34-37) + overflow counters (dfxp:60-66); returns the integral mantissa as float
-__device__ __forceinline__ float squant(float x, float u, const QC& c, uint32_t& n1, uint32_t& n2) {
-  const float y = __fmul_rn(x, c.m);
-  n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
-  n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
-  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
-}
-
-// min/max variant of the statistics (LBT_STATS_MINMAX): two FMNMX instead of four compares + adds
-__device__ __forceinline__ float squant_mm(float x, float u, const QC& c, float& mx, float& mn) {
-  const float y = __fmul_rn(x, c.m);
-  mx = fmaxf(mx, y);
-  mn = fminf(mn, y);
-  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
-}
-__device__ __forceinline__ void mm_to_counts(const QC& c, float mx, float mn, uint32_t& n1, uint32_t& n2) {
-  n1 = (mx >= c.L || mn < -c.L) ? 1u : 0u;
-  n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
-}
-
-__device__ __forceinline__ float4 site_noise(const QSite& s, uint32_t v, uint64_t off) {
-  if (s.noise) return __ldg(reinterpret_cast<const float4*>(s.noise) + v);
-  return philox_noise4(v, s.seed, off);
-}
-__device__ __forceinline__ uint64_t site_offset(const QSite& s) {
-  uint64_t off = s.offset;
-  if (s.dev_step) off += (*s.dev_step) << 32;
-  return off;
-}
 
 __device__ __forceinline__ void publish_counters(unsigned long long* counters, uint32_t n1, uint32_t n2, size_t numel,
                                                  uint32_t* s_red) {
@@ -285,6 +229,8 @@ struct Fwd2Params {
   float* run_mean;        // [C] optional, updated in place with `momentum` (dfxp:602-612)
   float* run_var;
   float momentum;
+  QSite q3;               // optional: the consuming layer's input quantiser (bits == 0: off)
+  uint8_t* next_mant;     // its mantissas (u8 for a 9-bit non-negative tensor, s8 otherwise: same byte)
 };
 
 __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
@@ -315,6 +261,16 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
   const bool mm = p.q2.minmax != 0;
+  const bool nxt = p.q3.bits != 0;
+  QC c3 = c2;
+  uint64_t off3 = 0;
+  if (nxt) {
+    c3 = make_qc(p.q3.bits, *reinterpret_cast<volatile const int32_t*>(p.q3.ib));
+    off3 = site_offset(p.q3);
+  }
+  uint32_t m1 = 0, m2 = 0;
+  float mx3 = -INFINITY, mn3 = INFINITY;
+  const bool mm3 = p.q3.minmax != 0;
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -322,6 +278,11 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
     const int c0 = (int)((4ull * v) % (uint64_t)C);
     const float4 u = site_noise(p.q2, v, off);
     const float un[4] = {u.x, u.y, u.z, u.w};
+    float u3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nxt) {
+      const float4 t = site_noise(p.q3, v, off3);
+      u3[0] = t.x; u3[1] = t.y; u3[2] = t.z; u3[3] = t.w;
+    }
     float mean[4], den[4], g[4], b[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -360,12 +321,22 @@ __global__ void __launch_bounds__(kThreads) bn_fwd2_kernel(const Fwd2Params p) {
             o[j] = y2;
           }
           *reinterpret_cast<uint32_t*>(p.k2 + idx) = pack4(k2);
-          *reinterpret_cast<float4*>(p.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.out) *reinterpret_cast<float4*>(p.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (nxt) {                                                          // the consumer's Xq, dfxp:287
+            float k3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) k3[j] = mm3 ? squant_mm(o[j], u3[j], c3, mx3, mn3) : squant(o[j], u3[j], c3, m1, m2);
+            *reinterpret_cast<uint32_t*>(p.next_mant + idx) = pack4(k3);
+          }
         }
     }
   }
   if (mm) mm_to_counts(c2, mx, mn, n1, n2);
   publish_counters(p.q2.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
+  if (nxt) {
+    if (mm3) mm_to_counts(c3, mx3, mn3, m1, m2);
+    publish_counters(p.q3.counters, m1, m2, p.t.n_outer * p.t.n_inner, s_red);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -487,12 +458,25 @@ struct Bwd2Params {
   int bitsg1;
   const int32_t* ibg1;
   const long long* bsums;  // [4*C] backward sums (uses [2C..4C))
-  float* dx;
+  float* dx;               // may be NULL when qg is on
+  QSite qg;                // optional: the producing convolution's gradient quantiser (bits == 0: off)
+  int8_t* g_mant;
 };
 
 __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   extern __shared__ float s_par[];  // [5*C]: mean, 1/den, mean_g, mean_gxhat, (unused)
+  __shared__ uint32_t s_red[16];
   const int C = p.t.C;
+  const bool gq_on = p.qg.bits != 0;
+  QC cq = make_qc(8, 0);
+  uint64_t offq = 0;
+  if (gq_on) {
+    cq = make_qc(p.qg.bits, *reinterpret_cast<volatile const int32_t*>(p.qg.ib));
+    offq = site_offset(p.qg);
+  }
+  uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  const bool mmq = p.qg.minmax != 0;
   const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
   const QC cg = make_qc(p.bitsg1, *reinterpret_cast<volatile const int32_t*>(p.ibg1));
   const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
@@ -524,6 +508,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
       mg[j] = s_par[2 * C + c0 + j];
       mgx[j] = s_par[3 * C + c0 + j];
     }
+    float uq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gq_on) {
+      const float4 t = site_noise(p.qg, v, offq);
+      uq[0] = t.x; uq[1] = t.y; uq[2] = t.z; uq[3] = t.w;
+    }
     const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
     for (size_t r = r0; r < r1; r += kRows) {
       uint32_t wg[kRows], w1[kRows];
@@ -549,9 +538,19 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
             // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616)
             o[j] = __fdiv_rn(gq - mg[j] - xhat * mgx[j], den[j]);
           }
-          *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (gq_on) {                                                        // the convolution's gradq, dfxp:300
+            float kq[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) kq[j] = mmq ? squant_mm(o[j], uq[j], cq, mx, mn) : squant(o[j], uq[j], cq, n1, n2);
+            *reinterpret_cast<uint32_t*>(p.g_mant + idx) = pack4(kq);
+          }
         }
     }
+  }
+  if (gq_on) {
+    if (mmq) mm_to_counts(cq, mx, mn, n1, n2);
+    publish_counters(p.qg.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
   }
 }
 
@@ -639,12 +638,21 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
                                 uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                                 const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                                 float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                                float momentum, int stats_minmax, void* stream) {
-  if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2 || !out) return LBT_EINVAL;
+                                float momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                                void* stream) {
+  if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2) return LBT_EINVAL;
+  if (!out && !q_next) return LBT_EINVAL;
   if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
+  if (q_next) {
+    if (!next_mant || !q_next->ib || !al4(next_mant) || (q_next->noise && !al16(q_next->noise))) return LBT_EINVAL;
+    // u8 holds a 9-bit mantissa only when the tensor is non-negative, i.e. the ReLU is fused here
+    if (next_kind == LBT_MANT_U8 ? (q_next->bits < 2 || q_next->bits > 9 || !relu)
+                                 : (next_kind != LBT_MANT_S8 || q_next->bits < 2 || q_next->bits > 8))
+      return LBT_EUNSUPPORTED;
+  }
   if ((run_mean == nullptr) != (run_var == nullptr)) return LBT_EINVAL;
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
-  if (!al4(k1) || !al4(k2) || !al16(out) || (add && !al16(add)) || (noise2 && !al16(noise2))) return LBT_EUNSUPPORTED;
+  if (!al4(k1) || !al4(k2) || (out && !al16(out)) || (add && !al16(add)) || (noise2 && !al16(noise2))) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   Fwd2Params p{};
   unsigned grid;
@@ -667,6 +675,8 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.run_mean = run_mean;
   p.run_var = run_var;
   p.momentum = momentum;
+  p.q3 = site_from_abi(q_next);
+  p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
   const size_t smem = (size_t)4 * C * 4;
   if ((rc = set_smem(bn_fwd2_kernel, smem))) return rc;
   bn_fwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
@@ -714,10 +724,15 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
 
 extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
                                 const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
-                                const int64_t* bwd_sums, float* dx, void* stream) {
-  if (!kg1 || !k1 || !ib1 || !fwd_sums || !ib_g1 || !bwd_sums || !dx) return LBT_EINVAL;
+                                const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream) {
+  if (!kg1 || !k1 || !ib1 || !fwd_sums || !ib_g1 || !bwd_sums) return LBT_EINVAL;
+  if (!dx && !q_grad) return LBT_EINVAL;
+  if (q_grad) {
+    if (!g_mant || !q_grad->ib || !al4(g_mant) || (q_grad->noise && !al16(q_grad->noise))) return LBT_EINVAL;
+    if (q_grad->bits < 2 || q_grad->bits > 8) return LBT_EUNSUPPORTED;
+  }
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
-  if (!al4(kg1) || !al4(k1) || !al16(dx)) return LBT_EUNSUPPORTED;
+  if (!al4(kg1) || !al4(k1) || (dx && !al16(dx))) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   Bwd2Params p{};
   unsigned grid;
@@ -733,6 +748,8 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   p.ibg1 = ib_g1;
   p.bsums = reinterpret_cast<const long long*>(bwd_sums);
   p.dx = dx;
+  p.qg = site_from_abi(q_grad);
+  p.g_mant = g_mant;
   const size_t smem = (size_t)4 * C * 4;
   if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
   bn_bwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);

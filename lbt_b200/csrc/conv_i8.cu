@@ -14,6 +14,7 @@
 // Channel chunk Cb = min(C, 128) in {16, 32, 64, 128} selects the shared-memory layout: 16-byte rows of
 // interleaved 8x16B core matrices, or 32/64/128-byte swizzled rows; a pipeline stage always carries 128 bytes
 // of K per row (128/Cb tap-blocks), i.e. four K=32 MMAs.  Same warp roles and mbarrier protocol as gemm_i8.cu.
+#include "qsite.cuh"
 #include "tcgen05.cuh"
 
 namespace lbt {
@@ -47,6 +48,7 @@ struct ConvParams {
   float* out;
   size_t ldc;
   uint32_t idesc;
+  BnqParams bnq;                 // fused re-quantising epilogue (bnq.q.bits == 0: off)
 };
 
 template <int BN>
@@ -79,6 +81,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty_bar[C::kAccStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
+  __shared__ int s_stat[4][2 * BN];              // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -192,6 +195,16 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
+    const bool fused = p.bnq.q.bits != 0;
+    int* my_stat = s_stat[quad];
+    BnqState bst;
+    bst.tiles = 0;
+    uint32_t stat_ntile = 0;
+    if (fused) {
+      bst.init(p.bnq);
+      for (int i = lane; i < 2 * BN; i += 32) my_stat[i] = 0;
+      __syncwarp();
+    }
     uint32_t acc = 0, acc_phase = 0;
     bool ok = true;
     for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
@@ -203,12 +216,28 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
       const uint32_t col0 = n_tile * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
+        bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+        stat_ntile = n_tile;
+        bst.tiles = 0;
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
-        if (row < p.M && col0 + c < p.N) {
+        if (fused) {
+          if (col0 + c < p.N) {   // warp-uniform
+            const uint32_t ncol = min(16u, p.N - (col0 + c));
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[j] = __int2float_rn((int)v[j]) * scale;
+              if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+            }
+            bnq_chunk(p.bnq, bst, f, row, row < p.M, col0 + c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+          }
+        } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));
           float* o = p.out + (size_t)row * p.ldc + col0 + c;
           float f[16];
@@ -227,6 +256,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      ++bst.tiles;
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -234,6 +264,10 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if (fused) {
+      bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, quad == 0, lane);
     }
   }
 
@@ -469,8 +503,15 @@ using namespace lbt;
 extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind,
                                  size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
                                  int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
-                                 float* out, size_t ldc, void* stream) {
-  if (!src || !wp || !out) return LBT_EINVAL;
+                                 float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
+                                 void* stream) {
+  if (!src || !wp) return LBT_EINVAL;
+  if (q_out) {
+    if (!k_out || !sums || !q_out->ib) return LBT_EINVAL;
+    if (q_out->bits < 2 || q_out->bits > 8 || (Cout & 3)) return LBT_EUNSUPPORTED;
+  } else if (!out) {
+    return LBT_EINVAL;
+  }
   if ((src_kind != LBT_MANT_S8 && src_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
     return LBT_EINVAL;
@@ -479,7 +520,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (cb != 16 && cb != 32 && cb != 64 && cb != 128) return LBT_EUNSUPPORTED;
   if (C % cb) return LBT_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15) || (ldw & 15)) return LBT_EUNSUPPORTED;
-  if (ldc < (size_t)Cout) return LBT_EINVAL;
+  if (!q_out && ldc < (size_t)Cout) return LBT_EINVAL;
   const size_t Ktot = (size_t)kh * kw * C;
   if (ldw < Ktot) return LBT_EINVAL;
   if (Ktot > 65536) return LBT_EUNSUPPORTED;  // exactness bound of one s32 accumulator
@@ -525,6 +566,10 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   p.out = out;
   p.ldc = ldc;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
+  p.bnq.q = site_from_abi(q_out);
+  p.bnq.k = k_out;
+  p.bnq.sums = reinterpret_cast<long long*>(sums);
+  p.bnq.rows_per_image = (uint32_t)(OH * OW);
 
   // A: im2col map over (C, W, H, N).  The bounding box of base pixels is [lower, dim + upper): with
   // lower = -pad_before and upper = pad_after - (k - 1) it has exactly (out - 1) * stride + 1 positions.

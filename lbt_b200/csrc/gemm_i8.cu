@@ -18,7 +18,7 @@
 //                 bit-reproducible; per-split K <= 65536 keeps the s32 partial exact)
 #include <cuda.h>
 
-#include "common.cuh"
+#include "qsite.cuh"
 
 namespace lbt {
 namespace {
@@ -44,6 +44,7 @@ struct GemmParams {
   long long* acc64;
   int alpha;
   uint32_t idesc;
+  BnqParams bnq;  // fused re-quantising epilogue (bnq.q.bits == 0: off)
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -165,6 +166,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
+  __shared__ int s_stat[4][2 * BN];  // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -258,6 +260,16 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
+    const bool fused = p.bnq.q.bits != 0;   // host guarantees LBT_EPI_F32 and k_splits == 1
+    int* my_stat = s_stat[quad];
+    BnqState bst;
+    bst.tiles = 0;
+    uint32_t stat_ntile = 0;
+    if (fused) {
+      bst.init(p.bnq);
+      for (int i = lane; i < 2 * BN; i += 32) my_stat[i] = 0;
+      __syncwarp();
+    }
     uint32_t acc = 0, acc_phase = 0;
     bool ok = true;
     for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
@@ -270,12 +282,29 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
       const uint32_t col0 = n_tile * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
+        bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+        stat_ntile = n_tile;
+        bst.tiles = 0;
+      }
+      ++bst.tiles;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
-        if (row < p.M && col0 + c < p.N) {
+        if (fused) {
+          if (col0 + c < p.N) {  // warp-uniform
+            const uint32_t ncol = min(16u, p.N - (col0 + c));
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[j] = __int2float_rn((int)v[j]) * scale;
+              if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+            }
+            bnq_chunk(p.bnq, bst, f, row, row < p.M, col0 + c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+          }
+        } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));
           if (p.epilogue == LBT_EPI_F32) {
             float* o = p.out + (size_t)row * p.ldc + col0 + c;
@@ -311,6 +340,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc = 0;
         acc_phase ^= 1;
       }
+    }
+    if (fused) {
+      bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, quad == 0, lane);
     }
   }
 
@@ -393,13 +426,18 @@ using namespace lbt;
 
 extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M, size_t N,
                            size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
-                           float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits, void* stream) {
+                           float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits, const lbt_qsite* q_out,
+                           int8_t* k_out, int64_t* sums, size_t rows_per_image, void* stream) {
   if (!A || !B) return LBT_EINVAL;
+  if (q_out) {
+    if (epilogue != LBT_EPI_F32 || !k_out || !sums || !q_out->ib || rows_per_image == 0) return LBT_EINVAL;
+    if (q_out->bits < 2 || q_out->bits > 8 || (N & 3) || rows_per_image > 0xffffffffull) return LBT_EUNSUPPORTED;
+  }
   if ((a_kind != LBT_MANT_S8 && a_kind != LBT_MANT_U8) || (b_kind != LBT_MANT_S8 && b_kind != LBT_MANT_U8)) return LBT_EINVAL;
-  if (epilogue == LBT_EPI_F32 ? !out_f32 : (epilogue == LBT_EPI_ACC64 ? !acc64 : true)) return LBT_EINVAL;
+  if (epilogue == LBT_EPI_F32 ? (!out_f32 && !q_out) : (epilogue == LBT_EPI_ACC64 ? !acc64 : true)) return LBT_EINVAL;
   if (M == 0 || N == 0) return LBT_OK;
   if (K == 0) return LBT_EINVAL;
-  if (ldc < N) return LBT_EINVAL;
+  if (!q_out && ldc < N) return LBT_EINVAL;
   if (lda < K || ldb < K || (lda & 15) || (ldb & 15)) return LBT_EUNSUPPORTED;  // TMA: 16-byte row pitch
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return LBT_EUNSUPPORTED;
   if (M >= (1ull << 31) || N >= (1ull << 31) || K >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -440,6 +478,10 @@ extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B,
   p.ldc = ldc;
   p.acc64 = reinterpret_cast<long long*>(acc64);
   p.alpha = alpha;
+  p.bnq.q = site_from_abi(q_out);
+  p.bnq.k = k_out;
+  p.bnq.sums = reinterpret_cast<long long*>(sums);
+  p.bnq.rows_per_image = (uint32_t)rows_per_image;
   // instruction descriptor: c_format s32 (2) @4, a_format @7, b_format @10 (0 = u8, 1 = s8), K-major A and B,
   // N>>3 @17, M>>4 @24
   p.idesc = (2u << 4) | ((a_kind == LBT_MANT_S8 ? 1u : 0u) << 7) | ((b_kind == LBT_MANT_S8 ? 1u : 0u) << 10) |

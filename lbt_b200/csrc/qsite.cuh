@@ -1,0 +1,223 @@
+// Quantiser call sites shared by the fused kernels (bn.cu, conv_i8.cu, gemm_i8.cu): the arithmetic of
+// stochastic_identity + overflow_rate (/root/reference/dynamic_fixed_point.py:32-38, 48-67) on one value, and
+// the fused "quantise + per-channel statistics" epilogue of the tensor-core kernels (Normalization_q's input
+// quantiser applied to the accumulators, dfxp:584-588).
+#pragma once
+
+#include "common.cuh"
+
+namespace lbt {
+
+struct QSite {
+  int bits;
+  const int32_t* ib;
+  const float* noise;  // explicit noise [n_inner] or NULL -> Philox
+  uint64_t seed, offset;
+  const uint64_t* dev_step;
+  unsigned long long* counters;
+  int minmax;  // 1: min/max statistics (target_overflow_rate == 0)
+};
+
+struct QC {
+  float m, inv_m, L, hi, half;
+};
+
+__device__ __forceinline__ QC make_qc(int bits, int ib) {
+  QC c;
+  int f = bits - ib - 1;
+  f = max(-126, min(126, f));
+  c.m = exp2i(f);
+  c.inv_m = exp2i(-f);
+  c.L = exp2i(bits - 1);
+  c.hi = c.L - 1.0f;
+  c.half = c.L * 0.5f;
+  return c;
+}
+
+// stochastic_identity (dfxp:34-37) + overflow counters (dfxp:60-66); returns the integral mantissa as float
+__device__ __forceinline__ float squant(float x, float u, const QC& c, uint32_t& n1, uint32_t& n2) {
+  const float y = __fmul_rn(x, c.m);
+  n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
+  n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
+  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+
+// min/max variant of the statistics (LBT_STATS_MINMAX): two FMNMX instead of four compares + adds
+__device__ __forceinline__ float squant_mm(float x, float u, const QC& c, float& mx, float& mn) {
+  const float y = __fmul_rn(x, c.m);
+  mx = fmaxf(mx, y);
+  mn = fminf(mn, y);
+  return floorf(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi));
+}
+__device__ __forceinline__ void mm_to_counts(const QC& c, float mx, float mn, uint32_t& n1, uint32_t& n2) {
+  n1 = (mx >= c.L || mn < -c.L) ? 1u : 0u;
+  n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
+}
+
+__device__ __forceinline__ float4 site_noise(const QSite& s, uint32_t v, uint64_t off) {
+  if (s.noise) return __ldg(reinterpret_cast<const float4*>(s.noise) + v);
+  return philox_noise4(v, s.seed, off);
+}
+__device__ __forceinline__ uint64_t site_offset(const QSite& s) {
+  uint64_t off = s.offset;
+  if (s.dev_step) off += (*s.dev_step) << 32;
+  return off;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fused "quantise + batch statistics" epilogue of the tensor-core kernels: BN forward pass 1
+// (k = Q_norm(conv output), per-channel sum k and sum k^2; dfxp:584-588) applied to the accumulators while
+// they are still in registers, so the fp32 convolution output never touches HBM.
+// An epilogue thread owns one output row (pixel) and 16 consecutive channels per chunk.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBnqFlushTiles = 2048;  // 32 rows * 2^14 per tile and channel: int32 partials stay exact
+
+struct BnqParams {
+  QSite q;                  // bits == 0: disabled
+  int8_t* k;                // [M, N] mantissas, row pitch N
+  long long* sums;          // [2*N]: sum k, sum k^2 per channel (caller-zeroed)
+  uint32_t rows_per_image;  // OH*OW: noise index = (row % rows_per_image) * N + col  (noise is shared over the batch)
+};
+
+struct BnqState {
+  QC qc;
+  uint64_t off;
+  uint32_t n1, n2;
+  float mx, mn;
+  uint32_t tiles;
+  __device__ __forceinline__ void init(const BnqParams& b) {
+    qc = make_qc(b.q.bits, *reinterpret_cast<volatile const int32_t*>(b.q.ib));
+    off = site_offset(b.q);
+    n1 = n2 = 0;
+    mx = -INFINITY;
+    mn = INFINITY;
+    tiles = 0;
+  }
+};
+
+// Sum 16 per-lane values over the 32 lanes of a warp with a reduce-scatter butterfly (16 shuffles):
+// afterwards lanes 2c and 2c+1 both hold the warp total of v[c], c = (lane >> 1) & 15.
+__device__ __forceinline__ int warp_colsum16(const int (&v)[16], int lane) {
+  int w8[8], w4[4], w2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int send = b4 ? v[j] : v[j + 8];
+    const int recv = __shfl_xor_sync(0xffffffffu, send, 16);
+    w8[j] = (b4 ? v[j + 8] : v[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int send = b3 ? w8[j] : w8[j + 4];
+    const int recv = __shfl_xor_sync(0xffffffffu, send, 8);
+    w4[j] = (b3 ? w8[j + 4] : w8[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int send = b2 ? w4[j] : w4[j + 2];
+    const int recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    w2[j] = (b2 ? w4[j + 2] : w4[j]) + recv;
+  }
+  const int send = b1 ? w2[0] : w2[1];
+  const int recv = __shfl_xor_sync(0xffffffffu, send, 2);
+  int w1 = (b1 ? w2[1] : w2[0]) + recv;
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  return w1;
+}
+
+// One 16-channel chunk of one row.  f: the fp32 values the unfused path would have written (acc * 2^e).
+// row_ok / ncol mask the tile tails (masked elements quantise the value 0: no counts, no sums).
+// s_stat: this WARP's private [2][bn] int32 partial sums (bn = tile width); tcol = first column of the chunk inside the tile.
+__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const float (&f)[16], uint32_t row, bool row_ok,
+                                          uint32_t col, uint32_t ncol, uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+  const uint64_t inner = (uint64_t)(row % b.rows_per_image) * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
+  int ki[16], kq[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float4 u;
+    if (b.q.noise) u = row_ok && 4u * g < ncol ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else u = philox_noise4((inner >> 2) + g, b.q.seed, st.off);
+    const float un[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = 4 * g + t;
+      const float x = (row_ok && (uint32_t)j < ncol) ? f[j] : 0.0f;
+      const float kf = b.q.minmax ? squant_mm(x, un[t], st.qc, st.mx, st.mn) : squant(x, un[t], st.qc, st.n1, st.n2);
+      const int k = (row_ok && (uint32_t)j < ncol) ? __float2int_rn(kf) : 0;
+      ki[j] = k;
+      kq[j] = k * k;
+    }
+  }
+  if (row_ok) {
+    int8_t* o = b.k + (size_t)row * N + col;
+    if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+      uint4 w;
+      w.x = (uint32_t)(ki[0] & 0xff) | ((uint32_t)(ki[1] & 0xff) << 8) | ((uint32_t)(ki[2] & 0xff) << 16) | ((uint32_t)(ki[3] & 0xff) << 24);
+      w.y = (uint32_t)(ki[4] & 0xff) | ((uint32_t)(ki[5] & 0xff) << 8) | ((uint32_t)(ki[6] & 0xff) << 16) | ((uint32_t)(ki[7] & 0xff) << 24);
+      w.z = (uint32_t)(ki[8] & 0xff) | ((uint32_t)(ki[9] & 0xff) << 8) | ((uint32_t)(ki[10] & 0xff) << 16) | ((uint32_t)(ki[11] & 0xff) << 24);
+      w.w = (uint32_t)(ki[12] & 0xff) | ((uint32_t)(ki[13] & 0xff) << 8) | ((uint32_t)(ki[14] & 0xff) << 16) | ((uint32_t)(ki[15] & 0xff) << 24);
+      *reinterpret_cast<uint4*>(o) = w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if ((uint32_t)j < ncol) o[j] = (int8_t)ki[j];
+    }
+  }
+  const int t0 = warp_colsum16(ki, lane), t1 = warp_colsum16(kq, lane);
+  if ((lane & 1) == 0) {
+    const int c = (lane >> 1) & 15;
+    s_stat[tcol + c] += t0;
+    s_stat[bn + tcol + c] += t1;
+  }
+}
+
+// Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.
+__device__ __forceinline__ void bnq_flush(const BnqParams& b, int* s_stat, uint32_t col0, uint32_t bn, uint32_t N, int lane) {
+  __syncwarp();
+  for (uint32_t i = lane; i < bn; i += 32) {
+    const int v0 = s_stat[i], v1 = s_stat[bn + i];
+    if (col0 + i < N) {
+      if (v0) atomicAdd(reinterpret_cast<unsigned long long*>(b.sums) + col0 + i, (unsigned long long)(long long)v0);
+      if (v1) atomicAdd(reinterpret_cast<unsigned long long*>(b.sums) + N + col0 + i, (unsigned long long)(long long)v1);
+    }
+    s_stat[i] = 0;
+    s_stat[bn + i] = 0;
+  }
+  __syncwarp();
+}
+
+// End of the kernel: publish the overflow statistics; `ticket` (one warp per CTA) runs the CTA ticket that adds numel.
+__device__ __forceinline__ void bnq_finish(const BnqParams& b, BnqState& st, unsigned long long numel, bool ticket, int lane) {
+  if (b.q.minmax) mm_to_counts(st.qc, st.mx, st.mn, st.n1, st.n2);
+  const uint32_t n1 = warp_sum(st.n1), n2 = warp_sum(st.n2);
+  if (lane == 0 && b.q.counters) {
+    if (n1) atomicAdd(b.q.counters + LBT_CNT_OVER, (unsigned long long)n1);
+    if (n2) atomicAdd(b.q.counters + LBT_CNT_OVER_HALF, (unsigned long long)n2);
+    if (ticket) {
+      __threadfence();
+      const unsigned long long t = atomicAdd(b.q.counters + LBT_CNT_TICKET, 1ull);
+      if (t == (unsigned long long)gridDim.x - 1ull) {
+        atomicAdd(b.q.counters + LBT_CNT_NUMEL, numel);
+        b.q.counters[LBT_CNT_TICKET] = 0ull;
+      }
+    }
+  }
+}
+
+// Host: lbt_qsite (C ABI) -> QSite; a NULL descriptor gives a disabled site (bits == 0).
+inline QSite site_from_abi(const lbt_qsite* q) {
+  QSite s{};
+  if (!q) return s;
+  s.bits = q->bits;
+  s.ib = q->ib;
+  s.noise = q->noise;
+  s.seed = q->seed;
+  s.offset = q->offset;
+  s.dev_step = q->dev_step;
+  s.counters = reinterpret_cast<unsigned long long*>(q->counters);
+  s.minmax = q->stats_minmax;
+  return s;
+}
+
+}  // namespace lbt

@@ -19,6 +19,7 @@ All arithmetic on tensors runs in the library's kernels (quantiser, im2col, tcge
 there is no PyTorch/CPU fallback for them.  Range variables stay constant during a step and are
 advanced once per step by ``Runtime.update_ranges()`` (read-then-update).
 """
+import ctypes
 import math
 
 import torch
@@ -246,6 +247,19 @@ class QuantSite(nn.Module):
             kw['mode'] |= Q.STATS_MINMAX
         return Q.quantize(x, self.bits, self.range, **kw)
 
+    def abi(self, n_inner, device):
+        """This call site as an ``lbt_qsite`` for the fused kernels (same ids, ranges, Philox stream and
+        statistics block as quantize(), so fused and unfused runs are bit-identical)."""
+        rt = self.runtime
+        qs = _lib.QSiteStruct(bits=self.bits, stats_minmax=int(self.target == 0.0), ib=self.range.data_ptr(),
+                              noise=0, seed=rt.seed, offset=Q.make_offset(self.qid, 0),
+                              dev_step=_lib.ptr(rt.dev_step) or 0, counters=self.counters.data_ptr())
+        if rt.noise_fn is not None:
+            nz = rt.noise_fn(self, n_inner, device).contiguous()
+            qs.noise, qs.offset = nz.data_ptr(), 0
+            qs._keep = nz                 # the kernel is stream-ordered before the allocator can reuse it
+        return qs
+
     def extra_repr(self):
         return '%s bits=%d' % (self.name, self.bits)
 
@@ -339,12 +353,17 @@ def _implicit_ok(C, kh, kw):
     return (C in (16, 32, 64) or (C >= 128 and C % 128 == 0)) and kh * kw * C <= 65536 and kh <= 255 and kw <= 255
 
 
-def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d):
-    """lbt_conv_i8_fprop: out2d[N*OH*OW, Cout] = conv(src, wp) * 2^(exp_const + ib_src + ib_w) (+ bias)."""
+def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d,
+                   bnq=None):
+    """lbt_conv_i8_fprop: out2d[N*OH*OW, Cout] = conv(src, wp) * 2^(exp_const + ib_src + ib_w) (+ bias), or with
+    ``bnq = (QSiteStruct, k_out, sums)`` the fused re-quantising epilogue (s8 mantissas + batch statistics)."""
     N, H, W, C = src_nhwc.shape
+    qs, k_out, sums = bnq if bnq is not None else (None, None, None)
     _lib.call('lbt_conv_i8_fprop', _lib.ptr(src_nhwc), src_kind, N, H, W, C, _lib.ptr(wp), Q.MANT_S8, wp.stride(0), Cout,
               kh, kw, sh, sw, pt, pl, OH, OW, _lib.ptr(ib_src), _lib.ptr(ib_w), int(exp_const), _lib.ptr(bias),
-              _lib.ptr(out2d), out2d.stride(0), _lib.stream(), meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C))
+              _lib.ptr(out2d), out2d.stride(0) if out2d is not None else Cout,
+              ctypes.addressof(qs) if qs is not None else None, _lib.ptr(k_out), _lib.ptr(sums), _lib.stream(),
+              meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -352,158 +371,194 @@ def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW,
 # ------------------------------------------------------------------------------------------------
 
 
+def _conv_geom(layer, x, weight):
+    """(N, H, W, Cin, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW) of a Conv2d_q call on logical-NCHW ``x``."""
+    N, Cin, H, W = x.shape
+    kh, kw, _, Cout = weight.shape
+    sh, sw = layer.stride
+    if layer.padding == 'SAME':
+        OH, pt, _ = same_pad(H, kh, sh)
+        OW, pl, _ = same_pad(W, kw, sw)
+    else:
+        pt = pl = layer.pad_int
+        OH = (H + 2 * pt - kh) // sh + 1
+        OW = (W + 2 * pl - kw) // sw + 1
+    return (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW)
+
+
+def _conv_xkind(layer, geom):
+    """Mantissa type of the conv input (F7/H2): s8 up to 8 bits; the 9-bit activations are u8 when the input is
+    known non-negative, the {hi,hi,lo,0} x 16 split for a signed 3-channel image, else s16 hi|hi|lo."""
+    N, H, W, Cin, Cout, kh, kw = geom[:7]
+    xb = layer.qX.bits
+    if layer.qW.bits > 8 or xb > 16:
+        raise _lib.LbtError('Conv2d_q: weights wider than 8 bits need the hi/lo GEMM split (not built yet)')
+    if xb <= 8:
+        return Q.MANT_S8
+    if xb <= 9 and not layer.input_signed:
+        return Q.MANT_U8
+    if xb <= 9 and Cin == 3 and layer.implicit and kh * kw * 16 <= 65536 and _implicit_ok(Cout, 1, 1):
+        return Q.MANT_S9C3
+    return Q.MANT_S16
+
+
+def _conv_quantize_input(layer, x, geom):
+    """Xq of dfxp:287 as mantissas.  Uses the mantissas a fused producer already made with this very quantiser
+    (``x._lbt_q``, see conv_bn_unit) when there are any."""
+    xkind = _conv_xkind(layer, geom)
+    pre = getattr(x, '_lbt_q', None)
+    if pre is not None and id(layer.qX) in pre:
+        xm, kind = pre[id(layer.qX)]
+        assert kind == xkind, (kind, xkind)
+        return xm, xkind
+    if getattr(x, '_lbt_hollow', False):
+        raise _lib.LbtError('Conv2d_q: got a mantissa-only activation made for a different quantiser')
+    N, H, W = geom[:3]
+    x_nhwc = _mem_contig(x).permute(0, 2, 3, 1)
+    if xkind == Q.MANT_S9C3:
+        xm = torch.empty(N, H, W, 16, dtype=torch.int8, device=x.device)
+        layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind, out_mant=xm)
+        return xm, xkind
+    _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)
+    return xm, xkind
+
+
+def _conv_params(layer, weight, bias):
+    """(prep entry or None, weight mantissas or None, quantised bias or None) for this step."""
+    if not weight.is_contiguous():      # HWIO memory order is part of the semantics (noise broadcasts over kh)
+        weight = weight.contiguous()
+    prep = _prepared(layer)
+    bq = wm = None
+    if prep is None:
+        _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)               # dfxp:289
+        if bias is not None:
+            bq, _ = layer.qb.quantize(bias)                                                    # dfxp:294
+    else:
+        bq = prep.get('bq')
+    return prep, wm, bq
+
+
+def _conv_fprop(layer, geom, xm, xkind, prep, wm, bq, out2d, bnq=None):
+    """dfxp:291-296 on mantissas: out2d (fp32 [M, Cout]) or, with ``bnq``, the fused quantise + statistics epilogue."""
+    N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
+    e = -(layer.qX.bits - 1) - (layer.qW.bits - 1)
+    Kf = kh * kw * Cin
+    ibx, ibw = layer.qX.range, layer.qW.range
+    if xkind == Q.MANT_S9C3:
+        if prep is not None:
+            wt = prep['wt']
+        else:
+            w3 = wm.view(kh * kw, 3, Cout)
+            w16 = torch.cat([w3, w3, w3, torch.zeros(kh * kw, 7, Cout, dtype=torch.int8, device=xm.device)], dim=1)
+            wt = _transpose_bytes(w16.view(kh * kw * 16, Cout))
+        _conv_implicit(xm, Q.MANT_S8, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ibx, ibw, e, bq, out2d, bnq)
+        return
+    segs = 3 if xkind == Q.MANT_S16 else 1
+    wt = prep['wt'] if prep is not None else _transpose_bytes(wm.view(Kf, Cout))     # B operand [Cout, Kf]
+    if segs == 3:
+        wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
+    gbnq = None if bnq is None else (bnq[0], bnq[1], bnq[2], OH * OW)
+    if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
+        G.gemm_i8(xm.reshape(N * H * W, Cin), wt, ibA=ibx, ibB=ibw, exp_const=e, bias=bq, out=out2d, bnq=gbnq)   # 1x1
+    elif layer.implicit and segs == 1 and _implicit_ok(Cin, kh, kw):
+        _conv_implicit(xm, xkind, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ibx, ibw, e, bq, out2d, bnq)        # dfxp:291
+    else:
+        A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+        G.gemm_i8(A, wt, ibA=ibx, ibB=ibw, exp_const=e, bias=bq, out=out2d, bnq=gbnq)
+
+
+def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_db):
+    """dfxp:302-305 from the quantised gradient mantissas gm [N, OH, OW, Cout] (s8): (dX NHWC fp32, dW, db)."""
+    N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
+    xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
+    dev = gm.device
+    M = N * OH * OW
+    g2 = gm.view(M, Cout)
+    Kf = kh * kw * Cin
+    dW = db = dx = None
+    rt = layer.qX.runtime
+    # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
+    if need_dw:
+        acc = rt.zeros_i64(Kf * Cout, dev).view(Kf, Cout)
+        at = gt = None
+        if xkind == Q.MANT_S9C3:
+            if not _implicit_ok(Cout, 1, 1):
+                raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
+            # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
+            acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
+            _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                      sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+            a = acc16.view(kh * kw, 16, Cout)
+            acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+        elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
+            # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
+            _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                      sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+        else:
+            gt = _transpose_bytes(g2)                                                       # [Cout, M]
+            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+            at = _transpose_bytes(A)                                                        # [Kf*segs, M]
+        if at is None:
+            pass
+        elif xkind == Q.MANT_S16:
+            G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
+            G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
+        else:
+            G.gemm_i8_acc64(at, gt, acc, alpha=1)
+        dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                        add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))         # dfxp:302
+    if need_db:
+        db = _emit_grad(rt, layer.bias, _colsum(g2, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))      # dfxp:304
+    # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
+    if need_dx:
+        K2 = kh * kw * Cout
+        dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dev)
+        e = -(gb - 1) - (wb - 1)
+        pw2 = prep['w2'] if prep is not None else None        # packed by lbt_param_prep in the form used below
+        if prep is not None and pw2 is None:
+            raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
+        if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
+            w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
+            G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+        elif layer.implicit and sh == 1 and sw == 1 and _implicit_ok(Cout, kh, kw):
+            # stride 1: dX = conv(G, rot180(W)) with padding (k - 1 - pad): the same implicit-GEMM kernel
+            w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
+            _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
+                           layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
+        else:
+            w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+            A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
+            G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+    return dx, dW, db
+
+
 class _QConv2dFn(torch.autograd.Function):
     """dfxp:272-305 on integer mantissas: quantise X (bits+1), W, [b]; implicit GEMM fprop; in backward
-    quantise the gradient, then wgrad (+2*wd*W), bias grad, dgrad — all through lbt_gemm_i8."""
+    quantise the gradient, then wgrad (+2*wd*W), bias grad, dgrad."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, layer):
-        x = _mem_contig(x)
-        if not weight.is_contiguous():      # HWIO memory order is part of the semantics (noise broadcasts over kh)
-            weight = weight.contiguous()
-        N, Cin, H, W = x.shape
-        kh, kw, _, Cout = weight.shape
-        sh, sw = layer.stride
-        if layer.padding == 'SAME':
-            OH, pt, _ = same_pad(H, kh, sh)
-            OW, pl, _ = same_pad(W, kw, sw)
-        else:
-            pt = pl = layer.pad_int
-            OH = (H + 2 * pt - kh) // sh + 1
-            OW = (W + 2 * pl - kw) // sw + 1
-        xb = layer.qX.bits
-        # F7/H2: 9-bit activations are u8 when the input is known non-negative, else s16 split hi|hi|lo
-        if xb <= 8:
-            xkind = Q.MANT_S8
-        elif xb <= 9 and not layer.input_signed:
-            xkind = Q.MANT_U8
-        else:
-            xkind = Q.MANT_S16
-        if layer.qW.bits > 8 or xb > 16:
-            raise _lib.LbtError('Conv2d_q: weights wider than 8 bits need the hi/lo GEMM split (not built yet)')
-        x_nhwc = x.permute(0, 2, 3, 1)
-        prep = _prepared(layer)      # weights / bias already quantised + packed by this step's lbt_param_prep?
-        Kf = kh * kw * Cin
-        bq = wm = None
-        if prep is None:
-            _, wm = layer.qW.quantize(weight, want_fp32=False, mant_kind=Q.MANT_S8)           # dfxp:289
-            if bias is not None:
-                bq, _ = layer.qb.quantize(bias)                                                # dfxp:294
-        else:
-            bq = prep.get('bq')
-        ctx.prep = prep
+        geom = _conv_geom(layer, x, weight)
+        N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
+        xm, xkind = _conv_quantize_input(layer, x, geom)                                       # dfxp:287
+        prep, wm, bq = _conv_params(layer, weight, bias)
         y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
-        e = -(xb - 1) - (layer.qW.bits - 1)
-        if (xkind == Q.MANT_S16 and xb <= 9 and Cin == 3 and layer.implicit and kh * kw * 16 <= 65536 and
-                _implicit_ok(Cout, 1, 1)):
-            # image input: signed 9-bit k = 2*hi + lo as a 16-channel s8 tensor {hi,hi,lo,0} against {W,W,W,0}
-            xkind = Q.MANT_S9C3
-            xm = torch.empty(N, H, W, 16, dtype=torch.int8, device=x.device)
-            layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind, out_mant=xm)           # dfxp:287
-            if prep is not None:
-                wt = prep['wt']
-            else:
-                w3 = wm.view(kh * kw, 3, Cout)
-                w16 = torch.cat([w3, w3, w3, torch.zeros(kh * kw, 7, Cout, dtype=torch.int8, device=x.device)], dim=1)
-                wt = _transpose_bytes(w16.view(kh * kw * 16, Cout))
-            _conv_implicit(xm, Q.MANT_S8, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, layer.qX.range, layer.qW.range, e, bq,
-                           y.view(N * OH * OW, Cout))
-            ctx.layer = layer
-            ctx.geom = (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind)
-            ctx.save_for_backward(xm, wm, weight)
-            return y.permute(0, 3, 1, 2)
-        _, xm = layer.qX.quantize(x_nhwc, want_fp32=False, mant_kind=xkind)                   # dfxp:287
-        segs = 3 if xkind == Q.MANT_S16 else 1
-        # B operand [Cout, Kf]: transpose of the HWIO mantissas (tiny)
-        wt = prep['wt'] if prep is not None else _transpose_bytes(wm.view(Kf, Cout))
-        if segs == 3:
-            wt = _as_operand(torch.cat([wt, wt, wt], dim=1))
-        if kh == 1 and kw == 1 and sh == 1 and sw == 1 and segs == 1 and Cin % 16 == 0 and pt == 0 and pl == 0:
-            G.gemm_i8(xm.reshape(N * H * W, Cin), wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=e, bias=bq,
-                      out=y.view(N * OH * OW, Cout))                                           # 1x1: plain GEMM
-        elif layer.implicit and segs == 1 and _implicit_ok(Cin, kh, kw):
-            _conv_implicit(xm, xkind, wt, Cout, kh, kw, sh, sw, pt, pl, OH, OW, layer.qX.range, layer.qW.range, e, bq,
-                           y.view(N * OH * OW, Cout))                                          # dfxp:291, 296
-        else:
-            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
-            G.gemm_i8(A, wt, ibA=layer.qX.range, ibB=layer.qW.range, exp_const=e, bias=bq, out=y.view(N * OH * OW, Cout))
-        ctx.layer = layer
-        ctx.geom = (N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind)
-        ctx.save_for_backward(xm, wm, weight)
+        _conv_fprop(layer, geom, xm, xkind, prep, wm, bq, y.view(N * OH * OW, Cout))
+        ctx.layer, ctx.geom, ctx.xkind, ctx.prep = layer, geom, xkind, prep
+        ctx.save_for_backward(xm, wm)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         layer = ctx.layer
-        xm, wm, weight = ctx.saved_tensors
-        N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW, xkind = ctx.geom
-        xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
-        if gb > 8:
+        xm, wm = ctx.saved_tensors
+        if layer.qG.bits > 8:
             raise _lib.LbtError('Conv2d_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
         dy = _mem_contig(dy).permute(0, 2, 3, 1)
         _, gm = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S8)                    # dfxp:300
-        M = N * OH * OW
-        g2 = gm.view(M, Cout)
-        Kf = kh * kw * Cin
-        dW = db = dX = None
-        # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
-        rt = layer.qX.runtime
-        prep = ctx.prep
-        if ctx.needs_input_grad[1]:
-            acc = rt.zeros_i64(Kf * Cout, dy.device).view(Kf, Cout)
-            if xkind == Q.MANT_S9C3 and _implicit_ok(Cout, 1, 1):
-                # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
-                acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dy.device).view(kh * kw * 16, Cout)
-                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                          sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
-                a = acc16.view(kh * kw, 16, Cout)
-                acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
-                gt = at = None
-            elif xkind == Q.MANT_S9C3:
-                raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
-            elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
-                # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
-                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                          sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(),
-                          meta=dict(ops=2 * M * Cout * Kf))
-                gt = at = None
-            else:
-                gt = _transpose_bytes(g2)                                                       # [Cout, M]
-                A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
-                at = _transpose_bytes(A)                                                        # [Kf*segs, M]
-            if at is None:
-                pass
-            elif xkind == Q.MANT_S16:
-                G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
-                G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
-            else:
-                G.gemm_i8_acc64(at, gt, acc, alpha=1)
-            dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
-                            add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))         # dfxp:302
-        if layer.qb is not None and ctx.needs_input_grad[2]:
-            db = _emit_grad(rt, layer.bias, _colsum(g2, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))  # dfxp:304
-        # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
-        if ctx.needs_input_grad[0]:
-            K2 = kh * kw * Cout
-            dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dy.device)
-            e = -(gb - 1) - (wb - 1)
-            pw2 = prep['w2'] if prep is not None else None        # packed by lbt_param_prep in the form used below
-            if prep is not None and pw2 is None:
-                raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
-            if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
-                w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
-                G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
-            elif layer.implicit and sh == 1 and sw == 1 and _implicit_ok(Cout, kh, kw):
-                # stride 1: dX = conv(G, rot180(W)) with padding (k - 1 - pad): the same implicit-GEMM kernel
-                w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
-                _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
-                               layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
-            else:
-                w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
-                A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
-                G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
-            dX = dx.permute(0, 3, 1, 2)
-        return dX, dW, db, None
+        dx, dW, db = _conv_backward(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, ctx.needs_input_grad[0],
+                                    ctx.needs_input_grad[1], layer.qb is not None and ctx.needs_input_grad[2])
+        return (dx.permute(0, 3, 1, 2) if dx is not None else None), dW, db, None
 
 
 class Conv2d_q(nn.Module):
@@ -527,6 +582,7 @@ class Conv2d_q(nn.Module):
             self.padding, self.pad_int = 'INT', int(padding)
         self.bits, self.weight_decay, self.input_signed, self.name = bits, float(weight_decay), input_signed, name
         self.implicit = implicit    # implicit-GEMM kernels where the shape allows; False = explicit im2col + GEMM
+        self.fuse_bn = True         # may run as one unit with the BatchNorm2d_q that follows (conv_bn_unit)
         limit = (3 / (kh * kw * in_channels)) ** 0.5                                           # dfxp:247-254
         self.weight = nn.Parameter(torch.empty(kh, kw, in_channels, out_channels).uniform_(-limit, limit))
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None                  # dfxp:264
@@ -716,77 +772,238 @@ def _site_args(site, x_like):
     return None, Q.make_offset(site.qid, 0)
 
 
+def _to_mem(x):
+    """Memory-order view of an activation: NHWC for logical-NCHW channels_last tensors, as is for 2-D."""
+    x = _mem_contig(x)
+    return x.permute(0, 2, 3, 1) if x.dim() == 4 else x
+
+
+def _from_mem(t):
+    return t.permute(0, 3, 1, 2) if t.dim() == 4 else t
+
+
+def _bn_params(resc, gamma, beta):
+    prep = _prepared(resc)
+    if prep is not None:
+        return prep['gq'], prep['bq']
+    gq, _ = resc.qg.quantize(gamma.detach())                                                   # dfxp:679
+    bq, _ = resc.qb.quantize(beta.detach())                                                    # dfxp:681
+    return gq, bq
+
+
+def _bn_fwd1(bn, xm_):
+    """BN forward pass 1 on an fp32 memory-order tensor: (k1 s8, sums int64[2C])."""
+    norm = bn[0]
+    rt = norm.qX.runtime
+    N, C = xm_.shape[0], xm_.shape[-1]
+    n_inner = xm_.numel() // N
+    sums = rt.zeros_i64(2 * C, xm_.device)
+    k1 = torch.empty(xm_.shape, dtype=torch.int8, device=xm_.device)
+    nz1, off1 = _site_args(norm.qX, xm_)
+    _lib.call('lbt_bn_fwd_quant_stats', _lib.ptr(xm_), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
+              _lib.ptr(nz1), rt.seed, off1, _lib.ptr(rt.dev_step), _lib.ptr(k1), _lib.ptr(sums),
+              _lib.ptr(norm.qX.counters), int(norm.qX.target == 0), _lib.stream(), meta=dict(bytes=xm_.numel() * 5))
+    return k1, sums
+
+
+def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_NONE, want_fp32=True):
+    """BN forward pass 2 (+ residual add, ReLU, the consumer's input quantiser): (k2, out or None, next mantissas or None,
+    relu_mode)."""
+    norm, resc = bn[0], bn[1]
+    rt = norm.qX.runtime
+    N, C = k1.shape[0], k1.shape[-1]
+    n_inner = k1.numel() // N
+    dev = k1.device
+    k2 = torch.empty_like(k1)
+    out = torch.empty(k1.shape, dtype=torch.float32, device=dev) if want_fp32 else None
+    nz2, off2 = _site_args(resc.qX, k1)
+    relu_mode = 0 if not relu else (2 if add_ is not None else 1)
+    qn = nm = None
+    if next_site is not None:
+        qn = next_site.abi(n_inner, dev)
+        nm = torch.empty(k1.shape, dtype=torch.uint8 if next_kind == Q.MANT_U8 else torch.int8, device=dev)
+    _lib.call('lbt_bn_fwd_apply', _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range), _lib.ptr(sums),
+              float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
+              _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add_),
+              1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
+              _lib.ptr(norm.X_var_running), float(norm.momentum), int(resc.qX.target == 0),
+              ctypes.addressof(qn) if qn is not None else None, _lib.ptr(nm), int(next_kind), _lib.stream(),
+              meta=dict(bytes=k1.numel() * (2 + (4 if want_fp32 else 0) + (4 if add_ is not None else 0) +
+                                            (1 if nm is not None else 0))))
+    return k2, out, nm, relu_mode
+
+
+def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_site=None, want_dx=True):
+    """Both BN backward passes on memory-order tensors: (dx fp32 or None, gradient mantissas of `grad_site` or None,
+    dgamma, dbeta, d_add)."""
+    norm, resc = bn[0], bn[1]
+    rt = norm.qX.runtime
+    N, C = g_.shape[0], g_.shape[-1]
+    n_inner = g_.numel() // N
+    dev = g_.device
+    bsums = rt.zeros_i64(4 * C, dev)
+    kg1 = torch.empty_like(k1)
+    d_add = torch.empty_like(g_) if has_add else None
+    nzg2, offg2 = _site_args(resc.qG, g_)
+    nzg1, offg1 = _site_args(norm.qG, g_)
+    _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g_), _lib.ptr(out_), relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
+              C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
+              _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
+              _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
+              _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
+              int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
+              meta=dict(bytes=g_.numel() * (7 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
+    dx = torch.empty_like(g_) if want_dx else None
+    qg = gm = None
+    if grad_site is not None:
+        qg = grad_site.abi(n_inner, dev)
+        gm = torch.empty_like(k1)
+    _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
+              _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
+              ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), _lib.stream(),
+              meta=dict(bytes=g_.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
+    # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
+    dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
+    dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
+                        exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add_scale=2 * resc.weight_decay)
+    return dx, gm, dgamma, dbeta, d_add
+
+
 class _FusedBNFn(torch.autograd.Function):
     """Normalization_q + Rescale_q (+ residual add, + ReLU) in 2 forward and 2 backward passes over the
     activation (csrc/bn.cu), saving only the two s8 mantissa tensors for backward."""
 
     @staticmethod
     def forward(ctx, x, gamma, beta, add, bn, relu):
-        norm, resc = bn[0], bn[1]
-        rt = norm.qX.runtime
-        x = _mem_contig(x)
-        N, C = x.shape[0], x.shape[1]
-        n_inner = x.numel() // N
-        dev = x.device
-        sums = rt.zeros_i64(2 * C, dev)
-        k1 = torch.empty_like(x, dtype=torch.int8)
-        nz1, off1 = _site_args(norm.qX, x)
-        _lib.call('lbt_bn_fwd_quant_stats', _lib.ptr(x), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
-                  _lib.ptr(nz1), rt.seed, off1, _lib.ptr(rt.dev_step), _lib.ptr(k1), _lib.ptr(sums),
-                  _lib.ptr(norm.qX.counters), int(norm.qX.target == 0), _lib.stream(), meta=dict(bytes=x.numel() * 5))
-        prep = _prepared(resc)
-        if prep is not None:
-            gq, bq = prep['gq'], prep['bq']
-        else:
-            gq, _ = resc.qg.quantize(gamma.detach())                                           # dfxp:679
-            bq, _ = resc.qb.quantize(beta.detach())                                            # dfxp:681
-        k2 = torch.empty_like(k1)
-        out = torch.empty_like(x)
-        if add is not None:
-            add = _mem_contig(add)
-        nz2, off2 = _site_args(resc.qX, x)
-        relu_mode = 0 if not relu else (2 if add is not None else 1)
-        _lib.call('lbt_bn_fwd_apply', _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range), _lib.ptr(sums),
-                  float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
-                  _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add),
-                  1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
-                  _lib.ptr(norm.X_var_running), float(norm.momentum), int(resc.qX.target == 0), _lib.stream(),
-                  meta=dict(bytes=x.numel() * (6 + (4 if add is not None else 0))))
+        x_ = _to_mem(x)
+        k1, sums = _bn_fwd1(bn, x_)
+        gq, bq = _bn_params(bn[1], gamma, beta)
+        add_ = _to_mem(add) if add is not None else None
+        k2, out, _, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu)
         ctx.bn, ctx.relu_mode, ctx.has_add = bn, relu_mode, add is not None
-        ctx.save_for_backward(k1, k2, sums, gq, bq, gamma, out if relu_mode == 2 else None)
-        return out
+        ctx.save_for_backward(k1, k2, sums, gq, bq, out if relu_mode == 2 else None)
+        return _from_mem(out)
 
     @staticmethod
     def backward(ctx, g):
-        bn = ctx.bn
+        k1, k2, sums, gq, bq, out = ctx.saved_tensors
+        dx, _, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g), k1, k2, sums, gq, bq, out, ctx.relu_mode, ctx.has_add)
+        return _from_mem(dx), dgamma, dbeta, (_from_mem(d_add) if d_add is not None else None), None, None
+
+
+class _ConvBNFn(torch.autograd.Function):
+    """One Conv2d_q + BatchNorm2d_q unit (+ residual add, + ReLU) with every hand-off between the two modules kept
+    in integer mantissas (north_star (2): the GEMM epilogue re-quantises its output, no fake-quant fp32 round trip):
+
+      forward   X --Q_conv.X--> u8/s8 --tcgen05 conv, epilogue Q_norm.X + sum k, sum k^2--> k1 (s8)
+                k1 --lbt_bn_fwd_apply--> k2 (s8, saved), out fp32 (only if wanted), mantissas for the NEXT conv
+      backward  g --lbt_bn_bwd_quant_stats--> kg1 --lbt_bn_bwd_apply, epilogue Q_conv.grad--> gm (s8) --> wgrad, dgrad
+
+    Same quantiser ids, ranges, noise streams and arithmetic as running the two modules one after the other:
+    the results are bit-identical (tests/test_fused_gpu.py)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32):
+        geom = _conv_geom(conv, x, weight)
+        N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         norm, resc = bn[0], bn[1]
         rt = norm.qX.runtime
-        k1, k2, sums, gq, bq, gamma, out = ctx.saved_tensors
-        g = _mem_contig(g)
-        N, C = g.shape[0], g.shape[1]
-        n_inner = g.numel() // N
-        dev = g.device
-        bsums = rt.zeros_i64(4 * C, dev)
-        kg1 = torch.empty_like(k1)
-        d_add = torch.empty_like(g) if ctx.has_add else None
-        nzg2, offg2 = _site_args(resc.qG, g)
-        nzg1, offg1 = _site_args(norm.qG, g)
-        _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g), _lib.ptr(out), ctx.relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
-                  C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
-                  _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
-                  _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
-                  _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
-                  int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
-                  meta=dict(bytes=g.numel() * (7 + (4 if ctx.relu_mode == 2 else 0) + (4 if ctx.has_add else 0))))
-        dx = torch.empty_like(g)
-        _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
-                  _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
-                  _lib.stream(), meta=dict(bytes=g.numel() * 6))
-        # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
-        dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
-        dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
-                            exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add_scale=2 * resc.weight_decay)
-        return dx, dgamma, dbeta, d_add, None, None
+        dev = x.device
+        xm, xkind = _conv_quantize_input(conv, x, geom)                                        # dfxp:287
+        prep, wm, _ = _conv_params(conv, weight, None)
+        sums = rt.zeros_i64(2 * Cout, dev)
+        k1 = torch.empty(N, OH, OW, Cout, dtype=torch.int8, device=dev)
+        _conv_fprop(conv, geom, xm, xkind, prep, wm, None, None,
+                    bnq=(norm.qX.abi(OH * OW * Cout, dev), k1, sums))                          # dfxp:291 + :584-588
+        gq, bq = _bn_params(resc, gamma, beta)
+        add_ = _to_mem(add) if add is not None else None
+        k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
+        ctx.conv, ctx.bn, ctx.geom, ctx.xkind, ctx.prep = conv, bn, geom, xkind, prep
+        ctx.relu_mode, ctx.has_add = relu_mode, add is not None
+        ctx.save_for_backward(xm, wm, k1, k2, sums, gq, bq, out if relu_mode == 2 else None)
+        if out is None:       # mantissa-only activation: the fp32 tensor is never materialised (shape carrier only)
+            out = torch.empty(1, dtype=torch.float32, device=dev).expand(N, OH, OW, Cout)
+        if nm is None:
+            nm = torch.empty(0, dtype=torch.uint8, device=dev)
+        ctx.mark_non_differentiable(nm)
+        return _from_mem(out), nm
+
+    @staticmethod
+    def backward(ctx, g, _g_nm):
+        conv = ctx.conv
+        xm, wm, k1, k2, sums, gq, bq, out = ctx.saved_tensors
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        _, gm, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g), k1, k2, sums, gq, bq, out, ctx.relu_mode,
+                                                   ctx.has_add, grad_site=conv.qG, want_dx=False)   # ... dfxp:300
+        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False)
+        return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
+                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None)
+
+
+FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused units (tests compare both settings)
+
+
+def _unit_fusable(conv, bn, x):
+    return (FUSE_UNITS and isinstance(conv, Conv2d_q) and isinstance(bn, BatchNorm2d_q) and conv.bias is None and conv.fuse_bn and
+            bn._can_fuse_c(conv.weight.shape[3], 4) and conv.qG.bits <= 8 and conv.qW.bits <= 8 and conv.qX.bits <= 9 and
+            x.is_cuda)
+
+
+def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True):
+    """``bn(conv(x), add=add, relu=relu)`` as ONE fused unit when the shapes allow (else exactly that expression).
+
+    next_conv: the Conv2d_q that consumes the result — its input quantiser then runs inside this unit's last kernel
+    and the mantissas travel with the returned tensor (``_lbt_q``); want_fp32=False (only legal when next_conv is the
+    ONLY consumer) skips the fp32 tensor altogether."""
+    relu = relu or getattr(bn, 'relu', False)
+    if not _unit_fusable(conv, bn, x):
+        return bn(conv(x), add=add, relu=relu) if isinstance(bn, BatchNorm2d_q) else bn(conv(x))
+    next_site, next_kind = None, Q.MANT_NONE
+    if next_conv is not None and isinstance(next_conv, Conv2d_q) and next_conv.fuse_bn:
+        nb = next_conv.qX.bits
+        if nb <= 8:
+            next_site, next_kind = next_conv.qX, Q.MANT_S8
+        elif nb == 9 and relu and not next_conv.input_signed:
+            next_site, next_kind = next_conv.qX, Q.MANT_U8
+    if next_site is None or add is not None:
+        want_fp32 = True
+    out, nm = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
+                              want_fp32)
+    if next_site is not None:
+        out._lbt_q = {id(next_site): (nm, next_kind)}
+    if not want_fp32:
+        out._lbt_hollow = True
+    return out
+
+
+def run_layers(layers, x, next_conv=None):
+    """Forward through a layer list with the Conv2d_q -> BatchNorm2d_q peephole: adjacent pairs run as fused units
+    and hand mantissas to the convolution that follows (``next_conv`` = the consumer after the last layer)."""
+    layers = list(layers)
+    i = 0
+    while i < len(layers):
+        m = layers[i]
+        nxt = layers[i + 1] if i + 1 < len(layers) else None
+        if isinstance(m, Conv2d_q) and isinstance(nxt, BatchNorm2d_q):
+            after = layers[i + 2] if i + 2 < len(layers) else next_conv
+            x = conv_bn_unit(m, nxt, x, next_conv=_first_conv(after))
+            i += 2
+        elif isinstance(m, ResidualBlock_q):
+            x = m(x, next_conv=_first_conv(nxt if nxt is not None else next_conv))
+            i += 1
+        else:
+            x = m(x)
+            i += 1
+    return x
+
+
+def _first_conv(m):
+    """The Conv2d_q that quantises the input of module ``m`` FIRST AND ONLY ONCE per site, or None."""
+    if isinstance(m, Conv2d_q):
+        return m
+    if isinstance(m, ResidualBlock_q):
+        return m.residual[0] if isinstance(m.residual[0], Conv2d_q) else None
+    return None
 
 
 class BatchNorm2d_q(nn.Sequential):
@@ -810,10 +1027,13 @@ class BatchNorm2d_q(nn.Sequential):
         self.fused = fused
         self.relu = relu            # apply the ReLU that follows this BN in the reference's layer lists
 
-    def _can_fuse(self, x):
+    def _can_fuse_c(self, C, dim):
         norm, resc = self[0], self[1]
-        return (self.fused and self.training and x.dim() in (2, 4) and x.shape[1] % 4 == 0 and
+        return (self.fused and self.training and dim in (2, 4) and C % 4 == 0 and
                 max(norm.qX.bits, norm.qG.bits, resc.qX.bits, resc.qG.bits) <= 8 and min(norm.qX.bits, resc.qX.bits) >= 2)
+
+    def _can_fuse(self, x):
+        return self._can_fuse_c(x.shape[1], x.dim())
 
     def forward(self, x, add=None, relu=False):
         relu = relu or self.relu
@@ -935,13 +1155,25 @@ class ResidualBlock_q(nn.Module):
             Conv2d_q(bits, channels, channels, 3, 1, 'SAME', name=name + '-2', **ckw),
             self._bn(name + '-bn2', channels))
 
-    def forward(self, x):
+    def forward(self, x, next_conv=None):
         # y = relu(residual(x) + shortcut(x)) (dfxp:858-863); the sum and the ReLU ride in the last BN's kernels.
         # Block inputs come from a ReLU (or a max-pool of one) in every reference model: non-negative.
+        # Conv+BN pairs run as fused units (conv_bn_unit): inside the block the activations between them exist
+        # only as mantissas; next_conv is the convolution that consumes the block output (wired by run_layers).
+        res = list(self.residual)
+        sc_layers = list(self.shortcut)
+        paired = len(res) % 2 == 0 and all(isinstance(res[i], Conv2d_q) and isinstance(res[i + 1], BatchNorm2d_q)
+                                           for i in range(0, len(res), 2))
+        if paired:
+            r = x
+            for i in range(0, len(res) - 2, 2):
+                r = conv_bn_unit(res[i], res[i + 1], r, next_conv=res[i + 2], want_fp32=False)
+            sc = conv_bn_unit(sc_layers[0], sc_layers[1], x) if len(sc_layers) == 2 else self.shortcut(x)
+            return conv_bn_unit(res[-2], res[-1], r, add=sc, relu=True, next_conv=next_conv)
         r = x
-        for m in list(self.residual)[:-1]:
+        for m in res[:-1]:
             r = m(r)
-        last = self.residual[-1]
+        last = res[-1]
         sc = self.shortcut(x)
         if isinstance(last, BatchNorm2d_q):
             return last(r, add=sc, relu=True)

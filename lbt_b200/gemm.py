@@ -1,4 +1,6 @@
 """Host wrappers of the tcgen05 int8 GEMM (csrc/gemm_i8.cu) — raw pointers across the C ABI."""
+import ctypes
+
 import torch
 
 from . import _lib
@@ -21,16 +23,26 @@ def _check_operand(t, K):
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), K)
 
 
-def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None):
-    """fp32 out[M,N] = (A[M,K] @ B[N,K]^T) * 2^(exp_const + ibA + ibB) (+ bias)."""
+def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=None):
+    """fp32 out[M,N] = (A[M,K] @ B[N,K]^T) * 2^(exp_const + ibA + ibB) (+ bias).
+
+    ``bnq = (QSiteStruct, k_out int8 [M,N], sums int64 [2N], rows_per_image)`` switches to the fused re-quantising
+    epilogue (no fp32 output): k_out = Q_site(result), sums += (k, k^2) per column."""
     M, K = A.shape
     N = B.shape[0]
     lda, ldb = _check_operand(A, K), _check_operand(B, K)
+    if bnq is not None:
+        qs, k_out, sums, rpi = bnq
+        _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
+                  _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), None, None, N, 1, 1,
+                  ctypes.addressof(qs), _lib.ptr(k_out), _lib.ptr(sums), int(rpi), _lib.stream(),
+                  meta=dict(ops=2 * M * N * K))
+        return None
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                                       _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), _lib.ptr(out), None,
-                                      out.stride(0), 1, 1, _lib.stream(), meta=dict(ops=2 * M * N * K))
+                                      out.stride(0), 1, 1, None, None, None, 0, _lib.stream(), meta=dict(ops=2 * M * N * K))
     return out
 
 
@@ -47,7 +59,7 @@ def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
         k_splits = max(1, sms // max(1, tiles))
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
                                       None, None, 0, None, None, _lib.ptr(acc64), N, int(alpha), int(k_splits),
-                                      _lib.stream(), meta=dict(ops=2 * M * N * K))
+                                      None, None, None, 0, _lib.stream(), meta=dict(ops=2 * M * N * K))
     return acc64
 
 

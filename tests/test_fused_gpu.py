@@ -1,0 +1,72 @@
+"""Fused Conv2d_q + BatchNorm2d_q units (tensor-core epilogue re-quantisation, mantissa hand-offs between
+modules) against the same modules run one after the other: identical quantiser ids, ranges, noise streams and
+arithmetic, so every result must be BIT-identical."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lbt_b200 import dfxp as D, models as M  # noqa: E402
+from lbt_b200.trainer import Trainer  # noqa: E402
+
+
+def _run(name, fused, steps, batch, image, kw):
+    D.FUSE_UNITS = fused
+    try:
+        torch.manual_seed(3)
+        model = getattr(M, name)(8, weight_decay=2e-4, seed=9, **kw).cuda()
+        tr = Trainer(model, lr=1e-2, momentum=0.9)
+        rng = np.random.default_rng(1)
+        losses = []
+        for _ in range(steps):
+            X = torch.from_numpy((rng.standard_normal((batch, image, image, 3)) * 0.5).astype(np.float32)).cuda()
+            y = torch.from_numpy(rng.integers(0, 10, batch)).cuda()
+            losses.append(float(tr.step(X.permute(0, 3, 1, 2), y)))
+        torch.cuda.synchronize()
+        return dict(losses=losses, w=tr.flat_w.clone(), g=tr.flat_g.clone(), a=tr.flat_a.clone(),
+                    ranges=model.runtime.flat['ranges'].clone(), counters=model.runtime.flat['counters'].clone(),
+                    bn=[b.clone() for n, b in model.named_buffers() if 'running' in n])
+    finally:
+        D.FUSE_UNITS = True
+
+
+@pytest.mark.parametrize('name,batch,image,kw', [
+    ('CIFAR10_Resnet20', 16, 32, {}),
+    ('CIFAR10_Resnet20', 5, 32, {}),                                  # ragged M tiles (5*32*32 = 40 tiles; 5*8*8 = 2.5 tiles)
+    ('Resnet18', 4, 64, dict(image=64, num_classes=10)),              # stride-2 units, max-pool after the stem, 128..512 channels
+    ('Resnet50', 2, 64, dict(image=64, num_classes=10)),              # bottlenecks: 1x1 units through lbt_gemm_i8
+])
+def test_fused_units_equal_unfused_bit_for_bit(name, batch, image, kw):
+    a = _run(name, True, 3, batch, image, kw)
+    b = _run(name, False, 3, batch, image, kw)
+    assert a['losses'] == b['losses'], (a['losses'], b['losses'])
+    assert torch.equal(a['ranges'], b['ranges'])
+    assert torch.equal(a['counters'], b['counters'])
+    for k in ('g', 'w', 'a'):
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
+    for x, y in zip(a['bn'], b['bn']):
+        assert torch.equal(x, y)
+
+
+def test_fused_unit_hands_mantissas_to_the_next_conv():
+    """Inside a residual block the activation between bn1 and conv2 exists only as mantissas."""
+    torch.manual_seed(0)
+    rt = D.Runtime(1)
+    blk = D.ResidualBlock_q(8, 16, 16, 1, runtime=rt).cuda()
+    x = torch.rand(4, 16, 8, 8, device='cuda').contiguous(memory_format=torch.channels_last)
+    seen = {}
+    orig = D._conv_quantize_input
+
+    def spy(layer, t, geom):
+        seen[layer.name] = (getattr(t, '_lbt_hollow', False), id(layer.qX) in (getattr(t, '_lbt_q', None) or {}))
+        return orig(layer, t, geom)
+
+    D._conv_quantize_input = spy
+    try:
+        y = blk(x)
+    finally:
+        D._conv_quantize_input = orig
+    assert seen['block-2'] == (True, True)          # conv2 consumed bn1's fused mantissas, no fp32 tensor
+    assert seen['block-1'] == (False, False)
+    assert y.shape == x.shape and bool(torch.isfinite(y).all())
