@@ -196,6 +196,8 @@ int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W, int C, int
  * source + tcgen05.mma.kind::i8.  Replaces tf.nn.conv2d (dynamic_fixed_point.py:196, 291); run on the
  * output-gradient map with the 180-degree-rotated filter it is tf.gradients(y, X, gradq) of a stride-1
  * convolution (:210, :305).
+ *   Narrow inputs (C in {16, 32, 64}, Cout <= 128) are gathered by cp.async loader warps with the filter bank
+ *   resident in shared memory (the TMA engine retires only one pixel row per ~3 clocks per SM).
  *   src[N,H,W,C] s8|u8, C in {16, 32, 64} or a multiple of 128;  wp[Cout, kh*kw*C] packed K-major
  *   (k = (r*kw + s)*C + c, row pitch ldw bytes);  out[N*OH*OW, Cout] fp32 (row pitch ldc floats):
  *   out = fp32(acc) * 2^(exp_const + *ib_src + *ib_w) (+ bias[co]).  kh*kw*C <= 65536.
@@ -206,6 +208,17 @@ int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C,
                       size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
                       int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
                       float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, void* stream);
+
+/*
+ * Input gradient of a convolution of ANY stride as an implicit GEMM (no im2col matrix in HBM), the transposed
+ * gather of lbt_im2col_i8(transposed = 1) done by the kernel's loader warps: dx[(n,h,w), ci] = 2^e * sum over taps
+ * (r,s) and co of g[n, (h + pad_top - r)/sh, (w + pad_left - s)/sw, co] * wp[ci, (r*kw + s)*Cout + co] where
+ * divisible — tf.gradients(y, X, gradq) (dynamic_fixed_point.py:210, 305).  g[N,OH,OW,Cout] s8|u8 with
+ * Cout in {16, 32, 64}; Cin <= 128; dx[N*H*W, Cin] fp32 (row pitch ldc floats); e = exp_const + *ib_g + *ib_w.
+ */
+int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* wp, int w_kind,
+                      size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
+                      const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, void* stream);
 
 /*
  * Implicit-GEMM weight gradient: acc64[(r*kw+s)*C + c, co] += alpha * sum over output pixels m of

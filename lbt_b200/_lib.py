@@ -33,6 +33,8 @@ SIGNATURES = {
     'lbt_im2col_i8': (c_int, [c_void_p, c_int] + [c_int] * 13 + [c_void_p, c_size_t, c_void_p]),
     'lbt_conv_i8_fprop': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_size_t] + [c_int] * 9 +
                           [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'lbt_conv_i8_dgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_size_t] + [c_int] * 9 +
+                          [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'lbt_conv_i8_wgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_int] * 9 +
                           [c_void_p, c_int, c_int, c_void_p]),
     'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
@@ -60,6 +62,8 @@ _INTERNAL = {
     'lbt_quantize_tune': (c_int, [c_int, c_int]),
     'lbt_gemm_debug_error': (c_int, []),
     'lbt_conv_debug_error': (c_int, []),
+    'lbt_conv_ldg_debug_error': (c_int, []),
+    'lbt_conv_set_path': (c_int, [c_int]),
 }
 
 

@@ -14,6 +14,7 @@
 // Channel chunk Cb = min(C, 128) in {16, 32, 64, 128} selects the shared-memory layout: 16-byte rows of
 // interleaved 8x16B core matrices, or 32/64/128-byte swizzled rows; a pipeline stage always carries 128 bytes
 // of K per row (128/Cb tap-blocks), i.e. four K=32 MMAs.  Same warp roles and mbarrier protocol as gemm_i8.cu.
+#include "conv_internal.h"
 #include "qsite.cuh"
 #include "tcgen05.cuh"
 
@@ -516,6 +517,12 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
     return LBT_EINVAL;
   if (C % 16) return LBT_EUNSUPPORTED;
+  if (conv_ldg_enabled() && conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
+      !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
+    LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
+    return conv_ldg_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, 0, ib_src,
+                        ib_w, exp_const, bias, out, ldc, q_out, k_out, sums, stream);
+  }
   const uint32_t cb = C >= 128 ? 128u : (uint32_t)C;
   if (cb != 16 && cb != 32 && cb != 64 && cb != 128) return LBT_EUNSUPPORTED;
   if (C % cb) return LBT_EUNSUPPORTED;

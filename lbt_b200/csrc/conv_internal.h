@@ -1,0 +1,19 @@
+// Internal (not part of the C ABI): the cp.async-gather implicit-GEMM kernel of conv_ldg.cu, shared by
+// lbt_conv_i8_fprop and lbt_conv_i8_dgrad.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/lbt.h"
+
+namespace lbt {
+
+bool conv_ldg_ok(int C, int Cout, int kh, int kw);
+bool conv_ldg_enabled();
+int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, const void* wp, int w_kind, size_t ldw, int Cout,
+                 int kh, int kw, int sh, int sw, int pt, int pl, int OH, int OW, int gather, const int32_t* ibA,
+                 const int32_t* ibB, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
+                 int8_t* k_out, int64_t* sums, void* stream);
+
+}  // namespace lbt

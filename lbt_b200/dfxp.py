@@ -353,6 +353,16 @@ def _implicit_ok(C, kh, kw):
     return (C in (16, 32, 64) or (C >= 128 and C % 128 == 0)) and kh * kw * C <= 65536 and kh <= 255 and kw <= 255
 
 
+def _gather_ok(C, Cout, kh, kw):
+    """Shapes of the cp.async-gather kernel (csrc/conv_ldg.cu): gathered channels 16/32/64, <= 128 output channels,
+    filter bank resident in shared memory."""
+    if C not in (16, 32, 64) or not 1 <= Cout <= 128:
+        return False
+    kcp = (kh * kw * (C // 16) + 1) & ~1
+    bn = 16 if Cout <= 16 else (32 if Cout <= 32 else (64 if Cout <= 64 else 128))
+    return kcp * bn * 16 + 2 * 16384 + 1024 <= 200 * 1024 and kh * kw * C <= 65536
+
+
 def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d,
                    bnq=None):
     """lbt_conv_i8_fprop: out2d[N*OH*OW, Cout] = conv(src, wp) * 2^(exp_const + ib_src + ib_w) (+ bias), or with
@@ -525,6 +535,12 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
             w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
             _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
                            layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
+        elif layer.implicit and _gather_ok(Cout, Cin, kh, kw):
+            # any stride: the transposed gather runs in the kernel's loader warps (lbt_conv_i8_dgrad), no im2col matrix
+            w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+            _lib.call('lbt_conv_i8_dgrad', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2), Q.MANT_S8, w2.stride(0),
+                      Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
+                      _lib.ptr(dx), Cin, _lib.stream(), meta=dict(ops=2 * N * H * W * Cin * K2))
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
