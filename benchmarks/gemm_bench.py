@@ -19,7 +19,11 @@ from lbt_b200 import _lib, dfxp, gemm as G, quantizer as Q  # noqa: E402
 INT8_PEAK_TOPS = 4500.0     # B200 dense int8 nominal (B200_PROFILING.md); no measured int8 figure in MEASURED_PEAKS.json
 
 
-def timeit(fn, iters=10, warmup=3, flush=None):
+ITERS = [10]
+
+
+def timeit(fn, iters=None, warmup=3, flush=None):
+    iters = iters or ITERS[0]
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -101,14 +105,19 @@ def main():
     ap.add_argument('--square', default='4096,8192,16384')
     ap.add_argument('--layers', default='resnet20,resnet18')
     ap.add_argument('--flush', action='store_true')
+    ap.add_argument('--only', default='', help='substring filter on the layer name')
+    ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--out', default='gpurun_out/gemm_bench.json')
     a = ap.parse_args()
+    ITERS[0] = a.iters
     flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda') if a.flush else None
     rows = []
     for n in [int(s) for s in a.square.split(',') if s]:
         rows.append(bench_square(n, flush))
     for fam in [f for f in a.layers.split(',') if f and f != 'none']:
         for (N, H, W, Ci, Co, k, s, name) in LAYERS[fam]:
+            if a.only and a.only not in name:
+                continue
             rows += conv_case(N, H, W, Ci, Co, k, s, flush, fam + ' ' + name)
     for r in rows:
         r['frac_int8_peak'] = r['tops'] / INT8_PEAK_TOPS

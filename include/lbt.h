@@ -262,6 +262,21 @@ typedef struct lbt_finalize_job {
 int lbt_finalize_multi(const lbt_finalize_job* jobs_dev, size_t njobs, uint64_t total, void* stream);
 
 /*
+ * One launch for the noise vectors of many quantiser sites: u[e] for e < n of each job = the Philox4x32-10 stream of
+ * lbt_noise_fill with (seed, job.offset + (*dev_step << 32)).  `start` is the running sum of ceil(n/4) over the
+ * preceding jobs and total_groups the sum over all jobs; every u is 16-byte aligned.  Feeds lbt_qsite.noise of the
+ * fused tensor-core epilogues (their threads then load the noise instead of generating it).
+ */
+typedef struct lbt_noise_job {
+  float* u;
+  uint64_t n;
+  uint64_t offset;
+  uint64_t start;
+} lbt_noise_job;
+int lbt_noise_fill_multi(const lbt_noise_job* jobs_dev, size_t njobs, uint64_t total_groups, uint64_t seed,
+                         const uint64_t* dev_step, void* stream);
+
+/*
  * One launch for every PARAMETER quantiser of the step (weights dfxp:289, 386; biases :294, 391; BN gamma /
  * beta :679-682): stochastic DFXP quantisation with the in-kernel Philox stream (offset = quantiser id,
  * + *dev_step << 32), overflow counters, and the operands the tensor-core kernels consume:

@@ -42,6 +42,7 @@ SIGNATURES = {
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
                                  c_void_p]),
     'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),
+    'lbt_noise_fill_multi': (c_int, [c_void_p, c_size_t, c_u64, c_u64, c_void_p, c_void_p]),
     'lbt_param_prep': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.c_uint32, c_u64, c_void_p, c_void_p]),
     'lbt_bn_fwd_quant_stats': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_u64, c_u64,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -64,6 +65,7 @@ _INTERNAL = {
     'lbt_conv_debug_error': (c_int, []),
     'lbt_conv_ldg_debug_error': (c_int, []),
     'lbt_conv_set_path': (c_int, [c_int]),
+    'lbt_conv_ldg_set_debug': (c_int, [c_void_p]),
 }
 
 
@@ -81,6 +83,11 @@ class QSiteStruct(ctypes.Structure):
     """lbt_qsite (include/lbt.h): one quantiser call site as the fused kernels see it."""
     _fields_ = [('bits', ctypes.c_int32), ('stats_minmax', ctypes.c_int32), ('ib', c_void_p), ('noise', c_void_p),
                 ('seed', c_u64), ('offset', c_u64), ('dev_step', c_void_p), ('counters', c_void_p)]
+
+
+class NoiseJob(ctypes.Structure):
+    """lbt_noise_job (include/lbt.h)."""
+    _fields_ = [('u', c_void_p), ('n', c_u64), ('offset', c_u64), ('start', c_u64)]
 
 
 class PrepJob(ctypes.Structure):

@@ -32,6 +32,35 @@ __global__ void __launch_bounds__(kThreads) finalize_multi_kernel(const lbt_fina
   }
 }
 
+// ---- noise for the fused tensor-core epilogues ---------------------------------------------------------------
+// The epilogue threads of the convolution kernels would otherwise run Philox4x32-10 themselves (100 instructions per
+// four outputs on four warps); the noise of a site is shared over the batch, so ONE launch per step materialises
+// every site's [n_inner] vector (<= 1/batch of the activation, L2-resident) from the very same stream.
+__global__ void __launch_bounds__(kThreads) noise_fill_multi_kernel(const lbt_noise_job* __restrict__ jobs, int njobs,
+                                                                    unsigned long long total_groups, uint64_t seed,
+                                                                    const uint64_t* dev_step) {
+  const uint64_t step_off = dev_step ? ((*dev_step) << 32) : 0ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < total_groups;
+       i += (unsigned long long)gridDim.x * kThreads) {
+    int lo = 0, hi = njobs - 1;  // last job with start <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+    }
+    const lbt_noise_job j = jobs[lo];
+    const unsigned long long g = i - j.start;
+    const float4 v = philox_noise4(g, seed, j.offset + step_off);
+    const unsigned long long e = 4ull * g;
+    if (e + 3 < j.n) {
+      *reinterpret_cast<float4*>(j.u + e) = v;
+    } else {
+      if (e + 0 < j.n) j.u[e + 0] = v.x;
+      if (e + 1 < j.n) j.u[e + 1] = v.y;
+      if (e + 2 < j.n) j.u[e + 2] = v.z;
+    }
+  }
+}
+
 // ---- parameter preparation ---------------------------------------------------------------------
 struct QC {
   float m, inv_m, L, hi, half;
@@ -144,4 +173,17 @@ extern "C" int lbt_param_prep(const lbt_prep_job* jobs_dev, const uint32_t* bloc
   param_prep_kernel<<<(unsigned)nblocks, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       jobs_dev, block_job_dev, block_chunk_dev, seed, dev_step, chunk_elems);
   return check_launch("lbt_param_prep");
+}
+
+extern "C" int lbt_noise_fill_multi(const lbt_noise_job* jobs_dev, size_t njobs, uint64_t total_groups, uint64_t seed,
+                                    const uint64_t* dev_step, void* stream) {
+  if (!jobs_dev) return LBT_EINVAL;
+  if (njobs == 0 || total_groups == 0) return LBT_OK;
+  if (njobs > 0x7fffffffull) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const unsigned long long blocks = (total_groups + kThreads - 1) / kThreads;
+  const unsigned grid = (unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16);
+  noise_fill_multi_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_dev, (int)njobs, total_groups,
+                                                                                        seed, dev_step);
+  return check_launch("lbt_noise_fill_multi");
 }

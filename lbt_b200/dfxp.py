@@ -50,6 +50,44 @@ class Runtime:
         self._arena_off = 0
         self._arena_used = 0
         self._arena_on = False
+        self._noise_req = {}         # (quantiser id, n_inner) wanted by fused tensor-core epilogues
+        self._noise_tab = None       # dict(map={key: fp32 view}, jobs=device table, total=groups, keep=[...])
+        self._noise_valid = False
+
+    # ---- per-step noise arena: ONE launch fills the noise vectors the conv epilogues read (same Philox stream) ----
+    def noise_for(self, site, n_inner, device):
+        """The [n_inner] noise vector of `site` for the current step, or None (the kernel then runs Philox itself).
+        Only inside a Trainer step; a vector requested for the first time is available from the next step on."""
+        if self.noise_fn is not None or not self._arena_on:
+            return None
+        key = (site.qid, int(n_inner))
+        tab = self._noise_tab
+        if tab is not None and self._noise_valid and key in tab['map']:
+            return tab['map'][key]
+        self._noise_req[key] = True
+        return None
+
+    def _fill_noise(self, device):
+        if not self._noise_req:
+            return
+        tab = self._noise_tab
+        if tab is None or any(k not in tab['map'] for k in self._noise_req):
+            keys = sorted(self._noise_req)
+            total = sum(-(-n // 4) for _, n in keys)
+            arena = torch.empty(total * 4, dtype=torch.float32, device=device)
+            jobs, m, start = [], {}, 0
+            for qid, n in keys:
+                u = arena[start * 4:start * 4 + n]
+                m[(qid, n)] = u
+                jobs.append(_lib.NoiseJob(u=u.data_ptr(), n=n, offset=Q.make_offset(qid, 0), start=start))
+                start += -(-n // 4)
+            keep = []
+            tab = dict(map=m, jobs=_lib.to_device_table(jobs, device, keep=keep), njobs=len(jobs), total=total,
+                       arena=arena, keep=keep)
+            self._noise_tab = tab
+        _lib.call('lbt_noise_fill_multi', _lib.ptr(tab['jobs']), tab['njobs'], tab['total'], self.seed,
+                  _lib.ptr(self.dev_step), _lib.stream())
+        self._noise_valid = True
 
     # ---- per-step workspace: exact integer sums live in one arena that is zeroed with a single launch ----
     def begin_step(self, device):
@@ -66,6 +104,7 @@ class Runtime:
         if self.prep is not None:
             self.prep.run()
             self._prep_valid = True      # until update_ranges() closes the step
+        self._fill_noise(device)
 
     def zeros_i64(self, n, device):
         """n zeroed int64 slots (16-byte aligned) from the arena; a fresh tensor when the arena is off or full."""
@@ -107,6 +146,7 @@ class Runtime:
         _lib.call('lbt_step_advance', _lib.ptr(self.dev_step), _lib.stream())
         self._arena_on = False           # the step is closed: prepared operands and arena slices are stale now
         self._prep_valid = False
+        self._noise_valid = False
 
     def ranges(self):
         """{quantiser name: integer_bits} — the cheap parity probe (tf.summary of *_range, dfxp:180-190)."""
@@ -247,9 +287,10 @@ class QuantSite(nn.Module):
             kw['mode'] |= Q.STATS_MINMAX
         return Q.quantize(x, self.bits, self.range, **kw)
 
-    def abi(self, n_inner, device):
+    def abi(self, n_inner, device, arena=False):
         """This call site as an ``lbt_qsite`` for the fused kernels (same ids, ranges, Philox stream and
-        statistics block as quantize(), so fused and unfused runs are bit-identical)."""
+        statistics block as quantize(), so fused and unfused runs are bit-identical).  arena=True: take the
+        step's pre-generated noise vector when the runtime has one (tensor-core epilogues)."""
         rt = self.runtime
         qs = _lib.QSiteStruct(bits=self.bits, stats_minmax=int(self.target == 0.0), ib=self.range.data_ptr(),
                               noise=0, seed=rt.seed, offset=Q.make_offset(self.qid, 0),
@@ -258,6 +299,10 @@ class QuantSite(nn.Module):
             nz = rt.noise_fn(self, n_inner, device).contiguous()
             qs.noise, qs.offset = nz.data_ptr(), 0
             qs._keep = nz                 # the kernel is stream-ordered before the allocator can reuse it
+        elif arena:
+            nz = rt.noise_for(self, n_inner, device)
+            if nz is not None:
+                qs.noise = nz.data_ptr()
         return qs
 
     def extra_repr(self):
@@ -360,7 +405,7 @@ def _gather_ok(C, Cout, kh, kw):
         return False
     kcp = (kh * kw * (C // 16) + 1) & ~1
     bn = 16 if Cout <= 16 else (32 if Cout <= 32 else (64 if Cout <= 64 else 128))
-    return kcp * bn * 16 + 2 * 16384 + 1024 <= 200 * 1024 and kh * kw * C <= 65536
+    return kcp * bn * 16 + 2 * 16384 + 1024 <= 200 * 1024 and kh * kw * C <= 65536 and kcp <= 256 and kh * kw <= 64 and kh <= 16 and kw <= 16
 
 
 def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d,
@@ -535,7 +580,7 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
             w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
             _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
                            layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
-        elif layer.implicit and _gather_ok(Cout, Cin, kh, kw):
+        elif layer.implicit and _gather_ok(Cout, Cin, kh, kw) and sh <= 4 and sw <= 4:
             # any stride: the transposed gather runs in the kernel's loader warps (lbt_conv_i8_dgrad), no im2col matrix
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             _lib.call('lbt_conv_i8_dgrad', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2), Q.MANT_S8, w2.stride(0),
@@ -930,7 +975,7 @@ class _ConvBNFn(torch.autograd.Function):
         sums = rt.zeros_i64(2 * Cout, dev)
         k1 = torch.empty(N, OH, OW, Cout, dtype=torch.int8, device=dev)
         _conv_fprop(conv, geom, xm, xkind, prep, wm, None, None,
-                    bnq=(norm.qX.abi(OH * OW * Cout, dev), k1, sums))                          # dfxp:291 + :584-588
+                    bnq=(norm.qX.abi(OH * OW * Cout, dev, arena=True), k1, sums))                          # dfxp:291 + :584-588
         gq, bq = _bn_params(resc, gamma, beta)
         add_ = _to_mem(add) if add is not None else None
         k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
@@ -942,6 +987,7 @@ class _ConvBNFn(torch.autograd.Function):
         if nm is None:
             nm = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.mark_non_differentiable(nm)
+        ctx.set_materialize_grads(False)      # no zero-filled "gradient" for the mantissa output
         return _from_mem(out), nm
 
     @staticmethod
