@@ -555,24 +555,45 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
 }
 
 // ---- host helpers ----------------------------------------------------------------------------
-int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid) {
+// Resident CTAs per SM of a kernel with `smem` dynamic bytes (cached per kernel and device).
+template <typename K>
+int ctas_per_sm(K kernel, size_t smem) {
+  static int cache[16] = {};
+  const int dev = device_info().device;
+  if (dev < 0 || dev >= 16) return 1;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+// Tiles = (256-float4 column chunks) x (groups of batch rows).  These tensors are small (a few MB): what matters is
+// that the launch is ONE balanced wave of resident CTAs — a 1.15-wave grid costs two CTA latencies.  So the row
+// groups are sized to give at most `occ * SMs` tiles; only tensors with more column chunks than that run a
+// persistent multi-tile loop.
+int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid, int occ) {
   if (C <= 0 || (C & 3) || n_inner % (size_t)C) return LBT_EUNSUPPORTED;
   if (n_inner / 4 >= 0xffffffffull) return LBT_EUNSUPPORTED;
-  if (n_outer * n_inner >= (1ull << 36)) return LBT_EUNSUPPORTED;  // keeps every thread's 32-bit partial sums exact
+  if (n_outer * n_inner >= (1ull << 33)) return LBT_EUNSUPPORTED;  // keeps every thread's 32-bit partial sums exact
   const DeviceInfo& di = device_info();
   t.n_outer = n_outer;
   t.n_inner = n_inner;
   t.C = C;
   t.n_vec = (uint32_t)(n_inner / 4);
   t.chunks = (t.n_vec + kThreads - 1) / kThreads;
-  uint32_t rpg = 32;
-  if (rpg > n_outer) rpg = (uint32_t)n_outer;
-  while (rpg > 1 && (uint64_t)t.chunks * ((n_outer + rpg - 1) / rpg) < 2ull * di.sm_count) rpg = (rpg + 1) / 2;
-  t.rows_per_group = rpg;
-  t.total_tiles = (uint64_t)t.chunks * ((n_outer + rpg - 1) / rpg);
-  const int groups = C >> 2;
-  t.fixed_channels = (groups <= kThreads && (kThreads % groups) == 0) ? 1 : 0;
-  const uint64_t cap = (uint64_t)di.sm_count * 6;
+  const uint64_t cap = (uint64_t)di.sm_count * (uint64_t)(occ < 1 ? 1 : occ);
+  uint64_t groups = cap / t.chunks;
+  if (groups < 1) groups = 1;
+  if (groups > n_outer) groups = n_outer;
+  uint64_t rpg = (n_outer + groups - 1) / groups;
+  if (rpg > 4096) rpg = 4096;                 // 32-bit per-thread partial sums: <= 4096 rows x 2^14 per tile visit
+  groups = (n_outer + rpg - 1) / rpg;
+  t.rows_per_group = (uint32_t)rpg;
+  t.total_tiles = (uint64_t)t.chunks * groups;
+  const int cgroups = C >> 2;
+  t.fixed_channels = (cgroups <= kThreads && (kThreads % cgroups) == 0) ? 1 : 0;
   grid = (unsigned)(t.total_tiles < cap ? t.total_tiles : cap);
   return LBT_OK;
 }
@@ -621,7 +642,7 @@ extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_i
   LBT_REQUIRE_ARCH();
   Fwd1Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd1_kernel, (size_t)2 * C * 8));
   if (rc) return rc;
   p.x = x;
   p.q = make_site(bits, ib, noise, seed, offset, dev_step, counters, stats_minmax);
@@ -656,7 +677,7 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   LBT_REQUIRE_ARCH();
   Fwd2Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel, (size_t)4 * C * 4));
   if (rc) return rc;
   p.k1 = k1;
   p.bits1 = bits1;
@@ -700,7 +721,7 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   LBT_REQUIRE_ARCH();
   Bwd1Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel, (size_t)4 * C * 8));
   if (rc) return rc;
   p.g = g;
   p.out = out;
@@ -736,7 +757,7 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   LBT_REQUIRE_ARCH();
   Bwd2Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel, (size_t)4 * C * 4));
   if (rc) return rc;
   p.kg1 = kg1;
   p.k1 = k1;
