@@ -375,27 +375,39 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
   if (vec) {
     p.n_vec = (uint32_t)(n_inner / 4);
     p.chunks = (p.n_vec + kThreads - 1) / kThreads;
-    // rows per tile: as many as requested, fewer when the tensor is too small to fill the chip
-    uint32_t rpg = (uint32_t)g_rows_per_group;
-    if (rpg > n_outer) rpg = (uint32_t)n_outer;
-    while (rpg > 1 && (uint64_t)p.chunks * ((n_outer + rpg - 1) / rpg) < 2ull * di.sm_count) rpg = (rpg + 1) / 2;
-    p.rows_per_group = rpg;
-    p.total_tiles = (uint64_t)p.chunks * ((n_outer + rpg - 1) / rpg);
-    const unsigned grid = (unsigned)(p.total_tiles < cap ? p.total_tiles : cap);
+    void (*kern)(const QParams) = nullptr;
     switch (mode) {
-      case LBT_ROUND_NEAREST:
-        if (minmax) quantize_vec_kernel<0, true><<<grid, kThreads, 0, st>>>(p);
-        else quantize_vec_kernel<0, false><<<grid, kThreads, 0, st>>>(p);
-        break;
-      case LBT_ROUND_STOCHASTIC_NOISE:
-        if (minmax) quantize_vec_kernel<1, true><<<grid, kThreads, 0, st>>>(p);
-        else quantize_vec_kernel<1, false><<<grid, kThreads, 0, st>>>(p);
-        break;
-      default:
-        if (minmax) quantize_vec_kernel<2, true><<<grid, kThreads, 0, st>>>(p);
-        else quantize_vec_kernel<2, false><<<grid, kThreads, 0, st>>>(p);
-        break;
+      case LBT_ROUND_NEAREST: kern = minmax ? quantize_vec_kernel<0, true> : quantize_vec_kernel<0, false>; break;
+      case LBT_ROUND_STOCHASTIC_NOISE: kern = minmax ? quantize_vec_kernel<1, true> : quantize_vec_kernel<1, false>; break;
+      default: kern = minmax ? quantize_vec_kernel<2, true> : quantize_vec_kernel<2, false>; break;
     }
+    // One balanced wave of resident CTAs: a grid of 1.15 waves costs two CTA latencies on the few-MB tensors of a
+    // training step, and a persistent grid larger than the resident set leaves the last wave part empty.
+    static int occ_cache[16][3][2] = {};
+    int& occ = occ_cache[di.device][mode][minmax ? 1 : 0];
+    if (occ == 0) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kThreads, 0) != cudaSuccess || n < 1) n = 1;
+      occ = n;
+    }
+    const uint64_t wave = (uint64_t)di.sm_count * (uint64_t)(g_blocks_per_sm < occ ? g_blocks_per_sm : occ);
+    uint64_t rpg, grid64;
+    const uint64_t big_tiles = (uint64_t)p.chunks * ((n_outer + g_rows_per_group - 1) / g_rows_per_group);
+    if (big_tiles >= 4 * wave) {
+      // large tensor: many tiles per CTA; a grid of several CTA generations per SM evens out the tail (measured)
+      rpg = (uint64_t)g_rows_per_group;
+      grid64 = (uint64_t)di.sm_count * (uint64_t)g_blocks_per_sm;
+    } else {
+      uint64_t groups = wave / p.chunks;
+      if (groups < 1) groups = 1;
+      if (groups > n_outer) groups = n_outer;
+      rpg = (n_outer + groups - 1) / groups;
+      grid64 = wave;
+    }
+    p.rows_per_group = (uint32_t)rpg;
+    p.total_tiles = (uint64_t)p.chunks * ((n_outer + rpg - 1) / rpg);
+    const unsigned grid = (unsigned)(p.total_tiles < grid64 ? p.total_tiles : grid64);
+    kern<<<grid, kThreads, 0, st>>>(p);
   } else {
     const uint64_t n = (uint64_t)n_outer * n_inner;
     const uint64_t blocks = (n + kThreads - 1) / kThreads;
