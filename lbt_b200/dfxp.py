@@ -19,6 +19,7 @@ All arithmetic on tensors runs in the library's kernels (quantiser, im2col, tcge
 there is no PyTorch/CPU fallback for them.  Range variables stay constant during a step and are
 advanced once per step by ``Runtime.update_ranges()`` (read-then-update).
 """
+import contextlib
 import ctypes
 import math
 
@@ -50,6 +51,8 @@ class Runtime:
         self._arena_off = 0
         self._arena_used = 0
         self._arena_on = False
+        self._side = None            # side stream: wgrad runs beside dgrad (independent consumers of the same gradient)
+        self.overlap = True
         self._noise_req = {}         # (quantiser id, n_inner) wanted by fused tensor-core epilogues
         self._noise_tab = None       # dict(map={key: fp32 view}, jobs=device table, total=groups, keep=[...])
         self._noise_valid = False
@@ -117,6 +120,11 @@ class Runtime:
             self._arena_used = off + n_al
             return self._arena[off:off + n]
         return torch.zeros(int(n), dtype=torch.int64, device=device)
+
+    def side_stream(self, device):
+        if self._side is None or self._side.device != torch.device(device):
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
 
     def register(self, site):
         site.qid = len(self.sites)
@@ -532,36 +540,43 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     Kf = kh * kw * Cin
     dW = db = dx = None
     rt = layer.qX.runtime
-    # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs ----
+    # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs.  It shares only its
+    # inputs with dgrad, so (inside a Trainer step) it runs on a side stream: a parallel branch of the step's graph ----
+    fork = need_dw and need_dx and rt.overlap and rt._arena_on and _lib.profiler is None
+    main = torch.cuda.current_stream(dev) if fork else None
+    side = rt.side_stream(dev) if fork else None
+    if fork:
+        side.wait_stream(main)
     if need_dw:
-        acc = rt.zeros_i64(Kf * Cout, dev).view(Kf, Cout)
-        at = gt = None
-        if xkind == Q.MANT_S9C3:
-            if not _implicit_ok(Cout, 1, 1):
-                raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
-            # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
-            acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
-            _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                      sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
-            a = acc16.view(kh * kw, 16, Cout)
-            acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
-        elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
-            # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
-            _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                      sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
-        else:
-            gt = _transpose_bytes(g2)                                                       # [Cout, M]
-            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
-            at = _transpose_bytes(A)                                                        # [Kf*segs, M]
-        if at is None:
-            pass
-        elif xkind == Q.MANT_S16:
-            G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
-            G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
-        else:
-            G.gemm_i8_acc64(at, gt, acc, alpha=1)
-        dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
-                        add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))         # dfxp:302
+      with (torch.cuda.stream(side) if fork else contextlib.nullcontext()):
+          acc = rt.zeros_i64(Kf * Cout, dev).view(Kf, Cout)
+          at = gt = None
+          if xkind == Q.MANT_S9C3:
+              if not _implicit_ok(Cout, 1, 1):
+                  raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
+              # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
+              acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
+              _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+              a = acc16.view(kh * kw, 16, Cout)
+              acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+          elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
+              # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
+              _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+          else:
+              gt = _transpose_bytes(g2)                                                       # [Cout, M]
+              A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+              at = _transpose_bytes(A)                                                        # [Kf*segs, M]
+          if at is None:
+              pass
+          elif xkind == Q.MANT_S16:
+              G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2)                                      # k = 2*hi + lo
+              G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=1)
+          else:
+              G.gemm_i8_acc64(at, gt, acc, alpha=1)
+          dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                          add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))         # dfxp:302
     if need_db:
         db = _emit_grad(rt, layer.bias, _colsum(g2, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))      # dfxp:304
     # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
@@ -590,6 +605,8 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
             G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+    if fork:
+        main.wait_stream(side)     # join before anything downstream (or the allocator) can touch the operands
     return dx, dW, db
 
 
