@@ -328,8 +328,7 @@ def run_native(a):
     gemm_tops = (gemm['ops'] / 1e12) / (gemm['ms'] * 1e-3) if gemm and gemm['ms'] > 0 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     # ---- CPU baseline (the oracle port on this box's host cores), N=1 only -------------------------
@@ -366,8 +365,20 @@ def run_native(a):
         for k, d in breakdown.items():
             print('[breakdown] %-28s %s' % (k, d), file=sys.stderr)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    _finish(world)
+
+
+def _finish(world):
+    """End of a rank.  With several ranks the NCCL communicator is referenced by the captured CUDA graph, and tearing
+    the process group down under it has been seen to block forever (the measurement itself is complete): skip the
+    teardown and leave with a hard exit once everything is flushed."""
+    if world <= 1:
+        return
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':
