@@ -365,6 +365,17 @@ int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t
                      const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
                      const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream);
 
+/*
+ * tf.nn.max_pool on an NHWC fp32 tensor (`MaxPool_q`, dynamic_fixed_point.py:993-1006): 'SAME' padding ignores
+ * out-of-range taps (pad_top / pad_left = TF's pad_before), 'VALID' is pad 0.  C % 4 == 0.  idx[N,OH,OW,C] receives the
+ * winning tap r*k + s (first maximum in scan order); lbt_maxpool_bwd routes g[N,OH,OW,C] back through it as a gather
+ * over the windows covering each input pixel (no atomics; dx is written exactly once).
+ */
+int lbt_maxpool_fwd(const float* x, int N, int H, int W, int C, int k, int s, int pad_top, int pad_left, int OH, int OW,
+                    float* out, uint8_t* idx, void* stream);
+int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H, int W, int C, int k, int s, int pad_top,
+                    int pad_left, int OH, int OW, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

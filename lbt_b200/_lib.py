@@ -39,6 +39,8 @@ SIGNATURES = {
                           [c_void_p, c_int, c_int, c_void_p]),
     'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
     'lbt_colsum_i': (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
+    'lbt_maxpool_fwd': (c_int, [c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),
+    'lbt_maxpool_bwd': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p]),
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
                                  c_void_p]),
     'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),
@@ -142,8 +144,13 @@ class Profiler:
     """Brackets every C-ABI launch with CUDA events on the launching stream (bench.py's live roofline
     measurement).  ``meta`` carries the algorithmic bytes / ops of the launch."""
 
-    def __init__(self):
+    def __init__(self, external=False):
         self.records = []          # (name, start_event, end_event, meta)
+        self.external = external   # True: events are recorded as nodes of a CUDA graph being captured; every replay
+                                   # re-times every launch back to back on the device (no host launch gaps)
+
+    def event(self):
+        return torch.cuda.Event(enable_timing=True, external=True) if self.external else torch.cuda.Event(enable_timing=True)
 
     def summary(self):
         """{name: dict(launches, ms, bytes, ops)} after a synchronize."""
@@ -167,7 +174,7 @@ def call(name, *args, meta=None):
     if profiler is None:
         check(fn(*args))
         return
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a, b = profiler.event(), profiler.event()
     a.record()
     rc = fn(*args)
     b.record()

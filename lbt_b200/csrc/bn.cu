@@ -605,12 +605,22 @@ int make_tiling(Tiling& t, size_t n_outer, size_t n_inner, int C, unsigned& grid
   t.n_vec = (uint32_t)(n_inner / 4);
   t.chunks = (t.n_vec + kThreads - 1) / kThreads;
   const uint64_t cap = (uint64_t)di.sm_count * (uint64_t)(occ < 1 ? 1 : occ);
-  uint64_t groups = cap / t.chunks;
-  if (groups < 1) groups = 1;
-  if (groups > n_outer) groups = n_outer;
-  uint64_t rpg = (n_outer + groups - 1) / groups;
-  if (rpg > 4096) rpg = 4096;                 // 32-bit per-thread partial sums: <= 4096 rows x 2^14 per tile visit
-  groups = (n_outer + rpg - 1) / rpg;
+  // pick the number of row groups g that minimises (waves of resident CTAs) x (rows per CTA + fixed cost per wave)
+  uint64_t best_g = 1, best_cost = ~0ull;
+  const uint64_t gmax = n_outer < 4096 ? n_outer : 4096;
+  for (uint64_t g = 1; g <= gmax; ++g) {
+    const uint64_t rows = (n_outer + g - 1) / g;
+    if (rows > 4096) continue;              // 32-bit per-thread partial sums: <= 4096 rows x 2^14 per tile visit
+    const uint64_t gg = (n_outer + rows - 1) / rows;
+    const uint64_t waves = (t.chunks * gg + cap - 1) / cap;
+    const uint64_t cost = waves * (rows + 3);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best_g = gg;
+    }
+  }
+  uint64_t rpg = (n_outer + best_g - 1) / best_g;
+  const uint64_t groups = (n_outer + rpg - 1) / rpg;
   t.rows_per_group = (uint32_t)rpg;
   t.total_tiles = (uint64_t)t.chunks * groups;
   const int cgroups = C >> 2;

@@ -426,7 +426,8 @@ def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW,
               kh, kw, sh, sw, pt, pl, OH, OW, _lib.ptr(ib_src), _lib.ptr(ib_w), int(exp_const), _lib.ptr(bias),
               _lib.ptr(out2d), out2d.stride(0) if out2d is not None else Cout,
               ctypes.addressof(qs) if qs is not None else None, _lib.ptr(k_out), _lib.ptr(sums), _lib.stream(),
-              meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C))
+              meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C,
+                        bytes=N * H * W * C + Cout * kh * kw * C + N * OH * OW * Cout * (1 if qs is not None else 4)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -557,13 +558,15 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
               # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
               acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
               _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(),
+                        meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
               a = acc16.view(kh * kw, 16, Cout)
               acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
           elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
               # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
               _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(),
+                        meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * Cin + M * Cout + 8 * Kf * Cout))
           else:
               gt = _transpose_bytes(g2)                                                       # [Cout, M]
               A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
@@ -600,7 +603,8 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             _lib.call('lbt_conv_i8_dgrad', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2), Q.MANT_S8, w2.stride(0),
                       Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
-                      _lib.ptr(dx), Cin, _lib.stream(), meta=dict(ops=2 * N * H * W * Cin * K2))
+                      _lib.ptr(dx), Cin, _lib.stream(),
+                      meta=dict(ops=2 * N * H * W * Cin * K2, bytes=N * OH * OW * Cout + Cin * K2 + N * H * W * Cin * 4))
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
@@ -1140,6 +1144,32 @@ class ReLU_q(nn.ReLU):
         return 'ReLU'
 
 
+class _MaxPoolFn(torch.autograd.Function):
+    """lbt_maxpool_fwd / lbt_maxpool_bwd on the NHWC memory of a channels_last tensor."""
+
+    @staticmethod
+    def forward(ctx, x, k, s, pt, pl, OH, OW):
+        x_ = _to_mem(x)
+        N, H, W, C = x_.shape
+        out = torch.empty(N, OH, OW, C, dtype=torch.float32, device=x.device)
+        idx = torch.empty(N, OH, OW, C, dtype=torch.uint8, device=x.device)
+        _lib.call('lbt_maxpool_fwd', _lib.ptr(x_), N, H, W, C, k, s, pt, pl, OH, OW, _lib.ptr(out), _lib.ptr(idx),
+                  _lib.stream(), meta=dict(bytes=x_.numel() * 4 + out.numel() * 5))
+        ctx.geom = (N, H, W, C, k, s, pt, pl, OH, OW)
+        ctx.save_for_backward(idx)
+        return _from_mem(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        N, H, W, C, k, s, pt, pl, OH, OW = ctx.geom
+        g_ = _to_mem(g)
+        dx = torch.empty(N, H, W, C, dtype=torch.float32, device=g.device)
+        _lib.call('lbt_maxpool_bwd', _lib.ptr(g_), _lib.ptr(idx), N, H, W, C, k, s, pt, pl, OH, OW, _lib.ptr(dx),
+                  _lib.stream(), meta=dict(bytes=g_.numel() * 5 + dx.numel() * 4))
+        return _from_mem(dx), None, None, None, None, None, None
+
+
 class MaxPool_q(nn.Module):
     """tf.nn.max_pool with 'SAME' (padding ignored in the max) or 'VALID' (dfxp:993-1006)."""
 
@@ -1148,11 +1178,17 @@ class MaxPool_q(nn.Module):
         self.k, self.s, self.padding = kernel_size, stride, padding
 
     def forward(self, x):
+        H, W = x.shape[2], x.shape[3]
         if self.padding == 'SAME':
-            _, pt, pb = same_pad(x.shape[2], self.k, self.s)
-            _, pl, pr = same_pad(x.shape[3], self.k, self.s)
-            if pt or pb or pl or pr:
-                x = F.pad(x, (pl, pr, pt, pb), value=float('-inf'))
+            OH, pt, pb = same_pad(H, self.k, self.s)
+            OW, pl, pr = same_pad(W, self.k, self.s)
+        else:
+            pt = pb = pl = pr = 0
+            OH, OW = (H - self.k) // self.s + 1, (W - self.k) // self.s + 1
+        if x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype == torch.float32 and self.k <= 15:
+            return _MaxPoolFn.apply(x, self.k, self.s, pt, pl, OH, OW)
+        if pt or pb or pl or pr:
+            x = F.pad(x, (pl, pr, pt, pb), value=float('-inf'))
         return F.max_pool2d(x, self.k, self.s)
 
 

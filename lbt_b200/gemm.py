@@ -36,13 +36,14 @@ def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=N
         _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                   _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), None, None, N, 1, 1,
                   ctypes.addressof(qs), _lib.ptr(k_out), _lib.ptr(sums), int(rpi), _lib.stream(),
-                  meta=dict(ops=2 * M * N * K))
+                  meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + M * N))
         return None
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                                       _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), _lib.ptr(out), None,
-                                      out.stride(0), 1, 1, None, None, None, 0, _lib.stream(), meta=dict(ops=2 * M * N * K))
+                                      out.stride(0), 1, 1, None, None, None, 0, _lib.stream(),
+              meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + 4 * M * N))
     return out
 
 
@@ -59,7 +60,8 @@ def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
         k_splits = max(1, sms // max(1, tiles))
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
                                       None, None, 0, None, None, _lib.ptr(acc64), N, int(alpha), int(k_splits),
-                                      None, None, None, 0, _lib.stream(), meta=dict(ops=2 * M * N * K))
+                                      None, None, None, 0, _lib.stream(),
+              meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + 8 * M * N))
     return acc64
 
 

@@ -70,3 +70,30 @@ def test_fused_unit_hands_mantissas_to_the_next_conv():
     assert seen['block-2'] == (True, True)          # conv2 consumed bn1's fused mantissas, no fp32 tensor
     assert seen['block-1'] == (False, False)
     assert y.shape == x.shape and bool(torch.isfinite(y).all())
+
+
+@pytest.mark.parametrize('N,C,H,W,k,s,padding', [(3, 8, 9, 7, 3, 2, 'SAME'), (2, 64, 32, 32, 3, 2, 'SAME'),
+                                                 (2, 16, 8, 8, 2, 2, 'VALID'), (1, 4, 5, 5, 3, 1, 'SAME'), (2, 12, 11, 13, 5, 3, 'SAME')])
+def test_maxpool_kernels_equal_torch(N, C, H, W, k, s, padding):
+    """lbt_maxpool_fwd/bwd vs -inf padding + torch max_pool2d (the oracle's restatement of tf.nn.max_pool), with exact
+    ties (post-ReLU zeros): forward and gradient bit-identical."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(N * 100 + C)
+    x = torch.relu(torch.randn(N, C, H, W, generator=g)).mul(4).round().div(4)         # many ties, many zeros
+    pool = D.MaxPool_q(k, s, padding)
+    xa = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ya = pool(xa)
+    xb = x.clone().requires_grad_(True)
+    if padding == 'SAME':
+        _, pt, pb = D.same_pad(H, k, s)
+        _, pl, pr = D.same_pad(W, k, s)
+        xp = F.pad(xb, (pl, pr, pt, pb), value=float('-inf'))
+    else:
+        xp = xb
+    yb = F.max_pool2d(xp, k, s)
+    assert ya.shape == yb.shape
+    assert torch.equal(ya.cpu(), yb)
+    go = torch.randn(yb.shape, generator=g)
+    ya.backward(go.cuda())
+    yb.backward(go)
+    assert torch.equal(xa.grad.cpu(), xb.grad)
