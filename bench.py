@@ -32,7 +32,8 @@ WORKLOADS = {
     'resnet20': ('CIFAR10_Resnet20', 32, 10, 256, 8, None),
     'cifar10': ('CIFAR10_Model', 32, 10, 128, 8, None),
     'resnet18': ('Resnet18', 224, 1000, 256, 8, None),
-    'resnet50': ('Resnet50', 224, 1000, 128, 8, None),
+    'resnet50': ('Resnet50', 224, 1000, 128, 8, 16),          # BASELINE config 5: 8-bit W/A + 16-bit G
+    'resnet50_g8': ('Resnet50', 224, 1000, 128, 8, None),
 }
 
 

@@ -232,6 +232,13 @@ int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C,
                       int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
                       int alpha, int k_splits, void* stream);
 
+/*
+ * Mantissas wider than 8 bits (the 16-bit gradients of BASELINE config 5) as two tensor-core operands:
+ * k = 256 * hi + lo with hi = k >> 8 (s8) and lo = k & 255 (u8).  The GEMMs run once per half and add
+ * alpha * acc into the int64 accumulator with alpha = 256 and 1 (exact).
+ */
+int lbt_split_s16(const int16_t* in, size_t n, int8_t* hi, uint8_t* lo, void* stream);
+
 /* out[c*ld_out + r] = in[r*ld_in + c] for an R x C byte matrix (operand re-majoring for wgrad). */
 int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in, void* out, size_t ld_out,
                      void* stream);

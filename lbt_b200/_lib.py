@@ -37,6 +37,7 @@ SIGNATURES = {
                           [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     'lbt_conv_i8_wgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_int] * 9 +
                           [c_void_p, c_int, c_int, c_void_p]),
+    'lbt_split_s16': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
     'lbt_colsum_i': (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
     'lbt_maxpool_fwd': (c_int, [c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),

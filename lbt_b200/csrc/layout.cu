@@ -205,3 +205,43 @@ extern "C" int lbt_colsum_i(const void* in, int kind, size_t R, size_t C, int64_
                                                   reinterpret_cast<long long*>(acc64));
   return check_launch("lbt_colsum_i");
 }
+
+// ---- 16-bit mantissas as two 8-bit tensor-core operands: k = 256 * hi + lo, hi = k >> 8 (s8), lo = k & 255 (u8) ----
+namespace lbt {
+namespace {
+__global__ void __launch_bounds__(256) split_s16_kernel(const int16_t* __restrict__ in, size_t n, int8_t* __restrict__ hi,
+                                                        uint8_t* __restrict__ lo) {
+  const size_t nv = n / 8;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nv; i += (size_t)gridDim.x * 256) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t h[2] = {0, 0}, l[2] = {0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t k = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+      h[j >> 2] |= (k >> 8) << ((j & 3) * 8);
+      l[j >> 2] |= (k & 0xffu) << ((j & 3) * 8);
+    }
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(h[0], h[1]);
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(l[0], l[1]);
+  }
+  for (size_t i = nv * 8 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const int k = in[i];
+    hi[i] = (int8_t)(k >> 8);
+    lo[i] = (uint8_t)(k & 0xff);
+  }
+}
+}  // namespace
+}  // namespace lbt
+
+extern "C" int lbt_split_s16(const int16_t* in, size_t n, int8_t* hi, uint8_t* lo, void* stream) {
+  if (!in || !hi || !lo) return LBT_EINVAL;
+  if (n == 0) return LBT_OK;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(hi) & 7) || (reinterpret_cast<uintptr_t>(lo) & 7))
+    return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const size_t blocks = (n / 8 + 255) / 256 + 1;
+  const size_t cap = (size_t)lbt::device_info().sm_count * 8;
+  lbt::split_s16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, n, hi, lo);
+  return lbt::check_launch("lbt_split_s16");
+}

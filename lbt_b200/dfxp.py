@@ -614,6 +614,84 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     return dx, dW, db
 
 
+def _split16(gm16):
+    """s16 mantissas -> (hi s8, lo u8) with k = 256*hi + lo (lbt_split_s16)."""
+    hi = torch.empty(gm16.shape, dtype=torch.int8, device=gm16.device)
+    lo = torch.empty(gm16.shape, dtype=torch.uint8, device=gm16.device)
+    _lib.call('lbt_split_s16', _lib.ptr(gm16), gm16.numel(), _lib.ptr(hi), _lib.ptr(lo), _lib.stream(),
+              meta=dict(bytes=gm16.numel() * 4))
+    return hi, lo
+
+
+def _conv_backward16(layer, geom, xm, xkind, wm, prep, gm16, need_dx, need_dw, need_db):
+    """dfxp:302-305 with a gradient quantiser wider than 8 bits (BASELINE config 5: 16-bit G): the mantissas are split
+    k = 256*hi + lo and every product runs twice on the 8-bit tensor cores, alpha = 256 / 1 into the exact int64
+    accumulators; the input gradient is finished from int64 as well, so it is still RN_fp32(exact integer dot * 2^e)."""
+    N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
+    xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
+    dev = gm16.device
+    M = N * OH * OW
+    Kf = kh * kw * Cin
+    rt = layer.qX.runtime
+    hi, lo = _split16(gm16)
+    halves = ((hi, Q.MANT_S8, 256), (lo, Q.MANT_U8, 1))
+    dW = db = dx = None
+    if need_dw:
+        acc = rt.zeros_i64(Kf * Cout, dev).view(Kf, Cout)
+        if xkind == Q.MANT_S9C3:
+            if not _implicit_ok(Cout, 1, 1):
+                raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
+            acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
+            for g_, kind, alpha in halves:
+                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
+                          pt, pl, OH, OW, _lib.ptr(acc16), alpha, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+            a = acc16.view(kh * kw, 16, Cout)
+            acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+        elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
+            for g_, kind, alpha in halves:
+                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
+                          pt, pl, OH, OW, _lib.ptr(acc), alpha, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+        else:
+            A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
+            at = _transpose_bytes(A)
+            for g_, kind, alpha in halves:
+                gt = _transpose_bytes(g_.view(M, Cout))
+                if xkind == Q.MANT_S16:
+                    G.gemm_i8_acc64(at[:Kf], gt, acc, alpha=2 * alpha)
+                    G.gemm_i8_acc64(at[2 * Kf:], gt, acc, alpha=alpha)
+                else:
+                    G.gemm_i8_acc64(at, gt, acc, alpha=alpha)
+        dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
+                        add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))
+    if need_db:
+        db = _emit_grad(rt, layer.bias, _colsum(gm16.view(M, Cout), Q.MANT_S16, rt), ibA=layer.qG.range, exp_const=-(gb - 1))
+    if need_dx:
+        K2 = kh * kw * Cout
+        e = -(gb - 1) - (wb - 1)
+        pw2 = prep['w2'] if prep is not None else None
+        if prep is not None and pw2 is None:
+            raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
+        acc = torch.zeros(N * H * W, Cin, dtype=torch.int64, device=dev)
+        one_by_one = kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0
+        rot = bool(prep is not None and prep.get('rot180'))
+        if one_by_one:
+            w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
+        elif rot:
+            w2 = pw2                                      # rot180-packed: dX = conv(G, rot180 W), padding k - 1 - pad
+        else:
+            w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
+        for g_, kind, alpha in halves:
+            if one_by_one:
+                A2 = g_.view(M, Cout)
+            elif rot:
+                A2 = _im2col(g_, kind, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
+            else:
+                A2 = _im2col(g_, kind, H, W, kh, kw, sh, sw, pt, pl, True)
+            G.gemm_i8_acc64(A2, w2, acc, alpha=alpha, k_splits=1)
+        dx = G.acc64_finalize(acc, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e).view(N, H, W, Cin)
+    return dx, dW, db
+
+
 class _QConv2dFn(torch.autograd.Function):
     """dfxp:272-305 on integer mantissas: quantise X (bits+1), W, [b]; implicit GEMM fprop; in backward
     quantise the gradient, then wgrad (+2*wd*W), bias grad, dgrad."""
@@ -634,9 +712,14 @@ class _QConv2dFn(torch.autograd.Function):
     def backward(ctx, dy):
         layer = ctx.layer
         xm, wm = ctx.saved_tensors
-        if layer.qG.bits > 8:
-            raise _lib.LbtError('Conv2d_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
         dy = _mem_contig(dy).permute(0, 2, 3, 1)
+        needs = (ctx.needs_input_grad[0], ctx.needs_input_grad[1], layer.qb is not None and ctx.needs_input_grad[2])
+        if layer.qG.bits > 8:                                                                  # 16-bit G: hi/lo split
+            if layer.qG.bits > 16:
+                raise _lib.LbtError('Conv2d_q: gradient quantisers wider than 16 bits are not supported')
+            _, gm16 = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S16)
+            dx, dW, db = _conv_backward16(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm16, *needs)
+            return (dx.permute(0, 3, 1, 2) if dx is not None else None), dW, db, None
         _, gm = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S8)                    # dfxp:300
         dx, dW, db = _conv_backward(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, ctx.needs_input_grad[0],
                                     ctx.needs_input_grad[1], layer.qb is not None and ctx.needs_input_grad[2])
@@ -722,12 +805,32 @@ class _QLinearFn(torch.autograd.Function):
         layer = ctx.layer
         xm, wm, weight = ctx.saved_tensors
         xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
-        if gb > 8:
-            raise _lib.LbtError('Linear_q: gradients wider than 8 bits need the hi/lo GEMM split (not built yet)')
-        _, gm = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S8)       # dfxp:453
         In, Out = weight.shape
         rt = layer.qX.runtime
         dX = dW = db = None
+        if gb > 8:                                                                             # 16-bit G: hi/lo split
+            if gb > 16:
+                raise _lib.LbtError('Linear_q: gradient quantisers wider than 16 bits are not supported')
+            _, gm16 = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S16)
+            hi, lo = _split16(gm16)
+            halves = ((hi, 256), (lo, 1))
+            if ctx.needs_input_grad[1]:
+                acc = rt.zeros_i64(In * Out, dy.device).view(In, Out)
+                xt = _transpose_bytes(xm)
+                for g_, alpha in halves:
+                    G.gemm_i8_acc64(xt, _transpose_bytes(g_), acc, alpha=alpha, k_splits=1)
+                dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range,
+                                exp_const=-(xb - 1) - (gb - 1), add_scale=2 * layer.weight_decay)
+            if layer.qb is not None and ctx.needs_input_grad[2]:
+                db = _emit_grad(rt, layer.bias, _colsum(gm16, Q.MANT_S16, rt), ibA=layer.qG.range, exp_const=-(gb - 1))
+            if ctx.needs_input_grad[0]:
+                w2 = ctx.prep['w2'] if ctx.prep is not None else _as_operand(wm)
+                acc = torch.zeros(gm16.shape[0], In, dtype=torch.int64, device=dy.device)
+                for g_, alpha in halves:
+                    G.gemm_i8_acc64(_as_operand(g_), w2, acc, alpha=alpha, k_splits=1)
+                dX = G.acc64_finalize(acc, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=-(gb - 1) - (wb - 1))
+            return dX, dW, db, None
+        _, gm = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S8)       # dfxp:453
         if ctx.needs_input_grad[1]:
             acc = rt.zeros_i64(In * Out, dy.device).view(In, Out)
             G.gemm_i8_acc64(_transpose_bytes(xm), _transpose_bytes(gm), acc, alpha=1, k_splits=1)

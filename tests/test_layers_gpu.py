@@ -59,12 +59,28 @@ CONV_CASES = [
 
 @pytest.mark.parametrize('Cin,Cout,k,s,H,B,bias,signed', CONV_CASES)
 def test_conv2d_q_forward_backward(Cin, Cout, k, s, H, B, bias, signed):
+    _conv_case(Cin, Cout, k, s, H, B, bias, signed, None)
+
+
+@pytest.mark.parametrize('Cin,Cout,k,s,H,B,bias,signed', [
+    (16, 32, 3, 1, 8, 4, False, False), (32, 64, 3, 2, 9, 3, True, False), (64, 64, 1, 1, 6, 3, False, False),
+    (3, 16, 3, 1, 10, 4, False, True), (128, 256, 3, 2, 7, 3, False, False), (24, 40, 3, 2, 7, 3, True, False),
+    (16, 32, 1, 2, 8, 4, False, False)])
+@pytest.mark.parametrize('gbits', [16, 12])
+def test_conv2d_q_wide_gradients(Cin, Cout, k, s, H, B, bias, signed, gbits):
+    """BASELINE config 5 (8-bit W/A, 16-bit G): gradient mantissas split k = 256*hi + lo, still exactly rounded."""
+    _conv_case(Cin, Cout, k, s, H, B, bias, signed, gbits)
+
+
+def _conv_case(Cin, Cout, k, s, H, B, bias, signed, gbits):
     rng = np.random.default_rng(Cin * 100 + Cout + k + s)
     ctx = O.Context(O.PhiloxNoise(SEED))
     wd = 2e-4
-    ol = O.Conv2d_q(ctx, 'c', 8, [k, k, Cin, Cout], [1, s, s, 1], 'SAME', use_bias=bias, weight_decay=wd, rng=rng)
+    ol = O.Conv2d_q(ctx, 'c', 8, [k, k, Cin, Cout], [1, s, s, 1], 'SAME', use_bias=bias, weight_decay=wd, rng=rng,
+                    grad_bits=gbits)
     rt = D.Runtime(SEED)
-    pl = D.Conv2d_q(8, Cin, Cout, k, s, 'SAME', bias=bias, weight_decay=wd, input_signed=signed, runtime=rt).cuda()
+    pl = D.Conv2d_q(8, Cin, Cout, k, s, 'SAME', bias=bias, weight_decay=wd, input_signed=signed, runtime=rt,
+                    grad_bits=gbits).cuda()
     rt.finalize('cuda')
     pl.weight.data.copy_(ol.W.detach())
     x = torch.from_numpy(rng.standard_normal((B, H, H, Cin)).astype(np.float32) * 1.5)
@@ -110,13 +126,14 @@ def test_conv2d_q_forward_backward(Cin, Cout, k, s, H, B, bias, signed):
 
 
 @pytest.mark.parametrize('B,In,Out,bias', [(128, 2048, 400, True), (128, 400, 10, True), (256, 64, 10, False), (7, 20, 5, True)])
-def test_linear_q_forward_backward(B, In, Out, bias):
+@pytest.mark.parametrize('gbits', [None, 16])
+def test_linear_q_forward_backward(B, In, Out, bias, gbits):
     rng = np.random.default_rng(B + In + Out)
     ctx = O.Context(O.PhiloxNoise(SEED))
     wd = 2e-4
-    ol = O.Dense_q(ctx, 'd', 8, In, Out, use_bias=bias, weight_decay=wd, rng=rng)
+    ol = O.Dense_q(ctx, 'd', 8, In, Out, use_bias=bias, weight_decay=wd, rng=rng, grad_bits=gbits)
     rt = D.Runtime(SEED)
-    pl = D.Linear_q(8, In, Out, bias=bias, weight_decay=wd, runtime=rt).cuda()
+    pl = D.Linear_q(8, In, Out, bias=bias, weight_decay=wd, runtime=rt, grad_bits=gbits).cuda()
     rt.finalize('cuda')
     pl.weight.data.copy_(ol.W.detach())
     x = torch.from_numpy(rng.standard_normal((B, In)).astype(np.float32))
