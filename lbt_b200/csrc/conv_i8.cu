@@ -25,7 +25,9 @@ using namespace tc;
 
 constexpr int kBlockM = 128;
 constexpr int kStageK = 128;  // bytes of K per row per stage
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // wgrad: producer, MMA issuer, 4 epilogue warps
+constexpr int kEpiWarps = 8;         // fprop: two epilogue warps per TMEM lane quadrant (the fused epilogue is ALU-heavy)
+constexpr int kThreadsF = 32 * (2 + kEpiWarps);
 
 __device__ int g_conv_error = 0;
 
@@ -71,7 +73,7 @@ struct Cfg {
 inline int ctas_per_sm(int bn) { return bn <= 16 ? 3 : (bn <= 128 ? 2 : 1); }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
+__global__ void __launch_bounds__(kThreadsF, Cfg<BN>::kCtasPerSm)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +84,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty_bar[C::kAccStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[4][2 * BN];              // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
+  __shared__ int s_stat[kEpiWarps][2 * BN];              // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -92,7 +94,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < C::kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);
+      mbar_init(&tmem_empty_bar[s], kEpiWarps);
     }
     s_abort = 0;
     fence_barrier_init();
@@ -192,12 +194,13 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     const uint32_t quad = warp & 3;
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;  // which of the quadrant's two warps: chunks half, half + 2, ...
     int e = p.exp_const;
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
     const bool fused = p.bnq.q.bits != 0;
-    int* my_stat = s_stat[quad];
+    int* my_stat = s_stat[warp - 2];
     BnqState bst;
     bst.tiles = 0;
     uint32_t stat_ntile = 0;
@@ -223,7 +226,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         bst.tiles = 0;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16)) {
+        if (BN == 16 && half) break;  // a single chunk: the second warp of the quadrant has nothing to do
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
@@ -268,7 +272,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (fused) {
       bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
-      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, quad == 0, lane);
+      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == 2, lane);
     }
   }
 
@@ -492,7 +496,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, un
     }
     attr_done[dev] = true;
   }
-  conv_fprop_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  conv_fprop_kernel<BN><<<grid, kThreadsF, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
   return check_launch("lbt_conv_i8_fprop");
 }
 

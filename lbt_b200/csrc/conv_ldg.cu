@@ -31,7 +31,8 @@ using namespace tc;
 
 constexpr int kBlockM = 128;
 constexpr int kLoaderWarps = 4;
-constexpr int kThreads = 32 * (kLoaderWarps + 1 + 4);  // loaders, MMA issuer, epilogue
+constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, interleaved over the 16-column chunks
+constexpr int kThreads = 32 * (kLoaderWarps + 1 + kEpiWarps);  // loaders, MMA issuer, epilogue
 constexpr int kChunksPerStage = 8;
 constexpr int kStageBytes = kChunksPerStage * kBlockM * 16;  // 16 KB
 constexpr int kMaxStages = 8;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   __shared__ __align__(8) uint64_t b_bar;   // the resident filter bank has landed
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[4][2 * BN];
+  __shared__ int s_stat[kEpiWarps][2 * BN];
   __shared__ int2 s_tab[kMaxKC + 8];       // tap slot: {byte offset from the row's base pixel, tap code}
 
   constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
@@ -117,9 +118,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);
+      mbar_init(&tmem_empty_bar[s], kEpiWarps);
     }
-    mbar_init(&b_bar, 4 * 32);
+    mbar_init(&b_bar, kEpiWarps * 32);
     s_abort = 0;
     fence_barrier_init();
   }
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   } else {
     // ===== epilogue warps; first they fetch the resident filter bank (the loaders are already gathering tile 0):
     // chunk kc, output channel n -> 16 bytes (zeros beyond Cout / KC), all copies in flight at once =====
-    for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 128) {
+    for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 32 * kEpiWarps) {
       const uint32_t kc = i / BN, n = i % BN;
       const bool v = kc < p.KC && n < p.N;
       cp_async16(smem_u32(sB + (size_t)i * 16), v ? p.wp + (size_t)n * p.ldw + (size_t)kc * 16 : p.wp, v ? 16u : 0u);
@@ -269,12 +270,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     cp_async_arrive_noinc(&b_bar);
     // TMEM lane quadrant = warp % 4
     const uint32_t quad = warp & 3;
+    const uint32_t half = (uint32_t)(warp - (kLoaderWarps + 1)) >> 2;  // which of the quadrant's two warps
     int e = p.exp_const;
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
     const bool fused = p.bnq.q.bits != 0;
-    int* my_stat = s_stat[quad];
+    int* my_stat = s_stat[warp - (kLoaderWarps + 1)];
     BnqState bst;
     bst.tiles = 0;
     if (fused) {
@@ -298,8 +300,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       }
       ++bst.tiles;
       constexpr int G = BN < 32 ? BN : 32;  // columns fetched from tensor memory per wait
+      constexpr bool kSplit = BN > G;       // both warps of a quadrant work: alternate the G-column groups
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += G) {
+      for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G) {
+        if (!kSplit && half) break;
         uint32_t vv[G / 16][16];
 #pragma unroll
         for (int q = 0; q < G / 16; ++q) tmem_ld16(taddr + c0 + 16 * q, vv[q]);
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     }
     if (fused) {
       bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
-      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, quad == 0, lane);
+      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == kLoaderWarps + 1, lane);
     }
   }
 

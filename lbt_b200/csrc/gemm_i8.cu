@@ -26,7 +26,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // bytes == int8 elements == one 128B swizzle row
 constexpr int kUmmaK = 32;    // kind::i8: 32 bytes of K per instruction
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant, interleaved over the 16-column chunks
+constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr long long kWatchdogCycles = 4000000000ll;
 
 __device__ int g_gemm_error = 0;
@@ -166,7 +167,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[4][2 * BN];  // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
+  __shared__ int s_stat[kEpiWarps][2 * BN];  // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -177,7 +178,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[s], kEpiWarps);  // one arrive per epilogue warp
     }
     s_abort = 0;
     fence_barrier_init();
@@ -256,12 +257,13 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===== epilogue warps 2..5: TMEM -> registers -> global =====
     const uint32_t quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the only ones this warp may read
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;  // which of the quadrant's two warps: chunks half, half + 2, ...
     int e = p.exp_const;
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
     const bool fused = p.bnq.q.bits != 0;   // host guarantees LBT_EPI_F32 and k_splits == 1
-    int* my_stat = s_stat[quad];
+    int* my_stat = s_stat[warp - 2];
     BnqState bst;
     bst.tiles = 0;
     uint32_t stat_ntile = 0;
@@ -289,7 +291,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ++bst.tiles;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16)) {
+        if (BN == 16 && half) break;  // a single chunk: the second warp of the quadrant has nothing to do
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
@@ -343,7 +346,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (fused) {
       bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
-      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, quad == 0, lane);
+      bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == 2, lane);
     }
   }
 
