@@ -7,6 +7,7 @@
 namespace lbt {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_pdl{1};
 
 namespace {
 thread_local std::string t_last_error;
@@ -58,3 +59,9 @@ extern "C" const char* lbt_strerror(int status) {
 extern "C" const char* lbt_last_cuda_error(void) { return lbt::t_last_error.c_str(); }
 
 extern "C" uint64_t lbt_launch_count(void) { return lbt::g_launches.load(std::memory_order_relaxed); }
+
+// Bench / test knob (not in lbt.h): 0 = plain stream-ordered launches, 1 (default) = programmatic dependent launch.
+extern "C" int lbt_set_pdl(int on) {
+  lbt::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return LBT_OK;
+}

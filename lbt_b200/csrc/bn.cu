@@ -161,6 +161,8 @@ struct Fwd1Params {
 __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
+  pdl_trigger();
+  pdl_wait();
   const QC c = make_qc(p.q.bits, *reinterpret_cast<volatile const int32_t*>(p.q.ib));
   const uint64_t off = site_offset(p.q);
   uint32_t n1 = 0, n2 = 0;
@@ -240,6 +242,8 @@ struct Fwd2Params {
 __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p) {
   extern __shared__ float s_par[];  // [4*C]: mean, denom, gq, bq
   __shared__ uint32_t s_red[16];
+  pdl_trigger();
+  pdl_wait();
   const int C = p.t.C;
   const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
   const QC c2 = make_qc(p.q2.bits, *reinterpret_cast<volatile const int32_t*>(p.q2.ib));
@@ -374,6 +378,8 @@ struct Bwd1Params {
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
+  pdl_trigger();
+  pdl_wait();
   const int C = p.t.C;
   const QC c2 = make_qc(p.bits2, *reinterpret_cast<volatile const int32_t*>(p.ib2));
   const QC cg2 = make_qc(p.qg2.bits, *reinterpret_cast<volatile const int32_t*>(p.qg2.ib));
@@ -486,6 +492,8 @@ struct Bwd2Params {
 __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   extern __shared__ float s_par[];  // [5*C]: mean, 1/den, mean_g, mean_gxhat, (unused)
   __shared__ uint32_t s_red[16];
+  pdl_trigger();
+  pdl_wait();
   const int C = p.t.C;
   const bool gq_on = p.qg.bits != 0;
   QC cq = make_qc(8, 0);
@@ -681,7 +689,7 @@ extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_i
   p.sums = reinterpret_cast<long long*>(sums);
   const size_t smem = (size_t)2 * C * 8;
   if ((rc = set_smem(bn_fwd1_kernel, smem))) return rc;
-  bn_fwd1_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_fwd1_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_fwd_quant_stats");
 }
 
@@ -731,7 +739,7 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
   const size_t smem = (size_t)4 * C * 4;
   if ((rc = set_smem(bn_fwd2_kernel, smem))) return rc;
-  bn_fwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_fwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_fwd_apply");
 }
 
@@ -770,7 +778,7 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   p.sums = reinterpret_cast<long long*>(sums);
   const size_t smem = (size_t)4 * C * 8;
   if ((rc = set_smem(bn_bwd1_kernel, smem))) return rc;
-  bn_bwd1_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_bwd1_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_quant_stats");
 }
 
@@ -804,6 +812,6 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   p.g_mant = g_mant;
   const size_t smem = (size_t)4 * C * 4;
   if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
-  bn_bwd2_kernel<<<grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(bn_bwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_apply");
 }

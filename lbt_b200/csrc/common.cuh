@@ -33,6 +33,28 @@ inline int check_launch(const char* where) {
   return LBT_OK;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A training step is ~140 short kernels back to back.  Launched with the programmatic-serialization attribute, kernel
+// N+1 is scheduled while kernel N drains: its prologue (barrier init, TMEM allocation, tables) overlaps N's tail and it
+// blocks at pdl_wait() — before its first global-memory access — until N has completed and flushed.  Captured into the
+// step's CUDA graph as programmatic edges.  lbt_set_pdl(0) turns the attribute off (plain stream order).
+extern std::atomic<int> g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define LBT_REQUIRE_ARCH()                        \
   do {                                            \
     const ::lbt::DeviceInfo& _di = ::lbt::device_info(); \
@@ -41,6 +63,11 @@ inline int check_launch(const char* where) {
 
 // ---- device helpers --------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Everything a kernel reads or writes in global memory must come after pdl_wait(); pdl_trigger() lets the next
+// kernel of the stream start being scheduled (it still waits for this grid's completion at its own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -102,9 +102,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  pdl_trigger();
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   volatile int* abort_flag = &s_abort;
 
@@ -334,9 +336,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmG);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  pdl_trigger();
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   volatile int* abort_flag = &s_abort;
 
@@ -496,7 +500,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, un
     }
     attr_done[dev] = true;
   }
-  conv_fprop_kernel<BN><<<grid, kThreadsF, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  launch_pdl(conv_fprop_kernel<BN>, grid, kThreadsF, Cfg<BN>::kSmemBytes, st, ta, tb, p);
   return check_launch("lbt_conv_i8_fprop");
 }
 
@@ -642,7 +646,7 @@ int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tg, const WgradParams
     }
     attr_done[dev] = true;
   }
-  conv_wgrad_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(tx, tg, p);
+  launch_pdl(conv_wgrad_kernel<BN>, grid, kThreads, Cfg<BN>::kSmemBytes, st, tx, tg, p);
   return check_launch("lbt_conv_i8_wgrad");
 }
 }  // namespace

@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
 
   constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) dbg_stamp(p, 0);
   uint8_t* sB = smem;                                        // KCp * BN * 16
   uint8_t* sA = smem + (((size_t)p.KCp * BN * 16 + 127) & ~(size_t)127);
 
@@ -136,9 +135,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     const int code = ts < p.taps ? (int)ts : (ts * CPP < p.KCp ? 255 : 254);
     s_tab[ts] = make_int2(ts < p.taps ? d : 0, code);
   }
+  pdl_trigger();
   fence_before();
   __syncthreads();
   fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   volatile int* abort_flag = &s_abort;
   if (threadIdx.x == 0) dbg_stamp(p, 1);
@@ -371,7 +372,7 @@ int launch_ldg2(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st)
     }
     attr_smem[dev] = smem;
   }
-  conv_ldg_kernel<BN, CPP><<<grid, kThreads, smem, st>>>(p);
+  launch_pdl(conv_ldg_kernel<BN, CPP>, grid, kThreads, smem, st, p);
   return check_launch("lbt_conv_i8 (cp.async gather)");
 }
 

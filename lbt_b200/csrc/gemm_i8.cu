@@ -186,9 +186,11 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   volatile int* abort_flag = &s_abort;
 
@@ -418,7 +420,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, un
     }
     attr_done[dev] = true;
   }
-  gemm_i8_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, st>>>(ta, tb, p);
+  launch_pdl(gemm_i8_kernel<BN>, grid, kThreads, Cfg<BN>::kSmemBytes, st, ta, tb, p);
   return check_launch("lbt_gemm_i8");
 }
 

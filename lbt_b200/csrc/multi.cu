@@ -14,6 +14,8 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) finalize_multi_kernel(const lbt_finalize_job* __restrict__ jobs, int njobs,
                                                                   unsigned long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < total;
        i += (unsigned long long)gridDim.x * kThreads) {
     int lo = 0, hi = njobs - 1;  // last job with start <= i
@@ -39,6 +41,8 @@ __global__ void __launch_bounds__(kThreads) finalize_multi_kernel(const lbt_fina
 __global__ void __launch_bounds__(kThreads) noise_fill_multi_kernel(const lbt_noise_job* __restrict__ jobs, int njobs,
                                                                     unsigned long long total_groups, uint64_t seed,
                                                                     const uint64_t* dev_step) {
+  pdl_trigger();
+  pdl_wait();
   const uint64_t step_off = dev_step ? ((*dev_step) << 32) : 0ull;
   for (unsigned long long i = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; i < total_groups;
        i += (unsigned long long)gridDim.x * kThreads) {
@@ -81,6 +85,8 @@ __global__ void __launch_bounds__(kThreads) param_prep_kernel(const lbt_prep_job
                                                               const uint32_t* __restrict__ block_job,
                                                               const uint32_t* __restrict__ block_chunk, uint64_t seed,
                                                               const uint64_t* dev_step, uint32_t chunk_elems) {
+  pdl_trigger();
+  pdl_wait();
   const lbt_prep_job j = jobs[block_job[blockIdx.x]];
   const QC c = make_qc(j.bits, *j.ib);
   uint64_t off = j.offset;

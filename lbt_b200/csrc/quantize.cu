@@ -145,6 +145,8 @@ __device__ __forceinline__ void store_mant4(void* mant, int kind, size_t idx, fl
 
 template <int MODE, bool MM>
 __global__ void __launch_bounds__(kThreads) quantize_vec_kernel(const QParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int ib = *reinterpret_cast<volatile const int32_t*>(p.ib);
   const QConst c = make_const(p.bits, ib);
   uint64_t off = p.offset;
@@ -407,7 +409,7 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
     p.rows_per_group = (uint32_t)rpg;
     p.total_tiles = (uint64_t)p.chunks * ((n_outer + rpg - 1) / rpg);
     const unsigned grid = (unsigned)(p.total_tiles < grid64 ? p.total_tiles : grid64);
-    kern<<<grid, kThreads, 0, st>>>(p);
+    launch_pdl(kern, grid, kThreads, 0, st, p);
   } else {
     const uint64_t n = (uint64_t)n_outer * n_inner;
     const uint64_t blocks = (n + kThreads - 1) / kThreads;
