@@ -28,10 +28,19 @@ def timeit(fn, iters=None, warmup=3, flush=None):
         fn()
     torch.cuda.synchronize()
     if flush is None:
+        # the launches are captured in a CUDA graph: small kernels are otherwise bound by the ~15 us Python/ctypes call
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(iters):
+                fn()
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(iters):
-            fn()
+        g.replay()
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e-3 / iters
@@ -107,9 +116,11 @@ def main():
     ap.add_argument('--flush', action='store_true')
     ap.add_argument('--only', default='', help='substring filter on the layer name')
     ap.add_argument('--iters', type=int, default=10)
+    ap.add_argument('--path', type=int, default=1, help='0: TMA kernels only, 1: gather kernels for narrow channels')
     ap.add_argument('--out', default='gpurun_out/gemm_bench.json')
     a = ap.parse_args()
     ITERS[0] = a.iters
+    _lib.lib().lbt_conv_set_path(a.path)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda') if a.flush else None
     rows = []
     for n in [int(s) for s in a.square.split(',') if s]:

@@ -525,7 +525,9 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
     return LBT_EINVAL;
   if (C % 16) return LBT_EUNSUPPORTED;
-  if (conv_ldg_enabled() && conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
+  // measured (benchmarks/gemm_bench.py --path 0|1): the cp.async gather wins for 16- and 32-byte pixel rows (3.1x / 1.1x),
+  // the TMA im2col kernel for 64 bytes and more
+  if (conv_ldg_enabled() && C <= 32 && conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
     return conv_ldg_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, 0, ib_src,
@@ -666,6 +668,12 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return LBT_EUNSUPPORTED;
   if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
+  // the gather wgrad only pays off for 16-byte pixel rows (elsewhere both kernels are bound by the int64 atomics)
+  if (conv_ldg_enabled() && k_splits <= 0 && C == 16 && Cout <= 16 && conv_wgrad_ldg_ok(C, Cout, kh, kw)) {
+    const int rc = conv_wgrad_ldg_run(src, src_kind, N, H, W, C, g, g_kind, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, acc64,
+                                      alpha, stream);
+    if (rc != LBT_EUNSUPPORTED) return rc;
+  }
   const DeviceInfo& di = device_info();
   static EncodeTiledFn enc_tiled = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
   static EncodeIm2colFn enc_im2col = reinterpret_cast<EncodeIm2colFn>(driver_fn("cuTensorMapEncodeIm2col"));

@@ -385,7 +385,196 @@ int launch_ldg(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient for narrow channels: acc64[(tap, c), co] += alpha * sum over output pixels of X[pixel + tap, c] * G[pixel, co]
+// (tf.gradients(y, W, gradq), dynamic_fixed_point.py:302).  The reduction runs over pixels, so a pipeline stage is one
+// block of 128 output pixels: the loader warps gather every tap of X ([KC chunk planes][128 pixels][16 B]) and the
+// gradient rows ([Cout/16 planes][128 pixels][16 B]) once, and the tensor core consumes both MN-major (planes = groups of
+// 16 M/N indices, pixels = K): all MT = ceil(KC/8) M tiles accumulate in tensor memory across the CTA's pixel blocks, and
+// one epilogue at the end adds the s32 partials into the int64 sums.  Unlike the TMA kernel (which re-reads X per M tile
+// and pays the 3-clock-per-row TMA rate on 16-byte rows) every pixel block is loaded exactly once.
+// ------------------------------------------------------------------------------------------------------------------
+struct WgLdgParams {
+  const uint8_t* x;
+  const uint8_t* g;
+  uint32_t Mpix, Cout;
+  uint32_t SH, SW, C;
+  uint32_t OW, OHW;
+  uint32_t ohw_mul, ohw_shr, ow_mul, ow_shr;
+  int sh, sw, pt, pl;
+  uint32_t kw, taps, cpp, np;       // filter width, kh*kw, C/16, Cout/16
+  uint32_t KC, MT;                  // chunk planes of X per stage, M tiles
+  uint32_t a_planes;                // 8 * MT
+  uint32_t stage_bytes, nstages;
+  uint32_t pix_blocks;
+  uint32_t Kf;
+  unsigned long long rspread;       // sum over filter rows of 1 << (r * kw)
+  long long* acc64;
+  int alpha;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+};
+
+template <int CPP>
+__global__ void __launch_bounds__(32 * (kLoaderWarps + 1 + 4), 2) conv_wgrad_ldg_kernel(const WgLdgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+  __shared__ int s_delta[kMaxTaps];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < p.nstages; ++s) {
+      mbar_init(&full_bar[s], kLoaderWarps * 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    s_abort = 0;
+    fence_barrier_init();
+  }
+  if (warp == kLoaderWarps) tmem_alloc(&tmem_slot, p.tmem_cols);
+  for (uint32_t ts = threadIdx.x; ts < p.taps; ts += blockDim.x)
+    s_delta[ts] = ((int)(ts / p.kw) * (int)p.SW + (int)(ts % p.kw)) * (int)p.C;
+  pdl_trigger();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  volatile int* abort_flag = &s_abort;
+  const uint32_t kh = p.taps / p.kw;
+  const uint32_t b_off = p.a_planes * (kBlockM * 16);  // gradient planes follow the X planes inside a stage
+
+  if (warp < kLoaderWarps) {
+    constexpr int RPI = 32 / CPP;
+    const uint32_t cc = lane % CPP;
+    const uint32_t rloc0 = warp * 32 + lane / CPP;
+    const uint32_t grow = threadIdx.x;  // the gradient row this thread copies
+    uint32_t stage = 0, phase = 0;
+    bool ok = true;
+    for (uint32_t pb = blockIdx.x; pb < p.pix_blocks && ok; pb += gridDim.x) {
+      unsigned long long mask[CPP];
+      const uint8_t* base[CPP];
+#pragma unroll
+      for (int i = 0; i < CPP; ++i) {
+        const uint32_t m = pb * kBlockM + rloc0 + i * RPI;
+        const uint32_t img = fast_div(m, p.OHW, p.ohw_mul, p.ohw_shr), rem = m - img * p.OHW;
+        const uint32_t oyu = fast_div(rem, p.OW, p.ow_mul, p.ow_shr);
+        const int by = (int)oyu * p.sh - p.pt, bx = (int)(rem - oyu * p.OW) * p.sw - p.pl;
+        const int lo = max(0, -bx), hi = min((int)p.kw, (int)p.SW - bx);
+        const int rlo = max(0, -by), rhi = min((int)kh, (int)p.SH - by);
+        const uint32_t colbits = hi > lo ? ((1u << hi) - (1u << lo)) : 0u;
+        unsigned long long mk = 0ull;
+        if (rhi > rlo) {
+          const int b0 = rlo * (int)p.kw, b1 = rhi * (int)p.kw;
+          const unsigned long long range = (b1 >= 64 ? ~0ull : ((1ull << b1) - 1ull)) & ~((1ull << b0) - 1ull);
+          mk = (unsigned long long)colbits * (p.rspread & range);
+        }
+        mask[i] = m < p.Mpix ? mk : 0ull;
+        base[i] = p.x + ((long long)img * p.SH * p.SW + (long long)by * (int)p.SW + bx) * (long long)p.C + cc * 16;
+      }
+      ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_ldg_error);
+      if (!ok) break;
+      const uint32_t st0 = smem_u32(smem + (size_t)stage * p.stage_bytes);
+      const uint32_t dst0 = st0 + cc * (kBlockM * 16) + rloc0 * 16;
+#pragma unroll 2
+      for (uint32_t ts = 0; ts < p.taps; ++ts) {
+        const int d = s_delta[ts];
+#pragma unroll
+        for (int i = 0; i < CPP; ++i)
+          cp_async16(dst0 + ts * (CPP * kBlockM * 16) + i * (RPI * 16), base[i] + d, (mask[i] >> ts) & 1ull ? 16u : 0u);
+      }
+      {  // gradient rows: thread t copies the Cout bytes of pixel t into the np planes
+        const uint32_t m = pb * kBlockM + grow;
+        const bool v = m < p.Mpix;
+        const uint8_t* src = p.g + (size_t)(v ? m : 0) * p.Cout;
+        const uint32_t dstb = st0 + b_off + grow * 16;
+        for (uint32_t j = 0; j < p.np; ++j) cp_async16(dstb + j * (kBlockM * 16), src + j * 16, v ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(&full_bar[stage]);
+      if (++stage == p.nstages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == kLoaderWarps) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true, first = true;
+      for (uint32_t pb = blockIdx.x; pb < p.pix_blocks && ok; pb += gridDim.x) {
+        if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_ldg_error))) break;
+        fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sb = sa + b_off;
+        for (uint32_t mt = 0; mt < p.MT; ++mt)
+#pragma unroll
+          for (uint32_t kk = 0; kk < kBlockM / 32; ++kk)
+            umma_i8(tmem_base + mt * p.Cout, make_desc_mnmajor(sa + mt * 8 * (kBlockM * 16) + kk * 32 * 16, 0, kBlockM * 16),
+                    make_desc_mnmajor(sb + kk * 32 * 16, 0, kBlockM * 16), p.idesc, (first && kk == 0) ? 0u : 1u);
+        first = false;
+        umma_commit(&empty_bar[stage]);
+        if (++stage == p.nstages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (ok) umma_commit(&done_bar);
+    }
+  } else {
+    // ===== epilogue (once): s32 partials -> int64 sums =====
+    const uint32_t quad = warp & 3;
+    const bool has_work = blockIdx.x < p.pix_blocks;
+    bool ok = has_work && mbar_wait(&done_bar, 0, abort_flag, &g_ldg_error);
+    ok = __all_sync(0xffffffffu, ok);
+    if (ok) {
+      fence_after();
+      for (uint32_t mt = 0; mt < p.MT; ++mt) {
+        const uint32_t kf = mt * kBlockM + quad * 32 + lane;
+        for (uint32_t c = 0; c < p.Cout; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + mt * p.Cout + c + ((quad * 32u) << 16), v);
+          tmem_ld_wait();
+          if (kf < p.Kf) {
+            unsigned long long* o = reinterpret_cast<unsigned long long*>(p.acc64) + (size_t)kf * p.Cout + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const long long a = (long long)(int)v[j] * (long long)p.alpha;
+              if (a != 0) atomicAdd(o + j, (unsigned long long)a);
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if (warp == kLoaderWarps) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+template <int CPP>
+int launch_wgrad_ldg(const WgLdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  static size_t attr_smem[16] = {};
+  const int dev = device_info().device;
+  if (attr_smem[dev] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_ldg_kernel<CPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_ldg_kernel)");
+      return LBT_ECUDA;
+    }
+    attr_smem[dev] = smem;
+  }
+  launch_pdl(conv_wgrad_ldg_kernel<CPP>, grid, 32 * (kLoaderWarps + 1 + 4), smem, st, p);
+  return check_launch("lbt_conv_i8_wgrad (cp.async gather)");
+}
+
 }  // namespace
+
 
 std::atomic<int> g_use_ldg{1};
 std::atomic<unsigned long long*> g_dbg{nullptr};
@@ -400,6 +589,85 @@ bool conv_ldg_ok(int C, int Cout, int kh, int kw) {
   const int bn = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128));
   return kcp * bn * 16 + 2 * kStageBytes + 1024 <= 200 * 1024 && (size_t)kh * kw * C <= 65536 && kcp <= (size_t)kMaxKC &&
          kh * kw <= kMaxTaps && kw <= 16 && kh <= 16;
+}
+
+// Shapes the gather wgrad kernel takes: all M tiles of the filter must fit tensor memory next to each other.
+bool conv_wgrad_ldg_ok(int C, int Cout, int kh, int kw) {
+  if (C != 16 && C != 32 && C != 64) return false;
+  if (Cout != 16 && Cout != 32 && Cout != 64 && Cout != 128) return false;
+  if (kh * kw > kMaxTaps || kw > 16 || kh > 16) return false;
+  const int kc = kh * kw * (C / 16), mt = (kc + 7) / 8;
+  if (mt * Cout > 512) return false;
+  const size_t stage = (size_t)(8 * mt + Cout / 16) * kBlockM * 16;
+  return 2 * stage + 1024 <= 200 * 1024;
+}
+
+int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout, int kh, int kw,
+                       int sh, int sw, int pt, int pl, int OH, int OW, int64_t* acc64, int alpha, void* stream) {
+  const DeviceInfo& di = device_info();
+  if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  WgLdgParams p{};
+  p.x = reinterpret_cast<const uint8_t*>(src);
+  p.g = reinterpret_cast<const uint8_t*>(g);
+  p.Mpix = (uint32_t)((size_t)N * OH * OW);
+  p.Cout = (uint32_t)Cout;
+  p.SH = (uint32_t)H;
+  p.SW = (uint32_t)W;
+  p.C = (uint32_t)C;
+  p.OW = (uint32_t)OW;
+  p.OHW = (uint32_t)(OH * OW);
+  auto magic = [](uint32_t d, uint32_t& mul, uint32_t& shr) {
+    if (d <= 1) {
+      mul = 0;
+      shr = 0;
+      return;
+    }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const uint32_t pw = 31 + lg;
+    mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+    shr = pw - 32;
+  };
+  magic(p.OHW, p.ohw_mul, p.ohw_shr);
+  magic(p.OW, p.ow_mul, p.ow_shr);
+  p.sh = sh;
+  p.sw = sw;
+  p.pt = pt;
+  p.pl = pl;
+  p.kw = (uint32_t)kw;
+  p.taps = (uint32_t)(kh * kw);
+  p.cpp = (uint32_t)C / 16;
+  p.np = (uint32_t)Cout / 16;
+  p.KC = p.taps * p.cpp;
+  p.MT = (p.KC + 7) / 8;
+  p.a_planes = 8 * p.MT;
+  p.stage_bytes = (p.a_planes + p.np) * kBlockM * 16;
+  p.pix_blocks = (p.Mpix + kBlockM - 1) / kBlockM;
+  p.Kf = (uint32_t)(kh * kw * C);
+  for (int r = 0; r < kh; ++r) p.rspread |= 1ull << (r * kw);
+  p.acc64 = reinterpret_cast<long long*>(acc64);
+  p.alpha = alpha;
+  p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, g_kind == LBT_MANT_S8, true, true, Cout, kBlockM);
+  uint32_t cols = 32;
+  while (cols < p.MT * p.Cout) cols <<= 1;
+  p.tmem_cols = cols;
+  const bool two = cols <= 256 && 2 * (size_t)p.stage_bytes + 1024 <= 100 * 1024;
+  size_t budget = (two ? 108 * 1024 : 200 * 1024) - 1024;
+  uint32_t nst = (uint32_t)(budget / p.stage_bytes);
+  if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
+  if (nst < 2) return LBT_EUNSUPPORTED;
+  p.nstages = nst;
+  const size_t smem = (size_t)nst * p.stage_bytes + 256;
+  const uint64_t cap = (uint64_t)di.sm_count * (two ? 2u : 1u);
+  unsigned grid = (unsigned)(p.pix_blocks < cap ? p.pix_blocks : cap);
+  // one CTA may sum at most 65536 products per s32 accumulator: 512 pixel blocks
+  if ((p.pix_blocks + grid - 1) / grid > 512) return LBT_EUNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p.cpp) {
+    case 1: return launch_wgrad_ldg<1>(p, grid, smem, st);
+    case 2: return launch_wgrad_ldg<2>(p, grid, smem, st);
+    default: return launch_wgrad_ldg<4>(p, grid, smem, st);
+  }
 }
 
 // Shared by lbt_conv_i8_fprop (gather 0) and lbt_conv_i8_dgrad (gather 1).  (M rows) x (Cout columns); the gathered
