@@ -84,7 +84,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_empty_bar[C::kAccStages];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[kEpiWarps][2 * BN];              // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
+  __shared__ int s_stat[kEpiWarps][2 * BN];
+  __shared__ unsigned long long s_tot[2 * BN];   // CTA totals of the fused statistics (last N tile of the CTA)              // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -102,6 +103,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  for (uint32_t i = threadIdx.x; i < 2 * BN; i += kThreadsF) s_tot[i] = 0ull;
   pdl_trigger();
   fence_before();
   __syncthreads();
@@ -272,8 +274,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc_phase ^= 1;
       }
     }
-    if (fused) {
-      bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+    if (fused && ok) {
+      bnq_flush_cta(p.bnq, my_stat, s_tot, stat_ntile * BN, BN, p.N, lane, threadIdx.x - 64, 32 * kEpiWarps, 1);
       bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == 2, lane);
     }
   }
@@ -710,6 +712,9 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   if (!splits) {
     const uint32_t tiles = p.m_tiles * p.n_tiles;
     splits = (uint32_t)(di.sm_count * ctas_per_sm(bn)) / (tiles ? tiles : 1);
+    // every split ends in Kf x Cout int64 atomics: give it at least 8 pixel blocks of work (measured optimum on the
+    // ResNet-20 shapes, benchmarks/wgrad_sweep.py)
+    if (splits > p.pix_blocks / 8) splits = p.pix_blocks / 8;
     if (splits < 1) splits = 1;
   }
   if (splits > p.pix_blocks) splits = p.pix_blocks;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
   __shared__ int s_stat[kEpiWarps][2 * BN];
+  __shared__ unsigned long long s_tot[2 * BN];   // CTA totals of the fused statistics
   __shared__ int2 s_tab[kMaxKC + 8];       // tap slot: {byte offset from the row's base pixel, tap code}
 
   constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     fence_barrier_init();
   }
   if (warp == kLoaderWarps) tmem_alloc(&tmem_slot, kTmemCols);
+  for (uint32_t i = threadIdx.x; i < 2 * BN; i += kThreads) s_tot[i] = 0ull;
   // gather table, one entry per tap slot: source of (row, slot) = base(row) + x, valid iff bit y of the row's tap mask;
   // y == 255: zero chunk (K padding), y == 254: beyond the tile's chunks (nothing to copy)
   constexpr int TPS = kChunksPerStage / CPP;  // tap slots per pipeline stage
@@ -346,8 +348,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
         acc_phase ^= 1;
       }
     }
-    if (fused) {
-      bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
+    if (fused && ok) {
+      bnq_flush_cta(p.bnq, my_stat, s_tot, 0, BN, p.N, lane, threadIdx.x - 32 * (kLoaderWarps + 1), 32 * kEpiWarps, 1);
       bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == kLoaderWarps + 1, lane);
     }
   }

@@ -167,7 +167,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[kEpiWarps][2 * BN];  // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
+  __shared__ int s_stat[kEpiWarps][2 * BN];
+  __shared__ unsigned long long s_tot[2 * BN];  // CTA totals of the fused statistics (last N tile of the CTA)  // per epilogue warp: partial sum k, sum k^2 (fused BN statistics)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -186,6 +187,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
+  for (uint32_t i = threadIdx.x; i < 2 * BN; i += kThreads) s_tot[i] = 0ull;
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
@@ -346,8 +348,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc_phase ^= 1;
       }
     }
-    if (fused) {
-      bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
+    if (fused && ok) {
+      bnq_flush_cta(p.bnq, my_stat, s_tot, stat_ntile * BN, BN, p.N, lane, threadIdx.x - 64, 32 * kEpiWarps, 1);
       bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == 2, lane);
     }
   }

@@ -187,6 +187,26 @@ __device__ __forceinline__ void bnq_flush(const BnqParams& b, int* s_stat, uint3
   __syncwarp();
 }
 
+// Final flush of a CTA: the epilogue warps first combine their partials in shared memory (s_tot: [2][bn] 64-bit, zeroed
+// at kernel start) and only then touch the global sums — one int64 atomic per channel per CTA instead of one per warp
+// (the per-warp version put 8 x 296 CTAs deep contention on 2 x Cout addresses: ~10 us at the tail of every launch).
+// Must be reached by ALL `nthreads` epilogue threads (named barrier `bar_id`); tid = index within the epilogue group.
+__device__ __forceinline__ void bnq_flush_cta(const BnqParams& b, int* s_stat, unsigned long long* s_tot, uint32_t col0, uint32_t bn,
+                                              uint32_t N, int lane, uint32_t tid, uint32_t nthreads, int bar_id) {
+  __syncwarp();
+  for (uint32_t i = lane; i < 2 * bn; i += 32) {
+    const int v = s_stat[i];
+    if (v) atomicAdd(s_tot + i, (unsigned long long)(long long)v);
+    s_stat[i] = 0;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+  for (uint32_t i = tid; i < 2 * bn; i += nthreads) {
+    const uint32_t c = i < bn ? i : i - bn;
+    const unsigned long long v = s_tot[i];
+    if (v && col0 + c < N) atomicAdd(reinterpret_cast<unsigned long long*>(b.sums) + (i < bn ? 0 : N) + col0 + c, v);
+  }
+}
+
 // End of the kernel: publish the overflow statistics; `ticket` (one warp per CTA) runs the CTA ticket that adds numel.
 __device__ __forceinline__ void bnq_finish(const BnqParams& b, BnqState& st, unsigned long long numel, bool ticket, int lane) {
   if (b.q.minmax) mm_to_counts(st.qc, st.mx, st.mn, st.n1, st.n2);
