@@ -49,6 +49,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the CPU baseline sample (0 = same as GPU)')
     ap.add_argument('--breakdown', action='store_true', help='also print the per-kernel time table to stderr')
+    ap.add_argument('--dump-launches', default='', help='write the per-launch device times of one step (CSV) to this file')
     return ap.parse_args()
 
 
@@ -338,6 +339,14 @@ def run_native(a):
                 d['ms'] += max(0.0, ea.elapsed_time(eb) - overhead)
                 d['bytes'] += (meta or {}).get('bytes', 0)
                 d['ops'] += (meta or {}).get('ops', 0)
+        if a.dump_launches and rank == 0:
+            with open(a.dump_launches, 'w') as f:
+                f.write('# one %s step, per-launch device time from event nodes inside the replayed CUDA graph (event overhead %.2f us subtracted)\n'
+                        % (a.workload, overhead * 1e3))
+                f.write('index,entry,us,algorithmic_bytes,ops\n')
+                for i, (name, ea, eb, meta) in enumerate(prof.records):
+                    f.write('%d,%s,%.2f,%d,%d\n' % (i, name, max(0.0, ea.elapsed_time(eb) - overhead) * 1e3,
+                                                   (meta or {}).get('bytes', 0), (meta or {}).get('ops', 0)))
         summ, timing_mode = acc, 'per-launch CUDA events inside a replayed graph of the step'
     except Exception as e:      # fall back to eager bracketing (includes host launch gaps on tiny kernels)
         _lib.profiler = None

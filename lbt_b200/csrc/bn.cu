@@ -22,6 +22,16 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kRows = 4;  // rows (batch entries) in flight per thread
 
+// bench aid (lbt_bn_set_debug): phase timestamps of CTA 0 / thread 0 (globaltimer ns)
+__device__ unsigned long long* g_bn_dbg = nullptr;
+__device__ __forceinline__ void bn_stamp(int slot) {
+  if (g_bn_dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    g_bn_dbg[slot] = t;
+  }
+}
+
 struct Tiling {
   size_t n_outer, n_inner;
   int C;
@@ -32,8 +42,8 @@ struct Tiling {
 
 __device__ __forceinline__ void publish_counters(unsigned long long* counters, uint32_t n1, uint32_t n2, size_t numel,
                                                  uint32_t* s_red) {
-  // block reduce two u32 counters and add them to the site's statistics block; the last CTA (ticket)
-  // adds the element count.  Must be called by all threads.
+  // block reduce two u32 counters and add them to the site's statistics block; CTA 0 adds the element count.
+  // Must be called by all threads.
   n1 = warp_sum(n1);
   n2 = warp_sum(n2);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -51,12 +61,8 @@ __device__ __forceinline__ void publish_counters(unsigned long long* counters, u
     }
     if (b1) atomicAdd(counters + LBT_CNT_OVER, (unsigned long long)b1);
     if (b2) atomicAdd(counters + LBT_CNT_OVER_HALF, (unsigned long long)b2);
-    __threadfence();
-    const unsigned long long t = atomicAdd(counters + LBT_CNT_TICKET, 1ull);
-    if (t == (unsigned long long)gridDim.x - 1ull) {
-      atomicAdd(counters + LBT_CNT_NUMEL, (unsigned long long)numel);
-      counters[LBT_CNT_TICKET] = 0ull;
-    }
+    // the element count does not need a "last CTA": CTA 0 adds it (fire-and-forget reductions, no ticket round trip)
+    if (blockIdx.x == 0) atomicAdd(counters + LBT_CNT_NUMEL, (unsigned long long)numel);
   }
 }
 
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
   __shared__ uint32_t s_red[16];
   pdl_trigger();
   pdl_wait();
-  const QC c = make_qc(p.q.bits, *reinterpret_cast<volatile const int32_t*>(p.q.ib));
+  const QC c = make_qc(p.q.bits, __ldg(p.q.ib));
   const uint64_t off = site_offset(p.q);
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
@@ -245,8 +251,22 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
   pdl_trigger();
   pdl_wait();
   const int C = p.t.C;
-  const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
-  const QC c2 = make_qc(p.q2.bits, *reinterpret_cast<volatile const int32_t*>(p.q2.ib));
+  {  // start pulling this CTA's first rows while the (slow, fp64) per-channel prologue runs
+    const uint64_t tile = blockIdx.x;
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), v = (uint32_t)(tile % p.t.chunks) * kThreads + threadIdx.x;
+    if (tile < p.t.total_tiles && v < p.t.n_vec) {
+      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r0 + i < r1) {
+          const size_t idx = (r0 + i) * p.t.n_inner + 4 * (size_t)v;
+          prefetch_l1(p.k1 + idx);
+          if (p.add) prefetch_l1(p.add + idx);
+        }
+    }
+  }
+  const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
+  const QC c2 = make_qc(p.q2.bits, __ldg(p.q2.ib));
   const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
   for (int ch = threadIdx.x; ch < C; ch += kThreads) {
     float mean, var;
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
   QC c3 = c2;
   uint64_t off3 = 0;
   if (nxt) {
-    c3 = make_qc(p.q3.bits, *reinterpret_cast<volatile const int32_t*>(p.q3.ib));
+    c3 = make_qc(p.q3.bits, __ldg(p.q3.ib));
     off3 = site_offset(p.q3);
   }
   uint32_t m1 = 0, m2 = 0;
@@ -381,9 +401,9 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
   pdl_trigger();
   pdl_wait();
   const int C = p.t.C;
-  const QC c2 = make_qc(p.bits2, *reinterpret_cast<volatile const int32_t*>(p.ib2));
-  const QC cg2 = make_qc(p.qg2.bits, *reinterpret_cast<volatile const int32_t*>(p.qg2.ib));
-  const QC cg1 = make_qc(p.qg1.bits, *reinterpret_cast<volatile const int32_t*>(p.qg1.ib));
+  const QC c2 = make_qc(p.bits2, __ldg(p.ib2));
+  const QC cg2 = make_qc(p.qg2.bits, __ldg(p.qg2.ib));
+  const QC cg1 = make_qc(p.qg1.bits, __ldg(p.qg1.ib));
   const uint64_t off2 = site_offset(p.qg2), off1 = site_offset(p.qg1);
   uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
   float amx = -INFINITY, amn = INFINITY, bmx = -INFINITY, bmn = INFINITY;
@@ -494,19 +514,34 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   __shared__ uint32_t s_red[16];
   pdl_trigger();
   pdl_wait();
+  bn_stamp(0);
   const int C = p.t.C;
   const bool gq_on = p.qg.bits != 0;
   QC cq = make_qc(8, 0);
   uint64_t offq = 0;
   if (gq_on) {
-    cq = make_qc(p.qg.bits, *reinterpret_cast<volatile const int32_t*>(p.qg.ib));
+    cq = make_qc(p.qg.bits, __ldg(p.qg.ib));
     offq = site_offset(p.qg);
   }
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
   const bool mmq = p.qg.minmax != 0;
-  const QC c1 = make_qc(p.bits1, *reinterpret_cast<volatile const int32_t*>(p.ib1));
-  const QC cg = make_qc(p.bitsg1, *reinterpret_cast<volatile const int32_t*>(p.ibg1));
+  {  // start pulling this CTA's first rows while the (slow, fp64) per-channel prologue runs
+    const uint64_t tile = blockIdx.x;
+    const uint32_t rg = (uint32_t)(tile / p.t.chunks), v = (uint32_t)(tile % p.t.chunks) * kThreads + threadIdx.x;
+    if (tile < p.t.total_tiles && v < p.t.n_vec) {
+      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r0 + i < r1) {
+          const size_t idx = (r0 + i) * p.t.n_inner + 4 * (size_t)v;
+          prefetch_l1(p.kg1 + idx);
+          prefetch_l1(p.k1 + idx);
+        }
+    }
+  }
+  const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
+  const QC cg = make_qc(p.bitsg1, __ldg(p.ibg1));
   const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
   for (int ch = threadIdx.x; ch < C; ch += kThreads) {
     float mean, var;
@@ -522,7 +557,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     s_par[2 * C + ch] = (float)mg;
     s_par[3 * C + ch] = (float)mgx;
   }
+  bn_stamp(1);
   __syncthreads();
+  bn_stamp(2);
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -577,10 +614,12 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
         }
     }
   }
+  bn_stamp(3);
   if (gq_on) {
     if (mmq) mm_to_counts(cq, mx, mn, n1, n2);
     publish_counters(p.qg.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
   }
+  bn_stamp(4);
 }
 
 // ---- host helpers ----------------------------------------------------------------------------
@@ -814,4 +853,9 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
   launch_pdl(bn_bwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_apply");
+}
+
+extern "C" int lbt_bn_set_debug(void* dev_u64) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_u64);
+  return cudaMemcpyToSymbol(lbt::g_bn_dbg, &p, sizeof(p)) == cudaSuccess ? LBT_OK : LBT_ECUDA;
 }

@@ -87,7 +87,7 @@ struct BnqState {
   float mx, mn;
   uint32_t tiles;
   __device__ __forceinline__ void init(const BnqParams& b) {
-    qc = make_qc(b.q.bits, *reinterpret_cast<volatile const int32_t*>(b.q.ib));
+    qc = make_qc(b.q.bits, __ldg(b.q.ib));
     off = site_offset(b.q);
     n1 = n2 = 0;
     mx = -INFINITY;
@@ -207,21 +207,14 @@ __device__ __forceinline__ void bnq_flush_cta(const BnqParams& b, int* s_stat, u
   }
 }
 
-// End of the kernel: publish the overflow statistics; `ticket` (one warp per CTA) runs the CTA ticket that adds numel.
+// End of the kernel: publish the overflow statistics; the `ticket` warp of CTA 0 adds the element count.
 __device__ __forceinline__ void bnq_finish(const BnqParams& b, BnqState& st, unsigned long long numel, bool ticket, int lane) {
   if (b.q.minmax) mm_to_counts(st.qc, st.mx, st.mn, st.n1, st.n2);
   const uint32_t n1 = warp_sum(st.n1), n2 = warp_sum(st.n2);
   if (lane == 0 && b.q.counters) {
     if (n1) atomicAdd(b.q.counters + LBT_CNT_OVER, (unsigned long long)n1);
     if (n2) atomicAdd(b.q.counters + LBT_CNT_OVER_HALF, (unsigned long long)n2);
-    if (ticket) {
-      __threadfence();
-      const unsigned long long t = atomicAdd(b.q.counters + LBT_CNT_TICKET, 1ull);
-      if (t == (unsigned long long)gridDim.x - 1ull) {
-        atomicAdd(b.q.counters + LBT_CNT_NUMEL, numel);
-        b.q.counters[LBT_CNT_TICKET] = 0ull;
-      }
-    }
+    if (ticket && blockIdx.x == 0) atomicAdd(b.q.counters + LBT_CNT_NUMEL, numel);   // fire-and-forget, no ticket
   }
 }
 
