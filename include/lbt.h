@@ -373,6 +373,37 @@ int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t
                      const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream);
 
 /*
+ * lbt_bn_bwd_quant_stats + lbt_bn_bwd_apply in ONE launch, for tensors small enough that the whole tensor is one wave of
+ * resident CTAs (<= 16 batch rows per CTA): the mantissas the second pass needs stay in shared memory and the CTAs meet
+ * at a grid-wide barrier (`barrier`: one zeroed uint64 on the device).  Same arithmetic, bit-identical results.  Returns
+ * LBT_EUNSUPPORTED when the tensor does not fit that shape — the caller then runs the two passes as separate launches.
+ */
+typedef struct lbt_bn_bwd_args {
+  const float* g;          /* gradient w.r.t. the module output [n_outer, n_inner] */
+  const float* out;        /* module output (relu == 2), or NULL */
+  const int8_t* k2;
+  const int8_t* k1;
+  uint64_t n_outer, n_inner;
+  int32_t C, relu;
+  int32_t bits2, bits1;    /* Rescale_q X bits / Normalization_q X bits */
+  const int32_t* ib2;
+  const int32_t* ib1;
+  const float* gamma_q;
+  const float* beta_q;
+  lbt_qsite q_g2, q_g1;    /* Rescale_q / Normalization_q gradient quantisers */
+  float* d_add;            /* optional */
+  int64_t* bwd_sums;       /* [4*C], zeroed */
+  const int64_t* fwd_sums; /* [2*C] */
+  float eps;
+  int32_t has_q_grad;
+  lbt_qsite q_grad;        /* the producing convolution's gradient quantiser (has_q_grad != 0) */
+  float* dx;               /* optional when has_q_grad */
+  int8_t* g_mant;
+  uint64_t* barrier;
+} lbt_bn_bwd_args;
+int lbt_bn_bwd_fused(const lbt_bn_bwd_args* args, void* stream);
+
+/*
  * tf.nn.max_pool on an NHWC fp32 tensor (`MaxPool_q`, dynamic_fixed_point.py:993-1006): 'SAME' padding ignores
  * out-of-range taps (pad_top / pad_left = TF's pad_before), 'VALID' is pad 0.  C % 4 == 0.  idx[N,OH,OW,C] receives the
  * winning tap r*k + s (first maximum in scan order); lbt_maxpool_bwd routes g[N,OH,OW,C] back through it as a gather

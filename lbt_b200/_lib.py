@@ -40,6 +40,7 @@ SIGNATURES = {
     'lbt_split_s16': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     'lbt_transpose_i8': (c_int, [c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_void_p]),
     'lbt_colsum_i': (c_int, [c_void_p, c_int, c_size_t, c_size_t, c_void_p, c_void_p]),
+    'lbt_bn_bwd_fused': (c_int, [c_void_p, c_void_p]),
     'lbt_maxpool_fwd': (c_int, [c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),
     'lbt_maxpool_bwd': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p]),
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
@@ -88,6 +89,16 @@ class QSiteStruct(ctypes.Structure):
     """lbt_qsite (include/lbt.h): one quantiser call site as the fused kernels see it."""
     _fields_ = [('bits', ctypes.c_int32), ('stats_minmax', ctypes.c_int32), ('ib', c_void_p), ('noise', c_void_p),
                 ('seed', c_u64), ('offset', c_u64), ('dev_step', c_void_p), ('counters', c_void_p)]
+
+
+class BnBwdArgs(ctypes.Structure):
+    """lbt_bn_bwd_args (include/lbt.h)."""
+    _fields_ = [('g', c_void_p), ('out', c_void_p), ('k2', c_void_p), ('k1', c_void_p), ('n_outer', c_u64), ('n_inner', c_u64),
+                ('C', ctypes.c_int32), ('relu', ctypes.c_int32), ('bits2', ctypes.c_int32), ('bits1', ctypes.c_int32),
+                ('ib2', c_void_p), ('ib1', c_void_p), ('gamma_q', c_void_p), ('beta_q', c_void_p), ('q_g2', QSiteStruct),
+                ('q_g1', QSiteStruct), ('d_add', c_void_p), ('bwd_sums', c_void_p), ('fwd_sums', c_void_p), ('eps', c_float),
+                ('has_q_grad', ctypes.c_int32), ('q_grad', QSiteStruct), ('dx', c_void_p), ('g_mant', c_void_p),
+                ('barrier', c_void_p)]
 
 
 class NoiseJob(ctypes.Structure):
@@ -149,6 +160,7 @@ class Profiler:
 
     def __init__(self, external=False):
         self.records = []          # (name, start_event, end_event, meta)
+        self.keep = []
         self.external = external   # True: events are recorded as nodes of a CUDA graph being captured; every replay
                                    # re-times every launch back to back on the device (no host launch gaps)
 
@@ -183,6 +195,27 @@ def call(name, *args, meta=None):
     b.record()
     profiler.records.append((name, a, b, meta))
     check(rc)
+
+
+def try_call(name, *args, meta=None):
+    """Like call(), but returns False (without raising) when the entry point answers LBT_EUNSUPPORTED — for kernels
+    that only take some shapes and have a general path behind them (still inside the library, never a CPU fallback)."""
+    fn = getattr(lib(), name)
+    if profiler is None:
+        rc = fn(*args)
+    else:
+        a, b = profiler.event(), profiler.event()
+        a.record()
+        rc = fn(*args)
+        b.record()
+        if rc == 0:
+            profiler.records.append((name, a, b, meta))
+        else:
+            profiler.keep.append((a, b))     # event nodes already captured into a graph must outlive the capture
+    if rc == -2:
+        return False
+    check(rc)
+    return True
 
 
 def ptr(t):

@@ -622,6 +622,210 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   bn_stamp(4);
 }
 
+// ------------------------------------------------------------------------------------------------
+// bwd 1 + bwd 2 in ONE launch for tensors that fit one wave of resident CTAs (every tensor of a CIFAR-size step):
+// pass 1 as above, but the mantissas the second pass needs (kg1, k1) stay in shared memory; the CTAs then meet at a
+// grid-wide barrier (one int64 word from the step's zeroed arena: all CTAs are co-resident by construction) and run
+// pass 2 from shared memory.  Saves a launch + dependent-launch gap, the kg1 round trip through HBM and a prologue.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxSavedRows = 16;
+
+struct BwdFusedParams {
+  Bwd1Params a;
+  Bwd2Params b;               // b.kg1 / b.k1 unused (shared memory)
+  unsigned long long* bar;    // grid barrier word, zero at launch
+};
+
+__device__ int g_bn_error = 0;
+
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFusedParams q) {
+  extern __shared__ unsigned long long s_dyn[];
+  __shared__ uint32_t s_red[16];
+  const Bwd1Params& p = q.a;
+  const Bwd2Params& p2 = q.b;
+  const int C = p.t.C;
+  unsigned long long* s_acc = s_dyn;                                    // [4*C] (pass 1), then float s_par[4*C]
+  uint2* s_save = reinterpret_cast<uint2*>(s_dyn + 4 * C);              // [rows_per_group][kThreads]: {kg1 word, k1 word}
+  pdl_trigger();
+  pdl_wait();
+  const QC c2 = make_qc(p.bits2, __ldg(p.ib2));
+  const QC cg2 = make_qc(p.qg2.bits, __ldg(p.qg2.ib));
+  const QC cg1 = make_qc(p.qg1.bits, __ldg(p.qg1.ib));
+  const QC c1 = make_qc(p2.bits1, __ldg(p2.ib1));
+  const bool gq_on = p2.qg.bits != 0;
+  QC cq = cg1;
+  uint64_t offq = 0;
+  if (gq_on) {
+    cq = make_qc(p2.qg.bits, __ldg(p2.qg.ib));
+    offq = site_offset(p2.qg);
+  }
+  const uint64_t off2 = site_offset(p.qg2), off1 = site_offset(p.qg1);
+  uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  float amx = -INFINITY, amn = INFINITY, bmx = -INFINITY, bmn = INFINITY;
+  const bool mm2 = p.qg2.minmax != 0, mm1 = p.qg1.minmax != 0;
+  Acc<4> acc;
+  acc.zero();
+  const uint64_t tile = blockIdx.x;   // exactly one tile per CTA
+  const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
+  const uint32_t v = chk * kThreads + threadIdx.x;
+  const bool active = v < p.t.n_vec;
+  const int c0 = active ? (int)((4ull * v) % (uint64_t)C) : 0;
+  const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+  if (active) {
+    const float4 u2v = site_noise(p.qg2, v, off2), u1v = site_noise(p.qg1, v, off1);
+    const float u2[4] = {u2v.x, u2v.y, u2v.z, u2v.w}, u1[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
+    float g[4], b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g[j] = __ldg(p.gq + c0 + j);
+      b[j] = __ldg(p.bq + c0 + j);
+    }
+    for (size_t r = r0; r < r1; r += kRows) {
+      float4 gv[kRows], ov[kRows];
+      uint32_t w2[kRows], w1[kRows];
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
+          w2[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k2 + idx));
+          w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
+          if (p.relu == 2) ov[i] = __ldcs(reinterpret_cast<const float4*>(p.out + idx));
+        }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + kRows + i < r1) {
+          const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+          prefetch_l1(p.g + idx);
+          prefetch_l1(p.k2 + idx);
+          prefetch_l1(p.k1 + idx);
+          if (p.relu == 2) prefetch_l1(p.out + idx);
+        }
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + i < r1) {
+          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          int k2[4], k1[4];
+          unpack4(w2[i], k2);
+          unpack4(w1[i], k1);
+          const float gin[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+          const float oin[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
+          float gm[4], kq1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float gj = gin[j];
+            if (p.relu == 1) {
+              const float y2 = __fadd_rn(__fmul_rn(__int2float_rn(k2[j]) * c2.inv_m, g[j]), b[j]);
+              if (!(y2 > 0.0f)) gj = 0.0f;
+            } else if (p.relu == 2) {
+              if (!(oin[j] > 0.0f)) gj = 0.0f;
+            }
+            gm[j] = gj;
+            const float kg2 = mm2 ? squant_mm(gj, u2[j], cg2, amx, amn) : squant(gj, u2[j], cg2, a1, a2);   // dfxp:687
+            const int kg2i = __float2int_rn(kg2);
+            acc.s[0][j] += kg2i;
+            acc.s[1][j] += kg2i * k2[j];
+            const float dx2 = __fmul_rn(kg2 * cg2.inv_m, g[j]);                  // dfxp:691
+            kq1[j] = mm1 ? squant_mm(dx2, u1[j], cg1, bmx, bmn) : squant(dx2, u1[j], cg1, b1, b2);         // dfxp:621
+            const int kg1i = __float2int_rn(kq1[j]);
+            acc.s[2][j] += kg1i;
+            acc.s[3][j] += kg1i * k1[j];
+          }
+          if (p.d_add) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+          s_save[(r + i - r0) * kThreads + threadIdx.x] = make_uint2(pack4(kq1), w1[i]);
+        }
+    }
+  }
+  flush_block<4>(acc, p.sums, C, s_acc);
+  const size_t numel = p.t.n_outer * p.t.n_inner;
+  if (mm2) mm_to_counts(cg2, amx, amn, a1, a2);
+  if (mm1) mm_to_counts(cg1, bmx, bmn, b1, b2);
+  publish_counters(p.qg2.counters, a1, a2, numel, s_red);
+  publish_counters(p.qg1.counters, b1, b2, numel, s_red);
+
+  // ---- grid-wide barrier: every CTA's sums are in global memory before anyone reads them ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(q.bar, 1ull);
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (*reinterpret_cast<volatile unsigned long long*>(q.bar) < (unsigned long long)gridDim.x) {
+      if ((++spins & 0xff) == 0) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ll) {  // ~2 s: never hang the GPU on a protocol bug
+          atomicExch(&g_bn_error, 1);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+
+  // ---- pass 2 from shared memory ----
+  float* s_par = reinterpret_cast<float*>(s_dyn);
+  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  for (int ch = threadIdx.x; ch < C; ch += kThreads) {
+    float mean, var;
+    moments(p2.fsums, C, ch, n, c1.inv_m, mean, var);
+    const float den = __fsqrt_rn(__fadd_rn(var, p2.eps));
+    const double sg = (double)__ldcg(p.sums + 2 * C + ch) * (double)cg1.inv_m;
+    const double sgx = (double)__ldcg(p.sums + 3 * C + ch) * (double)cg1.inv_m * (double)c1.inv_m;
+    const double mg = sg / n;
+    const double mgx = ((sgx - (double)mean * sg) / (double)den) / n;
+    s_par[ch] = mean;
+    s_par[C + ch] = den;
+    s_par[2 * C + ch] = (float)mg;
+    s_par[3 * C + ch] = (float)mgx;
+  }
+  __syncthreads();
+  uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  const bool mmq = p2.qg.minmax != 0;
+  if (active) {
+    float mean[4], den[4], mg[4], mgx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mean[j] = s_par[c0 + j];
+      den[j] = s_par[C + c0 + j];
+      mg[j] = s_par[2 * C + c0 + j];
+      mgx[j] = s_par[3 * C + c0 + j];
+    }
+    float uq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gq_on) {
+      const float4 t = site_noise(p2.qg, v, offq);
+      uq[0] = t.x; uq[1] = t.y; uq[2] = t.z; uq[3] = t.w;
+    }
+    for (size_t r = r0; r < r1; ++r) {
+      const size_t idx = r * p.t.n_inner + 4 * (size_t)v;
+      const uint2 sv = s_save[(r - r0) * kThreads + threadIdx.x];
+      int kg[4], k1[4];
+      unpack4(sv.x, kg);
+      unpack4(sv.y, k1);
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gqv = __int2float_rn(kg[j]) * cg1.inv_m;
+        const float xhat = __fdiv_rn(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j]);
+        o[j] = __fdiv_rn(gqv - mg[j] - xhat * mgx[j], den[j]);
+      }
+      if (p2.dx) *reinterpret_cast<float4*>(p2.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+      if (gq_on) {
+        float kq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) kq[j] = mmq ? squant_mm(o[j], uq[j], cq, mx, mn) : squant(o[j], uq[j], cq, n1, n2);
+        *reinterpret_cast<uint32_t*>(p2.g_mant + idx) = pack4(kq);
+      }
+    }
+  }
+  if (gq_on) {
+    if (mmq) mm_to_counts(cq, mx, mn, n1, n2);
+    publish_counters(p2.qg.counters, n1, n2, numel, s_red);
+  }
+}
+
 // ---- host helpers ----------------------------------------------------------------------------
 // Resident CTAs per SM of a kernel with `smem` dynamic bytes (cached per kernel and device).
 template <typename K>
@@ -695,7 +899,7 @@ inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) {
+  if (bytes > 40 * 1024) {   // the 48 KB default covers static + dynamic shared memory: opt in with some margin
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(bn)");
@@ -853,6 +1057,62 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
   launch_pdl(bn_bwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_apply");
+}
+
+extern "C" int lbt_bn_bwd_fused(const lbt_bn_bwd_args* a, void* stream) {
+  if (!a || !a->g || !a->k2 || !a->k1 || !a->ib2 || !a->gamma_q || !a->beta_q || !a->q_g2.ib || !a->q_g1.ib || !a->bwd_sums ||
+      !a->ib1 || !a->fwd_sums || !a->barrier)
+    return LBT_EINVAL;
+  if (a->relu < 0 || a->relu > 2 || (a->relu == 2 && !a->out)) return LBT_EINVAL;
+  if (!a->dx && !a->has_q_grad) return LBT_EINVAL;
+  if (a->has_q_grad && (!a->g_mant || !a->q_grad.ib || a->q_grad.bits < 2 || a->q_grad.bits > 8)) return LBT_EINVAL;
+  for (int b : {a->bits2, a->q_g2.bits, a->q_g1.bits, a->bits1})
+    if (b < 2 || b > 8) return LBT_EUNSUPPORTED;
+  if (a->n_outer == 0 || a->n_inner == 0) return LBT_OK;
+  if (!al16(a->g) || !al4(a->k2) || !al4(a->k1) || (a->out && !al16(a->out)) || (a->d_add && !al16(a->d_add)) ||
+      (a->dx && !al16(a->dx)) || (a->g_mant && !al4(a->g_mant)))
+    return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const int C = a->C;
+  BwdFusedParams q{};
+  // occupancy with the largest row buffer; the tiling must then be ONE tile per resident CTA with <= kMaxSavedRows rows
+  const size_t smem_max = (size_t)4 * C * 8 + (size_t)kMaxSavedRows * kThreads * sizeof(uint2);
+  int rc = set_smem(bn_bwd_fused_kernel, smem_max);
+  if (rc) return rc;
+  unsigned grid;
+  rc = make_tiling(q.a.t, a->n_outer, a->n_inner, C, grid, ctas_per_sm(bn_bwd_fused_kernel, smem_max));
+  if (rc) return rc;
+  if (!q.a.t.fixed_channels || q.a.t.total_tiles != grid || q.a.t.rows_per_group > (uint32_t)kMaxSavedRows) return LBT_EUNSUPPORTED;
+  q.b.t = q.a.t;
+  q.a.g = a->g;
+  q.a.out = a->out;
+  q.a.relu = a->relu;
+  q.a.k2 = a->k2;
+  q.a.k1 = a->k1;
+  q.a.bits2 = a->bits2;
+  q.a.ib2 = a->ib2;
+  q.a.gq = a->gamma_q;
+  q.a.bq = a->beta_q;
+  q.a.qg2 = site_from_abi(&a->q_g2);
+  q.a.qg1 = site_from_abi(&a->q_g1);
+  q.a.d_add = a->d_add;
+  q.a.kg1 = nullptr;
+  q.a.sums = reinterpret_cast<long long*>(a->bwd_sums);
+  q.b.bits1 = a->bits1;
+  q.b.ib1 = a->ib1;
+  q.b.fsums = reinterpret_cast<const long long*>(a->fwd_sums);
+  q.b.eps = a->eps;
+  q.b.bitsg1 = a->q_g1.bits;
+  q.b.ibg1 = a->q_g1.ib;
+  q.b.bsums = reinterpret_cast<const long long*>(a->bwd_sums);
+  q.b.dx = a->dx;
+  q.b.qg = site_from_abi(a->has_q_grad ? &a->q_grad : nullptr);
+  q.b.g_mant = a->g_mant;
+  q.bar = reinterpret_cast<unsigned long long*>(a->barrier);
+  const size_t smem = (size_t)4 * C * 8 + (size_t)q.a.t.rows_per_group * kThreads * sizeof(uint2);
+  launch_pdl(bn_bwd_fused_kernel, grid, kThreads, smem_max, reinterpret_cast<cudaStream_t>(stream), q);
+  (void)smem;
+  return check_launch("lbt_bn_bwd_fused");
 }
 
 extern "C" int lbt_bn_set_debug(void* dev_u64) {

@@ -1026,27 +1026,43 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
     N, C = g_.shape[0], g_.shape[-1]
     n_inner = g_.numel() // N
     dev = g_.device
-    bsums = rt.zeros_i64(4 * C, dev)
-    kg1 = torch.empty_like(k1)
+    bsums = rt.zeros_i64(4 * C + 2, dev)          # [4C] sums + the grid-barrier word of the fused launch
     d_add = torch.empty_like(g_) if has_add else None
-    nzg2, offg2 = _site_args(resc.qG, g_)
-    nzg1, offg1 = _site_args(norm.qG, g_)
-    _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g_), _lib.ptr(out_), relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
-              C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
-              _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
-              _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
-              _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
-              int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
-              meta=dict(bytes=g_.numel() * (7 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
     dx = torch.empty_like(g_) if want_dx else None
     qg = gm = None
     if grad_site is not None:
         qg = grad_site.abi(n_inner, dev)
         gm = torch.empty_like(k1)
-    _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
-              _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
-              ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), _lib.stream(),
-              meta=dict(bytes=g_.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
+    nbytes = g_.numel() * (6 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0) + (4 if want_dx else 0) +
+                           (1 if gm is not None else 0))
+    # small tensors: both passes in one launch (lbt_bn_bwd_fused); it declines shapes that are not one wave of CTAs
+    fused = False
+    if FUSE_BN_BWD:
+        a = _lib.BnBwdArgs(g=_lib.ptr(g_), out=_lib.ptr(out_), k2=_lib.ptr(k2), k1=_lib.ptr(k1), n_outer=N, n_inner=n_inner, C=C,
+                           relu=relu_mode, bits2=resc.qX.bits, bits1=norm.qX.bits, ib2=_lib.ptr(resc.qX.range),
+                           ib1=_lib.ptr(norm.qX.range), gamma_q=_lib.ptr(gq), beta_q=_lib.ptr(bq),
+                           q_g2=resc.qG.abi(n_inner, dev), q_g1=norm.qG.abi(n_inner, dev), d_add=_lib.ptr(d_add),
+                           bwd_sums=_lib.ptr(bsums), fwd_sums=_lib.ptr(sums), eps=float(norm.eps),
+                           has_q_grad=int(qg is not None), dx=_lib.ptr(dx), g_mant=_lib.ptr(gm),
+                           barrier=bsums[4 * C:].data_ptr())
+        if qg is not None:
+            a.q_grad = qg
+        fused = _lib.try_call('lbt_bn_bwd_fused', ctypes.addressof(a), _lib.stream(), meta=dict(bytes=nbytes))
+    if not fused:
+        kg1 = torch.empty_like(k1)
+        nzg2, offg2 = _site_args(resc.qG, g_)
+        nzg1, offg1 = _site_args(norm.qG, g_)
+        _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g_), _lib.ptr(out_), relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
+                  C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
+                  _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
+                  _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
+                  _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
+                  int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
+                  meta=dict(bytes=g_.numel() * (7 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
+        _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
+                  _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
+                  ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), _lib.stream(),
+                  meta=dict(bytes=g_.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
     # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
     dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
     dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
@@ -1126,6 +1142,9 @@ class _ConvBNFn(torch.autograd.Function):
                 (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None)
 
 
+FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lbt_bn_bwd_fused, grid barrier) where the
+                      # tensor is one wave of CTAs.  Bit-identical; measured no faster on B200 (1.77 vs 1.75 ms ResNet-20
+                      # step: the barrier + second fp64 prologue cost what the saved launch gains), so off by default
 FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused units (tests compare both settings)
 
 

@@ -11,8 +11,9 @@ from lbt_b200 import dfxp as D, models as M  # noqa: E402
 from lbt_b200.trainer import Trainer  # noqa: E402
 
 
-def _run(name, fused, steps, batch, image, kw):
+def _run(name, fused, steps, batch, image, kw, bn_bwd=False):
     D.FUSE_UNITS = fused
+    D.FUSE_BN_BWD = bn_bwd
     try:
         torch.manual_seed(3)
         model = getattr(M, name)(8, weight_decay=2e-4, seed=9, **kw).cuda()
@@ -29,6 +30,7 @@ def _run(name, fused, steps, batch, image, kw):
                     bn=[b.clone() for n, b in model.named_buffers() if 'running' in n])
     finally:
         D.FUSE_UNITS = True
+        D.FUSE_BN_BWD = False
 
 
 @pytest.mark.parametrize('name,batch,image,kw', [
@@ -47,6 +49,19 @@ def test_fused_units_equal_unfused_bit_for_bit(name, batch, image, kw):
         assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
     for x, y in zip(a['bn'], b['bn']):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('name,batch,image,kw', [('CIFAR10_Resnet20', 64, 32, {}), ('CIFAR10_Resnet20', 7, 32, {}),
+                                                 ('Resnet18', 4, 64, dict(image=64, num_classes=10))])
+def test_single_launch_bn_backward_equals_two_passes(name, batch, image, kw):
+    """lbt_bn_bwd_fused (both BN backward passes + grid barrier in one launch) vs the two separate launches."""
+    a = _run(name, True, 3, batch, image, kw, bn_bwd=True)
+    b = _run(name, True, 3, batch, image, kw, bn_bwd=False)
+    assert a['losses'] == b['losses']
+    assert torch.equal(a['ranges'], b['ranges'])
+    assert torch.equal(a['counters'], b['counters'])
+    for k in ('g', 'w', 'a'):
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
 
 
 def test_fused_unit_hands_mantissas_to_the_next_conv():
