@@ -121,6 +121,12 @@ class Runtime:
             return self._arena[off:off + n]
         return torch.zeros(int(n), dtype=torch.int64, device=device)
 
+    def join_side(self):
+        """Make the current stream wait for the weight-gradient kernels still running on the side stream."""
+        if getattr(self, '_side_pending', False) and self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+        self._side_pending = False
+
     def side_stream(self, device):
         if self._side is None or self._side.device != torch.device(device):
             self._side = torch.cuda.Stream(device=device)
@@ -543,7 +549,7 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     rt = layer.qX.runtime
     # ---- wgrad: dW[Kf, Cout] = A^T[Kf, M] . G[M, Cout], reduction over M split across the SMs.  It shares only its
     # inputs with dgrad, so (inside a Trainer step) it runs on a side stream: a parallel branch of the step's graph ----
-    fork = need_dw and need_dx and rt.overlap and rt._arena_on and _lib.profiler is None
+    fork = need_dw and rt.overlap and rt._arena_on and rt.grad_sink is not None and rt.grad_sink.active and _lib.profiler is None
     main = torch.cuda.current_stream(dev) if fork else None
     side = rt.side_stream(dev) if fork else None
     if fork:
@@ -610,7 +616,12 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
             G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
     if fork:
-        main.wait_stream(side)     # join before anything downstream (or the allocator) can touch the operands
+        # NO join here: the weight gradient is needed only by the end-of-backward finalize (Runtime.join_side, called by
+        # the Trainer before lbt_finalize_multi), so it overlaps the rest of the backward chain.  Its operands must not
+        # be recycled by the allocator before the side stream is done with them.
+        for t in (xm, gm):
+            t.record_stream(side)
+        rt._side_pending = True
     return dx, dW, db
 
 

@@ -120,6 +120,7 @@ class Trainer:
         logits = self.model(X)
         loss = self.model.loss(logits, y)
         loss.backward()
+        rt.join_side()                       # weight-gradient kernels run on a side stream beside the backward chain
         if self.batched:
             self.sink.flush()
         return loss.detach(), logits.detach()
