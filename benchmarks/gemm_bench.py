@@ -63,11 +63,54 @@ def rand_i8(*shape, unsigned=False):
     return torch.randint(-128, 128, shape, dtype=torch.int8, device='cuda')
 
 
-def bench_square(n, flush):
-    A, B = rand_i8(n, n, unsigned=True), rand_i8(n, n)
+def sustained(fn, seconds=2.0):
+    """Run fn back to back for ~`seconds`, sampling SM clock / power / throttle reasons with nvidia-smi meanwhile."""
+    import subprocess
+    import time
+    q = 'clocks.sm,power.draw,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown'
+    mon = subprocess.Popen(['nvidia-smi', '-i', '0', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, t0 = 0, time.time()
+    a.record()
+    while time.time() - t0 < seconds:
+        for _ in range(8):
+            fn()
+        n += 8
+        torch.cuda.synchronize()
+    b.record()
+    torch.cuda.synchronize()
+    dt = a.elapsed_time(b) * 1e-3 / n
+    time.sleep(0.15)
+    mon.terminate()
+    rows = [l.split(',') for l in mon.stdout.read().strip().splitlines() if l.count(',') >= 4]
+    mid = rows[len(rows) // 3:] or rows
+    clk = sorted(float(r[0]) for r in mid)
+    return dt, dict(sm_mhz_median=clk[len(clk) // 2] if clk else None, power_w_max=max(float(r[1]) for r in mid) if mid else None,
+                    sw_power_cap=any('Active' in r[2] and 'Not' not in r[2] for r in mid),
+                    hw_slowdown=any('Active' in r[3] and 'Not' not in r[3] for r in mid),
+                    sw_thermal=any('Active' in r[4] and 'Not' not in r[4] for r in mid))
+
+
+def rand_bits(n, bits, unsigned=False):
+    """Mantissas uniform over the full range of a `bits`-wide DFXP quantiser (activations: bits+1 unsigned)."""
+    if unsigned:
+        return torch.randint(0, 1 << bits, (n, n), dtype=torch.int32, device='cuda').to(torch.uint8)
+    return torch.randint(-(1 << (bits - 1)), 1 << (bits - 1), (n, n), dtype=torch.int32, device='cuda').to(torch.int8)
+
+
+def bench_square(n, flush, bits=8):
+    A, B = rand_bits(n, bits, unsigned=True), rand_bits(n, bits)
     out = torch.empty(n, n, dtype=torch.float32, device='cuda')
     t = timeit(lambda: G.gemm_i8(A, B, exp_const=-14, out=out), flush=flush)
-    return dict(kind='gemm', M=n, N=n, K=n, us=t * 1e6, tops=2 * n ** 3 / t / 1e12)
+    row = dict(kind='gemm', M=n, N=n, K=n, bits=bits, us=t * 1e6, tops=2 * n ** 3 / t / 1e12)
+    if n >= 8192:
+        ts, clocks = sustained(lambda: G.gemm_i8(A, B, exp_const=-14, out=out))
+        row.update(sustained_tops=2 * n ** 3 / ts / 1e12, clocks=clocks)
+        print('   sustained %.0f TOPS, clocks %s' % (row['sustained_tops'], clocks))
+    return row
 
 
 def conv_case(N, H, W, Cin, Cout, k, s, flush, name):
@@ -114,6 +157,7 @@ def main():
     ap.add_argument('--square', default='4096,8192,16384')
     ap.add_argument('--layers', default='resnet20,resnet18')
     ap.add_argument('--flush', action='store_true')
+    ap.add_argument('--bits', default='8', help='operand widths of the square GEMM sweep (config 3: 4,6,8)')
     ap.add_argument('--only', default='', help='substring filter on the layer name')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--path', type=int, default=1, help='0: TMA kernels only, 1: gather kernels for narrow channels')
@@ -124,7 +168,8 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda') if a.flush else None
     rows = []
     for n in [int(s) for s in a.square.split(',') if s]:
-        rows.append(bench_square(n, flush))
+        for bits in [int(b) for b in a.bits.split(',')]:
+            rows.append(bench_square(n, flush, bits))
     for fam in [f for f in a.layers.split(',') if f and f != 'none']:
         for (N, H, W, Ci, Co, k, s, name) in LAYERS[fam]:
             if a.only and a.only not in name:
@@ -133,7 +178,7 @@ def main():
     for r in rows:
         r['frac_int8_peak'] = r['tops'] / INT8_PEAK_TOPS
         print('%-6s %-32s M=%-8d N=%-6d K=%-8d %9.1f us %8.1f TOPS (%.3f of %.0f)%s' % (
-            r['kind'], r.get('layer', 'square'), r['M'], r['N'], r['K'], r['us'], r['tops'], r['frac_int8_peak'],
+            r['kind'], r.get('layer', 'square %d-bit' % r.get('bits', 8)), r['M'], r['N'], r['K'], r['us'], r['tops'], r['frac_int8_peak'],
             INT8_PEAK_TOPS, '  %.0f GB/s' % r['gbs'] if 'gbs' in r else ''))
     assert G.debug_error() == 0
     os.makedirs(os.path.dirname(a.out), exist_ok=True)

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], kEpiWarps);
+      mbar_init(&tmem_empty_bar[s], BN > 32 ? kEpiWarps : 4);   // narrow tiles: the two warps of a quadrant alternate TILES
     }
     mbar_init(&b_bar, kEpiWarps * 32);
     s_abort = 0;
@@ -287,9 +287,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       for (int i = lane; i < 2 * BN; i += 32) my_stat[i] = 0;
       __syncwarp();
     }
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, tcount = 0;
     bool ok = true;
-    for (uint32_t tile = blockIdx.x; tile < p.m_tiles && ok; tile += gridDim.x) {
+    constexpr bool kByTile = BN <= 32;   // one 16/32-column group per tile: split the TILES between the quadrant's warps
+    for (uint32_t tile = blockIdx.x; tile < p.m_tiles && ok; tile += gridDim.x, ++tcount) {
+      if (kByTile && (tcount & 1u) != half) {   // the other warp of this quadrant drains this accumulator
+        if (++acc == kAccStages) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_ldg_error);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
@@ -303,10 +311,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       }
       ++bst.tiles;
       constexpr int G = BN < 32 ? BN : 32;  // columns fetched from tensor memory per wait
-      constexpr bool kSplit = BN > G;       // both warps of a quadrant work: alternate the G-column groups
+      constexpr bool kSplit = BN > G;       // wide tiles: both warps of a quadrant alternate the G-column groups
 #pragma unroll 1
       for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G) {
-        if (!kSplit && half) break;
         uint32_t vv[G / 16][16];
 #pragma unroll
         for (int q = 0; q < G / 16; ++q) tmem_ld16(taddr + c0 + 16 * q, vv[q]);
