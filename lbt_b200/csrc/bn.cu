@@ -319,6 +319,9 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
       g[j] = s_par[2 * C + c0 + j];
       b[j] = s_par[3 * C + c0 + j];
     }
+    float rden[4];   // one reciprocal per channel: every quotient below is fdiv_by (== IEEE division, 5 FMAs)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rden[j] = __frcp_rn(den[j]);
     const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
     for (size_t r = r0; r < r1; r += kRows) {
       uint32_t kw[kRows];
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float xq = __int2float_rn(k1[j]) * c1.inv_m;
-            const float y1 = __fdiv_rn(__fsub_rn(xq, mean[j]), den[j]);      // dfxp:616
+            const float y1 = fdiv_by(__fsub_rn(xq, mean[j]), den[j], rden[j]);   // dfxp:616
             k2[j] = mm ? squant_mm(y1, un[j], c2, mx, mn) : squant(y1, un[j], c2, n1, n2);   // dfxp:677
             float y2 = __fadd_rn(__fmul_rn(k2[j] * c2.inv_m, g[j]), b[j]);    // dfxp:683
             if (p.add) y2 = __fadd_rn(y2, a4[j]);                             // residual sum, dfxp:862
@@ -573,6 +576,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
       mg[j] = s_par[2 * C + c0 + j];
       mgx[j] = s_par[3 * C + c0 + j];
     }
+    float rden[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rden[j] = __frcp_rn(den[j]);
     float uq[4] = {0.f, 0.f, 0.f, 0.f};
     if (gq_on) {
       const float4 t = site_noise(p.qg, v, offq);
@@ -600,9 +606,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float gq = __int2float_rn(kg[j]) * cg.inv_m;
-            const float xhat = __fdiv_rn(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j]);
+            const float xhat = fdiv_by(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j], rden[j]);
             // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616)
-            o[j] = __fdiv_rn(gq - mg[j] - xhat * mgx[j], den[j]);
+            o[j] = fdiv_by(gq - mg[j] - xhat * mgx[j], den[j], rden[j]);
           }
           if (p.dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
           if (gq_on) {                                                        // the convolution's gradq, dfxp:300
@@ -793,6 +799,9 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
       mg[j] = s_par[2 * C + c0 + j];
       mgx[j] = s_par[3 * C + c0 + j];
     }
+    float rden[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rden[j] = __frcp_rn(den[j]);
     float uq[4] = {0.f, 0.f, 0.f, 0.f};
     if (gq_on) {
       const float4 t = site_noise(p2.qg, v, offq);
@@ -808,8 +817,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float gqv = __int2float_rn(kg[j]) * cg1.inv_m;
-        const float xhat = __fdiv_rn(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j]);
-        o[j] = __fdiv_rn(gqv - mg[j] - xhat * mgx[j], den[j]);
+        const float xhat = fdiv_by(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j], rden[j]);
+        o[j] = fdiv_by(gqv - mg[j] - xhat * mgx[j], den[j], rden[j]);
       }
       if (p2.dx) *reinterpret_cast<float4*>(p2.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
       if (gq_on) {
@@ -1118,4 +1127,49 @@ extern "C" int lbt_bn_bwd_fused(const lbt_bn_bwd_args* a, void* stream) {
 extern "C" int lbt_bn_set_debug(void* dev_u64) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_u64);
   return cudaMemcpyToSymbol(lbt::g_bn_dbg, &p, sizeof(p)) == cudaSuccess ? LBT_OK : LBT_ECUDA;
+}
+
+// Test hook (not in lbt.h): counts the pairs where fdiv_by(a, b, frcp_rn(b)) differs from __fdiv_rn(a, b) bit for bit.
+// Pairs are generated on the device: b over [2^-9, 2^14) (any mantissa), a as a small-integer multiple of a power of two
+// (mantissa differences like the batch-norm numerators), as a full random mantissa, or exactly 0 / -0.
+namespace lbt {
+namespace {
+__global__ void test_fdiv_kernel(unsigned long long n, uint64_t seed, unsigned long long* mismatches, float* first_bad) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 7u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const int eb = (int)(rnd.x % 23u) - 9;                      // exponent of b
+    const float b = __int_as_float(((eb + 127) << 23) | (rnd.y & 0x7fffffu));
+    float a;
+    const uint32_t kind = rnd.z & 3u;
+    if (kind == 0) {
+      a = (float)((int)(rnd.w % 513u) - 256) * exp2i((int)((rnd.z >> 2) % 24u) - 16);      // k * 2^-f
+    } else if (kind == 1) {
+      const float t = (float)((int)(rnd.w % 513u) - 256) * exp2i(-7);
+      a = __fsub_rn(t, __int_as_float(0x3d000000u | (rnd.z >> 9)));                          // k*2^-f - mean
+    } else if (kind == 2) {
+      a = __int_as_float((rnd.w & 0x807fffffu) | ((((rnd.z >> 2) % 60u) + 97u) << 23));     // any mantissa, 2^-30 .. 2^29
+    } else {
+      a = (rnd.w & 1u) ? 0.0f : -0.0f;
+    }
+    const float want = __fdiv_rn(a, b), got = fdiv_by(a, b, __frcp_rn(b));
+    if (__float_as_uint(want) != __float_as_uint(got)) {
+      if (bad == 0 && first_bad) {
+        first_bad[0] = a;
+        first_bad[1] = b;
+      }
+      ++bad;
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+}  // namespace lbt
+
+extern "C" int lbt_test_fdiv(uint64_t n, uint64_t seed, uint64_t* mismatches_dev, float* first_bad_dev, void* stream) {
+  if (!mismatches_dev) return LBT_EINVAL;
+  LBT_REQUIRE_ARCH();
+  lbt::test_fdiv_kernel<<<148 * 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (unsigned long long)n, seed, reinterpret_cast<unsigned long long*>(mismatches_dev), first_bad_dev);
+  return lbt::check_launch("lbt_test_fdiv");
 }

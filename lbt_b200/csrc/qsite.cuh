@@ -54,6 +54,19 @@ __device__ __forceinline__ void mm_to_counts(const QC& c, float mx, float mn, ui
   n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
 }
 
+// a / b, correctly rounded (== __fdiv_rn), for MANY numerators over ONE denominator: r = frcp_rn(b) is computed once
+// (per channel) and each quotient costs five FMA-class instructions instead of the ~12 + special-case branch of the
+// generic IEEE division.  Markstein's scheme: q0 = RN(a*r); two residual corrections q += RN(a - b*q) * r with exact
+// FMA residuals.  Valid while a/b and the residuals stay in the normal range (|a/b| in [2^-100, 2^100] or a == 0), which
+// the batch-norm operands do (b = sqrt(var + eps) in [3e-3, 1e4]); checked against __fdiv_rn over 2^32 random and
+// structured pairs by tests/test_quantize_gpu.py::test_fast_division_is_correctly_rounded (lbt_test_fdiv).
+__device__ __forceinline__ float fdiv_by(float a, float b, float r) {
+  const float q0 = __fmul_rn(a, r);
+  float q = __fmaf_rn(__fmaf_rn(-b, q0, a), r, q0);
+  q = __fmaf_rn(__fmaf_rn(-b, q, a), r, q);
+  return a == 0.0f ? q0 : q;   // keeps the sign of a zero numerator
+}
+
 __device__ __forceinline__ float4 site_noise(const QSite& s, uint32_t v, uint64_t off) {
   if (s.noise) return __ldg(reinterpret_cast<const float4*>(s.noise) + v);
   return philox_noise4(v, s.seed, off);

@@ -242,3 +242,15 @@ def test_large_tensor_properties():
     x[1] = x[0]
     q3, _ = Q.quantize(x[:2], 8, ibt(2), mode=Q.ROUND_PHILOX, seed=1, offset=3)
     assert torch.equal(q3[0], q3[1])
+
+
+def test_fast_division_is_correctly_rounded():
+    """fdiv_by (one reciprocal per denominator + two FMA corrections, used by the batch-norm kernels) must equal the IEEE
+    division bit for bit: 2^32 device-generated pairs covering the batch-norm operand ranges, zero mismatches."""
+    from lbt_b200 import _lib
+    bad = torch.zeros(1, dtype=torch.int64, device='cuda')
+    first = torch.zeros(2, dtype=torch.float32, device='cuda')
+    for seed in range(4):
+        _lib.check(_lib.lib().lbt_test_fdiv(1 << 30, seed, bad.data_ptr(), first.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(bad) == 0, (int(bad), first.tolist())
