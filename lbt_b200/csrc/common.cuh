@@ -55,6 +55,23 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// n / d for runtime-constant d without the ~25-instruction integer division: q = umulhi(n, mul) >> shr, valid for n < 2^31
+// (CUTLASS FastDivmod).  Host: make_fastdiv(d); device: fastdiv(n, fd), fastmod via n - q*d.
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const uint32_t pw = 31 + lg;
+    f.mul = (uint32_t)(((1ull << pw) + d - 1) / d);
+    f.shr = pw - 32;
+  }
+  return f;
+}
+
 #define LBT_REQUIRE_ARCH()                        \
   do {                                            \
     const ::lbt::DeviceInfo& _di = ::lbt::device_info(); \
@@ -66,6 +83,8 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Everything a kernel reads or writes in global memory must come after pdl_wait(); pdl_trigger() lets the next
 // kernel of the stream start being scheduled (it still waits for this grid's completion at its own pdl_wait()).
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

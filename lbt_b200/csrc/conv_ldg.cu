@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       fence_after();
       if (threadIdx.x == 32 * (kLoaderWarps + 1) && tile == blockIdx.x) dbg_stamp(p, 15);
       const uint32_t row = tile * kBlockM + quad * 32 + lane;
+      const uint32_t pix = fused ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
       if (fused && bst.tiles >= (uint32_t)kBnqFlushTiles) {
         bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
               if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + c + j));
           }
           if (fused) {
-            bnq_chunk(p.bnq, bst, f, row, row < p.M, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+            bnq_chunk(p.bnq, bst, f, row, pix, row < p.M, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
           } else if (row < p.M) {
             float* o = p.out + (size_t)row * p.ldc + c;
             if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {

@@ -286,6 +286,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!ok) break;
       tc_fence_after();
       const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
+      const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
       const uint32_t col0 = n_tile * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
       if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
@@ -309,7 +310,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[j] = __int2float_rn((int)v[j]) * scale;
               if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
             }
-            bnq_chunk(p.bnq, bst, f, row, row < p.M, col0 + c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+            bnq_chunk(p.bnq, bst, f, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
           }
         } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));

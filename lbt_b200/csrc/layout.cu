@@ -21,6 +21,7 @@ struct Im2colParams {
   size_t ld;             // row pitch of out in bytes
   int K;                 // kh*kw*C
   size_t M;              // N*OH*OW rows
+  FastDiv d_kvecs, d_cvecs, d_kw, d_OW, d_OH, d_sh, d_sw;   // vec16 kernel: no integer divisions in the loop
 };
 
 // Source coordinate of output row (n, oh, ow), tap (r, s).  Returns false when the tap reads padding.
@@ -39,22 +40,36 @@ __device__ __forceinline__ bool tap_coord(const Im2colParams& p, int oh, int ow,
   return ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
 }
 
-// C % 16 == 0: one thread moves 16 channels of one tap (one 16-byte load, one 16-byte store).
+// C % 16 == 0: one thread moves 16 channels of one tap (one 16-byte load, one 16-byte store).  total < 2^31.
 __global__ void __launch_bounds__(256) im2col_vec16_kernel(const Im2colParams p) {
-  const int kvecs = p.K >> 4;
-  const int cvecs = p.C >> 4;
-  const size_t total = p.M * (size_t)kvecs;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t m = i / kvecs;
-    const int kv = (int)(i % kvecs);
-    const int tap = kv / cvecs, cv = kv % cvecs;
-    const int r = tap / p.kw, s = tap % p.kw;
-    const int ow = (int)(m % p.OW);
-    const size_t t = m / p.OW;
-    const int oh = (int)(t % p.OH), n = (int)(t / p.OH);
+  const uint32_t kvecs = (uint32_t)p.K >> 4;
+  const uint32_t cvecs = (uint32_t)p.C >> 4;
+  const uint32_t total = (uint32_t)p.M * kvecs;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t m = fastdiv(i, p.d_kvecs);
+    const uint32_t kv = i - m * kvecs;
+    const uint32_t tap = fastdiv(kv, p.d_cvecs), cv = kv - tap * cvecs;
+    const int r = (int)fastdiv(tap, p.d_kw), s = (int)(tap - (uint32_t)r * (uint32_t)p.kw);
+    const uint32_t t = fastdiv(m, p.d_OW);
+    const int ow = (int)(m - t * (uint32_t)p.OW);
+    const int n = (int)fastdiv(t, p.d_OH);
+    const int oh = (int)(t - (uint32_t)n * (uint32_t)p.OH);
     int ih, iw;
+    bool ok;
+    if (!p.transposed) {
+      ih = oh * p.sh - p.pt + r;
+      iw = ow * p.sw - p.pl + s;
+      ok = true;
+    } else {
+      const int th = oh + p.pt - r, tw = ow + p.pl - s;
+      ok = th >= 0 && tw >= 0;
+      ih = ok ? (int)fastdiv((uint32_t)th, p.d_sh) : 0;
+      iw = ok ? (int)fastdiv((uint32_t)tw, p.d_sw) : 0;
+      ok = ok && ih * p.sh == th && iw * p.sw == tw;
+    }
+    ok = ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (tap_coord(p, oh, ow, r, s, ih, iw))
+    if (ok)
       v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.src) +
                                                (((size_t)n * p.H + ih) * p.W + iw) * p.C) + cv);
     *reinterpret_cast<uint4*>(p.out + m * p.ld + ((size_t)kv << 4)) = v;
@@ -161,13 +176,22 @@ extern "C" int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W,
   p.M = (size_t)N * OH * OW;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool vec = segs == 1 && (C % 16 == 0) && (ld % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && p.M * (K / 16) < (1ull << 31);
   const size_t work = vec ? p.M * (K / 16) : p.M * K * segs;
   const size_t blocks = (work + 255) / 256;
   const size_t cap = (size_t)di.sm_count * 16;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   if (vec)
-    im2col_vec16_kernel<<<grid, 256, 0, st>>>(p);
+    {
+      p.d_kvecs = make_fastdiv((uint32_t)p.K >> 4);
+      p.d_cvecs = make_fastdiv((uint32_t)p.C >> 4);
+      p.d_kw = make_fastdiv((uint32_t)p.kw);
+      p.d_OW = make_fastdiv((uint32_t)p.OW);
+      p.d_OH = make_fastdiv((uint32_t)p.OH);
+      p.d_sh = make_fastdiv((uint32_t)p.sh);
+      p.d_sw = make_fastdiv((uint32_t)p.sw);
+        im2col_vec16_kernel<<<grid, 256, 0, st>>>(p);
+    }
   else
     im2col_scalar_kernel<<<grid, 256, 0, st>>>(p);
   return check_launch("lbt_im2col_i8");

@@ -142,9 +142,10 @@ __device__ __forceinline__ int warp_colsum16(const int (&v)[16], int lane) {
 // One 16-channel chunk of one row.  f: the fp32 values the unfused path would have written (acc * 2^e).
 // row_ok / ncol mask the tile tails (masked elements quantise the value 0: no counts, no sums).
 // s_stat: this WARP's private [2][bn] int32 partial sums (bn = tile width); tcol = first column of the chunk inside the tile.
-__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const float (&f)[16], uint32_t row, bool row_ok,
+// pix = row % rows_per_image (the pixel inside its image; computed once per tile by the caller).
+__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const float (&f)[16], uint32_t row, uint32_t pix, bool row_ok,
                                           uint32_t col, uint32_t ncol, uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
-  const uint64_t inner = (uint64_t)(row % b.rows_per_image) * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
+  const uint64_t inner = (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
   int ki[16], kq[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
