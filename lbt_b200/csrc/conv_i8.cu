@@ -34,6 +34,7 @@ __device__ int g_conv_error = 0;
 struct ConvParams {
   uint32_t M, N;                 // output pixels, output channels
   uint32_t OW, OHW;              // output width, OH*OW
+  FastDiv d_OW, d_OHW;           // constant-divisor division for the producer's pixel decomposition
   int lower_w, lower_h;          // base-pixel offset of output (0,0): -pad_left, -pad_top
   int sw, sh;
   uint32_t kw;                   // filter width (tap -> (r, s))
@@ -124,9 +125,11 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         const uint32_t m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
         const uint32_t m0 = m_tile * kBlockM;
-        const uint32_t img = m0 / p.OHW, rem = m0 % p.OHW;
-        const int oh = (int)(rem / p.OW), ow = (int)(rem % p.OW);
+        const uint32_t img = fastdiv(m0, p.d_OHW), rem = m0 - img * p.OHW;
+        const uint32_t ohu = fastdiv(rem, p.d_OW);
+        const int oh = (int)ohu, ow = (int)(rem - ohu * p.OW);
         const int base_w = p.lower_w + ow * p.sw, base_h = p.lower_h + oh * p.sh;
+        uint32_t cc = 0, r = 0, s = 0;   // running decomposition of the k-step: no integer divisions in this loop
         for (uint32_t ks = 0; ks < nstages_k; ++ks) {
           if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_conv_error))) break;
           uint8_t* sa = smem + stage * C::kStageBytes;
@@ -135,14 +138,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t nblk = min(spb, p.ksteps - k0);
           mbar_expect_tx(&full_bar[stage], nblk * (a_block + b_block));
           for (uint32_t j = 0; j < nblk; ++j) {
-            uint32_t kstep = k0 + j;
+            const uint32_t kstep = k0 + j;
             const bool pad = kstep >= p.ksteps_real;        // Cb == 16 pairing pad: B is OOB-zero, A is any tap
-            const uint32_t ka = pad ? 0u : kstep;
-            const uint32_t tap = ka / p.cchunks, cc = ka % p.cchunks;
-            const uint32_t r = tap / p.kw, s = tap % p.kw;
-            tma_load_im2col_4d(&tmA, &full_bar[stage], sa + j * a_block, (int)(cc * p.cb), base_w, base_h, (int)img,
-                               (uint16_t)s, (uint16_t)r);
+            tma_load_im2col_4d(&tmA, &full_bar[stage], sa + j * a_block, pad ? 0 : (int)(cc * p.cb), base_w, base_h, (int)img,
+                               (uint16_t)(pad ? 0u : s), (uint16_t)(pad ? 0u : r));
             tma_load_2d(&tmB, &full_bar[stage], sb + j * b_block, (int)(kstep * p.cb), (int)(n_tile * BN));
+            if (++cc == p.cchunks) {
+              cc = 0;
+              if (++s == p.kw) {
+                s = 0;
+                ++r;
+              }
+            }
           }
           if (++stage == C::kStages) {
             stage = 0;
@@ -298,6 +305,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 struct WgradParams {
   uint32_t Mpix, N;              // output pixels (reduction length), output channels
   uint32_t OW, OHW;
+  FastDiv d_OW, d_OHW;
   int lower_w, lower_h, sw, sh;
   uint32_t kw, cchunks, ksteps;  // filter width, C / Cb, taps * cchunks
   uint32_t cb, mode_a;           // channel chunk bytes of X, log2(cb/16)
@@ -362,21 +370,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t pb0 = ks * p.blocks_per_split, pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
         const uint32_t k0 = m_tile * spb;
         const uint32_t nblk = min(spb, p.ksteps - k0);
+        // the (channel chunk, tap) of each of the item's <= 8 tap-blocks: decomposed once, not per pixel block
+        int jc[8];
+        uint16_t js[8], jr[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+          const uint32_t kstep = k0 + (j < nblk ? j : 0);
+          const uint32_t tap = kstep / p.cchunks;
+          jc[j] = (int)((kstep - tap * p.cchunks) * p.cb);
+          jr[j] = (uint16_t)(tap / p.kw);
+          js[j] = (uint16_t)(tap - (uint32_t)jr[j] * p.kw);
+        }
         for (uint32_t pb = pb0; pb < pb1; ++pb) {
           if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_conv_error))) break;
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kStageA;
           const uint32_t m0 = pb * kBlockM;
-          const uint32_t img = m0 / p.OHW, rem = m0 % p.OHW;
-          const int oh = (int)(rem / p.OW), ow = (int)(rem % p.OW);
+          const uint32_t img = fastdiv(m0, p.d_OHW), rem = m0 - img * p.OHW;
+          const uint32_t ohu = fastdiv(rem, p.d_OW);
+          const int oh = (int)ohu, ow = (int)(rem - ohu * p.OW);
           const int base_w = p.lower_w + ow * p.sw, base_h = p.lower_h + oh * p.sh;
           mbar_expect_tx(&full_bar[stage], nblk * a_block + p.nchunks * b_block);
-          for (uint32_t j = 0; j < nblk; ++j) {
-            const uint32_t kstep = k0 + j;
-            const uint32_t tap = kstep / p.cchunks, cc = kstep % p.cchunks;
-            tma_load_im2col_4d(&tmX, &full_bar[stage], sa + j * a_block, (int)(cc * p.cb), base_w, base_h, (int)img,
-                               (uint16_t)(tap % p.kw), (uint16_t)(tap / p.kw));
-          }
+#pragma unroll
+          for (uint32_t j = 0; j < 8; ++j)
+            if (j < nblk)
+              tma_load_im2col_4d(&tmX, &full_bar[stage], sa + j * a_block, jc[j], base_w, base_h, (int)img, js[j], jr[j]);
           for (uint32_t j = 0; j < p.nchunks; ++j)
             tma_load_2d(&tmG, &full_bar[stage], sb + j * b_block, (int)(n_tile * BN + j * p.cbn), (int)m0);
           if (++stage == C::kStages) {
@@ -565,6 +583,9 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   p.N = (uint32_t)Cout;
   p.OW = (uint32_t)OW;
   p.OHW = (uint32_t)(OH * OW);
+  p.d_OW = make_fastdiv(p.OW);
+  p.d_OHW = make_fastdiv(p.OHW);
+  if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
   p.lower_w = -pad_left;
   p.lower_h = -pad_top;
   p.sw = sw;
@@ -693,6 +714,9 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   p.N = (uint32_t)Cout;
   p.OW = (uint32_t)OW;
   p.OHW = (uint32_t)(OH * OW);
+  p.d_OW = make_fastdiv(p.OW);
+  p.d_OHW = make_fastdiv(p.OHW);
+  if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
   p.lower_w = -pad_left;
   p.lower_h = -pad_top;
   p.sw = sw;
