@@ -72,6 +72,55 @@ class CIFAR10_Model(Model):
         ]
 
 
+class PI_MNIST_Model(Model):
+    """models.py:57-88: 784 -> 1024 -> 1024 -> 10 dense network (input [N, 784])."""
+
+    def get_layers(self):
+        b = self.bits
+        drop = lambda: dfxp.Dropout_q(self.dropout)
+        return [
+            dfxp.Linear_q(b, 784, 1024, **self._kw(name='dense1')), dfxp.ReLU_q(), drop(),
+            dfxp.Linear_q(b, 1024, 1024, **self._kw(name='dense2')), dfxp.ReLU_q(), drop(),
+            dfxp.Linear_q(b, 1024, 10, **self._kw(name='softmax')),
+        ]
+
+
+class MNIST_Model(Model):
+    """models.py:91-152: LeNet-5 on [N, 1, 28, 28]."""
+
+    def get_layers(self):
+        b = self.bits
+        pool = lambda: dfxp.MaxPool_q(2, 2, 'VALID')
+        drop = lambda: dfxp.Dropout_q(self.dropout)
+        return [
+            dfxp.Conv2d_q(b, 1, 6, 5, 1, 'SAME', **self._kw(name='conv1', input_signed=True)), dfxp.ReLU_q(), pool(),
+            dfxp.Conv2d_q(b, 6, 16, 5, 1, 'VALID', **self._kw(name='conv2', input_signed=False)), dfxp.ReLU_q(), pool(),
+            dfxp.Conv2d_q(b, 16, 120, 5, 1, 'VALID', **self._kw(name='conv3', input_signed=False)), dfxp.ReLU_q(),
+            dfxp.Flatten_q(120), drop(),
+            dfxp.Linear_q(b, 120, 84, **self._kw(name='dense1')), dfxp.ReLU_q(), drop(),
+            dfxp.Linear_q(b, 84, 10, **self._kw(name='softmax')),
+        ]
+
+
+class CIFAR10_VGG_Model(Model):
+    """models.py:237-368."""
+
+    def get_layers(self):
+        b = self.bits
+        pool = lambda: dfxp.MaxPool_q(3, 2, 'SAME')
+        drop = lambda: dfxp.Dropout_q(self.dropout)
+        conv = lambda n, ci, co, signed=False: dfxp.Conv2d_q(b, ci, co, 3, 1, 'SAME', **self._kw(name=n, input_signed=signed))
+        return [
+            conv('conv1-1', 3, 128, True), dfxp.ReLU_q(), conv('conv1-2', 128, 128), dfxp.ReLU_q(), pool(),
+            drop(), conv('conv2-1', 128, 256), dfxp.ReLU_q(), conv('conv2-2', 256, 256), dfxp.ReLU_q(), pool(),
+            drop(), conv('conv3-1', 256, 512), dfxp.ReLU_q(), conv('conv3-2', 512, 512), dfxp.ReLU_q(), pool(),
+            dfxp.Flatten_q(512 * 4 * 4),
+            drop(), dfxp.Linear_q(b, 512 * 4 * 4, 1024, **self._kw(name='dense1')), dfxp.ReLU_q(),
+            drop(), dfxp.Linear_q(b, 1024, 1024, **self._kw(name='dense2')), dfxp.ReLU_q(),
+            drop(), dfxp.Linear_q(b, 1024, 10, **self._kw(name='softmax')),
+        ]
+
+
 class CIFAR10_Resnet(Model):
     """models.py:371-450."""
 

@@ -807,6 +807,55 @@ class CIFAR10_Model(Model):
         ]
 
 
+class PI_MNIST_Model(Model):
+    """models.py:57-88: 784 -> 1024 -> 1024 -> 10 dense network (permutation-invariant MNIST)."""
+
+    def get_layers(self):
+        c, b, wd, r, gb = self.ctx, self.bits, self.weight_decay, self.rng, self.grad_bits
+        drop = lambda: Dropout_q(self.dropout, True, getattr(self, 'dropout_uniform', None))
+        return [
+            Dense_q(c, 'dense1', b, 784, 1024, weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(), drop(),
+            Dense_q(c, 'dense2', b, 1024, 1024, weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(), drop(),
+            Dense_q(c, 'softmax', b, 1024, 10, weight_decay=wd, rng=r, grad_bits=gb),
+        ]
+
+
+class MNIST_Model(Model):
+    """models.py:91-152: LeNet-5 (5x5 SAME conv 1->6, 2x2 VALID pool, 5x5 VALID 6->16, pool, 5x5 VALID 16->120, 84, 10)."""
+
+    def get_layers(self):
+        c, b, wd, r, gb = self.ctx, self.bits, self.weight_decay, self.rng, self.grad_bits
+        pool = lambda: MaxPool_q([1, 2, 2, 1], [1, 2, 2, 1], 'VALID')
+        drop = lambda: Dropout_q(self.dropout, True, getattr(self, 'dropout_uniform', None))
+        return [
+            Conv2d_q(c, 'conv1', b, [5, 5, 1, 6], [1, 1, 1, 1], 'SAME', weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(), pool(),
+            Conv2d_q(c, 'conv2', b, [5, 5, 6, 16], [1, 1, 1, 1], 'VALID', weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(), pool(),
+            Conv2d_q(c, 'conv3', b, [5, 5, 16, 120], [1, 1, 1, 1], 'VALID', weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(),
+            Flatten_q(120), drop(),
+            Dense_q(c, 'dense1', b, 120, 84, weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(), drop(),
+            Dense_q(c, 'softmax', b, 84, 10, weight_decay=wd, rng=r, grad_bits=gb),
+        ]
+
+
+class CIFAR10_VGG_Model(Model):
+    """models.py:237-368: 2x(3x3 128) pool 2x(3x3 256) pool 2x(3x3 512) pool, 1024, 1024, 10."""
+
+    def get_layers(self):
+        c, b, wd, r, gb = self.ctx, self.bits, self.weight_decay, self.rng, self.grad_bits
+        pool = lambda: MaxPool_q([1, 3, 3, 1], [1, 2, 2, 1], 'SAME')
+        drop = lambda: Dropout_q(self.dropout, True, getattr(self, 'dropout_uniform', None))
+        conv = lambda n, ci, co: Conv2d_q(c, n, b, [3, 3, ci, co], [1, 1, 1, 1], 'SAME', weight_decay=wd, rng=r, grad_bits=gb)
+        return [
+            conv('conv1-1', 3, 128), ReLU_q(), conv('conv1-2', 128, 128), ReLU_q(), pool(),
+            drop(), conv('conv2-1', 128, 256), ReLU_q(), conv('conv2-2', 256, 256), ReLU_q(), pool(),
+            drop(), conv('conv3-1', 256, 512), ReLU_q(), conv('conv3-2', 512, 512), ReLU_q(), pool(),
+            Flatten_q(512 * 4 * 4),
+            drop(), Dense_q(c, 'dense1', b, 512 * 4 * 4, 1024, weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(),
+            drop(), Dense_q(c, 'dense2', b, 1024, 1024, weight_decay=wd, rng=r, grad_bits=gb), ReLU_q(),
+            drop(), Dense_q(c, 'softmax', b, 1024, 10, weight_decay=wd, rng=r, grad_bits=gb),
+        ]
+
+
 class CIFAR10_Resnet(Model):
     """models.py:371-450."""
 

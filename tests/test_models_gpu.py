@@ -227,6 +227,32 @@ def test_cifar10_model_step_bit_exact_vs_exact_oracle():
     assert list(pm.ranges().values()) == om.ranges()
 
 
+@pytest.mark.parametrize('name,shape', [('PI_MNIST_Model', (16, 784)), ('MNIST_Model', (16, 28, 28, 1)),
+                                        ('CIFAR10_VGG_Model', (4, 32, 32, 3))])
+def test_model_zoo_step_bit_exact_vs_exact_oracle(name, shape):
+    """The rest of models.py: dense-only, LeNet (1-, 6-, 16-channel convolutions: the non-tensor-core-
+    friendly shapes) and VGG (K up to 4608, dense 8192 -> 1024): logits, every gradient and every range bit-exact."""
+    rng = np.random.default_rng(6)
+    om, pm = build_pair_exact(name)
+    tie_dropout(om, pm, rng, None)
+    tr = Trainer(pm, lr=1e-2, momentum=0.9)
+    X = torch.from_numpy((rng.standard_normal(shape) * 0.5).astype(np.float32))
+    y = torch.from_numpy(rng.integers(0, 10, shape[0]))
+    lo = om.forward(X)
+    tr.flat_g.zero_()
+    lp = pm((X.permute(0, 3, 1, 2) if X.dim() == 4 else X).cuda())
+    assert torch.equal(lp.detach().cpu(), lo), float((lp.detach().cpu() - lo).abs().max())
+    om.loss, dlogits = om.loss_and_grad(y)
+    g = dlogits
+    for layer in reversed(om.layers):
+        g = layer.backward(g, True)
+    lp.backward(dlogits.cuda())
+    for (go, vo), p in zip(om.grads_and_vars(), tr.params):
+        assert torch.equal(p.grad.cpu(), go), 'gradient of a %s variable differs' % (tuple(vo.shape),)
+    pm.runtime.update_ranges()
+    assert list(pm.ranges().values()) == om.ranges()
+
+
 @pytest.mark.parametrize('name', ['CIFAR10_Model', 'CIFAR10_Resnet20'])
 def test_batched_parameter_launches_are_bit_identical(name):
     """lbt_param_prep + lbt_finalize_multi + the int64 arena (one launch each per step) give exactly the
@@ -244,3 +270,18 @@ def test_batched_parameter_launches_are_bit_identical(name):
     assert results[0][0] == results[1][0]
     assert torch.equal(results[0][1], results[1][1])
     assert results[0][2] == results[1][2]
+
+
+def test_custom_lenet_from_custom_py_trains():
+    """custom.py's CUSTOM_MNIST against the real layers: forward, backward and one SGD step run and stay finite."""
+    from lbt_b200.custom import custom
+    torch.manual_seed(0)
+    m = custom(8).cuda()
+    x = (torch.randn(8, 1, 28, 28, device='cuda') * 0.5).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (8,), device='cuda')
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    assert logits.shape == (8, 10) and bool(torch.isfinite(loss))
+    for p in m.parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all())
