@@ -414,6 +414,21 @@ int lbt_maxpool_fwd(const float* x, int N, int H, int W, int C, int k, int s, in
 int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H, int W, int C, int k, int s, int pad_top,
                     int pad_left, int OH, int OW, float* dx, void* stream);
 
+/*
+ * tf.nn.avg_pool 'VALID' on an NHWC fp32 tensor (`AvgPool_q`, dynamic_fixed_point.py:1009-1022): window sums in
+ * (row, column) order divided by k*k, and the gradient (each input pixel gathers g / (k*k) from the windows covering it).
+ */
+int lbt_avgpool_fwd(const float* x, int N, int H, int W, int C, int k, int s, int OH, int OW, float* out, void* stream);
+int lbt_avgpool_bwd(const float* g, int N, int H, int W, int C, int k, int s, int OH, int OW, float* dx, void* stream);
+
+/*
+ * Mean sparse softmax cross-entropy (models.py:30-32): probs[B,C] = softmax(logits), *loss = mean_b -log probs[b,label_b];
+ * backward: dlogits = (probs - onehot(labels)) * (*grad_loss) / B  (grad_loss NULL = 1).
+ */
+int lbt_softmax_xent_fwd(const float* logits, const int64_t* labels, int B, int C, float* probs, float* loss, void* stream);
+int lbt_softmax_xent_bwd(const float* probs, const int64_t* labels, const float* grad_loss, int B, int C, float* dlogits,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

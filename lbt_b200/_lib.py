@@ -43,6 +43,10 @@ SIGNATURES = {
     'lbt_bn_bwd_fused': (c_int, [c_void_p, c_void_p]),
     'lbt_maxpool_fwd': (c_int, [c_void_p] + [c_int] * 10 + [c_void_p, c_void_p, c_void_p]),
     'lbt_maxpool_bwd': (c_int, [c_void_p, c_void_p] + [c_int] * 10 + [c_void_p, c_void_p]),
+    'lbt_avgpool_fwd': (c_int, [c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
+    'lbt_avgpool_bwd': (c_int, [c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
+    'lbt_softmax_xent_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'lbt_softmax_xent_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
                                  c_void_p]),
     'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),

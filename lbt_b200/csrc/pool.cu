@@ -140,3 +140,156 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
                                                                                                                   total);
   return check_launch("lbt_maxpool_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// tf.nn.avg_pool 'VALID' on NHWC fp32 (`AvgPool_q`, dynamic_fixed_point.py:1009-1022) and its gradient, and the mean
+// sparse softmax cross-entropy of models.py:30-32 with its gradient w.r.t. the logits.  Small kernels that keep the last
+// few operations of a training step inside the library instead of a handful of framework launches.
+// ------------------------------------------------------------------------------------------------------------------
+namespace lbt {
+namespace {
+
+__global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                const PoolParams p, size_t total) {
+  const float inv = 1.0f;  // the window sum is DIVIDED by k*k below (same arithmetic as the oracle's restatement)
+  (void)inv;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
+    const uint32_t c = (uint32_t)i - pix * p.c4;
+    uint32_t t = fastdiv(pix, p.d_OW);
+    const int ow = (int)(pix - t * (uint32_t)p.OW);
+    const int n = (int)fastdiv(t, p.d_OH);
+    const int oh = (int)(t - (uint32_t)n * (uint32_t)p.OH);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < p.k; ++r)
+      for (int q = 0; q < p.k; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * p.H + oh * p.s + r) * p.W + ow * p.s + q) * p.C) + c);
+        acc.x = __fadd_rn(acc.x, v.x);
+        acc.y = __fadd_rn(acc.y, v.y);
+        acc.z = __fadd_rn(acc.z, v.z);
+        acc.w = __fadd_rn(acc.w, v.w);
+      }
+    const float d = (float)(p.k * p.k);
+    reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, const PoolParams p,
+                                                                size_t total) {
+  const float d = (float)(p.k * p.k);
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
+    const uint32_t c = (uint32_t)i - pix * p.c4;
+    uint32_t t = fastdiv(pix, p.d_W);
+    const int iw = (int)(pix - t * (uint32_t)p.W);
+    const int n = (int)fastdiv(t, p.d_H);
+    const int ih = (int)(t - (uint32_t)n * (uint32_t)p.H);
+    const int oh_lo = ih - p.k + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(ih - p.k + p.s), p.d_s);
+    const int ow_lo = iw - p.k + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(iw - p.k + p.s), p.d_s);
+    const int oh_hi = min(p.OH - 1, (int)fastdiv((uint32_t)ih, p.d_s)), ow_hi = min(p.OW - 1, (int)fastdiv((uint32_t)iw, p.d_s));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh)
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c));
+        acc.x = __fadd_rn(acc.x, __fdiv_rn(gv.x, d));
+        acc.y = __fadd_rn(acc.y, __fdiv_rn(gv.y, d));
+        acc.z = __fadd_rn(acc.z, __fdiv_rn(gv.z, d));
+        acc.w = __fadd_rn(acc.w, __fdiv_rn(gv.w, d));
+      }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+// ONE CTA of 32 warps (the logits are a few hundred KB at most): warp w takes rows w, w+32, ...; p = softmax(logits) is
+// kept for the backward; the mean is summed in a FIXED order (per warp, then over the 32 warps) so the loss is
+// bit-reproducible from run to run.
+__global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C,
+                                                        float* __restrict__ probs, float* __restrict__ loss) {
+  __shared__ float s_part[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float part = 0.f;
+  for (int row = warp; row < B; row += 32) {
+    const float* x = logits + (size_t)row * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(x[c] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float ls = logf(s);
+    for (int c = lane; c < C; c += 32) probs[(size_t)row * C + c] = expf(x[c] - m - ls);
+    const long long y = labels[row];
+    if (y >= 0 && y < C) part += -(x[y] - m - ls);
+  }
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += s_part[w];
+    *loss = t / (float)B;
+  }
+}
+
+__global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__ probs, const long long* __restrict__ labels,
+                                                       const float* __restrict__ gout, int B, int C, float* __restrict__ dlogits) {
+  const float scale = (gout ? *gout : 1.0f) / (float)B;
+  const size_t total = (size_t)B * C;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int row = (int)(i / C), c = (int)(i % C);
+    dlogits[i] = (probs[i] - (labels[row] == c ? 1.0f : 0.0f)) * scale;
+  }
+}
+
+}  // namespace
+}  // namespace lbt
+
+extern "C" int lbt_avgpool_fwd(const float* x, int N, int H, int W, int C, int k, int s, int OH, int OW, float* out, void* stream) {
+  if (!x || !out) return LBT_EINVAL;
+  PoolParams p{};
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  int rc = check(p);
+  if (rc) return rc;
+  if ((OH - 1) * s + k > H || (OW - 1) * s + k > W) return LBT_EINVAL;   // 'VALID': every window inside the input
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const size_t total = (size_t)N * OH * OW * p.c4;
+  if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  fill_divs(p);
+  const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
+  avgpool_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, p, total);
+  return check_launch("lbt_avgpool_fwd");
+}
+
+extern "C" int lbt_avgpool_bwd(const float* g, int N, int H, int W, int C, int k, int s, int OH, int OW, float* dx, void* stream) {
+  if (!g || !dx) return LBT_EINVAL;
+  PoolParams p{};
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  int rc = check(p);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const size_t total = (size_t)N * H * W * p.c4;
+  if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  fill_divs(p);
+  const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
+  avgpool_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, dx, p, total);
+  return check_launch("lbt_avgpool_bwd");
+}
+
+extern "C" int lbt_softmax_xent_fwd(const float* logits, const int64_t* labels, int B, int C, float* probs, float* loss, void* stream) {
+  if (!logits || !labels || !probs || !loss || B <= 0 || C <= 0) return LBT_EINVAL;
+  LBT_REQUIRE_ARCH();
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  xent_fwd_kernel<<<1, 1024, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
+  return check_launch("lbt_softmax_xent_fwd");
+}
+
+extern "C" int lbt_softmax_xent_bwd(const float* probs, const int64_t* labels, const float* grad_loss, int B, int C, float* dlogits,
+                                    void* stream) {
+  if (!probs || !labels || !dlogits || B <= 0 || C <= 0) return LBT_EINVAL;
+  LBT_REQUIRE_ARCH();
+  const size_t total = (size_t)B * C, blocks = (total + 255) / 256, cap = (size_t)device_info().sm_count * 8;
+  xent_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      probs, reinterpret_cast<const long long*>(labels), grad_loss, B, C, dlogits);
+  return check_launch("lbt_softmax_xent_bwd");
+}

@@ -1325,6 +1325,30 @@ class MaxPool_q(nn.Module):
         return F.max_pool2d(x, self.k, self.s)
 
 
+class _AvgPoolFn(torch.autograd.Function):
+    """lbt_avgpool_fwd / lbt_avgpool_bwd on the NHWC memory of a channels_last tensor ('VALID' windows)."""
+
+    @staticmethod
+    def forward(ctx, x, k, s):
+        x_ = _to_mem(x)
+        N, H, W, C = x_.shape
+        OH, OW = (H - k) // s + 1, (W - k) // s + 1
+        out = torch.empty(N, OH, OW, C, dtype=torch.float32, device=x.device)
+        _lib.call('lbt_avgpool_fwd', _lib.ptr(x_), N, H, W, C, k, s, OH, OW, _lib.ptr(out), _lib.stream(),
+                  meta=dict(bytes=(x_.numel() + out.numel()) * 4))
+        ctx.geom = (N, H, W, C, k, s, OH, OW)
+        return _from_mem(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, C, k, s, OH, OW = ctx.geom
+        g_ = _to_mem(g)
+        dx = torch.empty(N, H, W, C, dtype=torch.float32, device=g.device)
+        _lib.call('lbt_avgpool_bwd', _lib.ptr(g_), N, H, W, C, k, s, OH, OW, _lib.ptr(dx), _lib.stream(),
+                  meta=dict(bytes=(g_.numel() + dx.numel()) * 4))
+        return _from_mem(dx), None, None
+
+
 class AvgPool_q(nn.Module):
     """tf.nn.avg_pool 'VALID' (dfxp:1009-1022)."""
 
@@ -1333,7 +1357,39 @@ class AvgPool_q(nn.Module):
         self.k, self.s = kernel_size, stride
 
     def forward(self, x):
+        if x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype == torch.float32 and self.k <= 15:
+            return _AvgPoolFn.apply(x, self.k, self.s)
         return F.avg_pool2d(x, self.k, self.s)
+
+
+class _XentFn(torch.autograd.Function):
+    """Mean sparse softmax cross-entropy (models.py:30-32) and its gradient: lbt_softmax_xent_fwd / _bwd."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = logits.contiguous()
+        B, C = logits.shape
+        probs = torch.empty_like(logits)
+        loss = torch.empty((), dtype=torch.float32, device=logits.device)
+        _lib.call('lbt_softmax_xent_fwd', _lib.ptr(logits), _lib.ptr(labels), B, C, _lib.ptr(probs), _lib.ptr(loss), _lib.stream())
+        ctx.save_for_backward(probs, labels)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        probs, labels = ctx.saved_tensors
+        B, C = probs.shape
+        d = torch.empty_like(probs)
+        _lib.call('lbt_softmax_xent_bwd', _lib.ptr(probs), _lib.ptr(labels), _lib.ptr(gout.contiguous()), B, C, _lib.ptr(d),
+                  _lib.stream())
+        return d, None
+
+
+def softmax_cross_entropy(logits, labels):
+    """reduce_mean(sparse_softmax_cross_entropy_with_logits) of models.py:30-32."""
+    if logits.is_cuda and logits.dim() == 2 and logits.dtype == torch.float32 and labels.dtype == torch.int64:
+        return _XentFn.apply(logits, labels.contiguous())
+    return F.cross_entropy(logits, labels, reduction='mean')
 
 
 class Dropout_q(nn.Module):

@@ -32,7 +32,7 @@ class Model(nn.Module):
 
     @staticmethod
     def loss(logits, labels):
-        return F.cross_entropy(logits, labels, reduction='mean')                               # models.py:30-32
+        return dfxp.softmax_cross_entropy(logits, labels)                                      # models.py:30-32
 
     def info(self):
         return '\n'.join(getattr(l, 'info', lambda: type(l).__name__)() for l in self.layers)

@@ -112,3 +112,32 @@ def test_maxpool_kernels_equal_torch(N, C, H, W, k, s, padding):
     ya.backward(go.cuda())
     yb.backward(go)
     assert torch.equal(xa.grad.cpu(), xb.grad)
+
+
+def test_avgpool_and_xent_kernels_match_torch():
+    """lbt_avgpool_* bit-identical to torch's avg_pool2d (the oracle's restatement of tf.nn.avg_pool); the softmax
+    cross-entropy within fp32 round-off of torch's (different exp/log implementations)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    for (N, C, H, k, s) in [(5, 64, 8, 8, 1), (3, 16, 9, 3, 2), (2, 8, 7, 2, 2)]:
+        x = torch.randn(N, C, H, H, generator=g)
+        xa = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        ya = D.AvgPool_q(k, s)(xa)
+        xb = x.clone().requires_grad_(True)
+        yb = F.avg_pool2d(xb, k, s)
+        assert torch.equal(ya.cpu(), yb)
+        go = torch.randn(yb.shape, generator=g)
+        ya.backward(go.cuda())
+        yb.backward(go)
+        assert torch.equal(xa.grad.cpu(), xb.grad)
+    for (B, C) in [(256, 10), (7, 1000), (1, 3)]:
+        z = torch.randn(B, C, generator=g) * 3
+        y = torch.randint(0, C, (B,), generator=g)
+        za = z.cuda().requires_grad_(True)
+        la = D.softmax_cross_entropy(za, y.cuda())
+        zb = z.clone().requires_grad_(True)
+        lb = F.cross_entropy(zb, y)
+        la.backward()
+        lb.backward()
+        assert abs(float(la) - float(lb)) <= 1e-6 * max(1.0, abs(float(lb)))
+        assert float((za.grad.cpu() - zb.grad).abs().max()) <= 1e-7
