@@ -429,6 +429,16 @@ int lbt_softmax_xent_fwd(const float* logits, const int64_t* labels, int B, int 
 int lbt_softmax_xent_bwd(const float* probs, const int64_t* labels, const float* grad_loss, int B, int C, float* dlogits,
                          void* stream);
 
+/*
+ * ReLU_q (dynamic_fixed_point.py:983-990): g == NULL: out = max(0, x); g != NULL: out = g where x > 0, else 0 (x may be
+ * the forward input or output).  Dropout_q (:1025-1040): out = x / keep_prob * floor(keep_prob + u), u an explicit
+ * uniform tensor [n] or (NULL) the Philox stream of lbt_noise_fill with (seed, offset + (*dev_step << 32)); the gradient is
+ * the same call on g (the mask is recomputed, not stored).
+ */
+int lbt_relu(const float* x, const float* g, float* out, size_t n, void* stream);
+int lbt_dropout(const float* x, const float* u, float keep_prob, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                float* out, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

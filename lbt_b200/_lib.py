@@ -47,6 +47,8 @@ SIGNATURES = {
     'lbt_avgpool_bwd': (c_int, [c_void_p] + [c_int] * 8 + [c_void_p, c_void_p]),
     'lbt_softmax_xent_fwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'lbt_softmax_xent_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'lbt_relu': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'lbt_dropout': (c_int, [c_void_p, c_void_p, c_float, c_u64, c_u64, c_void_p, c_void_p, c_size_t, c_void_p]),
     'lbt_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_float,
                                  c_void_p]),
     'lbt_finalize_multi': (c_int, [c_void_p, c_size_t, c_u64, c_void_p]),

@@ -293,3 +293,77 @@ extern "C" int lbt_softmax_xent_bwd(const float* probs, const int64_t* labels, c
       probs, reinterpret_cast<const long long*>(labels), grad_loss, B, C, dlogits);
   return check_launch("lbt_softmax_xent_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// ReLU_q (tf.maximum(0.0, X), dynamic_fixed_point.py:983-990) and Dropout_q (tf.nn.dropout(x, keep) = x / keep *
+// floor(keep + u), :1025-1040) for the models without batch-norm (where they are not folded into a BN kernel).  The
+// dropout uniforms are an explicit tensor (parity tests) or the Philox stream (seed, offset + (*dev_step << 32)); the
+// backward pass recomputes the same mask from the same stream, so no mask tensor is stored.
+// ------------------------------------------------------------------------------------------------------------------
+namespace lbt {
+namespace {
+
+__global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out,
+                                                   size_t n4, size_t n) {
+  // g == NULL: out = max(0, x);  else: out = g where x > 0 (x = the forward OUTPUT or input: same sign test), else 0
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 o;
+    if (g) {
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+      o = make_float4(v.x > 0.f ? gv.x : 0.f, v.y > 0.f ? gv.y : 0.f, v.z > 0.f ? gv.z : 0.f, v.w > 0.f ? gv.w : 0.f);
+    } else {
+      o = make_float4(fmaxf(0.f, v.x), fmaxf(0.f, v.y), fmaxf(0.f, v.z), fmaxf(0.f, v.w));
+    }
+    reinterpret_cast<float4*>(out)[i] = o;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+    out[i] = g ? (x[i] > 0.f ? g[i] : 0.f) : fmaxf(0.f, x[i]);
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, const float* __restrict__ u, float keep, uint64_t seed,
+                                                      uint64_t offset, const uint64_t* dev_step, float* __restrict__ out, size_t n) {
+  const uint64_t off = offset + (dev_step ? ((*dev_step) << 32) : 0ull);
+  const size_t ng = (n + 3) / 4;
+  for (size_t gidx = (size_t)blockIdx.x * 256 + threadIdx.x; gidx < ng; gidx += (size_t)gridDim.x * 256) {
+    float4 r;
+    const size_t e = 4 * gidx;
+    if (u) {
+      r.x = e + 0 < n ? u[e + 0] : 0.f;
+      r.y = e + 1 < n ? u[e + 1] : 0.f;
+      r.z = e + 2 < n ? u[e + 2] : 0.f;
+      r.w = e + 3 < n ? u[e + 3] : 0.f;
+    } else {
+      r = philox_noise4(gidx, seed, off);
+    }
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e + j < n) out[e + j] = __fmul_rn(__fdiv_rn(x[e + j], keep), floorf(__fadd_rn(keep, rr[j])));
+  }
+}
+
+}  // namespace
+}  // namespace lbt
+
+extern "C" int lbt_relu(const float* x, const float* g, float* out, size_t n, void* stream) {
+  if (!x || !out) return LBT_EINVAL;
+  if (n == 0) return LBT_OK;
+  LBT_REQUIRE_ARCH();
+  const bool al = !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | (g ? reinterpret_cast<uintptr_t>(g) : 0)) & 15);
+  const size_t n4 = al ? n / 4 : 0;
+  const size_t blocks = ((n4 ? n4 : n) + 255) / 256, cap = (size_t)device_info().sm_count * 8;
+  relu_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, g, out, n4, n);
+  return check_launch("lbt_relu");
+}
+
+extern "C" int lbt_dropout(const float* x, const float* u, float keep_prob, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
+                           float* out, size_t n, void* stream) {
+  if (!x || !out || !(keep_prob > 0.0f)) return LBT_EINVAL;
+  if (n == 0) return LBT_OK;
+  LBT_REQUIRE_ARCH();
+  const size_t blocks = ((n + 3) / 4 + 255) / 256, cap = (size_t)device_info().sm_count * 8;
+  dropout_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, u, keep_prob, seed, offset,
+                                                                                                       dev_step, out, n);
+  return check_launch("lbt_dropout");
+}

@@ -1272,7 +1272,34 @@ BatchNorm_q = BatchNorm2d_q
 # ------------------------------------------------------------------------------------------------
 
 
-class ReLU_q(nn.ReLU):
+class _ReLUFn(torch.autograd.Function):
+    """lbt_relu: tf.maximum(0.0, X) and its gradient (to X only where X > 0)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _mem_contig(x)
+        y = torch.empty_like(x)
+        _lib.call('lbt_relu', _lib.ptr(x), None, _lib.ptr(y), x.numel(), _lib.stream(), meta=dict(bytes=x.numel() * 8))
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _mem_contig(g)              # same memory order as y (channels_last for 4-D)
+        dx = torch.empty_like(y)
+        _lib.call('lbt_relu', _lib.ptr(y), _lib.ptr(g), _lib.ptr(dx), y.numel(), _lib.stream(), meta=dict(bytes=y.numel() * 12))
+        return dx
+
+
+class ReLU_q(nn.Module):
+    """dfxp:983-990."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32:
+            return _ReLUFn.apply(x)
+        return F.relu(x)
+
     def info(self):
         return 'ReLU'
 
@@ -1392,17 +1419,56 @@ def softmax_cross_entropy(logits, labels):
     return F.cross_entropy(logits, labels, reduction='mean')
 
 
+class _DropoutFn(torch.autograd.Function):
+    """lbt_dropout: x / keep * floor(keep + u); the backward recomputes the mask from the same uniforms / Philox stream."""
+
+    @staticmethod
+    def forward(ctx, x, keep, u, seed, offset, dev_step):
+        x = _mem_contig(x)
+        y = torch.empty_like(x)
+        _lib.call('lbt_dropout', _lib.ptr(x), _lib.ptr(u), float(keep), int(seed), int(offset), _lib.ptr(dev_step), _lib.ptr(y),
+                  x.numel(), _lib.stream(), meta=dict(bytes=x.numel() * 8))
+        ctx.args = (keep, seed, offset, dev_step)
+        ctx.fmt4 = x.dim() == 4
+        ctx.save_for_backward(u)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        keep, seed, offset, dev_step = ctx.args
+        g = _mem_contig(g)
+        dx = torch.empty_like(g)
+        _lib.call('lbt_dropout', _lib.ptr(g), _lib.ptr(u), float(keep), int(seed), int(offset), _lib.ptr(dev_step), _lib.ptr(dx),
+                  g.numel(), _lib.stream(), meta=dict(bytes=g.numel() * 8))
+        return dx, None, None, None, None, None
+
+
 class Dropout_q(nn.Module):
     """tf.nn.dropout(x, keep_prob) = x / keep * floor(keep + u) (dfxp:1025-1040); keep_prob is KEEP."""
 
-    def __init__(self, keep_prob):
+    _next_id = [0]
+
+    def __init__(self, keep_prob, runtime=None):
         super().__init__()
         self.keep_prob = keep_prob
-        self.uniform_fn = None      # tests: callable(shape, device) -> the reference's uniform tensor
+        self.uniform_fn = None      # tests: callable(x) -> the reference's uniform tensor (memory order of x)
+        self.runtime = runtime
+        self.did = Dropout_q._next_id[0]
+        Dropout_q._next_id[0] += 1
 
     def forward(self, x):
         if not self.training or self.keep_prob >= 1.0:
             return x
+        if x.is_cuda and x.dtype == torch.float32:
+            rt = self.runtime
+            if self.uniform_fn is not None:
+                u = _mem_contig(self.uniform_fn(x).to(torch.float32))
+                return _DropoutFn.apply(x, self.keep_prob, u, 0, 0, None)
+            seed = rt.seed if rt is not None else 0
+            # Philox stream disjoint from the quantisers': ids count down from 2^31
+            return _DropoutFn.apply(x, self.keep_prob, None, seed, Q.make_offset(0x7fffffff - self.did, 0),
+                                    rt.dev_step if rt is not None else None)
         u = self.uniform_fn(x) if self.uniform_fn is not None else torch.rand_like(x)
         return x / self.keep_prob * torch.floor(self.keep_prob + u)
 

@@ -53,7 +53,7 @@ class CIFAR10_Model(Model):
     def get_layers(self):
         b = self.bits
         pool = lambda: dfxp.MaxPool_q(3, 2, 'SAME')
-        drop = lambda: dfxp.Dropout_q(self.dropout)
+        drop = lambda: dfxp.Dropout_q(self.dropout, runtime=self.runtime)
         return [
             dfxp.Conv2d_q(b, 3, 64, 5, 1, 'SAME', **self._kw(name='conv1', input_signed=True)),
             dfxp.ReLU_q(), pool(),
@@ -77,7 +77,7 @@ class PI_MNIST_Model(Model):
 
     def get_layers(self):
         b = self.bits
-        drop = lambda: dfxp.Dropout_q(self.dropout)
+        drop = lambda: dfxp.Dropout_q(self.dropout, runtime=self.runtime)
         return [
             dfxp.Linear_q(b, 784, 1024, **self._kw(name='dense1')), dfxp.ReLU_q(), drop(),
             dfxp.Linear_q(b, 1024, 1024, **self._kw(name='dense2')), dfxp.ReLU_q(), drop(),
@@ -91,7 +91,7 @@ class MNIST_Model(Model):
     def get_layers(self):
         b = self.bits
         pool = lambda: dfxp.MaxPool_q(2, 2, 'VALID')
-        drop = lambda: dfxp.Dropout_q(self.dropout)
+        drop = lambda: dfxp.Dropout_q(self.dropout, runtime=self.runtime)
         return [
             dfxp.Conv2d_q(b, 1, 6, 5, 1, 'SAME', **self._kw(name='conv1', input_signed=True)), dfxp.ReLU_q(), pool(),
             dfxp.Conv2d_q(b, 6, 16, 5, 1, 'VALID', **self._kw(name='conv2', input_signed=False)), dfxp.ReLU_q(), pool(),
@@ -108,7 +108,7 @@ class CIFAR10_VGG_Model(Model):
     def get_layers(self):
         b = self.bits
         pool = lambda: dfxp.MaxPool_q(3, 2, 'SAME')
-        drop = lambda: dfxp.Dropout_q(self.dropout)
+        drop = lambda: dfxp.Dropout_q(self.dropout, runtime=self.runtime)
         conv = lambda n, ci, co, signed=False: dfxp.Conv2d_q(b, ci, co, 3, 1, 'SAME', **self._kw(name=n, input_signed=signed))
         return [
             conv('conv1-1', 3, 128, True), dfxp.ReLU_q(), conv('conv1-2', 128, 128), dfxp.ReLU_q(), pool(),
