@@ -163,11 +163,14 @@ enum lbt_gemm_epilogue {
  *         statistics: Normalization_q's input quantiser + batch moments (dfxp:584-588) folded into the GEMM
  *         that produces its input.  The noise index of element (m, n) is (m % rows_per_image) * N + n.
  *         out_f32 may be NULL.
+ *   addend != NULL (LBT_EPI_F32 without q_out): out_f32 = result + addend[m*ldc + n] — the other branch of a gradient
+ *         sum (residual shortcut) folded into the epilogue instead of a separate add over the tensor.
  */
 int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M,
                 size_t N, size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const,
                 const float* bias, float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits,
-                const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, size_t rows_per_image, void* stream);
+                const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, size_t rows_per_image, const float* addend,
+                void* stream);
 
 /*
  * out[i] = fp32(acc64[i]) * 2^(exp_const + *ibA + *ibB) (+ add_scale * add[i]) — the wgrad tail
@@ -202,12 +205,13 @@ int lbt_im2col_i8(const void* src, int src_kind, int N, int H, int W, int C, int
  *   (k = (r*kw + s)*C + c, row pitch ldw bytes);  out[N*OH*OW, Cout] fp32 (row pitch ldc floats):
  *   out = fp32(acc) * 2^(exp_const + *ib_src + *ib_w) (+ bias[co]).  kh*kw*C <= 65536.
  *   q_out != NULL (Cout % 4 == 0): fused re-quantising epilogue as in lbt_gemm_i8 — k_out[N*OH*OW, Cout] s8,
- *   sums[2*Cout], rows_per_image = OH*OW; `out` may then be NULL.
+ *   sums[2*Cout], rows_per_image = OH*OW; `out` may then be NULL.  addend: as in lbt_gemm_i8 (fp32 [M, ldc]).
  */
 int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind,
                       size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
                       int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
-                      float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, void* stream);
+                      float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend,
+                      void* stream);
 
 /*
  * Input gradient of a convolution of ANY stride as an implicit GEMM (no im2col matrix in HBM), the transposed
@@ -218,7 +222,8 @@ int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C,
  */
 int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* wp, int w_kind,
                       size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
-                      const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, void* stream);
+                      const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, const float* addend,
+                      void* stream);
 
 /*
  * Implicit-GEMM weight gradient: acc64[(r*kw+s)*C + c, co] += alpha * sum over output pixels m of

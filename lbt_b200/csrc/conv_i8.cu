@@ -49,6 +49,7 @@ struct ConvParams {
   const int32_t* ibB;
   int exp_const;
   const float* bias;
+  const float* addend;           // optional fp32 [M, ldc] added to the fp32 result (F32 epilogue only)
   float* out;
   size_t ldc;
   uint32_t idesc;
@@ -262,6 +263,25 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int j = 0; j < 16; ++j) {
             f[j] = __int2float_rn((int)v[j]) * scale;
             if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+          }
+          if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
+            const float* ad = p.addend + (o - p.out);
+            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(ad) & 15u) == 0)) {
+              float4 a4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) a4[j] = __ldcs(reinterpret_cast<const float4*>(ad) + j);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[4 * j + 0] = __fadd_rn(f[4 * j + 0], a4[j].x);
+                f[4 * j + 1] = __fadd_rn(f[4 * j + 1], a4[j].y);
+                f[4 * j + 2] = __fadd_rn(f[4 * j + 2], a4[j].z);
+                f[4 * j + 3] = __fadd_rn(f[4 * j + 3], a4[j].w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(ad + j));
+            }
           }
           if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
 #pragma unroll
@@ -534,7 +554,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
                                  size_t ldw, int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH,
                                  int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
                                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
-                                 void* stream) {
+                                 const float* addend, void* stream) {
   if (!src || !wp) return LBT_EINVAL;
   if (q_out) {
     if (!k_out || !sums || !q_out->ib) return LBT_EINVAL;
@@ -552,7 +572,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
     return conv_ldg_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, 0, ib_src,
-                        ib_w, exp_const, bias, out, ldc, q_out, k_out, sums, stream);
+                        ib_w, exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream);
   }
   const uint32_t cb = C >= 128 ? 128u : (uint32_t)C;
   if (cb != 16 && cb != 32 && cb != 64 && cb != 128) return LBT_EUNSUPPORTED;
@@ -604,6 +624,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   p.ibB = ib_w;
   p.exp_const = exp_const;
   p.bias = bias;
+  p.addend = q_out ? nullptr : addend;
   p.out = out;
   p.ldc = ldc;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);

@@ -63,6 +63,7 @@ struct LdgParams {
   const int32_t* ibB;
   int exp_const;
   const float* bias;
+  const float* addend;           // optional fp32 [M, ldc] added to the fp32 result (F32 epilogue only)
   float* out;
   size_t ldc;
   uint32_t idesc;
@@ -336,7 +337,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
             bnq_chunk(p.bnq, bst, f, row, pix, row < p.M, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
           } else if (row < p.M) {
             float* o = p.out + (size_t)row * p.ldc + c;
-            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+            if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
+            const float* ad = p.addend + (o - p.out);
+            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(ad) & 15u) == 0)) {
+              float4 a4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) a4[j] = __ldcs(reinterpret_cast<const float4*>(ad) + j);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[4 * j + 0] = __fadd_rn(f[4 * j + 0], a4[j].x);
+                f[4 * j + 1] = __fadd_rn(f[4 * j + 1], a4[j].y);
+                f[4 * j + 2] = __fadd_rn(f[4 * j + 2], a4[j].z);
+                f[4 * j + 3] = __fadd_rn(f[4 * j + 3], a4[j].w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(ad + j));
+            }
+          }
+          if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
@@ -685,7 +705,7 @@ int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C
 int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                  int kh, int kw, int sh, int sw, int pt, int pl, int OH, int OW, int gather, const int32_t* ibA,
                  const int32_t* ibB, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
-                 int8_t* k_out, int64_t* sums, void* stream) {
+                 int8_t* k_out, int64_t* sums, const float* addend, void* stream) {
   const DeviceInfo& di = device_info();
   const int bn = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128));
   if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -742,6 +762,7 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   p.ibB = ibB;
   p.exp_const = exp_const;
   p.bias = bias;
+  p.addend = q_out ? nullptr : addend;
   p.out = out;
   p.ldc = ldc;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
@@ -777,7 +798,8 @@ using namespace lbt;
 
 extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* wp, int w_kind, size_t ldw,
                                  int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
-                                 const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, void* stream) {
+                                 const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, const float* addend,
+                                 void* stream) {
   if (!g || !wp || !dx) return LBT_EINVAL;
   if ((g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
@@ -788,7 +810,7 @@ extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int O
   LBT_REQUIRE_ARCH();
   // rows = input pixels (n, h, w); gathered tensor = g[N, OH, OW, Cout]; output channels = Cin
   return conv_ldg_run(g, g_kind, N, OH, OW, Cout, wp, w_kind, ldw, Cin, kh, kw, sh, sw, pad_top, pad_left, H, W, 1, ib_g, ib_w,
-                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, stream);
+                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, addend, stream);
 }
 
 // Test / bench knob (not in lbt.h): 0 routes every convolution through the TMA-im2col kernel, 1 (default) lets the

@@ -40,6 +40,7 @@ struct GemmParams {
   const int32_t* ibB;
   int exp_const;
   const float* bias;
+  const float* addend;           // optional fp32 [M, ldc] added to the fp32 result (F32 epilogue only)
   float* out;
   size_t ldc;
   long long* acc64;
@@ -322,7 +323,26 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[j] = __int2float_rn((int)v[j]) * scale;
               if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
             }
-            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+            if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
+            const float* ad = p.addend + (o - p.out);
+            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(ad) & 15u) == 0)) {
+              float4 a4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) a4[j] = __ldcs(reinterpret_cast<const float4*>(ad) + j);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[4 * j + 0] = __fadd_rn(f[4 * j + 0], a4[j].x);
+                f[4 * j + 1] = __fadd_rn(f[4 * j + 1], a4[j].y);
+                f[4 * j + 2] = __fadd_rn(f[4 * j + 2], a4[j].z);
+                f[4 * j + 3] = __fadd_rn(f[4 * j + 3], a4[j].w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(ad + j));
+            }
+          }
+          if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
@@ -435,7 +455,7 @@ using namespace lbt;
 extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind, size_t ldb, size_t M, size_t N,
                            size_t K, int epilogue, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
                            float* out_f32, int64_t* acc64, size_t ldc, int alpha, int k_splits, const lbt_qsite* q_out,
-                           int8_t* k_out, int64_t* sums, size_t rows_per_image, void* stream) {
+                           int8_t* k_out, int64_t* sums, size_t rows_per_image, const float* addend, void* stream) {
   if (!A || !B) return LBT_EINVAL;
   if (q_out) {
     if (epilogue != LBT_EPI_F32 || !k_out || !sums || !q_out->ib || rows_per_image == 0) return LBT_EINVAL;
@@ -482,6 +502,7 @@ extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B,
   p.ibB = ibB;
   p.exp_const = exp_const;
   p.bias = bias;
+  p.addend = (epilogue == LBT_EPI_F32 && !q_out) ? addend : nullptr;
   p.out = out_f32;
   p.ldc = ldc;
   p.acc64 = reinterpret_cast<long long*>(acc64);

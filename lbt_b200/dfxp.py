@@ -423,7 +423,7 @@ def _gather_ok(C, Cout, kh, kw):
 
 
 def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW, ib_src, ib_w, exp_const, bias, out2d,
-                   bnq=None):
+                   bnq=None, addend=None):
     """lbt_conv_i8_fprop: out2d[N*OH*OW, Cout] = conv(src, wp) * 2^(exp_const + ib_src + ib_w) (+ bias), or with
     ``bnq = (QSiteStruct, k_out, sums)`` the fused re-quantising epilogue (s8 mantissas + batch statistics)."""
     N, H, W, C = src_nhwc.shape
@@ -431,7 +431,7 @@ def _conv_implicit(src_nhwc, src_kind, wp, Cout, kh, kw, sh, sw, pt, pl, OH, OW,
     _lib.call('lbt_conv_i8_fprop', _lib.ptr(src_nhwc), src_kind, N, H, W, C, _lib.ptr(wp), Q.MANT_S8, wp.stride(0), Cout,
               kh, kw, sh, sw, pt, pl, OH, OW, _lib.ptr(ib_src), _lib.ptr(ib_w), int(exp_const), _lib.ptr(bias),
               _lib.ptr(out2d), out2d.stride(0) if out2d is not None else Cout,
-              ctypes.addressof(qs) if qs is not None else None, _lib.ptr(k_out), _lib.ptr(sums), _lib.stream(),
+              ctypes.addressof(qs) if qs is not None else None, _lib.ptr(k_out), _lib.ptr(sums), _lib.ptr(addend), _lib.stream(),
               meta=dict(ops=2 * N * OH * OW * Cout * kh * kw * C,
                         bytes=N * H * W * C + Cout * kh * kw * C + N * OH * OW * Cout * (1 if qs is not None else 4)))
 
@@ -537,8 +537,10 @@ def _conv_fprop(layer, geom, xm, xkind, prep, wm, bq, out2d, bnq=None):
         G.gemm_i8(A, wt, ibA=ibx, ibB=ibw, exp_const=e, bias=bq, out=out2d, bnq=gbnq)
 
 
-def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_db):
-    """dfxp:302-305 from the quantised gradient mantissas gm [N, OH, OW, Cout] (s8): (dX NHWC fp32, dW, db)."""
+def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_db, addend=None):
+    """dfxp:302-305 from the quantised gradient mantissas gm [N, OH, OW, Cout] (s8): (dX NHWC fp32, dW, db).
+    ``addend`` (NHWC fp32, the shape of dX): the gradient reaching the same input along another branch (residual
+    shortcut), added in the dgrad epilogue instead of by a separate pass over the tensor."""
     N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
     xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
     dev = gm.device
@@ -592,29 +594,30 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     if need_dx:
         K2 = kh * kw * Cout
         dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dev)
+        ad2 = addend.reshape(N * H * W, Cin) if addend is not None else None
         e = -(gb - 1) - (wb - 1)
         pw2 = prep['w2'] if prep is not None else None        # packed by lbt_param_prep in the form used below
         if prep is not None and pw2 is None:
             raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
         if kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
-            G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+            G.gemm_i8(g2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin), addend=ad2)
         elif layer.implicit and sh == 1 and sw == 1 and _implicit_ok(Cout, kh, kw):
             # stride 1: dX = conv(G, rot180(W)) with padding (k - 1 - pad): the same implicit-GEMM kernel
             w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
             _conv_implicit(gm, Q.MANT_S8, w2, Cin, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, H, W, layer.qG.range,
-                           layer.qW.range, e, None, dx.view(N * H * W, Cin))               # dfxp:305
+                           layer.qW.range, e, None, dx.view(N * H * W, Cin), addend=ad2)   # dfxp:305
         elif layer.implicit and _gather_ok(Cout, Cin, kh, kw) and sh <= 4 and sw <= 4:
             # any stride: the transposed gather runs in the kernel's loader warps (lbt_conv_i8_dgrad), no im2col matrix
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             _lib.call('lbt_conv_i8_dgrad', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2), Q.MANT_S8, w2.stride(0),
                       Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
-                      _lib.ptr(dx), Cin, _lib.stream(),
+                      _lib.ptr(dx), Cin, _lib.ptr(ad2), _lib.stream(),
                       meta=dict(ops=2 * N * H * W * Cin * K2, bytes=N * OH * OW * Cout + Cin * K2 + N * H * W * Cin * 4))
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
-            G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin))
+            G.gemm_i8(A2, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin), addend=ad2)
     if fork:
         # NO join here: the weight gradient is needed only by the end-of-backward finalize (Runtime.join_side, called by
         # the Trainer before lbt_finalize_multi), so it overlaps the rest of the backward chain.  Its operands must not
@@ -1115,7 +1118,7 @@ class _ConvBNFn(torch.autograd.Function):
     the results are bit-identical (tests/test_fused_gpu.py)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32):
+    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias):
         geom = _conv_geom(conv, x, weight)
         N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         norm, resc = bn[0], bn[1]
@@ -1139,18 +1142,22 @@ class _ConvBNFn(torch.autograd.Function):
             nm = torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.mark_non_differentiable(nm)
         ctx.set_materialize_grads(False)      # no zero-filled "gradient" for the mantissa output
-        return _from_mem(out), nm
+        # alias: a second handle on the INPUT for the block's other branch (residual shortcut).  Its gradient then comes
+        # back into THIS backward and is added inside the dgrad epilogue, instead of autograd summing two full tensors.
+        xa = x.view_as(x) if alias else torch.empty(0, dtype=torch.float32, device=dev)
+        return _from_mem(out), nm, xa
 
     @staticmethod
-    def backward(ctx, g, _g_nm):
+    def backward(ctx, g, _g_nm, g_alias):
         conv = ctx.conv
         xm, wm, k1, k2, sums, gq, bq, out = ctx.saved_tensors
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         _, gm, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g), k1, k2, sums, gq, bq, out, ctx.relu_mode,
                                                    ctx.has_add, grad_site=conv.qG, want_dx=False)   # ... dfxp:300
-        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False)
+        addend = _to_mem(g_alias) if (g_alias is not None and need_dx) else None
+        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend)
         return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
-                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None)
+                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None)
 
 
 FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lbt_bn_bwd_fused, grid barrier) where the
@@ -1165,7 +1172,7 @@ def _unit_fusable(conv, bn, x):
             x.is_cuda)
 
 
-def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True):
+def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True, alias=False):
     """``bn(conv(x), add=add, relu=relu)`` as ONE fused unit when the shapes allow (else exactly that expression).
 
     next_conv: the Conv2d_q that consumes the result — its input quantiser then runs inside this unit's last kernel
@@ -1173,7 +1180,8 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     ONLY consumer) skips the fp32 tensor altogether."""
     relu = relu or getattr(bn, 'relu', False)
     if not _unit_fusable(conv, bn, x):
-        return bn(conv(x), add=add, relu=relu) if isinstance(bn, BatchNorm2d_q) else bn(conv(x))
+        y = bn(conv(x), add=add, relu=relu) if isinstance(bn, BatchNorm2d_q) else bn(conv(x))
+        return (y, x) if alias else y
     next_site, next_kind = None, Q.MANT_NONE
     if next_conv is not None and isinstance(next_conv, Conv2d_q) and next_conv.fuse_bn:
         nb = next_conv.qX.bits
@@ -1183,12 +1191,17 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
             next_site, next_kind = next_conv.qX, Q.MANT_U8
     if next_site is None or add is not None:
         want_fp32 = True
-    out, nm = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
-                              want_fp32)
+    # measured: folding pays while the dgrad output is narrow (ResNet-18/20 blocks: -1.6 % step time); for the 256..2048-
+    # channel block inputs of ResNet-50 the epilogue-bound 1x1 dgrad GEMMs lose more than the coalesced add costs (+3 %)
+    use_alias = bool(alias and x.requires_grad and not getattr(x, '_lbt_hollow', False) and conv.weight.shape[2] <= 128)
+    out, nm, xa = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
+                                  want_fp32, use_alias)
     if next_site is not None:
         out._lbt_q = {id(next_site): (nm, next_kind)}
     if not want_fp32:
         out._lbt_hollow = True
+    if alias:
+        return out, (xa if use_alias else x)
     return out
 
 
@@ -1535,10 +1548,12 @@ class ResidualBlock_q(nn.Module):
         paired = len(res) % 2 == 0 and all(isinstance(res[i], Conv2d_q) and isinstance(res[i + 1], BatchNorm2d_q)
                                            for i in range(0, len(res), 2))
         if paired:
-            r = x
-            for i in range(0, len(res) - 2, 2):
+            # the first unit hands back an alias of x for the shortcut branch: the shortcut's gradient then returns
+            # through that unit's backward and is added in its dgrad epilogue (no separate add over the tensor)
+            r, xs = conv_bn_unit(res[0], res[1], x, next_conv=res[2], want_fp32=False, alias=True)
+            for i in range(2, len(res) - 2, 2):
                 r = conv_bn_unit(res[i], res[i + 1], r, next_conv=res[i + 2], want_fp32=False)
-            sc = conv_bn_unit(sc_layers[0], sc_layers[1], x) if len(sc_layers) == 2 else self.shortcut(x)
+            sc = conv_bn_unit(sc_layers[0], sc_layers[1], xs) if len(sc_layers) == 2 else self.shortcut(xs)
             return conv_bn_unit(res[-2], res[-1], r, add=sc, relu=True, next_conv=next_conv)
         r = x
         for m in res[:-1]:

@@ -23,11 +23,12 @@ def _check_operand(t, K):
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), K)
 
 
-def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=None):
+def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=None, addend=None):
     """fp32 out[M,N] = (A[M,K] @ B[N,K]^T) * 2^(exp_const + ibA + ibB) (+ bias).
 
     ``bnq = (QSiteStruct, k_out int8 [M,N], sums int64 [2N], rows_per_image)`` switches to the fused re-quantising
-    epilogue (no fp32 output): k_out = Q_site(result), sums += (k, k^2) per column."""
+    epilogue (no fp32 output): k_out = Q_site(result), sums += (k, k^2) per column.  ``addend`` (fp32, the shape and row
+    pitch of ``out``) is added to the fp32 result in the epilogue."""
     M, K = A.shape
     N = B.shape[0]
     lda, ldb = _check_operand(A, K), _check_operand(B, K)
@@ -35,15 +36,15 @@ def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=N
         qs, k_out, sums, rpi = bnq
         _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                   _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), None, None, N, 1, 1,
-                  ctypes.addressof(qs), _lib.ptr(k_out), _lib.ptr(sums), int(rpi), _lib.stream(),
+                  ctypes.addressof(qs), _lib.ptr(k_out), _lib.ptr(sums), int(rpi), None, _lib.stream(),
                   meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + M * N))
         return None
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_F32,
                                       _lib.ptr(ibA), _lib.ptr(ibB), int(exp_const), _lib.ptr(bias), _lib.ptr(out), None,
-                                      out.stride(0), 1, 1, None, None, None, 0, _lib.stream(),
-              meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + 4 * M * N))
+                                      out.stride(0), 1, 1, None, None, None, 0, _lib.ptr(addend), _lib.stream(),
+              meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + 4 * M * N * (2 if addend is not None else 1)))
     return out
 
 
@@ -60,7 +61,7 @@ def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
         k_splits = max(1, sms // max(1, tiles))
     _lib.call('lbt_gemm_i8', _lib.ptr(A), _kind(A), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, EPI_ACC64,
                                       None, None, 0, None, None, _lib.ptr(acc64), N, int(alpha), int(k_splits),
-                                      None, None, None, 0, _lib.stream(),
+                                      None, None, None, 0, None, _lib.stream(),
               meta=dict(ops=2 * M * N * K, bytes=M * K + N * K + 8 * M * N))
     return acc64
 
