@@ -407,7 +407,13 @@ def run_native(a):
         'metric': 'quantized train imgs/sec', 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 's8/u8 mantissas, s32 accumulate (8-bit dfxp); fp32 master weights', 'data': 'synthetic',
-        'config': describe(a, batch),
+        'config': dict(describe(a, batch), exchange={
+            'fused': 'lbt_dp_step: one kernel over NVLink peer memory (reduce-scatter by peer loads + SGD on the owned slice + '
+                     'all-gather of the weights by peer stores + counter sum + range controller)',
+            'nccl': 'NCCL all-reduce of gradients and counters + lbt_sgd_momentum + lbt_update_ranges',
+            'unfused': 'single GPU: lbt_sgd_momentum + lbt_update_ranges'}[trainer.dp_mode] if world > 1 or trainer.dp_mode != 'fused'
+            else 'single GPU: lbt_dp_step (SGD + range controller + step counter in one launch)'),
+        'dp_error': trainer.dp.error() if trainer.dp is not None else None,
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms, 'wall_ms_per_step': wall / a.steps * 1e3},

@@ -444,6 +444,47 @@ int lbt_relu(const float* x, const float* g, float* out, size_t n, void* stream)
 int lbt_dropout(const float* x, const float* u, float keep_prob, uint64_t seed, uint64_t offset, const uint64_t* dev_step,
                 float* out, size_t n, void* stream);
 
+/*
+ * Data-parallel end of a step as ONE kernel over NVLink peer memory (the reference, trainer.py:79-84 +
+ * :157-160, is single-device): barrier, reduce-scatter of the replicas' flat gradients by peer loads (sum in rank order),
+ * momentum SGD on the owned slice with grad_scale = 1/world (as lbt_sgd_momentum), all-gather of the UPDATED WEIGHTS by
+ * peer stores, overflow counters summed over the replicas + the range controller (as lbt_update_ranges), barrier,
+ * counters zeroed, *dev_step += 1 (as lbt_step_advance).  Replaces two all-reduces and three launches.
+ *
+ * lbt_dp_peers: for every replica r the peer-mapped addresses of its flat gradient [n], flat weights [n], counters
+ * [n_sites][LBT_CNT_WORDS] and a zero-initialised uint32 pad[LBT_DP_PAD_WORDS] (flags written by the peers' kernels).
+ * Entry `rank` is the caller's own memory.  shard = 0: every replica reduces and updates all n parameters itself (no weight
+ * stores, w[r != rank] unused); shard = 1: replica r owns parameters [r*ceil(n/4/world)*4, ...) and `accum` is only
+ * maintained there.  n % 4 == 0.  All replicas must launch the call once per step (it spins on the peers' flags; waits are
+ * bounded: after 20 s pad[LBT_DP_PAD_ERROR] is set and the kernel carries on).
+ */
+#define LBT_DP_MAX_WORLD 8
+#define LBT_DP_PAD_READY 0   /* [world] flags: replica r has finished its backward (epoch number) */
+#define LBT_DP_PAD_DONE 8    /* [world] flags: replica r has finished reading / writing peer memory */
+#define LBT_DP_PAD_EPOCH 16
+#define LBT_DP_PAD_TICKET 17
+#define LBT_DP_PAD_ERROR 18  /* != 0: a wait timed out */
+#define LBT_DP_PAD_WORDS 32
+#define LBT_DP_HANDLE_BYTES 64
+typedef struct lbt_dp_peers {
+  int32_t world, rank;
+  const float* grad[LBT_DP_MAX_WORLD];
+  float* w[LBT_DP_MAX_WORLD];
+  const uint64_t* counters[LBT_DP_MAX_WORLD];
+  uint32_t* pad[LBT_DP_MAX_WORLD];
+} lbt_dp_peers;
+int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, float lr, const float* dev_lr, float momentum,
+                int shard, int32_t* ranges, const int32_t* bits, const float* target, size_t n_sites, uint64_t* dev_step,
+                void* stream);
+/*
+ * Peer mapping of caller-owned buffers between the replica processes (CUDA IPC): lbt_dp_export gives the handle
+ * (LBT_DP_HANDLE_BYTES) of the allocation containing ptr and ptr's offset in it; the caller ships both to the peers over
+ * its own control plane; lbt_dp_open maps the allocation there (*base + offset = the buffer); lbt_dp_close unmaps.
+ */
+int lbt_dp_export(const void* ptr, void* handle64, size_t* offset);
+int lbt_dp_open(const void* handle64, void** base);
+int lbt_dp_close(void* base);
+
 #ifdef __cplusplus
 }
 #endif

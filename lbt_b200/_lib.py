@@ -67,6 +67,11 @@ SIGNATURES = {
                                        c_void_p, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'lbt_dp_step': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                            c_size_t, c_void_p, c_void_p]),
+    'lbt_dp_export': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'lbt_dp_open': (c_int, [c_void_p, c_void_p]),
+    'lbt_dp_close': (c_int, [c_void_p]),
 }
 
 # not part of the public header: tuning knobs used by bench sweeps
@@ -107,6 +112,15 @@ class BnBwdArgs(ctypes.Structure):
                 ('q_g1', QSiteStruct), ('d_add', c_void_p), ('bwd_sums', c_void_p), ('fwd_sums', c_void_p), ('eps', c_float),
                 ('has_q_grad', ctypes.c_int32), ('q_grad', QSiteStruct), ('dx', c_void_p), ('g_mant', c_void_p),
                 ('barrier', c_void_p)]
+
+
+DP_MAX_WORLD, DP_PAD_WORDS, DP_PAD_ERROR, DP_HANDLE_BYTES = 8, 32, 18, 64
+
+
+class DpPeers(ctypes.Structure):
+    """lbt_dp_peers (include/lbt.h)."""
+    _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32), ('grad', c_void_p * DP_MAX_WORLD),
+                ('w', c_void_p * DP_MAX_WORLD), ('counters', c_void_p * DP_MAX_WORLD), ('pad', c_void_p * DP_MAX_WORLD)]
 
 
 class NoiseJob(ctypes.Structure):

@@ -136,12 +136,15 @@ class Runtime:
         site.qid = len(self.sites)
         self.sites.append(site)
 
-    def finalize(self, device):
+    def finalize(self, device, counters=None):
         """Flatten every quantiser's range/counters into contiguous device arrays (one
-        lbt_update_ranges launch per step; one all-reduce of the counters under data parallelism)."""
+        lbt_update_ranges launch per step; one exchange of the counters under data parallelism).
+        ``counters``: zeroed int64 [n, CNT_WORDS] storage to use (the peer-mapped arena of lbt_b200.dp)."""
         n = len(self.sites)
         ranges = torch.empty(n, dtype=torch.int32, device=device)
-        counters = torch.zeros(n, Q.CNT_WORDS, dtype=torch.int64, device=device)
+        if counters is None:
+            counters = torch.zeros(n, Q.CNT_WORDS, dtype=torch.int64, device=device)
+        assert counters.shape == (n, Q.CNT_WORDS) and counters.dtype == torch.int64
         bits = torch.tensor([s.bits for s in self.sites], dtype=torch.int32, device=device)
         target = torch.tensor([s.target for s in self.sites], dtype=torch.float32, device=device)
         for i, s in enumerate(self.sites):
@@ -158,6 +161,9 @@ class Runtime:
         _lib.call('lbt_update_ranges', _lib.ptr(f['ranges']), _lib.ptr(f['counters']), _lib.ptr(f['bits']),
                                        _lib.ptr(f['target']), len(self.sites), _lib.stream())
         _lib.call('lbt_step_advance', _lib.ptr(self.dev_step), _lib.stream())
+        self.close_step()
+
+    def close_step(self):
         self._arena_on = False           # the step is closed: prepared operands and arena slices are stale now
         self._prep_valid = False
         self._noise_valid = False

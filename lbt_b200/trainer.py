@@ -4,12 +4,18 @@ One ``Trainer.step(X, y)`` is one ``sess.run([train_op, update_range_op])`` (tra
 forward, loss, backward (the layers quantise their own gradients), momentum SGD on the fp32 master
 weights (trainer.py:79-84), then the range controller of every quantiser.  New here (the reference
 is single-device): data parallelism over the batch — one process per GPU, the
-flattened gradient all-reduced with NCCL, and the overflow counters all-reduced before the
-controller runs so every replica keeps identical ranges and sees the global-batch overflow rate.
+gradients reduced over the replicas and the overflow counters summed before the controller runs, so
+every replica keeps identical ranges and sees the global-batch overflow rate.  On GPUs the whole
+exchange is ONE kernel over NVLink peer memory (lbt_dp_step: reduce-scatter by peer loads, momentum
+SGD on the owned slice, all-gather of the updated weights by peer stores, counter sum + controller);
+``dp='nccl'`` keeps the two-all-reduce formulation (also what the gloo CPU tests drive).
 
 Per step the parameter side costs four launches regardless of depth: lbt_param_prep (quantise + pack
 every parameter), lbt_finalize_multi (every gradient), lbt_sgd_momentum, lbt_update_ranges.
 """
+import os
+import sys
+
 import torch
 import torch.distributed as dist
 
@@ -68,7 +74,7 @@ class GradSink:
 
 
 class Trainer:
-    def __init__(self, model, lr=1e-2, momentum=0.9, *, process_group=None, sync_counters=True, batched=True):
+    def __init__(self, model, lr=1e-2, momentum=0.9, *, process_group=None, sync_counters=True, batched=True, dp=None):
         self.model = model
         self.lr, self.momentum = float(lr), float(momentum)
         self.group = process_group
@@ -80,15 +86,43 @@ class Trainer:
         dev = params[0].device
         self.device = dev
         rt = model.runtime
-        rt.finalize(dev)
-        # flatten parameters / gradients / momentum: one SGD launch and one all-reduce per step
+        # flatten parameters / gradients / momentum: one SGD launch and one exchange per step
         sizes = [p.numel() for p in params]
         offs, total = [], 0
         for n in sizes:
             offs.append(total)
             total += -(-n // 4) * 4                      # keep every view 16-byte aligned
-        self.flat_w = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        # end of the step: 'fused' = ONE lbt_dp_step launch (over peer-mapped arenas when world > 1),
+        # 'nccl' = all-reduces + lbt_sgd_momentum + lbt_update_ranges + lbt_step_advance
+        dp = dp or os.environ.get('LBT_DP', 'fused')
+        self.dp = None
+        if dp == 'fused' and (sync_counters or self.world == 1):
+            from .dp import DpExchange
+            ok, why = 1.0, ''
+            try:
+                self.dp = DpExchange(len(rt.sites), total, dev, process_group)
+            except Exception as e:               # e.g. no peer access between the devices: say so, use NCCL
+                if self.world == 1:
+                    raise
+                ok, why = 0.0, str(e)
+            if self.world > 1:                   # all replicas must agree on the path; doubles as the start barrier
+                torch.cuda.synchronize(dev)
+                flag = torch.full((1,), ok, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=process_group)
+                if not bool(flag.item()):
+                    print('lbt_b200: fused data-parallel exchange unavailable (%s); using NCCL all-reduce' % (why or 'a peer failed'),
+                          file=sys.stderr)
+                    if self.dp is not None:
+                        self.dp.close()
+                    self.dp = None
+        self.dp_mode = 'fused' if self.dp is not None else ('nccl' if self.world > 1 else 'unfused')
+        if self.dp is not None:
+            rt.finalize(dev, counters=self.dp.arena.counters)
+            self.flat_w, self.flat_g = self.dp.arena.flat_w, self.dp.arena.flat_g
+        else:
+            rt.finalize(dev)
+            self.flat_w = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_a = torch.zeros(total, dtype=torch.float32, device=dev)        # optimizer slots start at 0 (trainer.py:83)
         for p, o, n in zip(params, offs, sizes):
             self.flat_w[o:o + n].copy_(p.data.reshape(-1))
@@ -127,6 +161,10 @@ class Trainer:
 
     def apply(self):
         rt = self.model.runtime
+        if self.dp is not None:              # the whole exchange + optimizer + controller: one kernel over NVLink
+            self.dp.step(self.flat_a, self.lr, self.dev_lr, self.momentum, rt)
+            rt.close_step()
+            return
         if self.world > 1:
             sync_replicas(self.flat_g, rt.flat['counters'], self.group, self.sync_counters)
         _lib.call('lbt_sgd_momentum', _lib.ptr(self.flat_w), _lib.ptr(self.flat_a), _lib.ptr(self.flat_g),
