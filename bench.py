@@ -190,6 +190,8 @@ def run_native(a):
         raise SystemExit('bench.py --impl native needs a GPU: the DFXP path has no CPU fallback')
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'        # NCCL's "NCCL version ..." banner goes to stdout: keep it to ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     assert world == a.gpus, 'launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)' % (a.gpus, world)
     dev = torch.device('cuda', local)
