@@ -161,10 +161,12 @@ def main():
     ap.add_argument('--only', default='', help='substring filter on the layer name')
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--path', type=int, default=1, help='0: TMA kernels only, 1: gather kernels for narrow channels')
+    ap.add_argument('--pair', type=int, default=1, help='0: single-CTA GEMM kernel only, 1: CTA-pair kernel for large GEMMs')
     ap.add_argument('--out', default='gpurun_out/gemm_bench.json')
     a = ap.parse_args()
     ITERS[0] = a.iters
     _lib.lib().lbt_conv_set_path(a.path)
+    _lib.lib().lbt_gemm_set_pair(a.pair)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device='cuda') if a.flush else None
     rows = []
     for n in [int(s) for s in a.square.split(',') if s]:

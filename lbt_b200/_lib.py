@@ -81,6 +81,7 @@ _INTERNAL = {
     'lbt_conv_debug_error': (c_int, []),
     'lbt_conv_ldg_debug_error': (c_int, []),
     'lbt_conv_set_path': (c_int, [c_int]),
+    'lbt_gemm_set_pair': (c_int, [c_int]),
     'lbt_set_pdl': (c_int, [c_int]),
     'lbt_test_fdiv': (c_int, [c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
     'lbt_bn_set_debug': (c_int, [c_void_p]),

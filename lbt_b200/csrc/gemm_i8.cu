@@ -381,6 +381,257 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// =====================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2) for large fp32-epilogue GEMMs.  One 128x256 tile per SM asks the L2 for
+// (128 + 256) * 128 B per 512 tensor-core clocks = 96 B/clk/SM, more than the ~43 B/clk/SM the L2 can deliver to 148 SMs at
+// once (B300_MICROARCH.md: ~6300 B/clk chip-wide), so the single-CTA kernel tops out near half of the tensor peak.  A pair
+// of SMs (a 2-CTA cluster on one TPC) computes a 256x256 tile: each CTA stages ITS 128 rows of A and ITS 128 rows of B, the
+// leader's single thread issues M256 x N256 x K32 instructions that read both shared memories, and each CTA's tensor memory
+// receives its 128 accumulator rows: 64 B/clk/SM for the same math.
+//
+//   full_bar   (leader only)  : tx-count barrier; BOTH CTAs' TMA loads complete on it (.cta_group::2 loads may signal the peer)
+//   empty_bar  (both)         : tcgen05.commit multicast — the smem slot of BOTH CTAs is free when the pair's MMAs have read it
+//   tmem_full  (both)         : tcgen05.commit multicast — accumulator stage complete
+//   tmem_empty (leader only)  : 2 x 8 epilogue warps arrive (the peer's remotely) before the leader reuses the stage
+constexpr int k2BN = 256;              // columns of the pair's tile
+constexpr int k2StageA = kBlockM * kBlockK;
+constexpr int k2StageB = (k2BN / 2) * kBlockK;
+constexpr int k2StageBytes = k2StageA + k2StageB;
+constexpr int k2Stages = 6;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024;
+constexpr int k2TmemCols = 512;        // two 256-column accumulator stages
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair when the issued MMAs complete
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_i8_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[k2Stages];
+  __shared__ __align__(8) uint64_t empty_bar[k2Stages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_abort;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // the epilogue warps of BOTH CTAs (leader's copy is the live one)
+    }
+    s_abort = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_slot, k2TmemCols);
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised, tensor memory allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  volatile int* abort_flag = &s_abort;
+
+  const uint32_t m_pairs = (p.m_tiles + 1) / 2;
+  const uint32_t total_items = m_pairs * p.n_tiles;
+  const uint32_t first = cluster_id_x(), stride = cluster_nid_x();
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane per CTA): my 128 rows of A, my 128 rows of B; completion on the LEADER's barrier =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (uint32_t item = first; item < total_items && ok; item += stride) {
+        const uint32_t m_pair = item % m_pairs, n_tile = item / m_pairs;
+        for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+          if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag))) break;
+          uint8_t* sa = smem + stage * k2StageBytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * k2StageBytes);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(&tmA, bar, sa, (int)(kb * kBlockK), (int)(m_pair * 2 * kBlockM + rank * kBlockM));
+          tma_load_2d_pair(&tmB, bar, sa + k2StageA, (int)(kb * kBlockK), (int)(n_tile * k2BN + rank * (k2BN / 2)));
+          if (++stage == k2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one lane of the LEADER CTA drives both tensor cores =====
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      bool ok = true;
+      for (uint32_t item = first; item < total_items && ok; item += stride) {
+        if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag))) break;
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * k2BN;
+        for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+          if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag))) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
+          const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + k2StageA);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_i8_pair(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), p.idesc,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == k2Stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (!ok) break;
+        umma_commit_pair(&tmem_full_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): my 128 accumulator rows -> fp32 =====
+    const uint32_t quad = warp & 3;
+    const uint32_t half = (uint32_t)(warp - 2) >> 2;
+    int e = p.exp_const;
+    if (p.ibA) e += *p.ibA;
+    if (p.ibB) e += *p.ibB;
+    const float scale = exp2i(e);
+    uint32_t acc = 0, acc_phase = 0;
+    bool ok = true;
+    for (uint32_t item = first; item < total_items && ok; item += stride) {
+      const uint32_t m_pair = item % m_pairs, n_tile = item / m_pairs;
+      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t row = m_pair * 2 * kBlockM + rank * kBlockM + quad * 32 + lane;
+      const uint32_t col0 = n_tile * k2BN;
+      const uint32_t taddr = tmem_base + acc * k2BN + ((quad * 32u) << 16);
+#pragma unroll 1
+      for (int c = 16 * (int)half; c < k2BN; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (row < p.M && col0 + c < p.N) {
+          const uint32_t ncol = min(16u, p.N - (col0 + c));
+          float* o = p.out + (size_t)row * p.ldc + col0 + c;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = __int2float_rn((int)v[j]) * scale;
+            if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
+          }
+          if (p.addend) {
+            const float* ad = p.addend + (o - p.out);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(ad + j));
+          }
+          if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < (int)ncol) o[j] = f[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees tensor memory) while the peer may still signal into this CTA
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, k2TmemCols);
+}
+
+std::atomic<int> g_gemm_pair{1};       // lbt_gemm_set_pair(): 0 = always the single-CTA kernel
+
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, unsigned clusters, cudaStream_t st) {
+  static bool attr_done[16] = {};
+  const int dev = device_info().device;
+  if (!attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "cudaFuncSetAttribute(gemm_i8_pair_kernel)");
+      return LBT_ECUDA;
+    }
+    attr_done[dev] = true;
+  }
+  gemm_i8_pair_kernel<<<2 * clusters, kThreads, k2SmemBytes, st>>>(ta, tb, p);
+  return check_launch("lbt_gemm_i8(pair)");
+}
+
 // out[i] = fp32(acc64[i]) * 2^e (+ add_scale * add[i])   — wgrad finalize: scale + weight-decay term
 // (dynamic_fixed_point.py:302 `+ 2 * weight_decay * W`: a separate fp32 multiply then add).
 __global__ void acc64_finalize_kernel(const long long* acc, size_t n, const int32_t* ibA, const int32_t* ibB, int exp_const,
@@ -519,12 +770,23 @@ extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B,
   CUtensorMap ta, tb;
   int rc = make_operand_map(&ta, A, M, K, lda, kBlockM);
   if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // large fp32-epilogue GEMMs: CTA pairs on 256x256 tiles (two thirds of the L2 -> shared-memory traffic per MAC)
+  if (g_gemm_pair.load(std::memory_order_relaxed) && epilogue == LBT_EPI_F32 && !q_out && bn == 256 && M >= 256 &&
+      (uint64_t)((p.m_tiles + 1) / 2) * p.n_tiles >= (uint64_t)(di.sm_count / 2)) {
+    rc = make_operand_map(&tb, B, N, K, ldb, (uint32_t)(k2BN / 2));
+    if (rc) return rc;
+    p.idesc = (2u << 4) | ((a_kind == LBT_MANT_S8 ? 1u : 0u) << 7) | ((b_kind == LBT_MANT_S8 ? 1u : 0u) << 10) |
+              ((uint32_t)(k2BN >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+    const uint64_t pair_items = (uint64_t)((p.m_tiles + 1) / 2) * p.n_tiles;
+    const uint64_t max_clusters = (uint64_t)(di.sm_count / 2);
+    return launch_pair(ta, tb, p, (unsigned)(pair_items < max_clusters ? pair_items : max_clusters), st);
+  }
   rc = make_operand_map(&tb, B, N, K, ldb, (uint32_t)bn);
   if (rc) return rc;
 
   const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
   const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
     case 16: return launch<16>(ta, tb, p, grid, st);
     case 32: return launch<32>(ta, tb, p, grid, st);
@@ -544,6 +806,12 @@ extern "C" int lbt_acc64_finalize(const int64_t* acc64, size_t n, const int32_t*
   acc64_finalize_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(acc64), n, ibA, ibB, exp_const, add, add_scale, out);
   return check_launch("lbt_acc64_finalize");
+}
+
+// Bench / test knob (not in lbt.h): 0 = never use the CTA-pair kernel, 1 (default) = use it for large fp32-epilogue GEMMs.
+extern "C" int lbt_gemm_set_pair(int on) {
+  g_gemm_pair.store(on ? 1 : 0, std::memory_order_relaxed);
+  return LBT_OK;
 }
 
 // Test hook: 1 if any GEMM CTA hit the bounded-wait watchdog since the last call (synchronises).

@@ -84,3 +84,35 @@ def test_gemm_worst_case_magnitudes_do_not_overflow():
     with pytest.raises(Exception):
         G.gemm_i8(torch.zeros(128, K + 128, dtype=torch.uint8, device='cuda'),
                   torch.zeros(16, K + 128, dtype=torch.int8, device='cuda'))
+
+
+# ---- CTA-pair kernel (tcgen05 cta_group::2, 256x256 tiles): taken for large fp32-epilogue GEMMs with N > 128 ----
+
+@pytest.mark.parametrize('M,N,K', [(2048, 2560, 384), (2304 + 57, 2048 + 24, 1000), (4096, 4096, 4096), (256, 19000, 130),
+                                   (18944 + 129, 256, 64)])
+@pytest.mark.parametrize('kinds', ['ss', 'us'])
+def test_gemm_pair_kernel_bit_exact(M, N, K, kinds):
+    from lbt_b200 import _lib
+    rng = np.random.default_rng(M + N + K)
+    A, a64 = _operand(rng, M, K, kinds[0] == 's')
+    B, b64 = _operand(rng, N, K, kinds[1] == 's')
+    bias = torch.randn(N, device='cuda')
+    addend = torch.randn(M, N, device='cuda')
+    ib = torch.tensor(-3, dtype=torch.int32, device='cuda')
+    try:
+        _lib.lib().lbt_gemm_set_pair(1)
+        out = G.gemm_i8(A, B, exp_const=0)
+        out2 = G.gemm_i8(A, B, ibA=ib, exp_const=-9, bias=bias, addend=addend)
+        torch.cuda.synchronize()
+        assert G.debug_error() == 0, 'GEMM pipeline watchdog fired'
+        _lib.lib().lbt_gemm_set_pair(0)
+        single = G.gemm_i8(A, B, exp_const=0)
+        single2 = G.gemm_i8(A, B, ibA=ib, exp_const=-9, bias=bias, addend=addend)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().lbt_gemm_set_pair(1)
+    ref = _exact(a64, b64)
+    assert torch.equal(out.double(), ref.float().double()), (out.double() - ref).abs().max()
+    assert torch.equal(out, single)
+    assert torch.equal(out2, single2)
+    assert torch.equal(out2, (ref.float() * 2.0 ** -12 + bias) + addend)
