@@ -485,6 +485,19 @@ int lbt_dp_export(const void* ptr, void* handle64, size_t* offset);
 int lbt_dp_open(const void* handle64, void** base);
 int lbt_dp_close(void* base);
 
+/*
+ * The input pipeline of one training batch on the device (main.py:71-75 normalisation; trainer.py:24-28 preprocess_image;
+ * trainer.py:92-96 shuffle + batch).  For output sample b, with i = index[b] (NULL: i = b):
+ *   img = (double(src[i]) - mean) / 128, rounded to fp32 once (numpy float64 arithmetic, fp32 feed);
+ *   flipped left-right if do_flip && flip_b; padded by `pad` zeros on every side; cropped H x W at (oy_b, ox_b).
+ * params int32 [B][3] = (flip, oy, ox) explicit, or NULL: drawn in-kernel from Philox4x32-10 with counter (b, 0, offset) and
+ * key seed: flip = r0 & 1, oy = r1 % (2*pad+1), ox = r2 % (2*pad+1).  src uint8 [n, H, W, C]; mean float64 [H, W, C] or NULL;
+ * out fp32 NHWC [B, H, W, C]; labels_out[b] = labels[i] when both are given.  pad = 0, do_flip = 0: plain normalised batch.
+ */
+int lbt_augment_batch(const uint8_t* src, const double* mean, const int64_t* index, int B, int H, int W, int C, int pad,
+                      int do_flip, const int32_t* params, uint64_t seed, uint64_t offset, const int64_t* labels,
+                      int64_t* labels_out, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

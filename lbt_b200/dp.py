@@ -97,6 +97,14 @@ class DpExchange:
                   _lib.ptr(f['target']), len(rt.sites), _lib.ptr(rt.dev_step), _lib.stream(),
                   meta=dict(bytes=self.arena.n_params * 4 * 2))
 
+    def owned(self, shard=True):
+        """[lo, hi) of the flat parameter index this replica reduces and updates (lbt_dp_step's slicing)."""
+        n = self.arena.n_params
+        if not shard or self.world == 1:
+            return 0, n
+        chunk = -(-(n // 4) // self.world) * 4
+        return min(n, self.rank * chunk), min(n, (self.rank + 1) * chunk)
+
     def error(self):
         """Non-zero when a cross-replica wait timed out (synchronises)."""
         return int(self.arena.pad[_lib.DP_PAD_ERROR].item())

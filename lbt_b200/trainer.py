@@ -176,3 +176,89 @@ class Trainer:
         loss, _ = self.forward_backward(X, y)
         self.apply()
         return loss
+
+    # ---- evaluation (trainer.py:164-187) ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, X, y, batch_size=1000):
+        """Mean loss and accuracy over (X, y) in batches of ``batch_size`` — the reference's test loop.  Like the
+        reference (its ``set_testing`` call is commented out, trainer.py:164-165, "TODO BatchNorm bug") the forward pass
+        runs in TRAINING mode: batch statistics, stochastic quantisers; nothing is updated — no range controller
+        (``update_range_op`` is not fetched), no running statistics, no step counter."""
+        from .dfxp import Normalization_q
+        rt = self.model.runtime
+        norms = [m for m in self.model.modules() if isinstance(m, Normalization_q)]
+        saved = [m.momentum for m in norms]
+        for m in norms:
+            m.momentum = 1.0                       # running <- 1.0 * running + 0.0 * batch: unchanged
+        counters = rt.flat['counters'].clone()
+        loss_sum, acc_sum, n_batches = 0.0, 0.0, 0
+        try:
+            for i in range(0, X.shape[0], batch_size):
+                xb, yb = X[i:i + batch_size], y[i:i + batch_size]
+                logits = self.model(xb)
+                loss_sum += float(self.model.loss(logits, yb))
+                acc_sum += float((logits.argmax(dim=1) == yb).float().mean())
+                n_batches += 1
+        finally:
+            for m, mom in zip(norms, saved):
+                m.momentum = mom
+            rt.flat['counters'].copy_(counters)    # the overflow statistics of a test batch never reach the controller
+        return loss_sum / max(1, n_batches), acc_sum / max(1, n_batches)          # mean of per-batch means, as trainer.py:185-186
+
+    # ---- the epoch loop (trainer.py:109-187) ---------------------------------------------------------------------------
+    def fit(self, pipeline, n_epoch, batch_size, *, lr_decay_factor=0.1, decay_epochs=(80, 120, 140), test=None, log=None,
+            max_batches=None):
+        """``pipeline``: lbt_b200.data.Pipeline over the device-resident training set (shuffle + flip / pad-4 / crop on
+        the GPU).  The learning rate is multiplied by ``lr_decay_factor`` at epochs 80, 120 and 140 and the optimizer is
+        re-created (momentum slots zeroed) exactly there (trainer.py:117-132).  ``test`` = (X, y) evaluated after each
+        epoch.  Returns [(epoch, last_train_loss, test_loss, test_acc)]."""
+        history = []
+        for epoch in range(n_epoch):
+            if epoch in decay_epochs:
+                self.set_lr(self.lr * lr_decay_factor, reset_momentum=True)
+            loss = None
+            for b, (X, y) in enumerate(pipeline.epoch(batch_size, epoch)):
+                if max_batches is not None and b >= max_batches:
+                    break
+                loss = self.step(X, y)
+                if log is not None and (b + 1) % 100 == 0:
+                    log('Batch %d loss %f' % (b + 1, float(loss)))
+            tl, ta = self.evaluate(*test) if test is not None else (None, None)
+            history.append((epoch, float(loss) if loss is not None else None, tl, ta))
+            if log is not None and ta is not None:
+                log('Epoch %d test accuracy %f' % (epoch + 1, ta))
+        return history
+
+    # ---- checkpoint / resume (trainer.py:189-192: tf.train.Saver over all variables) -----------------------------------
+    def state_dict(self):
+        """Everything the reference's Saver holds — weights, every ``*_range`` variable, the BN running statistics, the
+        optimizer slots — plus what the TF session held implicitly (step counter = noise stream position, lr)."""
+        rt = self.model.runtime
+        accum = self.flat_a.clone()
+        if self.dp is not None and self.world > 1:       # sharded optimizer: every replica holds only its slice
+            dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=self.group)
+        return {'model': {k: v.detach().clone() for k, v in self.model.state_dict().items()},
+                'momentum_slots': accum, 'lr': self.lr, 'momentum': self.momentum,
+                'step': int(rt.dev_step.item()), 'seed': rt.seed}
+
+    def load_state_dict(self, sd):
+        rt = self.model.runtime
+        self.model.load_state_dict(sd['model'])            # copies into the flat views (weights, ranges, counters)
+        if int(sd['seed']) != rt.seed:
+            raise _lib.LbtError('checkpoint was written with noise seed %d; build the model with seed=%d to resume its stream'
+                                % (sd['seed'], sd['seed']))
+        self.flat_a.copy_(sd['momentum_slots'].to(self.device))
+        if self.dp is not None and self.world > 1:       # keep only the slice this replica owns (see state_dict)
+            lo, hi = self.dp.owned()
+            self.flat_a[:lo].zero_()
+            self.flat_a[hi:].zero_()
+        self.lr, self.momentum = float(sd['lr']), float(sd['momentum'])
+        self.dev_lr.fill_(self.lr)
+        rt.dev_step.fill_(int(sd['step']))
+        rt.close_step()
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location=self.device))
