@@ -498,6 +498,17 @@ int lbt_augment_batch(const uint8_t* src, const double* mean, const int64_t* ind
                       int do_flip, const int32_t* params, uint64_t seed, uint64_t offset, const int64_t* labels,
                       int64_t* labels_out, float* out, void* stream);
 
+/*
+ * GradientBuffer_q (dynamic_fixed_point.py:473-509), the error-feedback gradient quantiser, in one pass:
+ *   total = pad(grad, to n_outer rows) + buffer ; q = Q(total) (rounding / noise / statistics as lbt_quantize) ;
+ *   buffer <- total - q ; out[r] = q[r] for r < n_grad_rows.
+ * grad, out: [n_grad_rows, n_inner] (n_grad_rows <= n_outer: a short last batch); buffer: [n_outer, n_inner] in/out.
+ * counters accumulate over all n_outer * n_inner elements of `total`; the range moves in lbt_update_ranges.
+ */
+int lbt_quantize_residual(const float* grad, size_t n_grad_rows, float* buffer, size_t n_outer, size_t n_inner, int bits,
+                          int32_t* integer_bits, int mode, const float* noise, uint64_t seed, uint64_t offset,
+                          const uint64_t* dev_step, float* out, uint64_t* counters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ SIGNATURES = {
     'lbt_dp_export': (c_int, [c_void_p, c_void_p, c_void_p]),
     'lbt_dp_open': (c_int, [c_void_p, c_void_p]),
     'lbt_dp_close': (c_int, [c_void_p]),
+    'lbt_quantize_residual': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_int, c_void_p, c_u64,
+                                      c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'lbt_augment_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_u64, c_u64,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
 }

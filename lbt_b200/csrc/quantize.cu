@@ -270,6 +270,34 @@ __global__ void __launch_bounds__(kThreads) quantize_c3_kernel(const QParams p) 
   finish_stats(n1, n2, p, ib);
 }
 
+// GradientBuffer_q (dynamic_fixed_point.py:473-509), one pass: total = pad(grad) + buffer; q = Q_stochastic(total);
+// buffer <- total - q; out = q[:n_grad_rows].  One element per thread-iteration (the layer is disabled in the reference's
+// models: correctness and a single pass matter here, not the last 20 % of bandwidth).
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) quantize_residual_kernel(const QParams p, float* __restrict__ buffer, size_t n_grad_rows) {
+  const int ib = *reinterpret_cast<volatile const int32_t*>(p.ib);
+  const QConst c = make_const(p.bits, ib);
+  uint64_t off = p.offset;
+  if (MODE == LBT_ROUND_STOCHASTIC_PHILOX && p.dev_step) off += (*p.dev_step) << 32;
+  uint32_t n1 = 0, n2 = 0;
+  const size_t n = p.n_outer * p.n_inner, n_grad = n_grad_rows * p.n_inner;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) {
+    const size_t col = i % p.n_inner;
+    float u = 0.f;
+    if (MODE == LBT_ROUND_STOCHASTIC_NOISE) u = __ldg(p.noise + col);
+    if (MODE == LBT_ROUND_STOCHASTIC_PHILOX) {
+      const float4 u4 = philox_noise4(col >> 2, p.seed, off);
+      const int l = (int)(col & 3);
+      u = l == 0 ? u4.x : (l == 1 ? u4.y : (l == 2 ? u4.z : u4.w));
+    }
+    const float total = __fadd_rn(i < n_grad ? p.x[i] : 0.f, buffer[i]);       // dfxp:499 tf.pad(grad) + buffer
+    const float q = quant1<MODE>(total, u, c, n1, n2) * c.inv_m;              // dfxp:500
+    buffer[i] = __fsub_rn(total, q);                                           // dfxp:503
+    if (i < n_grad) p.out[i] = q;                                              // dfxp:506
+  }
+  finish_stats(n1, n2, p, ib);
+}
+
 __global__ void noise_fill_kernel(float* u, size_t n_inner, uint64_t seed, uint64_t offset, const uint64_t* dev_step) {
   uint64_t off = offset;
   if (dev_step) off += (*dev_step) << 32;
@@ -421,6 +449,39 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
     }
   }
   return check_launch("lbt_quantize");
+}
+
+extern "C" int lbt_quantize_residual(const float* grad, size_t n_grad_rows, float* buffer, size_t n_outer, size_t n_inner, int bits,
+                                     int32_t* integer_bits, int mode, const float* noise, uint64_t seed, uint64_t offset,
+                                     const uint64_t* dev_step, float* out, uint64_t* counters, void* stream) {
+  if (!buffer || !integer_bits || (n_grad_rows && (!grad || !out))) return LBT_EINVAL;
+  if (bits < 2 || bits > 24 || mode < 0 || mode > 2 || n_grad_rows > n_outer) return LBT_EINVAL;
+  if (mode == LBT_ROUND_STOCHASTIC_NOISE && !noise) return LBT_EINVAL;
+  if (n_outer == 0 || n_inner == 0) return LBT_OK;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+  QParams p{};
+  p.x = grad;
+  p.n_outer = n_outer;
+  p.n_inner = n_inner;
+  p.bits = bits;
+  p.ib = integer_bits;
+  p.noise = noise;
+  p.seed = seed;
+  p.offset = offset;
+  p.dev_step = dev_step;
+  p.out = out;
+  p.counters = reinterpret_cast<unsigned long long*>(counters);
+  const uint64_t n = (uint64_t)n_outer * n_inner, blocks = (n + kThreads - 1) / kThreads;
+  const uint64_t cap = (uint64_t)di.sm_count * 8;
+  const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (mode) {
+    case LBT_ROUND_NEAREST: quantize_residual_kernel<0><<<grid, kThreads, 0, st>>>(p, buffer, n_grad_rows); break;
+    case LBT_ROUND_STOCHASTIC_NOISE: quantize_residual_kernel<1><<<grid, kThreads, 0, st>>>(p, buffer, n_grad_rows); break;
+    default: quantize_residual_kernel<2><<<grid, kThreads, 0, st>>>(p, buffer, n_grad_rows); break;
+  }
+  return check_launch("lbt_quantize_residual");
 }
 
 extern "C" int lbt_noise_fill(float* u, size_t n_inner, uint64_t seed, uint64_t offset, const uint64_t* dev_step,

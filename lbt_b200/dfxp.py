@@ -1505,6 +1505,52 @@ class Flatten_q(nn.Module):
         return x.reshape(-1, self.dim)
 
 
+class _GradBufferFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, layer):
+        ctx.layer = layer
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        layer = ctx.layer
+        site, rt = layer.qG, layer.qG.runtime
+        g = _to_mem(dy).contiguous()                    # TF layout: [batch, ...]
+        n_outer = layer.buffer.shape[0]
+        n_inner = layer.buffer.numel() // n_outer
+        if g.shape[0] > n_outer or g.numel() // max(1, g.shape[0]) != n_inner:
+            raise _lib.LbtError('GradientBuffer_q: gradient %s does not fit the buffer %s' % (tuple(g.shape), tuple(layer.buffer.shape)))
+        out = torch.empty_like(g)
+        if rt.noise_fn is not None:
+            mode, noise, dev_step = Q.ROUND_NOISE, rt.noise_fn(site, n_inner, g.device).contiguous(), None
+        else:
+            mode, noise, dev_step = Q.ROUND_PHILOX, None, rt.dev_step
+        _lib.call('lbt_quantize_residual', _lib.ptr(g), g.shape[0], _lib.ptr(layer.buffer), n_outer, n_inner, site.bits,
+                  _lib.ptr(site.range), mode, _lib.ptr(noise), rt.seed, Q.make_offset(site.qid, 0), _lib.ptr(dev_step),
+                  _lib.ptr(out), _lib.ptr(site.counters), _lib.stream(), meta=dict(bytes=n_outer * n_inner * 16))
+        return _from_mem(out), None
+
+
+class GradientBuffer_q(nn.Module):
+    """dfxp:473-509: error-feedback gradient quantiser.  Identity forward; backward quantises ``grad + buffer``
+    (stochastic) and keeps the rounding residual in ``buffer`` for the next step (one pass: lbt_quantize_residual).
+    ``shape`` is the gradient's shape in the reference's layout ([batch, H, W, C] or [batch, features]); a shorter
+    last batch is zero-padded along dim 0 (dfxp:495-499) and the result sliced back (dfxp:506)."""
+
+    def __init__(self, bits, shape, *, target_overflow_rate=0.0, grad_range=2, name='grad_buffer', runtime=None):
+        super().__init__()
+        rt = runtime or default_runtime()
+        self.bits, self.name = bits, name
+        self.register_buffer('buffer', torch.zeros(*shape))                                    # dfxp:490-491
+        self.qG = QuantSite(rt, name + '/grad', bits, grad_range, target_overflow_rate)          # dfxp:492-493
+
+    def forward(self, x):
+        return _GradBufferFn.apply(x, self)
+
+    def info(self):
+        return 'Gradient buffer'
+
+
 class Sequential_q(nn.Sequential):
     """dfxp:512-536."""
 

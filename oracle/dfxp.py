@@ -618,6 +618,31 @@ class Dropout_q(Layer_q):
         return self.y.detach()
 
 
+class GradientBuffer_q(Layer_q):
+    """dfxp:473-509: quantise ``pad(grad) + buffer`` (always stochastic, :500), keep the residual (:503)."""
+
+    def __init__(self, ctx, bits, shape, target_overflow_rate=0.0, grad_range=2):
+        self.buffer = torch.zeros(*shape)
+        self.qG = Quantizer(ctx, bits, grad_range, target_overflow_rate)
+
+    def forward(self, X):
+        self.X = X
+        self.y = X
+        return X
+
+    def backward(self, grad, stochastic=True):
+        pad = []
+        for have, want in zip(reversed(grad.shape), reversed(self.buffer.shape)):              # :495-498 pads every dim at the end
+            pad += [0, want - have]
+        total = torch.nn.functional.pad(grad, pad) + self.buffer                               # :499
+        gradq = self.qG(total).detach()                                                        # :500
+        self.buffer = total - gradq                                                            # :503
+        return gradq[:grad.shape[0]]                                                           # :506
+
+    def quantizers(self):
+        return [self.qG]
+
+
 class Flatten_q(Layer_q):
     """dfxp:1043-1053."""
 

@@ -219,3 +219,32 @@ def test_plumbing_layers_match_tf_semantics():
     assert torch.equal(d(xg), xg / 0.5 * torch.floor(0.5 + u))
     d.eval()
     assert d(xg) is xg
+
+
+def test_gradient_buffer_error_feedback_bit_exact():
+    """GradientBuffer_q (dfxp:473-509): quantised gradient, residual buffer, counters and range over several
+    steps incl. a short last batch, against the oracle with the same explicit noise."""
+    rng = np.random.default_rng(9)
+    shape = (8, 4, 4, 16)                                                    # reference layout [batch, H, W, C]
+    ctx = O.Context(noise=O.NumpyNoise(3))
+    ol = O.GradientBuffer_q(ctx, 8, shape)
+    rt = D.Runtime(seed=0)
+    pl = D.GradientBuffer_q(8, shape, runtime=rt).cuda()
+    noises = {}
+    rt.noise_fn = lambda site, n_inner, dev: noises['u'].to(dev)
+    rt.finalize('cuda')
+    for step, batch in enumerate([8, 8, 5, 8]):
+        g = (rng.standard_normal((batch,) + shape[1:]) * (0.05 if step else 3.0)).astype(np.float32)
+        want = ol.backward(torch.from_numpy(g))
+        noises['u'] = torch.from_numpy(np.ascontiguousarray(ol.qG.last_noise).reshape(-1))
+        x = torch.zeros(batch, shape[3], shape[1], shape[2], device='cuda').contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        y = pl(x)
+        y.backward(torch.from_numpy(g).cuda().permute(0, 3, 1, 2))
+        got = x.grad.permute(0, 2, 3, 1).contiguous().cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), want.numpy().view(np.uint32)), step
+        assert np.array_equal(pl.buffer.cpu().numpy().view(np.uint32), ol.buffer.numpy().view(np.uint32)), step
+        n1, n2, numel = ctx.last_counts[ol.qG.qid]
+        c = pl.qG.counters.cpu().tolist()
+        assert c[:3] == [n1, n2, numel] and numel == int(np.prod(shape))
+        rt.update_ranges()
+        assert int(pl.qG.range) == int(ol.qG.range), step

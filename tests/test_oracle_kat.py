@@ -69,3 +69,28 @@ def test_overflow_rate_uses_raw_input():
     assert (n1, n2) == (2, 5)            # >=L: 4.0 ; <-L: -4.0001 ; half: 3.99,4.0,2.0 ; -4.0,-4.0001
     r1, r2 = O.overflow_rate(x, 8, 2)
     assert r1 == np.float32(2) / np.float32(6) and r2 == np.float32(5) / np.float32(6)
+
+
+def test_gradient_buffer_known_answer():
+    """GradientBuffer_q (dfxp:473-509) by hand: 8 bits, noise 0.5 everywhere; the range starts at 2 and, with no element
+    reaching half of it, drops by one after every call (dfxp:84-94), so the step is 2^-5, 2^-6, 2^-7.
+    call 1: total 0.01   -> floor(0.01 * 32 + 0.5) = 0      -> q = 0,     buffer = 0.01
+    call 2: total 0.02   -> floor(0.02 * 64 + 0.5) = 1      -> q = 1/64,  buffer = 0.02 - 1/64 (carried)
+    call 3: a batch of 1 into the 2-row buffer: row 0 = 0.01 + buffer -> floor(1.84 + 0.5) = 2 -> q = 2/128, residual < 0;
+            row 1 is zero padding + its buffer -> floor(0.56 + 0.5) = 1; only row 0 is returned (dfxp:506)."""
+    import torch
+    from oracle import dfxp as O
+    f = np.float32
+    ctx = O.Context(noise=lambda qid, shape: np.full(shape, 0.5, dtype=np.float32))
+    gb = O.GradientBuffer_q(ctx, 8, (2, 1))
+    g = torch.full((2, 1), 0.01)
+    assert gb.backward(g).tolist() == [[0.0], [0.0]]
+    assert gb.buffer.tolist() == [[f(0.01)], [f(0.01)]] and gb.qG.range.value == 1
+    out = gb.backward(g)
+    assert out.tolist() == [[0.015625], [0.015625]] and gb.qG.range.value == 0
+    b2 = f(f(0.01) + f(0.01)) - f(0.015625)
+    assert gb.buffer[0, 0].item() == b2 and b2 > 0
+    out = gb.backward(torch.full((1, 1), 0.01))
+    assert out.tolist() == [[0.015625]] and gb.buffer.shape == (2, 1)
+    assert gb.buffer[0, 0].item() == f(f(0.01) + b2) - f(0.015625) < 0
+    assert gb.buffer[1, 0].item() == b2 - f(0.0078125)
