@@ -262,3 +262,70 @@ class Trainer:
 
     def load(self, path):
         self.load_state_dict(torch.load(path, map_location=self.device))
+
+
+class HostFeeder:
+    """Feeds a (CUDA-graph captured) training step from pinned host batches without stalling the GPU — the device-side
+    replacement of the reference's ``feed_dict`` round trip (trainer.py:143-160), where every step waits for its inputs to
+    cross PCIe and for its loss to come back.
+
+    The next batch is copied host -> device on a copy stream into one of two staging buffers while the current step runs;
+    at step start a device-to-device copy moves it into the step's static input tensors.  Each step's loss is copied back to
+    pinned host memory asynchronously and read one step later, so every step still does its own H2D input copy and its own
+    D2H loss read, but neither sits on the critical path.
+
+        feeder = HostFeeder(run_step, X_static, y_static)     # run_step() -> loss tensor (e.g. graph.replay + static loss)
+        feeder.prefetch(hX0, hy0)
+        for i in range(n):
+            if i + 1 < n: feeder.prefetch(hX[i + 1], hy[i + 1])
+            prev_loss = feeder.step()                           # python float of step i-1 (None for i == 0)
+        last_loss = feeder.drain()
+    """
+
+    def __init__(self, run_step, X_static, y_static):
+        self.run_step, self.Xs, self.ys = run_step, X_static, y_static
+        dev = X_static.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.stage = [(torch.empty_like(X_static), torch.empty_like(y_static)) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_done = [torch.cuda.Event() for _ in range(2)]
+        self.fill, self.take, self.pending = 0, 0, None
+        cur = torch.cuda.current_stream(dev)
+        for e in self.consumed:
+            e.record(cur)
+
+    def prefetch(self, hX, hy):
+        """Start the host -> device copy of the NEXT batch (pinned tensors shaped like the static inputs)."""
+        s = self.fill
+        self.fill ^= 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[s])          # the step that last used this buffer has taken its data
+            self.stage[s][0].copy_(hX, non_blocking=True)
+            self.stage[s][1].copy_(hy, non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+
+    def step(self):
+        """Run one step on the oldest prefetched batch; returns the PREVIOUS step's loss (float) or None."""
+        s = self.take
+        self.take ^= 1
+        cur = torch.cuda.current_stream(self.Xs.device)
+        cur.wait_event(self.ready[s])
+        self.Xs.copy_(self.stage[s][0], non_blocking=True)         # device to device, a few microseconds
+        self.ys.copy_(self.stage[s][1], non_blocking=True)
+        self.consumed[s].record(cur)
+        loss = self.run_step()
+        self.loss_host[s].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.loss_done[s].record(cur)
+        prev = self.drain()
+        self.pending = s
+        return prev
+
+    def drain(self):
+        """Wait for and return the loss of the last step issued (None if there is none outstanding)."""
+        if self.pending is None:
+            return None
+        s, self.pending = self.pending, None
+        self.loss_done[s].synchronize()
+        return float(self.loss_host[s])

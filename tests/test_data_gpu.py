@@ -114,3 +114,26 @@ def test_fit_epoch_loop_lr_schedule():
     assert len(hist) == 3 and all(np.isfinite(h[1]) and 0 <= h[3] <= 1 for h in hist)
     assert abs(tr.lr - 1e-4) < 1e-12 and abs(float(tr.dev_lr) - 1e-4) < 1e-10
     assert int(pm.runtime.dev_step) == 9 and len(logs) == 3
+
+
+def test_host_feeder_matches_plain_loop():
+    """HostFeeder (prefetched H2D, lagged D2H loss) runs the same steps as the synchronous feed loop."""
+    from lbt_b200.trainer import HostFeeder
+    rng = np.random.default_rng(6)
+    hX = [torch.from_numpy((rng.standard_normal((16, 32, 32, 3)) * 0.5).astype(np.float32)).pin_memory() for _ in range(5)]
+    hy = [torch.from_numpy(rng.integers(0, 10, 16)).pin_memory() for _ in range(5)]
+    pm, tr = _trainer()
+    want = [float(tr.step(x.cuda().permute(0, 3, 1, 2), y.cuda())) for x, y in zip(hX, hy)]
+    pm2, tr2 = _trainer()
+    Xs = torch.empty(16, 32, 32, 3, device='cuda')
+    ys = torch.empty(16, dtype=torch.int64, device='cuda')
+    feeder = HostFeeder(lambda: tr2.step(Xs.permute(0, 3, 1, 2), ys), Xs, ys)
+    got = []
+    feeder.prefetch(hX[0], hy[0])
+    for i in range(5):
+        if i + 1 < 5:
+            feeder.prefetch(hX[i + 1], hy[i + 1])
+        got.append(feeder.step())
+    got.append(feeder.drain())
+    assert got[0] is None and got[1:] == want
+    assert torch.equal(tr2.flat_w.view(torch.int32), tr.flat_w.view(torch.int32))
