@@ -16,7 +16,7 @@ wt = torch.zeros(Cout, dfxp._pitch16(Kf), dtype=torch.int8, device='cuda')[:, :K
 wt.copy_(torch.randint(-128, 128, (Cout, Kf), dtype=torch.int8, device='cuda'))
 ib = torch.tensor(2, dtype=torch.int32, device='cuda')
 y = torch.empty(N * OH * OW, Cout, dtype=torch.float32, device='cuda')
-dbg = torch.zeros(32, dtype=torch.int64, device='cuda')
+dbg = torch.zeros(64, dtype=torch.int64, device='cuda')
 run = lambda: dfxp._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, s, s, pt, pl, OH, OW, ib, ib, -15, None, y)
 for _ in range(3):
     run()
@@ -33,6 +33,9 @@ names = {0: 'kernel start', 1: 'prologue done', 2: 'load st0 issued', 3: 'load s
          7: 'load st5+', 8: 'mma st0 full', 9: 'mma st1', 10: 'mma st2', 11: 'mma st3', 12: 'mma st4', 13: 'mma st5+',
          14: 'mma tile committed', 15: 'epi got acc', 16: 'epi tile done', 17: 'all warps done', 18: 'tmem freed'}
 print('event time %.1f us' % (a.elapsed_time(b) * 1e3))
+t[0] = t[0] or t[1]
+for base, nm in ((44, 'loader issued tile'), (32, 'mma full tile'), (20, 'epilogue done tile')):
+    print(nm, ' '.join('%.2f' % ((t[base + i] - t[0]) / 1e3) for i in range(10) if t[base + i]))
 for i in sorted(names):
     if t[i]:
         print('%-22s +%7.2f us' % (names[i], (t[i] - t[0]) / 1e3))

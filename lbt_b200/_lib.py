@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblbt_b200.so')
+LIB_PATH = os.environ.get('LBT_LIB') or os.path.join(_HERE, 'liblbt_b200.so')       # LBT_LIB: an experimental build of the same ABI
 
 c_void_p, c_int, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
 c_u64, c_char_p = ctypes.c_uint64, ctypes.c_char_p
@@ -85,8 +85,10 @@ _INTERNAL = {
     'lbt_conv_debug_error': (c_int, []),
     'lbt_conv_ldg_debug_error': (c_int, []),
     'lbt_conv_set_path': (c_int, [c_int]),
+    'lbt_conv_set_halo': (c_int, [c_int]),
     'lbt_gemm_set_pair': (c_int, [c_int]),
     'lbt_set_pdl': (c_int, [c_int]),
+    'lbt_set_carveout': (c_int, [c_int]),
     'lbt_test_fdiv': (c_int, [c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
     'lbt_bn_set_debug': (c_int, [c_void_p]),
     'lbt_conv_ldg_set_debug': (c_int, [c_void_p]),

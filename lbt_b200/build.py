@@ -13,12 +13,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT = os.path.join(HERE, 'liblbt_b200.so')
-OBJ = os.path.join(HERE, 'build')
+OUT = os.environ.get('LBT_BUILD_OUT') or os.path.join(HERE, 'liblbt_b200.so')      # experiments: a second library with other -D flags
+OBJ = os.path.join(HERE, 'build' + os.environ.get('LBT_BUILD_TAG', ''))
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC,-O2', '--expt-relaxed-constexpr', '-Xptxas', '-v',
-         '-I' + os.path.join(os.path.dirname(HERE), 'include')]
+         '-I' + os.path.join(os.path.dirname(HERE), 'include')] + os.environ.get('LBT_NVCC_DEFS', '').split()
 
 
 def sources():

@@ -1,13 +1,34 @@
 // Library-level entry points of liblbt_b200: version, error strings, device check, launch counter.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 
 namespace lbt {
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_pdl{1};
+std::atomic<int> g_carveout{-2};   // -2: not initialised (reads LBT_CARVEOUT on first use)
+
+void apply_carveout(const void* kernel) {
+  int c = g_carveout.load(std::memory_order_relaxed);
+  if (c == -2) {
+    const char* e = std::getenv("LBT_CARVEOUT");
+    c = e ? std::atoi(e) : -1;
+    g_carveout.store(c, std::memory_order_relaxed);
+  }
+  if (c < 0) return;
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> done;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find(kernel);
+  if (it != done.end() && it->second == c) return;
+  (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, c > 100 ? 100 : c);
+  (void)cudaGetLastError();
+  done[kernel] = c;
+}
 
 namespace {
 thread_local std::string t_last_error;
@@ -59,6 +80,12 @@ extern "C" const char* lbt_strerror(int status) {
 extern "C" const char* lbt_last_cuda_error(void) { return lbt::t_last_error.c_str(); }
 
 extern "C" uint64_t lbt_launch_count(void) { return lbt::g_launches.load(std::memory_order_relaxed); }
+
+// Bench / test knob (not in lbt.h): shared-memory carveout percent for all launch_pdl kernels, -1 = driver default.
+extern "C" int lbt_set_carveout(int percent) {
+  lbt::g_carveout.store(percent < 0 ? -1 : percent, std::memory_order_relaxed);
+  return LBT_OK;
+}
 
 // Bench / test knob (not in lbt.h): 0 = plain stream-ordered launches, 1 (default) = programmatic dependent launch.
 extern "C" int lbt_set_pdl(int on) {

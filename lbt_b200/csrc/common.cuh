@@ -39,9 +39,15 @@ inline int check_launch(const char* where) {
 // blocks at pdl_wait() — before its first global-memory access — until N has completed and flushed.  Captured into the
 // step's CUDA graph as programmatic edges.  lbt_set_pdl(0) turns the attribute off (plain stream order).
 extern std::atomic<int> g_pdl;
+// Shared-memory carveout preference (percent, -1 = leave the driver's heuristic) applied to every kernel launched through
+// launch_pdl: consecutive kernels that want different L1 / shared-memory splits force the SM to drain and reconfigure
+// between them, and cannot overlap under programmatic dependent launch.  lbt_set_carveout() / LBT_CARVEOUT.
+extern std::atomic<int> g_carveout;
+void apply_carveout(const void* kernel);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  apply_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -69,6 +69,12 @@ struct LdgParams {
   uint32_t idesc;
   BnqParams bnq;
   unsigned long long* dbg;       // optional timeline of CTA 0 (globaltimer ns), see lbt_conv_ldg_set_debug
+  // halo mode (stride-1 gather 0): an M tile is an 8-wide x 16-high patch of output pixels of ONE image
+  uint32_t OH, n_img;
+  uint32_t halo_w, halo_px;      // 8 + kw - 1, halo_w * (16 + kh - 1)
+  uint32_t halo_plane;           // bytes of one 16-channel plane of the halo: halo_px * 16
+  uint32_t stage_bytes;          // ring slot: kStageBytes (gather modes) / CPP planes + slack (halo mode)
+  FastDiv d_tiles_img, d_tiles_x;
 };
 
 __device__ __forceinline__ void dbg_stamp(const LdgParams& p, int slot) {
@@ -91,7 +97,19 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int BN, int CPP>   // CPP = C / 16: 16-byte chunks per pixel
+// Shared-memory descriptor of a K-major, un-swizzled operand with explicit strides: `lbo` between the two 16-byte K chunks
+// of an instruction, `sbo` between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_k16(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+
+// HALO = true (stride-1 convolutions on images of at least ~8 x 16 output pixels): instead of gathering the im2col rows of a
+// tile — every input pixel crosses L2 -> shared memory kh*kw times, which is what bounds the gather path — the loaders copy the
+// (16 + kh - 1) x (8 + kw - 1) input patch under an 8 x 16 output patch ONCE ([C/16 planes][halo pixels][16 B]), and the MMA
+// descriptors walk it: the 8 rows of a core matrix are 8 neighbouring pixels of an output row (16-byte pitch), consecutive
+// 8-row groups are halo rows (stride halo_w * 16 B), and a filter tap is just a different start address.
+template <int BN, int CPP, bool HALO>   // CPP = C / 16: 16-byte chunks per pixel
 __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -106,6 +124,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   __shared__ int s_stat[kEpiWarps][2 * BN];
   __shared__ unsigned long long s_tot[2 * BN];   // CTA totals of the fused statistics
   __shared__ int2 s_tab[kMaxKC + 8];       // tap slot: {byte offset from the row's base pixel, tap code}
+  __shared__ uint2 s_mma[HALO ? kMaxKC / 2 : 1];   // halo mode, MMA j: {A start offset in the stage, leading byte offset}
 
   constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < p.nstages; ++s) {
-      mbar_init(&full_bar[s], kLoaderWarps * 32);
+      mbar_init(&full_bar[s], HALO ? 32 : kLoaderWarps * 32);   // halo mode: one loader warp fills a slot
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -130,13 +149,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   // gather table, one entry per tap slot: source of (row, slot) = base(row) + x, valid iff bit y of the row's tap mask;
   // y == 255: zero chunk (K padding), y == 254: beyond the tile's chunks (nothing to copy)
   constexpr int TPS = kChunksPerStage / CPP;  // tap slots per pipeline stage
-  for (uint32_t ts = threadIdx.x; ts < p.stages_per_tile * TPS; ts += kThreads) {
+  for (uint32_t ts = threadIdx.x; !HALO && ts < p.stages_per_tile * TPS; ts += kThreads) {
     const int r = (int)(ts / p.kw), sx = (int)(ts % p.kw);
     int d;
     if (p.gather == 0) d = (r * (int)p.SW + sx) * (int)p.C;
     else d = -((r / p.sh) * (int)p.SW + (sx / p.sw)) * (int)p.C;
     const int code = ts < p.taps ? (int)ts : (ts * CPP < p.KCp ? 255 : 254);
     s_tab[ts] = make_int2(ts < p.taps ? d : 0, code);
+  }
+  if (HALO) {   // s_tab[hp] = (row, column) of halo pixel hp; s_tab is big enough for 5x5 filters (20 x 12 halo)
+    for (uint32_t hp = threadIdx.x; hp < p.halo_px; hp += kThreads) s_tab[hp] = make_int2((int)(hp / p.halo_w), (int)(hp % p.halo_w));
+    for (uint32_t j = threadIdx.x; j < (p.KCp >> 1); j += kThreads) {
+      const uint32_t kc = 2 * j, tap = kc / CPP;   // K chunk = tap * CPP + cc
+      const uint32_t r = tap / p.kw, sx = tap - r * p.kw;
+      uint32_t lbo = p.halo_plane;
+      if (CPP == 1) {   // the instruction's second chunk is the NEXT tap (or, past the last one, anything: zero weights)
+        const uint32_t t1 = tap + 1 < p.taps ? tap + 1 : tap, r1 = t1 / p.kw, s1 = t1 - r1 * p.kw;
+        lbo = t1 > tap ? ((r1 * p.halo_w + s1) - (r * p.halo_w + sx)) * 16 : 16;
+      }
+      s_mma[j] = make_uint2((kc % CPP) * p.halo_plane + (r * p.halo_w + sx) * 16, lbo);
+    }
   }
   pdl_trigger();
   fence_before();
@@ -147,7 +179,34 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   volatile int* abort_flag = &s_abort;
   if (threadIdx.x == 0) dbg_stamp(p, 1);
 
-  if (warp < kLoaderWarps) {
+  if (HALO && warp < kLoaderWarps) {
+    // ===== halo loaders: the input patch of a tile, each 16-byte chunk exactly once (zero-fill outside the image).  A loader
+    // warp completes one ring slot per memory round trip (measured: ~0.8 us per tile whatever the copy count), so each of the
+    // four warps loads WHOLE tiles, round robin: four patches are in flight per CTA =====
+    bool ok = true;
+    uint32_t seq = warp;                          // this warp's tiles: sequence numbers warp, warp + 4, ...
+    for (uint32_t tile = blockIdx.x + warp * gridDim.x; tile < p.m_tiles && ok; tile += kLoaderWarps * gridDim.x, seq += kLoaderWarps) {
+      const uint32_t stage = seq % p.nstages, phase = (seq / p.nstages) & 1u;
+      const uint32_t img = fastdiv(tile, p.d_tiles_img), t2 = tile - img * p.d_tiles_img.d;
+      const uint32_t ty = fastdiv(t2, p.d_tiles_x), tx = t2 - ty * p.d_tiles_x.d;
+      const int y0 = (int)(ty * 16) - p.pt, x0 = (int)(tx * 8) - p.pl;
+      const uint8_t* ibase = p.src + (size_t)img * p.SH * p.SW * p.C;
+      ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_ldg_error);
+      if (!ok) break;
+      const uint32_t dst0 = smem_u32(sA + (size_t)stage * p.stage_bytes);
+      for (uint32_t idx = lane; idx < p.halo_px * CPP; idx += 32) {
+        const uint32_t hp = idx / CPP, cc = idx % CPP;
+        const int2 yx = s_tab[hp];
+        const int iy = y0 + yx.x, ix = x0 + yx.y;
+        const bool v = iy >= 0 && iy < (int)p.SH && ix >= 0 && ix < (int)p.SW;
+        cp_async16(dst0 + cc * p.halo_plane + hp * 16, v ? ibase + ((size_t)iy * p.SW + ix) * p.C + cc * 16 : p.src, v ? 16u : 0u);
+      }
+      cp_async_arrive_noinc(&full_bar[stage]);
+      if (threadIdx.x == 0 && tile == blockIdx.x) dbg_stamp(p, 2);
+      if (p.dbg && lane == 0 && seq < 10) dbg_stamp(p, 44 + seq);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < kLoaderWarps) {
     // ===== loaders: one warp instruction copies 32/CPP consecutive pixels x C bytes (512 contiguous bytes when the
     // pixels are neighbours in memory); a thread serves CPP rows of the tile and always the same 16-byte chunk cc =====
     constexpr int RPI = 32 / CPP;  // rows per instruction
@@ -236,7 +295,26 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
         fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t first = 1;
-        for (uint32_t st = 0; st < p.stages_per_tile; ++st) {
+        if (HALO) {
+          if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_ldg_error))) break;
+          fence_after();
+          if (tile == blockIdx.x) dbg_stamp(p, 8);
+          if (p.dbg && blockIdx.x == 0 && tile / gridDim.x < 10) dbg_stamp(p, 32 + tile / gridDim.x);
+          const uint32_t sa = smem_u32(sA + (size_t)stage * p.stage_bytes);
+          const uint32_t sbo = p.halo_w * 16;
+          for (uint32_t j = 0; j < (p.KCp >> 1); ++j) {
+            const uint2 t = s_mma[j];
+            umma_i8(d_tmem, make_desc_k16(sa + t.x, t.y, sbo), make_desc_kmajor(sb0 + 2 * j * (BN * 16), 0, BN * 16), p.idesc,
+                    first ? 0u : 1u);
+            first = 0;
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        for (uint32_t st = 0; !HALO && st < p.stages_per_tile; ++st) {
           if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_ldg_error))) break;
           fence_after();
           if (tile == blockIdx.x) dbg_stamp(p, 8 + (st < 5 ? st : 5));
@@ -304,8 +382,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       if (!ok) break;
       fence_after();
       if (threadIdx.x == 32 * (kLoaderWarps + 1) && tile == blockIdx.x) dbg_stamp(p, 15);
-      const uint32_t row = tile * kBlockM + quad * 32 + lane;
-      const uint32_t pix = fused ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
+      uint32_t row, pix;
+      bool rvalid;
+      if (HALO) {   // accumulator row m = 8 * (row of the patch) + column of the patch
+        const uint32_t m = quad * 32 + lane;
+        const uint32_t img = fastdiv(tile, p.d_tiles_img), t2 = tile - img * p.d_tiles_img.d;
+        const uint32_t ty = fastdiv(t2, p.d_tiles_x), tx = t2 - ty * p.d_tiles_x.d;
+        const uint32_t oy = ty * 16 + (m >> 3), ox = tx * 8 + (m & 7);
+        rvalid = oy < p.OH && ox < p.OW;
+        pix = oy * p.OW + ox;
+        row = img * p.OHW + pix;
+      } else {
+        row = tile * kBlockM + quad * 32 + lane;
+        pix = fused ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
+        rvalid = row < p.M;
+      }
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
       if (fused && bst.tiles >= (uint32_t)kBnqFlushTiles) {
         bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
@@ -334,8 +425,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
               if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + c + j));
           }
           if (fused) {
-            bnq_chunk(p.bnq, bst, f, row, pix, row < p.M, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
-          } else if (row < p.M) {
+            bnq_chunk(p.bnq, bst, f, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+          } else if (rvalid) {
             float* o = p.out + (size_t)row * p.ldc + c;
             if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
             const float* ad = p.addend + (o - p.out);
@@ -371,6 +462,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (threadIdx.x == 32 * (kLoaderWarps + 1) && tile == blockIdx.x) dbg_stamp(p, 16);
+      if (p.dbg && (warp & 3) == ((kLoaderWarps + 1) & 3) && lane == 0 && tcount < 10) dbg_stamp(p, 20 + tcount);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -390,28 +482,35 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   if (threadIdx.x == 32 * kLoaderWarps) dbg_stamp(p, 18);
 }
 
-template <int BN, int CPP>
+template <int BN, int CPP, bool HALO>
 int launch_ldg2(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
   static size_t attr_smem[16] = {};
   const int dev = device_info().device;
   if (attr_smem[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_ldg_kernel)");
       return LBT_ECUDA;
     }
     attr_smem[dev] = smem;
   }
-  launch_pdl(conv_ldg_kernel<BN, CPP>, grid, kThreads, smem, st, p);
+  launch_pdl(conv_ldg_kernel<BN, CPP, HALO>, grid, kThreads, smem, st, p);
   return check_launch("lbt_conv_i8 (cp.async gather)");
 }
 
 template <int BN>
-int launch_ldg(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+int launch_ldg(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st, bool halo) {
+  if (halo) {
+    switch (p.cpp) {
+      case 1: return launch_ldg2<BN, 1, true>(p, grid, smem, st);
+      case 2: return launch_ldg2<BN, 2, true>(p, grid, smem, st);
+      default: return launch_ldg2<BN, 4, true>(p, grid, smem, st);
+    }
+  }
   switch (p.cpp) {
-    case 1: return launch_ldg2<BN, 1>(p, grid, smem, st);
-    case 2: return launch_ldg2<BN, 2>(p, grid, smem, st);
-    default: return launch_ldg2<BN, 4>(p, grid, smem, st);
+    case 1: return launch_ldg2<BN, 1, false>(p, grid, smem, st);
+    case 2: return launch_ldg2<BN, 2, false>(p, grid, smem, st);
+    default: return launch_ldg2<BN, 4, false>(p, grid, smem, st);
   }
 }
 
@@ -607,10 +706,21 @@ int launch_wgrad_ldg(const WgLdgParams& p, unsigned grid, size_t smem, cudaStrea
 
 
 std::atomic<int> g_use_ldg{1};
+std::atomic<int> g_use_halo{1};   // lbt_conv_set_halo(): 0 = gather the im2col rows even where the halo patch applies
 std::atomic<unsigned long long*> g_dbg{nullptr};
 bool conv_ldg_enabled() { return g_use_ldg.load(std::memory_order_relaxed) != 0; }
+std::atomic<int> g_c64_halo{0};   // measured: ResNet-18's 64-channel layers lose 4 % in the step against the TMA kernel (the microbench gains 15 %)
+int conv_ldg_c64_halo() { return g_c64_halo.load(std::memory_order_relaxed); }
 
 // Shapes this kernel takes.
+// Halo-patch loader: stride-1 gather of a filter up to 5x5 on images that fill 8 x 16 output patches reasonably (<= 35 % of
+// the patch pixels outside the image).
+bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw) {
+  if (!g_use_halo.load(std::memory_order_relaxed) || sh != 1 || sw != 1 || kh > 5 || kw > 5 || kh * kw <= 1) return false;
+  const uint64_t tx = (uint64_t)(OW + 7) / 8, ty = (uint64_t)(OH + 15) / 16;
+  return tx * 8 * ty * 16 * 100 <= (uint64_t)OH * OW * 135 && (uint64_t)N * tx * ty < (1ull << 31);
+}
+
 bool conv_ldg_ok(int C, int Cout, int kh, int kw) {
   if (C != 16 && C != 32 && C != 64) return false;
   if (Cout < 1 || Cout > 128) return false;
@@ -771,24 +881,41 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   p.bnq.sums = reinterpret_cast<long long*>(sums);
   p.bnq.rows_per_image = (uint32_t)(OH * OW);
   p.dbg = g_dbg.load(std::memory_order_relaxed);
+  // halo mode: every input pixel is copied to shared memory ~1.4 times instead of kh * kw times
+  p.OH = (uint32_t)OH;
+  p.n_img = (uint32_t)N;
+  p.stage_bytes = kStageBytes;
+  bool halo = false;
+  if (gather == 0 && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw)) {
+    const uint32_t tx = (uint32_t)(OW + 7) / 8, ty = (uint32_t)(OH + 15) / 16;
+    halo = true;
+    p.halo_w = 8 + (uint32_t)kw - 1;
+    p.halo_px = p.halo_w * (16 + (uint32_t)kh - 1);
+    p.halo_plane = p.halo_px * 16;
+    p.stage_bytes = ((p.cpp * p.halo_plane + 64) + 127) & ~127u;   // + slack: the padding chunk of an odd tap count
+    p.d_tiles_img = make_fastdiv(tx * ty);
+    p.d_tiles_x = make_fastdiv(tx);
+    p.m_tiles = (uint32_t)N * tx * ty;
+    p.stages_per_tile = 1;
+  }
   const size_t b_bytes = (((size_t)p.KCp * bn * 16) + 127) & ~(size_t)127;
   // ring depth: two CTAs per SM when the filter bank is small, else one CTA with a deep ring
   const bool two = b_bytes <= 44 * 1024;
   size_t budget = (two ? 108 * 1024 : 200 * 1024) - b_bytes - 1024;
-  uint32_t nst = (uint32_t)(budget / kStageBytes);
+  uint32_t nst = (uint32_t)(budget / p.stage_bytes);
   if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
   if (nst < 2) return LBT_EUNSUPPORTED;
   p.nstages = nst;
-  const size_t smem = b_bytes + (size_t)nst * kStageBytes + 256;
+  const size_t smem = b_bytes + (size_t)nst * p.stage_bytes + 256;
   const unsigned ctas_per_sm = two ? 2u : 1u;
   const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm;
   const unsigned grid = (unsigned)(p.m_tiles < cap ? p.m_tiles : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (bn) {
-    case 16: return launch_ldg<16>(p, grid, smem, st);
-    case 32: return launch_ldg<32>(p, grid, smem, st);
-    case 64: return launch_ldg<64>(p, grid, smem, st);
-    default: return launch_ldg<128>(p, grid, smem, st);
+    case 16: return launch_ldg<16>(p, grid, smem, st, halo);
+    case 32: return launch_ldg<32>(p, grid, smem, st, halo);
+    case 64: return launch_ldg<64>(p, grid, smem, st, halo);
+    default: return launch_ldg<128>(p, grid, smem, st, halo);
   }
 }
 
@@ -817,6 +944,14 @@ extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int O
 // narrow-channel shapes take the cp.async-gather kernel.
 extern "C" int lbt_conv_set_path(int use_ldg) {
   g_use_ldg.store(use_ldg ? 1 : 0, std::memory_order_relaxed);
+  return LBT_OK;
+}
+
+// Test / bench knob (not in lbt.h): bit 0 = use the halo-patch loader of the gather kernel where it applies; bit 1 = also
+// route 64-channel inputs to it (otherwise they stay on the TMA im2col kernel).  Default 1.
+extern "C" int lbt_conv_set_halo(int mask) {
+  g_use_halo.store(mask & 1, std::memory_order_relaxed);
+  g_c64_halo.store((mask >> 1) & 1, std::memory_order_relaxed);
   return LBT_OK;
 }
 

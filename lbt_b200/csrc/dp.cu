@@ -84,11 +84,13 @@ __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(pad + LBT_DP_PAD_EPOCH) + 1u;
 
   // ---- barrier A: my gradients and counters are final (kernel boundary), tell everybody; wait for everybody ----
-  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
-    __threadfence_system();
-    st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_READY + rank, epoch);
+  if (world > 1) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+      __threadfence_system();
+      st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_READY + rank, epoch);
+    }
+    wait_flags(pad, LBT_DP_PAD_READY, world, epoch);
   }
-  wait_flags(pad, LBT_DP_PAD_READY, world, epoch);
 
   // ---- owned slice: sum the replicas' gradients in rank order, momentum SGD, publish the new weights ----
   const float lr = p.dev_lr ? *p.dev_lr : p.lr;
@@ -153,18 +155,21 @@ __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
   }
 
   // ---- the last CTA to finish runs barrier B and closes the step ----
+  // (bar.sync orders the CTA's accesses before thread 0's fence, which is cumulative: one fence per CTA, not per thread)
   __shared__ uint32_t s_last;
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (world > 1) __threadfence_system(); else __threadfence();
     const uint32_t t = atomicAdd(pad + LBT_DP_PAD_TICKET, 1u);
     s_last = (t == gridDim.x - 1) ? 1u : 0u;
-    __threadfence_system();
+    if (world > 1) __threadfence_system(); else __threadfence();
   }
   __syncthreads();
   if (!s_last) return;
-  if ((int)threadIdx.x < world) st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_DONE + rank, epoch);
-  wait_flags(pad, LBT_DP_PAD_DONE, world, epoch);
+  if (world > 1) {
+    if ((int)threadIdx.x < world) st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_DONE + rank, epoch);
+    wait_flags(pad, LBT_DP_PAD_DONE, world, epoch);
+  }
   unsigned long long* mine = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(pe.counters[rank]));
   for (size_t i = threadIdx.x; i < p.n_sites * LBT_CNT_WORDS; i += blockDim.x) mine[i] = 0ull;
   if (threadIdx.x == 0) {

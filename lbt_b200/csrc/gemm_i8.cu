@@ -29,6 +29,10 @@ constexpr int kUmmaK = 32;    // kind::i8: 32 bytes of K per instruction
 constexpr int kEpiWarps = 8;   // two warps per TMEM lane quadrant, interleaved over the 16-column chunks
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr long long kWatchdogCycles = 4000000000ll;
+#ifndef LBT_SUSPEND_HINT_NS
+#define LBT_SUSPEND_HINT_NS 0
+#endif
+constexpr uint32_t kSuspendHintNs = LBT_SUSPEND_HINT_NS;   // see tcgen05.cuh
 
 __device__ int g_gemm_error = 0;
 
@@ -64,12 +68,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  if (kSuspendHintNs == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+  }
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }

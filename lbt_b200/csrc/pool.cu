@@ -161,14 +161,29 @@ __global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __re
     const int n = (int)fastdiv(t, p.d_OH);
     const int oh = (int)(t - (uint32_t)n * (uint32_t)p.OH);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < p.k; ++r)
-      for (int q = 0; q < p.k; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * p.H + oh * p.s + r) * p.W + ow * p.s + q) * p.C) + c);
-        acc.x = __fadd_rn(acc.x, v.x);
-        acc.y = __fadd_rn(acc.y, v.y);
-        acc.z = __fadd_rn(acc.z, v.z);
-        acc.w = __fadd_rn(acc.w, v.w);
+    // the window is summed in (r, q) order like the oracle; the loads of 16 taps are issued together so a global 8x8
+    // pool costs 4 memory round trips per thread instead of 64
+    const int taps = p.k * p.k;
+    const float* base = x + (((size_t)n * p.H + oh * p.s) * p.W + ow * p.s) * p.C;
+    for (int t0 = 0; t0 < taps; t0 += 16) {
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int t = t0 + j;
+        if (t < taps) {
+          const int r = t / p.k, q = t - r * p.k;
+          v[j] = __ldg(reinterpret_cast<const float4*>(base + ((size_t)r * p.W + q) * p.C) + c);
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (t0 + j < taps) {
+          acc.x = __fadd_rn(acc.x, v[j].x);
+          acc.y = __fadd_rn(acc.y, v[j].y);
+          acc.z = __fadd_rn(acc.z, v[j].z);
+          acc.w = __fadd_rn(acc.w, v[j].w);
+        }
+    }
     const float d = (float)(p.k * p.k);
     reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
   }
@@ -203,13 +218,27 @@ __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const float* __re
 // ONE CTA of 32 warps (the logits are a few hundred KB at most): warp w takes rows w, w+32, ...; p = softmax(logits) is
 // kept for the backward; the mean is summed in a FIXED order (per warp, then over the 32 warps) so the loss is
 // bit-reproducible from run to run.
+constexpr int kXentStage = 8192;   // floats of shared memory: logits of small problems are staged with ONE coalesced pass
+
 __global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C,
                                                         float* __restrict__ probs, float* __restrict__ loss) {
   __shared__ float s_part[32];
+  __shared__ float s_x[kXentStage];
+  __shared__ int s_y[1024];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool staged = (size_t)B * C <= (size_t)kXentStage && B <= 1024;
+  if (staged) {   // one memory round trip for the whole problem instead of four dependent ones per row
+    for (int i = threadIdx.x; i < B * C; i += 1024) s_x[i] = logits[i];
+    if ((int)threadIdx.x < B) {
+      const long long y = labels[threadIdx.x];
+      s_y[threadIdx.x] = (y >= 0 && y < C) ? (int)y : -1;
+    }
+    __syncthreads();
+  }
   float part = 0.f;
   for (int row = warp; row < B; row += 32) {
-    const float* x = logits + (size_t)row * C;
+    const float* x = staged ? s_x + (size_t)row * C : logits + (size_t)row * C;
+    const long long y = staged ? (long long)s_y[row] : labels[row];
     float m = -INFINITY;
     for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -218,7 +247,6 @@ __global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict_
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float ls = logf(s);
     for (int c = lane; c < C; c += 32) probs[(size_t)row * C + c] = expf(x[c] - m - ls);
-    const long long y = labels[row];
     if (y >= 0 && y < C) part += -(x[y] - m - ls);
   }
   if (lane == 0) s_part[warp] = part;

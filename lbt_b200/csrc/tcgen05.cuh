@@ -11,6 +11,12 @@ namespace lbt {
 namespace tc {
 
 constexpr long long kWatchdogCycles = 4000000000ll;  // ~2 s at boost clock
+// Optional suspend-time hint of mbarrier.try_wait (ns).  Measured on B200 (A/B builds, -DLBT_SUSPEND_HINT_NS=4000 vs 0): no
+// effect on the convolution kernels or the training step, -2 % on the 8192^3 GEMM: the default (0 = no hint) stays.
+#ifndef LBT_SUSPEND_HINT_NS
+#define LBT_SUSPEND_HINT_NS 0
+#endif
+constexpr uint32_t kSuspendHintNs = LBT_SUSPEND_HINT_NS;   // 0: plain try_wait (system-default suspend time)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -27,12 +33,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  if (kSuspendHintNs == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+  }
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs)
       : "memory");
   return ok != 0;
 }

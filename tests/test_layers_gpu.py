@@ -248,3 +248,49 @@ def test_gradient_buffer_error_feedback_bit_exact():
         assert c[:3] == [n1, n2, numel] and numel == int(np.prod(shape))
         rt.update_ranges()
         assert int(pl.qG.range) == int(ol.qG.range), step
+
+
+# ---- halo-patch loader of the gather kernel (stride-1 convolutions on large images) vs the im2col-row gather -------------
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,pad', [(3, 32, 32, 16, 16, 3, 1), (2, 56, 56, 32, 64, 3, 1), (2, 16, 16, 32, 32, 3, 1),
+                                                  (2, 24, 40, 64, 64, 5, 2), (2, 32, 32, 16, 32, 3, 0), (1, 64, 48, 64, 128, 3, 1),
+                                                  (5, 32, 32, 16, 16, 1, 0), (2, 30, 30, 16, 16, 3, 2)])
+def test_conv_halo_loader_equals_row_gather(N, H, W, Cin, Cout, k, pad):
+    from lbt_b200 import _lib, quantizer as Q
+    rng = np.random.default_rng(N * H + Cin + k)
+    OH, OW = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x = torch.from_numpy(rng.integers(0, 256, (N, H, W, Cin), dtype=np.uint8)).cuda()
+    Kf = k * k * Cin
+    w = torch.from_numpy(rng.integers(-128, 128, (Cout, Kf), dtype=np.int8))
+    wt = torch.zeros(Cout, D._pitch16(Kf), dtype=torch.int8, device='cuda')[:, :Kf]
+    wt.copy_(w)
+    ib = torch.tensor(1, dtype=torch.int32, device='cuda')
+    bias = torch.randn(Cout, device='cuda')
+    addend = torch.randn(N * OH * OW, Cout, device='cuda')
+    rt = D.Runtime(seed=5)
+    site = D.QuantSite(rt, 'q', 8, 2).cuda()
+    rt.finalize('cuda')
+    res = {}
+    try:
+        for halo in (1, 0):
+            _lib.lib().lbt_conv_set_halo(3 if halo else 0)
+            y = torch.full((N * OH * OW, Cout), float('nan'), device='cuda')
+            D._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, 1, 1, pad, pad, OH, OW, ib, ib, -12, bias, y, addend=addend)
+            k_out = torch.zeros(N * OH * OW, Cout, dtype=torch.int8, device='cuda')
+            sums = torch.zeros(2 * Cout, dtype=torch.int64, device='cuda')
+            site.counters.zero_()
+            qs = site.abi(OH * OW * Cout, 'cuda')
+            D._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, 1, 1, pad, pad, OH, OW, ib, ib, -12, None, None, bnq=(qs, k_out, sums))
+            torch.cuda.synchronize()
+            res[halo] = (y, k_out, sums, site.counters.clone())
+    finally:
+        _lib.lib().lbt_conv_set_halo(1)
+    assert _lib.lib().lbt_conv_ldg_debug_error() == 0
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+    # and against the exact convolution (fp64): RN_fp32(exact * 2^e) + bias + addend
+    xe = x.double().permute(0, 3, 1, 2)
+    we = w.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2).cuda()
+    ref = F.conv2d(xe, we, padding=pad).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
+    want = ((ref * 2.0 ** (-12 + 2)).float() + bias) + addend
+    assert torch.equal(res[1][0], want)
