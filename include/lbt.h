@@ -509,6 +509,31 @@ int lbt_quantize_residual(const float* grad, size_t n_grad_rows, float* buffer, 
                           int32_t* integer_bits, int mode, const float* noise, uint64_t seed, uint64_t offset,
                           const uint64_t* dev_step, float* out, uint64_t* counters, void* stream);
 
+/*
+ * Stride-1 input gradient of a convolution whose INPUT was produced by a fused batch-norm unit, with that batch-norm's
+ * backward pass 1 (lbt_bn_bwd_quant_stats) run in the epilogue: the fp32 gradient dX = conv(g, rot180(W)) is never written;
+ * instead, per element, the ReLU mask is recomputed from k2 (relu = 1) or skipped (0), kg2 = Q_g2(dX) (dfxp:687),
+ * dx2 = gq2 * gamma_q (:691), kg1 = Q_g1(dx2) (:621) is stored, and sums[0..C) += kg2, [C..2C) += kg2*k2, [2C..3C) += kg1,
+ * [3C..4C) += kg1*k1 (C = Cout of this call = the batch-norm's channels; caller-zeroed).  Same quantiser ids, noise streams,
+ * counters and arithmetic as the two separate launches: bit-identical.  g[N,H,W,C] gradient mantissas of the convolution's
+ * output; wp: filter packed for the transposed convolution as for lbt_conv_i8_fprop; OH x OW: the convolution's input grid.
+ * Narrow-channel shapes only (LBT_EUNSUPPORTED otherwise: run lbt_conv_i8_fprop + lbt_bn_bwd_quant_stats).
+ */
+typedef struct lbt_bn_bwd_link {
+  lbt_qsite q_g2, q_g1;      /* Rescale_q / Normalization_q gradient quantisers */
+  int32_t bits2, relu;       /* Rescale_q input quantiser bits; ReLU: 0 none, 1 recomputed from k2 */
+  const int32_t* ib2;
+  const float* gamma_q;      /* [C] fake-quantised gamma / beta (16-byte aligned) */
+  const float* beta_q;
+  const int8_t* k2;          /* [N*OH*OW, C] saved forward mantissas */
+  const int8_t* k1;
+  int8_t* kg1;               /* [N*OH*OW, C] out */
+  int64_t* sums;             /* [4*C] out */
+} lbt_bn_bwd_link;
+int lbt_conv_i8_dgrad_bn(const void* g, int g_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout,
+                         int kh, int kw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_g, const int32_t* ib_w,
+                         int exp_const, const lbt_bn_bwd_link* link, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ SIGNATURES = {
     'lbt_dp_export': (c_int, [c_void_p, c_void_p, c_void_p]),
     'lbt_dp_open': (c_int, [c_void_p, c_void_p]),
     'lbt_dp_close': (c_int, [c_void_p]),
+    'lbt_conv_i8_dgrad_bn': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_size_t] + [c_int] * 7 +
+                             [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'lbt_quantize_residual': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_int, c_void_p, c_u64,
                                       c_u64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'lbt_augment_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_u64, c_u64,
@@ -109,6 +111,12 @@ class QSiteStruct(ctypes.Structure):
     """lbt_qsite (include/lbt.h): one quantiser call site as the fused kernels see it."""
     _fields_ = [('bits', ctypes.c_int32), ('stats_minmax', ctypes.c_int32), ('ib', c_void_p), ('noise', c_void_p),
                 ('seed', c_u64), ('offset', c_u64), ('dev_step', c_void_p), ('counters', c_void_p)]
+
+
+class BnBwdLink(ctypes.Structure):
+    """lbt_bn_bwd_link (include/lbt.h)."""
+    _fields_ = [('q_g2', QSiteStruct), ('q_g1', QSiteStruct), ('bits2', ctypes.c_int32), ('relu', ctypes.c_int32), ('ib2', c_void_p),
+                ('gamma_q', c_void_p), ('beta_q', c_void_p), ('k2', c_void_p), ('k1', c_void_p), ('kg1', c_void_p), ('sums', c_void_p)]
 
 
 class BnBwdArgs(ctypes.Structure):

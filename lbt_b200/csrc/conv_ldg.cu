@@ -68,6 +68,7 @@ struct LdgParams {
   size_t ldc;
   uint32_t idesc;
   BnqParams bnq;
+  GqParams gq;                   // fused "BN backward pass 1" epilogue (gq.g2.bits == 0: off); excludes bnq
   unsigned long long* dbg;       // optional timeline of CTA 0 (globaltimer ns), see lbt_conv_ldg_set_debug
   // halo mode (stride-1 gather 0): an M tile is an 8-wide x 16-high patch of output pixels of ONE image
   uint32_t OH, n_img;
@@ -109,7 +110,7 @@ __device__ __forceinline__ uint64_t make_desc_k16(uint32_t smem_addr, uint32_t l
 // (16 + kh - 1) x (8 + kw - 1) input patch under an 8 x 16 output patch ONCE ([C/16 planes][halo pixels][16 B]), and the MMA
 // descriptors walk it: the 8 rows of a core matrix are 8 neighbouring pixels of an output row (16-byte pitch), consecutive
 // 8-row groups are halo rows (stride halo_w * 16 B), and a filter tap is just a different start address.
-template <int BN, int CPP, bool HALO>   // CPP = C / 16: 16-byte chunks per pixel
+template <int BN, int CPP, bool HALO, bool GQ>   // CPP = C / 16: 16-byte chunks per pixel; GQ: the fused BN-backward epilogue
 __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -121,8 +122,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   __shared__ __align__(8) uint64_t b_bar;   // the resident filter bank has landed
   __shared__ uint32_t tmem_slot;
   __shared__ int s_abort;
-  __shared__ int s_stat[kEpiWarps][2 * BN];
-  __shared__ unsigned long long s_tot[2 * BN];   // CTA totals of the fused statistics
+  constexpr int kStats = GQ ? 4 : 2;             // per-channel sums of the fused epilogue: bnq 2, gq 4
+  __shared__ int s_stat[kEpiWarps][kStats * BN];
+  __shared__ unsigned long long s_tot[kStats * BN];   // CTA totals of the fused statistics
   __shared__ int2 s_tab[kMaxKC + 8];       // tap slot: {byte offset from the row's base pixel, tap code}
   __shared__ uint2 s_mma[HALO ? kMaxKC / 2 : 1];   // halo mode, MMA j: {A start offset in the stage, leading byte offset}
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     fence_barrier_init();
   }
   if (warp == kLoaderWarps) tmem_alloc(&tmem_slot, kTmemCols);
-  for (uint32_t i = threadIdx.x; i < 2 * BN; i += kThreads) s_tot[i] = 0ull;
+  for (uint32_t i = threadIdx.x; i < kStats * BN; i += kThreads) s_tot[i] = 0ull;
   // gather table, one entry per tap slot: source of (row, slot) = base(row) + x, valid iff bit y of the row's tap mask;
   // y == 255: zero chunk (K padding), y == 254: beyond the tile's chunks (nothing to copy)
   constexpr int TPS = kChunksPerStage / CPP;  // tap slots per pipeline stage
@@ -357,13 +359,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
-    const bool fused = p.bnq.q.bits != 0;
+    const bool fused = !GQ && p.bnq.q.bits != 0;
+    const bool fusedg = GQ;
     int* my_stat = s_stat[warp - (kLoaderWarps + 1)];
     BnqState bst;
+    GqState gst;
     bst.tiles = 0;
-    if (fused) {
-      bst.init(p.bnq);
-      for (int i = lane; i < 2 * BN; i += 32) my_stat[i] = 0;
+    if (fused) bst.init(p.bnq);
+    if (fusedg) gst.init(p.gq);
+    if (fused || fusedg) {
+      for (int i = lane; i < kStats * BN; i += 32) my_stat[i] = 0;
       __syncwarp();
     }
     uint32_t acc = 0, acc_phase = 0, tcount = 0;
@@ -377,11 +382,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
         }
         continue;
       }
-      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_ldg_error);
-      ok = __all_sync(0xffffffffu, ok);
-      if (!ok) break;
-      fence_after();
-      if (threadIdx.x == 32 * (kLoaderWarps + 1) && tile == blockIdx.x) dbg_stamp(p, 15);
       uint32_t row, pix;
       bool rvalid;
       if (HALO) {   // accumulator row m = 8 * (row of the patch) + column of the patch
@@ -394,19 +394,41 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
         row = img * p.OHW + pix;
       } else {
         row = tile * kBlockM + quad * 32 + lane;
-        pix = fused ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
+        pix = (fused || fusedg) ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
         rvalid = row < p.M;
       }
+      constexpr int G = BN < 32 ? BN : 32;  // columns fetched from tensor memory per wait
+      constexpr bool kSplit = BN > G;       // wide tiles: both warps of a quadrant alternate the G-column groups
+      // fused BN-backward epilogue: the saved mantissas of this warp's FIRST column group are fetched before the wait
+      uint32_t pw2[GQ ? G / 16 : 1][4], pw1[GQ ? G / 16 : 1][4];
+      if constexpr (GQ) {
+        const int cf = kSplit ? G * (int)half : 0;
+#pragma unroll
+        for (int q = 0; q < G / 16; ++q) {
+          const uint32_t c = (uint32_t)(cf + 16 * q);
+          gq_load_k(p.gq, row, rvalid && c < p.N, c, c < p.N ? min(16u, p.N - c) : 0u, p.N, pw2[q], pw1[q]);
+        }
+      }
+      ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_ldg_error);
+      ok = __all_sync(0xffffffffu, ok);
+      if (!ok) break;
+      fence_after();
+      if (threadIdx.x == 32 * (kLoaderWarps + 1) && tile == blockIdx.x) dbg_stamp(p, 15);
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
       if (fused && bst.tiles >= (uint32_t)kBnqFlushTiles) {
         bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
         bst.tiles = 0;
       }
+      if constexpr (GQ) if (bst.tiles >= (uint32_t)kBnqFlushTiles) {
+        gq_flush(p.gq, my_stat, 0, BN, p.N, lane);
+        bst.tiles = 0;
+      }
       ++bst.tiles;
-      constexpr int G = BN < 32 ? BN : 32;  // columns fetched from tensor memory per wait
-      constexpr bool kSplit = BN > G;       // wide tiles: both warps of a quadrant alternate the G-column groups
+      bool first_group = true;
 #pragma unroll 1
       for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G) {
+        const bool fg = first_group;   // this group's mantissas were fetched before the wait
+        first_group = false;
         uint32_t vv[G / 16][16];
 #pragma unroll
         for (int q = 0; q < G / 16; ++q) tmem_ld16(taddr + c0 + 16 * q, vv[q]);
@@ -426,6 +448,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
           }
           if (fused) {
             bnq_chunk(p.bnq, bst, f, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+          } else if (GQ) {
+            if constexpr (GQ) {
+              if (!fg) gq_load_k(p.gq, row, rvalid, (uint32_t)c, ncol, p.N, pw2[q], pw1[q]);
+              gq_chunk(p.gq, gst, f, pw2[q], pw1[q], row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+            }
           } else if (rvalid) {
             float* o = p.out + (size_t)row * p.ldc + c;
             if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
@@ -472,6 +499,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       bnq_flush_cta(p.bnq, my_stat, s_tot, 0, BN, p.N, lane, threadIdx.x - 32 * (kLoaderWarps + 1), 32 * kEpiWarps, 1);
       bnq_finish(p.bnq, bst, (unsigned long long)p.M * p.N, warp == kLoaderWarps + 1, lane);
     }
+    if constexpr (GQ) if (ok) {
+      gq_flush_cta(p.gq, my_stat, s_tot, 0, BN, p.N, lane, threadIdx.x - 32 * (kLoaderWarps + 1), 32 * kEpiWarps, 1);
+      gq_finish(p.gq, gst, (unsigned long long)p.M * p.N, warp == kLoaderWarps + 1, lane);
+    }
   }
 
   fence_before();
@@ -482,36 +513,38 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   if (threadIdx.x == 32 * kLoaderWarps) dbg_stamp(p, 18);
 }
 
-template <int BN, int CPP, bool HALO>
+template <int BN, int CPP, bool HALO, bool GQ>
 int launch_ldg2(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
   static size_t attr_smem[16] = {};
   const int dev = device_info().device;
   if (attr_smem[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP, HALO, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_ldg_kernel)");
       return LBT_ECUDA;
     }
     attr_smem[dev] = smem;
   }
-  launch_pdl(conv_ldg_kernel<BN, CPP, HALO>, grid, kThreads, smem, st, p);
+  launch_pdl(conv_ldg_kernel<BN, CPP, HALO, GQ>, grid, kThreads, smem, st, p);
   return check_launch("lbt_conv_i8 (cp.async gather)");
+}
+
+template <int BN, bool HALO, bool GQ>
+int launch_ldg1(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  switch (p.cpp) {
+    case 1: return launch_ldg2<BN, 1, HALO, GQ>(p, grid, smem, st);
+    case 2: return launch_ldg2<BN, 2, HALO, GQ>(p, grid, smem, st);
+    default: return launch_ldg2<BN, 4, HALO, GQ>(p, grid, smem, st);
+  }
 }
 
 template <int BN>
 int launch_ldg(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st, bool halo) {
-  if (halo) {
-    switch (p.cpp) {
-      case 1: return launch_ldg2<BN, 1, true>(p, grid, smem, st);
-      case 2: return launch_ldg2<BN, 2, true>(p, grid, smem, st);
-      default: return launch_ldg2<BN, 4, true>(p, grid, smem, st);
-    }
+  if (p.gq.g2.bits != 0) {   // fused BN-backward epilogue: stride-1 input gradients (halo loader where the image allows)
+    if constexpr (BN <= 64) return halo ? launch_ldg1<BN, true, true>(p, grid, smem, st) : launch_ldg1<BN, false, true>(p, grid, smem, st);
+    else return LBT_EUNSUPPORTED;
   }
-  switch (p.cpp) {
-    case 1: return launch_ldg2<BN, 1, false>(p, grid, smem, st);
-    case 2: return launch_ldg2<BN, 2, false>(p, grid, smem, st);
-    default: return launch_ldg2<BN, 4, false>(p, grid, smem, st);
-  }
+  return halo ? launch_ldg1<BN, true, false>(p, grid, smem, st) : launch_ldg1<BN, false, false>(p, grid, smem, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -815,7 +848,7 @@ int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C
 int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                  int kh, int kw, int sh, int sw, int pt, int pl, int OH, int OW, int gather, const int32_t* ibA,
                  const int32_t* ibB, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
-                 int8_t* k_out, int64_t* sums, const float* addend, void* stream) {
+                 int8_t* k_out, int64_t* sums, const float* addend, void* stream, const lbt_bn_bwd_link* link) {
   const DeviceInfo& di = device_info();
   const int bn = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128));
   if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -880,6 +913,20 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   p.bnq.k = k_out;
   p.bnq.sums = reinterpret_cast<long long*>(sums);
   p.bnq.rows_per_image = (uint32_t)(OH * OW);
+  if (link) {
+    p.gq.g2 = site_from_abi(&link->q_g2);
+    p.gq.g1 = site_from_abi(&link->q_g1);
+    p.gq.bits2 = link->bits2;
+    p.gq.ib2 = link->ib2;
+    p.gq.gamma_q = link->gamma_q;
+    p.gq.beta_q = link->beta_q;
+    p.gq.k2 = link->k2;
+    p.gq.k1 = link->k1;
+    p.gq.relu = link->relu;
+    p.gq.kg1 = link->kg1;
+    p.gq.sums = reinterpret_cast<long long*>(link->sums);
+    p.gq.rows_per_image = (uint32_t)(OH * OW);
+  }
   p.dbg = g_dbg.load(std::memory_order_relaxed);
   // halo mode: every input pixel is copied to shared memory ~1.4 times instead of kh * kw times
   p.OH = (uint32_t)OH;
@@ -937,7 +984,27 @@ extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int O
   LBT_REQUIRE_ARCH();
   // rows = input pixels (n, h, w); gathered tensor = g[N, OH, OW, Cout]; output channels = Cin
   return conv_ldg_run(g, g_kind, N, OH, OW, Cout, wp, w_kind, ldw, Cin, kh, kw, sh, sw, pad_top, pad_left, H, W, 1, ib_g, ib_w,
-                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, addend, stream);
+                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr);
+}
+
+extern "C" int lbt_conv_i8_dgrad_bn(const void* g, int g_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw,
+                                    int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_g,
+                                    const int32_t* ib_w, int exp_const, const lbt_bn_bwd_link* link, void* stream) {
+  if (!g || !wp || !link) return LBT_EINVAL;
+  if ((g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || OH <= 0 || OW <= 0) return LBT_EINVAL;
+  if (!link->k2 || !link->k1 || !link->kg1 || !link->sums || !link->gamma_q || !link->beta_q || !link->ib2 || !link->q_g2.ib ||
+      !link->q_g1.ib)
+    return LBT_EINVAL;
+  if (link->relu != 0 && link->relu != 1) return LBT_EUNSUPPORTED;
+  if (link->q_g2.bits < 2 || link->q_g2.bits > 8 || link->q_g1.bits < 2 || link->q_g1.bits > 8 || (Cout & 3)) return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15) || (ldw & 15) || ldw < (size_t)kh * kw * C)
+    return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(link->gamma_q) | reinterpret_cast<uintptr_t>(link->beta_q)) & 15) return LBT_EUNSUPPORTED;
+  if (!conv_ldg_enabled() || !conv_ldg_ok(C, Cout, kh, kw)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  return conv_ldg_run(g, g_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, 1, 1, pad_top, pad_left, OH, OW, 0, ib_g, ib_w, exp_const,
+                      nullptr, nullptr, (size_t)Cout, nullptr, nullptr, nullptr, nullptr, stream, link);
 }
 
 // Test / bench knob (not in lbt.h): 0 routes every convolution through the TMA-im2col kernel, 1 (default) lets the

@@ -21,6 +21,7 @@ advanced once per step by ``Runtime.update_ranges()`` (read-then-update, SURVEY.
 """
 import contextlib
 import ctypes
+import os
 import math
 
 import torch
@@ -543,7 +544,7 @@ def _conv_fprop(layer, geom, xm, xkind, prep, wm, bq, out2d, bnq=None):
         G.gemm_i8(A, wt, ibA=ibx, ibB=ibw, exp_const=e, bias=bq, out=out2d, bnq=gbnq)
 
 
-def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_db, addend=None):
+def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_db, addend=None, link=None):
     """dfxp:302-305 from the quantised gradient mantissas gm [N, OH, OW, Cout] (s8): (dX NHWC fp32, dW, db).
     ``addend`` (NHWC fp32, the shape of dX): the gradient reaching the same input along another branch (residual
     shortcut), added in the dgrad epilogue instead of by a separate pass over the tensor."""
@@ -597,7 +598,27 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     if need_db:
         db = _emit_grad(rt, layer.bias, _colsum(g2, Q.MANT_S8, rt), ibA=layer.qG.range, exp_const=-(gb - 1))      # dfxp:304
     # ---- dgrad: dX[NHW, Cin] = im2colT(G)[NHW, kh*kw*Cout] . Wt[Cin, kh*kw*Cout] ----
-    if need_dx:
+    linked = False
+    if (need_dx and link is not None and link.k1 is not None and addend is None and layer.implicit and sh == 1 and sw == 1 and
+            kh * kw > 1 and _implicit_ok(Cout, kh, kw) and tuple(link.k1.shape) == (N, H, W, Cin)):
+        # the producing unit's BN backward pass 1 in this dgrad's epilogue: no fp32 dX (lbt_conv_i8_dgrad_bn)
+        K2 = kh * kw * Cout
+        pw2 = prep['w2'] if prep is not None else None
+        w2 = pw2 if pw2 is not None else _as_operand(wm.flip(0, 1).permute(2, 0, 1, 3).reshape(Cin, K2))
+        rt = layer.qX.runtime
+        kg1 = torch.empty_like(link.k1)
+        bsums = rt.zeros_i64(4 * Cin + 2, dev)
+        ls = link.struct(H * W * Cin, dev, kg1, bsums)
+        linked = _lib.try_call('lbt_conv_i8_dgrad_bn', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2), Q.MANT_S8,
+                               w2.stride(0), Cin, kh, kw, kh - 1 - pt, kw - 1 - pl, H, W, _lib.ptr(layer.qG.range),
+                               _lib.ptr(layer.qW.range), int(-(gb - 1) - (wb - 1)), ctypes.addressof(ls), _lib.stream(),
+                               meta=dict(ops=2 * N * H * W * Cin * K2, bytes=N * OH * OW * Cout + Cin * K2 + 3 * N * H * W * Cin))
+        if linked:
+            global _link_count
+            _link_count += 1
+            link.kg1, link.bsums, link.done = kg1, bsums, True
+            dx = torch.empty(1, dtype=torch.float32, device=dev).expand(N, H, W, Cin)      # shape carrier only
+    if need_dx and not linked:
         K2 = kh * kw * Cout
         dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dev)
         ad2 = addend.reshape(N * H * W, Cin) if addend is not None else None
@@ -1038,26 +1059,27 @@ def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_
     return k2, out, nm, relu_mode
 
 
-def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_site=None, want_dx=True):
+def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_site=None, want_dx=True, pre=None):
     """Both BN backward passes on memory-order tensors: (dx fp32 or None, gradient mantissas of `grad_site` or None,
-    dgamma, dbeta, d_add)."""
+    dgamma, dbeta, d_add).  ``pre = (kg1, bsums)``: pass 1 already ran in the epilogue of the consuming convolution's
+    input-gradient kernel (lbt_conv_i8_dgrad_bn); ``g_`` is then not read (may be None)."""
     norm, resc = bn[0], bn[1]
     rt = norm.qX.runtime
-    N, C = g_.shape[0], g_.shape[-1]
-    n_inner = g_.numel() // N
-    dev = g_.device
-    bsums = rt.zeros_i64(4 * C + 2, dev)          # [4C] sums + the grid-barrier word of the fused launch
-    d_add = torch.empty_like(g_) if has_add else None
-    dx = torch.empty_like(g_) if want_dx else None
+    N, C = k1.shape[0], k1.shape[-1]
+    n_inner = k1.numel() // N
+    dev = k1.device
+    bsums = pre[1] if pre is not None else rt.zeros_i64(4 * C + 2, dev)   # [4C] sums + the grid-barrier word of the fused launch
+    d_add = torch.empty(k1.shape, dtype=torch.float32, device=dev) if has_add else None
+    dx = torch.empty(k1.shape, dtype=torch.float32, device=dev) if want_dx else None
     qg = gm = None
     if grad_site is not None:
         qg = grad_site.abi(n_inner, dev)
         gm = torch.empty_like(k1)
-    nbytes = g_.numel() * (6 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0) + (4 if want_dx else 0) +
+    nbytes = k1.numel() * (6 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0) + (4 if want_dx else 0) +
                            (1 if gm is not None else 0))
     # small tensors: both passes in one launch (lbt_bn_bwd_fused); it declines shapes that are not one wave of CTAs
     fused = False
-    if FUSE_BN_BWD:
+    if FUSE_BN_BWD and pre is None:
         a = _lib.BnBwdArgs(g=_lib.ptr(g_), out=_lib.ptr(out_), k2=_lib.ptr(k2), k1=_lib.ptr(k1), n_outer=N, n_inner=n_inner, C=C,
                            relu=relu_mode, bits2=resc.qX.bits, bits1=norm.qX.bits, ib2=_lib.ptr(resc.qX.range),
                            ib1=_lib.ptr(norm.qX.range), gamma_q=_lib.ptr(gq), beta_q=_lib.ptr(bq),
@@ -1068,7 +1090,9 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
         if qg is not None:
             a.q_grad = qg
         fused = _lib.try_call('lbt_bn_bwd_fused', ctypes.addressof(a), _lib.stream(), meta=dict(bytes=nbytes))
-    if not fused:
+    if not fused and pre is not None:
+        kg1 = pre[0]
+    elif not fused:
         kg1 = torch.empty_like(k1)
         nzg2, offg2 = _site_args(resc.qG, g_)
         nzg1, offg1 = _site_args(norm.qG, g_)
@@ -1079,10 +1103,11 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
                   _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
                   int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
                   meta=dict(bytes=g_.numel() * (7 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
+    if not fused:
         _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
                   _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
                   ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), _lib.stream(),
-                  meta=dict(bytes=g_.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
+                  meta=dict(bytes=k1.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
     # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
     dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
     dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
@@ -1112,6 +1137,39 @@ class _FusedBNFn(torch.autograd.Function):
         return _from_mem(dx), dgamma, dbeta, (_from_mem(d_add) if d_add is not None else None), None, None
 
 
+_link_count = 0        # fused backward links taken (tests)
+FUSE_BWD_LINK = os.environ.get('LBT_BWD_LINK', '0') == '1'   # module switch: a unit's BN backward pass 1 runs in the epilogue of the NEXT unit's input-gradient kernel
+                       # (lbt_conv_i8_dgrad_bn).  Bit-identical; measured on B200: the fused launch takes 29 us where dgrad (13-17 us)
+                       # and the BN pass (12-15 us) take the same in two — its epilogue warps wait on the k1 / k2 / noise loads of
+                       # every tile — and ResNet-20's step goes from 1.433 to 1.484 ms, so it is OFF by default.
+
+
+class _BwdLink:
+    """Backward hand-off between two consecutive fused units A -> B whose only connection is A's (mantissa-only) output:
+    B's input-gradient kernel runs A's BN backward pass 1 in its epilogue (lbt_conv_i8_dgrad_bn) and leaves (kg1, sums)
+    here; A's backward then starts at pass 2.  No fp32 gradient tensor exists between the two units."""
+
+    def __init__(self):
+        self.bn = self.k1 = self.k2 = self.gq = self.bq = None
+        self.relu_mode = 0
+        self.kg1 = self.bsums = None
+        self.done = False
+
+    def offer(self, bn, k1, k2, gq, bq, relu_mode, has_add):
+        norm, resc = bn[0], bn[1]
+        if has_add or relu_mode not in (0, 1) or resc.qG.bits > 8 or norm.qG.bits > 8 or k1.shape[-1] % 4:
+            return
+        self.bn, self.k1, self.k2, self.gq, self.bq, self.relu_mode = bn, k1, k2, gq, bq, relu_mode
+
+    def struct(self, n_inner, dev, kg1, bsums):
+        norm, resc = self.bn[0], self.bn[1]
+        # arena=True: the step's pre-generated noise vectors (a GEMM epilogue cannot reuse a Philox draw down the batch the
+        # way the BN kernels do: in-kernel generation costs ~30 instructions per element there)
+        return _lib.BnBwdLink(q_g2=resc.qG.abi(n_inner, dev, arena=True), q_g1=norm.qG.abi(n_inner, dev, arena=True), bits2=resc.qX.bits,
+                              relu=self.relu_mode, ib2=_lib.ptr(resc.qX.range), gamma_q=_lib.ptr(self.gq), beta_q=_lib.ptr(self.bq),
+                              k2=_lib.ptr(self.k2), k1=_lib.ptr(self.k1), kg1=_lib.ptr(kg1), sums=_lib.ptr(bsums))
+
+
 class _ConvBNFn(torch.autograd.Function):
     """One Conv2d_q + BatchNorm2d_q unit (+ residual add, + ReLU) with every hand-off between the two modules kept
     in integer mantissas (north_star (2): the GEMM epilogue re-quantises its output, no fake-quant fp32 round trip):
@@ -1124,7 +1182,7 @@ class _ConvBNFn(torch.autograd.Function):
     the results are bit-identical (tests/test_fused_gpu.py)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias):
+    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias, link_in, link_out):
         geom = _conv_geom(conv, x, weight)
         N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         norm, resc = bn[0], bn[1]
@@ -1141,6 +1199,9 @@ class _ConvBNFn(torch.autograd.Function):
         k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
         ctx.conv, ctx.bn, ctx.geom, ctx.xkind, ctx.prep = conv, bn, geom, xkind, prep
         ctx.relu_mode, ctx.has_add = relu_mode, add is not None
+        ctx.link_in, ctx.link_out = link_in, link_out
+        if link_out is not None and out is None:     # the next unit may run this BN's backward pass 1 in its dgrad epilogue
+            link_out.offer(bn, k1, k2, gq, bq, relu_mode, add is not None)
         ctx.save_for_backward(xm, wm, k1, k2, sums, gq, bq, out if relu_mode == 2 else None)
         if out is None:       # mantissa-only activation: the fp32 tensor is never materialised (shape carrier only)
             out = torch.empty(1, dtype=torch.float32, device=dev).expand(N, OH, OW, Cout)
@@ -1158,12 +1219,15 @@ class _ConvBNFn(torch.autograd.Function):
         conv = ctx.conv
         xm, wm, k1, k2, sums, gq, bq, out = ctx.saved_tensors
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        _, gm, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g), k1, k2, sums, gq, bq, out, ctx.relu_mode,
-                                                   ctx.has_add, grad_site=conv.qG, want_dx=False)   # ... dfxp:300
+        lo = ctx.link_out
+        pre = (lo.kg1, lo.bsums) if (lo is not None and lo.done) else None     # pass 1 ran in the consumer's dgrad epilogue
+        _, gm, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g) if pre is None else None, k1, k2, sums, gq, bq, out,
+                                                   ctx.relu_mode, ctx.has_add, grad_site=conv.qG, want_dx=False, pre=pre)   # ... dfxp:300
         addend = _to_mem(g_alias) if (g_alias is not None and need_dx) else None
-        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend)
+        li = ctx.link_in if (addend is None and FUSE_BWD_LINK) else None
+        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend, link=li)
         return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
-                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None)
+                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None)
 
 
 FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lbt_bn_bwd_fused, grid barrier) where the
@@ -1178,7 +1242,7 @@ def _unit_fusable(conv, bn, x):
             x.is_cuda)
 
 
-def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True, alias=False):
+def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True, alias=False, link_in=None, link_out=None):
     """``bn(conv(x), add=add, relu=relu)`` as ONE fused unit when the shapes allow (else exactly that expression).
 
     next_conv: the Conv2d_q that consumes the result — its input quantiser then runs inside this unit's last kernel
@@ -1201,7 +1265,7 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     # channel block inputs of ResNet-50 the epilogue-bound 1x1 dgrad GEMMs lose more than the coalesced add costs (+3 %)
     use_alias = bool(alias and x.requires_grad and not getattr(x, '_lbt_hollow', False) and conv.weight.shape[2] <= 128)
     out, nm, xa = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
-                                  want_fp32, use_alias)
+                                  want_fp32, use_alias, link_in if FUSE_BWD_LINK else None, link_out if FUSE_BWD_LINK else None)
     if next_site is not None:
         out._lbt_q = {id(next_site): (nm, next_kind)}
     if not want_fp32:
@@ -1602,11 +1666,16 @@ class ResidualBlock_q(nn.Module):
         if paired:
             # the first unit hands back an alias of x for the shortcut branch: the shortcut's gradient then returns
             # through that unit's backward and is added in its dgrad epilogue (no separate add over the tensor)
-            r, xs = conv_bn_unit(res[0], res[1], x, next_conv=res[2], want_fp32=False, alias=True)
+            # consecutive units of the residual branch are linked: the later unit's input-gradient kernel runs the earlier
+            # unit's BN backward pass 1 in its epilogue (_BwdLink)
+            link = _BwdLink()
+            r, xs = conv_bn_unit(res[0], res[1], x, next_conv=res[2], want_fp32=False, alias=True, link_out=link)
             for i in range(2, len(res) - 2, 2):
-                r = conv_bn_unit(res[i], res[i + 1], r, next_conv=res[i + 2], want_fp32=False)
+                nxt = _BwdLink()
+                r = conv_bn_unit(res[i], res[i + 1], r, next_conv=res[i + 2], want_fp32=False, link_in=link, link_out=nxt)
+                link = nxt
             sc = conv_bn_unit(sc_layers[0], sc_layers[1], xs) if len(sc_layers) == 2 else self.shortcut(xs)
-            return conv_bn_unit(res[-2], res[-1], r, add=sc, relu=True, next_conv=next_conv)
+            return conv_bn_unit(res[-2], res[-1], r, add=sc, relu=True, next_conv=next_conv, link_in=link)
         r = x
         for m in res[:-1]:
             r = m(r)

@@ -11,9 +11,11 @@ from lbt_b200 import dfxp as D, models as M  # noqa: E402
 from lbt_b200.trainer import Trainer  # noqa: E402
 
 
-def _run(name, fused, steps, batch, image, kw, bn_bwd=False):
+def _run(name, fused, steps, batch, image, kw, bn_bwd=False, link=False):
     D.FUSE_UNITS = fused
     D.FUSE_BN_BWD = bn_bwd
+    D.FUSE_BWD_LINK = link
+    D._link_count = 0
     try:
         torch.manual_seed(3)
         model = getattr(M, name)(8, weight_decay=2e-4, seed=9, **kw).cuda()
@@ -31,6 +33,7 @@ def _run(name, fused, steps, batch, image, kw, bn_bwd=False):
     finally:
         D.FUSE_UNITS = True
         D.FUSE_BN_BWD = False
+        D.FUSE_BWD_LINK = False
 
 
 @pytest.mark.parametrize('name,batch,image,kw', [
@@ -49,6 +52,25 @@ def test_fused_units_equal_unfused_bit_for_bit(name, batch, image, kw):
         assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
     for x, y in zip(a['bn'], b['bn']):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('name,batch,image,kw', [('CIFAR10_Resnet20', 16, 32, {}), ('CIFAR10_Resnet20', 3, 32, {}),
+                                                 ('Resnet18', 4, 64, dict(image=64, num_classes=10)),
+                                                 ('Resnet50', 2, 64, dict(image=64, num_classes=10))])
+def test_backward_link_equals_separate_bn_pass(name, batch, image, kw):
+    """lbt_conv_i8_dgrad_bn (a unit's BN backward pass 1 in the epilogue of the next unit's input-gradient kernel, no fp32
+    gradient tensor between them) vs lbt_conv_i8_fprop + lbt_bn_bwd_quant_stats."""
+    a = _run(name, True, 3, batch, image, kw, link=True)
+    linked = D._link_count
+    b = _run(name, True, 3, batch, image, kw, link=False)
+    assert D._link_count == 0
+    if name == 'CIFAR10_Resnet20':
+        assert linked == 3 * 9, linked              # every residual block, every step
+    assert a['losses'] == b['losses']
+    assert torch.equal(a['ranges'], b['ranges'])
+    assert torch.equal(a['counters'], b['counters'])
+    for k in ('g', 'w', 'a'):
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
 
 
 @pytest.mark.parametrize('name,batch,image,kw', [('CIFAR10_Resnet20', 64, 32, {}), ('CIFAR10_Resnet20', 7, 32, {}),
