@@ -142,12 +142,28 @@ __device__ __forceinline__ uint32_t pack4(const float (&k)[4]) {
   return (uint32_t)(i0 & 0xff) | ((uint32_t)(i1 & 0xff) << 8) | ((uint32_t)(i2 & 0xff) << 16) | ((uint32_t)(i3 & 0xff) << 24);
 }
 
+// x / n for the per-channel element count n.  The fp64 division is a ~20-deep dependent chain on a chip with a token fp64
+// pipe (it is most of the 1.8 us per-CTA prologue of the apply kernels); when n is a power of two — every CIFAR-shaped
+// layer at a power-of-two batch — the quotient is the exact scaling x * 2^-k, bit-identical to the division.
+struct DivN {
+  double n, inv;
+  bool pow2;
+};
+__device__ __forceinline__ DivN make_divn(unsigned long long nn) {
+  DivN d;
+  d.n = (double)nn;
+  d.pow2 = nn != 0ull && (nn & (nn - 1ull)) == 0ull;
+  d.inv = d.pow2 ? __longlong_as_double((long long)(1023 - (__ffsll((long long)nn) - 1)) << 52) : 0.0;
+  return d;
+}
+__device__ __forceinline__ double div_n(double x, const DivN& d) { return d.pow2 ? x * d.inv : x / d.n; }
+
 // Batch moments of the quantised input from the exact integer sums (dfxp:588, biased variance),
 // finished in fp64 and rounded once: mean = 2^-f * S1/n, var = 2^-2f * (S2/n - (S1/n)^2).
-__device__ __forceinline__ void moments(const long long* sums, int C, int c, double n, float inv_m, float& mean, float& var) {
+__device__ __forceinline__ void moments(const long long* sums, int C, int c, const DivN& n, float inv_m, float& mean, float& var) {
   const double s1 = (double)sums[c], s2 = (double)sums[C + c];
-  const double mu = s1 / n;
-  double v = s2 / n - mu * mu;
+  const double mu = div_n(s1, n);
+  double v = div_n(s2, n) - mu * mu;
   if (v < 0.0) v = 0.0;
   mean = (float)(mu * (double)inv_m);
   var = (float)(v * (double)inv_m * (double)inv_m);
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
   }
   const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
   const QC c2 = make_qc(p.q2.bits, __ldg(p.q2.ib));
-  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  const DivN n = make_divn((unsigned long long)(p.t.n_outer * (p.t.n_inner / C)));
   for (int ch = threadIdx.x; ch < C; ch += kThreads) {
     float mean, var;
     moments(p.sums, C, ch, n, c1.inv_m, mean, var);
@@ -545,7 +561,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   }
   const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
   const QC cg = make_qc(p.bitsg1, __ldg(p.ibg1));
-  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  const DivN n = make_divn((unsigned long long)(p.t.n_outer * (p.t.n_inner / C)));
   for (int ch = threadIdx.x; ch < C; ch += kThreads) {
     float mean, var;
     moments(p.fsums, C, ch, n, c1.inv_m, mean, var);
@@ -553,8 +569,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     // mean(gq) and mean(gq * xhat) from the exact integer sums, finished in fp64
     const double sg = (double)p.bsums[2 * C + ch] * (double)cg.inv_m;                       // sum gq
     const double sgx = (double)p.bsums[3 * C + ch] * (double)cg.inv_m * (double)c1.inv_m;   // sum gq*xq
-    const double mg = sg / n;
-    const double mgx = ((sgx - (double)mean * sg) / (double)den) / n;                        // mean(gq * xhat)
+    const double mg = div_n(sg, n);
+    const double mgx = div_n((sgx - (double)mean * sg) / (double)den, n);                        // mean(gq * xhat)
     s_par[ch] = mean;
     s_par[C + ch] = den;
     s_par[2 * C + ch] = (float)mg;
@@ -772,15 +788,15 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
 
   // ---- pass 2 from shared memory ----
   float* s_par = reinterpret_cast<float*>(s_dyn);
-  const double n = (double)(p.t.n_outer * (p.t.n_inner / C));
+  const DivN n = make_divn((unsigned long long)(p.t.n_outer * (p.t.n_inner / C)));
   for (int ch = threadIdx.x; ch < C; ch += kThreads) {
     float mean, var;
     moments(p2.fsums, C, ch, n, c1.inv_m, mean, var);
     const float den = __fsqrt_rn(__fadd_rn(var, p2.eps));
     const double sg = (double)__ldcg(p.sums + 2 * C + ch) * (double)cg1.inv_m;
     const double sgx = (double)__ldcg(p.sums + 3 * C + ch) * (double)cg1.inv_m * (double)c1.inv_m;
-    const double mg = sg / n;
-    const double mgx = ((sgx - (double)mean * sg) / (double)den) / n;
+    const double mg = div_n(sg, n);
+    const double mgx = div_n((sgx - (double)mean * sg) / (double)den, n);
     s_par[ch] = mean;
     s_par[C + ch] = den;
     s_par[2 * C + ch] = (float)mg;
