@@ -41,6 +41,28 @@ WORKLOADS = {
 }
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Everything libraries print to fd 1 during the run (NCCL's version banner, for one) goes to stderr; the ONE JSON line is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -113,7 +135,7 @@ def run_reference(a):
         'e2e': {'value': ips, 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'TensorFlow 1.x reference cannot run in this image (SURVEY.md F10); this is the CPU oracle port',
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,7 +473,7 @@ def run_native(a):
     if a.breakdown:
         for k, d in breakdown.items():
             print('[breakdown] %-28s %s' % (k, d), file=sys.stderr)
-    print(json.dumps(line), flush=True)
+    emit(line)
     _finish(world)
 
 
@@ -470,6 +492,7 @@ def _finish(world):
 
 if __name__ == '__main__':
     args = parse()
+    guard_stdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
