@@ -26,8 +26,9 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed ncu captures
 # (profiles/): (workload, C-ABI entry) -> bytes per launch (average over the class), or absent = null
 TRAFFIC = {
-    # profiles/r1_step_resnet20_final_{fwd,bwd}_ncu_full_summary.csv: the stage-1 launches (conv_ldg_kernel<16, 1>) read
-    # 4.25-4.31 MB from DRAM and write ~0 (their 4-17 MB outputs stay in the 126 MB L2) vs 8.4-21 MB algorithmic
+    # profiles/r1_conv_ldg_halo_step_ncu_full_summary.csv (ncu --set full inside bench.py, halo-patch loader): the stage-1 launches
+    # (conv_ldg_kernel<16, 1, 1, 0>) read 4.25-4.32 MB from DRAM and write ~0 (their 4-17 MB outputs stay in the 126 MB L2)
+    # vs 8.4-21 MB algorithmic
     ('resnet20', 'lbt_conv_i8_fprop'): 4.3e6,
 }
 
