@@ -78,6 +78,8 @@ __device__ __forceinline__ void wait_flags(uint32_t* pad, int slot0, int world, 
 }
 
 __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   const lbt_dp_peers& pe = p.peers;
   const int world = pe.world, rank = pe.rank;
   uint32_t* pad = pe.pad[rank];
@@ -219,7 +221,7 @@ extern "C" int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, fl
   const size_t cap = (size_t)di.sm_count * 4;     // peer loads need many requests in flight; all CTAs co-resident
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  dp_step_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(dp_step_kernel, (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), a);
   return check_launch("lbt_dp_step");
 }
 

@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) im2col_scalar_kernel(const Im2colParams p
 // out[c, r] = in[r, c] for byte matrices, 64x64 tiles through shared memory (both sides coalesced).
 __global__ void __launch_bounds__(256) transpose_i8_kernel(const uint8_t* __restrict__ in, size_t R, size_t C, size_t ld_in,
                                                            uint8_t* __restrict__ out, size_t ld_out) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   __shared__ uint8_t tile[64][64 + 4];
   const size_t tiles_c = (C + 63) / 64, tiles_r = (R + 63) / 64;
   for (size_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
@@ -205,7 +207,7 @@ extern "C" int lbt_transpose_i8(const void* in, size_t R, size_t C, size_t ld_in
   const DeviceInfo& di = device_info();
   const size_t tiles = ((R + 63) / 64) * ((C + 63) / 64);
   const size_t cap = (size_t)di.sm_count * 8;
-  transpose_i8_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(transpose_i8_kernel, (unsigned)(tiles < cap ? tiles : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const uint8_t*>(in), R, C, ld_in, reinterpret_cast<uint8_t*>(out), ld_out);
   return check_launch("lbt_transpose_i8");
 }

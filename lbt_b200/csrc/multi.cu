@@ -166,7 +166,7 @@ extern "C" int lbt_finalize_multi(const lbt_finalize_job* jobs_dev, size_t njobs
   const DeviceInfo& di = device_info();
   const uint64_t blocks = (total + kThreads - 1) / kThreads;
   const uint64_t cap = (uint64_t)di.sm_count * 8;
-  finalize_multi_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(finalize_multi_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), 
       jobs_dev, (int)njobs, (unsigned long long)total);
   return check_launch("lbt_finalize_multi");
 }
@@ -176,7 +176,7 @@ extern "C" int lbt_param_prep(const lbt_prep_job* jobs_dev, const uint32_t* bloc
   if (!jobs_dev || !block_job_dev || !block_chunk_dev || chunk_elems == 0) return LBT_EINVAL;
   if (nblocks == 0) return LBT_OK;
   LBT_REQUIRE_ARCH();
-  param_prep_kernel<<<(unsigned)nblocks, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(param_prep_kernel, (unsigned)nblocks, kThreads, 0, reinterpret_cast<cudaStream_t>(stream), 
       jobs_dev, block_job_dev, block_chunk_dev, seed, dev_step, chunk_elems);
   return check_launch("lbt_param_prep");
 }
@@ -189,7 +189,7 @@ extern "C" int lbt_noise_fill_multi(const lbt_noise_job* jobs_dev, size_t njobs,
   LBT_REQUIRE_ARCH();
   const unsigned long long blocks = (total_groups + kThreads - 1) / kThreads;
   const unsigned grid = (unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16);
-  noise_fill_multi_kernel<<<grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs_dev, (int)njobs, total_groups,
+  launch_pdl(noise_fill_multi_kernel, grid, kThreads, 0, reinterpret_cast<cudaStream_t>(stream), jobs_dev, (int)njobs, total_groups,
                                                                                         seed, dev_step);
   return check_launch("lbt_noise_fill_multi");
 }

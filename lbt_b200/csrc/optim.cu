@@ -10,6 +10,8 @@ namespace {
 __global__ void __launch_bounds__(256) sgd_momentum_kernel(float* __restrict__ w, float* __restrict__ a,
                                                            const float* __restrict__ g, size_t n, float lr,
                                                            const float* dev_lr, float momentum, float grad_scale) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   if (dev_lr) lr = *dev_lr;
   const size_t nv = n / 4;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
@@ -49,7 +51,7 @@ extern "C" int lbt_sgd_momentum(float* w, float* accum, const float* grad, size_
   const DeviceInfo& di = device_info();
   const size_t blocks = (n / 4 + 255) / 256 + 1;
   const size_t cap = (size_t)di.sm_count * 8;
-  sgd_momentum_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(sgd_momentum_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       w, accum, grad, n, lr, dev_lr, momentum, grad_scale);
   return check_launch("lbt_sgd_momentum");
 }

@@ -18,6 +18,8 @@ struct PoolParams {
 
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                                 uint8_t* __restrict__ idx, const PoolParams p, size_t total) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
     uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
     const uint32_t c = (uint32_t)i - pix * p.c4;
@@ -49,6 +51,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
 
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
                                                                 float* __restrict__ dx, const PoolParams p, size_t total) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
     uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
     const uint32_t c = (uint32_t)i - pix * p.c4;
@@ -116,7 +120,7 @@ extern "C" int lbt_maxpool_fwd(const float* x, int N, int H, int W, int C, int k
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads;
   const size_t cap = (size_t)device_info().sm_count * 8;
-  maxpool_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, idx, p,
+  launch_pdl(maxpool_fwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), x, out, idx, p,
                                                                                                                   total);
   return check_launch("lbt_maxpool_fwd");
 }
@@ -136,7 +140,7 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads;
   const size_t cap = (size_t)device_info().sm_count * 8;
-  maxpool_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, idx, dx, p,
+  launch_pdl(maxpool_bwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), g, idx, dx, p,
                                                                                                                   total);
   return check_launch("lbt_maxpool_bwd");
 }
@@ -151,6 +155,8 @@ namespace {
 
 __global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                                 const PoolParams p, size_t total) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   const float inv = 1.0f;  // the window sum is DIVIDED by k*k below (same arithmetic as the oracle's restatement)
   (void)inv;
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
@@ -191,6 +197,8 @@ __global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __re
 
 __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, const PoolParams p,
                                                                 size_t total) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   const float d = (float)(p.k * p.k);
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
     uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
@@ -222,6 +230,8 @@ constexpr int kXentStage = 8192;   // floats of shared memory: logits of small p
 
 __global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C,
                                                         float* __restrict__ probs, float* __restrict__ loss) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   __shared__ float s_part[32];
   __shared__ float s_x[kXentStage];
   __shared__ int s_y[1024];
@@ -260,6 +270,8 @@ __global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__ probs, const long long* __restrict__ labels,
                                                        const float* __restrict__ gout, int B, int C, float* __restrict__ dlogits) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   const float scale = (gout ? *gout : 1.0f) / (float)B;
   const size_t total = (size_t)B * C;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -284,7 +296,7 @@ extern "C" int lbt_avgpool_fwd(const float* x, int N, int H, int W, int C, int k
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
-  avgpool_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, out, p, total);
+  launch_pdl(avgpool_fwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), x, out, p, total);
   return check_launch("lbt_avgpool_fwd");
 }
 
@@ -300,7 +312,7 @@ extern "C" int lbt_avgpool_bwd(const float* g, int N, int H, int W, int C, int k
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
-  avgpool_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g, dx, p, total);
+  launch_pdl(avgpool_bwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), g, dx, p, total);
   return check_launch("lbt_avgpool_bwd");
 }
 
@@ -308,7 +320,7 @@ extern "C" int lbt_softmax_xent_fwd(const float* logits, const int64_t* labels, 
   if (!logits || !labels || !probs || !loss || B <= 0 || C <= 0) return LBT_EINVAL;
   LBT_REQUIRE_ARCH();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  xent_fwd_kernel<<<1, 1024, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
+  launch_pdl(xent_fwd_kernel, 1, 1024, 0, st, logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
   return check_launch("lbt_softmax_xent_fwd");
 }
 
@@ -317,7 +329,7 @@ extern "C" int lbt_softmax_xent_bwd(const float* probs, const int64_t* labels, c
   if (!probs || !labels || !dlogits || B <= 0 || C <= 0) return LBT_EINVAL;
   LBT_REQUIRE_ARCH();
   const size_t total = (size_t)B * C, blocks = (total + 255) / 256, cap = (size_t)device_info().sm_count * 8;
-  xent_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(xent_bwd_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream), 
       probs, reinterpret_cast<const long long*>(labels), grad_loss, B, C, dlogits);
   return check_launch("lbt_softmax_xent_bwd");
 }
@@ -333,6 +345,8 @@ namespace {
 
 __global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, const float* __restrict__ g, float* __restrict__ out,
                                                    size_t n4, size_t n) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   // g == NULL: out = max(0, x);  else: out = g where x > 0 (x = the forward OUTPUT or input: same sign test), else 0
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -351,6 +365,8 @@ __global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, const float* __restrict__ u, float keep, uint64_t seed,
                                                       uint64_t offset, const uint64_t* dev_step, float* __restrict__ out, size_t n) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
   const uint64_t off = offset + (dev_step ? ((*dev_step) << 32) : 0ull);
   const size_t ng = (n + 3) / 4;
   for (size_t gidx = (size_t)blockIdx.x * 256 + threadIdx.x; gidx < ng; gidx += (size_t)gridDim.x * 256) {
@@ -381,7 +397,7 @@ extern "C" int lbt_relu(const float* x, const float* g, float* out, size_t n, vo
   const bool al = !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | (g ? reinterpret_cast<uintptr_t>(g) : 0)) & 15);
   const size_t n4 = al ? n / 4 : 0;
   const size_t blocks = ((n4 ? n4 : n) + 255) / 256, cap = (size_t)device_info().sm_count * 8;
-  relu_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, g, out, n4, n);
+  launch_pdl(relu_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, g, out, n4, n);
   return check_launch("lbt_relu");
 }
 
@@ -391,7 +407,7 @@ extern "C" int lbt_dropout(const float* x, const float* u, float keep_prob, uint
   if (n == 0) return LBT_OK;
   LBT_REQUIRE_ARCH();
   const size_t blocks = ((n + 3) / 4 + 255) / 256, cap = (size_t)device_info().sm_count * 8;
-  dropout_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, u, keep_prob, seed, offset,
+  launch_pdl(dropout_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream), x, u, keep_prob, seed, offset,
                                                                                                        dev_step, out, n);
   return check_launch("lbt_dropout");
 }
