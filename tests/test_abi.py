@@ -55,3 +55,38 @@ def test_cpu_tensor_is_an_error():
     from lbt_b200 import quantizer
     with pytest.raises(_lib.LbtError):
         quantizer.quantize(torch.zeros(4, 4), 8, torch.tensor(2, dtype=torch.int32))
+
+
+def test_new_entry_points_validate_arguments_without_gpu():
+    """lbt_dp_step / lbt_augment_batch / lbt_quantize_residual / lbt_conv_i8_dgrad_bn reject bad arguments before any CUDA call."""
+    h = _lib.lib()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    ib = ctypes.cast((ctypes.c_int32 * 1)(2), ctypes.c_void_p)
+    # data-parallel step: null descriptor, world out of range, rank out of range
+    assert h.lbt_dp_step(None, p, 16, 0.1, None, 0.9, 0, None, None, None, 0, None, None) == -1
+    peers = _lib.DpPeers()
+    peers.world, peers.rank = 9, 0
+    assert h.lbt_dp_step(ctypes.addressof(peers), p, 16, 0.1, None, 0.9, 0, None, None, None, 0, None, None) == -1
+    peers.world, peers.rank = 2, 2
+    assert h.lbt_dp_step(ctypes.addressof(peers), p, 16, 0.1, None, 0.9, 0, None, None, None, 0, None, None) == -1
+    assert h.lbt_dp_export(None, None, None) == -1 and h.lbt_dp_open(None, None) == -1 and h.lbt_dp_close(None) == -1
+    # input pipeline: null images, negative pad; an empty batch is a no-op
+    assert h.lbt_augment_batch(None, None, None, 4, 8, 8, 3, 4, 1, None, 0, 0, None, None, p, None) == -1
+    assert h.lbt_augment_batch(p, None, None, 4, 8, 8, 3, -1, 1, None, 0, 0, None, None, p, None) == -1
+    assert h.lbt_augment_batch(p, None, None, 0, 8, 8, 3, 4, 1, None, 0, 0, None, None, p, None) == 0
+    # error-feedback quantiser: more gradient rows than buffer rows, bad bits, noise mode without noise; empty is a no-op
+    assert h.lbt_quantize_residual(p, 3, p, 2, 4, 8, ib, 0, None, 0, 0, None, p, None, None) == -1
+    assert h.lbt_quantize_residual(p, 1, p, 2, 4, 1, ib, 0, None, 0, 0, None, p, None, None) == -1
+    assert h.lbt_quantize_residual(p, 1, p, 2, 4, 8, ib, 1, None, 0, 0, None, p, None, None) == -1
+    assert h.lbt_quantize_residual(p, 0, p, 0, 4, 8, ib, 0, None, 0, 0, None, p, None, None) == 0
+    # fused dgrad + BN backward: the link descriptor is mandatory and must be complete
+    assert h.lbt_conv_i8_dgrad_bn(p, 1, 1, 16, 16, 16, p, 1, 144, 16, 3, 3, 1, 1, 16, 16, ib, ib, 0, None, None) == -1
+    link = _lib.BnBwdLink()
+    assert h.lbt_conv_i8_dgrad_bn(p, 1, 1, 16, 16, 16, p, 1, 144, 16, 3, 3, 1, 1, 16, 16, ib, ib, 0, ctypes.addressof(link), None) == -1
+
+
+def test_struct_mirrors_of_the_new_descriptors():
+    assert ctypes.sizeof(_lib.DpPeers) == 8 + 4 * 8 * 8
+    assert ctypes.sizeof(_lib.BnBwdLink) == 2 * ctypes.sizeof(_lib.QSiteStruct) + 8 + 7 * 8
+    assert _lib.DP_PAD_WORDS * 4 <= 256 and _lib.DP_HANDLE_BYTES == 64
