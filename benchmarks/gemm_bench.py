@@ -101,7 +101,25 @@ def rand_bits(n, bits, unsigned=False):
     return torch.randint(-(1 << (bits - 1)), 1 << (bits - 1), (n, n), dtype=torch.int32, device='cuda').to(torch.int8)
 
 
+def bench_square16(n, flush):
+    """16-bit mantissas on both operands: four 8-bit passes into the int64 accumulator (ops counted once: 2*n^3)."""
+    A = torch.randint(-32768, 32768, (n, n), dtype=torch.int32, device='cuda').to(torch.int16)
+    B = torch.randint(-32768, 32768, (n, n), dtype=torch.int32, device='cuda').to(torch.int16)
+    acc = torch.zeros(n, n, dtype=torch.int64, device='cuda')
+    ah, al = G.split_s16(A)
+    bh, bl = G.split_s16(B)
+
+    def run():
+        for a, b, alpha in ((ah, bh, 65536), (ah, bl, 256), (al, bh, 256), (al, bl, 1)):
+            G.gemm_i8_acc64(a, b, acc, alpha=alpha, k_splits=1)
+    t = timeit(run, flush=flush)
+    return dict(kind='gemm', M=n, N=n, K=n, bits=16, us=t * 1e6, tops=2 * n ** 3 / t / 1e12,
+                note='16-bit x 16-bit mantissas = four 8-bit tensor-core passes + int64 atomics epilogue; operand split not timed')
+
+
 def bench_square(n, flush, bits=8):
+    if bits > 9:
+        return bench_square16(n, flush)
     A, B = rand_bits(n, bits, unsigned=True), rand_bits(n, bits)
     out = torch.empty(n, n, dtype=torch.float32, device='cuda')
     t = timeit(lambda: G.gemm_i8(A, B, exp_const=-14, out=out), flush=flush)

@@ -66,6 +66,32 @@ def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
     return acc64
 
 
+def split_s16(m16):
+    """s16 mantissas -> (hi s8, lo u8) with k = 256 * hi + lo (lbt_split_s16)."""
+    hi = torch.empty(m16.shape, dtype=torch.int8, device=m16.device)
+    lo = torch.empty(m16.shape, dtype=torch.uint8, device=m16.device)
+    _lib.call('lbt_split_s16', _lib.ptr(m16), m16.numel(), _lib.ptr(hi), _lib.ptr(lo), _lib.stream(), meta=dict(bytes=m16.numel() * 4))
+    return hi, lo
+
+
+def gemm_i16_acc64(A16, B16, acc64=None):
+    """acc64[M,N] += A16[M,K] @ B16[N,K]^T for s16 mantissas (DFXP quantisers of 9..16 bits on BOTH operands: the 16-bit point
+    of the bit-width sweep, BASELINE config 3), exact: a = 256*ah + al, b = 256*bh + bl, so
+    a*b = 65536*ah*bh + 256*(ah*bl + al*bh) + al*bl — four passes of the 8-bit tensor-core kernel into the int64 accumulator
+    (alpha = 65536, 256, 256, 1).  K must be a multiple of 16 (operand row pitch)."""
+    M, K = A16.shape
+    N = B16.shape[0]
+    if A16.dtype != torch.int16 or B16.dtype != torch.int16 or B16.shape[1] != K:
+        raise _lib.LbtError('gemm_i16_acc64 takes int16 [M,K] and [N,K] mantissa tensors')
+    if acc64 is None:
+        acc64 = torch.zeros(M, N, dtype=torch.int64, device=A16.device)
+    ah, al = split_s16(A16.contiguous())
+    bh, bl = split_s16(B16.contiguous())
+    for a, b, alpha in ((ah, bh, 65536), (ah, bl, 256), (al, bh, 256), (al, bl, 1)):
+        gemm_i8_acc64(a, b, acc64, alpha=alpha)
+    return acc64
+
+
 def acc64_finalize(acc64, *, ibA=None, ibB=None, exp_const=0, add=None, add_scale=0.0, out=None):
     """fp32 out = acc64 * 2^(exp_const + ibA + ibB) + add_scale * add."""
     if out is None:

@@ -116,3 +116,22 @@ def test_gemm_pair_kernel_bit_exact(M, N, K, kinds):
     assert torch.equal(out, single)
     assert torch.equal(out2, single2)
     assert torch.equal(out2, (ref.float() * 2.0 ** -12 + bias) + addend)
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 16, 128), (300, 200, 1024), (2048, 512, 4096)])
+def test_gemm_16bit_operands_exact(M, N, K):
+    """16-bit mantissas on BOTH operands (config 3's 16-bit point): four 8-bit tensor-core passes, exact in int64."""
+    rng = np.random.default_rng(M + K)
+    a = torch.from_numpy(rng.integers(-32768, 32768, (M, K)).astype(np.int16)).cuda()
+    b = torch.from_numpy(rng.integers(-32768, 32768, (N, K)).astype(np.int16)).cuda()
+    a[0, :] = -32768
+    b[0, :] = -32768                                      # the extreme corner: K * 2^30
+    acc = G.gemm_i16_acc64(a, b)
+    torch.cuda.synchronize()
+    assert G.debug_error() == 0
+    # int64 reference in chunks (the products reach 2^30: fp64 accumulation is exact up to K = 2^23)
+    ref = (a.double() @ b.double().T).to(torch.int64)
+    assert torch.equal(acc, ref)
+    ib = torch.tensor(-1, dtype=torch.int32, device='cuda')
+    out = G.acc64_finalize(acc, ibA=ib, ibB=ib, exp_const=-30)
+    assert torch.equal(out, (ref.double() * 2.0 ** -32).float())
