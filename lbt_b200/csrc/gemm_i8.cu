@@ -366,12 +366,24 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             unsigned long long* o = reinterpret_cast<unsigned long long*>(p.acc64) + (size_t)row * p.ldc + col0 + c;
+            if (p.k_splits == 1 && ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+              // one CTA owns this output element (no K split): plain 128-bit read-modify-write instead of 16 atomics
+              ulonglong2* o2 = reinterpret_cast<ulonglong2*>(o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < (int)ncol) {
-                const long long a = (long long)(int)v[j] * (long long)p.alpha;
-                if (a != 0) atomicAdd(o + j, (unsigned long long)a);
+              for (int j = 0; j < 8; ++j) {
+                ulonglong2 t = o2[j];
+                t.x += (unsigned long long)((long long)(int)v[2 * j] * (long long)p.alpha);
+                t.y += (unsigned long long)((long long)(int)v[2 * j + 1] * (long long)p.alpha);
+                o2[j] = t;
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) {
+                  const long long a = (long long)(int)v[j] * (long long)p.alpha;
+                  if (a != 0) atomicAdd(o + j, (unsigned long long)a);
+                }
+            }
           }
         }
       }

@@ -194,3 +194,28 @@ def test_fused_exchange_equals_nccl_on_two_gpus(tmp_path):
     assert torch.equal(r0['fused']['w'].view(torch.int32), r0['nccl']['w'].view(torch.int32))
     assert r0['fused']['r'] == r0['nccl']['r']
     assert r0['fused']['loss'] == r0['nccl']['loss']
+
+
+def test_trainer_fused_step_end_equals_separate_kernels():
+    """Trainer(dp='fused') (lbt_dp_step) vs Trainer(dp='nccl') (at world 1: lbt_sgd_momentum + lbt_update_ranges +
+    lbt_step_advance) on one GPU: identical weights, momentum, ranges and losses."""
+    from lbt_b200 import models as M
+    from lbt_b200.trainer import Trainer
+    res = {}
+    for mode in ('fused', 'nccl'):
+        torch.manual_seed(0)
+        pm = M.CIFAR10_Resnet20(8, weight_decay=2e-4, seed=3).cuda()
+        tr = Trainer(pm, lr=1e-2, momentum=0.9, dp=mode)
+        assert tr.dp_mode == ('fused' if mode == 'fused' else 'unfused')
+        rng = np.random.default_rng(5)
+        losses = []
+        for _ in range(3):
+            X = torch.from_numpy((rng.standard_normal((8, 3, 32, 32)) * 0.5).astype(np.float32)).cuda().contiguous(
+                memory_format=torch.channels_last)
+            y = torch.from_numpy(rng.integers(0, 10, 8)).cuda()
+            losses.append(float(tr.step(X, y)))
+        res[mode] = (losses, tr.flat_w.clone(), tr.flat_a.clone(), list(pm.ranges().values()), int(pm.runtime.dev_step))
+    assert res['fused'][0] == res['nccl'][0]
+    assert torch.equal(res['fused'][1].view(torch.int32), res['nccl'][1].view(torch.int32))
+    assert torch.equal(res['fused'][2].view(torch.int32), res['nccl'][2].view(torch.int32))
+    assert res['fused'][3] == res['nccl'][3] and res['fused'][4] == res['nccl'][4] == 3
