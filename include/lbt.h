@@ -56,7 +56,12 @@ enum lbt_mant_kind {
   /* 3-channel signed 9-bit input (the image fed to a first Conv2d_q, bits+1 = 9): every pixel becomes 16
    * s8 bytes {hi0,hi1,hi2, hi0,hi1,hi2, lo0,lo1,lo2, 0 x 7} with k = 2*hi + lo, i.e. a 16-channel s8 NHWC
    * tensor the implicit-GEMM kernels consume against weights packed {W, W, W, 0}.  n_inner % 3 == 0. */
-  LBT_MANT_S9C3 = 4
+  LBT_MANT_S9C3 = 4,
+  /* OR-able flag on the FILTER kind of the convolution entry points: the packed filter was written at least two launches
+   * before this call on the same stream (e.g. by lbt_param_prep at the start of the step), so the kernel may start copying
+   * it before it waits for its immediate predecessor (programmatic dependent launch).  Never set it for a filter produced by
+   * the launch right before the call. */
+  LBT_MANT_PREPARED = 0x100
 };
 
 /* Per-quantiser overflow statistics block: uint64_t[4] on the device. */

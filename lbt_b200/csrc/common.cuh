@@ -91,8 +91,23 @@ inline FastDiv make_fastdiv(uint32_t d) {
 // kernel of the stream start being scheduled (it still waits for this grid's completion at its own pdl_wait()).
 __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr); }
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef LBT_PDL_TRIGGER_AFTER_WAIT
+#define LBT_PDL_TRIGGER_AFTER_WAIT 1
+#endif
+// LBT_PDL_TRIGGER_AFTER_WAIT = 1: a kernel lets its successor start only once its OWN wait has returned, i.e. once its
+// predecessor has completed.  By induction everything older than the immediate predecessor is then complete when a kernel
+// starts, so data produced two or more launches earlier (the packed weights of lbt_param_prep) may be read BEFORE the wait.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if LBT_PDL_TRIGGER_AFTER_WAIT
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#if !LBT_PDL_TRIGGER_AFTER_WAIT
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -555,6 +555,8 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
                                  int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
                                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
                                  const float* addend, void* stream) {
+  const bool w_prepared = (w_kind & LBT_MANT_PREPARED) != 0;
+  w_kind &= ~LBT_MANT_PREPARED;
   if (!src || !wp) return LBT_EINVAL;
   if (q_out) {
     if (!k_out || !sums || !q_out->ib) return LBT_EINVAL;
@@ -573,7 +575,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
     return conv_ldg_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, 0, ib_src,
-                        ib_w, exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream);
+                        ib_w, exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream, nullptr, w_prepared);
   }
   const uint32_t cb = C >= 128 ? 128u : (uint32_t)C;
   if (cb != 16 && cb != 32 && cb != 64 && cb != 128) return LBT_EUNSUPPORTED;

@@ -59,6 +59,7 @@ struct LdgParams {
   uint32_t nstages;              // ring depth
   uint32_t m_tiles;
   int gather;                    // 0 fprop, 1 transposed (dgrad)
+  int w_prepared;                // LBT_MANT_PREPARED: the filter may be read before the programmatic-dependency wait
   const int32_t* ibA;
   const int32_t* ibB;
   int exp_const;
@@ -176,7 +177,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   fence_before();
   __syncthreads();
   fence_after();
-  pdl_wait();   // everything above touched only shared / tensor memory and kernel parameters
+  // everything above touched only shared / tensor memory and kernel parameters.  With LBT_PDL_TRIGGER_AFTER_WAIT the packed
+  // filter bank (written by lbt_param_prep, at least two launches ago) is already final when this kernel starts, so the
+  // epilogue warps start copying it BEFORE waiting for the predecessor (which produced the activations / gradients).
+#if LBT_PDL_TRIGGER_AFTER_WAIT
+  if (p.w_prepared && warp > kLoaderWarps) {
+    for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 32 * kEpiWarps) {
+      const uint32_t kc = i / BN, n = i % BN;
+      const bool v = kc < p.KC && n < p.N;
+      cp_async16(smem_u32(sB + (size_t)i * 16), v ? p.wp + (size_t)n * p.ldw + (size_t)kc * 16 : p.wp, v ? 16u : 0u);
+    }
+    cp_async_arrive_noinc(&b_bar);
+  }
+#endif
+  pdl_wait();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
   volatile int* abort_flag = &s_abort;
   if (threadIdx.x == 0) dbg_stamp(p, 1);
@@ -346,12 +360,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   } else {
     // ===== epilogue warps; first they fetch the resident filter bank (the loaders are already gathering tile 0):
     // chunk kc, output channel n -> 16 bytes (zeros beyond Cout / KC), all copies in flight at once =====
+#if LBT_PDL_TRIGGER_AFTER_WAIT
+    if (!p.w_prepared)
+#endif
+    {
     for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 32 * kEpiWarps) {
       const uint32_t kc = i / BN, n = i % BN;
       const bool v = kc < p.KC && n < p.N;
       cp_async16(smem_u32(sB + (size_t)i * 16), v ? p.wp + (size_t)n * p.ldw + (size_t)kc * 16 : p.wp, v ? 16u : 0u);
     }
     cp_async_arrive_noinc(&b_bar);
+    }
     // TMEM lane quadrant = warp % 4
     const uint32_t quad = warp & 3;
     const uint32_t half = (uint32_t)(warp - (kLoaderWarps + 1)) >> 2;  // which of the quadrant's two warps
@@ -848,7 +867,7 @@ int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C
 int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                  int kh, int kw, int sh, int sw, int pt, int pl, int OH, int OW, int gather, const int32_t* ibA,
                  const int32_t* ibB, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
-                 int8_t* k_out, int64_t* sums, const float* addend, void* stream, const lbt_bn_bwd_link* link) {
+                 int8_t* k_out, int64_t* sums, const float* addend, void* stream, const lbt_bn_bwd_link* link, bool w_prepared) {
   const DeviceInfo& di = device_info();
   const int bn = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128));
   if ((size_t)N * OH * OW >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -901,6 +920,7 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   p.stages_per_tile = (p.KCp + kChunksPerStage - 1) / kChunksPerStage;
   p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
   p.gather = gather;
+  p.w_prepared = w_prepared ? 1 : 0;
   p.ibA = ibA;
   p.ibB = ibB;
   p.exp_const = exp_const;
@@ -974,6 +994,8 @@ extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int O
                                  int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
                                  const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc, const float* addend,
                                  void* stream) {
+  const bool w_prepared = (w_kind & LBT_MANT_PREPARED) != 0;
+  w_kind &= ~LBT_MANT_PREPARED;
   if (!g || !wp || !dx) return LBT_EINVAL;
   if ((g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
@@ -984,12 +1006,14 @@ extern "C" int lbt_conv_i8_dgrad(const void* g, int g_kind, int N, int OH, int O
   LBT_REQUIRE_ARCH();
   // rows = input pixels (n, h, w); gathered tensor = g[N, OH, OW, Cout]; output channels = Cin
   return conv_ldg_run(g, g_kind, N, OH, OW, Cout, wp, w_kind, ldw, Cin, kh, kw, sh, sw, pad_top, pad_left, H, W, 1, ib_g, ib_w,
-                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr);
+                      exp_const, nullptr, dx, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr, w_prepared);
 }
 
 extern "C" int lbt_conv_i8_dgrad_bn(const void* g, int g_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw,
                                     int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_g,
                                     const int32_t* ib_w, int exp_const, const lbt_bn_bwd_link* link, void* stream) {
+  const bool w_prepared = (w_kind & LBT_MANT_PREPARED) != 0;
+  w_kind &= ~LBT_MANT_PREPARED;
   if (!g || !wp || !link) return LBT_EINVAL;
   if ((g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8) || (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8)) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || OH <= 0 || OW <= 0) return LBT_EINVAL;
@@ -1004,7 +1028,7 @@ extern "C" int lbt_conv_i8_dgrad_bn(const void* g, int g_kind, int N, int H, int
   if (!conv_ldg_enabled() || !conv_ldg_ok(C, Cout, kh, kw)) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   return conv_ldg_run(g, g_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, 1, 1, pad_top, pad_left, OH, OW, 0, ib_g, ib_w, exp_const,
-                      nullptr, nullptr, (size_t)Cout, nullptr, nullptr, nullptr, nullptr, stream, link);
+                      nullptr, nullptr, (size_t)Cout, nullptr, nullptr, nullptr, nullptr, stream, link, w_prepared);
 }
 
 // Test / bench knob (not in lbt.h): 0 routes every convolution through the TMA-im2col kernel, 1 (default) lets the
