@@ -8,9 +8,13 @@ A "step" is one full training step (forward, loss, backward with quantised gradi
 range controller) of the workload below on synthetic data.  N > 1 is launched by torchrun, one rank
 per GPU, weak scaling (fixed per-GPU batch), gradient + overflow-counter all-reduce over NCCL.
 
-Workload at N=1 (BASELINE.json configs[1]): CIFAR10_Resnet20 (models.py:453), batch 256 per GPU,
-8-bit dynamic fixed point for W/A/G, stochastic rounding everywhere (the reference's behaviour).
-Rank 0 prints ONE JSON line.
+Default workload (BASELINE.json configs[3], the one the metric's "@1/2/4/8" names and the largest that fits one GPU at its
+stated batch): ResNet-18 composed from the reference's blocks, 224x224, batch 256 per GPU, 8-bit dynamic fixed point for
+W/A/G, stochastic rounding everywhere (the reference's behaviour).  ``--workload resnet20 | cifar10 | resnet50 | resnet50_g8``
+select configs[1] / configs[0] / configs[4] (8-bit W/A + 16-bit G) and its 8-bit-G variant.  The same JSON line carries the
+two microbenchmark halves of the metric (configs[2]): ``quantize`` (lbt_quantize over 2^28 elements, GB/s and fraction of the
+measured HBM peak) and ``gemm`` (lbt_gemm_i8 at 8192^3, TOPS, fraction of the int8 nominal and of torch._int_mm timed in the
+same run).  Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -23,14 +27,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed ncu captures
-# (profiles/): (workload, C-ABI entry) -> bytes per launch (average over the class), or absent = null
-TRAFFIC = {
-    # profiles/r1_conv_ldg_halo_step_ncu_full_summary.csv (ncu --set full inside bench.py, halo-patch loader): the stage-1 launches
-    # (conv_ldg_kernel<16, 1, 1, 0>) read 4.25-4.32 MB from DRAM and write ~0 (their 4-17 MB outputs stay in the 126 MB L2)
-    # vs 8.4-21 MB algorithmic
-    ('resnet20', 'lbt_conv_i8_fprop'): 4.3e6,
-}
+def measured_traffic(workload, entry):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel class, read at run time from the committed
+    `ncu --set full` capture of this very command (profiles/traffic.json, written by benchmarks/ncu_traffic.py from the
+    .ncu-rep): {"<workload>": {"<C-ABI entry>": {"bytes_per_launch": ..., "launches": ..., "source": "<csv>"}}}.
+    None when no capture of that class is committed."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            row = json.load(f).get(workload, {}).get(entry)
+        return (float(row['bytes_per_launch']), row.get('source')) if row else (None, None)
+    except Exception:
+        return None, None
 
 WORKLOADS = {
     # name: (model ctor name, image, classes, default batch per GPU, bits, grad_bits)
@@ -70,10 +77,11 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--workload', default='resnet20', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='resnet18', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (0 = the workload default)')
     ap.add_argument('--no-graph', action='store_true', help='do not capture the step in a CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-micro', action='store_true', help='skip the quantize / GEMM microbenchmark legs (configs[2])')
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the CPU baseline sample (0 = same as GPU)')
     ap.add_argument('--breakdown', action='store_true', help='also print the per-kernel time table to stderr')
     ap.add_argument('--dump-launches', default='', help='write the per-launch device times of one step (CSV) to this file')
@@ -119,24 +127,112 @@ def cpu_steps(a, batch, steps, warmup):
     return batch / dt, dt, cores
 
 
+CPU_BATCH = {'resnet20': 0, 'cifar10': 0, 'resnet18': 8, 'resnet50': 4, 'resnet50_g8': 4}     # 0 = the GPU batch
+
+
 def run_reference(a):
+    """The reference's CPU path (the oracle port: TensorFlow 1.x cannot run here) on all host threads.  The
+    reference is single-device (F11): with N > 1 the N shards of a global batch would be processed by the same host cores
+    one after the other, so the whole-job imgs/s IS the single-run imgs/s; rank 0 alone measures it, on the native arm's
+    config."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     batch = a.batch or WORKLOADS[a.workload][3]
-    cpu_batch = a.cpu_batch or (batch if a.workload in ('resnet20', 'cifar10') else 16)
+    cpu_batch = a.cpu_batch or CPU_BATCH[a.workload] or batch
     ips, dt, cores = cpu_steps(a, cpu_batch, a.steps, a.warmup)
     cfg = describe(a, batch)
-    sample = '%d timed steps of the oracle port (torch-CPU fp32 restatement of dynamic_fixed_point.py) at batch %d' % (a.steps, cpu_batch)
+    sample = ('%d timed steps (after %d warm-up) of the oracle port (torch-CPU fp32 restatement of dynamic_fixed_point.py) on a '
+              'bounded sample of the workload: batch %d per step, %.2f s/step; the host cores are shared by all %d shards, so '
+              'imgs/s does not depend on N' % (a.steps, a.warmup, cpu_batch, dt, a.gpus))
     line = {
         'impl': 'reference', 'metric': 'quantized train imgs/sec', 'value': ips, 'unit': 'imgs/s', 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 (fake-quant on CPU)', 'data': 'synthetic', 'config': cfg,
         'cpu_baseline': {'value': ips, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': ips, 'unit': 'imgs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
         'note': 'TensorFlow 1.x reference cannot run in this image (SURVEY.md F10); this is the CPU oracle port',
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[2]: the two microbenchmark halves of the metric, timed in the same run
+# ------------------------------------------------------------------------------------------------
+
+
+def micro_legs(dev, hbm_peak):
+    """quantize GB/s (2^28 fp32 elements -> s8 mantissas, Philox stochastic rounding, 5 B/element algorithmic) and int8 GEMM
+    TOPS (8192^3, fp32 rescaling epilogue) with the stock cuBLASLt s8 GEMM (torch._int_mm) beside it.  CUDA events around
+    back-to-back launches after warm-up; the 1 GiB quantiser input and the 3 x 64 MiB GEMM operands exceed / rotate past the
+    126 MB L2."""
+    import torch
+    from lbt_b200 import gemm as G, quantizer as Q
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    out = {}
+    n = 1 << 28
+    x = torch.randn(256, n // 256, device=dev)
+    m = torch.empty(256, n // 256, dtype=torch.int8, device=dev)
+    ib = torch.tensor(2, dtype=torch.int32, device=dev)
+    cnt = Q.new_counters(dev)
+    q = {}
+    for key, mode in (('minmax_stats', Q.ROUND_PHILOX | Q.STATS_MINMAX), ('exact_counts', Q.ROUND_PHILOX)):
+        t = timed(lambda: Q.quantize(x, 8, ib, mode=mode, seed=1, offset=Q.make_offset(3, 0), want_fp32=False,
+                                     mant_kind=Q.MANT_S8, out_mant=m, counters=cnt, update_range=False), 10)
+        q[key] = {'gbs': n * 5 / t / 1e9, 'us': t * 1e6, 'frac_hbm': n * 5 / t / 1e9 / hbm_peak}
+    out['quantize'] = {
+        'elements': n, 'bits': 8, 'rounding': 'stochastic (in-kernel Philox)', 'out': 's8 mantissas',
+        'algorithmic_bytes_per_element': 5, 'gbs': q['minmax_stats']['gbs'], 'frac_hbm': q['minmax_stats']['frac_hbm'],
+        'hbm_peak_gbs': hbm_peak, 'target_frac': 0.70,
+        'statistics': 'min/max overflow statistics (LBT_STATS_MINMAX: what every layer call site uses, the reference\'s '
+                      'target_overflow_rate is always 0); exact_counts = the C-ABI default the parity tests compare',
+        'modes': q}
+    del x, m
+    torch.cuda.empty_cache()
+    N = 8192
+    ops = 2.0 * N ** 3
+    pool = [(torch.randint(-128, 128, (N, N), dtype=torch.int8, device=dev),
+             torch.randint(-128, 128, (N, N), dtype=torch.int8, device=dev)) for _ in range(2)]
+    o32 = torch.empty(N, N, dtype=torch.float32, device=dev)
+    it = [0]
+
+    def ours():
+        A, B = pool[it[0] & 1]
+        it[0] += 1
+        G.gemm_i8(A, B, exp_const=-14, out=o32)
+
+    def stock():
+        A, B = pool[it[0] & 1]
+        it[0] += 1
+        torch._int_mm(A, B.t())
+
+    t_ours = timed(ours, 10)
+    try:
+        t_stock = timed(stock, 10)
+    except Exception:
+        t_stock = None
+    out['gemm'] = {
+        'shape': '8192^3 s8 x s8 -> s32 in TMEM, fp32 rescaling epilogue', 'tops': ops / t_ours / 1e12, 'us': t_ours * 1e6,
+        'int8_nominal_tops': 4500.0, 'frac_nominal': ops / t_ours / 1e12 / 4500.0, 'target_frac': 0.60,
+        'int_mm_tops': ops / t_stock / 1e12 if t_stock else None,
+        'frac_of_int_mm': t_stock / t_ours if t_stock else None,
+        'int_mm': 'torch._int_mm (cuBLASLt s8 x s8 -> s32, no epilogue) on the same operands in the same run'}
+    del pool, o32
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -255,33 +351,28 @@ def run_native(a):
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - l0
 
-    # ---- capture the whole step in a CUDA graph --------------------------------------------------
-    graph = None
-    loss_static = None
+    # ---- eager step time (the same step, launched kernel by kernel through ctypes + autograd) ------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        eager_step()
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / 3
+
+    # ---- the product path: Trainer.capture() owns the CUDA graph of the whole step ----------------
+    graph_ok = False
     if not a.no_graph:
         try:
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    eager_step()
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                loss_static = eager_step()
-            torch.cuda.synchronize()
+            trainer.capture(X_view, ys, warmup=2)
+            graph_ok = True
         except Exception as e:  # report, fall back to eager launches (still the CUDA path)
             if rank == 0:
                 print('[bench] CUDA graph capture failed (%s: %s); timing eager launches' % (type(e).__name__, e), file=sys.stderr)
-            graph = None
             torch.cuda.synchronize()
 
     def step():
-        if graph is not None:
-            graph.replay()
-            return loss_static
-        return eager_step()
+        return trainer.step_graph() if graph_ok else eager_step()
 
     def barrier():
         if world > 1:
@@ -322,7 +413,8 @@ def run_native(a):
     # every step: H2D copy of ITS inputs from pinned host memory (prefetched on a copy stream while the previous step runs,
     # lbt_b200.trainer.HostFeeder) and a D2H read of ITS loss (read by the host one step later) — all inside the timed region
     from lbt_b200.trainer import HostFeeder
-    feeder = HostFeeder(step, Xs, ys)
+    feeder = trainer.feeder() if graph_ok else HostFeeder(step, X_view, ys)
+    hostX = [x.permute(0, 3, 1, 2) for x in hostX]          # logical NCHW views of the pinned NHWC batches (same memory)
     feeder.prefetch(hostX[0], hosty[0])
     for i in range(min(3, a.warmup)):
         feeder.prefetch(hostX[(i + 1) % pool], hosty[(i + 1) % pool])
@@ -349,7 +441,6 @@ def run_native(a):
     # (external event nodes), so each replay times every kernel back to back on the device, without host gaps ----
     nprof = 3
     prof = None
-    eager_ms = None
     try:
         prof = _lib.Profiler(external=True)
         s2 = torch.cuda.Stream()
@@ -400,7 +491,6 @@ def run_native(a):
         e1.record()
         _lib.profiler = None
         summ, timing_mode = prof.summary(), 'per-launch CUDA events, eager launches'
-        eager_ms = e0.elapsed_time(e1) / nprof
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_kind = json.load(open(peaks_path))['hbm_gbs'], 'measured (MEASURED_PEAKS.json hbm_gbs)'
@@ -424,40 +514,79 @@ def run_native(a):
     achieved = (q['bytes'] / 1e9) / (q['ms'] * 1e-3) if q['ms'] > 0 else 0.0
     gemm = summ.get('lbt_gemm_i8')
     gemm_tops = (gemm['ops'] / 1e12) / (gemm['ms'] * 1e-3) if gemm and gemm['ms'] > 0 else None
+    conv_ops = sum(d['ops'] for k, d in summ.items() if d['ops'])
+    conv_ms = sum(d['ms'] for k, d in summ.items() if d['ops'])
+    conv_tops = (conv_ops / 1e12) / (conv_ms * 1e-3) if conv_ms > 0 else None     # every contraction of the step
+    dp_mode = trainer.dp_mode
+
+    # ---- after the timed regions: are the replicas still bit-identical? (weights, ranges, step counter) ----
+    rt = model.runtime
+    torch.cuda.synchronize()
+    sums = torch.stack([trainer.flat_w.view(torch.int32).to(torch.int64).sum(),
+                        rt.flat['ranges'].to(torch.int64).sum() * 1000003 + (rt.flat['ranges'].to(torch.int64) *
+                                                                          torch.arange(1, len(rt.sites) + 1, device=dev)).sum(),
+                        rt.dev_step.to(torch.int64).reshape(())])
+    replicas_identical = None
+    if world > 1:
+        lo, hi = sums.clone(), sums.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replicas_identical = bool(torch.equal(lo, hi))
+    dp_error = trainer.dp.error() if trainer.dp is not None else None
+    if world > 1:
+        t = torch.tensor([dp_error or 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dp_error = int(t)
 
     if rank != 0:
         _finish(world)
         return
 
+    # ---- configs[2]: quantise GB/s and int8 GEMM TOPS, same run, N=1 only ----------------------------
+    micro = None
+    if world == 1 and not a.no_micro:
+        torch.cuda.empty_cache()
+        try:
+            micro = micro_legs(dev, peak)
+        except Exception as e:
+            micro = {'error': '%s: %s' % (type(e).__name__, e)}
+
     # ---- CPU baseline (the oracle port on this box's host cores), N=1 only -------------------------
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        cpu_batch = a.cpu_batch or (batch if a.workload in ('resnet20', 'cifar10') else 16)
+        cpu_batch = a.cpu_batch or CPU_BATCH[a.workload] or batch
         ips, dt, cores = cpu_steps(a, cpu_batch, 2, 1)
         cpu = {'value': ips, 'unit': 'imgs/s', 'cores': cores, 'kind': 'port',
                'sample': '2 timed training steps (after 1 warm-up) of the oracle port at batch %d, %.2f s/step' % (cpu_batch, dt)}
 
+    traffic, traffic_src = measured_traffic(a.workload, top)
+    exchange = {
+        'fused': 'lbt_dp_step: one kernel over NVLink peer memory (reduce-scatter by peer loads + SGD on the owned slice + '
+                 'all-gather of the weights by peer stores + counter sum + range controller)',
+        'nccl': 'NCCL all-reduce of gradients and counters + lbt_sgd_momentum + lbt_update_ranges',
+        'unfused': 'single GPU: lbt_sgd_momentum + lbt_update_ranges'}[dp_mode] if world > 1 or dp_mode != 'fused' \
+        else 'single GPU: lbt_dp_step (SGD + range controller + step counter in one launch)'
     line = {
         'metric': 'quantized train imgs/sec', 'value': value, 'unit': 'imgs/s', 'n_gpus': world, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 's8/u8 mantissas, s32 accumulate (8-bit dfxp); fp32 master weights', 'data': 'synthetic',
-        'config': dict(describe(a, batch), exchange={
-            'fused': 'lbt_dp_step: one kernel over NVLink peer memory (reduce-scatter by peer loads + SGD on the owned slice + '
-                     'all-gather of the weights by peer stores + counter sum + range controller)',
-            'nccl': 'NCCL all-reduce of gradients and counters + lbt_sgd_momentum + lbt_update_ranges',
-            'unfused': 'single GPU: lbt_sgd_momentum + lbt_update_ranges'}[trainer.dp_mode] if world > 1 or trainer.dp_mode != 'fused'
-            else 'single GPU: lbt_dp_step (SGD + range controller + step counter in one launch)'),
-        'dp_error': trainer.dp.error() if trainer.dp is not None else None,
+        'dtype': 's8/u8 mantissas, s32 accumulate (8-bit dfxp%s); fp32 master weights' % (', 16-bit gradients as s8/u8 halves' if gbits else ''),
+        'data': 'synthetic',
+        'config': describe(a, batch),
+        'exchange': exchange,
+        'dp_error': dp_error,
+        'replicas_identical': replicas_identical,
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'imgs/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'ms_per_step': e2e_ms, 'wall_ms_per_step': wall / a.steps * 1e3,
-                'how': 'HostFeeder: per-step H2D of the inputs prefetched on a copy stream, per-step D2H loss read one step later'},
+                'how': 'Trainer.capture() + Trainer.feeder(): per-step H2D of the inputs prefetched on a copy stream, the step as '
+                       'one graph launch, per-step D2H loss read one step later'},
         'gpu_launches': launches_per_step * a.steps,
         'launches_per_step': launches_per_step,
-        'cuda_graph': graph is not None,
+        'cuda_graph': graph_ok,
+        'eager_ms_per_step': eager_ms,
         'roofline': {'bound': 'hbm', 'kernel': top, 'achieved': achieved,
                      'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak if peak else None,
-                     'traffic': TRAFFIC.get((a.workload, top)),
+                     'traffic': traffic, 'traffic_source': traffic_src,
                      'peak_kind': peak_kind, 'launches_per_step': q['launches'] // nprof,
                      'avg_launch_us': q['ms'] / max(1, q['launches']) * 1e3,
                      'share_of_step': (q['ms'] / nprof) / ms_step if ms_step else None,
@@ -465,7 +594,11 @@ def run_native(a):
                      'timing': timing_mode,
                      'note': 'tensors of this workload are 1-17 MB: the kernels are launch/latency bound, far below the HBM roofline'
                              if a.workload in ('resnet20', 'cifar10') else None},
+        'quantize': (micro or {}).get('quantize'),
+        'gemm': (micro or {}).get('gemm'),
+        'micro_error': (micro or {}).get('error'),
         'gemm_tops_in_step': gemm_tops,
+        'conv_tops_in_step': conv_tops,
         'breakdown_ms': breakdown,
         'kernel_ms_per_step': ours_ms,
         'loss': final_loss,

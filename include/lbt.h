@@ -95,7 +95,9 @@ uint64_t lbt_launch_count(void);
  *   update_range == 0: counters are left accumulated for lbt_update_ranges() (data-parallel:
  *     all-reduce them first).
  *
- * bits in [2, 24]; bits == 32 must be handled by the caller (pass-through, :22-23).
+ * bits in [1, 31] (everything dfxp:21 accepts below the pass-through); bits == 32 must be handled by the caller
+ * (pass-through, :22-23).  fp32 output for every width; packed mantissas up to 16 bits (17 unsigned).  For bits > 25 the
+ * clip bound L-1 is not an fp32 number and rounds to L, exactly as the reference's fp32 constant does.
  * out_fp32 and out_mant may each be NULL; with both NULL and counters given the launch is a
  * statistics-only pass (overflow_rate / update_range on their own, dynamic_fixed_point.py:48,70).
  * counters may be NULL only when update_range == 0 (no statistics are gathered).  dev_step (device uint64, may be NULL) is added

@@ -94,6 +94,11 @@ _INTERNAL = {
     'lbt_test_fdiv': (c_int, [c_u64, c_u64, c_void_p, c_void_p, c_void_p]),
     'lbt_bn_set_debug': (c_int, [c_void_p]),
     'lbt_conv_ldg_set_debug': (c_int, [c_void_p]),
+    'lbt_dp_tune': (c_int, [c_int]),
+    'lbt_dp_emulate_scratch_bytes': (c_size_t, [c_int]),
+    'lbt_dp_step_emulate': (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    'lbt_bn_debug_error': (c_int, []),
 }
 
 

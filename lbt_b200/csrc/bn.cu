@@ -1140,6 +1140,16 @@ extern "C" int lbt_bn_bwd_fused(const lbt_bn_bwd_args* a, void* stream) {
   return check_launch("lbt_bn_bwd_fused");
 }
 
+// Non-zero once the grid barrier of lbt_bn_bwd_fused has timed out (synchronises the device; not in lbt.h).
+extern "C" int lbt_bn_debug_error() {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, lbt::g_bn_error, sizeof(v)) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return v;
+}
+
 extern "C" int lbt_bn_set_debug(void* dev_u64) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_u64);
   return cudaMemcpyToSymbol(lbt::g_bn_dbg, &p, sizeof(p)) == cudaSuccess ? LBT_OK : LBT_ECUDA;

@@ -61,28 +61,41 @@ __device__ __forceinline__ unsigned long long globaltimer() {
   return t;
 }
 
-// Threads 0..world-1 of the calling CTA each wait for one replica's flag to reach `epoch`.
-__device__ __forceinline__ void wait_flags(uint32_t* pad, int slot0, int world, uint32_t epoch) {
+// Threads 0..world-1 of the calling CTA each wait for one replica's flag to reach `epoch`.  Returns false (CTA-uniform)
+// when a wait timed out or another CTA already raised the sticky error word: the caller must then leave the step
+// untouched (no optimizer, no all-gather, no controller) — summing a slow replica's half-written gradients and storing
+// the result into every peer would corrupt all replicas silently.
+__device__ __forceinline__ bool wait_flags(uint32_t* pad, int slot0, int world, uint32_t epoch) {
+  int bad = 0;
   if ((int)threadIdx.x < world) {
     const uint32_t* f = pad + slot0 + threadIdx.x;
     const unsigned long long t0 = globaltimer();
+    uint32_t spins = 0;
     while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+      if ((++spins & 0xff) == 0 && *reinterpret_cast<volatile uint32_t*>(pad + LBT_DP_PAD_ERROR) != 0u) {
+        bad = 1;
+        break;
+      }
       if (globaltimer() - t0 > kTimeoutNs) {
-        atomicExch(pad + LBT_DP_PAD_ERROR, 1u + (uint32_t)slot0 + threadIdx.x);
+        atomicCAS(pad + LBT_DP_PAD_ERROR, 0u, 1u + (uint32_t)slot0 + threadIdx.x);
+        bad = 1;
         break;
       }
       __nanosleep(64);
     }
   }
-  __syncthreads();
+  return __syncthreads_or(bad) == 0;
 }
 
-__global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
-  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
-  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
+int g_dp_max_blocks = 0;   // lbt_dp_tune: grid cap per replica (0 = 4 CTAs per SM)
+
+__device__ __forceinline__ void dp_step_body(const DpArgs& p) {
   const lbt_dp_peers& pe = p.peers;
   const int world = pe.world, rank = pe.rank;
   uint32_t* pad = pe.pad[rank];
+  // the error word is sticky: once a cross-replica wait has timed out this replica's state is no longer trustworthy and
+  // every later step is a no-op (Trainer raises on DpExchange.error())
+  if (*reinterpret_cast<volatile uint32_t*>(pad + LBT_DP_PAD_ERROR) != 0u) return;
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(pad + LBT_DP_PAD_EPOCH) + 1u;
 
   // ---- barrier A: my gradients and counters are final (kernel boundary), tell everybody; wait for everybody ----
@@ -91,7 +104,7 @@ __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
       __threadfence_system();
       st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_READY + rank, epoch);
     }
-    wait_flags(pad, LBT_DP_PAD_READY, world, epoch);
+    if (!wait_flags(pad, LBT_DP_PAD_READY, world, epoch)) return;   // nothing of this step is applied
   }
 
   // ---- owned slice: sum the replicas' gradients in rank order, momentum SGD, publish the new weights ----
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
   if (!s_last) return;
   if (world > 1) {
     if ((int)threadIdx.x < world) st_release_sys(pe.pad[threadIdx.x] + LBT_DP_PAD_DONE + rank, epoch);
-    wait_flags(pad, LBT_DP_PAD_DONE, world, epoch);
+    if (!wait_flags(pad, LBT_DP_PAD_DONE, world, epoch)) return;    // peers may still be using my buffers: do not close the step
   }
   unsigned long long* mine = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(pe.counters[rank]));
   for (size_t i = threadIdx.x; i < p.n_sites * LBT_CNT_WORDS; i += blockDim.x) mine[i] = 0ull;
@@ -181,6 +194,18 @@ __global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
   }
 }
 
+__global__ void __launch_bounds__(256) dp_step_kernel(const DpArgs p) {
+  pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
+  pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
+  dp_step_body(p);
+}
+
+// All replicas of a SIMULATED world in ONE cooperative launch (tests on a single GPU): grid.y = replica, every slice of the
+// grid runs the unmodified body against its own arguments, and the cooperative launch guarantees what the protocol needs —
+// that all replicas' CTAs are resident at the same time.  (Separate launches that spin on each other's flags have no such
+// guarantee on one GPU.)
+__global__ void __launch_bounds__(256) dp_step_multi_kernel(const DpArgs* all) { dp_step_body(all[blockIdx.y]); }
+
 typedef int (*GetAddressRangeFn)(unsigned long long*, size_t*, unsigned long long);
 
 }  // namespace
@@ -188,9 +213,9 @@ typedef int (*GetAddressRangeFn)(unsigned long long*, size_t*, unsigned long lon
 
 using namespace lbt;
 
-extern "C" int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, float lr, const float* dev_lr, float momentum,
-                           int shard, int32_t* ranges, const int32_t* bits, const float* target, size_t n_sites,
-                           uint64_t* dev_step, void* stream) {
+static int dp_make_args(DpArgs& a, size_t& blocks, const lbt_dp_peers* peers, float* accum, size_t n, float lr, const float* dev_lr,
+                        float momentum, int shard, int32_t* ranges, const int32_t* bits, const float* target, size_t n_sites,
+                        uint64_t* dev_step) {
   if (!peers || !accum) return LBT_EINVAL;
   const int world = peers->world, rank = peers->rank;
   if (world < 1 || world > LBT_DP_MAX_WORLD || rank < 0 || rank >= world) return LBT_EINVAL;
@@ -203,7 +228,6 @@ extern "C" int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, fl
   if ((n & 3) || (reinterpret_cast<uintptr_t>(accum) & 15)) return LBT_EUNSUPPORTED;   // flat buffers are padded to float4
   LBT_REQUIRE_ARCH();
   const DeviceInfo& di = device_info();
-  DpArgs a;
   a.peers = *peers;
   a.accum = accum;
   a.n = n;
@@ -217,12 +241,71 @@ extern "C" int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, fl
   a.n_sites = n_sites;
   a.dev_step = reinterpret_cast<unsigned long long*>(dev_step);
   const size_t mine = a.shard ? (n / 4 + world - 1) / world : n / 4;
-  size_t blocks = (mine + 255) / 256;
-  const size_t cap = (size_t)di.sm_count * 4;     // peer loads need many requests in flight; all CTAs co-resident
+  blocks = (mine + 255) / 256;
+  size_t cap = (size_t)di.sm_count * 4;     // peer loads need many requests in flight; all CTAs co-resident
+  if (g_dp_max_blocks > 0 && (size_t)g_dp_max_blocks < cap) cap = (size_t)g_dp_max_blocks;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  return LBT_OK;
+}
+
+extern "C" int lbt_dp_step(const lbt_dp_peers* peers, float* accum, size_t n, float lr, const float* dev_lr, float momentum,
+                           int shard, int32_t* ranges, const int32_t* bits, const float* target, size_t n_sites,
+                           uint64_t* dev_step, void* stream) {
+  DpArgs a;
+  size_t blocks = 1;
+  const int rc = dp_make_args(a, blocks, peers, accum, n, lr, dev_lr, momentum, shard, ranges, bits, target, n_sites, dev_step);
+  if (rc) return rc;
   launch_pdl(dp_step_kernel, (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), a);
   return check_launch("lbt_dp_step");
+}
+
+// Test entry point (not in lbt.h): the steps of `world` replicas that all live on THIS GPU as one cooperative launch.
+// peers[r] / accum[r] / ranges[r] / dev_step[r] are replica r's arguments of lbt_dp_step; `scratch` is caller-owned device
+// memory of at least lbt_dp_emulate_scratch_bytes(world) bytes.
+extern "C" size_t lbt_dp_emulate_scratch_bytes(int world) { return (size_t)(world > 0 ? world : 0) * sizeof(DpArgs); }
+
+extern "C" int lbt_dp_step_emulate(int world, const lbt_dp_peers* peers, float* const* accum, size_t n, float lr,
+                                   const float* const* dev_lr, float momentum, int shard, int32_t* const* ranges, const int32_t* bits,
+                                   const float* target, size_t n_sites, uint64_t* const* dev_step, void* scratch, void* stream) {
+  if (world < 1 || world > LBT_DP_MAX_WORLD || !peers || !accum || !scratch) return LBT_EINVAL;
+  DpArgs all[LBT_DP_MAX_WORLD];
+  size_t blocks = 1;
+  for (int r = 0; r < world; ++r) {
+    if (peers[r].world != world || peers[r].rank != r) return LBT_EINVAL;
+    size_t b = 1;
+    const int rc = dp_make_args(all[r], b, &peers[r], accum[r], n, lr, dev_lr ? dev_lr[r] : nullptr, momentum, shard,
+                                ranges ? ranges[r] : nullptr, bits, target, n_sites, dev_step ? dev_step[r] : nullptr);
+    if (rc) return rc;
+    blocks = b;   // same n, world, shard for every replica
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dp_step_multi_kernel, 256, 0) != cudaSuccess || occ < 1) occ = 1;
+  const size_t resident = (size_t)occ * (size_t)device_info().sm_count;
+  if (blocks * (size_t)world > resident) blocks = resident / (size_t)world;
+  if (blocks < 1) return LBT_EUNSUPPORTED;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemcpyAsync(scratch, all, sizeof(DpArgs) * world, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "lbt_dp_step_emulate(memcpy)");
+    return LBT_ECUDA;
+  }
+  const DpArgs* dev_all = reinterpret_cast<const DpArgs*>(scratch);
+  void* kargs[] = {(void*)&dev_all};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)dp_step_multi_kernel, dim3((unsigned)blocks, (unsigned)world, 1), dim3(256, 1, 1),
+                                              kargs, 0, st);
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "lbt_dp_step_emulate");
+    (void)cudaGetLastError();
+    return LBT_ECUDA;
+  }
+  return check_launch("lbt_dp_step_emulate");
+}
+
+// Tuning / test knob (not in lbt.h): cap the grid of lbt_dp_step.  Replicas wait for each other inside the kernel, so N
+// replicas simulated on ONE GPU (tests) need all their CTAs co-resident.
+extern "C" int lbt_dp_tune(int max_blocks) {
+  g_dp_max_blocks = max_blocks > 0 ? max_blocks : 0;
+  return LBT_OK;
 }
 
 // Export a caller-owned device buffer to the other replicas (one process per GPU): the CUDA IPC handle of the allocation

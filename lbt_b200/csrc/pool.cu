@@ -16,6 +16,38 @@ struct PoolParams {
   FastDiv d_c4, d_W, d_H, d_OW, d_OH, d_s;
 };
 
+// V = 4: a thread owns 4 consecutive channels (C % 4 == 0, 16-byte aligned tensors); V = 1: one channel (any C — the
+// LeNet-style 6-channel layers of models.py:91-152).  p.c4 holds C / V.
+template <int V>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[V]) {
+  if constexpr (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+template <int V>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[V]) {
+  if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else p[0] = v[0];
+}
+template <int V>
+__device__ __forceinline__ void ld_idx(const uint8_t* p, unsigned char (&w)[V]) {
+  if constexpr (V == 4) {
+    const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else {
+    w[0] = __ldg(p);
+  }
+}
+template <int V>
+__device__ __forceinline__ void st_idx(uint8_t* p, const unsigned char (&w)[V]) {
+  if constexpr (V == 4) *reinterpret_cast<uchar4*>(p) = make_uchar4(w[0], w[1], w[2], w[3]);
+  else p[0] = w[0];
+}
+
+template <int V>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                                 uint8_t* __restrict__ idx, const PoolParams p, size_t total) {
   pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
@@ -27,8 +59,13 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
     const int ow = (int)(pix - t * (uint32_t)p.OW);
     const int n = (int)fastdiv(t, p.d_OH);
     const int oh = (int)(t - (uint32_t)n * (uint32_t)p.OH);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    uchar4 w = make_uchar4(0, 0, 0, 0);
+    float m[V];
+    unsigned char w[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      m[j] = -INFINITY;
+      w[j] = 0;
+    }
     const int h0 = oh * p.s - p.pt, w0 = ow * p.s - p.pl;
     for (int r = 0; r < p.k; ++r) {
       const int ih = h0 + r;
@@ -36,19 +73,23 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
       for (int q = 0; q < p.k; ++q) {
         const int iw = w0 + q;
         if ((unsigned)iw >= (unsigned)p.W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)n * p.H + ih) * p.W + iw) * p.C) + c);
-        const unsigned char t = (unsigned char)(r * p.k + q);
-        if (v.x > m.x || v.x != v.x) { m.x = v.x; w.x = t; }
-        if (v.y > m.y || v.y != v.y) { m.y = v.y; w.y = t; }
-        if (v.z > m.z || v.z != v.z) { m.z = v.z; w.z = t; }
-        if (v.w > m.w || v.w != v.w) { m.w = v.w; w.w = t; }
+        float v[V];
+        ld_vec<V>(x + (((size_t)n * p.H + ih) * p.W + iw) * p.C + (size_t)V * c, v);
+        const unsigned char tt = (unsigned char)(r * p.k + q);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (v[j] > m[j] || v[j] != v[j]) {
+            m[j] = v[j];
+            w[j] = tt;
+          }
       }
     }
-    reinterpret_cast<float4*>(out)[i] = m;
-    reinterpret_cast<uchar4*>(idx)[i] = w;
+    st_vec<V>(out + (size_t)V * i, m);
+    st_idx<V>(idx + (size_t)V * i, w);
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
                                                                 float* __restrict__ dx, const PoolParams p, size_t total) {
   pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
@@ -60,7 +101,9 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
     const int iw = (int)(pix - t * (uint32_t)p.W);
     const int n = (int)fastdiv(t, p.d_H);
     const int ih = (int)(t - (uint32_t)n * (uint32_t)p.H);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
     // windows (oh, ow) with oh*s - pt <= ih < oh*s - pt + k
     const int th = ih + p.pt, tw = iw + p.pl;
     // ceil((th - k + 1) / s) for th - k + 1 >= 0, else 0
@@ -71,17 +114,18 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
       const int r = th - oh * p.s;
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         const int q = tw - ow * p.s;
-        const unsigned char t = (unsigned char)(r * p.k + q);
-        const size_t o = ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c);
-        const uchar4 w = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + o);
-        if (w.x == t) acc.x += gv.x;
-        if (w.y == t) acc.y += gv.y;
-        if (w.z == t) acc.z += gv.z;
-        if (w.w == t) acc.w += gv.w;
+        const unsigned char tt = (unsigned char)(r * p.k + q);
+        const size_t o = ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c) * V;
+        unsigned char w[V];
+        float gv[V];
+        ld_idx<V>(idx + o, w);
+        ld_vec<V>(g + o, gv);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (w[j] == tt) acc[j] += gv[j];
       }
     }
-    reinterpret_cast<float4*>(dx)[i] = acc;
+    st_vec<V>(dx + (size_t)V * i, acc);
   }
 }
 
@@ -187,8 +231,14 @@ void fill_divs(PoolParams& p) {
 
 int check(const PoolParams& p) {
   if (p.N <= 0 || p.H <= 0 || p.W <= 0 || p.C <= 0 || p.k <= 0 || p.s <= 0 || p.OH <= 0 || p.OW <= 0) return LBT_EINVAL;
-  if ((p.C & 3) || p.k > 15 || p.pt < 0 || p.pl < 0) return LBT_EUNSUPPORTED;
+  if (p.k > 15 || p.pt < 0 || p.pl < 0) return LBT_EUNSUPPORTED;
   return LBT_OK;
+}
+
+// vector width of a launch: 4 channels per thread when C % 4 == 0 and every tensor is 16-byte (index bytes: 4-byte) aligned
+inline int pool_vec(int C, const void* a, const void* b, const void* idx) {
+  const bool al = !((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) && !(reinterpret_cast<uintptr_t>(idx) & 3);
+  return ((C & 3) == 0 && al) ? 4 : 1;
 }
 
 }  // namespace
@@ -200,11 +250,10 @@ extern "C" int lbt_maxpool_fwd(const float* x, int N, int H, int W, int C, int k
                                float* out, uint8_t* idx, void* stream) {
   if (!x || !out || !idx) return LBT_EINVAL;
   PoolParams p{};
-  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = pad_top; p.pl = pad_left; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  const int V = pool_vec(C, x, out, idx);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = pad_top; p.pl = pad_left; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / V);
   int rc = check(p);
   if (rc) return rc;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(idx) & 3))
-    return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   const size_t total = (size_t)N * OH * OW * p.c4;
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -213,9 +262,10 @@ extern "C" int lbt_maxpool_fwd(const float* x, int N, int H, int W, int C, int k
   const size_t cap = (size_t)device_info().sm_count * 8;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (k == 3) launch_pdl(maxpool_fwd_k_kernel<3>, grid, kThreads, 0, st, x, out, idx, p, total);
+  if (V == 1) launch_pdl(maxpool_fwd_kernel<1>, grid, kThreads, 0, st, x, out, idx, p, total);
+  else if (k == 3) launch_pdl(maxpool_fwd_k_kernel<3>, grid, kThreads, 0, st, x, out, idx, p, total);
   else if (k == 2) launch_pdl(maxpool_fwd_k_kernel<2>, grid, kThreads, 0, st, x, out, idx, p, total);
-  else launch_pdl(maxpool_fwd_kernel, grid, kThreads, 0, st, x, out, idx, p, total);
+  else launch_pdl(maxpool_fwd_kernel<4>, grid, kThreads, 0, st, x, out, idx, p, total);
   return check_launch("lbt_maxpool_fwd");
 }
 
@@ -223,11 +273,10 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
                                int pad_left, int OH, int OW, float* dx, void* stream) {
   if (!g || !idx || !dx) return LBT_EINVAL;
   PoolParams p{};
-  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = pad_top; p.pl = pad_left; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  const int V = pool_vec(C, g, dx, idx);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = pad_top; p.pl = pad_left; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / V);
   int rc = check(p);
   if (rc) return rc;
-  if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15) || (reinterpret_cast<uintptr_t>(idx) & 3))
-    return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   const size_t total = (size_t)N * H * W * p.c4;
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
@@ -236,9 +285,10 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
   const size_t cap = (size_t)device_info().sm_count * 8;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (k == 3 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<3>, grid, kThreads, 0, st, g, idx, dx, p, total);
+  if (V == 1) launch_pdl(maxpool_bwd_kernel<1>, grid, kThreads, 0, st, g, idx, dx, p, total);
+  else if (k == 3 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<3>, grid, kThreads, 0, st, g, idx, dx, p, total);
   else if (k == 2 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<2>, grid, kThreads, 0, st, g, idx, dx, p, total);
-  else launch_pdl(maxpool_bwd_kernel, grid, kThreads, 0, st, g, idx, dx, p, total);
+  else launch_pdl(maxpool_bwd_kernel<4>, grid, kThreads, 0, st, g, idx, dx, p, total);
   return check_launch("lbt_maxpool_bwd");
 }
 
@@ -250,12 +300,11 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
 namespace lbt {
 namespace {
 
+template <int V>
 __global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                                 const PoolParams p, size_t total) {
   pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
   pdl_wait();      // ... and this one touches global memory only after its predecessor has completed
-  const float inv = 1.0f;  // the window sum is DIVIDED by k*k below (same arithmetic as the oracle's restatement)
-  (void)inv;
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
     uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
     const uint32_t c = (uint32_t)i - pix * p.c4;
@@ -263,35 +312,38 @@ __global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const float* __re
     const int ow = (int)(pix - t * (uint32_t)p.OW);
     const int n = (int)fastdiv(t, p.d_OH);
     const int oh = (int)(t - (uint32_t)n * (uint32_t)p.OH);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
     // the window is summed in (r, q) order like the oracle; the loads of 16 taps are issued together so a global 8x8
     // pool costs 4 memory round trips per thread instead of 64
     const int taps = p.k * p.k;
-    const float* base = x + (((size_t)n * p.H + oh * p.s) * p.W + ow * p.s) * p.C;
+    const float* base = x + (((size_t)n * p.H + oh * p.s) * p.W + ow * p.s) * p.C + (size_t)V * c;
     for (int t0 = 0; t0 < taps; t0 += 16) {
-      float4 v[16];
+      float v[16][V];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t = t0 + j;
-        if (t < taps) {
-          const int r = t / p.k, q = t - r * p.k;
-          v[j] = __ldg(reinterpret_cast<const float4*>(base + ((size_t)r * p.W + q) * p.C) + c);
+        const int tt = t0 + j;
+        if (tt < taps) {
+          const int r = tt / p.k, q = tt - r * p.k;
+          ld_vec<V>(base + ((size_t)r * p.W + q) * p.C, v[j]);
         }
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (t0 + j < taps) {
-          acc.x = __fadd_rn(acc.x, v[j].x);
-          acc.y = __fadd_rn(acc.y, v[j].y);
-          acc.z = __fadd_rn(acc.z, v[j].z);
-          acc.w = __fadd_rn(acc.w, v[j].w);
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = __fadd_rn(acc[e], v[j][e]);
         }
     }
-    const float d = (float)(p.k * p.k);
-    reinterpret_cast<float4*>(out)[i] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
+    const float d = (float)(p.k * p.k);   // the window sum is DIVIDED by k*k (same arithmetic as the oracle's restatement)
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = __fdiv_rn(acc[e], d);
+    st_vec<V>(out + (size_t)V * i, acc);
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const float* __restrict__ g, float* __restrict__ dx, const PoolParams p,
                                                                 size_t total) {
   pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
@@ -307,16 +359,17 @@ __global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const float* __re
     const int oh_lo = ih - p.k + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(ih - p.k + p.s), p.d_s);
     const int ow_lo = iw - p.k + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(iw - p.k + p.s), p.d_s);
     const int oh_hi = min(p.OH - 1, (int)fastdiv((uint32_t)ih, p.d_s)), ow_hi = min(p.OW - 1, (int)fastdiv((uint32_t)iw, p.d_s));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
     for (int oh = oh_lo; oh <= oh_hi; ++oh)
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c));
-        acc.x = __fadd_rn(acc.x, __fdiv_rn(gv.x, d));
-        acc.y = __fadd_rn(acc.y, __fdiv_rn(gv.y, d));
-        acc.z = __fadd_rn(acc.z, __fdiv_rn(gv.z, d));
-        acc.w = __fadd_rn(acc.w, __fdiv_rn(gv.w, d));
+        float gv[V];
+        ld_vec<V>(g + ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c) * V, gv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = __fadd_rn(acc[e], __fdiv_rn(gv[e], d));
       }
-    reinterpret_cast<float4*>(dx)[i] = acc;
+    st_vec<V>(dx + (size_t)V * i, acc);
   }
 }
 
@@ -383,33 +436,35 @@ __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__
 extern "C" int lbt_avgpool_fwd(const float* x, int N, int H, int W, int C, int k, int s, int OH, int OW, float* out, void* stream) {
   if (!x || !out) return LBT_EINVAL;
   PoolParams p{};
-  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  const int V = pool_vec(C, x, out, nullptr);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / V);
   int rc = check(p);
   if (rc) return rc;
   if ((OH - 1) * s + k > H || (OW - 1) * s + k > W) return LBT_EINVAL;   // 'VALID': every window inside the input
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   const size_t total = (size_t)N * OH * OW * p.c4;
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
-  launch_pdl(avgpool_fwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), x, out, p, total);
+  if (V == 4) launch_pdl(avgpool_fwd_kernel<4>, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), x, out, p, total);
+  else launch_pdl(avgpool_fwd_kernel<1>, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), x, out, p, total);
   return check_launch("lbt_avgpool_fwd");
 }
 
 extern "C" int lbt_avgpool_bwd(const float* g, int N, int H, int W, int C, int k, int s, int OH, int OW, float* dx, void* stream) {
   if (!g || !dx) return LBT_EINVAL;
   PoolParams p{};
-  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / 4);
+  const int V = pool_vec(C, g, dx, nullptr);
+  p.N = N; p.H = H; p.W = W; p.C = C; p.k = k; p.s = s; p.pt = 0; p.pl = 0; p.OH = OH; p.OW = OW; p.c4 = (uint32_t)(C / V);
   int rc = check(p);
   if (rc) return rc;
-  if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15)) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   const size_t total = (size_t)N * H * W * p.c4;
   if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
   fill_divs(p);
   const size_t blocks = (total + kThreads - 1) / kThreads, cap = (size_t)device_info().sm_count * 8;
-  launch_pdl(avgpool_bwd_kernel, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), g, dx, p, total);
+  if (V == 4) launch_pdl(avgpool_bwd_kernel<4>, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), g, dx, p, total);
+  else launch_pdl(avgpool_bwd_kernel<1>, (unsigned)(blocks < cap ? blocks : cap), kThreads, 0, reinterpret_cast<cudaStream_t>(stream), g, dx, p, total);
   return check_launch("lbt_avgpool_bwd");
 }
 

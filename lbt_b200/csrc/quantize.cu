@@ -351,7 +351,7 @@ extern "C" int lbt_quantize(const float* x, size_t n_outer, size_t n_inner, int 
                             const uint64_t* dev_step, float* out_fp32, void* out_mant, int mant_kind,
                             uint64_t* counters, int update_range, void* stream) {
   if (!x || !integer_bits) return LBT_EINVAL;
-  if (bits < 2 || bits > 24) return LBT_EINVAL;
+  if (bits < 1 || bits > 31) return LBT_EINVAL;   // dfxp:21 accepts 1..32; 32 is the caller's pass-through (:22-23)
   // LBT_STATS_MINMAX: min/max tracking instead of exact overflow counts (valid for target_overflow_rate == 0)
   const bool minmax = (mode & LBT_STATS_MINMAX) != 0 && target_overflow_rate == 0.0f && counters != nullptr;
   mode &= ~LBT_STATS_MINMAX;
@@ -455,7 +455,7 @@ extern "C" int lbt_quantize_residual(const float* grad, size_t n_grad_rows, floa
                                      int32_t* integer_bits, int mode, const float* noise, uint64_t seed, uint64_t offset,
                                      const uint64_t* dev_step, float* out, uint64_t* counters, void* stream) {
   if (!buffer || !integer_bits || (n_grad_rows && (!grad || !out))) return LBT_EINVAL;
-  if (bits < 2 || bits > 24 || mode < 0 || mode > 2 || n_grad_rows > n_outer) return LBT_EINVAL;
+  if (bits < 1 || bits > 31 || mode < 0 || mode > 2 || n_grad_rows > n_outer) return LBT_EINVAL;
   if (mode == LBT_ROUND_STOCHASTIC_NOISE && !noise) return LBT_EINVAL;
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
   LBT_REQUIRE_ARCH();

@@ -7,7 +7,6 @@ that module running against the real layers.  Two defects of the original are re
 classifier with 120*1*1 features only for 28x28 inputs (kept: the flatten adapts to whatever the features produce).
 """
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import dfxp
 from .dfxp import Conv2d_q, Linear_q
@@ -35,7 +34,7 @@ class CUSTOM_MNIST(nn.Module):
         out = out.permute(0, 2, 3, 1).reshape(out.size(0), -1)
         if self.fc1 is None:
             self.fc1 = Linear_q(self.bits, out.shape[1], 84, runtime=self.runtime, name='fc1').to(out.device)     # custom.py:29
-        out = F.relu(self.fc1(out))                                                                               # custom.py:35-36
+        out = dfxp.ReLU_q()(self.fc1(out))                                                                              # custom.py:35-36
         return self.fc2(out)
 
     def _make_layers(self, cfg):
@@ -45,7 +44,7 @@ class CUSTOM_MNIST(nn.Module):
                 layers.append(dfxp.MaxPool_q(2, 2, 'VALID'))                                                      # custom.py:45
             else:
                 layers += [conv5x5(self.bits, in_channels, x, runtime=self.runtime, name='conv%d' % i,
-                                   input_signed=(in_channels == 1)), nn.ReLU()]
+                                   input_signed=(in_channels == 1)), dfxp.ReLU_q()]
                 in_channels = x
         return nn.Sequential(*layers)
 

@@ -26,7 +26,6 @@ import math
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib, gemm as G, quantizer as Q
 
@@ -57,6 +56,12 @@ class Runtime:
         self._noise_req = {}         # (quantiser id, n_inner) wanted by fused tensor-core epilogues
         self._noise_tab = None       # dict(map={key: fp32 view}, jobs=device table, total=groups, keep=[...])
         self._noise_valid = False
+        self._n_dropout = 0          # dropout sites are numbered per runtime, like the quantisers (reproducible across processes)
+
+    def next_dropout_id(self):
+        d = self._n_dropout
+        self._n_dropout += 1
+        return d
 
     # ---- per-step noise arena: ONE launch fills the noise vectors the conv epilogues read (same Philox stream) ----
     def noise_for(self, site, n_inner, device):
@@ -356,6 +361,13 @@ class _GradQuant(torch.autograd.Function):
         dy = _mem_contig(dy)
         q, _ = ctx.site.quantize(dy)
         return q, None
+
+
+def _require_cuda_f32(x, who):
+    """The path has no CPU / PyTorch fallback: anything but an fp32 CUDA tensor is an error."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise _lib.LbtError('%s: expects an fp32 CUDA tensor (got %s on %s); there is no CPU or PyTorch fallback'
+                            % (who, x.dtype, x.device))
 
 
 def _mem_contig(x):
@@ -665,6 +677,17 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
     return dx, dW, db
 
 
+def _check_layer_bits(who, bits, grad_bits):
+    """Widths the tensor-core layers take, checked at construction (the reference's --bits is free, main.py:112; the
+    quantiser itself — lbt_quantize / weight_quantization — takes every width of dfxp:21): weights and activations ride the
+    8-bit integer tensor cores (conv activations bits+1 = 9 as u8 / split), gradients up to 16 bits as hi/lo halves."""
+    if not 2 <= int(bits) <= 8:
+        raise _lib.LbtError('%s: bits=%d — the integer tensor-core layers take 2..8-bit weights/activations '
+                            '(gradients up to 16 bits via grad_bits); wider DFXP only through weight_quantization()' % (who, bits))
+    if grad_bits is not None and not 2 <= int(grad_bits) <= 16:
+        raise _lib.LbtError('%s: grad_bits=%d — gradient quantisers take 2..16 bits' % (who, grad_bits))
+
+
 def _split16(gm16):
     """s16 mantissas -> (hi s8, lo u8) with k = 256*hi + lo (lbt_split_s16)."""
     hi = torch.empty(gm16.shape, dtype=torch.int8, device=gm16.device)
@@ -789,6 +812,7 @@ class Conv2d_q(nn.Module):
                  grad_bits=None, input_signed=True, name='conv', runtime=None, implicit=True):
         super().__init__()
         rt = runtime or default_runtime()
+        _check_layer_bits('Conv2d_q', bits, grad_bits)
         kh, kw = (kernel_size, kernel_size) if isinstance(kernel_size, int) else kernel_size
         self.stride = (stride, stride) if isinstance(stride, int) else tuple(stride)
         if isinstance(padding, str):
@@ -903,6 +927,7 @@ class Linear_q(nn.Module):
                  input_range=2, weight_range=2, bias_range=2, grad_range=2, grad_bits=None, name='dense', runtime=None):
         super().__init__()
         rt = runtime or default_runtime()
+        _check_layer_bits('Linear_q', bits, grad_bits)
         self.bits, self.weight_decay, self.name = bits, float(weight_decay), name
         limit = (6 / (in_features + out_features)) ** 0.5                                      # dfxp:338
         self.weight = nn.Parameter(torch.empty(in_features, out_features).uniform_(-limit, limit))
@@ -1089,7 +1114,8 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
                            (1 if gm is not None else 0))
     # small tensors: both passes in one launch (lbt_bn_bwd_fused); it declines shapes that are not one wave of CTAs
     fused = False
-    if FUSE_BN_BWD and pre is None:
+    # (its grid barrier needs every CTA co-resident: not while weight-gradient kernels share the SMs on the side stream)
+    if FUSE_BN_BWD and pre is None and not getattr(rt, '_side_pending', False):
         a = _lib.BnBwdArgs(g=_lib.ptr(g_), out=_lib.ptr(out_), k2=_lib.ptr(k2), k1=_lib.ptr(k1), n_outer=N, n_inner=n_inner, C=C,
                            relu=relu_mode, bits2=resc.qX.bits, bits1=norm.qX.bits, ib2=_lib.ptr(resc.qX.range),
                            ib1=_lib.ptr(norm.qX.range), gamma_q=_lib.ptr(gq), beta_q=_lib.ptr(bq),
@@ -1351,7 +1377,7 @@ class BatchNorm2d_q(nn.Sequential):
         y = self[1](self[0](x))
         if add is not None:
             y = y + add
-        return F.relu(y) if relu else y
+        return _ReLUFn.apply(y) if relu else y
 
     def info(self):
         return 'BatchNorm'
@@ -1389,9 +1415,8 @@ class ReLU_q(nn.Module):
     """dfxp:983-990."""
 
     def forward(self, x):
-        if x.is_cuda and x.dtype == torch.float32:
-            return _ReLUFn.apply(x)
-        return F.relu(x)
+        _require_cuda_f32(x, 'ReLU_q')
+        return _ReLUFn.apply(x)
 
     def info(self):
         return 'ReLU'
@@ -1438,11 +1463,10 @@ class MaxPool_q(nn.Module):
         else:
             pt = pb = pl = pr = 0
             OH, OW = (H - self.k) // self.s + 1, (W - self.k) // self.s + 1
-        if x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype == torch.float32 and self.k <= 15:
-            return _MaxPoolFn.apply(x, self.k, self.s, pt, pl, OH, OW)
-        if pt or pb or pl or pr:
-            x = F.pad(x, (pl, pr, pt, pb), value=float('-inf'))
-        return F.max_pool2d(x, self.k, self.s)
+        _require_cuda_f32(x, 'MaxPool_q')
+        if x.dim() != 4 or self.k > 15:
+            raise _lib.LbtError('MaxPool_q: needs a 4-d tensor and a window of at most 15x15')
+        return _MaxPoolFn.apply(x, self.k, self.s, pt, pl, OH, OW)
 
 
 class _AvgPoolFn(torch.autograd.Function):
@@ -1477,9 +1501,10 @@ class AvgPool_q(nn.Module):
         self.k, self.s = kernel_size, stride
 
     def forward(self, x):
-        if x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype == torch.float32 and self.k <= 15:
-            return _AvgPoolFn.apply(x, self.k, self.s)
-        return F.avg_pool2d(x, self.k, self.s)
+        _require_cuda_f32(x, 'AvgPool_q')
+        if x.dim() != 4:
+            raise _lib.LbtError('AvgPool_q: needs a 4-d tensor')
+        return _AvgPoolFn.apply(x, self.k, self.s)
 
 
 class _XentFn(torch.autograd.Function):
@@ -1507,9 +1532,10 @@ class _XentFn(torch.autograd.Function):
 
 def softmax_cross_entropy(logits, labels):
     """reduce_mean(sparse_softmax_cross_entropy_with_logits) of models.py:30-32."""
-    if logits.is_cuda and logits.dim() == 2 and logits.dtype == torch.float32 and labels.dtype == torch.int64:
-        return _XentFn.apply(logits, labels.contiguous())
-    return F.cross_entropy(logits, labels, reduction='mean')
+    _require_cuda_f32(logits, 'softmax_cross_entropy')
+    if logits.dim() != 2 or not labels.is_cuda:
+        raise _lib.LbtError('softmax_cross_entropy: expects [batch, classes] logits and CUDA integer labels')
+    return _XentFn.apply(logits, labels.to(torch.int64).contiguous())
 
 
 class _DropoutFn(torch.autograd.Function):
@@ -1540,30 +1566,23 @@ class _DropoutFn(torch.autograd.Function):
 class Dropout_q(nn.Module):
     """tf.nn.dropout(x, keep_prob) = x / keep * floor(keep + u) (dfxp:1025-1040); keep_prob is KEEP."""
 
-    _next_id = [0]
-
     def __init__(self, keep_prob, runtime=None):
         super().__init__()
         self.keep_prob = keep_prob
         self.uniform_fn = None      # tests: callable(x) -> the reference's uniform tensor (memory order of x)
-        self.runtime = runtime
-        self.did = Dropout_q._next_id[0]
-        Dropout_q._next_id[0] += 1
+        self.runtime = runtime or default_runtime()
+        self.did = self.runtime.next_dropout_id()      # per model, not per process: a resumed run replays the same stream
 
     def forward(self, x):
         if not self.training or self.keep_prob >= 1.0:
             return x
-        if x.is_cuda and x.dtype == torch.float32:
-            rt = self.runtime
-            if self.uniform_fn is not None:
-                u = _mem_contig(self.uniform_fn(x).to(torch.float32))
-                return _DropoutFn.apply(x, self.keep_prob, u, 0, 0, None)
-            seed = rt.seed if rt is not None else 0
-            # Philox stream disjoint from the quantisers': ids count down from 2^31
-            return _DropoutFn.apply(x, self.keep_prob, None, seed, Q.make_offset(0x7fffffff - self.did, 0),
-                                    rt.dev_step if rt is not None else None)
-        u = self.uniform_fn(x) if self.uniform_fn is not None else torch.rand_like(x)
-        return x / self.keep_prob * torch.floor(self.keep_prob + u)
+        _require_cuda_f32(x, 'Dropout_q')
+        rt = self.runtime
+        if self.uniform_fn is not None:
+            u = _mem_contig(self.uniform_fn(x).to(torch.float32))
+            return _DropoutFn.apply(x, self.keep_prob, u, 0, 0, None)
+        # Philox stream disjoint from the quantisers': ids count down from 2^31
+        return _DropoutFn.apply(x, self.keep_prob, None, rt.seed, Q.make_offset(0x7fffffff - self.did, 0), rt.dev_step)
 
 
 class Flatten_q(nn.Module):
@@ -1693,7 +1712,7 @@ class ResidualBlock_q(nn.Module):
         sc = self.shortcut(x)
         if isinstance(last, BatchNorm2d_q):
             return last(r, add=sc, relu=True)
-        return F.relu(last(r) + sc)
+        return _ReLUFn.apply(last(r) + sc)
 
     def info(self):
         return 'Residual block'

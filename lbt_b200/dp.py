@@ -113,3 +113,36 @@ class DpExchange:
         for b in self._opened:
             _lib.lib().lbt_dp_close(ctypes.c_void_p(b))
         self._opened = []
+
+
+def emulate_step(peers, accums, n_params, lr, momentum, ranges, bits, target, n_sites, dev_steps, *, dev_lrs=None, shard=True):
+    """The lbt_dp_step of every replica of a world that lives on ONE GPU, as a single cooperative launch (lbt_dp_step_emulate:
+    grid.y = replica).  Test plumbing for single-GPU boxes: separate launches that spin on each other's flags are not
+    guaranteed to run at the same time on one device.  ``peers``: list of DpPeers (replica r at index r); the other arguments
+    are per-replica lists of tensors (``bits`` / ``target`` are shared)."""
+    world = len(peers)
+    arr = (_lib.DpPeers * world)(*peers)
+    vp = ctypes.c_void_p * world
+    acc = vp(*[_lib.ptr(a) for a in accums])
+    rng = vp(*[_lib.ptr(r) for r in ranges])
+    stp = vp(*[_lib.ptr(s) for s in dev_steps])
+    lrs = vp(*[_lib.ptr(t) for t in dev_lrs]) if dev_lrs is not None else None
+    dev = accums[0].device
+    scratch = torch.empty(int(_lib.lib().lbt_dp_emulate_scratch_bytes(world)), dtype=torch.uint8, device=dev)
+    _lib.call('lbt_dp_step_emulate', world, ctypes.addressof(arr), ctypes.addressof(acc), int(n_params), float(lr),
+              ctypes.addressof(lrs) if lrs is not None else None, float(momentum), 1 if shard else 0, ctypes.addressof(rng),
+              _lib.ptr(bits), _lib.ptr(target), int(n_sites), ctypes.addressof(stp), _lib.ptr(scratch), _lib.stream())
+    return scratch      # keep alive until the stream has run the launch
+
+
+def emulate_trainers(trainers):
+    """``Trainer.apply()`` for N Trainers that simulate N replicas on one GPU (their DpExchange.peers wired to each other's
+    arenas): one cooperative launch instead of N launches that wait for each other."""
+    t0 = trainers[0]
+    rts = [t.model.runtime for t in trainers]
+    keep = emulate_step([t.dp.peers for t in trainers], [t.flat_a for t in trainers], t0.dp.arena.n_params, t0.lr, t0.momentum,
+                        [rt.flat['ranges'] for rt in rts], rts[0].flat['bits'], rts[0].flat['target'], len(rts[0].sites),
+                        [rt.dev_step for rt in rts], dev_lrs=[t.dev_lr for t in trainers])
+    for rt in rts:
+        rt.close_step()
+    return keep

@@ -7,7 +7,6 @@ over the layers' custom Functions (each of which quantises its incoming gradient
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import dfxp
 

@@ -177,6 +177,60 @@ class Trainer:
         self.apply()
         return loss
 
+    # ---- the hot loop as ONE graph launch per step (trainer.py:144-162) ------------------------------------------------
+    def capture(self, X_static, y_static, warmup=2):
+        """Capture ``step(X_static, y_static)`` — forward, loss, backward, exchange, optimizer, controller: ~150 launches
+        on two streams — into a CUDA graph.  Afterwards ``step_graph()`` replays it on whatever ``X_static`` / ``y_static``
+        hold at that moment and returns the (static) loss tensor; ``feeder()`` wraps it for pinned host batches.  All state
+        a step reads or writes (weights, ranges, counters, momentum, step counter = noise position) lives on the device, so
+        a replayed step is bit-identical to an eager one (tests/test_data_gpu.py).  ``warmup`` eager steps run first on a
+        side stream (allocator warm-up, lazy tables); they are REAL training steps."""
+        if not X_static.is_cuda or not y_static.is_cuda:
+            raise _lib.LbtError('Trainer.capture needs static CUDA input tensors')
+        self._static = (X_static, y_static)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(int(warmup)):
+                self.step(X_static, y_static)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.step(X_static, y_static)
+        torch.cuda.synchronize(self.device)
+        self._graph, self._graph_loss = graph, loss
+        return self
+
+    @property
+    def captured(self):
+        return getattr(self, '_graph', None) is not None
+
+    def step_graph(self):
+        """One training step = one graph launch, on the current contents of the static inputs.  Returns the loss tensor
+        (static: read it, or copy it, before the next replay overwrites it)."""
+        self._graph.replay()
+        return self._graph_loss
+
+    def feeder(self):
+        """HostFeeder over the captured step: per-step H2D of pinned host batches on a copy stream, per-step D2H of the loss
+        read one step later — the device-side replacement of the reference's feed_dict round trip (trainer.py:146-160)."""
+        if not self.captured:
+            raise _lib.LbtError('Trainer.feeder: call capture(X_static, y_static) first')
+        return HostFeeder(self.step_graph, *self._static)
+
+    def check(self):
+        """Raise if a device-side watchdog fired: a cross-replica wait of lbt_dp_step timed out (the kernel then skips the
+        optimizer and every later step: the error word is sticky), or a grid barrier of the fused BN backward gave up.
+        Synchronises; fit() calls it once per epoch, state_dict() always."""
+        if self.dp is not None:
+            e = self.dp.error()
+            if e:
+                raise _lib.LbtError('lbt_dp_step: a cross-replica wait timed out (flag slot %d); the replicas are no longer '
+                                    'in step — this run cannot continue' % (e - 1))
+        if _lib.lib().lbt_bn_debug_error():
+            raise _lib.LbtError('lbt_bn_bwd_fused: the grid barrier timed out; gradients of that step are invalid')
+
     # ---- evaluation (trainer.py:164-187) ---------------------------------------------------------------------------
     @torch.no_grad()
     def evaluate(self, X, y, batch_size=1000):
@@ -191,10 +245,16 @@ class Trainer:
         for m in norms:
             m.momentum = 1.0                       # running <- 1.0 * running + 0.0 * batch: unchanged
         counters = rt.flat['counters'].clone()
+        # the reference draws fresh quantiser / dropout noise at every sess.run (dfxp:36): every test batch gets its own
+        # position of the Philox stream, disjoint from the training steps' (bit 31 of the step word), and the training
+        # position is restored afterwards
+        step_saved = rt.dev_step.clone()
+        base = (int(step_saved.item()) & 0x7FFFF) << 12
         loss_sum, acc_sum, n_batches = 0.0, 0.0, 0
         try:
             for i in range(0, X.shape[0], batch_size):
                 xb, yb = X[i:i + batch_size], y[i:i + batch_size]
+                rt.dev_step.fill_(0x80000000 | ((base + n_batches) & 0x7FFFFFFF))
                 logits = self.model(xb)
                 loss_sum += float(self.model.loss(logits, yb))
                 acc_sum += float((logits.argmax(dim=1) == yb).float().mean())
@@ -203,16 +263,23 @@ class Trainer:
             for m, mom in zip(norms, saved):
                 m.momentum = mom
             rt.flat['counters'].copy_(counters)    # the overflow statistics of a test batch never reach the controller
+            rt.dev_step.copy_(step_saved)
         return loss_sum / max(1, n_batches), acc_sum / max(1, n_batches)          # mean of per-batch means, as trainer.py:185-186
 
     # ---- the epoch loop (trainer.py:109-187) ---------------------------------------------------------------------------
     def fit(self, pipeline, n_epoch, batch_size, *, lr_decay_factor=0.1, decay_epochs=(80, 120, 140), test=None, log=None,
-            max_batches=None):
+            max_batches=None, graph=False):
         """``pipeline``: lbt_b200.data.Pipeline over the device-resident training set (shuffle + flip / pad-4 / crop on
         the GPU).  The learning rate is multiplied by ``lr_decay_factor`` at epochs 80, 120 and 140 and the optimizer is
         re-created (momentum slots zeroed) exactly there (trainer.py:117-132).  ``test`` = (X, y) evaluated after each
-        epoch.  Returns [(epoch, last_train_loss, test_loss, test_acc)]."""
+        epoch.  ``graph=True``: full batches run as replays of the captured step (capture() on first use; the pipeline
+        writes each batch straight into the static inputs), a short last batch runs eagerly.  With several replicas the
+        pipeline must be rank-aware (lbt_b200.data.Pipeline shards every global batch by rank).
+        Returns [(epoch, last_train_loss, test_loss, test_acc)]."""
         history = []
+        if self.world > 1 and getattr(pipeline, 'world', 1) != self.world:
+            raise _lib.LbtError('Trainer.fit: %d replicas but the pipeline is sharded %d ways — every replica would train on '
+                                'the same samples' % (self.world, getattr(pipeline, 'world', 1)))
         for epoch in range(n_epoch):
             if epoch in decay_epochs:
                 self.set_lr(self.lr * lr_decay_factor, reset_momentum=True)
@@ -220,9 +287,18 @@ class Trainer:
             for b, (X, y) in enumerate(pipeline.epoch(batch_size, epoch)):
                 if max_batches is not None and b >= max_batches:
                     break
-                loss = self.step(X, y)
+                if graph and X.shape[0] == batch_size:
+                    if not self.captured:
+                        Xs = torch.empty_like(X, memory_format=torch.channels_last) if X.dim() == 4 else torch.empty_like(X)
+                        self.capture(Xs.copy_(X), torch.empty_like(y).copy_(y), warmup=0)
+                    self._static[0].copy_(X)
+                    self._static[1].copy_(y)
+                    loss = self.step_graph().clone()
+                else:
+                    loss = self.step(X, y)
                 if log is not None and (b + 1) % 100 == 0:
                     log('Batch %d loss %f' % (b + 1, float(loss)))
+            self.check()
             tl, ta = self.evaluate(*test) if test is not None else (None, None)
             history.append((epoch, float(loss) if loss is not None else None, tl, ta))
             if log is not None and ta is not None:
@@ -234,6 +310,7 @@ class Trainer:
         """Everything the reference's Saver holds — weights, every ``*_range`` variable, the BN running statistics, the
         optimizer slots — plus what the TF session held implicitly (step counter = noise stream position, lr)."""
         rt = self.model.runtime
+        self.check()
         accum = self.flat_a.clone()
         if self.dp is not None and self.world > 1:       # sharded optimizer: every replica holds only its slice
             dist.all_reduce(accum, op=dist.ReduceOp.SUM, group=self.group)

@@ -41,8 +41,8 @@ def test_argument_validation_without_gpu():
     ib = (ctypes.c_int32 * 1)(2)
     p = ctypes.cast(buf, ctypes.c_void_p)
     q = ctypes.cast(ib, ctypes.c_void_p)
-    assert h.lbt_quantize(p, 1, 4, 1, q, 0.0, 0, None, 0, 0, None, p, None, 0, None, 0, None) == -1     # bits < 2
-    assert h.lbt_quantize(p, 1, 4, 33, q, 0.0, 0, None, 0, 0, None, p, None, 0, None, 0, None) == -1    # bits > 24
+    assert h.lbt_quantize(p, 1, 4, 0, q, 0.0, 0, None, 0, 0, None, p, None, 0, None, 0, None) == -1     # bits < 1
+    assert h.lbt_quantize(p, 1, 4, 32, q, 0.0, 0, None, 0, 0, None, p, None, 0, None, 0, None) == -1    # bits > 31 (32 = the caller's pass-through)
     assert h.lbt_quantize(p, 1, 4, 8, q, 0.0, 1, None, 0, 0, None, p, None, 0, None, 0, None) == -1     # noise mode, no noise
     assert h.lbt_quantize(p, 1, 4, 9, q, 0.0, 0, None, 0, 0, None, None, p, 1, None, 0, None) == -1     # 9 bits into s8
     assert h.lbt_quantize(p, 1, 4, 8, q, 0.0, 0, None, 0, 0, None, p, None, 0, None, 1, None) == -1     # update w/o counters
@@ -77,7 +77,7 @@ def test_new_entry_points_validate_arguments_without_gpu():
     assert h.lbt_augment_batch(p, None, None, 0, 8, 8, 3, 4, 1, None, 0, 0, None, None, p, None) == 0
     # error-feedback quantiser: more gradient rows than buffer rows, bad bits, noise mode without noise; empty is a no-op
     assert h.lbt_quantize_residual(p, 3, p, 2, 4, 8, ib, 0, None, 0, 0, None, p, None, None) == -1
-    assert h.lbt_quantize_residual(p, 1, p, 2, 4, 1, ib, 0, None, 0, 0, None, p, None, None) == -1
+    assert h.lbt_quantize_residual(p, 1, p, 2, 4, 0, ib, 0, None, 0, 0, None, p, None, None) == -1
     assert h.lbt_quantize_residual(p, 1, p, 2, 4, 8, ib, 1, None, 0, 0, None, p, None, None) == -1
     assert h.lbt_quantize_residual(p, 0, p, 0, 4, 8, ib, 0, None, 0, 0, None, p, None, None) == 0
     # fused dgrad + BN backward: the link descriptor is mandatory and must be complete

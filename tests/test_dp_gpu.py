@@ -1,7 +1,8 @@
 """lbt_dp_step (csrc/dp.cu): the data-parallel end of a step as one kernel over peer memory.
 
 * world = 1: bit-identical to lbt_sgd_momentum + lbt_update_ranges + lbt_step_advance;
-* world = 2..4 simulated on ONE GPU (one arena and one stream per "replica", peers = each other's arenas): the flag
+* world = 2..4 simulated on ONE GPU (one arena per "replica", peers = each other's arenas, all replicas' kernel bodies in one
+  cooperative launch — lbt_dp_step_emulate — so they are co-resident by construction): the flag
   protocol, the rank-ordered gradient sum, the owner-computes SGD and the weight all-gather, the counter sum + controller
   against the oracle's range_delta, over several consecutive steps (epochs), sharded and replicated;
 * two real GPUs (skipped on a one-GPU box): Trainer(dp='fused') == Trainer(dp='nccl') bit for bit at world 2.
@@ -19,7 +20,7 @@ from oracle import dfxp as O
 pytestmark = pytest.mark.gpu
 
 from lbt_b200 import _lib  # noqa: E402
-from lbt_b200.dp import Arena, make_peers  # noqa: E402
+from lbt_b200.dp import Arena, emulate_step, make_peers  # noqa: E402
 
 
 def _ref_sgd(w, a, gs, lr, mom):
@@ -98,7 +99,6 @@ def test_simulated_replicas_on_one_gpu(world, shard):
     arenas = [Arena(n_sites, n, dev) for _ in range(world)]
     bases = [a.buf.data_ptr() for a in arenas]
     peers = [make_peers(r, bases, arenas[0]) for r in range(world)]
-    streams = [torch.cuda.Stream() for _ in range(world)]
     w0 = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(dev)
     for a in arenas:
         a.flat_w.copy_(w0)
@@ -116,12 +116,10 @@ def test_simulated_replicas_on_one_gpu(world, shard):
         for r in range(world):
             arenas[r].flat_g.copy_(gs[r])
             arenas[r].counters.copy_(cs[r])
+        # the replicas' lbt_dp_step bodies as ONE cooperative launch (grid.y = replica): co-residency guaranteed
+        keep = emulate_step(peers, accum, n, 0.01 * (it + 1), 0.9, ranges, bits, None, n_sites, steps, shard=bool(shard))
         torch.cuda.synchronize()
-        for r in range(world):
-            with torch.cuda.stream(streams[r]):
-                _lib.call('lbt_dp_step', ctypes.addressof(peers[r]), _lib.ptr(accum[r]), n, 0.01 * (it + 1), None, 0.9, shard,
-                          _lib.ptr(ranges[r]), _lib.ptr(bits), None, n_sites, _lib.ptr(steps[r]), _lib.stream())
-        torch.cuda.synchronize()
+        del keep
         w_ref, a_ref = _ref_sgd(w_ref, a_ref, gs, 0.01 * (it + 1), 0.9)
         tot = sum(c.cpu() for c in cs)
         for i in range(n_sites):

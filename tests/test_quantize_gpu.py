@@ -103,6 +103,40 @@ def test_parity_with_oracle(shape, bits, mode):
     assert cnt.cpu().numpy().tolist() == [0, 0, 0, 0]
 
 
+@pytest.mark.parametrize('bits', [1, 2, 3, 17, 24, 25, 26, 28, 31])
+@pytest.mark.parametrize('mode', ['nearest', 'noise'])
+def test_every_width_the_reference_accepts(bits, mode):
+    """dfxp:21 asserts 1 <= bits <= 32 and 32 is a pass-through: every width below it runs in lbt_quantize (fp32 output;
+    packed mantissas stop at 16 bits).  Includes the widths whose clip bound L-1 is not an fp32 number (bits > 25): it
+    rounds to L in the reference's fp32 constant, in the oracle and here alike."""
+    rng = np.random.default_rng(bits * 7 + len(mode))
+    for ib0 in (2, -3, min(bits - 1, 5)):
+        scale = 2.0 ** ib0
+        x = (rng.standard_normal((37, 515)) * scale * 0.7).astype(np.float32)
+        x.reshape(-1)[::97] = np.float32(scale)
+        x.reshape(-1)[1::97] = np.float32(-scale)
+        x.reshape(-1)[2::97] = np.float32(scale * (1 - 2.0 ** -20))
+        if mode == 'nearest':
+            q_ref, _ = O.quantize_nearest(x, bits, ib0)
+            kw = dict(mode=Q.ROUND_NEAREST)
+        else:
+            u = rng.random(x.shape[1:]).astype(np.float32)
+            q_ref, _ = O.quantize_stochastic(x, bits, ib0, u)
+            kw = dict(mode=Q.ROUND_NOISE, noise=dev(u))
+        n1, n2 = O.overflow_counts(x, bits, ib0)
+        r = O.Range(ib0)
+        O.update_range(x, 0.0, bits, r)
+        ib = ibt(ib0)
+        cnt = Q.new_counters('cuda')
+        q, _ = Q.quantize(dev(x), bits, ib, counters=cnt, update_range=False, **kw)
+        assert same_bits(q.cpu().numpy(), q_ref), (bits, ib0)
+        c = cnt.cpu().numpy()
+        assert (int(c[0]), int(c[1]), int(c[2])) == (n1, n2, x.size)
+        cnt.zero_()
+        Q.quantize(dev(x), bits, ib, want_fp32=False, counters=cnt, update_range=True, **kw)
+        assert int(ib) == r.value
+
+
 def test_philox_noise_fill_matches_oracle():
     for n in [1, 3, 4, 5, 1000, 4099]:
         u = Q.noise_fill(n, seed=0xDEADBEEFCAFE, offset=Q.make_offset(77, 123456))
