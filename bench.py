@@ -83,6 +83,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-micro', action='store_true', help='skip the quantize / GEMM microbenchmark legs (configs[2])')
     ap.add_argument('--cpu-batch', type=int, default=0, help='batch of the CPU baseline sample (0 = same as GPU)')
+    ap.add_argument('--no-pdl', action='store_true', help='A/B: launch without programmatic dependent launch edges')
+    ap.add_argument('--no-overlap', action='store_true', help='A/B: weight-gradient kernels on the main stream (no side branch)')
     ap.add_argument('--breakdown', action='store_true', help='also print the per-kernel time table to stderr')
     ap.add_argument('--dump-launches', default='', help='write the per-launch device times of one step (CSV) to this file')
     return ap.parse_args()
@@ -323,6 +325,10 @@ def run_native(a):
     torch.manual_seed(0)
     model = getattr(M, name)(bits, **kw).to(dev)
     trainer = Trainer(model, lr=1e-2, momentum=0.9)
+    if a.no_pdl:
+        _lib.lib().lbt_set_pdl(0)
+    if a.no_overlap:
+        model.runtime.overlap = False
 
     # synthetic data: a small pool of pinned host batches (NHWC fp32, like the reference's feed_dict)
     rng = np.random.default_rng(1234 + rank)

@@ -180,6 +180,18 @@ int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B, int b_kind
                 void* stream);
 
 /*
+ * The same GEMM with a 9..16-bit A operand given as its two byte planes k = 256 * hi + lo (A_hi s8, A_lo u8, same pitch):
+ *   out_f32[m*ldc + n] = RN_fp32((256 * A_hi + A_lo)[m, :] . B[n, :] * 2^(exp_const + *ibA + *ibB)) (+ addend[m*ldc + n]).
+ * The input-gradient GEMM of dfxp:305 / :460 with a gradient quantiser wider than 8 bits (BASELINE config 5, 16-bit G): both
+ * halves are staged per K block beside ONE copy of B, two s32 accumulators per tile live in tensor memory and the epilogue
+ * combines them in 64-bit integers before the single rounding — no int64 accumulator in HBM, no second pass over B.
+ * K <= 65536; N tiles of at most 128 columns (two accumulator pairs fill the 512 tensor-memory columns).
+ */
+int lbt_gemm_i8_dual(const int8_t* A_hi, const uint8_t* A_lo, size_t lda, const void* B, int b_kind, size_t ldb, size_t M,
+                     size_t N, size_t K, const int32_t* ibA, const int32_t* ibB, int exp_const, float* out_f32, size_t ldc,
+                     const float* addend, void* stream);
+
+/*
  * out[i] = fp32(acc64[i]) * 2^(exp_const + *ibA + *ibB) (+ add_scale * add[i]) — the wgrad tail
  * `tf.gradients(y, W, gradq) + 2 * weight_decay * W` (dynamic_fixed_point.py:207, 302, 457).
  */
@@ -366,6 +378,8 @@ int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, in
  * [-> d_add = masked g] -> kg2 = Q(g) (dfxp:687) -> sums[0..C) = sum kg2 (dbeta, :690),
  * sums[C..2C) = sum kg2*k2 (dgamma, :689) -> dx2 = gq2 * gamma_q (:691) -> kg1 = Q(dx2) (dfxp:621)
  * -> sums[2C..3C) = sum kg1, sums[3C..4C) = sum kg1*k1.
+ * kg1_kind: LBT_MANT_S8 (both gradient quantisers <= 8 bits) or LBT_MANT_S16 (up to 16 bits — BASELINE config 5's 16-bit
+ * gradients: kg1 is then int16 [n_outer, n_inner] and the per-thread partial sums are 64-bit).
  */
 int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
                            size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
@@ -373,16 +387,19 @@ int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int
                            const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
                            const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
                            uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
-                           int8_t* kg1, int64_t* sums, int stats_minmax, void* stream);
+                           void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, void* stream);
 /*
  * bwd 2: dx = (gq1 - mean(gq1) - xhat * mean(gq1 * xhat)) / sqrt(var + eps), the batch-norm VJP that
  * tf.gradients(y, X, gradq) yields for dfxp:616 (dfxp:623), from kg1, k1 and the two sum buffers.
  * q_grad != NULL: dx is quantised on the spot with the PRODUCING convolution's gradient quantiser (`gradq`,
- * dfxp:300) into g_mant (s8) with that site's statistics; `dx` may then be NULL.
+ * dfxp:300) into g_mant (s8) with that site's statistics; `dx` may then be NULL.  A q_grad of 9..16 bits writes the
+ * mantissa as its two byte planes k = 256 * hi + lo — g_mant = hi (s8), g_mant_lo = lo (u8) — the operands of
+ * lbt_gemm_i8_dual / the alpha = 256 | 1 passes of lbt_conv_i8_wgrad.  kg1_kind as in lbt_bn_bwd_quant_stats.
  */
-int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
+int lbt_bn_bwd_apply(const void* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
                      const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
-                     const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream);
+                     const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, int kg1_kind,
+                     uint8_t* g_mant_lo, void* stream);
 
 /*
  * lbt_bn_bwd_quant_stats + lbt_bn_bwd_apply in ONE launch, for tensors small enough that the whole tensor is one wave of

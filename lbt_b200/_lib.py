@@ -28,6 +28,8 @@ SIGNATURES = {
     'lbt_gemm_i8': (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_int,
                             c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
                             c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    'lbt_gemm_i8_dual': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p,
+                                 c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     'lbt_acc64_finalize': (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p,
                                    c_void_p]),
     'lbt_im2col_i8': (c_int, [c_void_p, c_int] + [c_int] * 13 + [c_void_p, c_size_t, c_void_p]),
@@ -64,9 +66,9 @@ SIGNATURES = {
     'lbt_bn_bwd_quant_stats': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,
                                        c_void_p, c_void_p, c_u64, c_void_p, c_u64, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_int, c_void_p]),
+                                       c_void_p, c_int, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
-                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'lbt_dp_step': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
                             c_size_t, c_void_p, c_void_p]),
     'lbt_dp_export': (c_int, [c_void_p, c_void_p, c_void_p]),

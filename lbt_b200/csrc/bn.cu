@@ -14,6 +14,8 @@
 // n_inner = H*W*C]; the rounding noise is indexed by the inner position and shared over N (dfxp:36).
 // A thread owns 4 consecutive channels of one inner position and walks down N, so its Philox draw and
 // its per-channel partial sums live in registers.
+#include <type_traits>
+
 #include "qsite.cuh"
 
 namespace lbt {
@@ -81,8 +83,8 @@ struct Acc {
 };
 
 // Add the thread's partials for channels c0..c0+3 straight into the global sums (general path).
-template <int NS>
-__device__ __forceinline__ void flush_global(Acc<NS>& a, long long* sums, int C, int c0) {
+template <int NS, typename T>
+__device__ __forceinline__ void flush_global(Acc<NS, T>& a, long long* sums, int C, int c0) {
 #pragma unroll
   for (int i = 0; i < NS; ++i)
 #pragma unroll
@@ -95,8 +97,8 @@ __device__ __forceinline__ void flush_global(Acc<NS>& a, long long* sums, int C,
 // Fixed-channel path: every thread kept the same channel group (c0 = 4 * (tid % (C/4))) for the whole
 // kernel.  Reduce across the lanes of a warp that share a group, then across warps through shared memory,
 // then one global atomic per (sum, channel) per CTA.
-template <int NS>
-__device__ __forceinline__ void flush_block(Acc<NS>& a32, long long* sums, int C, unsigned long long* s_acc) {
+template <int NS, typename T>
+__device__ __forceinline__ void flush_block(Acc<NS, T>& a32, long long* sums, int C, unsigned long long* s_acc) {
   const int groups = C >> 2;
   for (int i = threadIdx.x; i < NS * C; i += kThreads) s_acc[i] = 0ull;
   __syncthreads();
@@ -140,6 +142,28 @@ __device__ __forceinline__ void unpack4(uint32_t w, int (&k)[4]) {
 __device__ __forceinline__ uint32_t pack4(const float (&k)[4]) {
   const int i0 = __float2int_rn(k[0]), i1 = __float2int_rn(k[1]), i2 = __float2int_rn(k[2]), i3 = __float2int_rn(k[3]);
   return (uint32_t)(i0 & 0xff) | ((uint32_t)(i1 & 0xff) << 8) | ((uint32_t)(i2 & 0xff) << 16) | ((uint32_t)(i3 & 0xff) << 24);
+}
+
+// 16-bit gradient mantissas (BASELINE config 5: grad_bits = 16): four s16 values travel as one 8-byte word; a 16-bit
+// mantissa handed to the tensor cores is stored as its two byte planes k = 256 * hi + lo (hi s8, lo u8).
+__device__ __forceinline__ void unpack4_s16(uint2 w, int (&k)[4]) {
+  k[0] = (int)(short)(w.x & 0xffff);
+  k[1] = (int)(short)(w.x >> 16);
+  k[2] = (int)(short)(w.y & 0xffff);
+  k[3] = (int)(short)(w.y >> 16);
+}
+__device__ __forceinline__ uint2 pack4_s16(const float (&k)[4]) {
+  const int i0 = __float2int_rn(k[0]), i1 = __float2int_rn(k[1]), i2 = __float2int_rn(k[2]), i3 = __float2int_rn(k[3]);
+  return make_uint2((uint32_t)(i0 & 0xffff) | ((uint32_t)(i1 & 0xffff) << 16), (uint32_t)(i2 & 0xffff) | ((uint32_t)(i3 & 0xffff) << 16));
+}
+__device__ __forceinline__ void pack4_hilo(const float (&k)[4], uint32_t& hi, uint32_t& lo) {
+  hi = lo = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = __float2int_rn(k[j]);
+    hi |= (uint32_t)((v >> 8) & 0xff) << (8 * j);     // arithmetic shift: floor(v / 256) in [-128, 127]
+    lo |= (uint32_t)(v & 0xff) << (8 * j);
+  }
 }
 
 // x / n for the per-channel element count n.  The fp64 division is a ~20-deep dependent chain on a chip with a token fp64
@@ -227,10 +251,10 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
             *reinterpret_cast<uint32_t*>(p.k1 + (r + i) * p.t.n_inner + 4 * (size_t)v) = pack4(k);
           }
       }
-      if (!p.t.fixed_channels) flush_global<2>(acc, p.sums, p.t.C, (int)((4ull * v) % (uint64_t)p.t.C));
+      if (!p.t.fixed_channels) flush_global(acc, p.sums, p.t.C, (int)((4ull * v) % (uint64_t)p.t.C));
     }
   }
-  if (p.t.fixed_channels) flush_block<2>(acc, p.sums, p.t.C, s_acc);
+  if (p.t.fixed_channels) flush_block(acc, p.sums, p.t.C, s_acc);
   if (mm) mm_to_counts(c, mx, mn, n1, n2);
   publish_counters(p.q.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
 }
@@ -410,10 +434,13 @@ struct Bwd1Params {
   QSite qg2;            // Rescale_q's gradient quantiser (dfxp:687)
   QSite qg1;            // Normalization_q's gradient quantiser (dfxp:621)
   float* d_add;         // optional: gradient w.r.t. the fused shortcut input (= masked g)
-  int8_t* kg1;
+  void* kg1;            // s8, or s16 in the WIDE instantiation
   long long* sums;      // [4*C]: sum kg2, sum kg2*k2, sum kg1, sum kg1*k1
 };
 
+// WIDE: a gradient quantiser wider than 8 bits — kg1 is stored as s16 and the per-thread partial sums are 64-bit
+// (a 16-bit mantissa times an 8-bit one, summed down 4096 rows, does not fit 32).
+template <bool WIDE>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
@@ -427,7 +454,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
   uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
   float amx = -INFINITY, amn = INFINITY, bmx = -INFINITY, bmn = INFINITY;
   const bool mm2 = p.qg2.minmax != 0, mm1 = p.qg1.minmax != 0;
-  Acc<4> acc;
+  using AccT = typename std::conditional<WIDE, long long, int>::type;
+  Acc<4, AccT> acc;
   acc.zero();
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
@@ -495,13 +523,14 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
               acc.s[3][j] += kg1i * k1[j];
             }
             if (p.d_add) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
-            *reinterpret_cast<uint32_t*>(p.kg1 + idx) = pack4(kq1);
+            if (WIDE) *reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(p.kg1) + idx) = pack4_s16(kq1);
+            else *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(p.kg1) + idx) = pack4(kq1);
           }
       }
-      if (!p.t.fixed_channels) flush_global<4>(acc, p.sums, C, c0);
+      if (!p.t.fixed_channels) flush_global(acc, p.sums, C, c0);
     }
   }
-  if (p.t.fixed_channels) flush_block<4>(acc, p.sums, C, s_acc);
+  if (p.t.fixed_channels) flush_block(acc, p.sums, C, s_acc);
   const size_t numel = p.t.n_outer * p.t.n_inner;
   if (mm2) mm_to_counts(cg2, amx, amn, a1, a2);
   if (mm1) mm_to_counts(cg1, bmx, bmn, b1, b2);
@@ -514,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
 // ------------------------------------------------------------------------------------------------
 struct Bwd2Params {
   Tiling t;
-  const int8_t* kg1;
+  const void* kg1;         // s8, or s16 in the WIDE instantiation
   const int8_t* k1;
   int bits1;
   const int32_t* ib1;
@@ -525,9 +554,11 @@ struct Bwd2Params {
   const long long* bsums;  // [4*C] backward sums (uses [2C..4C))
   float* dx;               // may be NULL when qg is on
   QSite qg;                // optional: the producing convolution's gradient quantiser (bits == 0: off)
-  int8_t* g_mant;
+  int8_t* g_mant;          // its mantissas: s8, or the HIGH byte plane when qg.bits > 8 ...
+  uint8_t* g_mant_lo;      // ... with the low byte plane here (k = 256 * hi + lo)
 };
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   extern __shared__ float s_par[];  // [5*C]: mean, 1/den, mean_g, mean_gxhat, (unused)
   __shared__ uint32_t s_red[16];
@@ -554,11 +585,12 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
       for (int i = 0; i < kRows; ++i)
         if (r0 + i < r1) {
           const size_t idx = (r0 + i) * p.t.n_inner + 4 * (size_t)v;
-          prefetch_l1(p.kg1 + idx);
+          prefetch_l1(reinterpret_cast<const int8_t*>(p.kg1) + (WIDE ? 2 : 1) * idx);
           prefetch_l1(p.k1 + idx);
         }
     }
   }
+  const bool q16 = gq_on && p.qg.bits > 8;
   const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
   const QC cg = make_qc(p.bitsg1, __ldg(p.ibg1));
   const DivN n = make_divn((unsigned long long)(p.t.n_outer * (p.t.n_inner / C)));
@@ -570,7 +602,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     const double sg = (double)p.bsums[2 * C + ch] * (double)cg.inv_m;                       // sum gq
     const double sgx = (double)p.bsums[3 * C + ch] * (double)cg.inv_m * (double)c1.inv_m;   // sum gq*xq
     const double mg = div_n(sg, n);
-    const double mgx = div_n((sgx - (double)mean * sg) / (double)den, n);                        // mean(gq * xhat)
+    // mean(gq * xhat); every fp64 operation rounded on its own (no DFMA contraction) so the oracle can restate it
+    const double mgx = div_n(__ddiv_rn(__dsub_rn(sgx, __dmul_rn((double)mean, sg)), (double)den), n);
     s_par[ch] = mean;
     s_par[C + ch] = den;
     s_par[2 * C + ch] = (float)mg;
@@ -602,12 +635,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     }
     const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
     for (size_t r = r0; r < r1; r += kRows) {
-      uint32_t wg[kRows], w1[kRows];
+      uint2 wg[kRows];
+      uint32_t w1[kRows];
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
           const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
-          wg[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.kg1 + idx));
+          if (WIDE) wg[i] = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(p.kg1) + idx));
+          else wg[i].x = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(p.kg1) + idx));
           w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
         }
 
@@ -616,7 +651,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
         if (r + i < r1) {
           const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
           int kg[4], k1[4];
-          unpack4(wg[i], kg);
+          if (WIDE) unpack4_s16(wg[i], kg);
+          else unpack4(wg[i].x, kg);
           unpack4(w1[i], k1);
           float o[4];
 #pragma unroll
@@ -624,14 +660,21 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
             const float gq = __int2float_rn(kg[j]) * cg.inv_m;
             const float xhat = fdiv_by(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j], rden[j]);
             // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616)
-            o[j] = fdiv_by(gq - mg[j] - xhat * mgx[j], den[j], rden[j]);
+            o[j] = fdiv_by(__fsub_rn(__fsub_rn(gq, mg[j]), __fmul_rn(xhat, mgx[j])), den[j], rden[j]);   // one rounding per op
           }
           if (p.dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
           if (gq_on) {                                                        // the convolution's gradq, dfxp:300
             float kq[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) kq[j] = mmq ? squant_mm(o[j], uq[j], cq, mx, mn) : squant(o[j], uq[j], cq, n1, n2);
-            *reinterpret_cast<uint32_t*>(p.g_mant + idx) = pack4(kq);
+            if (q16) {   // 9..16-bit gradient: the two byte planes the tensor cores consume (no separate split pass)
+              uint32_t hi, lo;
+              pack4_hilo(kq, hi, lo);
+              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = hi;
+              *reinterpret_cast<uint32_t*>(p.g_mant_lo + idx) = lo;
+            } else {
+              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = pack4(kq);
+            }
           }
         }
     }
@@ -758,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
         }
     }
   }
-  flush_block<4>(acc, p.sums, C, s_acc);
+  flush_block(acc, p.sums, C, s_acc);
   const size_t numel = p.t.n_outer * p.t.n_inner;
   if (mm2) mm_to_counts(cg2, amx, amn, a1, a2);
   if (mm1) mm_to_counts(cg1, bmx, bmn, b1, b2);
@@ -796,7 +839,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
     const double sg = (double)__ldcg(p.sums + 2 * C + ch) * (double)cg1.inv_m;
     const double sgx = (double)__ldcg(p.sums + 3 * C + ch) * (double)cg1.inv_m * (double)c1.inv_m;
     const double mg = div_n(sg, n);
-    const double mgx = div_n((sgx - (double)mean * sg) / (double)den, n);
+    const double mgx = div_n(__ddiv_rn(__dsub_rn(sgx, __dmul_rn((double)mean, sg)), (double)den), n);
     s_par[ch] = mean;
     s_par[C + ch] = den;
     s_par[2 * C + ch] = (float)mg;
@@ -834,7 +877,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
       for (int j = 0; j < 4; ++j) {
         const float gqv = __int2float_rn(kg[j]) * cg1.inv_m;
         const float xhat = fdiv_by(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j], rden[j]);
-        o[j] = fdiv_by(gqv - mg[j] - xhat * mgx[j], den[j], rden[j]);
+        o[j] = fdiv_by(__fsub_rn(__fsub_rn(gqv, mg[j]), __fmul_rn(xhat, mgx[j])), den[j], rden[j]);
       }
       if (p2.dx) *reinterpret_cast<float4*>(p2.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
       if (gq_on) {
@@ -855,15 +898,28 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
 // Resident CTAs per SM of a kernel with `smem` dynamic bytes (cached per kernel and device).
 template <typename K>
 int ctas_per_sm(K kernel, size_t smem) {
-  static int cache[16] = {};
+  // keyed by the kernel's address: instantiations of one kernel template share their function-pointer TYPE
+  struct Entry {
+    const void* fn;
+    int n;
+  };
+  static Entry cache[16][4] = {};
   const int dev = device_info().device;
   if (dev < 0 || dev >= 16) return 1;
-  if (cache[dev] == 0) {
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
-    cache[dev] = n;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (Entry& e : cache[dev]) {
+    if (e.fn == key) return e.n;
+    if (e.fn == nullptr) {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+      e.n = n;
+      e.fn = key;
+      return n;
+    }
   }
-  return cache[dev];
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, smem) != cudaSuccess || n < 1) n = 1;
+  return n;
 }
 
 // Tiles = (256-float4 column chunks) x (groups of batch rows).  These tensors are small (a few MB): what matters is
@@ -1017,18 +1073,23 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
                                       const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
                                       const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
                                       uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
-                                      int8_t* kg1, int64_t* sums, int stats_minmax, void* stream) {
+                                      void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, void* stream) {
   if (!g || !k2 || !k1 || !ib2 || !gamma_q || !beta_q || !ib_g2 || !ib_g1 || !kg1 || !sums) return LBT_EINVAL;
   if (relu < 0 || relu > 2 || (relu == 2 && !out)) return LBT_EINVAL;
-  if (bits2 < 2 || bits2 > 8 || bits_g2 < 2 || bits_g2 > 8 || bits_g1 < 2 || bits_g1 > 8) return LBT_EUNSUPPORTED;
+  if (kg1_kind != LBT_MANT_S8 && kg1_kind != LBT_MANT_S16) return LBT_EINVAL;
+  const bool wide = kg1_kind == LBT_MANT_S16;
+  const int gmax = wide ? 16 : 8;
+  // the gradient quantisers take up to 16 bits with s16 storage; s8 storage needs BOTH <= 8 (32-bit partial sums)
+  if (bits2 < 2 || bits2 > 8 || bits_g2 < 2 || bits_g2 > gmax || bits_g1 < 2 || bits_g1 > gmax) return LBT_EUNSUPPORTED;
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
-  if (!al16(g) || !al4(k2) || !al4(k1) || !al4(kg1) || (out && !al16(out)) || (d_add && !al16(d_add)) ||
-      (noise_g2 && !al16(noise_g2)) || (noise_g1 && !al16(noise_g1)))
+  if (!al16(g) || !al4(k2) || !al4(k1) || !(wide ? (reinterpret_cast<uintptr_t>(kg1) & 7) == 0 : al4(kg1)) || (out && !al16(out)) ||
+      (d_add && !al16(d_add)) || (noise_g2 && !al16(noise_g2)) || (noise_g1 && !al16(noise_g1)))
     return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   Bwd1Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel, (size_t)4 * C * 8));
+  int rc = wide ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel<true>, (size_t)4 * C * 8))
+                : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel<false>, (size_t)4 * C * 8));
   if (rc) return rc;
   p.g = g;
   p.out = out;
@@ -1045,26 +1106,37 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   p.kg1 = kg1;
   p.sums = reinterpret_cast<long long*>(sums);
   const size_t smem = (size_t)4 * C * 8;
-  if ((rc = set_smem(bn_bwd1_kernel, smem))) return rc;
-  launch_pdl(bn_bwd1_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  if (wide) {
+    if ((rc = set_smem(bn_bwd1_kernel<true>, smem))) return rc;
+    launch_pdl(bn_bwd1_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  } else {
+    if ((rc = set_smem(bn_bwd1_kernel<false>, smem))) return rc;
+    launch_pdl(bn_bwd1_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  }
   return check_launch("lbt_bn_bwd_quant_stats");
 }
 
-extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
+extern "C" int lbt_bn_bwd_apply(const void* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,
                                 const int32_t* ib1, const int64_t* fwd_sums, float eps, int bits_g1, const int32_t* ib_g1,
-                                const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, void* stream) {
+                                const int64_t* bwd_sums, float* dx, const lbt_qsite* q_grad, int8_t* g_mant, int kg1_kind,
+                                uint8_t* g_mant_lo, void* stream) {
   if (!kg1 || !k1 || !ib1 || !fwd_sums || !ib_g1 || !bwd_sums) return LBT_EINVAL;
   if (!dx && !q_grad) return LBT_EINVAL;
+  if (kg1_kind != LBT_MANT_S8 && kg1_kind != LBT_MANT_S16) return LBT_EINVAL;
+  const bool wide = kg1_kind == LBT_MANT_S16;
+  if (bits1 < 2 || bits1 > 8 || bits_g1 < 2 || bits_g1 > (wide ? 16 : 8)) return LBT_EUNSUPPORTED;
   if (q_grad) {
     if (!g_mant || !q_grad->ib || !al4(g_mant) || (q_grad->noise && !al16(q_grad->noise))) return LBT_EINVAL;
-    if (q_grad->bits < 2 || q_grad->bits > 8) return LBT_EUNSUPPORTED;
+    if (q_grad->bits < 2 || q_grad->bits > 16) return LBT_EUNSUPPORTED;
+    if (q_grad->bits > 8 && (!g_mant_lo || !al4(g_mant_lo))) return LBT_EINVAL;   // two byte planes: k = 256 * hi + lo
   }
   if (n_outer == 0 || n_inner == 0) return LBT_OK;
-  if (!al4(kg1) || !al4(k1) || (dx && !al16(dx))) return LBT_EUNSUPPORTED;
+  if (!(wide ? (reinterpret_cast<uintptr_t>(kg1) & 7) == 0 : al4(kg1)) || !al4(k1) || (dx && !al16(dx))) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   Bwd2Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel, (size_t)4 * C * 4));
+  int rc = wide ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel<true>, (size_t)4 * C * 4))
+                : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel<false>, (size_t)4 * C * 4));
   if (rc) return rc;
   p.kg1 = kg1;
   p.k1 = k1;
@@ -1078,9 +1150,15 @@ extern "C" int lbt_bn_bwd_apply(const int8_t* kg1, const int8_t* k1, size_t n_ou
   p.dx = dx;
   p.qg = site_from_abi(q_grad);
   p.g_mant = g_mant;
+  p.g_mant_lo = g_mant_lo;
   const size_t smem = (size_t)4 * C * 4;
-  if ((rc = set_smem(bn_bwd2_kernel, smem))) return rc;
-  launch_pdl(bn_bwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  if (wide) {
+    if ((rc = set_smem(bn_bwd2_kernel<true>, smem))) return rc;
+    launch_pdl(bn_bwd2_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  } else {
+    if ((rc = set_smem(bn_bwd2_kernel<false>, smem))) return rc;
+    launch_pdl(bn_bwd2_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  }
   return check_launch("lbt_bn_bwd_apply");
 }
 

@@ -50,6 +50,7 @@ struct GemmParams {
   long long* acc64;
   int alpha;
   uint32_t idesc;
+  uint32_t idesc2;   // DUAL: descriptor of the low-half MMAs (A = u8)
   BnqParams bnq;  // fused re-quantising epilogue (bnq.q.bits == 0: off)
 };
 
@@ -160,20 +161,28 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN>
+// DUAL: the A operand is a 9..16-bit mantissa split k = 256 * hi + lo (hi s8, lo u8: the 16-bit gradients of BASELINE
+// config 5).  Both halves are staged per K block next to ONE copy of B, two accumulators per tile live in tensor memory
+// (hi . B and lo . B, each exact in s32), and the epilogue combines them 256 * acc_hi + acc_lo in 64-bit integers before the
+// single rounding to fp32 — the result is RN_fp32(exact 16x8-bit dot * 2^e), with no int64 round trip through HBM.
+template <int BN, bool DUAL = false>
 struct Cfg {
   static constexpr int kStageA = kBlockM * kBlockK;
+  static constexpr int kStageA2 = DUAL ? kStageA : 0;
   static constexpr int kStageB = BN * kBlockK;
-  static constexpr int kStageBytes = kStageA + kStageB;
+  static constexpr int kStageBytes = kStageA + kStageA2 + kStageB;
   static constexpr int kStages = (200 * 1024 / kStageBytes) > 8 ? 8 : (200 * 1024 / kStageBytes);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
-  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kAccCols = (DUAL ? 2 : 1) * BN;             // tensor-memory columns of one accumulator stage
+  static constexpr int kTmemCols = (2 * kAccCols) < 32 ? 32 : (2 * kAccCols);
+  static_assert(kTmemCols <= 512, "two accumulator stages must fit the 512 tensor-memory columns");
 };
 
-template <int BN>
+template <int BN, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using C = Cfg<BN>;
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  using C = Cfg<BN, DUAL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
@@ -199,6 +208,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     s_abort = 0;
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
+    if (DUAL) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
@@ -228,7 +238,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * C::kStageBytes;
           mbar_expect_tx(&full_bar[stage], C::kStageBytes);
           tma_load_2d(&tmA, &full_bar[stage], sa, (int)(kb * kBlockK), (int)(m_tile * kBlockM));
-          tma_load_2d(&tmB, &full_bar[stage], sa + C::kStageA, (int)(kb * kBlockK), (int)(n_tile * BN));
+          if (DUAL) tma_load_2d(&tmA2, &full_bar[stage], sa + C::kStageA, (int)(kb * kBlockK), (int)(m_tile * kBlockM));
+          tma_load_2d(&tmB, &full_bar[stage], sa + C::kStageA + C::kStageA2, (int)(kb * kBlockK), (int)(n_tile * BN));
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -247,17 +258,24 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
         if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag))) break;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * C::kAccCols;
         for (uint32_t kb = kb0; kb < kb1; ++kb) {
           if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag))) break;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + C::kStageA);
+          const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + C::kStageA + C::kStageA2);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance the descriptor start address by k*32 bytes inside the 128B swizzle row
             umma_i8(d_tmem, da + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), p.idesc,
                     (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (DUAL) {   // the low halves against the same B tile, into the second accumulator
+            const uint64_t da2 = make_desc_sw128(sa + C::kStageA);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_i8(d_tmem + BN, da2 + (uint64_t)(k * (kUmmaK >> 4)), db + (uint64_t)(k * (kUmmaK >> 4)), p.idesc2,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs have read it
           if (++stage == C::kStages) {
@@ -303,7 +321,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
       const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
       const uint32_t col0 = n_tile * BN;
-      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      const uint32_t taddr = tmem_base + acc * C::kAccCols + ((quad * 32u) << 16);
       if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
         bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
         stat_ntile = n_tile;
@@ -315,6 +333,34 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (BN == 16 && half) break;  // a single chunk: the second warp of the quadrant has nothing to do
         uint32_t v[16];
         tmem_ld16(taddr + c, v);
+        if (DUAL) {   // host guarantees LBT_EPI_F32, no fused quantiser, k_splits == 1
+          uint32_t w[16];
+          tmem_ld16(taddr + BN + c, w);
+          tmem_ld_wait();
+          if (row < p.M && col0 + c < p.N) {
+            const uint32_t ncol = min(16u, p.N - (col0 + c));
+            float* o = p.out + (size_t)row * p.ldc + col0 + c;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)   // 256 * (hi . B) + (lo . B): exact in 64 bits, ONE rounding to fp32
+              f[j] = __ll2float_rn((long long)(int)v[j] * 256ll + (long long)(int)w[j]) * scale;
+            if (p.addend) {
+              const float* ad = p.addend + (o - p.out);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldcs(ad + j));
+            }
+            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < (int)ncol) o[j] = f[j];
+            }
+          }
+          continue;
+        }
         tmem_ld_wait();
         if (fused) {
           if (col0 + c < p.N) {  // warp-uniform
@@ -720,20 +766,20 @@ int make_operand_map(CUtensorMap* map, const void* base, size_t rows, size_t K, 
   return LBT_OK;
 }
 
-template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, unsigned grid, cudaStream_t st) {
+template <int BN, bool DUAL = false>
+int launch(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const GemmParams& p, unsigned grid, cudaStream_t st) {
   static bool attr_done[16] = {};
   const int dev = device_info().device;
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, DUAL>::kSmemBytes);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(gemm_i8_kernel)");
       return LBT_ECUDA;
     }
     attr_done[dev] = true;
   }
-  launch_pdl(gemm_i8_kernel<BN>, grid, kThreads, Cfg<BN>::kSmemBytes, st, ta, tb, p);
-  return check_launch("lbt_gemm_i8");
+  launch_pdl(gemm_i8_kernel<BN, DUAL>, grid, kThreads, Cfg<BN, DUAL>::kSmemBytes, st, ta, ta2, tb, p);
+  return check_launch(DUAL ? "lbt_gemm_i8_dual" : "lbt_gemm_i8");
 }
 
 }  // namespace
@@ -826,11 +872,69 @@ extern "C" int lbt_gemm_i8(const void* A, int a_kind, size_t lda, const void* B,
   const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
   const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
   switch (bn) {
-    case 16: return launch<16>(ta, tb, p, grid, st);
-    case 32: return launch<32>(ta, tb, p, grid, st);
-    case 64: return launch<64>(ta, tb, p, grid, st);
-    case 128: return launch<128>(ta, tb, p, grid, st);
-    default: return launch<256>(ta, tb, p, grid, st);
+    case 16: return launch<16>(ta, ta, tb, p, grid, st);
+    case 32: return launch<32>(ta, ta, tb, p, grid, st);
+    case 64: return launch<64>(ta, ta, tb, p, grid, st);
+    case 128: return launch<128>(ta, ta, tb, p, grid, st);
+    default: return launch<256>(ta, ta, tb, p, grid, st);
+  }
+}
+
+// out[M, N] = fp32((256 * A_hi + A_lo)[M, K] . B[N, K]^T) * 2^(exp_const + ibA + ibB) (+ addend): the A operand is a 9..16-bit
+// mantissa tensor given as its two byte planes k = 256 * hi + lo (hi s8, lo u8) with the same row pitch — the 16-bit
+// gradients of BASELINE config 5 (dfxp:300, 305 with a 16-bit `gradq`).  One pass over B, two accumulators in tensor memory,
+// combined exactly in the epilogue (gemm_i8_kernel<BN, true>).
+extern "C" int lbt_gemm_i8_dual(const int8_t* A_hi, const uint8_t* A_lo, size_t lda, const void* B, int b_kind, size_t ldb, size_t M,
+                                size_t N, size_t K, const int32_t* ibA, const int32_t* ibB, int exp_const, float* out_f32, size_t ldc,
+                                const float* addend, void* stream) {
+  if (!A_hi || !A_lo || !B || !out_f32) return LBT_EINVAL;
+  if (b_kind != LBT_MANT_S8 && b_kind != LBT_MANT_U8) return LBT_EINVAL;
+  if (M == 0 || N == 0) return LBT_OK;
+  if (K == 0 || ldc < N) return LBT_EINVAL;
+  if (lda < K || ldb < K || (lda & 15) || (ldb & 15)) return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A_hi) | reinterpret_cast<uintptr_t>(A_lo) | reinterpret_cast<uintptr_t>(B)) & 15) return LBT_EUNSUPPORTED;
+  if (M >= (1ull << 31) || N >= (1ull << 31) || K >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+  int bn = 128;
+  for (int c : {16, 32, 64, 128})
+    if ((size_t)c >= N) {
+      bn = c;
+      break;
+    }
+  GemmParams p{};
+  p.M = (uint32_t)M;
+  p.N = (uint32_t)N;
+  p.K = (uint32_t)K;
+  p.m_tiles = (uint32_t)((M + kBlockM - 1) / kBlockM);
+  p.n_tiles = (uint32_t)((N + bn - 1) / bn);
+  p.k_blocks = (uint32_t)((K + kBlockK - 1) / kBlockK);
+  p.k_blocks_per_split = p.k_blocks;
+  p.k_splits = 1;
+  if (p.k_blocks > 65536 / kBlockK) return LBT_EUNSUPPORTED;   // each s32 accumulator sums at most 65536 products
+  p.epilogue = LBT_EPI_F32;
+  p.ibA = ibA;
+  p.ibB = ibB;
+  p.exp_const = exp_const;
+  p.addend = addend;
+  p.out = out_f32;
+  p.ldc = ldc;
+  const uint32_t common = (2u << 4) | ((b_kind == LBT_MANT_S8 ? 1u : 0u) << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  p.idesc = common | (1u << 7);    // hi: s8
+  p.idesc2 = common;               // lo: u8
+  CUtensorMap ta, ta2, tb;
+  int rc = make_operand_map(&ta, A_hi, M, K, lda, kBlockM);
+  if (rc) return rc;
+  if ((rc = make_operand_map(&ta2, A_lo, M, K, lda, kBlockM))) return rc;
+  if ((rc = make_operand_map(&tb, B, N, K, ldb, (uint32_t)bn))) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles;
+  const unsigned grid = (unsigned)(items < (uint64_t)di.sm_count ? items : (uint64_t)di.sm_count);
+  switch (bn) {
+    case 16: return launch<16, true>(ta, ta2, tb, p, grid, st);
+    case 32: return launch<32, true>(ta, ta2, tb, p, grid, st);
+    case 64: return launch<64, true>(ta, ta2, tb, p, grid, st);
+    default: return launch<128, true>(ta, ta2, tb, p, grid, st);
   }
 }
 

@@ -697,20 +697,28 @@ def _split16(gm16):
     return hi, lo
 
 
-def _conv_backward16(layer, geom, xm, xkind, wm, prep, gm16, need_dx, need_dw, need_db):
-    """dfxp:302-305 with a gradient quantiser wider than 8 bits (BASELINE config 5: 16-bit G): the mantissas are split
-    k = 256*hi + lo and every product runs twice on the 8-bit tensor cores, alpha = 256 / 1 into the exact int64
-    accumulators; the input gradient is finished from int64 as well, so it is still RN_fp32(exact integer dot * 2^e)."""
+def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw, need_db, gm16=None, addend=None):
+    """dfxp:302-305 with a gradient quantiser wider than 8 bits (BASELINE config 5: 16-bit G).  The gradient mantissas arrive
+    as their two byte planes k = 256*hi + lo (hi s8, lo u8; written directly by lbt_bn_bwd_apply in the fused units, by
+    lbt_split_s16 otherwise).  wgrad: every product runs twice on the 8-bit tensor cores, alpha = 256 / 1 into the exact
+    int64 accumulators.  dgrad: ONE launch of lbt_gemm_i8_dual — both planes against one copy of the filter, two accumulators
+    in tensor memory combined before the single rounding — so dX is RN_fp32(exact integer dot * 2^e) with no int64 tensor in
+    HBM.  ``addend``: the gradient of the other branch (residual shortcut), added in the dgrad epilogue."""
     N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
     xb, wb, gb = layer.qX.bits, layer.qW.bits, layer.qG.bits
-    dev = gm16.device
+    dev = hi.device
     M = N * OH * OW
     Kf = kh * kw * Cin
     rt = layer.qX.runtime
-    hi, lo = _split16(gm16)
     halves = ((hi, Q.MANT_S8, 256), (lo, Q.MANT_U8, 1))
     dW = db = dx = None
+    fork = need_dw and rt.overlap and rt._arena_on and rt.grad_sink is not None and rt.grad_sink.active and _lib.profiler is None
+    main = torch.cuda.current_stream(dev) if fork else None
+    side = rt.side_stream(dev) if fork else None
+    if fork:
+        side.wait_stream(main)
     if need_dw:
+      with (torch.cuda.stream(side) if fork else contextlib.nullcontext()):
         acc = rt.zeros_i64(Kf * Cout, dev).view(Kf, Cout)
         if xkind == Q.MANT_S9C3:
             if not _implicit_ok(Cout, 1, 1):
@@ -718,13 +726,15 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, gm16, need_dx, need_dw, n
             acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
             for g_, kind, alpha in halves:
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
-                          pt, pl, OH, OW, _lib.ptr(acc16), alpha, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+                          pt, pl, OH, OW, _lib.ptr(acc16), alpha, 0, _lib.stream(),
+                          meta=dict(ops=M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
             a = acc16.view(kh * kw, 16, Cout)
             acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
         elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
             for g_, kind, alpha in halves:
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
-                          pt, pl, OH, OW, _lib.ptr(acc), alpha, 0, _lib.stream(), meta=dict(ops=2 * M * Cout * Kf))
+                          pt, pl, OH, OW, _lib.ptr(acc), alpha, 0, _lib.stream(),
+                          meta=dict(ops=M * Cout * Kf, bytes=N * H * W * Cin + M * Cout + 8 * Kf * Cout))
         else:
             A = _im2col(xm, xkind, OH, OW, kh, kw, sh, sw, pt, pl, False)
             at = _transpose_bytes(A)
@@ -738,6 +748,8 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, gm16, need_dx, need_dw, n
         dW = _emit_grad(rt, layer.weight, acc, ibA=layer.qX.range, ibB=layer.qG.range, exp_const=-(xb - 1) - (gb - 1),
                         add_scale=2 * layer.weight_decay, shape=(kh, kw, Cin, Cout))
     if need_db:
+        if gm16 is None:
+            raise _lib.LbtError('Conv2d_q: the bias gradient of a 16-bit gradient needs the s16 mantissas')
         db = _emit_grad(rt, layer.bias, _colsum(gm16.view(M, Cout), Q.MANT_S16, rt), ibA=layer.qG.range, exp_const=-(gb - 1))
     if need_dx:
         K2 = kh * kw * Cout
@@ -745,24 +757,26 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, gm16, need_dx, need_dw, n
         pw2 = prep['w2'] if prep is not None else None
         if prep is not None and pw2 is None:
             raise _lib.LbtError('Conv2d_q: no input gradient for a 3-channel first-layer convolution')
-        acc = torch.zeros(N * H * W, Cin, dtype=torch.int64, device=dev)
+        dx = torch.empty(N, H, W, Cin, dtype=torch.float32, device=dev)
+        ad2 = addend.reshape(N * H * W, Cin) if addend is not None else None
         one_by_one = kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0
         rot = bool(prep is not None and prep.get('rot180'))
         if one_by_one:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
+            a_hi, a_lo = hi.view(M, Cout), lo.view(M, Cout)
         elif rot:
             w2 = pw2                                      # rot180-packed: dX = conv(G, rot180 W), padding k - 1 - pad
+            a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
+            a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
-        for g_, kind, alpha in halves:
-            if one_by_one:
-                A2 = g_.view(M, Cout)
-            elif rot:
-                A2 = _im2col(g_, kind, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
-            else:
-                A2 = _im2col(g_, kind, H, W, kh, kw, sh, sw, pt, pl, True)
-            G.gemm_i8_acc64(A2, w2, acc, alpha=alpha, k_splits=1)
-        dx = G.acc64_finalize(acc, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e).view(N, H, W, Cin)
+            a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
+            a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, sh, sw, pt, pl, True)
+        G.gemm_i8_dual(a_hi, a_lo, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin), addend=ad2)
+    if fork:
+        for t in (xm, hi, lo):
+            t.record_stream(side)
+        rt._side_pending = True
     return dx, dW, db
 
 
@@ -792,7 +806,8 @@ class _QConv2dFn(torch.autograd.Function):
             if layer.qG.bits > 16:
                 raise _lib.LbtError('Conv2d_q: gradient quantisers wider than 16 bits are not supported')
             _, gm16 = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S16)
-            dx, dW, db = _conv_backward16(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm16, *needs)
+            hi, lo = _split16(gm16)
+            dx, dW, db = _conv_backward16(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, hi, lo, *needs, gm16=gm16)
             return (dx.permute(0, 3, 1, 2) if dx is not None else None), dW, db, None
         _, gm = layer.qG.quantize(dy, want_fp32=False, mant_kind=Q.MANT_S8)                    # dfxp:300
         dx, dW, db = _conv_backward(layer, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, ctx.needs_input_grad[0],
@@ -900,10 +915,8 @@ class _QLinearFn(torch.autograd.Function):
                 db = _emit_grad(rt, layer.bias, _colsum(gm16, Q.MANT_S16, rt), ibA=layer.qG.range, exp_const=-(gb - 1))
             if ctx.needs_input_grad[0]:
                 w2 = ctx.prep['w2'] if ctx.prep is not None else _as_operand(wm)
-                acc = torch.zeros(gm16.shape[0], In, dtype=torch.int64, device=dy.device)
-                for g_, alpha in halves:
-                    G.gemm_i8_acc64(_as_operand(g_), w2, acc, alpha=alpha, k_splits=1)
-                dX = G.acc64_finalize(acc, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=-(gb - 1) - (wb - 1))
+                dX = G.gemm_i8_dual(_as_operand(hi), _as_operand(lo), w2, ibA=layer.qG.range, ibB=layer.qW.range,
+                                    exp_const=-(gb - 1) - (wb - 1))                            # dfxp:460, one rounding
             return dX, dW, db, None
         _, gm = layer.qG.quantize(dy.contiguous(), want_fp32=False, mant_kind=Q.MANT_S8)       # dfxp:453
         if ctx.needs_input_grad[1]:
@@ -1106,16 +1119,22 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
     bsums = pre[1] if pre is not None else rt.zeros_i64(4 * C + 2, dev)   # [4C] sums + the grid-barrier word of the fused launch
     d_add = torch.empty(k1.shape, dtype=torch.float32, device=dev) if has_add else None
     dx = torch.empty(k1.shape, dtype=torch.float32, device=dev) if want_dx else None
-    qg = gm = None
+    # gradient quantisers wider than 8 bits (config 5: 16-bit G): kg1 travels as s16, and the convolution's gradient
+    # mantissas leave the second pass as the two byte planes (hi s8, lo u8) its tensor-core kernels consume
+    wide = max(resc.qG.bits, norm.qG.bits) > 8
+    kg1_kind = Q.MANT_S16 if wide else Q.MANT_S8
+    qg = gm = gm_lo = None
     if grad_site is not None:
         qg = grad_site.abi(n_inner, dev)
         gm = torch.empty_like(k1)
+        if grad_site.bits > 8:
+            gm_lo = torch.empty(k1.shape, dtype=torch.uint8, device=dev)
     nbytes = k1.numel() * (6 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0) + (4 if want_dx else 0) +
                            (1 if gm is not None else 0))
     # small tensors: both passes in one launch (lbt_bn_bwd_fused); it declines shapes that are not one wave of CTAs
     fused = False
     # (its grid barrier needs every CTA co-resident: not while weight-gradient kernels share the SMs on the side stream)
-    if FUSE_BN_BWD and pre is None and not getattr(rt, '_side_pending', False):
+    if FUSE_BN_BWD and pre is None and not wide and gm_lo is None and not getattr(rt, '_side_pending', False):
         a = _lib.BnBwdArgs(g=_lib.ptr(g_), out=_lib.ptr(out_), k2=_lib.ptr(k2), k1=_lib.ptr(k1), n_outer=N, n_inner=n_inner, C=C,
                            relu=relu_mode, bits2=resc.qX.bits, bits1=norm.qX.bits, ib2=_lib.ptr(resc.qX.range),
                            ib1=_lib.ptr(norm.qX.range), gamma_q=_lib.ptr(gq), beta_q=_lib.ptr(bq),
@@ -1129,7 +1148,7 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
     if not fused and pre is not None:
         kg1 = pre[0]
     elif not fused:
-        kg1 = torch.empty_like(k1)
+        kg1 = torch.empty(k1.shape, dtype=torch.int16 if wide else torch.int8, device=dev)
         nzg2, offg2 = _site_args(resc.qG, g_)
         nzg1, offg1 = _site_args(norm.qG, g_)
         _lib.call('lbt_bn_bwd_quant_stats', _lib.ptr(g_), _lib.ptr(out_), relu_mode, _lib.ptr(k2), _lib.ptr(k1), N, n_inner,
@@ -1137,18 +1156,19 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
                   _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
                   _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
                   _lib.ptr(rt.dev_step), _lib.ptr(d_add), _lib.ptr(kg1), _lib.ptr(bsums),
-                  int(resc.qG.target == 0 and norm.qG.target == 0), _lib.stream(),
-                  meta=dict(bytes=g_.numel() * (7 + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
+                  int(resc.qG.target == 0 and norm.qG.target == 0), kg1_kind, _lib.stream(),
+                  meta=dict(bytes=g_.numel() * (7 + (1 if wide else 0) + (4 if relu_mode == 2 else 0) + (4 if has_add else 0))))
     if not fused:
         _lib.call('lbt_bn_bwd_apply', _lib.ptr(kg1), _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range),
                   _lib.ptr(sums), float(norm.eps), norm.qG.bits, _lib.ptr(norm.qG.range), _lib.ptr(bsums), _lib.ptr(dx),
-                  ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), _lib.stream(),
-                  meta=dict(bytes=k1.numel() * (2 + (4 if want_dx else 0) + (1 if gm is not None else 0))))
+                  ctypes.addressof(qg) if qg is not None else None, _lib.ptr(gm), kg1_kind, _lib.ptr(gm_lo), _lib.stream(),
+                  meta=dict(bytes=k1.numel() * (2 + (1 if wide else 0) + (4 if want_dx else 0) + (1 if gm is not None else 0) +
+                                                (1 if gm_lo is not None else 0))))
     # dbeta = sum gq2 (dfxp:690); dgamma = sum gq2 * xq2 + 2*wd*gamma (dfxp:689)
     dbeta = _emit_grad(rt, resc.beta, bsums[:C], ibA=resc.qG.range, exp_const=-(resc.qG.bits - 1))
     dgamma = _emit_grad(rt, resc.gamma, bsums[C:2 * C], ibA=resc.qG.range, ibB=resc.qX.range,
                         exp_const=-(resc.qG.bits - 1) - (resc.qX.bits - 1), add_scale=2 * resc.weight_decay)
-    return dx, gm, dgamma, dbeta, d_add
+    return dx, (gm if gm_lo is None else (gm, gm_lo)), dgamma, dbeta, d_add
 
 
 class _FusedBNFn(torch.autograd.Function):
@@ -1261,7 +1281,10 @@ class _ConvBNFn(torch.autograd.Function):
                                                    ctx.relu_mode, ctx.has_add, grad_site=conv.qG, want_dx=False, pre=pre)   # ... dfxp:300
         addend = _to_mem(g_alias) if (g_alias is not None and need_dx) else None
         li = ctx.link_in if (addend is None and FUSE_BWD_LINK) else None
-        dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend, link=li)
+        if isinstance(gm, tuple):        # 9..16-bit gradient: (hi, lo) byte planes
+            dx, dW, _ = _conv_backward16(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm[0], gm[1], need_dx, need_dw, False, addend=addend)
+        else:
+            dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend, link=li)
         return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
                 (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None)
 
@@ -1274,7 +1297,7 @@ FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused uni
 
 def _unit_fusable(conv, bn, x):
     return (FUSE_UNITS and isinstance(conv, Conv2d_q) and isinstance(bn, BatchNorm2d_q) and conv.bias is None and conv.fuse_bn and
-            bn._can_fuse_c(conv.weight.shape[3], 4) and conv.qG.bits <= 8 and conv.qW.bits <= 8 and conv.qX.bits <= 9 and
+            bn._can_fuse_c(conv.weight.shape[3], 4) and conv.qG.bits <= 16 and conv.qW.bits <= 8 and conv.qX.bits <= 9 and
             x.is_cuda)
 
 
@@ -1344,7 +1367,7 @@ def _first_conv(m):
 class BatchNorm2d_q(nn.Sequential):
     """dfxp:697-743: Normalization_q then Rescale_q (whose input range is hard-coded to 2, dfxp:735).
 
-    In training mode with <= 8-bit quantisers and C % 4 == 0 the pair runs as the fused kernels of
+    In training mode with <= 8-bit activation quantisers, <= 16-bit gradient quantisers and C % 4 == 0 the pair runs as the fused kernels of
     csrc/bn.cu; ``forward(x, add=None, relu=False)`` can additionally fold the residual sum and the ReLU
     that follow it in the reference's blocks (dfxp:862, 986).  Otherwise the two sub-modules run one
     after the other."""
@@ -1365,7 +1388,8 @@ class BatchNorm2d_q(nn.Sequential):
     def _can_fuse_c(self, C, dim):
         norm, resc = self[0], self[1]
         return (self.fused and self.training and dim in (2, 4) and C % 4 == 0 and
-                max(norm.qX.bits, norm.qG.bits, resc.qX.bits, resc.qG.bits) <= 8 and min(norm.qX.bits, resc.qX.bits) >= 2)
+                max(norm.qX.bits, resc.qX.bits) <= 8 and max(norm.qG.bits, resc.qG.bits) <= 16 and
+                min(norm.qX.bits, resc.qX.bits, norm.qG.bits, resc.qG.bits) >= 2)
 
     def _can_fuse(self, x):
         return self._can_fuse_c(x.shape[1], x.dim())

@@ -48,6 +48,22 @@ def gemm_i8(A, B, *, ibA=None, ibB=None, exp_const=0, bias=None, out=None, bnq=N
     return out
 
 
+def gemm_i8_dual(A_hi, A_lo, B, *, ibA=None, ibB=None, exp_const=0, out=None, addend=None):
+    """fp32 out[M,N] = ((256 * A_hi + A_lo)[M,K] @ B[N,K]^T) * 2^(exp_const + ibA + ibB) (+ addend), one rounding: a 9..16-bit
+    A operand as its two byte planes (lbt_gemm_i8_dual: both halves per K block, two accumulators in tensor memory)."""
+    M, K = A_hi.shape
+    N = B.shape[0]
+    if A_hi.dtype != torch.int8 or A_lo.dtype != torch.uint8 or A_lo.shape != A_hi.shape or A_lo.stride() != A_hi.stride():
+        raise _lib.LbtError('gemm_i8_dual takes an int8 high plane and a uint8 low plane of the same shape and pitch')
+    lda, ldb = _check_operand(A_hi, K), _check_operand(B, K)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A_hi.device)
+    _lib.call('lbt_gemm_i8_dual', _lib.ptr(A_hi), _lib.ptr(A_lo), lda, _lib.ptr(B), _kind(B), ldb, M, N, K, _lib.ptr(ibA), _lib.ptr(ibB),
+              int(exp_const), _lib.ptr(out), out.stride(0), _lib.ptr(addend), _lib.stream(),
+              meta=dict(ops=2 * M * N * K, bytes=2 * M * K + N * K + 4 * M * N * (2 if addend is not None else 1)))
+    return out
+
+
 def gemm_i8_acc64(A, B, acc64, *, alpha=1, k_splits=0):
     """acc64[M,N] += alpha * (A[M,K] @ B[N,K]^T), exact, K split across the SMs."""
     M, K = A.shape

@@ -507,7 +507,25 @@ class Normalization_q(Layer_q):
 
     def backward(self, grad, stochastic=True):
         self.gradq = self.qG(grad).detach()
+        if self.qX.ctx.exact and self.train:
+            return self._backward_exact()
         return torch.autograd.grad(self.y, self.X, self.gradq)[0]                 # dfxp:623
+
+    def _backward_exact(self):
+        """The VJP of dfxp:616 through the batch mean and (biased) variance, tf.gradients' result in closed form:
+        dx = (g - mean(g) - xhat * mean(g * xhat)) / sqrt(var + eps).  Exact mode: the two batch sums are accumulated
+        exactly (fp64 holds sums of DFXP mantissa products) and rounded once, like every other accumulation of this mode;
+        the elementwise part is plain fp32, one rounding per operation, in the order written here."""
+        g, xq = self.gradq, self.Xq.detach()
+        axes = list(range(g.dim() - 1))
+        n = float(g.numel() // g.shape[-1])
+        den = torch.sqrt(self.var + self.eps)
+        sg = g.double().sum(dim=axes)
+        sgx = (g.double() * xq.double()).sum(dim=axes)
+        mg = (sg / n).float()
+        mgx = (((sgx - self.mean.double() * sg) / den.double()) / n).float()      # mean(g * xhat)
+        xhat = (xq - self.mean) / den
+        return ((g - mg) - xhat * mgx) / den
 
     def quantizers(self):
         return [self.qX, self.qG]
@@ -536,6 +554,13 @@ class Rescale_q(Layer_q):
 
     def backward(self, grad, stochastic=True):
         self.gradq = self.qG(grad).detach()
+        if self.qX.ctx.exact:    # the two reductions over (batch, pixels) accumulate exactly and round once
+            axes = list(range(self.gradq.dim() - 1))
+            g64 = self.gradq.double()
+            dgamma = (g64 * self.Xq.detach().double()).sum(dim=axes).float()
+            self.dgamma = dgamma + 2 * self.weight_decay * self.gamma.detach()    # dfxp:689
+            self.dbeta = g64.sum(dim=axes).float()                                # dfxp:690
+            return self.gradq * self.gq.detach()                                  # dfxp:691
         g = torch.autograd.grad(self.y, [self.X, self.gamma, self.beta], self.gradq)
         self.dgamma = g[1] + 2 * self.weight_decay * self.gamma.detach()          # dfxp:689
         self.dbeta = g[2]                                                         # dfxp:690

@@ -40,6 +40,38 @@ def test_gemm_f32_bit_exact(M, N, K, kinds):
     assert torch.equal(out.double(), ref.float().double()), (out.double() - ref).abs().max()
 
 
+@pytest.mark.parametrize('M,N,K', [(128, 16, 128), (5, 3, 16), (257, 33, 144), (1000, 128, 1024), (4096, 64, 576), (300, 512, 2048),
+                                   (3136, 256, 64), (512, 1000, 4608), (8192, 130, 1152)])
+@pytest.mark.parametrize('b_signed', [True, False])
+def test_gemm_dual_16bit_operand_bit_exact(M, N, K, b_signed):
+    """lbt_gemm_i8_dual: a 16-bit A operand as its byte planes k = 256*hi + lo, two accumulators in tensor memory combined before
+    ONE rounding: equal to RN_fp32(exact 16x8-bit integer dot * 2^e) (+ addend), bit for bit — extremes included."""
+    rng = np.random.default_rng(M + N * 5 + K * 11 + b_signed)
+    a16 = rng.integers(-32768, 32768, size=(M, K)).astype(np.int64)
+    a16[0, :] = 32767
+    a16[-1, :] = -32768
+    ld = -(-K // 16) * 16
+    hi = torch.zeros(M, ld, dtype=torch.int8)
+    lo = torch.zeros(M, ld, dtype=torch.uint8)
+    hi[:, :K] = torch.from_numpy((a16 >> 8).astype(np.int8))
+    lo[:, :K] = torch.from_numpy((a16 & 255).astype(np.uint8))
+    hi[:, K:] = 55
+    lo[:, K:] = 201                                  # pitch padding must never be read
+    B, b64 = _operand(rng, N, K, b_signed)
+    if b_signed:
+        b64[0, :] = -128
+        B[0, :] = -128
+    ibA = torch.tensor(-3, dtype=torch.int32, device='cuda')
+    addend = torch.randn(M, N, device='cuda')
+    out = G.gemm_i8_dual(hi.cuda()[:, :K], lo.cuda()[:, :K], B, ibA=ibA, exp_const=-18)
+    out2 = G.gemm_i8_dual(hi.cuda()[:, :K], lo.cuda()[:, :K], B, ibA=ibA, exp_const=-18, addend=addend)
+    torch.cuda.synchronize()
+    assert G.debug_error() == 0, 'GEMM pipeline watchdog fired'
+    ref = (_exact(torch.from_numpy(a16), b64) * 2.0 ** -21).float()      # |dot| < 2^15 * 2^8 * 4608 < 2^53: exact in fp64
+    assert torch.equal(out, ref), float((out.double() - ref.double()).abs().max())
+    assert torch.equal(out2, ref + addend)
+
+
 def test_gemm_scale_and_bias_from_device_ranges():
     rng = np.random.default_rng(1)
     M, N, K = 384, 48, 300

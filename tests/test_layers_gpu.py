@@ -158,14 +158,15 @@ def test_linear_q_forward_backward(B, In, Out, bias, gbits):
     assert list(rt.ranges().values()) == [int(q.range) for q in ol.quantizers()]
 
 
+@pytest.mark.parametrize('gbits', [None, 16, 12])
 @pytest.mark.parametrize('C,H,B', [(16, 8, 8), (64, 4, 16), (10, 3, 5)])
-def test_batchnorm_q_forward_backward(C, H, B):
+def test_batchnorm_q_forward_backward(C, H, B, gbits):
     rng = np.random.default_rng(C + H + B)
     ctx = O.Context(O.PhiloxNoise(SEED))
     wd = 2e-4
-    ol = O.BatchNorm_q(ctx, 'bn', 8, C, True, weight_decay=wd)
+    ol = O.BatchNorm_q(ctx, 'bn', 8, C, True, weight_decay=wd, grad_bits=gbits)
     rt = D.Runtime(SEED)
-    pl = D.BatchNorm2d_q(8, C, weight_decay=wd, runtime=rt).cuda()
+    pl = D.BatchNorm2d_q(8, C, weight_decay=wd, runtime=rt, grad_bits=gbits).cuda()
     rt.finalize('cuda')
     g0 = torch.from_numpy((1 + 0.3 * rng.standard_normal(C)).astype(np.float32))
     b0 = torch.from_numpy((0.2 * rng.standard_normal(C)).astype(np.float32))
@@ -193,6 +194,45 @@ def test_batchnorm_q_forward_backward(C, H, B):
     assert torch.allclose(pl[1].gamma.grad.cpu(), dgam_o, rtol=1e-3, atol=step * B * H * H * 0.02 + 1e-4)
     ddiff = (nhwc(xg.grad) - dx_o).abs()
     assert float((ddiff > 1e-4 * float(dx_o.abs().max())).float().mean()) < 0.02
+    rt.update_ranges()
+    assert list(rt.ranges().values()) == [int(q.range) for q in ol.quantizers()]
+
+
+@pytest.mark.parametrize('gbits', [None, 16])
+@pytest.mark.parametrize('C,H,B,relu', [(16, 8, 8, False), (64, 4, 16, True), (128, 7, 6, True), (32, 5, 33, False)])
+def test_batchnorm_q_bit_exact_vs_exact_oracle(C, H, B, relu, gbits):
+    """Normalization_q + Rescale_q (+ the ReLU the blocks fold in) against the oracle in exactly-rounded-accumulation mode
+    (fp64 batch sums rounded once = the integer sums of the kernels; every elementwise operation a single fp32 rounding in the
+    same order): forward output, running statistics, dX, dgamma, dbeta and all six ranges BIT FOR BIT, for 8- and 16-bit
+    gradient quantisers."""
+    rng = np.random.default_rng(C * 3 + H + B + (gbits or 0))
+    ctx = O.Context(O.PhiloxNoise(SEED), exact=True)
+    wd = 2e-4
+    ol = O.BatchNorm_q(ctx, 'bn', 8, C, True, weight_decay=wd, grad_bits=gbits)
+    orelu = O.ReLU_q()
+    rt = D.Runtime(SEED)
+    pl = D.BatchNorm2d_q(8, C, weight_decay=wd, runtime=rt, grad_bits=gbits, relu=relu).cuda()
+    rt.finalize('cuda')
+    g0 = torch.from_numpy((1 + 0.3 * rng.standard_normal(C)).astype(np.float32))
+    b0 = torch.from_numpy((0.2 * rng.standard_normal(C)).astype(np.float32))
+    for t, v in ((ol.layers[1].gamma, g0), (ol.layers[1].beta, b0), (pl[1].gamma, g0), (pl[1].beta, b0)):
+        t.data.copy_(v)
+    x = torch.from_numpy((rng.standard_normal((B, H, H, C)) * 1.2 + 0.3).astype(np.float32))
+    y_o = ol.forward(x)
+    if relu:
+        y_o = orelu.forward(y_o)
+    xg = nchw(x).requires_grad_(True)
+    y_p = pl(xg)
+    assert torch.equal(nhwc(y_p.detach()), y_o), int((nhwc(y_p.detach()) != y_o).sum())
+    assert torch.equal(pl[0].X_mean_running.cpu(), ol.layers[0].X_mean_running)
+    assert torch.equal(pl[0].X_var_running.cpu(), ol.layers[0].X_var_running)
+    g = torch.from_numpy((rng.standard_normal(tuple(y_o.shape)) * (0.5 if gbits is None else 0.01)).astype(np.float32))
+    dx_o = ol.backward(orelu.backward(g) if relu else g)
+    y_p.backward(nchw(g))
+    assert torch.equal(pl[1].beta.grad.cpu(), ol.layers[1].dbeta)
+    assert torch.equal(pl[1].gamma.grad.cpu(), ol.layers[1].dgamma)
+    got = nhwc(xg.grad)
+    assert torch.equal(got, dx_o), '%d of %d elements differ, max %g' % (int((got != dx_o).sum()), dx_o.numel(), float((got - dx_o).abs().max()))
     rt.update_ranges()
     assert list(rt.ranges().values()) == [int(q.range) for q in ol.quantizers()]
 
