@@ -371,7 +371,7 @@ int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, in
                      uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                      const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                      float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                     float momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                     double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
                      void* stream);
 /*
  * bwd 1: g (w.r.t. the module output) -> ReLU mask (relu: 0 none, 1 recomputed from k2, 2 from `out`)

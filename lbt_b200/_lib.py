@@ -61,7 +61,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'lbt_bn_fwd_apply': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
                                  c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int,
+                                 c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_int,
                                  c_void_p, c_void_p, c_int, c_void_p]),
     'lbt_bn_bwd_quant_stats': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,

@@ -280,7 +280,7 @@ struct Fwd2Params {
   float* batch_var;       // [C] optional
   float* run_mean;        // [C] optional, updated in place with `momentum` (dfxp:602-612)
   float* run_var;
-  float momentum;
+  float momentum, one_minus_momentum;   // the reference's Python constants `momentum` and `(1-momentum)`, each rounded to fp32
   QSite q3;               // optional: the consuming layer's input quantiser (bits == 0: off)
   uint8_t* next_mant;     // its mantissas (u8 for a 9-bit non-negative tensor, s8 otherwise: same byte)
 };
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
       if (p.batch_mean) p.batch_mean[ch] = mean;
       if (p.batch_var) p.batch_var[ch] = var;
       if (p.run_mean) {  // momentum * average + (1 - momentum) * variable
-        p.run_mean[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_mean[ch]), __fmul_rn(1.0f - p.momentum, mean));
-        p.run_var[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_var[ch]), __fmul_rn(1.0f - p.momentum, var));
+        p.run_mean[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_mean[ch]), __fmul_rn(p.one_minus_momentum, mean));
+        p.run_var[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_var[ch]), __fmul_rn(p.one_minus_momentum, var));
       }
     }
   }
@@ -1022,7 +1022,7 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
                                 uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                                 const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
                                 float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                                float momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                                double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
                                 void* stream) {
   if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2) return LBT_EINVAL;
   if (!out && !q_next) return LBT_EINVAL;
@@ -1058,7 +1058,8 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.batch_var = batch_var;
   p.run_mean = run_mean;
   p.run_var = run_var;
-  p.momentum = momentum;
+  p.momentum = (float)momentum;
+  p.one_minus_momentum = (float)(1.0 - momentum);   // dfxp:606: `(1-momentum)` is evaluated in Python (double), THEN becomes an fp32 constant
   p.q3 = site_from_abi(q_next);
   p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
   const size_t smem = (size_t)4 * C * 4;

@@ -634,7 +634,9 @@ class Dropout_q(Layer_q):
 
     def forward(self, X):
         self.X = _leaf(X)
-        if self.train:
+        # tf.nn.dropout returns x untouched when keep_prob is the constant 1 ("Do nothing if we know keep_prob == 1");
+        # evaluating the formula instead would double an element whenever u = 1 - 2^-24 (1.0 + u rounds to 2.0 in fp32)
+        if self.train and self.keep_prob != 1:
             u = self.uniform_fn(tuple(self.X.shape))
             self.mask = torch.floor(self.keep_prob + u)
             self.y = self.X / self.keep_prob * self.mask

@@ -77,7 +77,9 @@ def test_simulated_replicas_train_like_the_oracle(world):
             Xr = X[r * b:(r + 1) * b].permute(0, 3, 1, 2).cuda()
             t.forward_backward(Xr, y[r * b:(r + 1) * b].cuda())
             for (go, p) in zip(grads[r], t.params):                                                   # rule (i)
-                assert torch.equal(p.grad.cpu(), go), 'replica %d step %d: gradient of %s differs' % (r, step, tuple(p.shape))
+                got = p.grad.cpu()
+                assert torch.equal(got, go), 'replica %d step %d: gradient of %s differs in %d elements (max %g)' % (
+                    r, step, tuple(p.shape), int((got != go).sum()), float((got - go).abs().max()))
         keep = emulate_trainers(trainers)
         torch.cuda.synchronize()
         del keep
