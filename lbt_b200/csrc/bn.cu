@@ -166,6 +166,65 @@ __device__ __forceinline__ void pack4_hilo(const float (&k)[4], uint32_t& hi, ui
   }
 }
 
+// ---- conversion-free arithmetic -------------------------------------------------------------------------------------
+// The kernels below are issue-bound, and I2F / F2I / FRND run on the quarter-rate conversion pipe: five of them per element
+// cost as much as ~40 FP32 instructions.  All of them are replaced by full-rate operations that give the SAME values:
+//   floor(t) for |t| < 2^22 : tm = RD(t + 1.5*2^23) (one FADD.RM); the integer is bits(tm) - 0x4B400000, the float tm - 1.5*2^23,
+//                             and the low byte(s) of bits(tm) are the two's-complement mantissa byte(s) to store;
+//   int8 -> float           : PRMT builds bits 0x4B0000bb from the biased byte bb = k + 128, minus (2^23 + 128) (exact).
+constexpr float kMagicF = 12582912.0f;   // 1.5 * 2^23
+constexpr int kMagicI = 0x4B400000;
+
+// stochastic_identity on an ALREADY SCALED value y = x * 2^f (dfxp:34-37) + overflow statistics (dfxp:60-66); returns the
+// magic-biased floor tm (see above).  MM: min/max statistics (LBT_STATS_MINMAX) instead of the four compares + adds.
+template <bool MM>
+__device__ __forceinline__ float sq_scaled(float y, float u, const QC& c, float& mx, float& mn, uint32_t& n1, uint32_t& n2) {
+  if (MM) {
+    mx = fmaxf(mx, y);
+    mn = fminf(mn, y);
+  } else {
+    n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
+    n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
+  }
+  return __fadd_rd(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi), kMagicF);
+}
+__device__ __forceinline__ int tm_int(float tm) { return __float_as_int(tm) - kMagicI; }
+__device__ __forceinline__ float tm_float(float tm) { return __fsub_rn(tm, kMagicF); }
+__device__ __forceinline__ uint32_t tm_pack4(const float (&tm)[4]) {   // four mantissas as s8 bytes
+  const uint32_t a = __byte_perm(__float_as_uint(tm[0]), __float_as_uint(tm[1]), 0x0040);
+  const uint32_t b = __byte_perm(__float_as_uint(tm[2]), __float_as_uint(tm[3]), 0x0040);
+  return __byte_perm(a, b, 0x5410);
+}
+__device__ __forceinline__ uint2 tm_pack4_s16(const float (&tm)[4]) {   // four mantissas as s16
+  return make_uint2(__byte_perm(__float_as_uint(tm[0]), __float_as_uint(tm[1]), 0x5410),
+                    __byte_perm(__float_as_uint(tm[2]), __float_as_uint(tm[3]), 0x5410));
+}
+__device__ __forceinline__ void tm_pack4_hilo(const float (&tm)[4], uint32_t& hi, uint32_t& lo) {   // k = 256 * hi + lo byte planes
+  lo = tm_pack4(tm);
+  const uint32_t a = __byte_perm(__float_as_uint(tm[0]), __float_as_uint(tm[1]), 0x0051);
+  const uint32_t b = __byte_perm(__float_as_uint(tm[2]), __float_as_uint(tm[3]), 0x0051);
+  hi = __byte_perm(a, b, 0x5410);
+}
+__device__ __forceinline__ void dec4_f(uint32_t w, float (&f)[4]) {   // four s8 mantissas -> float, no I2F
+  const uint32_t wb = w ^ 0x80808080u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) f[j] = __fsub_rn(__uint_as_float(__byte_perm(wb, 0x4B000000u, 0x7650u | (uint32_t)j)), 8388736.0f);
+}
+__device__ __forceinline__ void dec4_f_s16(uint2 w, float (&f)[4]) {  // four s16 mantissas -> float
+  const uint32_t a = w.x ^ 0x80008000u, b = w.y ^ 0x80008000u;
+  f[0] = __fsub_rn(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7610u)), 8421376.0f);   // 2^23 + 2^15
+  f[1] = __fsub_rn(__uint_as_float(__byte_perm(a, 0x4B000000u, 0x7632u)), 8421376.0f);
+  f[2] = __fsub_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7610u)), 8421376.0f);
+  f[3] = __fsub_rn(__uint_as_float(__byte_perm(b, 0x4B000000u, 0x7632u)), 8421376.0f);
+}
+// a / b for many a over one b, correctly rounded (see fdiv_by): without the select that only restores the sign of a zero
+// numerator — the quotient of +-0 is +-0 either way and nothing downstream depends on the sign of a zero.
+__device__ __forceinline__ float fdiv_fast(float a, float b, float r) {
+  const float q0 = __fmul_rn(a, r);
+  float q = __fmaf_rn(__fmaf_rn(-b, q0, a), r, q0);
+  return __fmaf_rn(__fmaf_rn(-b, q, a), r, q);
+}
+
 // x / n for the per-channel element count n.  The fp64 division is a ~20-deep dependent chain on a chip with a token fp64
 // pipe (it is most of the 1.8 us per-CTA prologue of the apply kernels); when n is a power of two — every CIFAR-shaped
 // layer at a power-of-two batch — the quotient is the exact scaling x * 2^-k, bit-identical to the division.
@@ -285,8 +344,13 @@ struct Fwd2Params {
   uint8_t* next_mant;     // its mantissas (u8 for a 9-bit non-negative tensor, s8 otherwise: same byte)
 };
 
+// MM: every quantiser of the launch keeps min/max statistics (LBT_STATS_MINMAX).  Per element: ~28 full-rate instructions,
+// no conversion-pipe instruction (see "conversion-free arithmetic" above); power-of-two scale factors are folded into the
+// per-channel constants where that commutes with the roundings exactly (x * 2^f scalings commute with RN):
+//   y1 * m2 = RN((xq - mean) / den) * m2 = RN((xq - mean) / (den / m2));   RN(xq2 * g) = RN(k2 * (g / m2)).
+template <bool MM>
 __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p) {
-  extern __shared__ float s_par[];  // [4*C]: mean, denom, gq, bq
+  extern __shared__ float s_par[];  // [4*C]: mean, den / m2, gq / m2, bq
   __shared__ uint32_t s_red[16];
   pdl_trigger();
   pdl_wait();
@@ -312,8 +376,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
     float mean, var;
     moments(p.sums, C, ch, n, c1.inv_m, mean, var);
     s_par[ch] = mean;
-    s_par[C + ch] = __fsqrt_rn(__fadd_rn(var, p.eps));  // (var + eps) ** 0.5, dfxp:616
-    s_par[2 * C + ch] = p.gq[ch];
+    s_par[C + ch] = __fsqrt_rn(__fadd_rn(var, p.eps)) * c2.inv_m;  // (var + eps) ** 0.5 (dfxp:616), pre-divided by m2 (exact)
+    s_par[2 * C + ch] = p.gq[ch] * c2.inv_m;                         // gq / m2 (exact)
     s_par[3 * C + ch] = p.bq[ch];
     if (blockIdx.x == 0) {
       if (p.batch_mean) p.batch_mean[ch] = mean;
@@ -328,7 +392,6 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
   const uint64_t off = site_offset(p.q2);
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
-  const bool mm = p.q2.minmax != 0;
   const bool nxt = p.q3.bits != 0;
   QC c3 = c2;
   uint64_t off3 = 0;
@@ -338,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
   }
   uint32_t m1 = 0, m2 = 0;
   float mx3 = -INFINITY, mn3 = INFINITY;
-  const bool mm3 = p.q3.minmax != 0;
+  const bool has_add = p.add != nullptr, relu = p.relu != 0, has_out = p.out != nullptr;
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -351,17 +414,15 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
       const float4 t = site_noise(p.q3, v, off3);
       u3[0] = t.x; u3[1] = t.y; u3[2] = t.z; u3[3] = t.w;
     }
-    float mean[4], den[4], g[4], b[4];
+    float nmean[4], den[4], rden[4], g[4], b[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mean[j] = s_par[c0 + j];
+      nmean[j] = -s_par[c0 + j];
       den[j] = s_par[C + c0 + j];
+      rden[j] = __frcp_rn(den[j]);   // one reciprocal per channel: every quotient below is a correctly rounded division (5 FMAs)
       g[j] = s_par[2 * C + c0 + j];
       b[j] = s_par[3 * C + c0 + j];
     }
-    float rden[4];   // one reciprocal per channel: every quotient below is fdiv_by (== IEEE division, 5 FMAs)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rden[j] = __frcp_rn(den[j]);
     const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
     for (size_t r = r0; r < r1; r += kRows) {
       uint32_t kw[kRows];
@@ -371,48 +432,48 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
         if (r + i < r1) {
           const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
           kw[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
-          if (p.add) av[i] = __ldcs(reinterpret_cast<const float4*>(p.add + idx));
+          if (has_add) av[i] = __ldcs(reinterpret_cast<const float4*>(p.add + idx));
         }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + kRows + i < r1) {
           const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
           prefetch_l1(p.k1 + idx);
-          if (p.add) prefetch_l1(p.add + idx);
+          if (has_add) prefetch_l1(p.add + idx);
         }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
           const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
-          int k1[4];
-          unpack4(kw[i], k1);
+          float k1f[4];
+          dec4_f(kw[i], k1f);
           const float a4[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
-          float k2[4], o[4];
+          float t2[4], o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float xq = __int2float_rn(k1[j]) * c1.inv_m;
-            const float y1 = fdiv_by(__fsub_rn(xq, mean[j]), den[j], rden[j]);   // dfxp:616
-            k2[j] = mm ? squant_mm(y1, un[j], c2, mx, mn) : squant(y1, un[j], c2, n1, n2);   // dfxp:677
-            float y2 = __fadd_rn(__fmul_rn(k2[j] * c2.inv_m, g[j]), b[j]);    // dfxp:683
-            if (p.add) y2 = __fadd_rn(y2, a4[j]);                             // residual sum, dfxp:862
-            if (p.relu) y2 = fmaxf(0.0f, y2);                                 // tf.maximum(0.0, X), dfxp:986
+            // xq - mean in one rounding (k1 * 2^-f is exact), then y1 * m2 = (xq - mean) / (den / m2)      dfxp:616
+            const float y1m = fdiv_fast(__fmaf_rn(k1f[j], c1.inv_m, nmean[j]), den[j], rden[j]);
+            t2[j] = sq_scaled<MM>(y1m, un[j], c2, mx, mn, n1, n2);                    // dfxp:677
+            float y2 = __fadd_rn(__fmul_rn(tm_float(t2[j]), g[j]), b[j]);               // dfxp:683 (xq2 * gq, then + bq)
+            if (has_add) y2 = __fadd_rn(y2, a4[j]);                                     // residual sum, dfxp:862
+            if (relu) y2 = fmaxf(0.0f, y2);                                             // tf.maximum(0.0, X), dfxp:986
             o[j] = y2;
           }
-          *reinterpret_cast<uint32_t*>(p.k2 + idx) = pack4(k2);
-          if (p.out) *reinterpret_cast<float4*>(p.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
-          if (nxt) {                                                          // the consumer's Xq, dfxp:287
-            float k3[4];
+          *reinterpret_cast<uint32_t*>(p.k2 + idx) = tm_pack4(t2);
+          if (has_out) *reinterpret_cast<float4*>(p.out + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (nxt) {                                                                    // the consumer's Xq, dfxp:287
+            float t3[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) k3[j] = mm3 ? squant_mm(o[j], u3[j], c3, mx3, mn3) : squant(o[j], u3[j], c3, m1, m2);
-            *reinterpret_cast<uint32_t*>(p.next_mant + idx) = pack4(k3);
+            for (int j = 0; j < 4; ++j) t3[j] = sq_scaled<MM>(__fmul_rn(o[j], c3.m), u3[j], c3, mx3, mn3, m1, m2);
+            *reinterpret_cast<uint32_t*>(p.next_mant + idx) = tm_pack4(t3);
           }
         }
     }
   }
-  if (mm) mm_to_counts(c2, mx, mn, n1, n2);
+  if (MM) mm_to_counts(c2, mx, mn, n1, n2);
   publish_counters(p.q2.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
   if (nxt) {
-    if (mm3) mm_to_counts(c3, mx3, mn3, m1, m2);
+    if (MM) mm_to_counts(c3, mx3, mn3, m1, m2);
     publish_counters(p.q3.counters, m1, m2, p.t.n_outer * p.t.n_inner, s_red);
   }
 }
@@ -439,8 +500,10 @@ struct Bwd1Params {
 };
 
 // WIDE: a gradient quantiser wider than 8 bits — kg1 is stored as s16 and the per-thread partial sums are 64-bit
-// (a 16-bit mantissa times an 8-bit one, summed down 4096 rows, does not fit 32).
-template <bool WIDE>
+// (a 16-bit mantissa times an 8-bit one, summed down 4096 rows, does not fit 32).  MM: min/max statistics for both sites.
+// RELU: 0 none, 1 mask recomputed from k2, 2 mask from `out`.  ~31 full-rate instructions per element, no conversions;
+// folded constants (exact, powers of two):  RN(xq2 * g) = RN(k2 * (g / m2));  dx2 * mg1 = RN(kg2 * (g * mg1 / mg2)).
+template <bool WIDE, bool MM, int RELU>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
@@ -453,10 +516,11 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
   const uint64_t off2 = site_offset(p.qg2), off1 = site_offset(p.qg1);
   uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;
   float amx = -INFINITY, amn = INFINITY, bmx = -INFINITY, bmn = INFINITY;
-  const bool mm2 = p.qg2.minmax != 0, mm1 = p.qg1.minmax != 0;
   using AccT = typename std::conditional<WIDE, long long, int>::type;
   Acc<4, AccT> acc;
   acc.zero();
+  const float gscale = cg2.inv_m * cg1.m;   // kg2 -> dx2 (x 2^-fg2) -> scaled for the second quantiser (x 2^fg1): exact
+  const bool has_dadd = p.d_add != nullptr;
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -464,10 +528,12 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
       const int c0 = (int)((4ull * v) % (uint64_t)C);
       const float4 u2v = site_noise(p.qg2, v, off2), u1v = site_noise(p.qg1, v, off1);
       const float u2[4] = {u2v.x, u2v.y, u2v.z, u2v.w}, u1[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
-      float g[4], b[4];
+      float gk[4], b[4], gd[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        g[j] = __ldg(p.gq + c0 + j);
+        const float gq = __ldg(p.gq + c0 + j);
+        gk[j] = gq * c2.inv_m;     // for the ReLU mask: xq2 * gq = k2 * (gq / m2)
+        gd[j] = gq * gscale;       // dx2 * mg1 = kg2 * (gq * mg1 / mg2)
         b[j] = __ldg(p.bq + c0 + j);
       }
       const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
@@ -481,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
             gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
             w2[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k2 + idx));
             w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
-            if (p.relu == 2) ov[i] = __ldcs(reinterpret_cast<const float4*>(p.out + idx));
+            if (RELU == 2) ov[i] = __ldcs(reinterpret_cast<const float4*>(p.out + idx));
           }
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
@@ -490,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
             prefetch_l1(p.g + idx);
             prefetch_l1(p.k2 + idx);
             prefetch_l1(p.k1 + idx);
-            if (p.relu == 2) prefetch_l1(p.out + idx);
+            if (RELU == 2) prefetch_l1(p.out + idx);
           }
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
@@ -499,32 +565,34 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
             int k2[4], k1[4];
             unpack4(w2[i], k2);
             unpack4(w1[i], k1);
+            float k2f[4];
+            if (RELU == 1) dec4_f(w2[i], k2f);
             const float gin[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
             const float oin[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w};
-            float gm[4], kq1[4];
+            float gm[4], t1[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float gj = gin[j];
-              if (p.relu == 1) {
-                const float y2 = __fadd_rn(__fmul_rn(__int2float_rn(k2[j]) * c2.inv_m, g[j]), b[j]);
+              if (RELU == 1) {
+                const float y2 = __fadd_rn(__fmul_rn(k2f[j], gk[j]), b[j]);
                 if (!(y2 > 0.0f)) gj = 0.0f;
-              } else if (p.relu == 2) {
+              } else if (RELU == 2) {
                 if (!(oin[j] > 0.0f)) gj = 0.0f;
               }
               gm[j] = gj;
-              const float kg2 = mm2 ? squant_mm(gj, u2[j], cg2, amx, amn) : squant(gj, u2[j], cg2, a1, a2);   // dfxp:687
-              const int kg2i = __float2int_rn(kg2);
+              const float tg2 = sq_scaled<MM>(__fmul_rn(gj, cg2.m), u2[j], cg2, amx, amn, a1, a2);   // dfxp:687
+              const int kg2i = tm_int(tg2);
               acc.s[0][j] += kg2i;                                                 // dbeta  (dfxp:690)
-              acc.s[1][j] += kg2i * k2[j];                                         // dgamma (dfxp:689)
-              const float dx2 = __fmul_rn(kg2 * cg2.inv_m, g[j]);                  // dfxp:691
-              kq1[j] = mm1 ? squant_mm(dx2, u1[j], cg1, bmx, bmn) : squant(dx2, u1[j], cg1, b1, b2);         // dfxp:621
-              const int kg1i = __float2int_rn(kq1[j]);
+              acc.s[1][j] += (AccT)kg2i * k2[j];                                   // dgamma (dfxp:689)
+              // dx2 = gq2 * gamma_q (dfxp:691), scaled for the next quantiser (dfxp:621) in the same multiply
+              t1[j] = sq_scaled<MM>(__fmul_rn(tm_float(tg2), gd[j]), u1[j], cg1, bmx, bmn, b1, b2);
+              const int kg1i = tm_int(t1[j]);
               acc.s[2][j] += kg1i;
-              acc.s[3][j] += kg1i * k1[j];
+              acc.s[3][j] += (AccT)kg1i * k1[j];
             }
-            if (p.d_add) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
-            if (WIDE) *reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(p.kg1) + idx) = pack4_s16(kq1);
-            else *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(p.kg1) + idx) = pack4(kq1);
+            if (has_dadd) *reinterpret_cast<float4*>(p.d_add + idx) = make_float4(gm[0], gm[1], gm[2], gm[3]);
+            if (WIDE) *reinterpret_cast<uint2*>(reinterpret_cast<int16_t*>(p.kg1) + idx) = tm_pack4_s16(t1);
+            else *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(p.kg1) + idx) = tm_pack4(t1);
           }
       }
       if (!p.t.fixed_channels) flush_global(acc, p.sums, C, c0);
@@ -532,8 +600,10 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
   }
   if (p.t.fixed_channels) flush_block(acc, p.sums, C, s_acc);
   const size_t numel = p.t.n_outer * p.t.n_inner;
-  if (mm2) mm_to_counts(cg2, amx, amn, a1, a2);
-  if (mm1) mm_to_counts(cg1, bmx, bmn, b1, b2);
+  if (MM) {
+    mm_to_counts(cg2, amx, amn, a1, a2);
+    mm_to_counts(cg1, bmx, bmn, b1, b2);
+  }
   publish_counters(p.qg2.counters, a1, a2, numel, s_red);
   publish_counters(p.qg1.counters, b1, b2, numel, s_red);
 }
@@ -558,9 +628,10 @@ struct Bwd2Params {
   uint8_t* g_mant_lo;      // ... with the low byte plane here (k = 256 * hi + lo)
 };
 
-template <bool WIDE>
+// WIDE: kg1 is s16.  MM: min/max statistics for the fused gradient quantiser.  ~27 full-rate instructions per element.
+template <bool WIDE, bool MM>
 __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
-  extern __shared__ float s_par[];  // [5*C]: mean, 1/den, mean_g, mean_gxhat, (unused)
+  extern __shared__ float s_par[];  // [4*C]: -mean, den, mean_g, mean_gxhat
   __shared__ uint32_t s_red[16];
   pdl_trigger();
   pdl_wait();
@@ -575,7 +646,6 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   }
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
-  const bool mmq = p.qg.minmax != 0;
   {  // start pulling this CTA's first rows while the (slow, fp64) per-channel prologue runs
     const uint64_t tile = blockIdx.x;
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), v = (uint32_t)(tile % p.t.chunks) * kThreads + threadIdx.x;
@@ -591,6 +661,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     }
   }
   const bool q16 = gq_on && p.qg.bits > 8;
+  const bool has_dx = p.dx != nullptr;
   const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
   const QC cg = make_qc(p.bitsg1, __ldg(p.ibg1));
   const DivN n = make_divn((unsigned long long)(p.t.n_outer * (p.t.n_inner / C)));
@@ -604,7 +675,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     const double mg = div_n(sg, n);
     // mean(gq * xhat); every fp64 operation rounded on its own (no DFMA contraction) so the oracle can restate it
     const double mgx = div_n(__ddiv_rn(__dsub_rn(sgx, __dmul_rn((double)mean, sg)), (double)den), n);
-    s_par[ch] = mean;
+    s_par[ch] = -mean;
     s_par[C + ch] = den;
     s_par[2 * C + ch] = (float)mg;
     s_par[3 * C + ch] = (float)mgx;
@@ -617,17 +688,15 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     const uint32_t v = chk * kThreads + threadIdx.x;
     if (v >= p.t.n_vec) continue;
     const int c0 = (int)((4ull * v) % (uint64_t)C);
-    float mean[4], den[4], mg[4], mgx[4];
+    float nmean[4], den[4], rden[4], mg[4], mgx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      mean[j] = s_par[c0 + j];
+      nmean[j] = s_par[c0 + j];
       den[j] = s_par[C + c0 + j];
+      rden[j] = __frcp_rn(den[j]);
       mg[j] = s_par[2 * C + c0 + j];
       mgx[j] = s_par[3 * C + c0 + j];
     }
-    float rden[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) rden[j] = __frcp_rn(den[j]);
     float uq[4] = {0.f, 0.f, 0.f, 0.f};
     if (gq_on) {
       const float4 t = site_noise(p.qg, v, offq);
@@ -645,35 +714,41 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
           else wg[i].x = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(p.kg1) + idx));
           w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
         }
-
+#pragma unroll
+      for (int i = 0; i < kRows; ++i)
+        if (r + kRows + i < r1) {
+          const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+          prefetch_l1(reinterpret_cast<const int8_t*>(p.kg1) + (WIDE ? 2 : 1) * idx);
+          prefetch_l1(p.k1 + idx);
+        }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
           const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
-          int kg[4], k1[4];
-          if (WIDE) unpack4_s16(wg[i], kg);
-          else unpack4(wg[i].x, kg);
-          unpack4(w1[i], k1);
+          float kgf[4], k1f[4];
+          if (WIDE) dec4_f_s16(wg[i], kgf);
+          else dec4_f(wg[i].x, kgf);
+          dec4_f(w1[i], k1f);
           float o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float gq = __int2float_rn(kg[j]) * cg.inv_m;
-            const float xhat = fdiv_by(__fsub_rn(__int2float_rn(k1[j]) * c1.inv_m, mean[j]), den[j], rden[j]);
-            // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616)
-            o[j] = fdiv_by(__fsub_rn(__fsub_rn(gq, mg[j]), __fmul_rn(xhat, mgx[j])), den[j], rden[j]);   // one rounding per op
+            const float gq = __fmul_rn(kgf[j], cg.inv_m);
+            const float xhat = fdiv_fast(__fmaf_rn(k1f[j], c1.inv_m, nmean[j]), den[j], rden[j]);
+            // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616); one rounding per operation
+            o[j] = fdiv_fast(__fsub_rn(__fsub_rn(gq, mg[j]), __fmul_rn(xhat, mgx[j])), den[j], rden[j]);
           }
-          if (p.dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (has_dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
           if (gq_on) {                                                        // the convolution's gradq, dfxp:300
-            float kq[4];
+            float tq[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) kq[j] = mmq ? squant_mm(o[j], uq[j], cq, mx, mn) : squant(o[j], uq[j], cq, n1, n2);
+            for (int j = 0; j < 4; ++j) tq[j] = sq_scaled<MM>(__fmul_rn(o[j], cq.m), uq[j], cq, mx, mn, n1, n2);
             if (q16) {   // 9..16-bit gradient: the two byte planes the tensor cores consume (no separate split pass)
               uint32_t hi, lo;
-              pack4_hilo(kq, hi, lo);
+              tm_pack4_hilo(tq, hi, lo);
               *reinterpret_cast<uint32_t*>(p.g_mant + idx) = hi;
               *reinterpret_cast<uint32_t*>(p.g_mant_lo + idx) = lo;
             } else {
-              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = pack4(kq);
+              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = tm_pack4(tq);
             }
           }
         }
@@ -681,7 +756,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   }
   bn_stamp(3);
   if (gq_on) {
-    if (mmq) mm_to_counts(cq, mx, mn, n1, n2);
+    if (MM) mm_to_counts(cq, mx, mn, n1, n2);
     publish_counters(p.qg.counters, n1, n2, p.t.n_outer * p.t.n_inner, s_red);
   }
   bn_stamp(4);
@@ -1040,7 +1115,10 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   LBT_REQUIRE_ARCH();
   Fwd2Params p{};
   unsigned grid;
-  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel, (size_t)4 * C * 4));
+  // one statistics flavour per launch: min/max only when EVERY site of the launch asked for it (exact counts are always valid)
+  const bool mm = stats_minmax && (!q_next || q_next->stats_minmax);
+  int rc = mm ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel<true>, (size_t)4 * C * 4))
+              : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel<false>, (size_t)4 * C * 4));
   if (rc) return rc;
   p.k1 = k1;
   p.bits1 = bits1;
@@ -1063,8 +1141,13 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.q3 = site_from_abi(q_next);
   p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
   const size_t smem = (size_t)4 * C * 4;
-  if ((rc = set_smem(bn_fwd2_kernel, smem))) return rc;
-  launch_pdl(bn_fwd2_kernel, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  if (mm) {
+    if ((rc = set_smem(bn_fwd2_kernel<true>, smem))) return rc;
+    launch_pdl(bn_fwd2_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  } else {
+    if ((rc = set_smem(bn_fwd2_kernel<false>, smem))) return rc;
+    launch_pdl(bn_fwd2_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  }
   return check_launch("lbt_bn_fwd_apply");
 }
 
@@ -1089,8 +1172,15 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   LBT_REQUIRE_ARCH();
   Bwd1Params p{};
   unsigned grid;
-  int rc = wide ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel<true>, (size_t)4 * C * 8))
-                : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd1_kernel<false>, (size_t)4 * C * 8));
+  void (*kern)(const Bwd1Params) = nullptr;
+  {
+    const bool mm = stats_minmax != 0;
+#define LBT_BWD1(W, M)                                                                                     \
+  (relu == 0 ? bn_bwd1_kernel<W, M, 0> : (relu == 1 ? bn_bwd1_kernel<W, M, 1> : bn_bwd1_kernel<W, M, 2>))
+    kern = wide ? (mm ? LBT_BWD1(true, true) : LBT_BWD1(true, false)) : (mm ? LBT_BWD1(false, true) : LBT_BWD1(false, false));
+#undef LBT_BWD1
+  }
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(kern, (size_t)4 * C * 8));
   if (rc) return rc;
   p.g = g;
   p.out = out;
@@ -1107,13 +1197,8 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   p.kg1 = kg1;
   p.sums = reinterpret_cast<long long*>(sums);
   const size_t smem = (size_t)4 * C * 8;
-  if (wide) {
-    if ((rc = set_smem(bn_bwd1_kernel<true>, smem))) return rc;
-    launch_pdl(bn_bwd1_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  } else {
-    if ((rc = set_smem(bn_bwd1_kernel<false>, smem))) return rc;
-    launch_pdl(bn_bwd1_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  }
+  if ((rc = set_smem(kern, smem))) return rc;
+  launch_pdl(kern, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_quant_stats");
 }
 
@@ -1136,8 +1221,10 @@ extern "C" int lbt_bn_bwd_apply(const void* kg1, const int8_t* k1, size_t n_oute
   LBT_REQUIRE_ARCH();
   Bwd2Params p{};
   unsigned grid;
-  int rc = wide ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel<true>, (size_t)4 * C * 4))
-                : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_bwd2_kernel<false>, (size_t)4 * C * 4));
+  const bool mm = q_grad != nullptr && q_grad->stats_minmax != 0;
+  void (*kern)(const Bwd2Params) = wide ? (mm ? bn_bwd2_kernel<true, true> : bn_bwd2_kernel<true, false>)
+                                        : (mm ? bn_bwd2_kernel<false, true> : bn_bwd2_kernel<false, false>);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(kern, (size_t)4 * C * 4));
   if (rc) return rc;
   p.kg1 = kg1;
   p.k1 = k1;
@@ -1153,13 +1240,8 @@ extern "C" int lbt_bn_bwd_apply(const void* kg1, const int8_t* k1, size_t n_oute
   p.g_mant = g_mant;
   p.g_mant_lo = g_mant_lo;
   const size_t smem = (size_t)4 * C * 4;
-  if (wide) {
-    if ((rc = set_smem(bn_bwd2_kernel<true>, smem))) return rc;
-    launch_pdl(bn_bwd2_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  } else {
-    if ((rc = set_smem(bn_bwd2_kernel<false>, smem))) return rc;
-    launch_pdl(bn_bwd2_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  }
+  if ((rc = set_smem(kern, smem))) return rc;
+  launch_pdl(kern, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_apply");
 }
 

@@ -570,7 +570,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (C % 16) return LBT_EUNSUPPORTED;
   // measured (benchmarks/gemm_bench.py --path 0|1): the cp.async gather wins for 16- and 32-byte pixel rows (3.1x / 1.1x),
   // the TMA im2col kernel for 64 bytes and more
-  if (conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw))) &&
+  if (conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C))) &&
       conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)

@@ -11,7 +11,7 @@ namespace lbt {
 
 bool conv_ldg_ok(int C, int Cout, int kh, int kw);
 bool conv_ldg_enabled();
-bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw);
+bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw, int C);
 int conv_ldg_c64_halo();   // 1: 64-channel inputs take the gather kernel when its halo loader applies
 int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                  int kh, int kw, int sh, int sw, int pt, int pl, int OH, int OW, int gather, const int32_t* ibA,

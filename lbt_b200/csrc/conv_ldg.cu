@@ -77,6 +77,12 @@ struct LdgParams {
   uint32_t halo_plane;           // bytes of one 16-channel plane of the halo: halo_px * 16
   uint32_t stage_bytes;          // ring slot: kStageBytes (gather modes) / CPP planes + slack (halo mode)
   FastDiv d_tiles_img, d_tiles_x;
+  // strided halo (sh = sw = 2, 16-byte pixels: the 7x7/2 ImageNet stem on the {hi,hi,lo,0} x 16 image layout): the patch is
+  // stored as `sw` column-parity planes so that neighbouring OUTPUT pixels are 16 bytes apart for every filter tap
+  uint32_t halo_hw2;             // columns of one parity plane: halo_w / sw
+  uint32_t halo_par_plane;       // bytes of one parity plane: halo rows * halo_hw2 * 16
+  uint32_t halo_mmas;            // MMA instructions per tile (stride 1: KCp / 2)
+  FastDiv d_halo_w;
 };
 
 __device__ __forceinline__ void dbg_stamp(const LdgParams& p, int slot) {
@@ -128,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   __shared__ unsigned long long s_tot[kStats * BN];   // CTA totals of the fused statistics
   __shared__ int2 s_tab[kMaxKC + 8];       // tap slot: {byte offset from the row's base pixel, tap code}
   __shared__ uint2 s_mma[HALO ? kMaxKC / 2 : 1];   // halo mode, MMA j: {A start offset in the stage, leading byte offset}
+  __shared__ short s_kmap[HALO ? kMaxKC : 1];      // halo mode: filter chunk at each position of the resident bank
 
   constexpr int kTmemCols = (kAccStages * BN) < 32 ? 32 : (kAccStages * BN);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -160,17 +167,33 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     const int code = ts < p.taps ? (int)ts : (ts * CPP < p.KCp ? 255 : 254);
     s_tab[ts] = make_int2(ts < p.taps ? d : 0, code);
   }
-  if (HALO) {   // s_tab[hp] = (row, column) of halo pixel hp; s_tab is big enough for 5x5 filters (20 x 12 halo)
-    for (uint32_t hp = threadIdx.x; hp < p.halo_px; hp += kThreads) s_tab[hp] = make_int2((int)(hp / p.halo_w), (int)(hp % p.halo_w));
-    for (uint32_t j = threadIdx.x; j < (p.KCp >> 1); j += kThreads) {
-      const uint32_t kc = 2 * j, tap = kc / CPP;   // K chunk = tap * CPP + cc
-      const uint32_t r = tap / p.kw, sx = tap - r * p.kw;
-      uint32_t lbo = p.halo_plane;
-      if (CPP == 1) {   // the instruction's second chunk is the NEXT tap (or, past the last one, anything: zero weights)
-        const uint32_t t1 = tap + 1 < p.taps ? tap + 1 : tap, r1 = t1 / p.kw, s1 = t1 - r1 * p.kw;
-        lbo = t1 > tap ? ((r1 * p.halo_w + s1) - (r * p.halo_w + sx)) * 16 : 16;
+  if (HALO) {
+    // MMA j of a tile: {A start offset inside the ring slot, leading byte offset}; s_kmap[kc] = the filter chunk (tap * CPP + cc)
+    // that sits at position kc of the resident bank (-1: zero chunk)
+    if (p.sw == 1) {
+      for (uint32_t j = threadIdx.x; j < p.halo_mmas; j += kThreads) {
+        const uint32_t kc = 2 * j, tap = kc / CPP;   // K chunk = tap * CPP + cc
+        const uint32_t r = tap / p.kw, sx = tap - r * p.kw;
+        uint32_t lbo = p.halo_plane;
+        if (CPP == 1) {   // the instruction's second chunk is the NEXT tap (or, past the last one, anything: zero weights)
+          const uint32_t t1 = tap + 1 < p.taps ? tap + 1 : tap, r1 = t1 / p.kw, s1 = t1 - r1 * p.kw;
+          lbo = t1 > tap ? ((r1 * p.halo_w + s1) - (r * p.halo_w + sx)) * 16 : 16;
+        }
+        s_mma[j] = make_uint2((kc % CPP) * p.halo_plane + (r * p.halo_w + sx) * 16, lbo);
       }
-      s_mma[j] = make_uint2((kc % CPP) * p.halo_plane + (r * p.halo_w + sx) * 16, lbo);
+      for (uint32_t kc = threadIdx.x; kc < p.KCp; kc += kThreads) s_kmap[kc] = kc < p.KC ? (short)kc : (short)-1;
+    } else {
+      // stride 2 (CPP == 1): an instruction covers taps (r, s) and (r, s + 2) — same column parity, neighbouring columns of
+      // that parity plane (lbo = 16 B); per filter row: ceil(n0 / 2) + ceil(n1 / 2) instructions, n0 / n1 even / odd columns
+      const uint32_t n0 = (p.kw + 1) / 2, n1 = p.kw / 2, p0 = (n0 + 1) / 2, per_row = p0 + (n1 + 1) / 2;
+      for (uint32_t j = threadIdx.x; j < p.halo_mmas; j += kThreads) {
+        const uint32_t r = j / per_row, jj = j - r * per_row;
+        const uint32_t q = jj < p0 ? 0u : 1u, pi = jj - (q ? p0 : 0u);
+        const uint32_t s0 = q + 4 * pi, s1 = s0 + 2;
+        s_mma[j] = make_uint2(q * p.halo_par_plane + (r * p.halo_hw2 + (s0 >> 1)) * 16, 16u);
+        s_kmap[2 * j] = (short)(r * p.kw + s0);
+        s_kmap[2 * j + 1] = s1 < p.kw ? (short)(r * p.kw + s1) : (short)-1;
+      }
     }
   }
   pdl_trigger();
@@ -183,8 +206,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
 #if LBT_PDL_TRIGGER_AFTER_WAIT
   if (p.w_prepared && warp > kLoaderWarps) {
     for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 32 * kEpiWarps) {
-      const uint32_t kc = i / BN, n = i % BN;
-      const bool v = kc < p.KC && n < p.N;
+      const uint32_t kp = i / BN, n = i % BN;
+      const int kc = HALO ? (int)s_kmap[kp] : (kp < p.KC ? (int)kp : -1);
+      const bool v = kc >= 0 && n < p.N;
       cp_async16(smem_u32(sB + (size_t)i * 16), v ? p.wp + (size_t)n * p.ldw + (size_t)kc * 16 : p.wp, v ? 16u : 0u);
     }
     cp_async_arrive_noinc(&b_bar);
@@ -205,17 +229,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       const uint32_t stage = seq % p.nstages, phase = (seq / p.nstages) & 1u;
       const uint32_t img = fastdiv(tile, p.d_tiles_img), t2 = tile - img * p.d_tiles_img.d;
       const uint32_t ty = fastdiv(t2, p.d_tiles_x), tx = t2 - ty * p.d_tiles_x.d;
-      const int y0 = (int)(ty * 16) - p.pt, x0 = (int)(tx * 8) - p.pl;
+      const int y0 = (int)(ty * 16) * p.sh - p.pt, x0 = (int)(tx * 8) * p.sw - p.pl;
       const uint8_t* ibase = p.src + (size_t)img * p.SH * p.SW * p.C;
       ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_ldg_error);
       if (!ok) break;
       const uint32_t dst0 = smem_u32(sA + (size_t)stage * p.stage_bytes);
       for (uint32_t idx = lane; idx < p.halo_px * CPP; idx += 32) {
         const uint32_t hp = idx / CPP, cc = idx % CPP;
-        const int2 yx = s_tab[hp];
-        const int iy = y0 + yx.x, ix = x0 + yx.y;
+        const uint32_t hr = fastdiv(hp, p.d_halo_w), hc = hp - hr * p.halo_w;   // (row, column) of the halo pixel
+        const int iy = y0 + (int)hr, ix = x0 + (int)hc;
         const bool v = iy >= 0 && iy < (int)p.SH && ix >= 0 && ix < (int)p.SW;
-        cp_async16(dst0 + cc * p.halo_plane + hp * 16, v ? ibase + ((size_t)iy * p.SW + ix) * p.C + cc * 16 : p.src, v ? 16u : 0u);
+        // stride 1: pixel hp of plane cc; stride 2 (CPP == 1): column-parity plane hc & 1, column hc >> 1
+        const uint32_t d = p.sw == 1 ? cc * p.halo_plane + hp * 16 : (hc & 1u) * p.halo_par_plane + (hr * p.halo_hw2 + (hc >> 1)) * 16;
+        cp_async16(dst0 + d, v ? ibase + ((size_t)iy * p.SW + ix) * p.C + cc * 16 : p.src, v ? 16u : 0u);
       }
       cp_async_arrive_noinc(&full_bar[stage]);
       if (threadIdx.x == 0 && tile == blockIdx.x) dbg_stamp(p, 2);
@@ -317,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
           if (tile == blockIdx.x) dbg_stamp(p, 8);
           if (p.dbg && blockIdx.x == 0 && tile / gridDim.x < 10) dbg_stamp(p, 32 + tile / gridDim.x);
           const uint32_t sa = smem_u32(sA + (size_t)stage * p.stage_bytes);
-          const uint32_t sbo = p.halo_w * 16;
-          for (uint32_t j = 0; j < (p.KCp >> 1); ++j) {
+          const uint32_t sbo = p.sw == 1 ? p.halo_w * 16 : p.sh * p.halo_hw2 * 16;   // next output row of the patch
+          for (uint32_t j = 0; j < p.halo_mmas; ++j) {
             const uint2 t = s_mma[j];
             umma_i8(d_tmem, make_desc_k16(sa + t.x, t.y, sbo), make_desc_kmajor(sb0 + 2 * j * (BN * 16), 0, BN * 16), p.idesc,
                     first ? 0u : 1u);
@@ -365,8 +391,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
 #endif
     {
     for (uint32_t i = threadIdx.x - 32 * (kLoaderWarps + 1); i < p.KCp * BN; i += 32 * kEpiWarps) {
-      const uint32_t kc = i / BN, n = i % BN;
-      const bool v = kc < p.KC && n < p.N;
+      const uint32_t kp = i / BN, n = i % BN;
+      const int kc = HALO ? (int)s_kmap[kp] : (kp < p.KC ? (int)kp : -1);
+      const bool v = kc >= 0 && n < p.N;
       cp_async16(smem_u32(sB + (size_t)i * 16), v ? p.wp + (size_t)n * p.ldw + (size_t)kc * 16 : p.wp, v ? 16u : 0u);
     }
     cp_async_arrive_noinc(&b_bar);
@@ -761,16 +788,21 @@ std::atomic<int> g_use_ldg{1};
 std::atomic<int> g_use_halo{1};   // lbt_conv_set_halo(): 0 = gather the im2col rows even where the halo patch applies
 std::atomic<unsigned long long*> g_dbg{nullptr};
 bool conv_ldg_enabled() { return g_use_ldg.load(std::memory_order_relaxed) != 0; }
+std::atomic<int> g_halo_any_fill{0};   // test knob: take the halo loader whatever fraction of the 8 x 16 patches lies outside the image
 std::atomic<int> g_c64_halo{0};   // measured: ResNet-18's 64-channel layers lose 4 % in the step against the TMA kernel (the microbench gains 15 %)
 int conv_ldg_c64_halo() { return g_c64_halo.load(std::memory_order_relaxed); }
 
 // Shapes this kernel takes.
 // Halo-patch loader: stride-1 gather of a filter up to 5x5 on images that fill 8 x 16 output patches reasonably (<= 35 % of
 // the patch pixels outside the image).
-bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw) {
-  if (!g_use_halo.load(std::memory_order_relaxed) || sh != 1 || sw != 1 || kh > 5 || kw > 5 || kh * kw <= 1) return false;
+bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw, int C) {
+  if (!g_use_halo.load(std::memory_order_relaxed) || kh * kw <= 1) return false;
+  const bool s1 = sh == 1 && sw == 1 && kh <= 5 && kw <= 5;
+  const bool s2 = sh == 2 && sw == 2 && C == 16 && kh <= 8 && kw <= 8 && kh * kw <= kMaxTaps;   // the 7x7/2 stem on 16-byte pixels
+  if (!s1 && !s2) return false;
   const uint64_t tx = (uint64_t)(OW + 7) / 8, ty = (uint64_t)(OH + 15) / 16;
-  return tx * 8 * ty * 16 * 100 <= (uint64_t)OH * OW * 135 && (uint64_t)N * tx * ty < (1ull << 31);
+  const bool fill_ok = g_halo_any_fill.load(std::memory_order_relaxed) || tx * 8 * ty * 16 * 100 <= (uint64_t)OH * OW * 135;
+  return fill_ok && (uint64_t)N * tx * ty < (1ull << 31);
 }
 
 bool conv_ldg_ok(int C, int Cout, int kh, int kw) {
@@ -953,12 +985,25 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   p.n_img = (uint32_t)N;
   p.stage_bytes = kStageBytes;
   bool halo = false;
-  if (gather == 0 && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw)) {
+  if (gather == 0 && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C)) {
     const uint32_t tx = (uint32_t)(OW + 7) / 8, ty = (uint32_t)(OH + 15) / 16;
     halo = true;
-    p.halo_w = 8 + (uint32_t)kw - 1;
-    p.halo_px = p.halo_w * (16 + (uint32_t)kh - 1);
+    const uint32_t halo_h = 15u * (uint32_t)sh + (uint32_t)kh;
+    p.halo_w = 7u * (uint32_t)sw + (uint32_t)kw;
+    p.halo_w = (p.halo_w + (uint32_t)sw - 1) / (uint32_t)sw * (uint32_t)sw;          // whole column-parity groups
+    p.halo_px = p.halo_w * halo_h;
     p.halo_plane = p.halo_px * 16;
+    p.halo_hw2 = p.halo_w / (uint32_t)sw;
+    p.halo_par_plane = halo_h * p.halo_hw2 * 16;
+    p.d_halo_w = make_fastdiv(p.halo_w);
+    if (sw == 1) {
+      p.halo_mmas = p.KCp >> 1;
+    } else {   // taps (r, s), (r, s + 2) per instruction: see the kernel
+      const uint32_t n0 = ((uint32_t)kw + 1) / 2, n1 = (uint32_t)kw / 2;
+      p.halo_mmas = (uint32_t)kh * ((n0 + 1) / 2 + (n1 + 1) / 2);
+      p.KCp = 2 * p.halo_mmas;
+      if (p.KCp > (uint32_t)kMaxKC) return LBT_EUNSUPPORTED;
+    }
     p.stage_bytes = ((p.cpp * p.halo_plane + 64) + 127) & ~127u;   // + slack: the padding chunk of an odd tap count
     p.d_tiles_img = make_fastdiv(tx * ty);
     p.d_tiles_x = make_fastdiv(tx);
@@ -1043,6 +1088,7 @@ extern "C" int lbt_conv_set_path(int use_ldg) {
 extern "C" int lbt_conv_set_halo(int mask) {
   g_use_halo.store(mask & 1, std::memory_order_relaxed);
   g_c64_halo.store((mask >> 1) & 1, std::memory_order_relaxed);
+  g_halo_any_fill.store((mask >> 2) & 1, std::memory_order_relaxed);   // bit 2: ignore the patch fill-ratio rule (tests)
   return LBT_OK;
 }
 

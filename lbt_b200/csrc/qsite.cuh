@@ -54,6 +54,24 @@ __device__ __forceinline__ void mm_to_counts(const QC& c, float mx, float mn, ui
   n2 = (mx >= c.half || mn < -c.half) ? 1u : 0u;
 }
 
+// Conversion-free floor (the fused kernels are issue-bound and FRND / F2I / I2F run at quarter rate): for |t| < 2^22,
+// tm = RD(t + 1.5 * 2^23) is ONE full-rate FADD.RM; floor(t) as an integer is bits(tm) - 0x4B400000, as a float tm - 1.5 * 2^23,
+// and the low byte(s) of bits(tm) are the two's-complement mantissa byte(s).
+constexpr float kFloorMagicF = 12582912.0f;
+constexpr int kFloorMagicI = 0x4B400000;
+__device__ __forceinline__ int squant_i(float x, float u, const QC& c, uint32_t& n1, uint32_t& n2) {
+  const float y = __fmul_rn(x, c.m);
+  n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
+  n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
+  return __float_as_int(__fadd_rd(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi), kFloorMagicF)) - kFloorMagicI;
+}
+__device__ __forceinline__ int squant_mm_i(float x, float u, const QC& c, float& mx, float& mn) {
+  const float y = __fmul_rn(x, c.m);
+  mx = fmaxf(mx, y);
+  mn = fminf(mn, y);
+  return __float_as_int(__fadd_rd(fminf(fmaxf(__fadd_rn(y, u), -c.L), c.hi), kFloorMagicF)) - kFloorMagicI;
+}
+
 // a / b, correctly rounded (== __fdiv_rn), for MANY numerators over ONE denominator: r = frcp_rn(b) is computed once
 // (per channel) and each quotient costs five FMA-class instructions instead of the ~12 + special-case branch of the
 // generic IEEE division.  Markstein's scheme: q0 = RN(a*r); two residual corrections q += RN(a - b*q) * r with exact
@@ -157,8 +175,8 @@ __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, cons
     for (int t = 0; t < 4; ++t) {
       const int j = 4 * g + t;
       const float x = (row_ok && (uint32_t)j < ncol) ? f[j] : 0.0f;
-      const float kf = b.q.minmax ? squant_mm(x, un[t], st.qc, st.mx, st.mn) : squant(x, un[t], st.qc, st.n1, st.n2);
-      const int k = (row_ok && (uint32_t)j < ncol) ? __float2int_rn(kf) : 0;
+      const int kk = b.q.minmax ? squant_mm_i(x, un[t], st.qc, st.mx, st.mn) : squant_i(x, un[t], st.qc, st.n1, st.n2);
+      const int k = (row_ok && (uint32_t)j < ncol) ? kk : 0;
       ki[j] = k;
       kq[j] = k * k;
     }
@@ -329,11 +347,12 @@ __device__ __forceinline__ void gq_chunk(const GqParams& b, GqState& st, const f
         const float y2 = __fadd_rn(__fmul_rn(__int2float_rn(k2) * st.c2.inv_m, gam[t]), bet[t]);
         if (!(y2 > 0.0f)) gj = 0.0f;
       }
-      const float kg2 = b.g2.minmax ? squant_mm(gj, un2[t], st.cg2, st.amx, st.amn) : squant(gj, un2[t], st.cg2, st.a1, st.a2);
-      const int kg2i = ok ? __float2int_rn(kg2) : 0;
+      const int kg2r = b.g2.minmax ? squant_mm_i(gj, un2[t], st.cg2, st.amx, st.amn) : squant_i(gj, un2[t], st.cg2, st.a1, st.a2);
+      const int kg2i = ok ? kg2r : 0;
+      const float kg2 = __fsub_rn(__int_as_float(kg2r + kFloorMagicI), kFloorMagicF);   // the mantissa as a float, no I2F
       const float dx2 = ok ? __fmul_rn(kg2 * st.cg2.inv_m, gam[t]) : 0.0f;
-      const float kq1 = b.g1.minmax ? squant_mm(dx2, un1[t], st.cg1, st.bmx, st.bmn) : squant(dx2, un1[t], st.cg1, st.b1, st.b2);
-      const int kg1i = ok ? __float2int_rn(kq1) : 0;
+      const int kg1r = b.g1.minmax ? squant_mm_i(dx2, un1[t], st.cg1, st.bmx, st.bmn) : squant_i(dx2, un1[t], st.cg1, st.b1, st.b2);
+      const int kg1i = ok ? kg1r : 0;
       v[t] = kg2i;
       v[4 + t] = kg2i * k2;
       v[8 + t] = kg1i;

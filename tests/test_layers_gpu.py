@@ -334,3 +334,51 @@ def test_conv_halo_loader_equals_row_gather(N, H, W, Cin, Cout, k, pad):
     ref = F.conv2d(xe, we, padding=pad).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
     want = ((ref * 2.0 ** (-12 + 2)).float() + bias) + addend
     assert torch.equal(res[1][0], want)
+
+
+@pytest.mark.parametrize('N,H,W,Cout,k', [(2, 64, 64, 64, 7), (3, 48, 40, 32, 7), (2, 32, 32, 16, 3), (1, 66, 50, 64, 5), (2, 37, 45, 64, 7),
+                                          (1, 224, 224, 64, 7), (2, 34, 34, 128, 4), (1, 40, 72, 48, 8)])
+def test_conv_halo_stride2_equals_row_gather(N, H, W, Cout, k):
+    """The strided halo-patch loader (7x7/2 ImageNet stem on 16-byte pixels: column-parity planes in shared memory, taps
+    (r, s) / (r, s + 2) per instruction) against the im2col-row gather of the same kernel and against the exact convolution,
+    TF 'SAME' padding, fp32 and fused re-quantising epilogues."""
+    from lbt_b200 import _lib, quantizer as Q
+    rng = np.random.default_rng(N * H + W + Cout + k)
+    Cin = 16
+    OH, pt, _ = D.same_pad(H, k, 2)
+    OW, pl, _ = D.same_pad(W, k, 2)
+    x = torch.from_numpy(rng.integers(-128, 128, (N, H, W, Cin), dtype=np.int8)).cuda()
+    Kf = k * k * Cin
+    w = torch.from_numpy(rng.integers(-128, 128, (Cout, Kf), dtype=np.int8))
+    wt = torch.zeros(Cout, D._pitch16(Kf), dtype=torch.int8, device='cuda')[:, :Kf]
+    wt.copy_(w)
+    ib = torch.tensor(1, dtype=torch.int32, device='cuda')
+    bias = torch.randn(Cout, device='cuda')
+    rt = D.Runtime(seed=5)
+    site = D.QuantSite(rt, 'q', 8, 2).cuda()
+    rt.finalize('cuda')
+    res = {}
+    try:
+        for halo in (1, 0):
+            _lib.lib().lbt_conv_set_halo(7 if halo else 0)      # bit 2: ragged images too (partial 8 x 16 patches)
+            y = torch.full((N * OH * OW, Cout), float('nan'), device='cuda')
+            D._conv_implicit(x, Q.MANT_S8, wt, Cout, k, k, 2, 2, pt, pl, OH, OW, ib, ib, -14, bias, y)
+            k_out = torch.zeros(N * OH * OW, Cout, dtype=torch.int8, device='cuda')
+            sums = torch.zeros(2 * Cout, dtype=torch.int64, device='cuda')
+            site.counters.zero_()
+            qs = site.abi(OH * OW * Cout, 'cuda')
+            D._conv_implicit(x, Q.MANT_S8, wt, Cout, k, k, 2, 2, pt, pl, OH, OW, ib, ib, -14, None, None, bnq=(qs, k_out, sums))
+            torch.cuda.synchronize()
+            res[halo] = (y, k_out, sums, site.counters.clone())
+    finally:
+        _lib.lib().lbt_conv_set_halo(1)
+    assert _lib.lib().lbt_conv_ldg_debug_error() == 0
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
+    xe = x.double().permute(0, 3, 1, 2)
+    pb, pr = max((OH - 1) * 2 + k - H, 0) - pt, max((OW - 1) * 2 + k - W, 0) - pl
+    xe = F.pad(xe, (pl, pr, pt, pb))
+    we = w.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2).cuda()
+    ref = F.conv2d(xe, we, stride=2).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
+    want = (ref * 2.0 ** (-14 + 2)).float() + bias
+    assert torch.equal(res[1][0], want)
