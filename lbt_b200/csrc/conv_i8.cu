@@ -225,13 +225,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     bool ok = true;
     for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
       const uint32_t m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
+      const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
+      const uint32_t col0 = n_tile * BN;
+      if (fused) {   // this warp's noise lines of the tile: into L1 while the accumulator is still being computed
+#pragma unroll 1
+        for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16))
+          bnq_prefetch(p.bnq, pix, p.N, col0 + (uint32_t)c, row < p.M && col0 + (uint32_t)c < p.N && !(BN == 16 && half));
+      }
       ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_conv_error);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       fence_after();
-      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
-      const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
-      const uint32_t col0 = n_tile * BN;
       const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
       if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
         bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
@@ -584,6 +589,12 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (!q_out && ldc < (size_t)Cout) return LBT_EINVAL;
   const size_t Ktot = (size_t)kh * kw * C;
   if (ldw < Ktot) return LBT_EINVAL;
+  // stride-1 filters on 64- / 128-channel images that fill 8 x 16 patches: halo patches through the TMA engine (conv_halo.cu)
+  if (conv_halo_applies(N, OH, OW, C, Cout, kh, kw, sh, sw)) {
+    LBT_REQUIRE_ARCH();
+    return conv_halo_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w, exp_const,
+                         bias, out, ldc, q_out, k_out, sums, addend, stream);
+  }
   if (Ktot > 65536) return LBT_EUNSUPPORTED;  // exactness bound of one s32 accumulator
   if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
@@ -820,5 +831,7 @@ extern "C" int lbt_conv_debug_error(void) {
   int v = 0, zero = 0;
   if (cudaMemcpyFromSymbol(&v, g_conv_error, sizeof(int)) != cudaSuccess) return -1;
   cudaMemcpyToSymbol(g_conv_error, &zero, sizeof(int));
+  const int h = conv_halo_debug_error();
+  if (h > 0) v |= h;
   return v;
 }

@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t d, uint32_t mu
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");   // .cg: L1 is kept for the epilogue's noise lines
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -454,6 +454,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
           const uint32_t c = (uint32_t)(cf + 16 * q);
           gq_load_k(p.gq, row, rvalid && c < p.N, c, c < p.N ? min(16u, p.N - c) : 0u, p.N, pw2[q], pw1[q]);
         }
+      }
+      if (fused) {   // this warp's noise lines of the tile: into L1 while the accumulator is still being computed
+#pragma unroll 1
+        for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G)
+#pragma unroll
+          for (int q = 0; q < G / 16; ++q) bnq_prefetch(p.bnq, pix, p.N, (uint32_t)(c0 + 16 * q), rvalid && (uint32_t)(c0 + 16 * q) < p.N);
       }
       ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_ldg_error);
       ok = __all_sync(0xffffffffu, ok);
@@ -1089,6 +1095,7 @@ extern "C" int lbt_conv_set_halo(int mask) {
   g_use_halo.store(mask & 1, std::memory_order_relaxed);
   g_c64_halo.store((mask >> 1) & 1, std::memory_order_relaxed);
   g_halo_any_fill.store((mask >> 2) & 1, std::memory_order_relaxed);   // bit 2: ignore the patch fill-ratio rule (tests)
+  conv_halo_enable(!((mask >> 3) & 1));                                  // bit 3: 64- / 128-channel layers back on the im2col TMA kernel
   return LBT_OK;
 }
 

@@ -314,13 +314,18 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (uint32_t item = blockIdx.x; item < total_items && ok; item += gridDim.x) {
       const uint32_t m_tile = item % p.m_tiles, rest = item / p.m_tiles;
       const uint32_t n_tile = rest % p.n_tiles;
+      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
+      const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
+      const uint32_t col0 = n_tile * BN;
+      if (fused) {   // this warp's noise lines of the tile: into L1 while the accumulator is still being computed
+#pragma unroll 1
+        for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16))
+          bnq_prefetch(p.bnq, pix, p.N, col0 + (uint32_t)c, row < p.M && col0 + (uint32_t)c < p.N && !(BN == 16 && half));
+      }
       ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       tc_fence_after();
-      const uint32_t row = m_tile * kBlockM + quad * 32 + lane;
-      const uint32_t pix = fused ? row % p.bnq.rows_per_image : 0u;
-      const uint32_t col0 = n_tile * BN;
       const uint32_t taddr = tmem_base + acc * C::kAccCols + ((quad * 32u) << 16);
       if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
         bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);

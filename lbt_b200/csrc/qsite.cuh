@@ -157,6 +157,53 @@ __device__ __forceinline__ int warp_colsum16(const int (&v)[16], int lane) {
   return w1;
 }
 
+// Per-channel sum k and sum k^2 of a warp's 32 rows x 16 channels from the PACKED mantissas (w[i] = channels 4i .. 4i+3 of
+// this lane's row, two's-complement bytes), ~58 instructions instead of the ~140 of two 16-value butterflies:
+//   1. a 4 x 4 byte transpose inside each lane quad (2 x {SHFL, PRMT} per word): the lane then holds ONE channel of FOUR rows,
+//      channel 4i + 2 * (lane & 1) + ((lane >> 1) & 1);
+//   2. IDP4A with 0x01010101 / with itself: the sum and the sum of squares of those four rows;
+//   3. a reduce-scatter butterfly over the 8 quads (lane bits 4, 3, 2) of the 8 partials (7 SHFL).
+// Afterwards every lane holds ONE total: kind = lane bit 4 (0: sum k, 1: sum k^2) of channel
+// 4 * (2 * bit3 + bit2) + 2 * bit0 + bit1.  Returns the total; `chan` / `kind` tell the caller where it belongs.
+__device__ __forceinline__ int warp_colstats_packed(const uint32_t (&w)[4], int lane, int& chan, int& kind) {
+  const uint32_t sel1 = (lane & 1) ? 0x3726u : 0x5140u;   // even lane: [a0 b0 a1 b1]; odd lane: [a2 b2 a3 b3] (a = even lane's row)
+  const uint32_t sel2 = (lane & 2) ? 0x3276u : 0x5410u;   // bit1 = 0: first channel of the pair x 4 rows; bit1 = 1: second
+  int sv[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, w[i], 1);
+    const uint32_t t1 = __byte_perm(w[i], r1, sel1);
+    const uint32_t r2 = __shfl_xor_sync(0xffffffffu, t1, 2);
+    const uint32_t t2 = __byte_perm(t1, r2, sel2);
+    sv[i] = __dp4a((int)t2, 0x01010101, 0);
+    sv[4 + i] = __dp4a((int)t2, (int)t2, 0);
+  }
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  int a[4], b[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int send = b4 ? sv[j] : sv[j + 4];
+    a[j] = (b4 ? sv[j + 4] : sv[j]) + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int send = b3 ? a[j] : a[j + 2];
+    b[j] = (b3 ? a[j + 2] : a[j]) + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const int send = b2 ? b[0] : b[1];
+  const int tot = (b2 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+  kind = b4 ? 1 : 0;
+  chan = 4 * (2 * (b3 ? 1 : 0) + (b2 ? 1 : 0)) + 2 * (lane & 1) + ((lane >> 1) & 1);
+  return tot;
+}
+
+// The noise of a row's 16-channel chunk lives in the L2-resident noise arena; without help every chunk of the epilogue
+// starts with a ~700-cycle L2 round trip that 8 - 16 epilogue warps per SM cannot hide (ncu: long_scoreboard is the top
+// stall of the fused convolutions).  Called BEFORE the accumulator wait: pulls the line into L1 at no register cost.
+__device__ __forceinline__ void bnq_prefetch(const BnqParams& b, uint32_t pix, uint32_t N, uint32_t col, bool ok) {
+  if (b.q.noise && ok) asm volatile("prefetch.global.L1 [%0];" ::"l"(b.q.noise + (uint64_t)pix * N + col));
+}
+
 // One 16-channel chunk of one row.  f: the fp32 values the unfused path would have written (acc * 2^e).
 // row_ok / ncol mask the tile tails (masked elements quantise the value 0: no counts, no sums).
 // s_stat: this WARP's private [2][bn] int32 partial sums (bn = tile width); tcol = first column of the chunk inside the tile.
@@ -164,7 +211,7 @@ __device__ __forceinline__ int warp_colsum16(const int (&v)[16], int lane) {
 __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const float (&f)[16], uint32_t row, uint32_t pix, bool row_ok,
                                           uint32_t col, uint32_t ncol, uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
   const uint64_t inner = (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
-  int ki[16], kq[16];
+  int ki[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float4 u;
@@ -176,32 +223,27 @@ __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, cons
       const int j = 4 * g + t;
       const float x = (row_ok && (uint32_t)j < ncol) ? f[j] : 0.0f;
       const int kk = b.q.minmax ? squant_mm_i(x, un[t], st.qc, st.mx, st.mn) : squant_i(x, un[t], st.qc, st.n1, st.n2);
-      const int k = (row_ok && (uint32_t)j < ncol) ? kk : 0;
-      ki[j] = k;
-      kq[j] = k * k;
+      ki[j] = (row_ok && (uint32_t)j < ncol) ? kk : 0;
     }
   }
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (uint32_t)(ki[4 * i] & 0xff) | ((uint32_t)(ki[4 * i + 1] & 0xff) << 8) | ((uint32_t)(ki[4 * i + 2] & 0xff) << 16) |
+           ((uint32_t)(ki[4 * i + 3] & 0xff) << 24);
   if (row_ok) {
     int8_t* o = b.k + (size_t)row * N + col;
     if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
-      uint4 w;
-      w.x = (uint32_t)(ki[0] & 0xff) | ((uint32_t)(ki[1] & 0xff) << 8) | ((uint32_t)(ki[2] & 0xff) << 16) | ((uint32_t)(ki[3] & 0xff) << 24);
-      w.y = (uint32_t)(ki[4] & 0xff) | ((uint32_t)(ki[5] & 0xff) << 8) | ((uint32_t)(ki[6] & 0xff) << 16) | ((uint32_t)(ki[7] & 0xff) << 24);
-      w.z = (uint32_t)(ki[8] & 0xff) | ((uint32_t)(ki[9] & 0xff) << 8) | ((uint32_t)(ki[10] & 0xff) << 16) | ((uint32_t)(ki[11] & 0xff) << 24);
-      w.w = (uint32_t)(ki[12] & 0xff) | ((uint32_t)(ki[13] & 0xff) << 8) | ((uint32_t)(ki[14] & 0xff) << 16) | ((uint32_t)(ki[15] & 0xff) << 24);
-      *reinterpret_cast<uint4*>(o) = w;
+      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if ((uint32_t)j < ncol) o[j] = (int8_t)ki[j];
     }
   }
-  const int t0 = warp_colsum16(ki, lane), t1 = warp_colsum16(kq, lane);
-  if ((lane & 1) == 0) {
-    const int c = (lane >> 1) & 15;
-    s_stat[tcol + c] += t0;
-    s_stat[bn + tcol + c] += t1;
-  }
+  int chan, kind;
+  const int tot = warp_colstats_packed(w, lane, chan, kind);   // masked elements are 0: they add nothing
+  s_stat[(kind ? bn : 0u) + tcol + (uint32_t)chan] += tot;
 }
 
 // Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.
