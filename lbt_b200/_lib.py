@@ -90,6 +90,7 @@ _INTERNAL = {
     'lbt_conv_ldg_debug_error': (c_int, []),
     'lbt_conv_set_path': (c_int, [c_int]),
     'lbt_conv_set_halo': (c_int, [c_int]),
+    'lbt_conv_halo_launches': (ctypes.c_longlong, []),
     'lbt_gemm_set_pair': (c_int, [c_int]),
     'lbt_set_pdl': (c_int, [c_int]),
     'lbt_set_carveout': (c_int, [c_int]),

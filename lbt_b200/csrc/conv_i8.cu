@@ -252,13 +252,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (fused) {
           if (col0 + c < p.N) {   // warp-uniform
             const uint32_t ncol = min(16u, p.N - (col0 + c));
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              f[j] = __int2float_rn((int)v[j]) * scale;
-              if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
-            }
-            bnq_chunk(p.bnq, bst, f, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
+            bnq_chunk(p.bnq, bst, v, scale, p.bias ? p.bias + col0 + c : nullptr, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
+                      (uint32_t)c, lane);
           }
         } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));

@@ -83,6 +83,7 @@ struct LdgParams {
   uint32_t halo_par_plane;       // bytes of one parity plane: halo rows * halo_hw2 * 16
   uint32_t halo_mmas;            // MMA instructions per tile (stride 1: KCp / 2)
   FastDiv d_halo_w;
+  int epi16;                     // host: launch the 16-epilogue-warp instantiation (one CTA per SM)
 };
 
 __device__ __forceinline__ void dbg_stamp(const LdgParams& p, int slot) {
@@ -117,13 +118,18 @@ __device__ __forceinline__ uint64_t make_desc_k16(uint32_t smem_addr, uint32_t l
 // (16 + kh - 1) x (8 + kw - 1) input patch under an 8 x 16 output patch ONCE ([C/16 planes][halo pixels][16 B]), and the MMA
 // descriptors walk it: the 8 rows of a core matrix are 8 neighbouring pixels of an output row (16-byte pitch), consecutive
 // 8-row groups are halo rows (stride halo_w * 16 B), and a filter tap is just a different start address.
-template <int BN, int CPP, bool HALO, bool GQ>   // CPP = C / 16: 16-byte chunks per pixel; GQ: the fused BN-backward epilogue
-__global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p) {
+// EPI epilogue warps: 8 with two CTAs per SM, or 16 in ONE CTA per SM when the resident filter bank is too big for two CTAs
+// (the 7x7 ImageNet stem: 8 epilogue warps alone on an SM cannot keep up with the fused epilogue).
+template <int BN, int CPP, bool HALO, bool GQ, int EPI = 8>   // CPP = C / 16: 16-byte chunks per pixel; GQ: the fused BN-backward epilogue
+__global__ void __launch_bounds__(32 * (kLoaderWarps + 1 + EPI), EPI == 8 ? 2 : 1) conv_ldg_kernel(const LdgParams p) {
+  constexpr int kEpiWarps = EPI;
+  constexpr int kThreads = 32 * (kLoaderWarps + 1 + EPI);
+  constexpr int kSub = EPI / 4;   // epilogue warps per TMEM lane quadrant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  constexpr int kAccStages = BN <= 64 ? 4 : 2;   // two CTAs per SM must fit the 512 TMEM columns
+  constexpr int kAccStages = (BN <= 64 || EPI == 16) ? 4 : 2;   // two CTAs per SM must fit the 512 TMEM columns
   __shared__ __align__(8) uint64_t tmem_full_bar[kMaxAccStages];
   __shared__ __align__(8) uint64_t tmem_empty_bar[kMaxAccStages];
   __shared__ __align__(8) uint64_t b_bar;   // the resident filter bank has landed
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
     }
     // TMEM lane quadrant = warp % 4
     const uint32_t quad = warp & 3;
-    const uint32_t half = (uint32_t)(warp - (kLoaderWarps + 1)) >> 2;  // which of the quadrant's two warps
+    const uint32_t half = (uint32_t)(warp - (kLoaderWarps + 1)) >> 2;  // which of the quadrant's kSub warps
     int e = p.exp_const;
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
@@ -443,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
         pix = (fused || fusedg) ? row - fast_div(row, p.OHW, p.ohw_mul, p.ohw_shr) * p.OHW : 0u;   // row % (OH*OW)
         rvalid = row < p.M;
       }
-      constexpr int G = BN < 32 ? BN : 32;  // columns fetched from tensor memory per wait
+      constexpr int G = BN >= 64 ? 16 : (BN < 32 ? BN : 32);  // columns fetched from tensor memory per wait (wide tiles: 16, register budget)
       constexpr bool kSplit = BN > G;       // wide tiles: both warps of a quadrant alternate the G-column groups
       // fused BN-backward epilogue: the saved mantissas of this warp's FIRST column group are fetched before the wait
       uint32_t pw2[GQ ? G / 16 : 1][4], pw1[GQ ? G / 16 : 1][4];
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       }
       if (fused) {   // this warp's noise lines of the tile: into L1 while the accumulator is still being computed
 #pragma unroll 1
-        for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G)
+        for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? kSub * G : G)
 #pragma unroll
           for (int q = 0; q < G / 16; ++q) bnq_prefetch(p.bnq, pix, p.N, (uint32_t)(c0 + 16 * q), rvalid && (uint32_t)(c0 + 16 * q) < p.N);
       }
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
       ++bst.tiles;
       bool first_group = true;
 #pragma unroll 1
-      for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? 2 * G : G) {
+      for (int c0 = kSplit ? G * (int)half : 0; c0 < BN; c0 += kSplit ? kSub * G : G) {
         const bool fg = first_group;   // this group's mantissas were fetched before the wait
         first_group = false;
         uint32_t vv[G / 16][16];
@@ -490,6 +496,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
           const int c = c0 + 16 * q;
           if ((uint32_t)c >= p.N) continue;  // warp-uniform
           const uint32_t ncol = min(16u, p.N - (uint32_t)c);
+          if (fused) {
+            bnq_chunk(p.bnq, bst, vv[q], scale, p.bias ? p.bias + c : nullptr, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN,
+                      (uint32_t)c, lane);
+            continue;
+          }
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __int2float_rn((int)vv[q][j]) * scale;
@@ -498,9 +509,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
             for (int j = 0; j < 16; ++j)
               if (j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + c + j));
           }
-          if (fused) {
-            bnq_chunk(p.bnq, bst, f, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
-          } else if (GQ) {
+          if (GQ) {
             if constexpr (GQ) {
               if (!fg) gq_load_k(p.gq, row, rvalid, (uint32_t)c, ncol, p.N, pw2[q], pw1[q]);
               gq_chunk(p.gq, gst, f, pw2[q], pw1[q], row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN, (uint32_t)c, lane);
@@ -565,20 +574,29 @@ __global__ void __launch_bounds__(kThreads, 2) conv_ldg_kernel(const LdgParams p
   if (threadIdx.x == 32 * kLoaderWarps) dbg_stamp(p, 18);
 }
 
-template <int BN, int CPP, bool HALO, bool GQ>
-int launch_ldg2(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+template <int BN, int CPP, bool HALO, bool GQ, int EPI>
+int launch_ldg3(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
   static size_t attr_smem[16] = {};
   const int dev = device_info().device;
   if (attr_smem[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP, HALO, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_ldg_kernel<BN, CPP, HALO, GQ, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_ldg_kernel)");
       return LBT_ECUDA;
     }
     attr_smem[dev] = smem;
   }
-  launch_pdl(conv_ldg_kernel<BN, CPP, HALO, GQ>, grid, kThreads, smem, st, p);
+  launch_pdl(conv_ldg_kernel<BN, CPP, HALO, GQ, EPI>, grid, 32 * (kLoaderWarps + 1 + EPI), smem, st, p);
   return check_launch("lbt_conv_i8 (cp.async gather)");
+}
+
+// p.epi16: one CTA per SM (big filter bank) with a halo loader and a wide tile -> the 16-epilogue-warp instantiation
+template <int BN, int CPP, bool HALO, bool GQ>
+int launch_ldg2(const LdgParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  if constexpr (HALO && !GQ && BN >= 64) {
+    if (p.epi16) return launch_ldg3<BN, CPP, HALO, GQ, 16>(p, grid, smem, st);
+  }
+  return launch_ldg3<BN, CPP, HALO, GQ, 8>(p, grid, smem, st);
 }
 
 template <int BN, bool HALO, bool GQ>
@@ -1024,8 +1042,10 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
   if (nst > (uint32_t)kMaxStages) nst = kMaxStages;
   if (nst < 2) return LBT_EUNSUPPORTED;
   p.nstages = nst;
-  const size_t smem = b_bytes + (size_t)nst * p.stage_bytes + 256;
+  size_t smem = b_bytes + (size_t)nst * p.stage_bytes + 256;
   const unsigned ctas_per_sm = two ? 2u : 1u;
+  p.epi16 = (!two && halo && bn >= 64 && !link) ? 1 : 0;
+  if (p.epi16 && smem < 120 * 1024) smem = 120 * 1024;   // that instantiation owns up to all 512 TMEM columns: never two per SM
   const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm;
   const unsigned grid = (unsigned)(p.m_tiles < cap ? p.m_tiles : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1095,7 +1115,7 @@ extern "C" int lbt_conv_set_halo(int mask) {
   g_use_halo.store(mask & 1, std::memory_order_relaxed);
   g_c64_halo.store((mask >> 1) & 1, std::memory_order_relaxed);
   g_halo_any_fill.store((mask >> 2) & 1, std::memory_order_relaxed);   // bit 2: ignore the patch fill-ratio rule (tests)
-  conv_halo_enable(!((mask >> 3) & 1));                                  // bit 3: 64- / 128-channel layers back on the im2col TMA kernel
+  conv_halo_enable((((mask >> 3) & 1) ? 0 : 1) | (((mask >> 2) & 1) << 1));                                  // bit 3: 64- / 128-channel layers back on the im2col TMA kernel
   return LBT_OK;
 }
 

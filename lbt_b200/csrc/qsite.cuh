@@ -204,46 +204,93 @@ __device__ __forceinline__ void bnq_prefetch(const BnqParams& b, uint32_t pix, u
   if (b.q.noise && ok) asm volatile("prefetch.global.L1 [%0];" ::"l"(b.q.noise + (uint64_t)pix * N + col));
 }
 
-// One 16-channel chunk of one row.  f: the fp32 values the unfused path would have written (acc * 2^e).
+// One 16-channel chunk of one row, straight from the s32 accumulators `v`: x = RN(acc) * scale (+ bias) is the fp32 value the
+// unfused path would have written (scale = 2^e), k = Q(x) the mantissa that is stored, sum k / sum k^2 the batch statistics.
 // row_ok / ncol mask the tile tails (masked elements quantise the value 0: no counts, no sums).
 // s_stat: this WARP's private [2][bn] int32 partial sums (bn = tile width); tcol = first column of the chunk inside the tile.
 // pix = row % rows_per_image (the pixel inside its image; computed once per tile by the caller).
-__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const float (&f)[16], uint32_t row, uint32_t pix, bool row_ok,
-                                          uint32_t col, uint32_t ncol, uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+// ~13 instructions per element (ncu source view of the first version: ~24, a third of them tail masks and byte packing):
+//   * FULL (warp-uniform: every row of the warp valid, 16 columns): no masks at all; else ONE select per element — a masked
+//     element becomes the value 0, which quantises to mantissa 0 (u < 1), leaves min / max and the counts alone and adds nothing;
+//   * without a bias the two power-of-two scalings fold into one multiply (exact while the exponents stay far from the
+//     subnormal range — checked on the host side of the branch);
+//   * the mantissa byte is the low byte of the magic-biased floor (squant_i), packed with three PRMT per four elements;
+//   * statistics from the packed bytes (warp_colstats_packed).
+__device__ __forceinline__ uint32_t pack4_low_bytes(float t0, float t1, float t2, float t3) {
+  const uint32_t p01 = __byte_perm(__float_as_uint(t0), __float_as_uint(t1), 0x0040);
+  const uint32_t p23 = __byte_perm(__float_as_uint(t2), __float_as_uint(t3), 0x0040);
+  return __byte_perm(p01, p23, 0x5410);
+}
+
+template <bool FULL, bool MM>
+__device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
+                                               uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
+                                               int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
   const uint64_t inner = (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
-  int ki[16];
+  const QC& c = st.qc;
+  // one multiply when no bias sits between the two scalings and neither product can leave the normal range
+  const bool fold = bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(c.m)) < 60.0f;
+  const float sm = scale * c.m;
+  float tm[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float4 u;
-    if (b.q.noise) u = row_ok && 4u * g < ncol ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b.q.noise) u = (FULL || (row_ok && 4u * g < ncol)) ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
     else u = philox_noise4((inner >> 2) + g, b.q.seed, st.off);
     const float un[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int j = 4 * g + t;
-      const float x = (row_ok && (uint32_t)j < ncol) ? f[j] : 0.0f;
-      const int kk = b.q.minmax ? squant_mm_i(x, un[t], st.qc, st.mx, st.mn) : squant_i(x, un[t], st.qc, st.n1, st.n2);
-      ki[j] = (row_ok && (uint32_t)j < ncol) ? kk : 0;
+      const float a = __int2float_rn((int)v[j]);
+      float y;
+      if (fold) {
+        y = __fmul_rn(a, sm);
+      } else {
+        float x = __fmul_rn(a, scale);
+        if (bias && (FULL || (uint32_t)j < ncol)) x = __fadd_rn(x, __ldg(bias + j));
+        y = __fmul_rn(x, c.m);
+      }
+      if (!FULL) y = (row_ok && (uint32_t)j < ncol) ? y : 0.0f;
+      if (MM) {
+        st.mx = fmaxf(st.mx, y);
+        st.mn = fminf(st.mn, y);
+      } else {
+        st.n1 += (uint32_t)(y >= c.L) + (uint32_t)(y < -c.L);
+        st.n2 += (uint32_t)(y >= c.half) + (uint32_t)(y < -c.half);
+      }
+      tm[j] = __fadd_rd(fminf(fmaxf(__fadd_rn(y, un[t]), -c.L), c.hi), kFloorMagicF);   // bits = 0x4B400000 + k
     }
   }
   uint32_t w[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    w[i] = (uint32_t)(ki[4 * i] & 0xff) | ((uint32_t)(ki[4 * i + 1] & 0xff) << 8) | ((uint32_t)(ki[4 * i + 2] & 0xff) << 16) |
-           ((uint32_t)(ki[4 * i + 3] & 0xff) << 24);
-  if (row_ok) {
+  for (int i = 0; i < 4; ++i) w[i] = pack4_low_bytes(tm[4 * i], tm[4 * i + 1], tm[4 * i + 2], tm[4 * i + 3]);
+  if (FULL || row_ok) {
     int8_t* o = b.k + (size_t)row * N + col;
-    if (ncol == 16 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
+    if ((FULL || ncol == 16) && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
       *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if ((uint32_t)j < ncol) o[j] = (int8_t)ki[j];
+        if ((uint32_t)j < ncol) o[j] = (int8_t)(w[j >> 2] >> (8 * (j & 3)));
     }
   }
   int chan, kind;
   const int tot = warp_colstats_packed(w, lane, chan, kind);   // masked elements are 0: they add nothing
   s_stat[(kind ? bn : 0u) + tcol + (uint32_t)chan] += tot;
+}
+
+// `bias`: this chunk's 16 bias values (NULL: none).
+__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
+                                          uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
+                                          uint32_t bn, uint32_t tcol, int lane) {
+  const bool full = ncol == 16 && __all_sync(0xffffffffu, row_ok);
+  if (b.q.minmax) {
+    if (full) bnq_chunk_impl<true, true>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, true>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  } else {
+    if (full) bnq_chunk_impl<true, false>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, false>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  }
 }
 
 // Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.

@@ -313,7 +313,7 @@ def test_conv_halo_loader_equals_row_gather(N, H, W, Cin, Cout, k, pad):
     res = {}
     try:
         for halo in (1, 0):
-            _lib.lib().lbt_conv_set_halo(3 if halo else 0)
+            _lib.lib().lbt_conv_set_halo(11 if halo else 8)     # bit 3: not the TMA halo kernel (its own test is below)
             y = torch.full((N * OH * OW, Cout), float('nan'), device='cuda')
             D._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, 1, 1, pad, pad, OH, OW, ib, ib, -12, bias, y, addend=addend)
             k_out = torch.zeros(N * OH * OW, Cout, dtype=torch.int8, device='cuda')
@@ -326,8 +326,10 @@ def test_conv_halo_loader_equals_row_gather(N, H, W, Cin, Cout, k, pad):
     finally:
         _lib.lib().lbt_conv_set_halo(1)
     assert _lib.lib().lbt_conv_ldg_debug_error() == 0
-    for a, b in zip(res[1], res[0]):
+    for a, b in zip(res[1][:3], res[0][:3]):
         assert torch.equal(a, b)
+    ca, cb = res[1][3], res[0][3]     # min/max statistics count THREADS that saw an overflow: only zero / non-zero is defined
+    assert torch.equal(ca[:2] > 0, cb[:2] > 0) and torch.equal(ca[2:], cb[2:])
     # and against the exact convolution (fp64): RN_fp32(exact * 2^e) + bias + addend
     xe = x.double().permute(0, 3, 1, 2)
     we = w.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2).cuda()
@@ -373,12 +375,69 @@ def test_conv_halo_stride2_equals_row_gather(N, H, W, Cout, k):
     finally:
         _lib.lib().lbt_conv_set_halo(1)
     assert _lib.lib().lbt_conv_ldg_debug_error() == 0
-    for a, b in zip(res[1], res[0]):
+    for a, b in zip(res[1][:3], res[0][:3]):
         assert torch.equal(a, b)
+    ca, cb = res[1][3], res[0][3]     # min/max statistics count THREADS that saw an overflow: only zero / non-zero is defined
+    assert torch.equal(ca[:2] > 0, cb[:2] > 0) and torch.equal(ca[2:], cb[2:])
     xe = x.double().permute(0, 3, 1, 2)
     pb, pr = max((OH - 1) * 2 + k - H, 0) - pt, max((OW - 1) * 2 + k - W, 0) - pl
     xe = F.pad(xe, (pl, pr, pt, pb))
     we = w.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2).cuda()
     ref = F.conv2d(xe, we, stride=2).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
     want = (ref * 2.0 ** (-14 + 2)).float() + bias
+    assert torch.equal(res[1][0], want)
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,pad', [(2, 56, 56, 64, 64, 3, 1), (3, 28, 28, 128, 128, 3, 1), (2, 32, 48, 64, 128, 3, 1),
+                                                  (1, 16, 8, 128, 64, 3, 1), (2, 19, 13, 64, 48, 3, 1), (1, 40, 24, 64, 48, 5, 2),
+                                                  (2, 17, 31, 64, 64, 3, 0), (1, 33, 9, 128, 128, 2, 0), (4, 14, 14, 128, 128, 3, 1)])
+def test_conv_tma_halo_equals_im2col(N, H, W, Cin, Cout, k, pad):
+    """conv_halo.cu (one tiled TMA load of the input patch per 8 x 16 output patch, MMA descriptors that start at unaligned
+    pixels of the swizzled patch, resident filter bank) against the im2col-mode TMA kernel and the exact convolution: fp32
+    epilogue with bias + addend, and the fused re-quantising epilogue (mantissas, exact sums, counters).  Ragged images run
+    with the fill-ratio rule off (partial patches, out-of-image rows masked)."""
+    from lbt_b200 import _lib, quantizer as Q
+    rng = np.random.default_rng(N * H + Cin + k + W)
+    OH, OW = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    x = torch.from_numpy(rng.integers(0, 256, (N, H, W, Cin), dtype=np.uint8)).cuda()
+    Kf = k * k * Cin
+    w = torch.from_numpy(rng.integers(-128, 128, (Cout, Kf), dtype=np.int8))
+    wt = torch.zeros(Cout, D._pitch16(Kf), dtype=torch.int8, device='cuda')[:, :Kf]
+    wt.copy_(w)
+    ib = torch.tensor(1, dtype=torch.int32, device='cuda')
+    bias = torch.randn(Cout, device='cuda')
+    addend = torch.randn(N * OH * OW, Cout, device='cuda')
+    rt = D.Runtime(seed=5)
+    site = D.QuantSite(rt, 'q', 8, 2).cuda()
+    rt.finalize('cuda')
+    res = {}
+    launches = {}
+    try:
+        for halo in (1, 0):
+            _lib.lib().lbt_conv_set_halo(5 if halo else 8)
+            before = _lib.lib().lbt_conv_halo_launches()
+            y = torch.full((N * OH * OW, Cout), float('nan'), device='cuda')
+            D._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, 1, 1, pad, pad, OH, OW, ib, ib, -12, bias, y, addend=addend)
+            k_out = torch.zeros(N * OH * OW, Cout, dtype=torch.int8, device='cuda')
+            sums = torch.zeros(2 * Cout, dtype=torch.int64, device='cuda')
+            site.counters.zero_()
+            qs = site.abi(OH * OW * Cout, 'cuda')
+            D._conv_implicit(x, Q.MANT_U8, wt, Cout, k, k, 1, 1, pad, pad, OH, OW, ib, ib, -12, None, None, bnq=(qs, k_out, sums))
+            torch.cuda.synchronize()
+            res[halo] = (y, k_out, sums, site.counters.clone())
+            launches[halo] = _lib.lib().lbt_conv_halo_launches() - before
+    finally:
+        _lib.lib().lbt_conv_set_halo(1)
+    assert launches == {1: 2, 0: 0}, launches      # the two routes really are two kernels
+    assert _lib.lib().lbt_conv_debug_error() == 0
+    for a, b in zip(res[1][:3], res[0][:3]):
+        assert torch.equal(a, b)
+    # min/max statistics: the overflow counters hold "threads that saw an overflow" (the controller only tests > 0), so they
+    # depend on the kernel's thread count; the element count and the zero / non-zero decision must agree
+    ca, cb = res[1][3], res[0][3]
+    assert torch.equal(ca[:2] > 0, cb[:2] > 0) and torch.equal(ca[2:], cb[2:])
+    xe = x.double().permute(0, 3, 1, 2)
+    we = w.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2).cuda()
+    ref = F.conv2d(xe, we, padding=pad).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
+    want = ((ref * 2.0 ** (-12 + 2)).float() + bias) + addend
     assert torch.equal(res[1][0], want)
