@@ -389,6 +389,28 @@ int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int
                            uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
                            void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, void* stream);
 /*
+ * bwd 1 behind a max-pool (the ImageNet stems: conv -> BN -> ReLU -> 3x3/2 max-pool, models.py layer lists with MaxPool_q,
+ * dfxp:993-1006): `g_pooled` [n_outer, OH, OW, C] is the gradient w.r.t. the POOLED tensor and `pool->idx` the winning tap
+ * lbt_maxpool_fwd recorded for every pooled element; the pool's backward (each pixel collects the gradient of every window
+ * it won, windows visited in (oh, ow) order as lbt_maxpool_bwd does) runs in this kernel's load stage, so the dense fp32
+ * gradient of the un-pooled tensor (4 B written + 4 B read per element) never exists.  Bit-identical to
+ * lbt_maxpool_bwd followed by lbt_bn_bwd_quant_stats.  Windows with k <= 2 * s, C % 4 == 0, relu in {0, 1}.
+ * n_inner = pool->H * pool->W * C.
+ */
+typedef struct lbt_pool_geom {
+  const uint8_t* idx;                 /* [n_outer, OH, OW, C] winning tap (r * k + s) */
+  int32_t H, W;                       /* un-pooled grid */
+  int32_t k, s, pad_top, pad_left;    /* window, stride, TF 'SAME' padding before */
+  int32_t OH, OW;                     /* pooled grid */
+} lbt_pool_geom;
+int lbt_bn_bwd_quant_stats_pooled(const float* g_pooled, const lbt_pool_geom* pool, int relu, const int8_t* k2,
+                                  const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                                  const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                                  const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                                  const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                                  uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, void* kg1,
+                                  int64_t* sums, int stats_minmax, int kg1_kind, void* stream);
+/*
  * bwd 2: dx = (gq1 - mean(gq1) - xhat * mean(gq1 * xhat)) / sqrt(var + eps), the batch-norm VJP that
  * tf.gradients(y, X, gradq) yields for dfxp:616 (dfxp:623), from kg1, k1 and the two sum buffers.
  * q_grad != NULL: dx is quantised on the spot with the PRODUCING convolution's gradient quantiser (`gradq`,

@@ -67,6 +67,10 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,
                                        c_void_p, c_void_p, c_u64, c_void_p, c_u64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_int, c_int, c_void_p]),
+    'lbt_bn_bwd_quant_stats_pooled': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
+                                              c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_u64, c_void_p, c_int,
+                                              c_void_p, c_void_p, c_u64, c_void_p, c_u64, c_void_p, c_void_p,
+                                              c_void_p, c_int, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'lbt_dp_step': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
@@ -119,6 +123,12 @@ class QSiteStruct(ctypes.Structure):
     """lbt_qsite (include/lbt.h): one quantiser call site as the fused kernels see it."""
     _fields_ = [('bits', ctypes.c_int32), ('stats_minmax', ctypes.c_int32), ('ib', c_void_p), ('noise', c_void_p),
                 ('seed', c_u64), ('offset', c_u64), ('dev_step', c_void_p), ('counters', c_void_p)]
+
+
+class PoolGeom(ctypes.Structure):
+    """lbt_pool_geom (include/lbt.h): a max-pool whose backward runs inside lbt_bn_bwd_quant_stats_pooled."""
+    _fields_ = [('idx', c_void_p), ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('k', ctypes.c_int32), ('s', ctypes.c_int32),
+                ('pad_top', ctypes.c_int32), ('pad_left', ctypes.c_int32), ('OH', ctypes.c_int32), ('OW', ctypes.c_int32)]
 
 
 class BnBwdLink(ctypes.Structure):

@@ -497,13 +497,18 @@ struct Bwd1Params {
   float* d_add;         // optional: gradient w.r.t. the fused shortcut input (= masked g)
   void* kg1;            // s8, or s16 in the WIDE instantiation
   long long* sums;      // [4*C]: sum kg2, sum kg2*k2, sum kg1, sum kg1*k1
+  // POOL instantiation: `g` is the gradient of a max-pool of the module output, [n_outer, pOH, pOW, C]; the pool's backward
+  // (a gather over the <= 2 x 2 windows that cover a pixel, lbt_maxpool_bwd) runs in this kernel's load stage
+  const uint8_t* pidx;  // winning tap of every pooled element
+  int pW, pk, ps, ppt, ppl, pOH, pOW;
+  FastDiv d_c4, d_pW, d_ps;
 };
 
 // WIDE: a gradient quantiser wider than 8 bits — kg1 is stored as s16 and the per-thread partial sums are 64-bit
 // (a 16-bit mantissa times an 8-bit one, summed down 4096 rows, does not fit 32).  MM: min/max statistics for both sites.
 // RELU: 0 none, 1 mask recomputed from k2, 2 mask from `out`.  ~31 full-rate instructions per element, no conversions;
 // folded constants (exact, powers of two):  RN(xq2 * g) = RN(k2 * (g / m2));  dx2 * mg1 = RN(kg2 * (g * mg1 / mg2)).
-template <bool WIDE, bool MM, int RELU>
+template <bool WIDE, bool MM, int RELU, bool POOL = false>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
@@ -537,6 +542,30 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
         b[j] = __ldg(p.bq + c0 + j);
       }
       const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      // POOL: the <= 2 x 2 pooling windows over this thread's pixel — the same for every batch row (tf.nn.max_pool's
+      // gradient, dfxp:993-1006: a pixel receives the gradient of each window it won; lbt_maxpool_bwd's gather and order)
+      uint32_t poff[4] = {0u, 0u, 0u, 0u};
+      uint32_t ptap[4] = {0u, 0u, 0u, 0u};
+      bool pok[4] = {false, false, false, false};
+      size_t pimg = 0;
+      if (POOL) {
+        const uint32_t pix = fastdiv(v, p.d_c4), cg = v - pix * p.d_c4.d;
+        const uint32_t ih = fastdiv(pix, p.d_pW), iw = pix - ih * (uint32_t)p.pW;
+        const int th = (int)ih + p.ppt, tw = (int)iw + p.ppl;
+        const int oh_lo = th - p.pk + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(th - p.pk + p.ps), p.d_ps);
+        const int ow_lo = tw - p.pk + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(tw - p.pk + p.ps), p.d_ps);
+        const int oh_hi = min(p.pOH - 1, (int)fastdiv((uint32_t)th, p.d_ps)), ow_hi = min(p.pOW - 1, (int)fastdiv((uint32_t)tw, p.d_ps));
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b2 = 0; b2 < 2; ++b2) {
+            const int oh = oh_lo + a, ow = ow_lo + b2;
+            pok[2 * a + b2] = oh <= oh_hi && ow <= ow_hi;
+            ptap[2 * a + b2] = (uint32_t)((th - oh * p.ps) * p.pk + (tw - ow * p.ps)) & 0xffu;
+            poff[2 * a + b2] = pok[2 * a + b2] ? ((uint32_t)(oh * p.pOW + ow) * (uint32_t)C + 4u * cg) : 0u;
+          }
+        pimg = (size_t)p.pOH * p.pOW * C;
+      }
       for (size_t r = r0; r < r1; r += kRows) {
         float4 gv[kRows], ov[kRows];
         uint32_t w2[kRows], w1[kRows];
@@ -544,7 +573,29 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
         for (int i = 0; i < kRows; ++i)
           if (r + i < r1) {
             const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
-            gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
+            if (POOL) {
+              const size_t base = (r + i) * pimg;
+              float4 gw[4];
+              uint32_t iw4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (pok[q]) {
+                  gw[q] = __ldg(reinterpret_cast<const float4*>(p.g + base + poff[q]));
+                  iw4[q] = __ldg(reinterpret_cast<const uint32_t*>(p.pidx + base + poff[q]));
+                }
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)       // (oh, ow) ascending: lbt_maxpool_bwd's order of additions
+                if (pok[q]) {
+                  if ((iw4[q] & 0xffu) == ptap[q]) a4.x += gw[q].x;
+                  if (((iw4[q] >> 8) & 0xffu) == ptap[q]) a4.y += gw[q].y;
+                  if (((iw4[q] >> 16) & 0xffu) == ptap[q]) a4.z += gw[q].z;
+                  if ((iw4[q] >> 24) == ptap[q]) a4.w += gw[q].w;
+                }
+              gv[i] = a4;
+            } else {
+              gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
+            }
             w2[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k2 + idx));
             w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
             if (RELU == 2) ov[i] = __ldcs(reinterpret_cast<const float4*>(p.out + idx));
@@ -553,7 +604,17 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
         for (int i = 0; i < kRows; ++i)
           if (r + kRows + i < r1) {
             const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
-            prefetch_l1(p.g + idx);
+            if (POOL) {
+              const size_t base = (r + kRows + i) * pimg;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (pok[q]) {
+                  prefetch_l1(p.g + base + poff[q]);
+                  prefetch_l1(p.pidx + base + poff[q]);
+                }
+            } else {
+              prefetch_l1(p.g + idx);
+            }
             prefetch_l1(p.k2 + idx);
             prefetch_l1(p.k1 + idx);
             if (RELU == 2) prefetch_l1(p.out + idx);
@@ -1151,14 +1212,23 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   return check_launch("lbt_bn_fwd_apply");
 }
 
-extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
-                                      size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
-                                      const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
-                                      const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
-                                      const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
-                                      uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
-                                      void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, void* stream) {
+static int bn_bwd1_run(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
+                       size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                       const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                       const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                       const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                       uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
+                       void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, const lbt_pool_geom* pool, void* stream) {
   if (!g || !k2 || !k1 || !ib2 || !gamma_q || !beta_q || !ib_g2 || !ib_g1 || !kg1 || !sums) return LBT_EINVAL;
+  if (pool) {
+    if (!pool->idx || pool->H <= 0 || pool->W <= 0 || pool->k <= 0 || pool->s <= 0 || pool->OH <= 0 || pool->OW <= 0 ||
+        pool->pad_top < 0 || pool->pad_left < 0)
+      return LBT_EINVAL;
+    // <= 2 x 2 windows per pixel, 4 channels per thread, no shortcut sum / saved-output mask in front of the pool
+    if (pool->k > 2 * pool->s || pool->k > 15 || (C & 3) || relu == 2 || d_add) return LBT_EUNSUPPORTED;
+    if (n_inner != (size_t)pool->H * pool->W * C) return LBT_EINVAL;
+    if ((size_t)pool->OH * pool->OW * C >= (1ull << 31) || (reinterpret_cast<uintptr_t>(pool->idx) & 3)) return LBT_EUNSUPPORTED;
+  }
   if (relu < 0 || relu > 2 || (relu == 2 && !out)) return LBT_EINVAL;
   if (kg1_kind != LBT_MANT_S8 && kg1_kind != LBT_MANT_S16) return LBT_EINVAL;
   const bool wide = kg1_kind == LBT_MANT_S16;
@@ -1177,8 +1247,11 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
     const bool mm = stats_minmax != 0;
 #define LBT_BWD1(W, M)                                                                                     \
   (relu == 0 ? bn_bwd1_kernel<W, M, 0> : (relu == 1 ? bn_bwd1_kernel<W, M, 1> : bn_bwd1_kernel<W, M, 2>))
-    kern = wide ? (mm ? LBT_BWD1(true, true) : LBT_BWD1(true, false)) : (mm ? LBT_BWD1(false, true) : LBT_BWD1(false, false));
+#define LBT_BWD1P(W, M) (relu == 0 ? bn_bwd1_kernel<W, M, 0, true> : bn_bwd1_kernel<W, M, 1, true>)
+    if (pool) kern = wide ? (mm ? LBT_BWD1P(true, true) : LBT_BWD1P(true, false)) : (mm ? LBT_BWD1P(false, true) : LBT_BWD1P(false, false));
+    else kern = wide ? (mm ? LBT_BWD1(true, true) : LBT_BWD1(true, false)) : (mm ? LBT_BWD1(false, true) : LBT_BWD1(false, false));
 #undef LBT_BWD1
+#undef LBT_BWD1P
   }
   int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(kern, (size_t)4 * C * 8));
   if (rc) return rc;
@@ -1196,10 +1269,48 @@ extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu
   p.d_add = d_add;
   p.kg1 = kg1;
   p.sums = reinterpret_cast<long long*>(sums);
+  if (pool) {
+    p.pidx = pool->idx;
+    p.pW = pool->W;
+    p.pk = pool->k;
+    p.ps = pool->s;
+    p.ppt = pool->pad_top;
+    p.ppl = pool->pad_left;
+    p.pOH = pool->OH;
+    p.pOW = pool->OW;
+    p.d_c4 = make_fastdiv((uint32_t)C / 4);
+    p.d_pW = make_fastdiv((uint32_t)pool->W);
+    p.d_ps = make_fastdiv((uint32_t)pool->s);
+  }
   const size_t smem = (size_t)4 * C * 8;
   if ((rc = set_smem(kern, smem))) return rc;
   launch_pdl(kern, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_bwd_quant_stats");
+}
+
+extern "C" int lbt_bn_bwd_quant_stats(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,
+                                      size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                                      const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                                      const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                                      const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                                      uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, float* d_add,
+                                      void* kg1, int64_t* sums, int stats_minmax, int kg1_kind, void* stream) {
+  return bn_bwd1_run(g, out, relu, k2, k1, n_outer, n_inner, C, bits2, ib2, gamma_q, beta_q, bits_g2, ib_g2, noise_g2, offset_g2,
+                     counters_g2, bits_g1, ib_g1, noise_g1, offset_g1, counters_g1, seed, dev_step, d_add, kg1, sums, stats_minmax,
+                     kg1_kind, nullptr, stream);
+}
+
+extern "C" int lbt_bn_bwd_quant_stats_pooled(const float* g_pooled, const lbt_pool_geom* pool, int relu, const int8_t* k2,
+                                             const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits2, const int32_t* ib2,
+                                             const float* gamma_q, const float* beta_q, int bits_g2, const int32_t* ib_g2,
+                                             const float* noise_g2, uint64_t offset_g2, uint64_t* counters_g2, int bits_g1,
+                                             const int32_t* ib_g1, const float* noise_g1, uint64_t offset_g1,
+                                             uint64_t* counters_g1, uint64_t seed, const uint64_t* dev_step, void* kg1,
+                                             int64_t* sums, int stats_minmax, int kg1_kind, void* stream) {
+  if (!pool) return LBT_EINVAL;
+  return bn_bwd1_run(g_pooled, nullptr, relu, k2, k1, n_outer, n_inner, C, bits2, ib2, gamma_q, beta_q, bits_g2, ib_g2, noise_g2,
+                     offset_g2, counters_g2, bits_g1, ib_g1, noise_g1, offset_g1, counters_g1, seed, dev_step, nullptr, kg1, sums,
+                     stats_minmax, kg1_kind, pool, stream);
 }
 
 extern "C" int lbt_bn_bwd_apply(const void* kg1, const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1,

@@ -1107,10 +1107,12 @@ def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_
     return k2, out, nm, relu_mode
 
 
-def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_site=None, want_dx=True, pre=None):
+def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_site=None, want_dx=True, pre=None, pool=None):
     """Both BN backward passes on memory-order tensors: (dx fp32 or None, gradient mantissas of `grad_site` or None,
     dgamma, dbeta, d_add).  ``pre = (kg1, bsums)``: pass 1 already ran in the epilogue of the consuming convolution's
-    input-gradient kernel (lbt_conv_i8_dgrad_bn); ``g_`` is then not read (may be None)."""
+    input-gradient kernel (lbt_conv_i8_dgrad_bn); ``g_`` is then not read (may be None).
+    ``pool = (idx, k, s, pad_top, pad_left, POH, POW)``: a max-pool sits behind the unit, ``g_`` is the gradient of the POOLED
+    tensor and the pool's backward runs inside pass 1 (lbt_bn_bwd_quant_stats_pooled)."""
     norm, resc = bn[0], bn[1]
     rt = norm.qX.runtime
     N, C = k1.shape[0], k1.shape[-1]
@@ -1134,7 +1136,7 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
     # small tensors: both passes in one launch (lbt_bn_bwd_fused); it declines shapes that are not one wave of CTAs
     fused = False
     # (its grid barrier needs every CTA co-resident: not while weight-gradient kernels share the SMs on the side stream)
-    if FUSE_BN_BWD and pre is None and not wide and gm_lo is None and not getattr(rt, '_side_pending', False):
+    if FUSE_BN_BWD and pre is None and pool is None and not wide and gm_lo is None and not getattr(rt, '_side_pending', False):
         a = _lib.BnBwdArgs(g=_lib.ptr(g_), out=_lib.ptr(out_), k2=_lib.ptr(k2), k1=_lib.ptr(k1), n_outer=N, n_inner=n_inner, C=C,
                            relu=relu_mode, bits2=resc.qX.bits, bits1=norm.qX.bits, ib2=_lib.ptr(resc.qX.range),
                            ib1=_lib.ptr(norm.qX.range), gamma_q=_lib.ptr(gq), beta_q=_lib.ptr(bq),
@@ -1147,6 +1149,19 @@ def _bn_backward(bn, g_, k1, k2, sums, gq, bq, out_, relu_mode, has_add, grad_si
         fused = _lib.try_call('lbt_bn_bwd_fused', ctypes.addressof(a), _lib.stream(), meta=dict(bytes=nbytes))
     if not fused and pre is not None:
         kg1 = pre[0]
+    elif not fused and pool is not None:
+        kg1 = torch.empty(k1.shape, dtype=torch.int16 if wide else torch.int8, device=dev)
+        nzg2, offg2 = _site_args(resc.qG, k1)
+        nzg1, offg1 = _site_args(norm.qG, k1)
+        pidx, pk, ps, ppt, ppl, POH, POW = pool
+        geo = _lib.PoolGeom(idx=_lib.ptr(pidx), H=k1.shape[1], W=k1.shape[2], k=pk, s=ps, pad_top=ppt, pad_left=ppl, OH=POH, OW=POW)
+        _lib.call('lbt_bn_bwd_quant_stats_pooled', _lib.ptr(g_), ctypes.addressof(geo), relu_mode, _lib.ptr(k2), _lib.ptr(k1), N,
+                  n_inner, C, resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(gq), _lib.ptr(bq), resc.qG.bits,
+                  _lib.ptr(resc.qG.range), _lib.ptr(nzg2), offg2, _lib.ptr(resc.qG.counters), norm.qG.bits,
+                  _lib.ptr(norm.qG.range), _lib.ptr(nzg1), offg1, _lib.ptr(norm.qG.counters), rt.seed,
+                  _lib.ptr(rt.dev_step), _lib.ptr(kg1), _lib.ptr(bsums),
+                  int(resc.qG.target == 0 and norm.qG.target == 0), kg1_kind, _lib.stream(),
+                  meta=dict(bytes=g_.numel() * 5 + k1.numel() * (3 + (1 if wide else 0))))
     elif not fused:
         kg1 = torch.empty(k1.shape, dtype=torch.int16 if wide else torch.int8, device=dev)
         nzg2, offg2 = _site_args(resc.qG, g_)
@@ -1238,7 +1253,7 @@ class _ConvBNFn(torch.autograd.Function):
     the results are bit-identical (tests/test_fused_gpu.py)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias, link_in, link_out):
+    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias, link_in, link_out, pool=None):
         geom = _conv_geom(conv, x, weight)
         N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         norm, resc = bn[0], bn[1]
@@ -1258,7 +1273,17 @@ class _ConvBNFn(torch.autograd.Function):
         ctx.link_in, ctx.link_out = link_in, link_out
         if link_out is not None and out is None:     # the next unit may run this BN's backward pass 1 in its dgrad epilogue
             link_out.offer(bn, k1, k2, gq, bq, relu_mode, add is not None)
-        ctx.save_for_backward(xm, wm, k1, k2, sums, gq, bq, out if relu_mode == 2 else None)
+        pidx = None
+        ctx.pool = None
+        if pool is not None:      # MaxPool_q behind the unit (ImageNet stem): its backward runs inside this unit's BN pass 1
+            pk, ps, ppt, ppl, POH, POW = pool
+            pooled = torch.empty(N, POH, POW, Cout, dtype=torch.float32, device=dev)
+            pidx = torch.empty(N, POH, POW, Cout, dtype=torch.uint8, device=dev)
+            _lib.call('lbt_maxpool_fwd', _lib.ptr(out), N, OH, OW, Cout, pk, ps, ppt, ppl, POH, POW, _lib.ptr(pooled), _lib.ptr(pidx),
+                      _lib.stream(), meta=dict(bytes=out.numel() * 4 + pooled.numel() * 5))
+            ctx.pool = (pk, ps, ppt, ppl, POH, POW)
+            out = pooled
+        ctx.save_for_backward(xm, wm, k1, k2, sums, gq, bq, out if relu_mode == 2 else None, pidx)
         if out is None:       # mantissa-only activation: the fp32 tensor is never materialised (shape carrier only)
             out = torch.empty(1, dtype=torch.float32, device=dev).expand(N, OH, OW, Cout)
         if nm is None:
@@ -1273,12 +1298,14 @@ class _ConvBNFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _g_nm, g_alias):
         conv = ctx.conv
-        xm, wm, k1, k2, sums, gq, bq, out = ctx.saved_tensors
+        xm, wm, k1, k2, sums, gq, bq, out, pidx = ctx.saved_tensors
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         lo = ctx.link_out
         pre = (lo.kg1, lo.bsums) if (lo is not None and lo.done) else None     # pass 1 ran in the consumer's dgrad epilogue
+        pool = ((pidx,) + ctx.pool) if ctx.pool is not None else None
         _, gm, dgamma, dbeta, d_add = _bn_backward(ctx.bn, _to_mem(g) if pre is None else None, k1, k2, sums, gq, bq, out,
-                                                   ctx.relu_mode, ctx.has_add, grad_site=conv.qG, want_dx=False, pre=pre)   # ... dfxp:300
+                                                   ctx.relu_mode, ctx.has_add, grad_site=conv.qG, want_dx=False, pre=pre,
+                                                   pool=pool)   # ... dfxp:300
         addend = _to_mem(g_alias) if (g_alias is not None and need_dx) else None
         li = ctx.link_in if (addend is None and FUSE_BWD_LINK) else None
         if isinstance(gm, tuple):        # 9..16-bit gradient: (hi, lo) byte planes
@@ -1286,9 +1313,13 @@ class _ConvBNFn(torch.autograd.Function):
         else:
             dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend, link=li)
         return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
-                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None)
+                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None, None)
 
 
+FUSE_POOL = os.environ.get('LBT_FUSE_POOL', '0') == '1'   # module switch: a MaxPool_q right behind a fused unit runs its backward inside the
+                      # unit's BN pass 1 (lbt_bn_bwd_quant_stats_pooled).  Bit-identical and 1.6 GB less DRAM traffic on ResNet-18's stem, but
+                      # measured slower on B200 (923 us vs 480 + 320 us for the two launches: 2.25 window gathers per element and 123
+                      # registers per thread leave the pass load-issue bound), so it is OFF by default
 FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lbt_bn_bwd_fused, grid barrier) where the
                       # tensor is one wave of CTAs.  Bit-identical; measured no faster on B200 (1.77 vs 1.75 ms ResNet-20
                       # step: the barrier + second fp64 prologue cost what the saved launch gains), so off by default
@@ -1301,7 +1332,8 @@ def _unit_fusable(conv, bn, x):
             x.is_cuda)
 
 
-def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True, alias=False, link_in=None, link_out=None):
+def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=True, alias=False, link_in=None, link_out=None,
+                 pool=None):
     """``bn(conv(x), add=add, relu=relu)`` as ONE fused unit when the shapes allow (else exactly that expression).
 
     next_conv: the Conv2d_q that consumes the result — its input quantiser then runs inside this unit's last kernel
@@ -1310,7 +1342,17 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     relu = relu or getattr(bn, 'relu', False)
     if not _unit_fusable(conv, bn, x):
         y = bn(conv(x), add=add, relu=relu) if isinstance(bn, BatchNorm2d_q) else bn(conv(x))
+        if pool is not None:
+            y = pool(y)
         return (y, x) if alias else y
+    pgeom = None
+    if pool is not None:      # ``pool``: a MaxPool_q that consumes the unit's output and nothing else does
+        if add is not None or alias or not pool_fusable(pool):
+            y = conv_bn_unit(conv, bn, x, add=add, relu=relu, alias=alias, link_in=link_in, link_out=link_out)
+            return (pool(y[0]), y[1]) if alias else pool(y)
+        Hc, Wc = _conv_geom(conv, x, conv.weight)[11:13]
+        pgeom = pool.geometry(Hc, Wc)
+        next_conv = None      # the consumer quantises the POOLED tensor
     next_site, next_kind = None, Q.MANT_NONE
     if next_conv is not None and isinstance(next_conv, Conv2d_q) and next_conv.fuse_bn:
         nb = next_conv.qX.bits
@@ -1324,7 +1366,8 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     # channel block inputs of ResNet-50 the epilogue-bound 1x1 dgrad GEMMs lose more than the coalesced add costs (+3 %)
     use_alias = bool(alias and x.requires_grad and not getattr(x, '_lbt_hollow', False) and conv.weight.shape[2] <= 128)
     out, nm, xa = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
-                                  want_fp32, use_alias, link_in if FUSE_BWD_LINK else None, link_out if FUSE_BWD_LINK else None)
+                                  want_fp32, use_alias, link_in if FUSE_BWD_LINK else None, link_out if FUSE_BWD_LINK else None,
+                                  pgeom)
     if next_site is not None:
         out._lbt_q = {id(next_site): (nm, next_kind)}
     if not want_fp32:
@@ -1344,6 +1387,10 @@ def run_layers(layers, x, next_conv=None):
         nxt = layers[i + 1] if i + 1 < len(layers) else None
         if isinstance(m, Conv2d_q) and isinstance(nxt, BatchNorm2d_q):
             after = layers[i + 2] if i + 2 < len(layers) else next_conv
+            if FUSE_POOL and isinstance(after, MaxPool_q) and i + 2 < len(layers):
+                x = conv_bn_unit(m, nxt, x, pool=after)       # conv -> BN -> ReLU -> max-pool (ImageNet stem)
+                i += 3
+                continue
             x = conv_bn_unit(m, nxt, x, next_conv=_first_conv(after))
             i += 2
         elif isinstance(m, ResidualBlock_q):
@@ -1479,18 +1526,28 @@ class MaxPool_q(nn.Module):
         super().__init__()
         self.k, self.s, self.padding = kernel_size, stride, padding
 
-    def forward(self, x):
-        H, W = x.shape[2], x.shape[3]
+    def geometry(self, H, W):
+        """(k, s, pad_top, pad_left, OH, OW) on an H x W grid."""
         if self.padding == 'SAME':
             OH, pt, pb = same_pad(H, self.k, self.s)
             OW, pl, pr = same_pad(W, self.k, self.s)
         else:
-            pt = pb = pl = pr = 0
+            pt = pl = 0
             OH, OW = (H - self.k) // self.s + 1, (W - self.k) // self.s + 1
+        return self.k, self.s, pt, pl, OH, OW
+
+    def forward(self, x):
+        H, W = x.shape[2], x.shape[3]
+        _, _, pt, pl, OH, OW = self.geometry(H, W)
         _require_cuda_f32(x, 'MaxPool_q')
         if x.dim() != 4 or self.k > 15:
             raise _lib.LbtError('MaxPool_q: needs a 4-d tensor and a window of at most 15x15')
         return _MaxPoolFn.apply(x, self.k, self.s, pt, pl, OH, OW)
+
+
+def pool_fusable(pool):
+    """A MaxPool_q whose backward lbt_bn_bwd_quant_stats_pooled can run: at most 2 x 2 windows over a pixel."""
+    return isinstance(pool, MaxPool_q) and pool.k <= 2 * pool.s and pool.k <= 15
 
 
 class _AvgPoolFn(torch.autograd.Function):

@@ -11,8 +11,9 @@ from lbt_b200 import dfxp as D, models as M  # noqa: E402
 from lbt_b200.trainer import Trainer  # noqa: E402
 
 
-def _run(name, fused, steps, batch, image, kw, bn_bwd=False, link=False):
+def _run(name, fused, steps, batch, image, kw, bn_bwd=False, link=False, pool=False):
     D.FUSE_UNITS = fused
+    D.FUSE_POOL = pool
     D.FUSE_BN_BWD = bn_bwd
     D.FUSE_BWD_LINK = link
     D._link_count = 0
@@ -32,8 +33,41 @@ def _run(name, fused, steps, batch, image, kw, bn_bwd=False, link=False):
                     bn=[b.clone() for n, b in model.named_buffers() if 'running' in n])
     finally:
         D.FUSE_UNITS = True
+        D.FUSE_POOL = False
         D.FUSE_BN_BWD = False
         D.FUSE_BWD_LINK = False
+
+
+@pytest.mark.parametrize('name,batch,image,kw', [('Resnet18', 4, 64, dict(image=64, num_classes=10)),
+                                                 ('Resnet18', 3, 60, dict(image=60, num_classes=10)),      # 30 x 30 -> 15 x 15: ragged windows
+                                                 ('Resnet18', 2, 72, dict(image=72, num_classes=10, grad_bits=16)),   # s16 kg1
+                                                 ('Resnet50', 2, 64, dict(image=64, num_classes=10))])
+def test_pool_backward_inside_bn_pass_equals_separate_kernels(name, batch, image, kw):
+    """lbt_bn_bwd_quant_stats_pooled (the stem's max-pool backward gathered in the load stage of the BN backward pass 1: no
+    dense fp32 gradient of the un-pooled tensor) vs lbt_maxpool_bwd + lbt_bn_bwd_quant_stats."""
+    from lbt_b200 import _lib
+    seen = []
+    orig = _lib.call
+
+    def spy(fn, *a, **k):
+        seen.append(fn)
+        return orig(fn, *a, **k)
+
+    _lib.call = spy
+    try:
+        a = _run(name, True, 3, batch, image, kw, pool=True)
+        fused_calls = list(seen)
+        del seen[:]
+        b = _run(name, True, 3, batch, image, kw, pool=False)
+    finally:
+        _lib.call = orig
+    assert fused_calls.count('lbt_bn_bwd_quant_stats_pooled') == 3 and 'lbt_maxpool_bwd' not in fused_calls
+    assert seen.count('lbt_maxpool_bwd') == 3 and 'lbt_bn_bwd_quant_stats_pooled' not in seen
+    assert a['losses'] == b['losses'], (a['losses'], b['losses'])
+    assert torch.equal(a['ranges'], b['ranges'])
+    assert torch.equal(a['counters'], b['counters'])
+    for k in ('g', 'w', 'a'):
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
 
 
 @pytest.mark.parametrize('name,batch,image,kw', [
