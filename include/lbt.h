@@ -331,7 +331,8 @@ typedef struct lbt_prep_job {
   uint64_t ld_a, ld_b;
   int32_t bits, layout;
   uint32_t kh, kw, Cin, Cout;
-  int32_t c3pad, rot180;
+  int32_t c3pad, rot180;   /* rot180: 0 filter order, 1 rotated by 180 degrees (stride-1 dgrad), 2 parity-class order (strided dgrad) */
+  int32_t sh, sw;          /* convolution strides (rot180 == 2) */
 } lbt_prep_job;
 int lbt_param_prep(const lbt_prep_job* jobs_dev, const uint32_t* block_job_dev, const uint32_t* block_chunk_dev,
                    size_t nblocks, uint32_t chunk_elems, uint64_t seed, const uint64_t* dev_step, void* stream);
@@ -579,6 +580,22 @@ typedef struct lbt_bn_bwd_link {
 int lbt_conv_i8_dgrad_bn(const void* g, int g_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                          int kh, int kw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_g, const int32_t* ib_w,
                          int exp_const, const lbt_bn_bwd_link* link, void* stream);
+
+/*
+ * Input gradient of a STRIDED convolution whose gathered tensor (the output gradient g[N,OH,OW,Cout]) is wide
+ * (tf.gradients(y, X, gradq), dfxp:305, for the 3x3/2 and 1x1/2 convolutions that open the ResNet stages): run as sh*sw
+ * stride-1 sub-convolutions, one per parity class (h mod sh, w mod sw) of input pixels, each on the sub-filter of the taps
+ * that reach that class and each writing its own sub-lattice of dX[N,H,W,Cin] (row pitch ldc) — no transposed im2col
+ * matrix, no multiplication by the zeros of a dilated gradient.  w2[Cin, kh*kw*Cout] (row pitch ldw) holds the filter
+ * with its taps in PARITY-CLASS ORDER (lbt_param_prep with rot180 = 2: taps grouped by (r mod sh, s mod sw), groups in
+ * row-major order, reversed (r / sh, s / sw) order inside a group).  Classes no tap reaches get `addend` (or zeros).
+ * dX = RN_fp32(exact * 2^(*ib_g + *ib_w + exp_const)) (+ addend), bit-identical to the im2col + GEMM formulation.
+ * Cout % 16 == 0 (and a multiple of 128 above 64), Cin % 4 == 0, strides <= 4.
+ */
+int lbt_conv_i8_dgrad_strided(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* w2, int w_kind, size_t ldw,
+                              int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
+                              const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
+                              const float* addend, void* stream);
 
 #ifdef __cplusplus
 }

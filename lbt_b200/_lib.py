@@ -73,6 +73,9 @@ SIGNATURES = {
                                               c_void_p, c_int, c_int, c_void_p]),
     'lbt_bn_bwd_apply': (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float,
                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'lbt_conv_i8_dgrad_strided': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_size_t, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                          c_void_p, c_void_p]),
     'lbt_dp_step': (c_int, [c_void_p, c_void_p, c_size_t, c_float, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p,
                             c_size_t, c_void_p, c_void_p]),
     'lbt_dp_export': (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -167,7 +170,7 @@ class PrepJob(ctypes.Structure):
                 ('offset', c_u64), ('out_f32', c_void_p), ('out_a', c_void_p), ('out_b', c_void_p), ('ld_a', c_u64),
                 ('ld_b', c_u64), ('bits', ctypes.c_int32), ('layout', ctypes.c_int32), ('kh', ctypes.c_uint32),
                 ('kw', ctypes.c_uint32), ('Cin', ctypes.c_uint32), ('Cout', ctypes.c_uint32), ('c3pad', ctypes.c_int32),
-                ('rot180', ctypes.c_int32)]
+                ('rot180', ctypes.c_int32), ('sh', ctypes.c_int32), ('sw', ctypes.c_int32)]
 
 
 def to_device_table(structs, device, keep=None):

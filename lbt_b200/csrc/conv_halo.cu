@@ -56,6 +56,8 @@ struct HaloParams {
   size_t ldc;
   uint32_t idesc;
   BnqParams bnq;
+  int remap;                     // fp32 rows go to out + img * rs_n + oy * rs_y + ox * rs_x (OutRemap) instead of row * ldc
+  long long rs_n, rs_y, rs_x;
 };
 
 __device__ __forceinline__ void tma_load_tiled_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h, int n) {
@@ -234,7 +236,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + c + j));
         }
         if (rvalid) {
-          float* o = p.out + (size_t)row * p.ldc + c;
+          float* o = p.remap ? p.out + ((long long)img * p.rs_n + (long long)oy * p.rs_y + (long long)ox * p.rs_x) + c
+                             : p.out + (size_t)row * p.ldc + c;
           if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
             const float* ad = p.addend + (o - p.out);
             if (ncol == 16 && ((reinterpret_cast<uintptr_t>(ad) & 15u) == 0)) {
@@ -335,7 +338,8 @@ bool conv_halo_applies(int N, int OH, int OW, int C, int Cout, int kh, int kw, i
 
 int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                   int kw, int pt, int pl, int OH, int OW, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
-                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream) {
+                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream,
+                  const OutRemap* remap) {
   const DeviceInfo& di = device_info();
   static EncodeTiledFn enc_tiled = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
   if (!enc_tiled) return LBT_ECUDA;
@@ -376,6 +380,13 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
   p.bnq.k = k_out;
   p.bnq.sums = reinterpret_cast<long long*>(sums);
   p.bnq.rows_per_image = (uint32_t)(OH * OW);
+  if (remap) {
+    if (q_out) return LBT_EINVAL;
+    p.remap = 1;
+    p.rs_n = remap->sn;
+    p.rs_y = remap->sy;
+    p.rs_x = remap->sx;
+  }
 
   const size_t b_bytes = (size_t)kh * kw * p.b_block;
   // two CTAs per SM (8 epilogue warps each) when two filter banks + rings fit; else one CTA with 16 epilogue warps

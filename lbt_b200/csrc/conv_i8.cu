@@ -54,6 +54,8 @@ struct ConvParams {
   size_t ldc;
   uint32_t idesc;
   BnqParams bnq;                 // fused re-quantising epilogue (bnq.q.bits == 0: off)
+  int remap;                     // fp32 rows go to out + img * rs_n + oh * rs_y + ow * rs_x (OutRemap) instead of row * ldc
+  long long rs_n, rs_y, rs_x;
 };
 
 template <int BN>
@@ -257,7 +259,14 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));
-          float* o = p.out + (size_t)row * p.ldc + col0 + c;
+          float* o;
+          if (p.remap) {
+            const uint32_t img = fastdiv(row, p.d_OHW), rem = row - img * p.OHW;
+            const uint32_t oh = fastdiv(rem, p.d_OW), ow = rem - oh * p.OW;
+            o = p.out + ((long long)img * p.rs_n + (long long)oh * p.rs_y + (long long)ow * p.rs_x) + col0 + c;
+          } else {
+            o = p.out + (size_t)row * p.ldc + col0 + c;
+          }
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -555,6 +564,14 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
                                  int OW, const int32_t* ib_src, const int32_t* ib_w, int exp_const, const float* bias,
                                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
                                  const float* addend, void* stream) {
+  return conv_fprop_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, ib_src, ib_w,
+                        exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream, nullptr);
+}
+
+int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout,
+                        int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_src,
+                        const int32_t* ib_w, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
+                        int8_t* k_out, int64_t* sums, const float* addend, void* stream, const OutRemap* remap) {
   const bool w_prepared = (w_kind & LBT_MANT_PREPARED) != 0;
   w_kind &= ~LBT_MANT_PREPARED;
   if (!src || !wp) return LBT_EINVAL;
@@ -570,7 +587,8 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (C % 16) return LBT_EUNSUPPORTED;
   // measured (benchmarks/gemm_bench.py --path 0|1): the cp.async gather wins for 16- and 32-byte pixel rows (3.1x / 1.1x),
   // the TMA im2col kernel for 64 bytes and more
-  if (conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C))) &&
+  if (remap && q_out) return LBT_EINVAL;
+  if (!remap && conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C))) &&
       conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
@@ -588,7 +606,7 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   if (conv_halo_applies(N, OH, OW, C, Cout, kh, kw, sh, sw)) {
     LBT_REQUIRE_ARCH();
     return conv_halo_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w, exp_const,
-                         bias, out, ldc, q_out, k_out, sums, addend, stream);
+                         bias, out, ldc, q_out, k_out, sums, addend, stream, remap);
   }
   if (Ktot > 65536) return LBT_EUNSUPPORTED;  // exactness bound of one s32 accumulator
   if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
@@ -641,6 +659,12 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
   p.bnq.k = k_out;
   p.bnq.sums = reinterpret_cast<long long*>(sums);
   p.bnq.rows_per_image = (uint32_t)(OH * OW);
+  if (remap) {
+    p.remap = 1;
+    p.rs_n = remap->sn;
+    p.rs_y = remap->sy;
+    p.rs_x = remap->sx;
+  }
 
   // A: im2col map over (C, W, H, N).  The bounding box of base pixels is [lower, dim + upper): with
   // lower = -pad_before and upper = pad_after - (k - 1) it has exactly (out - 1) * stride + 1 positions.

@@ -9,6 +9,13 @@
 
 namespace lbt {
 
+// Output rows of a convolution written through a strided (n, y, x) grid instead of `row * ldc`: the parity-class
+// sub-convolutions of a strided input gradient (lbt_conv_i8_dgrad_strided) each fill one (a::sh, b::sw) sub-lattice of dX.
+// Strides in ELEMENTS of the fp32 output (and of `addend`, which has the output's layout).
+struct OutRemap {
+  long long sn, sy, sx;
+};
+
 bool conv_ldg_ok(int C, int Cout, int kh, int kw);
 bool conv_ldg_enabled();
 bool conv_ldg_halo_applies(int N, int OH, int OW, int kh, int kw, int sh, int sw, int C);
@@ -25,7 +32,13 @@ void conv_halo_enable(int mode);   // bit 0: on, bit 1: ignore the patch fill-ra
 int conv_halo_debug_error();
 int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                   int kw, int pt, int pl, int OH, int OW, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
-                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream);
+                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream,
+                  const OutRemap* remap = nullptr);
+// lbt_conv_i8_fprop's body; remap != NULL: fp32 epilogue only, the im2col-TMA or halo kernels only
+int conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
+                   int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_src, const int32_t* ib_w,
+                   int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
+                   const float* addend, void* stream, const OutRemap* remap);
 
 bool conv_wgrad_ldg_ok(int C, int Cout, int kh, int kw);
 int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout, int kh, int kw,

@@ -5,6 +5,7 @@
 //                        layouts, straight from the fp32 masters                 [was ~6 launches per layer]
 // The reference does these as dozens of TF ops per variable (dynamic_fixed_point.py:194-200, 289-295, 386-392,
 // 679-682 for the quantisers; :207, :302, :457, :689-690 for the gradients).
+#include "conv_classes.h"
 #include "common.cuh"
 
 namespace lbt {
@@ -121,7 +122,10 @@ __global__ void __launch_bounds__(kThreads) param_prep_kernel(const lbt_prep_job
       }
       if (j.out_b) {
         const uint32_t r = tap / j.kw, s = tap % j.kw;
-        const uint32_t tap2 = j.rot180 ? ((j.kh - 1 - r) * j.kw + (j.kw - 1 - s)) : tap;
+        // rot180 = 1: stride-1 input gradient = correlation with the rotated filter; 2: taps grouped by parity class for
+        // the strided input gradient (conv_classes.h; strides in the job's sh / sw); 0: filter order
+        const uint32_t tap2 = j.rot180 == 1 ? ((j.kh - 1 - r) * j.kw + (j.kw - 1 - s))
+                                            : (j.rot180 == 2 ? class_tap_index((int)r, (int)s, (int)j.kh, (int)j.kw, j.sh, j.sw) : tap);
         j.out_b[(size_t)ci * j.ld_b + (size_t)tap2 * j.Cout + co] = kb;          // dgrad B: [Cin, (r',s',co)]
       }
     } else if (j.layout == LBT_PREP_DENSE) {

@@ -214,10 +214,13 @@ class ParamPrep:
                 e['c3'] = c3
                 e['wt'] = torch.zeros(Cout, _pitch16(Ka), dtype=torch.int8, device=device)[:, :Ka]
                 rot = bool(m.implicit and m.stride == (1, 1) and _implicit_ok(Cout, kh, kw) and not (kh == 1 and kw == 1))
+                cls = _dgrad_classes_ok(m, Cin, Cout, kh, kw, m.stride[0], m.stride[1])
                 K2 = kh * kw * Cout
                 e['rot180'] = rot
+                e['classes'] = cls
                 e['w2'] = None if c3 else torch.zeros(Cin, _pitch16(K2), dtype=torch.int8, device=device)[:, :K2]
-                job(m.qW, m.weight.data, layout=1, kh=kh, kw=kw, Cin=Cin, Cout=Cout, c3pad=int(c3), rot180=int(rot),
+                job(m.qW, m.weight.data, layout=1, kh=kh, kw=kw, Cin=Cin, Cout=Cout, c3pad=int(c3), rot180=2 if cls else int(rot),
+                    sh=m.stride[0], sw=m.stride[1],
                     out_a=e['wt'].data_ptr(), ld_a=e['wt'].stride(0),
                     out_b=0 if e['w2'] is None else e['w2'].data_ptr(), ld_b=0 if e['w2'] is None else e['w2'].stride(0))
                 if m.bias is not None:
@@ -439,6 +442,28 @@ def _gather_ok(C, Cout, kh, kw):
     kcp = (kh * kw * (C // 16) + 1) & ~1
     bn = 16 if Cout <= 16 else (32 if Cout <= 32 else (64 if Cout <= 64 else 128))
     return kcp * bn * 16 + 2 * 16384 + 1024 <= 200 * 1024 and kh * kw * C <= 65536 and kcp <= 256 and kh * kw <= 64 and kh <= 16 and kw <= 16
+
+
+def _class_perm(kh, kw, sh, sw):
+    """Filter taps in the parity-class order of csrc/conv_classes.h (the operand of lbt_conv_i8_dgrad_strided)."""
+    perm = []
+    for r0 in range(sh):
+        for s0 in range(sw):
+            for r in reversed(range(r0, kh, sh)):
+                for s_ in reversed(range(s0, kw, sw)):
+                    perm.append(r * kw + s_)
+    return perm
+
+
+DGRAD_CLASSES = True      # module switch (tests): strided input gradients with wide gathered channels as parity-class sub-convolutions
+
+
+def _dgrad_classes_ok(layer, Cin, Cout, kh, kw, sh, sw):
+    """Strided input gradients that run as stride-1 sub-convolutions per parity class (lbt_conv_i8_dgrad_strided) instead of
+    a transposed im2col matrix + GEMM: everything the gather kernel does not take."""
+    return (DGRAD_CLASSES and layer.implicit and (sh, sw) != (1, 1) and sh <= 4 and sw <= 4 and layer.qG.bits <= 8 and
+            layer.qW.bits <= 8 and (Cout in (16, 32, 64) or Cout % 128 == 0) and Cin % 4 == 0 and
+            not _gather_ok(Cout, Cin, kh, kw))
 
 
 # LBT_MANT_PREPARED (include/lbt.h): let the convolution kernels copy a filter packed by lbt_param_prep before they wait for their
@@ -663,6 +688,18 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
                       Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
                       _lib.ptr(dx), Cin, _lib.ptr(ad2), _lib.stream(),
                       meta=dict(ops=2 * N * H * W * Cin * K2, bytes=N * OH * OW * Cout + Cin * K2 + N * H * W * Cin * 4))
+        elif (prep['classes'] if prep is not None else _dgrad_classes_ok(layer, Cin, Cout, kh, kw, sh, sw)):
+            # wide gathered channels: one stride-1 sub-convolution per parity class of input pixels, no im2col matrix
+            if pw2 is not None:
+                w2 = pw2
+            else:
+                perm = torch.tensor(_class_perm(kh, kw, sh, sw), device=dev)
+                w2 = _as_operand(wm.view(kh * kw, Cin, Cout).index_select(0, perm).permute(1, 0, 2).reshape(Cin, K2))
+            _lib.call('lbt_conv_i8_dgrad_strided', _lib.ptr(gm), Q.MANT_S8, N, OH, OW, Cout, _lib.ptr(w2),
+                      Q.MANT_S8 | (_W_PREPARED if pw2 is not None else 0), w2.stride(0),
+                      Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
+                      _lib.ptr(dx), Cin, _lib.ptr(ad2), _lib.stream(),
+                      meta=dict(ops=2 * N * OH * OW * Cin * K2, bytes=N * OH * OW * Cout * min(sh * sw, kh * kw) + Cin * K2 + N * H * W * Cin * 4))
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             A2 = _im2col(gm, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)

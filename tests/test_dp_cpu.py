@@ -69,6 +69,6 @@ def test_finalize_and_prep_job_structs_match_header():
     import ctypes
     from lbt_b200 import _lib
     assert ctypes.sizeof(_lib.FinalizeJob) == 64
-    assert ctypes.sizeof(_lib.PrepJob) == 120
+    assert ctypes.sizeof(_lib.PrepJob) == 128
     assert _lib.FinalizeJob.start.offset == 56 and _lib.FinalizeJob.exp_const.offset == 32
-    assert _lib.PrepJob.bits.offset == 88 and _lib.PrepJob.rot180.offset == 116
+    assert _lib.PrepJob.bits.offset == 88 and _lib.PrepJob.rot180.offset == 116 and _lib.PrepJob.sw.offset == 124

@@ -441,3 +441,58 @@ def test_conv_tma_halo_equals_im2col(N, H, W, Cin, Cout, k, pad):
     ref = F.conv2d(xe, we, padding=pad).permute(0, 2, 3, 1).reshape(N * OH * OW, Cout)
     want = ((ref * 2.0 ** (-12 + 2)).float() + bias) + addend
     assert torch.equal(res[1][0], want)
+
+
+@pytest.mark.parametrize('N,H,W,Cin,Cout,k,s', [(2, 56, 56, 64, 128, 3, 2), (3, 28, 28, 128, 256, 3, 2), (2, 14, 14, 256, 512, 3, 2),
+                                                (2, 56, 56, 64, 128, 1, 2), (2, 28, 28, 128, 256, 1, 2), (2, 27, 31, 64, 128, 3, 2),
+                                                (1, 30, 30, 128, 128, 5, 3), (2, 16, 16, 256, 1024, 1, 2)])
+@pytest.mark.parametrize('with_addend', [False, True])
+def test_strided_dgrad_parity_classes_equal_im2col_and_exact(N, H, W, Cin, Cout, k, s, with_addend):
+    """lbt_conv_i8_dgrad_strided (one stride-1 sub-convolution per parity class of input pixels on the class-ordered filter
+    operand, output rows written through the class's sub-lattice of dX) against the transposed im2col matrix + GEMM and
+    against the exact transposed convolution (fp64), TF 'SAME' padding, with and without the shortcut branch's addend."""
+    from lbt_b200 import quantizer as Q
+    conv = D.Conv2d_q(8, Cin, Cout, k, s, 'SAME', bias=False).cuda()
+    rng = np.random.default_rng(N * H + Cin + k + s)
+    OH, pt, _ = D.same_pad(H, k, s)
+    OW, pl, _ = D.same_pad(W, k, s)
+    geom = (N, H, W, Cin, Cout, k, k, s, s, pt, pl, OH, OW)
+    xm = torch.from_numpy(rng.integers(0, 256, (N, H, W, Cin), dtype=np.uint8)).cuda()
+    wm = torch.from_numpy(rng.integers(-128, 128, (k, k, Cin, Cout), dtype=np.int8)).cuda()
+    gm = torch.from_numpy(rng.integers(-128, 128, (N, OH, OW, Cout), dtype=np.int8)).cuda()
+    addend = torch.randn(N, H, W, Cin, device='cuda') if with_addend else None
+    from lbt_b200 import _lib
+    calls = []
+    orig = _lib.call
+
+    def spy(fn, *a, **kw):
+        calls.append(fn)
+        return orig(fn, *a, **kw)
+
+    res = {}
+    _lib.call = spy
+    try:
+        for cls in (True, False):
+            D.DGRAD_CLASSES = cls
+            del calls[:]
+            dx, _, _ = D._conv_backward(conv, geom, xm, Q.MANT_U8, wm, None, gm, True, False, False, addend=addend)
+            torch.cuda.synchronize()
+            res[cls] = dx.clone()
+            assert ('lbt_conv_i8_dgrad_strided' in calls) == cls, calls
+    finally:
+        _lib.call = orig
+        D.DGRAD_CLASSES = True
+    assert _lib.lib().lbt_conv_debug_error() == 0
+    assert torch.equal(res[True], res[False])
+    # exact: dX = conv_transpose(g, W) in fp64, scaled by 2^(ib_g + ib_w - 7 - 7)
+    ge = gm.double().permute(0, 3, 1, 2)
+    we = wm.double().permute(3, 2, 0, 1)                       # [Cout, Cin, kh, kw] = conv_transpose2d's weight layout
+    full = F.conv_transpose2d(ge, we, stride=s)                 # [(OH-1)*s + k] grid that starts at input row -pt
+    ref = torch.zeros(N, Cin, H, W, dtype=torch.float64, device='cuda')
+    hh, ww = min(H, full.shape[2] - pt), min(W, full.shape[3] - pl)
+    ref[:, :, :hh, :ww] = full[:, :, pt:pt + hh, pl:pl + ww]
+    e = int(conv.qG.range.item()) + int(conv.qW.range.item()) - 14
+    want = (ref * 2.0 ** e).float().permute(0, 2, 3, 1)
+    if addend is not None:
+        want = want + addend
+    assert torch.equal(res[True], want.contiguous())
