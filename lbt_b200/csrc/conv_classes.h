@@ -23,13 +23,11 @@ LBT_HD inline int class_count(int r0, int k, int stride) { return r0 < k ? (k - 
 
 // first tap (in units of taps) of residue group (r0, s0)
 LBT_HD inline uint32_t class_group_offset(int r0, int s0, int kh, int kw, int sh, int sw) {
-  uint32_t off = 0;
-  for (int a = 0; a < sh; ++a)
-    for (int b = 0; b < sw; ++b) {
-      if (a == r0 && b == s0) return off;
-      off += (uint32_t)(class_count(a, kh, sh) * class_count(b, kw, sw));
-    }
-  return off;
+  // groups (a, b) before (r0, s0) in row-major order: whole rows a < r0 hold every column (kw taps per filter row)
+  int rows_before = 0, cols_before = 0;
+  for (int a = 0; a < r0; ++a) rows_before += class_count(a, kh, sh);
+  for (int b = 0; b < s0; ++b) cols_before += class_count(b, kw, sw);
+  return (uint32_t)(rows_before * kw + class_count(r0, kh, sh) * cols_before);
 }
 
 // position of filter tap (r, s) in the class-ordered operand
