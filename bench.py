@@ -403,12 +403,17 @@ def run_native(a):
         time.sleep(0.25)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profile_region = os.environ.get('LBT_PROFILE_REGION') == '1'     # `ncu --profile-from-start off`: capture exactly these steps
+    if profile_region:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(a.steps):
         Xs.copy_(devX[i % pool]); ys.copy_(devy[i % pool])
         loss = step()
     e1.record()
     barrier()
+    if profile_region:
+        torch.cuda.profiler.stop()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / a.steps

@@ -280,12 +280,12 @@ __global__ void __launch_bounds__(kThreads) bn_fwd1_kernel(const Fwd1Params p) {
     const uint32_t v = ch * kThreads + threadIdx.x;
     if (v < p.t.n_vec) {
       const float4 u = site_noise(p.q, v, off);
-      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
-      for (size_t r = r0; r < r1; r += kRows) {
+      const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
+      for (uint32_t r = r0; r < r1; r += kRows) {
         float4 xv[kRows];
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
-          if (r + i < r1) xv[i] = __ldcs(reinterpret_cast<const float4*>(p.x + (r + i) * p.t.n_inner) + v);
+          if (r + i < r1) xv[i] = __ldcs(reinterpret_cast<const float4*>(p.x) + ((r + i) * p.t.n_vec + v));
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
           if (r + i < r1) {
@@ -359,11 +359,11 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
     const uint64_t tile = blockIdx.x;
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), v = (uint32_t)(tile % p.t.chunks) * kThreads + threadIdx.x;
     if (tile < p.t.total_tiles && v < p.t.n_vec) {
-      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r0 + i < r1) {
-          const size_t idx = (r0 + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r0 + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           prefetch_l1(p.k1 + idx);
           if (p.add) prefetch_l1(p.add + idx);
         }
@@ -423,28 +423,28 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
       g[j] = s_par[2 * C + c0 + j];
       b[j] = s_par[3 * C + c0 + j];
     }
-    const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
-    for (size_t r = r0; r < r1; r += kRows) {
+    const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
+    for (uint32_t r = r0; r < r1; r += kRows) {
       uint32_t kw[kRows];
       float4 av[kRows];
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           kw[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
           if (has_add) av[i] = __ldcs(reinterpret_cast<const float4*>(p.add + idx));
         }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + kRows + i < r1) {
-          const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + kRows + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           prefetch_l1(p.k1 + idx);
           if (has_add) prefetch_l1(p.add + idx);
         }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           float k1f[4];
           dec4_f(kw[i], k1f);
           const float a4[4] = {av[i].x, av[i].y, av[i].z, av[i].w};
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
         gd[j] = gq * gscale;       // dx2 * mg1 = kg2 * (gq * mg1 / mg2)
         b[j] = __ldg(p.bq + c0 + j);
       }
-      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
       // POOL: the <= 2 x 2 pooling windows over this thread's pixel — the same for every batch row (tf.nn.max_pool's
       // gradient, dfxp:993-1006: a pixel receives the gradient of each window it won; lbt_maxpool_bwd's gather and order)
       uint32_t poff[4] = {0u, 0u, 0u, 0u};
@@ -566,15 +566,15 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
           }
         pimg = (size_t)p.pOH * p.pOW * C;
       }
-      for (size_t r = r0; r < r1; r += kRows) {
+      for (uint32_t r = r0; r < r1; r += kRows) {
         float4 gv[kRows], ov[kRows];
         uint32_t w2[kRows], w1[kRows];
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
           if (r + i < r1) {
-            const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+            const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
             if (POOL) {
-              const size_t base = (r + i) * pimg;
+              const size_t base = (size_t)(r + i) * pimg;
               float4 gw[4];
               uint32_t iw4[4];
 #pragma unroll
@@ -603,9 +603,9 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
           if (r + kRows + i < r1) {
-            const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+            const size_t idx = 4 * (size_t)((r + kRows + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
             if (POOL) {
-              const size_t base = (r + kRows + i) * pimg;
+              const size_t base = (size_t)(r + kRows + i) * pimg;
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 if (pok[q]) {
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p
 #pragma unroll
         for (int i = 0; i < kRows; ++i)
           if (r + i < r1) {
-            const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+            const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
             int k2[4], k1[4];
             unpack4(w2[i], k2);
             unpack4(w1[i], k1);
@@ -711,11 +711,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
     const uint64_t tile = blockIdx.x;
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), v = (uint32_t)(tile % p.t.chunks) * kThreads + threadIdx.x;
     if (tile < p.t.total_tiles && v < p.t.n_vec) {
-      const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+      const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r0 + i < r1) {
-          const size_t idx = (r0 + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r0 + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           prefetch_l1(reinterpret_cast<const int8_t*>(p.kg1) + (WIDE ? 2 : 1) * idx);
           prefetch_l1(p.k1 + idx);
         }
@@ -763,14 +763,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
       const float4 t = site_noise(p.qg, v, offq);
       uq[0] = t.x; uq[1] = t.y; uq[2] = t.z; uq[3] = t.w;
     }
-    const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
-    for (size_t r = r0; r < r1; r += kRows) {
+    const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
+    for (uint32_t r = r0; r < r1; r += kRows) {
       uint2 wg[kRows];
       uint32_t w1[kRows];
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           if (WIDE) wg[i] = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(p.kg1) + idx));
           else wg[i].x = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(p.kg1) + idx));
           w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
@@ -778,14 +778,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + kRows + i < r1) {
-          const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + kRows + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           prefetch_l1(reinterpret_cast<const int8_t*>(p.kg1) + (WIDE ? 2 : 1) * idx);
           prefetch_l1(p.k1 + idx);
         }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           float kgf[4], k1f[4];
           if (WIDE) dec4_f_s16(wg[i], kgf);
           else dec4_f(wg[i].x, kgf);
@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
   const uint32_t v = chk * kThreads + threadIdx.x;
   const bool active = v < p.t.n_vec;
   const int c0 = active ? (int)((4ull * v) % (uint64_t)C) : 0;
-  const size_t r0 = (size_t)rg * p.t.rows_per_group, r1 = min(r0 + (size_t)p.t.rows_per_group, p.t.n_outer);
+  const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
   if (active) {
     const float4 u2v = site_noise(p.qg2, v, off2), u1v = site_noise(p.qg1, v, off1);
     const float u2[4] = {u2v.x, u2v.y, u2v.z, u2v.w}, u1[4] = {u1v.x, u1v.y, u1v.z, u1v.w};
@@ -881,13 +881,13 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
       g[j] = __ldg(p.gq + c0 + j);
       b[j] = __ldg(p.bq + c0 + j);
     }
-    for (size_t r = r0; r < r1; r += kRows) {
+    for (uint32_t r = r0; r < r1; r += kRows) {
       float4 gv[kRows], ov[kRows];
       uint32_t w2[kRows], w1[kRows];
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           gv[i] = __ldcs(reinterpret_cast<const float4*>(p.g + idx));
           w2[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k2 + idx));
           w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + kRows + i < r1) {
-          const size_t idx = (r + kRows + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + kRows + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           prefetch_l1(p.g + idx);
           prefetch_l1(p.k2 + idx);
           prefetch_l1(p.k1 + idx);
@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_fused_kernel(const BwdFuse
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
         if (r + i < r1) {
-          const size_t idx = (r + i) * p.t.n_inner + 4 * (size_t)v;
+          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
           int k2[4], k1[4];
           unpack4(w2[i], k2);
           unpack4(w1[i], k1);

@@ -203,9 +203,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool rvalid = oy < p.OH && ox < p.OW;
       const uint32_t pix = oy * p.OW + ox;
       const uint32_t row = img * p.OHW + pix;
+      // fp32 epilogue: where this row goes (and where its addend comes from)
+      const long long obase = fused ? 0ll
+                              : (p.remap ? (long long)img * p.rs_n + (long long)oy * p.rs_y + (long long)ox * p.rs_x
+                                         : (long long)((size_t)row * p.ldc));
+      const bool add_vec = !fused && p.addend != nullptr && rvalid && ((reinterpret_cast<uintptr_t>(p.addend + obase) & 15u) == 0);
       if (fused) {   // this warp's noise lines of the tile: into L1 while the accumulator is still being computed
 #pragma unroll 1
         for (int c = 16 * (int)sub; c < BN; c += 16 * kSub) bnq_prefetch(p.bnq, pix, p.N, (uint32_t)c, rvalid && (uint32_t)c < p.N);
+      } else if (add_vec) {   // ... and the addend's lines (an fp32 tensor in HBM: a DRAM round trip per chunk otherwise)
+#pragma unroll 1
+        for (int c = 16 * (int)sub; c < BN; c += 16 * kSub)
+          if ((uint32_t)c < p.N) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.addend + obase + c));
       }
       ok = mbar_wait(&tmem_full_bar[acc], acc_phase, abort_flag, &g_halo_error);
       ok = __all_sync(0xffffffffu, ok);
@@ -220,12 +229,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 16 * (int)sub; c < BN; c += 16 * kSub) {
         uint32_t v[16];
+        const uint32_t ncol = (uint32_t)c < p.N ? min(16u, p.N - (uint32_t)c) : 0u;
+        // everything the chunk needs from memory is requested BEFORE the accumulator wait: the noise (fused) or the addend
+        float4 u4[4];
+        const bool addv = add_vec && ncol == 16;
+        if (fused) {
+          if (ncol) bnq_load_noise(p.bnq, bst, pix, rvalid, (uint32_t)c, ncol, p.N, u4);
+        } else if (addv) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) u4[j] = __ldcs(reinterpret_cast<const float4*>(p.addend + obase + c) + j);
+        }
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
-        if ((uint32_t)c >= p.N) continue;   // warp-uniform
-        const uint32_t ncol = min(16u, p.N - (uint32_t)c);
+        if (!ncol) continue;   // warp-uniform
         if (fused) {
-          bnq_chunk(p.bnq, bst, v, scale, p.bias ? p.bias + c : nullptr, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN,
+          bnq_chunk(p.bnq, bst, v, u4, scale, p.bias ? p.bias + c : nullptr, row, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN,
                     (uint32_t)c, lane);
           continue;
         }
@@ -236,20 +254,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + c + j));
         }
         if (rvalid) {
-          float* o = p.remap ? p.out + ((long long)img * p.rs_n + (long long)oy * p.rs_y + (long long)ox * p.rs_x) + c
-                             : p.out + (size_t)row * p.ldc + c;
+          float* o = p.out + obase + c;
           if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
-            const float* ad = p.addend + (o - p.out);
-            if (ncol == 16 && ((reinterpret_cast<uintptr_t>(ad) & 15u) == 0)) {
-              float4 a4[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) a4[j] = __ldcs(reinterpret_cast<const float4*>(ad) + j);
+            const float* ad = p.addend + obase + c;
+            if (addv) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                f[4 * j + 0] = __fadd_rn(f[4 * j + 0], a4[j].x);
-                f[4 * j + 1] = __fadd_rn(f[4 * j + 1], a4[j].y);
-                f[4 * j + 2] = __fadd_rn(f[4 * j + 2], a4[j].z);
-                f[4 * j + 3] = __fadd_rn(f[4 * j + 3], a4[j].w);
+                f[4 * j + 0] = __fadd_rn(f[4 * j + 0], u4[j].x);
+                f[4 * j + 1] = __fadd_rn(f[4 * j + 1], u4[j].y);
+                f[4 * j + 2] = __fadd_rn(f[4 * j + 2], u4[j].z);
+                f[4 * j + 3] = __fadd_rn(f[4 * j + 3], u4[j].w);
               }
             } else {
 #pragma unroll

@@ -249,12 +249,17 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16)) {
         if (BN == 16 && half) break;  // a single chunk: the second warp of the quadrant has nothing to do
         uint32_t v[16];
+        float4 u4[4];   // fused: the chunk's noise, requested before the accumulator wait (bnq_load_noise)
+        const bool fchunk = fused && col0 + c < p.N;   // warp-uniform
+        if (BN > 16 && fchunk) bnq_load_noise(p.bnq, bst, pix, row < p.M, col0 + c, min(16u, p.N - (col0 + c)), p.N, u4);
         tmem_ld16(taddr + c, v);
         tmem_ld_wait();
+        if (BN <= 16 && fchunk)   // the 16-column instantiation runs three CTAs per SM at 64 registers: no room for early loads
+          bnq_load_noise(p.bnq, bst, pix, row < p.M, col0 + c, min(16u, p.N - (col0 + c)), p.N, u4);
         if (fused) {
-          if (col0 + c < p.N) {   // warp-uniform
+          if (fchunk) {
             const uint32_t ncol = min(16u, p.N - (col0 + c));
-            bnq_chunk(p.bnq, bst, v, scale, p.bias ? p.bias + col0 + c : nullptr, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
+            bnq_chunk(p.bnq, bst, v, u4, scale, p.bias ? p.bias + col0 + c : nullptr, row, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
                       (uint32_t)c, lane);
           }
         } else if (row < p.M && col0 + c < p.N) {

@@ -418,6 +418,55 @@ __global__ void __launch_bounds__(1024) xent_fwd_kernel(const float* __restrict_
   }
 }
 
+// The same computation spread over a thread-block cluster: one CTA was the whole 80 us of a 256 x 1000 problem.  CTA r of the
+// cluster takes the 32-row groups g with g % kXentCluster == r; every row's loss goes to CTA 0's shared memory (distributed
+// shared memory), and CTA 0 adds them in exactly the single-CTA kernel's order (warp w: rows w, w + 32, ... from 0.0f; then
+// the 32 warp partials in order), so the loss is bit-identical.  Rows never interact elsewhere.
+constexpr int kXentCluster = 8;
+constexpr int kXentMaxRows = 4096;
+__global__ void __cluster_dims__(kXentCluster, 1, 1) __launch_bounds__(1024)
+xent_fwd_cluster_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C, float* __restrict__ probs,
+                        float* __restrict__ loss) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_row[kXentMaxRows];   // used in CTA 0 only
+  __shared__ float s_part[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  uint32_t row0_addr;   // CTA 0's s_row in the cluster's shared window
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(row0_addr) : "r"((uint32_t)__cvta_generic_to_shared(s_row)), "r"(0));
+  for (int row = warp + 32 * (int)rank; row < B; row += 32 * kXentCluster) {
+    const float* x = logits + (size_t)row * C;
+    const long long y = labels[row];
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, x[c]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += expf(x[c] - m);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float ls = logf(s);
+    for (int c = lane; c < C; c += 32) probs[(size_t)row * C + c] = expf(x[c] - m - ls);
+    if (lane == 0) {
+      const float l = (y >= 0 && y < C) ? -(x[y] - m - ls) : 0.f;   // + 0.0f leaves the running sum as the skipped row did
+      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(row0_addr + 4u * (uint32_t)row), "f"(l) : "memory");
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank != 0) return;
+  if (lane == 0) {
+    float part = 0.f;
+    for (int row = warp; row < B; row += 32) part += s_row[row];
+    s_part[warp] = part;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 32; ++w) t += s_part[w];
+    *loss = t / (float)B;
+  }
+}
+
 __global__ void __launch_bounds__(256) xent_bwd_kernel(const float* __restrict__ probs, const long long* __restrict__ labels,
                                                        const float* __restrict__ gout, int B, int C, float* __restrict__ dlogits) {
   pdl_trigger();   // programmatic dependent launch: the next kernel may be scheduled now ...
@@ -472,7 +521,10 @@ extern "C" int lbt_softmax_xent_fwd(const float* logits, const int64_t* labels, 
   if (!logits || !labels || !probs || !loss || B <= 0 || C <= 0) return LBT_EINVAL;
   LBT_REQUIRE_ARCH();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  launch_pdl(xent_fwd_kernel, 1, 1024, 0, st, logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
+  if (B > 32 && B <= kXentMaxRows && (size_t)B * C > (size_t)kXentStage)   // small problems: one CTA with staged logits
+    launch_pdl(xent_fwd_cluster_kernel, kXentCluster, 1024, 0, st, logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
+  else
+    launch_pdl(xent_fwd_kernel, 1, 1024, 0, st, logits, reinterpret_cast<const long long*>(labels), B, C, probs, loss);
   return check_launch("lbt_softmax_xent_fwd");
 }
 

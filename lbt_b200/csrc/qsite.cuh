@@ -222,11 +222,23 @@ __device__ __forceinline__ uint32_t pack4_low_bytes(float t0, float t1, float t2
   return __byte_perm(p01, p23, 0x5410);
 }
 
-template <bool FULL, bool MM>
-__device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
-                                               uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
-                                               int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+// The chunk's 16 noise values (four float4).  Split from bnq_chunk so that a caller can issue these loads BEFORE it waits for
+// the accumulator (tcgen05.wait::ld): the L1 / L2 round trip then overlaps the wait instead of stalling the first addition
+// (ncu source view of conv_halo_kernel: the four `y + u` FADDs held 28 % of all stall samples, long scoreboard).
+__device__ __forceinline__ void bnq_load_noise(const BnqParams& b, const BnqState& st, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol,
+                                               uint32_t N, float4 (&u)[4]) {
   const uint64_t inner = (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (b.q.noise) u[g] = (row_ok && 4u * g < ncol) ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else u[g] = philox_noise4((inner >> 2) + g, b.q.seed, st.off);
+  }
+}
+
+template <bool FULL, bool MM>
+__device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
+                                               const float* bias, uint32_t row, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
+                                               int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
   const QC& c = st.qc;
   // one multiply when no bias sits between the two scalings and neither product can leave the normal range
   const bool fold = bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(c.m)) < 60.0f;
@@ -234,10 +246,7 @@ __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st,
   float tm[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    float4 u;
-    if (b.q.noise) u = (FULL || (row_ok && 4u * g < ncol)) ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-    else u = philox_noise4((inner >> 2) + g, b.q.seed, st.off);
-    const float un[4] = {u.x, u.y, u.z, u.w};
+    const float un[4] = {u4[g].x, u4[g].y, u4[g].z, u4[g].w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int j = 4 * g + t;
@@ -279,18 +288,26 @@ __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st,
   s_stat[(kind ? bn : 0u) + tcol + (uint32_t)chan] += tot;
 }
 
-// `bias`: this chunk's 16 bias values (NULL: none).
-__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
-                                          uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
+// `bias`: this chunk's 16 bias values (NULL: none); `u4`: the chunk's noise from bnq_load_noise.
+__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
+                                          const float* bias, uint32_t row, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
                                           uint32_t bn, uint32_t tcol, int lane) {
   const bool full = ncol == 16 && __all_sync(0xffffffffu, row_ok);
   if (b.q.minmax) {
-    if (full) bnq_chunk_impl<true, true>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, true>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    if (full) bnq_chunk_impl<true, true>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, true>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
   } else {
-    if (full) bnq_chunk_impl<true, false>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, false>(b, st, v, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    if (full) bnq_chunk_impl<true, false>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, false>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
   }
+}
+// Noise fetched here, right before use (callers that cannot place the loads ahead of their accumulator wait).
+__device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
+                                          uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
+                                          uint32_t bn, uint32_t tcol, int lane) {
+  float4 u4[4];
+  bnq_load_noise(b, st, pix, row_ok, col, ncol, N, u4);
+  bnq_chunk(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
 }
 
 // Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.

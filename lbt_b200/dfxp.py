@@ -53,6 +53,7 @@ class Runtime:
         self._arena_on = False
         self._side = None            # side stream: wgrad runs beside dgrad (independent consumers of the same gradient)
         self.overlap = True
+        self._prep_pending = False   # begin_step() left the parameter branch running on the side stream
         self._noise_req = {}         # (quantiser id, n_inner) wanted by fused tensor-core epilogues
         self._noise_tab = None       # dict(map={key: fp32 view}, jobs=device table, total=groups, keep=[...])
         self._noise_valid = False
@@ -72,6 +73,7 @@ class Runtime:
         key = (site.qid, int(n_inner))
         tab = self._noise_tab
         if tab is not None and self._noise_valid and key in tab['map']:
+            self.join_prep()
             return tab['map'][key]
         self._noise_req[key] = True
         return None
@@ -110,10 +112,29 @@ class Runtime:
         self._arena_used = 0
         self._arena_on = True
         self._prep_valid = False
+        # the parameter side (quantise + pack every weight, fill the noise vectors) shares nothing with the quantisation of
+        # the step's input, so inside a Trainer step it runs as a parallel branch; its first consumer joins (join_prep)
+        fork = (self.prep is not None and self.overlap and self.grad_sink is not None and _lib.profiler is None
+                and os.environ.get('LBT_PREP_FORK', '1') != '0')
+        if fork:
+            main, side = torch.cuda.current_stream(device), self.side_stream(device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.prep.run()
+                self._fill_noise(device)
+            self._prep_valid = True
+            self._prep_pending = True
+            return
         if self.prep is not None:
             self.prep.run()
             self._prep_valid = True      # until update_ranges() closes the step
         self._fill_noise(device)
+
+    def join_prep(self):
+        """First consumer of a prepared operand or a noise vector: wait for the parameter branch of begin_step()."""
+        if self._prep_pending:
+            self._prep_pending = False
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
 
     def zeros_i64(self, n, device):
         """n zeroed int64 slots (16-byte aligned) from the arena; a fresh tensor when the arena is off or full."""
@@ -170,6 +191,7 @@ class Runtime:
         self.close_step()
 
     def close_step(self):
+        self.join_prep()
         self._arena_on = False           # the step is closed: prepared operands and arena slices are stale now
         self._prep_valid = False
         self._noise_valid = False
@@ -265,6 +287,7 @@ def _prepared(layer):
     rt = layer.qX.runtime
     if rt.prep is None or rt.noise_fn is not None or not getattr(rt, '_prep_valid', False):
         return None
+    rt.join_prep()
     return rt.prep.entries.get(layer)
 
 
