@@ -16,6 +16,7 @@
 // Replaces tf.nn.conv2d (dynamic_fixed_point.py:291) and, with the filter rotated by 180 degrees, its stride-1 input
 // gradient (:305) for the 3x3 layers of the ImageNet ResNets' first two stages.
 #include <atomic>
+#include <cstdlib>
 
 #include "conv_internal.h"
 #include "qsite.cuh"
@@ -57,6 +58,7 @@ struct HaloParams {
   uint32_t idesc;
   BnqParams bnq;
   int remap;                     // fp32 rows go to out + img * rs_n + oy * rs_y + ox * rs_x (OutRemap) instead of row * ldc
+  int sector_f32;                // fp32 epilogue through the .16x256b load shape (full-sector stores): N % 16 == 0, 8-byte aligned rows
   long long rs_n, rs_y, rs_x;
 };
 
@@ -192,6 +194,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int i = lane; i < 2 * BN; i += 32) my_stat[i] = 0;
       __syncwarp();
     }
+    // fp32 output in full sectors (see below): needs whole 16-column chunks and 8-byte aligned rows
+    const bool sect = !fused && p.sector_f32 != 0;
     uint32_t acc = 0, acc_phase = 0;
     bool ok = true;
     for (uint32_t tile = blockIdx.x; tile < p.m_tiles && ok; tile += gridDim.x) {
@@ -226,6 +230,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         bst.tiles = 0;
       }
       ++bst.tiles;
+      if (sect) {
+        // fp32 rows as full 32-byte sectors: the accumulator-fragment load shape puts 8 contiguous bytes of a row in each lane
+        // and a row's 32 bytes in four neighbouring lanes.  This lane's four rows: patch column lane / 4, patch rows
+        // 4 * quad + {0, 1, 2, 3} (the 16-lane halves h = 0, 1 of the quadrant x the fragment's row pair k = 0, 1).
+        const uint32_t ox2 = tx * kPatchW + ((uint32_t)lane >> 2), oy2 = ty * kPatchH + 4u * quad;
+        const long long ystep = p.remap ? (long long)p.rs_y : (long long)((size_t)p.OW * p.ldc);
+        const long long ob2 = (p.remap ? (long long)img * p.rs_n + (long long)oy2 * p.rs_y + (long long)ox2 * p.rs_x
+                                       : (long long)((size_t)(img * p.OHW + oy2 * p.OW + ox2) * p.ldc)) + 2 * (lane & 3);
+        bool rv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rv[j] = ox2 < p.OW && oy2 + (uint32_t)j < p.OH;
+#pragma unroll 1
+        for (int c = 16 * (int)sub; c < BN; c += 16 * kSub) {
+          if ((uint32_t)c >= p.N) break;   // warp-uniform (N % 16 == 0 on this path)
+          float2 ad[8];
+          if (p.addend) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int n = 0; n < 2; ++n)
+                if (rv[j]) ad[2 * j + n] = __ldcs(reinterpret_cast<const float2*>(p.addend + ob2 + j * ystep + c + 8 * n));
+          }
+          uint32_t va[8], vb[8];
+          tmem_ld_16x256b_x2(taddr + c, va);                 // lanes 0..15 of the quadrant: patch rows 4 * quad + {0, 1}
+          tmem_ld_16x256b_x2(taddr + c + (16u << 16), vb);   // lanes 16..31:                             + {2, 3}
+          tmem_ld_wait();
+          float2 bs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          if (p.bias) {
+            bs[0] = __ldg(reinterpret_cast<const float2*>(p.bias + c + 2 * (lane & 3)));
+            bs[1] = __ldg(reinterpret_cast<const float2*>(p.bias + c + 8 + 2 * (lane & 3)));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!rv[j]) continue;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const uint32_t* src = j < 2 ? va : vb;
+              float f0 = __int2float_rn((int)src[4 * n + 2 * (j & 1)]) * scale, f1 = __int2float_rn((int)src[4 * n + 2 * (j & 1) + 1]) * scale;
+              if (p.bias) {
+                f0 = __fadd_rn(f0, n ? bs[1].x : bs[0].x);
+                f1 = __fadd_rn(f1, n ? bs[1].y : bs[0].y);
+              }
+              if (p.addend) {
+                f0 = __fadd_rn(f0, ad[2 * j + n].x);
+                f1 = __fadd_rn(f1, ad[2 * j + n].y);
+              }
+              *reinterpret_cast<float2*>(p.out + ob2 + j * ystep + c + 8 * n) = make_float2(f0, f1);
+            }
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 16 * (int)sub; c < BN; c += 16 * kSub) {
         uint32_t v[16];
@@ -402,6 +457,18 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
     p.rs_x = remap->sx;
   }
 
+  {
+    static const int sector_on = [] {   // A/B switch: LBT_HALO_SECTOR=0 keeps the row-per-lane fp32 epilogue
+      const char* e = std::getenv("LBT_HALO_SECTOR");
+      return e ? std::atoi(e) : 1;
+    }();
+    const auto even = [](long long v) { return (v & 1) == 0; };
+    const bool al = (reinterpret_cast<uintptr_t>(out) & 7u) == 0 && (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 7u) == 0) &&
+                    (!bias || (reinterpret_cast<uintptr_t>(bias) & 7u) == 0);
+    p.sector_f32 = !q_out && out && Cout % 16 == 0 && al &&
+                   (p.remap ? even(p.rs_n) && even(p.rs_y) && even(p.rs_x) : even((long long)ldc)) &&
+                   sector_on;
+  }
   const size_t b_bytes = (size_t)kh * kw * p.b_block;
   // two CTAs per SM (8 epilogue warps each) when two filter banks + rings fit; else one CTA with 16 epilogue warps
   // (227 KB per SM; each CTA also holds ~1 KB of system shared memory and this kernel's static arrays: 7 - 20 KB)

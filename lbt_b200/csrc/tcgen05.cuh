@@ -127,6 +127,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 16 TMEM lanes x 16 columns in the accumulator-fragment distribution (shape .16x256b, two 8-column groups): thread t holds,
+// for column group n (0, 1), v[4n + 0..1] = row t/4, columns 8n + 2(t%4) + {0, 1} and v[4n + 2..3] = row t/4 + 8, same columns.
+// Four neighbouring lanes hold 32 contiguous bytes of one row: fp32 rows are then stored as full 32-byte sectors (the
+// 32x32b shape gives every lane its own row, i.e. 16-byte pieces 32 rows apart).  taddr's lane = first of the 16 lanes.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- shared-memory matrix descriptors (PTX ISA "tcgen05 matrix descriptor") ----
