@@ -77,7 +77,8 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t smem_addr, int m, ui
 }
 
 // EPI epilogue warps (a multiple of 4: EPI / 4 per TMEM lane quadrant, interleaved over the 16-column chunks).
-template <int BN, int EPI>
+// FUSED: the re-quantising epilogue (two instantiations per shape: either epilogue compiles without the other's registers).
+template <int BN, int EPI, bool FUSED>
 __global__ void __launch_bounds__(32 * (2 + EPI), EPI == 8 ? 2 : 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   constexpr int kThreadsH = 32 * (2 + EPI);
@@ -185,7 +186,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.ibA) e += *p.ibA;
     if (p.ibB) e += *p.ibB;
     const float scale = exp2i(e);
-    const bool fused = p.bnq.q.bits != 0;
+    constexpr bool fused = FUSED;   // == (p.bnq.q.bits != 0), chosen by the host
     int* my_stat = s_stat[warp - 2];
     BnqState bst;
     bst.tiles = 0;
@@ -367,21 +368,26 @@ void* driver_fn(const char* name) {
   return f;
 }
 
-template <int BN, int EPI>
-int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+template <int BN, int EPI, bool FUSED>
+int launch_halo_impl(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem, cudaStream_t st) {
   static size_t attr_done[16] = {};
   const int dev = device_info().device;
   if (attr_done[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, EPI, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_kernel)");
       return LBT_ECUDA;
     }
     attr_done[dev] = smem;
   }
-  launch_pdl(conv_halo_kernel<BN, EPI>, grid, 32 * (2 + EPI), smem, st, ta, tb, p);
+  launch_pdl(conv_halo_kernel<BN, EPI, FUSED>, grid, 32 * (2 + EPI), smem, st, ta, tb, p);
   g_halo_launches.fetch_add(1, std::memory_order_relaxed);
   return check_launch("lbt_conv_i8_fprop");
+}
+
+template <int BN, int EPI>
+int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  return p.bnq.q.bits != 0 ? launch_halo_impl<BN, EPI, true>(ta, tb, p, grid, smem, st) : launch_halo_impl<BN, EPI, false>(ta, tb, p, grid, smem, st);
 }
 
 std::atomic<int> g_use_tma_halo{1};   // bit 0: on; bit 1 (tests): take ragged images whatever the patch fill ratio

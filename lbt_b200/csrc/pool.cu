@@ -13,7 +13,7 @@ constexpr int kThreads = 256;
 struct PoolParams {
   int N, H, W, C, k, s, pt, pl, OH, OW;
   uint32_t c4;  // C / 4
-  FastDiv d_c4, d_W, d_H, d_OW, d_OH, d_s;
+  FastDiv d_c4, d_W, d_H, d_OW, d_OH, d_s, d_lanes;   // d_lanes: c4 / J of the multi-group backward kernel
 };
 
 // V = 4: a thread owns 4 consecutive channels (C % 4 == 0, 16-byte aligned tensors); V = 1: one channel (any C — the
@@ -174,14 +174,18 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_k_kernel(const float* __
 }
 
 // Backward for windows with ceil(K / s) <= 2 per axis (K <= 2 * s): at most 2 x 2 windows cover an input pixel.
-template <int K>
+// J: float4 channel groups per thread.  The window geometry (a dozen fast divisions) depends on the pixel only, so a thread that
+// owns J groups of one pixel pays it once (ncu of the J = 1 version on ResNet-18's stem: 57 instructions per element, issue-bound
+// at 0.35 of the HBM roofline); the c4 / J lanes of a pixel read neighbouring 16-byte groups, i.e. whole sectors.
+template <int K, int J>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_k_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
                                                                   float* __restrict__ dx, const PoolParams p, size_t total) {
   pdl_trigger();
   pdl_wait();
+  const uint32_t lanes = p.c4 / J;   // threads per pixel; thread `cq` owns groups cq, cq + lanes, ...
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
-    uint32_t pix = fastdiv((uint32_t)i, p.d_c4);
-    const uint32_t c = (uint32_t)i - pix * p.c4;
+    uint32_t pix = J == 1 ? fastdiv((uint32_t)i, p.d_c4) : fastdiv((uint32_t)i, p.d_lanes);
+    const uint32_t cq = (uint32_t)i - pix * lanes;
     uint32_t t = fastdiv(pix, p.d_W);
     const int iw = (int)(pix - t * (uint32_t)p.W);
     const int n = (int)fastdiv(t, p.d_H);
@@ -190,10 +194,9 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_k_kernel(const float* __
     const int oh_lo = th - K + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(th - K + p.s), p.d_s);
     const int ow_lo = tw - K + 1 <= 0 ? 0 : (int)fastdiv((uint32_t)(tw - K + p.s), p.d_s);
     const int oh_hi = min(p.OH - 1, (int)fastdiv((uint32_t)th, p.d_s)), ow_hi = min(p.OW - 1, (int)fastdiv((uint32_t)tw, p.d_s));
-    uchar4 wv[4];
-    float4 gv[4];
     bool ok[4];
     unsigned char tap[4];
+    size_t o[4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -201,22 +204,31 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_k_kernel(const float* __
         const int oh = oh_lo + a, ow = ow_lo + b;
         ok[2 * a + b] = oh <= oh_hi && ow <= ow_hi;
         tap[2 * a + b] = (unsigned char)((th - oh * p.s) * K + (tw - ow * p.s));
-        if (ok[2 * a + b]) {
-          const size_t o = ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c);
-          wv[2 * a + b] = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
-          gv[2 * a + b] = __ldg(reinterpret_cast<const float4*>(g) + o);
-        }
+        o[2 * a + b] = ok[2 * a + b] ? ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + cq) : 0;
       }
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 wv[J][4];
+    float4 gv[J][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)       // (oh, ow) ascending: the generic kernel's order of additions
-      if (ok[j]) {
-        if (wv[j].x == tap[j]) acc.x += gv[j].x;
-        if (wv[j].y == tap[j]) acc.y += gv[j].y;
-        if (wv[j].z == tap[j]) acc.z += gv[j].z;
-        if (wv[j].w == tap[j]) acc.w += gv[j].w;
-      }
-    reinterpret_cast<float4*>(dx)[i] = acc;
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (ok[q]) {
+          wv[j][q] = __ldg(reinterpret_cast<const uchar4*>(idx) + o[q] + j * lanes);
+          gv[j][q] = __ldg(reinterpret_cast<const float4*>(g) + o[q] + j * lanes);
+        }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)       // (oh, ow) ascending: the generic kernel's order of additions
+        if (ok[q]) {
+          if (wv[j][q].x == tap[q]) acc.x += gv[j][q].x;
+          if (wv[j][q].y == tap[q]) acc.y += gv[j][q].y;
+          if (wv[j][q].z == tap[q]) acc.z += gv[j][q].z;
+          if (wv[j][q].w == tap[q]) acc.w += gv[j][q].w;
+        }
+      __stcs(reinterpret_cast<float4*>(dx) + ((size_t)pix * p.c4 + cq + j * lanes), acc);
+    }
   }
 }
 
@@ -285,9 +297,17 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
   const size_t cap = (size_t)device_info().sm_count * 8;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (V == 4 && (k == 2 || k == 3) && k <= 2 * s && p.c4 % 4 == 0) {   // four channel groups per thread
+    const size_t total4 = total / 4, blocks4 = (total4 + kThreads - 1) / kThreads;
+    const unsigned grid4 = (unsigned)(blocks4 < cap ? blocks4 : cap);
+    p.d_lanes = make_fastdiv(p.c4 / 4);
+    if (k == 3) launch_pdl(maxpool_bwd_k_kernel<3, 4>, grid4, kThreads, 0, st, g, idx, dx, p, total4);
+    else launch_pdl(maxpool_bwd_k_kernel<2, 4>, grid4, kThreads, 0, st, g, idx, dx, p, total4);
+    return check_launch("lbt_maxpool_bwd");
+  }
   if (V == 1) launch_pdl(maxpool_bwd_kernel<1>, grid, kThreads, 0, st, g, idx, dx, p, total);
-  else if (k == 3 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<3>, grid, kThreads, 0, st, g, idx, dx, p, total);
-  else if (k == 2 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<2>, grid, kThreads, 0, st, g, idx, dx, p, total);
+  else if (k == 3 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<3, 1>, grid, kThreads, 0, st, g, idx, dx, p, total);
+  else if (k == 2 && k <= 2 * s) launch_pdl(maxpool_bwd_k_kernel<2, 1>, grid, kThreads, 0, st, g, idx, dx, p, total);
   else launch_pdl(maxpool_bwd_kernel<4>, grid, kThreads, 0, st, g, idx, dx, p, total);
   return check_launch("lbt_maxpool_bwd");
 }

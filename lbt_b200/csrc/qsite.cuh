@@ -235,10 +235,13 @@ __device__ __forceinline__ void bnq_load_noise(const BnqParams& b, const BnqStat
   }
 }
 
-template <bool FULL, bool MM>
+// PRE: the noise comes in `u4` (bnq_load_noise, issued by the caller ahead of its accumulator wait); else it is fetched here,
+// group by group between the arithmetic (what the register-bound gather kernels want; `pix` is only used then).
+template <bool FULL, bool MM, bool PRE>
 __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
-                                               const float* bias, uint32_t row, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
-                                               int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+                                               const float* bias, uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol,
+                                               uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+  const uint64_t inner = PRE ? 0ull : (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
   const QC& c = st.qc;
   // one multiply when no bias sits between the two scalings and neither product can leave the normal range
   const bool fold = bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(c.m)) < 60.0f;
@@ -246,7 +249,11 @@ __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st,
   float tm[16];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float un[4] = {u4[g].x, u4[g].y, u4[g].z, u4[g].w};
+    float4 u;
+    if (PRE) u = u4[g];
+    else if (b.q.noise) u = (FULL || (row_ok && 4u * g < ncol)) ? __ldg(reinterpret_cast<const float4*>(b.q.noise + inner) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    else u = philox_noise4((inner >> 2) + g, b.q.seed, st.off);
+    const float un[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int j = 4 * g + t;
@@ -289,25 +296,30 @@ __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st,
 }
 
 // `bias`: this chunk's 16 bias values (NULL: none); `u4`: the chunk's noise from bnq_load_noise.
+template <bool PRE>
+__device__ __forceinline__ void bnq_chunk_sel(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
+                                              const float* bias, uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
+                                              int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
+  const bool full = ncol == 16 && __all_sync(0xffffffffu, row_ok);
+  if (b.q.minmax) {
+    if (full) bnq_chunk_impl<true, true, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, true, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  } else {
+    if (full) bnq_chunk_impl<true, false, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    else bnq_chunk_impl<false, false, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  }
+}
 __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
                                           const float* bias, uint32_t row, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
                                           uint32_t bn, uint32_t tcol, int lane) {
-  const bool full = ncol == 16 && __all_sync(0xffffffffu, row_ok);
-  if (b.q.minmax) {
-    if (full) bnq_chunk_impl<true, true>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, true>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-  } else {
-    if (full) bnq_chunk_impl<true, false>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, false>(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-  }
+  bnq_chunk_sel<true>(b, st, v, u4, scale, bias, row, 0u, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
 }
-// Noise fetched here, right before use (callers that cannot place the loads ahead of their accumulator wait).
+// Noise fetched inside the chunk, right before use.
 __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
                                           uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
                                           uint32_t bn, uint32_t tcol, int lane) {
-  float4 u4[4];
-  bnq_load_noise(b, st, pix, row_ok, col, ncol, N, u4);
-  bnq_chunk(b, st, v, u4, scale, bias, row, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  float4 u4[4];   // not read
+  bnq_chunk_sel<false>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
 }
 
 // Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.

@@ -288,3 +288,24 @@ def test_fast_division_is_correctly_rounded():
         _lib.check(_lib.lib().lbt_test_fdiv(1 << 30, seed, bad.data_ptr(), first.data_ptr(), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert int(bad) == 0, (int(bad), first.tolist())
+
+
+@pytest.mark.parametrize('shape', [(5, 8, 12, 3), (3, 7, 5, 3), (64, 32, 32, 3)])
+@pytest.mark.parametrize('mode', [Q.ROUND_NEAREST, Q.ROUND_PHILOX])
+def test_image_mantissas_s9c3_equal_split_of_s16(shape, mode):
+    """LBT_MANT_S9C3 (the 16-byte pixels {hi x3, hi x3, lo x3, 0 x7} a first Conv2d_q consumes, k = 2*hi + lo) against the
+    plain s16 mantissas of the same call: both the 4-pixels-per-thread kernel (n_inner % 12 == 0) and the per-pixel one
+    (n_inner % 12 != 0), with the same counters."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(*shape, generator=g) * 1.7).cuda()
+    ib = torch.tensor(1, dtype=torch.int32, device='cuda')
+    c1, c2 = Q.new_counters('cuda'), Q.new_counters('cuda')
+    kw = dict(mode=mode, seed=9, offset=Q.make_offset(3, 1), want_fp32=False, update_range=False)
+    _, k16 = Q.quantize(x, 9, ib, mant_kind=Q.MANT_S16, counters=c1, **kw)
+    out = torch.empty(*shape[:-1], 16, dtype=torch.int8, device='cuda')
+    Q.quantize(x, 9, ib, mant_kind=Q.MANT_S9C3, counters=c2, out_mant=out, **kw)
+    k = k16.to(torch.int32)
+    hi, lo = k >> 1, k & 1
+    want = torch.cat([hi, hi, lo, torch.zeros(*shape[:-1], 7, dtype=torch.int32, device='cuda')], dim=-1).to(torch.int8)
+    assert torch.equal(out, want)
+    assert torch.equal(c1, c2)
