@@ -3,6 +3,8 @@
 // HBM-bound: forward reads each input once (k*k/s^2 re-reads hit L1/L2), writes the pooled tensor and one byte per
 // output (the winning tap); backward is a GATHER over the <= ceil(k/s)^2 windows that cover an input pixel, so it needs
 // no atomics and writes dX exactly once.  Ties go to the first maximum in (row, column) scan order.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lbt {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_k_kernel(const float* __
 // owns J groups of one pixel pays it once (ncu of the J = 1 version on ResNet-18's stem: 57 instructions per element, issue-bound
 // at 0.35 of the HBM roofline); the c4 / J lanes of a pixel read neighbouring 16-byte groups, i.e. whole sectors.
 template <int K, int J>
-__global__ void __launch_bounds__(kThreads) maxpool_bwd_k_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
+__global__ void __launch_bounds__(kThreads, J == 1 ? 1 : 2) maxpool_bwd_k_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
                                                                   float* __restrict__ dx, const PoolParams p, size_t total) {
   pdl_trigger();
   pdl_wait();
@@ -229,6 +231,67 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_k_kernel(const float* __
         }
       __stcs(reinterpret_cast<float4*>(dx) + ((size_t)pix * p.c4 + cq + j * lanes), acc);
     }
+  }
+}
+
+// Stride 2, K <= 4: one thread owns a 2 x 2 block of input pixels (padded coordinates th = 2a + {0, 1}, tw = 2b + {0, 1}) of one
+// channel group.  Exactly the windows (a - 1 .. a) x (b - 1 .. b) cover the block, so four gradient / index loads serve four
+// pixels (the per-pixel kernels fetch up to four windows for EACH pixel), the window geometry is computed once per block, and the
+// tap a window must have recorded for a pixel — r = py + 2 - 2 wy, q = px + 2 - 2 wx — is a compile-time constant.  Additions in
+// (oh, ow) ascending order like the other kernels: bit-identical.  ~10 instructions per element instead of 57 (3x3 / 2).
+template <int K>
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_s2_kernel(const float* __restrict__ g, const uint8_t* __restrict__ idx,
+                                                                   float* __restrict__ dx, const PoolParams p, uint32_t nBH, uint32_t nBW,
+                                                                   FastDiv d_nBW, FastDiv d_nBH, size_t total) {
+  pdl_trigger();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    uint32_t t = fastdiv((uint32_t)i, p.d_c4);
+    const uint32_t c = (uint32_t)i - t * p.c4;
+    uint32_t t2 = fastdiv(t, d_nBW);
+    const int b = (int)(t - t2 * nBW);
+    const int n = (int)fastdiv(t2, d_nBH);
+    const int a = (int)(t2 - (uint32_t)n * nBH);
+    uchar4 wv[4];
+    float4 gv[4];
+    bool ok[4];
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int oh = a - 1 + wy, ow = b - 1 + wx;
+        ok[2 * wy + wx] = (unsigned)oh < (unsigned)p.OH && (unsigned)ow < (unsigned)p.OW;
+        if (ok[2 * wy + wx]) {
+          const size_t o = ((((size_t)n * p.OH + oh) * p.OW + ow) * p.c4 + c);
+          wv[2 * wy + wx] = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
+          gv[2 * wy + wx] = __ldg(reinterpret_cast<const float4*>(g) + o);
+        }
+      }
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int ih = 2 * a + py - p.pt, iw = 2 * b + px - p.pl;
+        if ((unsigned)ih >= (unsigned)p.H || (unsigned)iw >= (unsigned)p.W) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+          for (int wx = 0; wx < 2; ++wx) {
+            constexpr int kNone = 255;
+            const int r = py + 2 - 2 * wy, q = px + 2 - 2 * wx;
+            const int tap = (r < K && q < K) ? r * K + q : kNone;   // compile-time after unrolling
+            if (tap != kNone && ok[2 * wy + wx]) {
+              const uchar4 w = wv[2 * wy + wx];
+              const float4 v = gv[2 * wy + wx];
+              if (w.x == tap) acc.x += v.x;
+              if (w.y == tap) acc.y += v.y;
+              if (w.z == tap) acc.z += v.z;
+              if (w.w == tap) acc.w += v.w;
+            }
+          }
+        __stcs(reinterpret_cast<float4*>(dx) + ((((size_t)n * p.H + ih) * p.W + iw) * p.c4 + c), acc);
+      }
   }
 }
 
@@ -297,12 +360,37 @@ extern "C" int lbt_maxpool_bwd(const float* g, const uint8_t* idx, int N, int H,
   const size_t cap = (size_t)device_info().sm_count * 8;
   const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (V == 4 && (k == 2 || k == 3) && k <= 2 * s && p.c4 % 4 == 0) {   // four channel groups per thread
-    const size_t total4 = total / 4, blocks4 = (total4 + kThreads - 1) / kThreads;
-    const unsigned grid4 = (unsigned)(blocks4 < cap ? blocks4 : cap);
-    p.d_lanes = make_fastdiv(p.c4 / 4);
-    if (k == 3) launch_pdl(maxpool_bwd_k_kernel<3, 4>, grid4, kThreads, 0, st, g, idx, dx, p, total4);
-    else launch_pdl(maxpool_bwd_k_kernel<2, 4>, grid4, kThreads, 0, st, g, idx, dx, p, total4);
+  static const int pool_blk = [] {   // A/B: LBT_POOL_BLOCK=0 keeps the per-pixel kernels for stride 2
+    const char* e = std::getenv("LBT_POOL_BLOCK");
+    return e ? std::atoi(e) : 1;
+  }();
+  if (V == 4 && s == 2 && (k == 2 || k == 3 || k == 4) && pad_top < 2 && pad_left < 2 && pool_blk) {
+    // blocks of padded rows th = 2a + {0,1}: a from 0 (pad < 2) to (pad + H - 1) / 2
+    const uint32_t nBH = (uint32_t)((pad_top + H - 1) / 2 + 1), nBW = (uint32_t)((pad_left + W - 1) / 2 + 1);
+    const size_t totalb = (size_t)N * nBH * nBW * p.c4;
+    if (totalb < (1ull << 31)) {
+      const size_t blocksb = (totalb + kThreads - 1) / kThreads;
+      const unsigned gridb = (unsigned)(blocksb < cap ? blocksb : cap);
+      const FastDiv dW = make_fastdiv(nBW), dH = make_fastdiv(nBH);
+      if (k == 2) launch_pdl(maxpool_bwd_s2_kernel<2>, gridb, kThreads, 0, st, g, idx, dx, p, nBH, nBW, dW, dH, totalb);
+      else if (k == 3) launch_pdl(maxpool_bwd_s2_kernel<3>, gridb, kThreads, 0, st, g, idx, dx, p, nBH, nBW, dW, dH, totalb);
+      else launch_pdl(maxpool_bwd_s2_kernel<4>, gridb, kThreads, 0, st, g, idx, dx, p, nBH, nBW, dW, dH, totalb);
+      return check_launch("lbt_maxpool_bwd");
+    }
+  }
+  static const int pool_j = [] {   // channel groups per thread (A/B: LBT_POOL_J = 1, 2 or 4)
+    const char* e = std::getenv("LBT_POOL_J");
+    return e ? std::atoi(e) : 2;
+  }();
+  const int J = (pool_j >= 4 && p.c4 % 4 == 0) ? 4 : ((pool_j >= 2 && p.c4 % 2 == 0) ? 2 : 1);
+  if (V == 4 && (k == 2 || k == 3) && k <= 2 * s && J > 1) {   // several channel groups per thread
+    const size_t totalj = total / J, blocksj = (totalj + kThreads - 1) / kThreads;
+    const unsigned gridj = (unsigned)(blocksj < cap ? blocksj : cap);
+    p.d_lanes = make_fastdiv(p.c4 / J);
+    if (k == 3 && J == 4) launch_pdl(maxpool_bwd_k_kernel<3, 4>, gridj, kThreads, 0, st, g, idx, dx, p, totalj);
+    else if (k == 3) launch_pdl(maxpool_bwd_k_kernel<3, 2>, gridj, kThreads, 0, st, g, idx, dx, p, totalj);
+    else if (J == 4) launch_pdl(maxpool_bwd_k_kernel<2, 4>, gridj, kThreads, 0, st, g, idx, dx, p, totalj);
+    else launch_pdl(maxpool_bwd_k_kernel<2, 2>, gridj, kThreads, 0, st, g, idx, dx, p, totalj);
     return check_launch("lbt_maxpool_bwd");
   }
   if (V == 1) launch_pdl(maxpool_bwd_kernel<1>, grid, kThreads, 0, st, g, idx, dx, p, total);
