@@ -257,6 +257,19 @@ int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C,
                       int alpha, int k_splits, void* stream);
 
 /*
+ * Weight gradient of a FIRST convolution (3-channel 9-bit image, LBT_MANT_S9C3 pixels x16[N,H,W,16]) of stride 2 with
+ * <= 8 x 8 taps and 64 output channels (the 7x7/2 ImageNet stem; tf.gradients(y, W, gradq), dynamic_fixed_point.py:207,
+ * 302 for models.py's first Conv2d_q): the image is re-packed into work8 (lbt_stem_pack8_bytes(N, H, OW) bytes: 8-byte
+ * pixels {hi0,hi1,hi2,0,lo0,lo1,lo2,0} with zero margins) and every filter row of a 128-pixel patch then arrives as ONE
+ * tiled TMA load.  acc8[((r*8 + s)*8 + b), co] (int64[512, Cout], zeroed by the caller) += sum over pixels of byte b of
+ * tap (r, s) times g; the caller combines dW[r,s,c,co] = 2 * acc8[r,s,c,co] + acc8[r,s,4+c,co].  g[N*OH*OW, Cout] s8.
+ * LBT_EUNSUPPORTED for other shapes (odd H, Cout != 64, ...): use lbt_conv_i8_wgrad on the 16-byte pixels.
+ */
+size_t lbt_stem_pack8_bytes(int N, int H, int OW);
+int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const int8_t* g, int Cout, int kh, int kw, int pad_top,
+                         int pad_left, int OH, int OW, int8_t* work8, int64_t* acc8, void* stream);
+
+/*
  * Mantissas wider than 8 bits (the 16-bit gradients of BASELINE config 5) as two tensor-core operands:
  * k = 256 * hi + lo with hi = k >> 8 (s8) and lo = k & 255 (u8).  The GEMMs run once per half and add
  * alpha * acc into the int64 accumulator with alpha = 256 and 1 (exact).

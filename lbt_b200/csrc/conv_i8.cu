@@ -857,5 +857,7 @@ extern "C" int lbt_conv_debug_error(void) {
   cudaMemcpyToSymbol(g_conv_error, &zero, sizeof(int));
   const int h = conv_halo_debug_error();
   if (h > 0) v |= h;
+  const int st = conv_stem_debug_error();
+  if (st > 0) v |= st;
   return v;
 }

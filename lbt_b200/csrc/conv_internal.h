@@ -30,6 +30,7 @@ int conv_ldg_run(const void* src, int src_kind, int N, int SH, int SW, int C, co
 bool conv_halo_applies(int N, int OH, int OW, int C, int Cout, int kh, int kw, int sh, int sw);
 void conv_halo_enable(int mode);   // bit 0: on, bit 1: ignore the patch fill-ratio rule (tests)
 int conv_halo_debug_error();
+int conv_stem_debug_error();   // conv_stem.cu (first-layer weight gradient)
 int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                   int kw, int pt, int pl, int OH, int OW, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
                   float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream,

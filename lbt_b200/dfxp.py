@@ -489,6 +489,9 @@ def _dgrad_classes_ok(layer, Cin, Cout, kh, kw, sh, sw):
             not _gather_ok(Cout, Cin, kh, kw))
 
 
+# First-layer weight gradient through lbt_conv_i8_wgrad_c3 (LBT_STEM_WGRAD=0: the general kernel on the 16-byte pixels).
+STEM_WGRAD = os.environ.get('LBT_STEM_WGRAD', '1') != '0'
+
 # LBT_MANT_PREPARED (include/lbt.h): let the convolution kernels copy a filter packed by lbt_param_prep before they wait for their
 # predecessor.  Measured on B200: the kernels' own time drops 3 % but the step does not move (same-box A/B 1.4347 vs 1.4345 ms),
 # so it is off unless LBT_W_PREFETCH=1.
@@ -639,13 +642,29 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
           if xkind == Q.MANT_S9C3:
               if not _implicit_ok(Cout, 1, 1):
                   raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
-              # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
-              acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
-              _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
-                        sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(),
-                        meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
-              a = acc16.view(kh * kw, 16, Cout)
-              acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+              done = False
+              if STEM_WGRAD and sh == 2 and sw == 2 and kh <= 8 and kw <= 8 and Cout == 64 and H % 2 == 0:
+                  # the 7x7/2 ImageNet stem: 8-byte pixels {hi, 0, lo, 0}, one tiled TMA load per filter row (conv_stem.cu);
+                  # dW[r, s, c] = 2 * acc8[r, s, c] + acc8[r, s, 4 + c]
+                  nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
+                  work = getattr(layer, '_stem_work8', None)
+                  if work is None or work.numel() != nb or work.device != xm.device:
+                      work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
+                  acc8 = rt.zeros_i64(512 * Cout, dev)
+                  done = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g2), Cout, kh, kw, pt, pl, OH, OW,
+                                       _lib.ptr(work), _lib.ptr(acc8), _lib.stream(),
+                                       meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + nb + M * Cout + 8 * 512 * Cout))
+                  if done:
+                      a = acc8.view(8, 8, 8, Cout)[:kh, :kw]
+                      acc = (2 * a[:, :, 0:3] + a[:, :, 4:7]).reshape(Kf, Cout).contiguous()
+              if not done:
+                  # 16 pseudo-channels {hi, hi, lo, 0}: dW[c] = acc[hi c] + acc[hi' c] + acc[lo c]  (k = 2*hi + lo)
+                  acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
+                  _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,
+                            sh, sw, pt, pl, OH, OW, _lib.ptr(acc16), 1, 0, _lib.stream(),
+                            meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
+                  a = acc16.view(kh * kw, 16, Cout)
+                  acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
           elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
               # implicit wgrad: X blocks and G blocks feed the tensor cores MN-major, no transposes
               _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw,

@@ -496,3 +496,44 @@ def test_strided_dgrad_parity_classes_equal_im2col_and_exact(N, H, W, Cin, Cout,
     if addend is not None:
         want = want + addend
     assert torch.equal(res[True], want.contiguous())
+
+
+@pytest.mark.parametrize('N,H,W,k', [(2, 32, 32, 7), (3, 30, 34, 7), (2, 64, 48, 7), (2, 18, 22, 3), (1, 20, 16, 5), (2, 224, 224, 7)])
+def test_stem_wgrad_c3_equals_general_kernel_and_exact_sum(N, H, W, k):
+    """lbt_conv_i8_wgrad_c3 (8-byte pixels, one tiled TMA load per filter row, all accumulator tiles resident) against
+    lbt_conv_i8_wgrad on the 16-byte pixels and against the exact integer sum (fp64 conv2d_weight on the CPU for the
+    small shapes): dW[r,s,c,co] = sum k[n, 2oh+r-pt, 2ow+s-pl, c] * g[n,oh,ow,co], k = 2*hi + lo.  Ragged patches included."""
+    from lbt_b200 import _lib, quantizer as Q
+    Cout, s = 64, 2
+    OH, pt, _ = D.same_pad(H, k, s)
+    OW, pl, _ = D.same_pad(W, k, s)
+    gen = torch.Generator().manual_seed(N * 1000 + H + k)
+    kx = torch.randint(-256, 256, (N, H, W, 3), generator=gen, dtype=torch.int32)
+    hi, lo = kx >> 1, kx & 1
+    x16 = torch.cat([hi, hi, lo, torch.zeros(N, H, W, 7, dtype=torch.int32)], dim=-1).to(torch.int8).cuda()
+    g = torch.randint(-128, 128, (N * OH * OW, Cout), generator=gen, dtype=torch.int32).to(torch.int8).cuda()
+    nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
+    work = torch.empty(nb, dtype=torch.int8, device='cuda')
+    acc8 = torch.zeros(512, Cout, dtype=torch.int64, device='cuda')
+    ok = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(x16), N, H, W, _lib.ptr(g), Cout, k, k, pt, pl, OH, OW, _lib.ptr(work),
+                       _lib.ptr(acc8), _lib.stream())
+    assert ok, 'lbt_conv_i8_wgrad_c3 declined a stem shape'
+    torch.cuda.synchronize()
+    assert _lib.lib().lbt_conv_debug_error() == 0
+    a = acc8.view(8, 8, 8, Cout)[:k, :k]
+    got = (2 * a[:, :, 0:3] + a[:, :, 4:7]).reshape(k * k * 3, Cout)
+    acc16 = torch.zeros(k * k * 16, Cout, dtype=torch.int64, device='cuda')
+    _lib.call('lbt_conv_i8_wgrad', _lib.ptr(x16), Q.MANT_S8, N, H, W, 16, _lib.ptr(g), Q.MANT_S8, Cout, k, k, s, s, pt, pl, OH, OW,
+              _lib.ptr(acc16), 1, 0, _lib.stream())
+    b = acc16.view(k * k, 16, Cout)
+    want = (b[:, 0:3] + b[:, 3:6] + b[:, 6:9]).reshape(k * k * 3, Cout)
+    assert torch.equal(got, want)
+    if N * H * W <= 8192:
+        xp = torch.zeros(N, 3, H + k, W + k, dtype=torch.float64)
+        xp[:, :, pt:pt + H, pl:pl + W] = kx.permute(0, 3, 1, 2).double()
+        gg = g.cpu().double().view(N, OH, OW, Cout).permute(0, 3, 1, 2)
+        cols = torch.nn.functional.unfold(xp, (k, k), stride=s)[:, :, :]          # [N, 3*k*k, L] over the padded image
+        Lw = (W + k - k) // s + 1
+        cols = cols.view(N, 3, k, k, -1, Lw)[:, :, :, :, :OH, :OW]                 # [N, c, r, s, oh, ow]
+        ref = torch.einsum('ncrsyx,nkyx->rsck', cols, gg).reshape(k * k * 3, Cout)
+        assert torch.equal(got.cpu().double(), ref)
