@@ -262,12 +262,15 @@ int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C,
  * 302 for models.py's first Conv2d_q): the image is re-packed into work8 (lbt_stem_pack8_bytes(N, H, OW) bytes: 8-byte
  * pixels {hi0,hi1,hi2,0,lo0,lo1,lo2,0} with zero margins) and every filter row of a 128-pixel patch then arrives as ONE
  * tiled TMA load.  acc8[((r*8 + s)*8 + b), co] (int64[512, Cout], zeroed by the caller) += sum over pixels of byte b of
- * tap (r, s) times g; the caller combines dW[r,s,c,co] = 2 * acc8[r,s,c,co] + acc8[r,s,4+c,co].  g[N*OH*OW, Cout] s8.
- * LBT_EUNSUPPORTED for other shapes (odd H, Cout != 64, ...): use lbt_conv_i8_wgrad on the 16-byte pixels.
+ * tap (r, s) times g, times alpha; the caller combines dW[r,s,c,co] = 2 * acc8[r,s,c,co] + acc8[r,s,4+c,co].
+ * g[N*OH*OW, Cout] s8 | u8 (g_kind; the byte planes of a 16-bit gradient: alpha = 256 | 1, repack = 0 on the second call:
+ * work8 still holds this step's image).  LBT_EUNSUPPORTED for other shapes (odd H, Cout != 64, ...): use
+ * lbt_conv_i8_wgrad on the 16-byte pixels.
  */
 size_t lbt_stem_pack8_bytes(int N, int H, int OW);
-int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const int8_t* g, int Cout, int kh, int kw, int pad_top,
-                         int pad_left, int OH, int OW, int8_t* work8, int64_t* acc8, void* stream);
+int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const void* g, int g_kind, int Cout, int kh, int kw,
+                         int pad_top, int pad_left, int OH, int OW, int8_t* work8, int repack, int64_t* acc8, int alpha,
+                         void* stream);
 
 /*
  * Mantissas wider than 8 bits (the 16-bit gradients of BASELINE config 5) as two tensor-core operands:

@@ -46,6 +46,7 @@ struct StemParams {
   int pt;
   uint32_t kh, kw, N;              // filter rows / columns, output channels
   long long* acc8;
+  int alpha;                       // acc8 += alpha * sum (256 | 1: the byte planes of a 16-bit gradient)
   uint32_t idesc;
 };
 
@@ -192,7 +193,7 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t ncol = min(16u, p.N - (uint32_t)c);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < (int)ncol && v[j] != 0u) atomicAdd(o + j, (unsigned long long)(long long)(int)v[j]);
+              if (j < (int)ncol && v[j] != 0u) atomicAdd(o + j, (unsigned long long)((long long)(int)v[j] * (long long)p.alpha));
           }
         }
       }
@@ -226,9 +227,11 @@ extern "C" size_t lbt_stem_pack8_bytes(int N, int H, int OW) {
   return (size_t)N * H * (size_t)(2 * OW + 6) * 8;
 }
 
-extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const int8_t* g, int Cout, int kh, int kw, int pad_top,
-                                    int pad_left, int OH, int OW, int8_t* work8, int64_t* acc8, void* stream) {
+extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const void* g, int g_kind, int Cout, int kh, int kw,
+                                    int pad_top, int pad_left, int OH, int OW, int8_t* work8, int repack, int64_t* acc8, int alpha,
+                                    void* stream) {
   if (!x16 || !g || !work8 || !acc8) return LBT_EINVAL;
+  if (g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || OH <= 0 || OW <= 0 || pad_top < 0 || pad_left < 0) return LBT_EINVAL;
   // shapes: stride 2 (implied), <= 8 x 8 taps, 64 output channels, an even number of input rows (parity split), and every
   // window inside the padded row
@@ -259,9 +262,10 @@ extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, cons
   p.kw = (uint32_t)kw;
   p.N = (uint32_t)Cout;
   p.acc8 = reinterpret_cast<long long*>(acc8);
-  p.idesc = tc::make_idesc_i8(true, true, true, true, 64, 128);
+  p.alpha = alpha;
+  p.idesc = tc::make_idesc_i8(true, g_kind == LBT_MANT_S8, true, true, 64, 128);
 
-  {  // the 8-byte image
+  if (repack) {  // the 8-byte image (repack == 0: work8 still holds it from the previous call of this step)
     const size_t total = (size_t)N * H * Wp;
     const size_t blocks = (total + 255) / 256, cap = (size_t)di.sm_count * 16;
     launch_pdl(stem_pack8_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, st, reinterpret_cast<const uint4*>(x16), H, W, Wp,
@@ -286,7 +290,7 @@ extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, cons
     cuuint64_t gstr[3] = {64, (cuuint64_t)OW * 64, (cuuint64_t)OH * OW * 64};
     cuuint32_t box[4] = {64, (cuuint32_t)kPatchOW, (cuuint32_t)kPatchOH, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc_tiled(&tg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(g), gdim, gstr, box, estr,
+    CUresult r = enc_tiled(&tg, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(g), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return LBT_EUNSUPPORTED;

@@ -651,8 +651,8 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
                   if work is None or work.numel() != nb or work.device != xm.device:
                       work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
                   acc8 = rt.zeros_i64(512 * Cout, dev)
-                  done = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g2), Cout, kh, kw, pt, pl, OH, OW,
-                                       _lib.ptr(work), _lib.ptr(acc8), _lib.stream(),
+                  done = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw, pt, pl,
+                                       OH, OW, _lib.ptr(work), 1, _lib.ptr(acc8), 1, _lib.stream(),
                                        meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + nb + M * Cout + 8 * 512 * Cout))
                   if done:
                       a = acc8.view(8, 8, 8, Cout)[:kh, :kw]
@@ -802,13 +802,30 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw,
         if xkind == Q.MANT_S9C3:
             if not _implicit_ok(Cout, 1, 1):
                 raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
-            acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
-            for g_, kind, alpha in halves:
-                _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
-                          pt, pl, OH, OW, _lib.ptr(acc16), alpha, 0, _lib.stream(),
-                          meta=dict(ops=M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
-            a = acc16.view(kh * kw, 16, Cout)
-            acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
+            done = False
+            if STEM_WGRAD and sh == 2 and sw == 2 and kh <= 8 and kw <= 8 and Cout == 64 and H % 2 == 0:
+                # the 7x7/2 ImageNet stem (conv_stem.cu): both byte planes against ONE re-packed copy of the image
+                nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
+                work = getattr(layer, '_stem_work8', None)
+                if work is None or work.numel() != nb or work.device != xm.device:
+                    work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
+                acc8 = rt.zeros_i64(512 * Cout, dev)
+                done = True
+                for i, (g_, kind, alpha) in enumerate(halves):
+                    done = done and _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g_), kind, Cout, kh, kw, pt,
+                                                  pl, OH, OW, _lib.ptr(work), 1 if i == 0 else 0, _lib.ptr(acc8), alpha, _lib.stream(),
+                                                  meta=dict(ops=M * Cout * Kf, bytes=(N * H * W * 16 + nb if i == 0 else 0) + nb + M * Cout))
+                if done:
+                    a = acc8.view(8, 8, 8, Cout)[:kh, :kw]
+                    acc = (2 * a[:, :, 0:3] + a[:, :, 4:7]).reshape(Kf, Cout).contiguous()
+            if not done:
+                acc16 = rt.zeros_i64(kh * kw * 16 * Cout, dev).view(kh * kw * 16, Cout)
+                for g_, kind, alpha in halves:
+                    _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), Q.MANT_S8, N, H, W, 16, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
+                              pt, pl, OH, OW, _lib.ptr(acc16), alpha, 0, _lib.stream(),
+                              meta=dict(ops=M * Cout * Kf, bytes=N * H * W * 16 + M * Cout + 8 * kh * kw * 16 * Cout))
+                a = acc16.view(kh * kw, 16, Cout)
+                acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
         elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
             for g_, kind, alpha in halves:
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,

@@ -515,9 +515,19 @@ def test_stem_wgrad_c3_equals_general_kernel_and_exact_sum(N, H, W, k):
     nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
     work = torch.empty(nb, dtype=torch.int8, device='cuda')
     acc8 = torch.zeros(512, Cout, dtype=torch.int64, device='cuda')
-    ok = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(x16), N, H, W, _lib.ptr(g), Cout, k, k, pt, pl, OH, OW, _lib.ptr(work),
-                       _lib.ptr(acc8), _lib.stream())
+    ok = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(x16), N, H, W, _lib.ptr(g), Q.MANT_S8, Cout, k, k, pt, pl, OH, OW,
+                       _lib.ptr(work), 1, _lib.ptr(acc8), 1, _lib.stream())
     assert ok, 'lbt_conv_i8_wgrad_c3 declined a stem shape'
+    # a second, unsigned gradient plane with alpha = 3 into its own sums, against the work buffer of the first call
+    gu = torch.randint(0, 256, (N * OH * OW, Cout), generator=gen, dtype=torch.int32).to(torch.uint8).cuda()
+    acc8u = torch.zeros(512, Cout, dtype=torch.int64, device='cuda')
+    assert _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(x16), N, H, W, _lib.ptr(gu), Q.MANT_U8, Cout, k, k, pt, pl, OH, OW,
+                         _lib.ptr(work), 0, _lib.ptr(acc8u), 3, _lib.stream())
+    acc16u = torch.zeros(k * k * 16, Cout, dtype=torch.int64, device='cuda')
+    _lib.call('lbt_conv_i8_wgrad', _lib.ptr(x16), Q.MANT_S8, N, H, W, 16, _lib.ptr(gu), Q.MANT_U8, Cout, k, k, s, s, pt, pl, OH, OW,
+              _lib.ptr(acc16u), 3, 0, _lib.stream())
+    au, bu = acc8u.view(8, 8, 8, Cout)[:k, :k], acc16u.view(k * k, 16, Cout)
+    assert torch.equal((2 * au[:, :, 0:3] + au[:, :, 4:7]).reshape(k * k * 3, Cout), (bu[:, 0:3] + bu[:, 3:6] + bu[:, 6:9]).reshape(k * k * 3, Cout))
     torch.cuda.synchronize()
     assert _lib.lib().lbt_conv_debug_error() == 0
     a = acc8.view(8, 8, 8, Cout)[:k, :k]
