@@ -268,6 +268,9 @@ int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C,
  * lbt_conv_i8_wgrad on the 16-byte pixels.
  */
 size_t lbt_stem_pack8_bytes(int N, int H, int OW);
+/* The re-pack alone (what lbt_conv_i8_wgrad_c3 does first when repack != 0): a caller that runs it during the forward pass,
+ * beside the first convolution, takes it off the end of the step. */
+int lbt_stem_pack8(const int8_t* x16, int N, int H, int W, int OW, int pad_left, int8_t* work8, void* stream);
 int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const void* g, int g_kind, int Cout, int kh, int kw,
                          int pad_top, int pad_left, int OH, int OW, int8_t* work8, int repack, int64_t* acc8, int alpha,
                          void* stream);

@@ -744,6 +744,12 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
   bn_stamp(1);
   __syncthreads();
   bn_stamp(2);
+  const uint32_t nv = p.t.n_vec;   // words (4 elements) per row
+  const uint32_t* const bkg = reinterpret_cast<const uint32_t*>(p.kg1);
+  const uint32_t* const bk1 = reinterpret_cast<const uint32_t*>(p.k1);
+  uint32_t* const bgm = reinterpret_cast<uint32_t*>(p.g_mant);
+  uint32_t* const bgl = reinterpret_cast<uint32_t*>(p.g_mant_lo);
+  float4* const bdx = reinterpret_cast<float4*>(p.dx);
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
     const uint32_t v = chk * kThreads + threadIdx.x;
@@ -764,28 +770,41 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
       uq[0] = t.x; uq[1] = t.y; uq[2] = t.z; uq[3] = t.w;
     }
     const uint32_t r0 = rg * p.t.rows_per_group, r1 = min(r0 + p.t.rows_per_group, (uint32_t)p.t.n_outer);   // rows: 32-bit (make_tiling)
-    for (uint32_t r = r0; r < r1; r += kRows) {
+    // One group of kRows rows.  FULL (all rows of the group exist — every group but a tile's last): no per-row predicates.
+    // Every tensor is addressed as base + 4-element word index (32-bit, one IMAD.WIDE per access).
+    auto group = [&](auto full_tag, const uint32_t r) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const uint32_t w0 = r * nv + v;
       uint2 wg[kRows];
       uint32_t w1[kRows];
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
-        if (r + i < r1) {
-          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
-          if (WIDE) wg[i] = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(p.kg1) + idx));
-          else wg[i].x = __ldcs(reinterpret_cast<const uint32_t*>(reinterpret_cast<const int8_t*>(p.kg1) + idx));
-          w1[i] = __ldcs(reinterpret_cast<const uint32_t*>(p.k1 + idx));
+        if (FULL || r + i < r1) {
+          const uint32_t w = w0 + (uint32_t)i * nv;
+          if (WIDE) wg[i] = __ldcs(reinterpret_cast<const uint2*>(bkg) + w);
+          else wg[i].x = __ldcs(bkg + w);
+          w1[i] = __ldcs(bk1 + w);
         }
+      if (r + 2 * kRows <= r1) {   // the next group, whole: into L1 while this one is computed
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          const uint32_t w = w0 + (uint32_t)(kRows + i) * nv;
+          prefetch_l1(WIDE ? reinterpret_cast<const void*>(reinterpret_cast<const uint2*>(bkg) + w) : reinterpret_cast<const void*>(bkg + w));
+          prefetch_l1(bk1 + w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kRows; ++i)
+          if (r + kRows + i < r1) {
+            const uint32_t w = w0 + (uint32_t)(kRows + i) * nv;
+            prefetch_l1(WIDE ? reinterpret_cast<const void*>(reinterpret_cast<const uint2*>(bkg) + w) : reinterpret_cast<const void*>(bkg + w));
+            prefetch_l1(bk1 + w);
+          }
+      }
 #pragma unroll
       for (int i = 0; i < kRows; ++i)
-        if (r + kRows + i < r1) {
-          const size_t idx = 4 * (size_t)((r + kRows + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
-          prefetch_l1(reinterpret_cast<const int8_t*>(p.kg1) + (WIDE ? 2 : 1) * idx);
-          prefetch_l1(p.k1 + idx);
-        }
-#pragma unroll
-      for (int i = 0; i < kRows; ++i)
-        if (r + i < r1) {
-          const size_t idx = 4 * (size_t)((r + i) * p.t.n_vec + v);   // element / 4 fits 32 bits
+        if (FULL || r + i < r1) {
+          const uint32_t w = w0 + (uint32_t)i * nv;
           float kgf[4], k1f[4];
           if (WIDE) dec4_f_s16(wg[i], kgf);
           else dec4_f(wg[i].x, kgf);
@@ -798,7 +817,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
             // batch-norm VJP through mean and biased variance (tf.gradients of dfxp:616); one rounding per operation
             o[j] = fdiv_fast(__fsub_rn(__fsub_rn(gq, mg[j]), __fmul_rn(xhat, mgx[j])), den[j], rden[j]);
           }
-          if (has_dx) *reinterpret_cast<float4*>(p.dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
+          if (has_dx) bdx[w] = make_float4(o[0], o[1], o[2], o[3]);
           if (gq_on) {                                                        // the convolution's gradq, dfxp:300
             float tq[4];
 #pragma unroll
@@ -806,13 +825,17 @@ __global__ void __launch_bounds__(kThreads) bn_bwd2_kernel(const Bwd2Params p) {
             if (q16) {   // 9..16-bit gradient: the two byte planes the tensor cores consume (no separate split pass)
               uint32_t hi, lo;
               tm_pack4_hilo(tq, hi, lo);
-              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = hi;
-              *reinterpret_cast<uint32_t*>(p.g_mant_lo + idx) = lo;
+              bgm[w] = hi;
+              bgl[w] = lo;
             } else {
-              *reinterpret_cast<uint32_t*>(p.g_mant + idx) = tm_pack4(tq);
+              bgm[w] = tm_pack4(tq);
             }
           }
         }
+    };
+    for (uint32_t r = r0; r < r1; r += kRows) {
+      if (r + kRows <= r1) group(std::true_type{}, r);
+      else group(std::false_type{}, r);
     }
   }
   bn_stamp(3);

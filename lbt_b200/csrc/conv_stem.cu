@@ -227,6 +227,20 @@ extern "C" size_t lbt_stem_pack8_bytes(int N, int H, int OW) {
   return (size_t)N * H * (size_t)(2 * OW + 6) * 8;
 }
 
+extern "C" int lbt_stem_pack8(const int8_t* x16, int N, int H, int W, int OW, int pad_left, int8_t* work8, void* stream) {
+  if (!x16 || !work8) return LBT_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || OW <= 0 || pad_left < 0) return LBT_EINVAL;
+  const int Wp = 2 * OW + 6;
+  if (pad_left + W > Wp) return LBT_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x16) & 15) || (reinterpret_cast<uintptr_t>(work8) & 15)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const size_t total = (size_t)N * H * Wp;
+  const size_t blocks = (total + 255) / 256, cap = (size_t)device_info().sm_count * 16;
+  launch_pdl(stem_pack8_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<const uint4*>(x16), H, W, Wp, pad_left, total, reinterpret_cast<uint2*>(work8));
+  return check_launch("lbt_stem_pack8");
+}
+
 extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, const void* g, int g_kind, int Cout, int kh, int kw,
                                     int pad_top, int pad_left, int OH, int OW, int8_t* work8, int repack, int64_t* acc8, int alpha,
                                     void* stream) {
@@ -265,12 +279,8 @@ extern "C" int lbt_conv_i8_wgrad_c3(const int8_t* x16, int N, int H, int W, cons
   p.alpha = alpha;
   p.idesc = tc::make_idesc_i8(true, g_kind == LBT_MANT_S8, true, true, 64, 128);
 
-  if (repack) {  // the 8-byte image (repack == 0: work8 still holds it from the previous call of this step)
-    const size_t total = (size_t)N * H * Wp;
-    const size_t blocks = (total + 255) / 256, cap = (size_t)di.sm_count * 16;
-    launch_pdl(stem_pack8_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, st, reinterpret_cast<const uint4*>(x16), H, W, Wp,
-               pad_left, total, reinterpret_cast<uint2*>(work8));
-    int rc = check_launch("lbt_conv_i8_wgrad_c3 (pack8)");
+  if (repack) {  // the 8-byte image (repack == 0: work8 already holds it — lbt_stem_pack8 or the previous call of this step)
+    int rc = lbt_stem_pack8(x16, N, H, W, OW, pad_left, work8, stream);
     if (rc) return rc;
   }
   CUtensorMap tx, tg;

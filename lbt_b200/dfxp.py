@@ -571,6 +571,57 @@ def _conv_quantize_input(layer, x, geom):
     return xm, xkind
 
 
+def _stem_applies(geom):
+    """Shapes lbt_conv_i8_wgrad_c3 takes (the 7x7/2 ImageNet stem): stride 2, <= 8 x 8 taps, 64 filters, even H."""
+    N, H, W, Cin, Cout, kh, kw, sh, sw = geom[:9]
+    return STEM_WGRAD and sh == 2 and sw == 2 and kh <= 8 and kw <= 8 and Cout == 64 and H % 2 == 0
+
+
+def _stem_work(layer, geom, dev):
+    N, H, OW = geom[0], geom[1], geom[12]
+    nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
+    work = getattr(layer, '_stem_work8', None)
+    if work is None or work.numel() != nb or work.device != torch.device(dev):
+        work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
+        layer._stem_packed = False
+    return work, nb
+
+
+def _stem_prepack(layer, xm, xkind, geom):
+    """Forward pass of a first convolution inside a Trainer step: re-pack the image for lbt_conv_i8_wgrad_c3 NOW, on the side
+    stream beside the convolution, instead of at the very end of the step in front of the weight-gradient kernel."""
+    rt = layer.qX.runtime
+    if (xkind != Q.MANT_S9C3 or not _stem_applies(geom) or not torch.is_grad_enabled() or not layer.weight.requires_grad or
+            not (rt.overlap and rt._arena_on and rt.grad_sink is not None and rt.grad_sink.active and _lib.profiler is None)):
+        return
+    N, H, W = geom[:3]
+    dev = xm.device
+    work, _ = _stem_work(layer, geom, dev)
+    main, side = torch.cuda.current_stream(dev), rt.side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        layer._stem_packed = _lib.try_call('lbt_stem_pack8', _lib.ptr(xm), N, H, W, geom[12], geom[10], _lib.ptr(work), _lib.stream(),
+                                           meta=dict(bytes=N * H * W * 16 + work.numel()))
+    xm.record_stream(side)
+    rt._side_pending = True
+
+
+def _flush_head_beside(rt, fork, main, side):
+    """Backward of the FIRST layer, before its weight-gradient kernel goes to the side stream: every gradient collected so far
+    is finalised on the main stream (which has nothing else left) while that last kernel runs (GradSink.flush_head)."""
+    sink = rt.grad_sink
+    if sink is None or not sink.active:
+        return
+    if fork:
+        ev = torch.cuda.Event()
+        ev.record(side)                      # every earlier weight-gradient kernel
+        with torch.cuda.stream(main):
+            main.wait_event(ev)
+            sink.flush_head()
+    else:
+        sink.flush_head()
+
+
 def _conv_params(layer, weight, bias):
     """(prep entry or None, weight mantissas or None, quantised bias or None) for this step."""
     if not weight.is_contiguous():      # HWIO memory order is part of the semantics (noise broadcasts over kh)
@@ -643,16 +694,16 @@ def _conv_backward(layer, geom, xm, xkind, wm, prep, gm, need_dx, need_dw, need_
               if not _implicit_ok(Cout, 1, 1):
                   raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
               done = False
-              if STEM_WGRAD and sh == 2 and sw == 2 and kh <= 8 and kw <= 8 and Cout == 64 and H % 2 == 0:
+              _flush_head_beside(rt, fork, main, side)
+              if _stem_applies(geom):
                   # the 7x7/2 ImageNet stem: 8-byte pixels {hi, 0, lo, 0}, one tiled TMA load per filter row (conv_stem.cu);
                   # dW[r, s, c] = 2 * acc8[r, s, c] + acc8[r, s, 4 + c]
-                  nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
-                  work = getattr(layer, '_stem_work8', None)
-                  if work is None or work.numel() != nb or work.device != xm.device:
-                      work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
+                  work, nb = _stem_work(layer, geom, dev)
+                  repack = 0 if getattr(layer, '_stem_packed', False) else 1       # 0: _stem_prepack ran in the forward pass
+                  layer._stem_packed = False
                   acc8 = rt.zeros_i64(512 * Cout, dev)
                   done = _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g2), Q.MANT_S8, Cout, kh, kw, pt, pl,
-                                       OH, OW, _lib.ptr(work), 1, _lib.ptr(acc8), 1, _lib.stream(),
+                                       OH, OW, _lib.ptr(work), repack, _lib.ptr(acc8), 1, _lib.stream(),
                                        meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * 16 + nb + M * Cout + 8 * 512 * Cout))
                   if done:
                       a = acc8.view(8, 8, 8, Cout)[:kh, :kw]
@@ -803,17 +854,17 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw,
             if not _implicit_ok(Cout, 1, 1):
                 raise _lib.LbtError('first-layer implicit wgrad needs Cout in {16,32,64} or a multiple of 128')
             done = False
-            if STEM_WGRAD and sh == 2 and sw == 2 and kh <= 8 and kw <= 8 and Cout == 64 and H % 2 == 0:
+            _flush_head_beside(rt, fork, main, side)
+            if _stem_applies(geom):
                 # the 7x7/2 ImageNet stem (conv_stem.cu): both byte planes against ONE re-packed copy of the image
-                nb = int(_lib.lib().lbt_stem_pack8_bytes(N, H, OW))
-                work = getattr(layer, '_stem_work8', None)
-                if work is None or work.numel() != nb or work.device != xm.device:
-                    work = layer._stem_work8 = torch.empty(nb, dtype=torch.int8, device=dev)
+                work, nb = _stem_work(layer, geom, dev)
+                repack = 0 if getattr(layer, '_stem_packed', False) else 1       # 0: _stem_prepack ran in the forward pass
+                layer._stem_packed = False
                 acc8 = rt.zeros_i64(512 * Cout, dev)
                 done = True
                 for i, (g_, kind, alpha) in enumerate(halves):
                     done = done and _lib.try_call('lbt_conv_i8_wgrad_c3', _lib.ptr(xm), N, H, W, _lib.ptr(g_), kind, Cout, kh, kw, pt,
-                                                  pl, OH, OW, _lib.ptr(work), 1 if i == 0 else 0, _lib.ptr(acc8), alpha, _lib.stream(),
+                                                  pl, OH, OW, _lib.ptr(work), repack if i == 0 else 0, _lib.ptr(acc8), alpha, _lib.stream(),
                                                   meta=dict(ops=M * Cout * Kf, bytes=(N * H * W * 16 + nb if i == 0 else 0) + nb + M * Cout))
                 if done:
                     a = acc8.view(8, 8, 8, Cout)[:kh, :kw]
@@ -886,6 +937,7 @@ class _QConv2dFn(torch.autograd.Function):
         N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         xm, xkind = _conv_quantize_input(layer, x, geom)                                       # dfxp:287
         prep, wm, bq = _conv_params(layer, weight, bias)
+        _stem_prepack(layer, xm, xkind, geom)      # after _conv_params: that joined the parameter branch of the side stream
         y = torch.empty(N, OH, OW, Cout, dtype=torch.float32, device=x.device)
         _conv_fprop(layer, geom, xm, xkind, prep, wm, bq, y.view(N * OH * OW, Cout))
         ctx.layer, ctx.geom, ctx.xkind, ctx.prep = layer, geom, xkind, prep
@@ -1357,6 +1409,7 @@ class _ConvBNFn(torch.autograd.Function):
         dev = x.device
         xm, xkind = _conv_quantize_input(conv, x, geom)                                        # dfxp:287
         prep, wm, _ = _conv_params(conv, weight, None)
+        _stem_prepack(conv, xm, xkind, geom)       # after _conv_params: that joined the parameter branch of the side stream
         sums = rt.zeros_i64(2 * Cout, dev)
         k1 = torch.empty(N, OH, OW, Cout, dtype=torch.int8, device=dev)
         _conv_fprop(conv, geom, xm, xkind, prep, wm, None, None,

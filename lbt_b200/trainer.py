@@ -38,8 +38,9 @@ class GradSink:
     def __init__(self, params):
         self.out = {id(p): p for p in params}
         self.jobs = []
-        self._key = None
-        self._table = None
+        self._key = {}               # per launch slot ('all' | 'head' | 'tail'): the uploaded job table and what it describes
+        self._table = {}
+        self._head = 0               # jobs already finalised by flush_head()
         self._pinned = []            # staging copies of uploaded tables (kept alive for captured CUDA graphs)
         self.active = False         # only between begin() and flush(): outside a Trainer step layers finalise themselves
 
@@ -48,17 +49,15 @@ class GradSink:
 
     def begin(self):
         self.jobs = []
+        self._head = 0
         self.active = True
 
     def add(self, param, acc, ibA, ibB, exp_const, add_scale):
         self.jobs.append((param, acc, ibA, ibB, int(exp_const), float(add_scale)))
 
-    def flush(self):
-        self.active = False
-        if not self.jobs:
-            return
+    def _launch(self, jobs, slot):
         structs, key, start = [], [], 0
-        for param, acc, ibA, ibB, e, s in self.jobs:
+        for param, acc, ibA, ibB, e, s in jobs:
             n = acc.numel()
             assert n == param.numel() and acc.is_contiguous()
             j = _lib.FinalizeJob(acc64=acc.data_ptr(), n=n, ibA=_lib.ptr(ibA) or 0, ibB=_lib.ptr(ibB) or 0, exp_const=e,
@@ -67,10 +66,24 @@ class GradSink:
             key.append((j.acc64, n, j.ibA, j.ibB, e, s, j.add, j.out))
             start += n
         key = tuple(key)
-        if key != self._key:                      # pointers are stable from step to step: upload the table once
-            self._table = _lib.to_device_table(structs, self.jobs[0][1].device, keep=self._pinned)
-            self._key = key
-        _lib.call('lbt_finalize_multi', _lib.ptr(self._table), len(structs), start, _lib.stream())
+        if key != self._key.get(slot):            # pointers are stable from step to step: upload the table once
+            self._table[slot] = _lib.to_device_table(structs, jobs[0][1].device, keep=self._pinned)
+            self._key[slot] = key
+        _lib.call('lbt_finalize_multi', _lib.ptr(self._table[slot]), len(structs), start, _lib.stream())
+
+    def flush_head(self):
+        """Finalise what has been collected so far on the CURRENT stream (its producers must be ordered before it): the
+        first layer's backward calls this so that every other gradient is converted while its own weight-gradient kernel
+        — the last one of the step, with nothing else left to overlap — is still running."""
+        if not self.active or len(self.jobs) == self._head:
+            return
+        self._launch(self.jobs[self._head:], 'head')
+        self._head = len(self.jobs)
+
+    def flush(self):
+        self.active = False
+        if len(self.jobs) > self._head:
+            self._launch(self.jobs[self._head:], 'tail' if self._head else 'all')
 
 
 class Trainer:
