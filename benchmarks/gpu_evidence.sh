@@ -19,16 +19,16 @@ timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
     --log-file $O/${T}_launches_resnet18.csv $B > $O/${T}_ncu_list.log 2>&1
 echo "ncu list rc $?"
 cap() {  # name, regex, skip, count
-  timeout 420 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 \
+  timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 \
       -o /tmp/${T}_$1 -f $B > $O/${T}_ncu_$1.log 2>&1
   echo "ncu $1 rc $?"
   ncu -i /tmp/${T}_$1.ncu-rep --page raw --csv > $O/${T}_ncu_$1_raw.csv 2>/dev/null
   ncu -i /tmp/${T}_$1.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $O/${T}_ncu_$1_source.csv.gz
   ls -la /tmp/${T}_$1.ncu-rep
 }
-cap bn "bn_fwd2|bn_bwd2|bn_bwd1" 3 9
-cap wgrad "wgrad" 17 3
-cap conv "halo|conv_ldg_kernel|conv_fprop|dgrad" 0 6
-cap convbwd "halo|conv_ldg_kernel|conv_fprop|dgrad" 30 5
-cap misc "maxpool|param_prep|xent_fwd|finalize|dp_step|quantize_" 0 12
+cap fprop "conv_halo|conv_ldg_kernel|conv_fprop" 0 45
+cap bnfwd "bn_fwd2|bn_bwd2|bn_bwd1" 3 6
+cap bnbwd "bn_fwd2|bn_bwd2|bn_bwd1" 48 12
+cap wgrad "wgrad" 14 6
+cap misc "maxpool|param_prep|xent_fwd|finalize|dp_step|quantize_|stem_pack8" 0 14
 du -sh $O

@@ -479,6 +479,196 @@ __global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p
 }
 
 // ------------------------------------------------------------------------------------------------
+// fwd 2 + stride-2 3x3 max-pool (the ImageNet stem: conv -> BN -> ReLU -> tf.nn.max_pool 3x3/2 'SAME', models.py / dfxp:993-1006)
+//
+// lbt_bn_fwd_apply followed by lbt_maxpool_fwd writes the fp32 module output (4 B per element) only for the pool to read it
+// back: 1.6 GB of the 2.3 GB the two kernels move on ResNet-18's stem.  Here a CTA owns an 8 x 16 pixel tile of the image for a
+// group of batch rows; a thread owns a 2 x 2 block of pixels x 4 channels (its noise and per-channel constants in registers,
+// like the stand-alone kernel), applies fwd 2 to them with the SAME arithmetic, stores k2, and leaves the post-ReLU values in
+// shared memory; the first 400 threads also evaluate one pixel each of the tile's one-pixel halo (row 8 / column 16: the
+// windows of the last block row / column reach into the next tile; values only — statistics and k2 belong to the owning tile).
+// After ONE barrier (two shared-memory buffers) every thread takes the 3 x 3 window whose top-left pixel is its block's:
+// maximum and winning tap in lbt_maxpool_fwd's scan order, so pooled values and indices are bit-identical.  C == 64.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPoolTH = 8, kPoolTW = 16, kPoolCG = 16, kPoolThreads = 512;
+constexpr int kPoolHalo = (kPoolTH + 1) * (kPoolTW + 1) - kPoolTH * kPoolTW;   // 25 halo pixels per tile
+
+struct Fwd2PoolParams {
+  const int8_t* k1;
+  int bits1;
+  const int32_t* ib1;
+  const long long* sums;
+  float eps;
+  QSite q2;
+  const float* gq;
+  const float* bq;
+  int relu;
+  int8_t* k2;
+  float* run_mean;
+  float* run_var;
+  float momentum, one_minus_momentum;
+  float* pooled;           // [N, POH, POW, 64]
+  uint8_t* pidx;           // winning tap r * 3 + q
+  uint32_t N, H, W, POH, POW;
+  uint32_t tiles_x, tiles_img, rows_per_group, total_tiles;
+};
+
+template <bool MM>
+__global__ void __launch_bounds__(kPoolThreads, 1) bn_fwd2_pool_kernel(const Fwd2PoolParams p) {
+  extern __shared__ float4 s_y[];   // [2][kPoolTH + 1][kPoolTW + 1][kPoolCG]
+  __shared__ float s_par[4 * 64];   // mean, den / m2, gq / m2, bq
+  pdl_trigger();
+  pdl_wait();
+  constexpr int C = 64;
+  const QC c1 = make_qc(p.bits1, __ldg(p.ib1));
+  const QC c2 = make_qc(p.q2.bits, __ldg(p.q2.ib));
+  const DivN n = make_divn((unsigned long long)p.N * p.H * p.W);
+  if (threadIdx.x < C) {
+    const int ch = threadIdx.x;
+    float mean, var;
+    moments(p.sums, C, ch, n, c1.inv_m, mean, var);
+    s_par[ch] = mean;
+    s_par[C + ch] = __fsqrt_rn(__fadd_rn(var, p.eps)) * c2.inv_m;
+    s_par[2 * C + ch] = p.gq[ch] * c2.inv_m;
+    s_par[3 * C + ch] = p.bq[ch];
+    if (blockIdx.x == 0 && p.run_mean) {
+      p.run_mean[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_mean[ch]), __fmul_rn(p.one_minus_momentum, mean));
+      p.run_var[ch] = __fadd_rn(__fmul_rn(p.momentum, p.run_var[ch]), __fmul_rn(p.one_minus_momentum, var));
+    }
+  }
+  __syncthreads();
+  const uint64_t off = site_offset(p.q2);
+  const uint32_t cg = threadIdx.x & (kPoolCG - 1), blk = threadIdx.x >> 4, by = blk >> 3, bx = blk & 7;
+  float nmean[4], den[4], rden[4], g[4], b[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    nmean[j] = -s_par[4 * cg + j];
+    den[j] = s_par[C + 4 * cg + j];
+    rden[j] = __frcp_rn(den[j]);
+    g[j] = s_par[2 * C + 4 * cg + j];
+    b[j] = s_par[3 * C + 4 * cg + j];
+  }
+  const bool relu = p.relu != 0;
+  // halo task of this thread: pixel hp of the tile's extra row (ly = 8, lx = 0..16) / extra column (lx = 16, ly = 0..7)
+  const uint32_t hp = threadIdx.x >> 4;
+  const bool halo_task = hp < (uint32_t)kPoolHalo;
+  const uint32_t hly = hp <= (uint32_t)kPoolTW ? (uint32_t)kPoolTH : hp - (kPoolTW + 1), hlx = hp <= (uint32_t)kPoolTW ? hp : (uint32_t)kPoolTW;
+  uint32_t n1 = 0, n2 = 0;
+  float mx = -INFINITY, mn = INFINITY;
+  const uint32_t HW = p.H * p.W, PHW = p.POH * p.POW;
+  const uint32_t* const k1w = reinterpret_cast<const uint32_t*>(p.k1);
+  uint32_t* const k2w = reinterpret_cast<uint32_t*>(p.k2);
+  uint32_t buf = 0;
+  auto apply4 = [&](uint32_t w, const float (&un)[4], float& smx, float& smn, uint32_t& s1, uint32_t& s2, float (&o)[4]) -> uint32_t {
+    float k1f[4], t2[4];
+    dec4_f(w, k1f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y1m = fdiv_fast(__fmaf_rn(k1f[j], c1.inv_m, nmean[j]), den[j], rden[j]);   // dfxp:616
+      t2[j] = sq_scaled<MM>(y1m, un[j], c2, smx, smn, s1, s2);                                // dfxp:677
+      float y2 = __fadd_rn(__fmul_rn(tm_float(t2[j]), g[j]), b[j]);                           // dfxp:683
+      if (relu) y2 = fmaxf(0.0f, y2);                                                          // dfxp:986
+      o[j] = y2;
+    }
+    return tm_pack4(t2);
+  };
+  for (uint32_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const uint32_t rg = tile / p.tiles_img, tt = tile - rg * p.tiles_img;
+    const uint32_t ty = tt / p.tiles_x, tx = tt - ty * p.tiles_x;
+    const uint32_t y0 = ty * kPoolTH, x0 = tx * kPoolTW;
+    // own 2 x 2 block
+    uint32_t pw[4];     // word index of pixel (py, px) inside an image: (y * W + x) * 16 + cg
+    bool pv[4];
+    float un[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t y = y0 + 2 * by + (q >> 1), x = x0 + 2 * bx + (q & 1);
+      pv[q] = y < p.H && x < p.W;
+      pw[q] = (y * p.W + x) * kPoolCG + cg;
+      const float4 u = pv[q] ? site_noise(p.q2, pw[q], off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      un[q][0] = u.x; un[q][1] = u.y; un[q][2] = u.z; un[q][3] = u.w;
+    }
+    const uint32_t hy = y0 + hly, hx = x0 + hlx;
+    const bool hv = halo_task && hy < p.H && hx < p.W;
+    const uint32_t hw = (hy * p.W + hx) * kPoolCG + cg;
+    float hun[4] = {0.f, 0.f, 0.f, 0.f};
+    if (hv) {
+      const float4 u = site_noise(p.q2, hw, off);
+      hun[0] = u.x; hun[1] = u.y; hun[2] = u.z; hun[3] = u.w;
+    }
+    // the pooling window of this thread: output (a, b), top-left pixel = the block's
+    const uint32_t pa = (y0 >> 1) + by, pb = (x0 >> 1) + bx;
+    const bool wv = pa < p.POH && pb < p.POW;
+    bool tok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) tok[3 * r + q] = (y0 + 2 * by + r) < p.H && (x0 + 2 * bx + q) < p.W;
+    const uint32_t r0 = rg * p.rows_per_group, r1 = min(r0 + p.rows_per_group, p.N);
+    for (uint32_t r = r0; r < r1; ++r) {
+      const uint32_t ibase = r * HW * kPoolCG;
+      uint32_t w[4], wh = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (pv[q]) w[q] = __ldcs(k1w + ibase + pw[q]);
+      if (hv) wh = __ldg(k1w + ibase + hw);   // the neighbouring tile reads this pixel too
+      if (r + 1 < r1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (pv[q]) prefetch_l1(k1w + ibase + HW * kPoolCG + pw[q]);
+      }
+      float4* sy = s_y + (size_t)buf * ((kPoolTH + 1) * (kPoolTW + 1) * kPoolCG);
+      float own[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (pv[q]) {
+          const uint32_t k2p = apply4(w[q], un[q], mx, mn, n1, n2, own[q]);
+          k2w[ibase + pw[q]] = k2p;
+          sy[((2 * by + (q >> 1)) * (kPoolTW + 1) + 2 * bx + (q & 1)) * kPoolCG + cg] = make_float4(own[q][0], own[q][1], own[q][2], own[q][3]);
+        }
+      if (hv) {
+        float ho[4], dmx = 0.f, dmn = 0.f;
+        uint32_t d1 = 0, d2 = 0;
+        (void)apply4(wh, hun, dmx, dmn, d1, d2, ho);
+        sy[(hly * (kPoolTW + 1) + hlx) * kPoolCG + cg] = make_float4(ho[0], ho[1], ho[2], ho[3]);
+      }
+      __syncthreads();
+      if (wv) {
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 wt = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+        for (int tq = 0; tq < 9; ++tq) {
+          const int tr = tq / 3, tc = tq % 3;
+          if (!tok[tq]) continue;
+          float4 a;
+          if (tr < 2 && tc < 2) a = make_float4(own[2 * tr + tc][0], own[2 * tr + tc][1], own[2 * tr + tc][2], own[2 * tr + tc][3]);
+          else a = sy[((2 * by + tr) * (kPoolTW + 1) + 2 * bx + tc) * kPoolCG + cg];
+          const unsigned char t8 = (unsigned char)tq;
+          if (a.x > m.x || a.x != a.x) { m.x = a.x; wt.x = t8; }
+          if (a.y > m.y || a.y != a.y) { m.y = a.y; wt.y = t8; }
+          if (a.z > m.z || a.z != a.z) { m.z = a.z; wt.z = t8; }
+          if (a.w > m.w || a.w != a.w) { m.w = a.w; wt.w = t8; }
+        }
+        const uint32_t o = (r * PHW + pa * p.POW + pb) * kPoolCG + cg;
+        reinterpret_cast<float4*>(p.pooled)[o] = m;
+        reinterpret_cast<uchar4*>(p.pidx)[o] = wt;
+      }
+      buf ^= 1u;
+    }
+    __syncthreads();   // the next tile's first write may target the buffer another thread still reads
+  }
+  if (MM) mm_to_counts(c2, mx, mn, n1, n2);
+  n1 = warp_sum(n1);
+  n2 = warp_sum(n2);
+  if ((threadIdx.x & 31) == 0 && p.q2.counters) {
+    if (n1) atomicAdd(p.q2.counters + LBT_CNT_OVER, (unsigned long long)n1);
+    if (n2) atomicAdd(p.q2.counters + LBT_CNT_OVER_HALF, (unsigned long long)n2);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.q2.counters)
+    atomicAdd(p.q2.counters + LBT_CNT_NUMEL, (unsigned long long)p.N * p.H * p.W * C);
+}
+
+// ------------------------------------------------------------------------------------------------
 // bwd 1
 // ------------------------------------------------------------------------------------------------
 struct Bwd1Params {
@@ -1233,6 +1423,68 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
     launch_pdl(bn_fwd2_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   }
   return check_launch("lbt_bn_fwd_apply");
+}
+
+extern "C" int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, int W, int C, int bits1, const int32_t* ib1,
+                                       const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                                       uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                                       const float* gamma_q, const float* beta_q, int relu, int8_t* k2, float* run_mean,
+                                       float* run_var, double momentum, int stats_minmax, int k, int s, int pad_top, int pad_left,
+                                       int POH, int POW, float* pooled, uint8_t* pidx, void* stream) {
+  if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2 || !pooled || !pidx) return LBT_EINVAL;
+  if (H <= 0 || W <= 0 || C <= 0 || POH <= 0 || POW <= 0 || k <= 0 || s <= 0 || pad_top < 0 || pad_left < 0) return LBT_EINVAL;
+  if ((run_mean == nullptr) != (run_var == nullptr)) return LBT_EINVAL;
+  if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
+  // the ImageNet stem's shape class: 3x3 / 2 windows that start on the even pixels, 64 channels
+  if (C != 64 || k != 3 || s != 2 || pad_top != 0 || pad_left != 0 || POH != (H + 1) / 2 || POW != (W + 1) / 2) return LBT_EUNSUPPORTED;
+  if (n_outer == 0) return LBT_OK;
+  if ((uint64_t)n_outer * H * W * 16 >= (1ull << 31)) return LBT_EUNSUPPORTED;   // 32-bit word indices
+  if (!al4(k1) || !al4(k2) || !al16(pooled) || !al4(pidx) || (noise2 && !al16(noise2))) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  const DeviceInfo& di = device_info();
+  Fwd2PoolParams p{};
+  p.k1 = k1;
+  p.bits1 = bits1;
+  p.ib1 = ib1;
+  p.sums = reinterpret_cast<const long long*>(sums);
+  p.eps = eps;
+  p.q2 = make_site(bits2, ib2, noise2, seed, offset2, dev_step, counters2, stats_minmax);
+  p.gq = gamma_q;
+  p.bq = beta_q;
+  p.relu = relu;
+  p.k2 = k2;
+  p.run_mean = run_mean;
+  p.run_var = run_var;
+  p.momentum = (float)momentum;
+  p.one_minus_momentum = (float)(1.0 - momentum);
+  p.pooled = pooled;
+  p.pidx = pidx;
+  p.N = (uint32_t)n_outer;
+  p.H = (uint32_t)H;
+  p.W = (uint32_t)W;
+  p.POH = (uint32_t)POH;
+  p.POW = (uint32_t)POW;
+  p.tiles_x = (uint32_t)((W + kPoolTW - 1) / kPoolTW);
+  p.tiles_img = p.tiles_x * (uint32_t)((H + kPoolTH - 1) / kPoolTH);
+  // row groups: about one wave of CTAs (one 512-thread CTA per SM), at least 4 rows per group
+  uint64_t groups = ((uint64_t)di.sm_count * 2 + p.tiles_img / 2) / p.tiles_img;
+  if (groups < 1) groups = 1;
+  if (groups > (n_outer + 3) / 4) groups = (n_outer + 3) / 4;
+  p.rows_per_group = (uint32_t)((n_outer + groups - 1) / groups);
+  const uint64_t total = (uint64_t)p.tiles_img * ((n_outer + p.rows_per_group - 1) / p.rows_per_group);
+  if (total >= (1ull << 31)) return LBT_EUNSUPPORTED;
+  p.total_tiles = (uint32_t)total;
+  const size_t smem = (size_t)2 * (kPoolTH + 1) * (kPoolTW + 1) * kPoolCG * sizeof(float4);
+  const unsigned grid = (unsigned)total;
+  int rc;
+  if (stats_minmax) {
+    if ((rc = set_smem(bn_fwd2_pool_kernel<true>, smem))) return rc;
+    launch_pdl(bn_fwd2_pool_kernel<true>, grid, kPoolThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  } else {
+    if ((rc = set_smem(bn_fwd2_pool_kernel<false>, smem))) return rc;
+    launch_pdl(bn_fwd2_pool_kernel<false>, grid, kPoolThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
+  }
+  return check_launch("lbt_bn_fwd_apply_pooled");
 }
 
 static int bn_bwd1_run(const float* g, const float* out, int relu, const int8_t* k2, const int8_t* k1,

@@ -489,6 +489,9 @@ def _dgrad_classes_ok(layer, Cin, Cout, kh, kw, sh, sw):
             not _gather_ok(Cout, Cin, kh, kw))
 
 
+# conv -> BN -> ReLU -> 3x3/2 max-pool: BN pass 2 and the pool in one kernel (LBT_FUSE_POOL_FWD=0: two launches and an fp32 tensor).
+FUSE_POOL_FWD = os.environ.get('LBT_FUSE_POOL_FWD', '1') != '0'
+
 # First-layer weight gradient through lbt_conv_i8_wgrad_c3 (LBT_STEM_WGRAD=0: the general kernel on the 16-byte pixels).
 STEM_WGRAD = os.environ.get('LBT_STEM_WGRAD', '1') != '0'
 
@@ -1416,15 +1419,36 @@ class _ConvBNFn(torch.autograd.Function):
                     bnq=(norm.qX.abi(OH * OW * Cout, dev, arena=True), k1, sums))                          # dfxp:291 + :584-588
         gq, bq = _bn_params(resc, gamma, beta)
         add_ = _to_mem(add) if add is not None else None
-        k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
+        pooled = pidx = None
+        if (pool is not None and FUSE_POOL_FWD and add is None and next_site is None and Cout == 64 and
+                pool[:4] == (3, 2, 0, 0)):
+            # the ImageNet stem: BN apply + ReLU + 3x3/2 max-pool in ONE kernel, the fp32 module output never exists
+            pk, ps, ppt, ppl, POH, POW = pool
+            k2 = torch.empty_like(k1)
+            pooled = torch.empty(N, POH, POW, Cout, dtype=torch.float32, device=dev)
+            pidx = torch.empty(N, POH, POW, Cout, dtype=torch.uint8, device=dev)
+            nz2, off2 = _site_args(resc.qX, k1)
+            if _lib.try_call('lbt_bn_fwd_apply_pooled', _lib.ptr(k1), N, OH, OW, Cout, norm.qX.bits, _lib.ptr(norm.qX.range),
+                             _lib.ptr(sums), float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
+                             _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), 1 if relu else 0,
+                             _lib.ptr(k2), _lib.ptr(norm.X_mean_running), _lib.ptr(norm.X_var_running), float(norm.momentum),
+                             int(resc.qX.target == 0), pk, ps, ppt, ppl, POH, POW, _lib.ptr(pooled), _lib.ptr(pidx), _lib.stream(),
+                             meta=dict(bytes=k1.numel() * 2 + pooled.numel() * 5)):
+                out, nm, relu_mode = None, None, (1 if relu else 0)
+            else:
+                pooled = pidx = None
+        if pooled is None:
+            k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
         ctx.conv, ctx.bn, ctx.geom, ctx.xkind, ctx.prep = conv, bn, geom, xkind, prep
         ctx.relu_mode, ctx.has_add = relu_mode, add is not None
         ctx.link_in, ctx.link_out = link_in, link_out
         if link_out is not None and out is None:     # the next unit may run this BN's backward pass 1 in its dgrad epilogue
             link_out.offer(bn, k1, k2, gq, bq, relu_mode, add is not None)
-        pidx = None
         ctx.pool = None
-        if pool is not None:      # MaxPool_q behind the unit (ImageNet stem): its backward runs inside this unit's BN pass 1
+        if pooled is not None:    # lbt_bn_fwd_apply_pooled did both
+            ctx.pool = tuple(pool)
+            out = pooled
+        elif pool is not None:    # MaxPool_q behind the unit (ImageNet stem): its backward runs inside this unit's BN pass 1
             pk, ps, ppt, ppl, POH, POW = pool
             pooled = torch.empty(N, POH, POW, Cout, dtype=torch.float32, device=dev)
             pidx = torch.empty(N, POH, POW, Cout, dtype=torch.uint8, device=dev)

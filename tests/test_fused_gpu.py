@@ -227,3 +227,42 @@ def test_xent_cluster_kernel_same_bits_as_single_cta_order():
         for w in range(32):
             t = np.float32(t + parts[w])
         assert np.float32(float(la)).tobytes() == np.float32(t / np.float32(B)).tobytes()
+
+
+@pytest.mark.parametrize('name,batch,image,kw', [('Resnet18', 4, 64, dict(image=64, num_classes=10)),
+                                                 ('Resnet18', 3, 60, dict(image=60, num_classes=10)),      # 30 x 30 -> 15 x 15: ragged tiles and windows
+                                                 ('Resnet18', 5, 96, dict(image=96, num_classes=10)),      # 48 x 48: several tiles per image, halo between them
+                                                 ('Resnet50', 2, 64, dict(image=64, num_classes=10, grad_bits=16))])
+def test_bn_apply_with_pool_folded_in_equals_two_kernels(name, batch, image, kw):
+    """lbt_bn_fwd_apply_pooled (BN pass 2 + ReLU + the stem's 3x3/2 max-pool in one kernel, no fp32 module output) vs
+    lbt_bn_fwd_apply + lbt_maxpool_fwd: losses, gradients, weights, momentum, ranges, counters and running statistics of three
+    training steps bit-identical."""
+    from lbt_b200 import _lib
+    seen = []
+    orig = _lib.try_call
+
+    def spy(fn, *a, **k):
+        ok = orig(fn, *a, **k)
+        seen.append((fn, ok))
+        return ok
+
+    res = {}
+    for on in (True, False):
+        D.FUSE_POOL_FWD = on
+        del seen[:]
+        _lib.try_call = spy
+        try:
+            res[on] = _run(name, True, 3, batch, image, kw)
+        finally:
+            _lib.try_call = orig
+            D.FUSE_POOL_FWD = True
+        n = sum(1 for fn, ok in seen if fn == 'lbt_bn_fwd_apply_pooled' and ok)
+        assert n == (3 if on else 0), (on, n)
+    a, b = res[True], res[False]
+    assert a['losses'] == b['losses'], (a['losses'], b['losses'])
+    assert torch.equal(a['ranges'], b['ranges'])
+    assert torch.equal(a['counters'], b['counters'])
+    for k in ('g', 'w', 'a'):
+        assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
+    for x, y in zip(a['bn'], b['bn']):
+        assert torch.equal(x, y)
