@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(32 * (kLoaderWarps + 1 + EPI), EPI == 8 ? 2 : 
           if ((uint32_t)c >= p.N) continue;  // warp-uniform
           const uint32_t ncol = min(16u, p.N - (uint32_t)c);
           if (fused) {
-            bnq_chunk(p.bnq, bst, vv[q], scale, p.bias ? p.bias + c : nullptr, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat, BN,
-                      (uint32_t)c, lane);
+            bnq_chunk<EPI != 16>(p.bnq, bst, vv[q], scale, p.bias ? p.bias + c : nullptr, row, pix, rvalid, (uint32_t)c, ncol, p.N, my_stat,
+                                 BN, (uint32_t)c, lane);   // the loader-paced 16-warp instantiation keeps the run-time fold test (qsite.cuh)
             continue;
           }
           float f[16];

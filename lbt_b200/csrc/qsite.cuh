@@ -237,14 +237,19 @@ __device__ __forceinline__ void bnq_load_noise(const BnqParams& b, const BnqStat
 
 // PRE: the noise comes in `u4` (bnq_load_noise, issued by the caller ahead of its accumulator wait); else it is fetched here,
 // group by group between the arithmetic (what the register-bound gather kernels want; `pix` is only used then).
-template <bool FULL, bool MM, bool PRE>
+// FOLD: compile-time copy of the `fold` test below.  As a run-time flag inside the unrolled element loop it cost a BSSY / BRA /
+// BSYNC triple per element (ncu source view of conv_halo_kernel: 3 of the ~18 per-element instructions) and, worse, a
+// reconvergence barrier between consecutive elements that kept the compiler from interleaving their dependent chains.
+// FOLD = 2: the test stays a run-time flag — the 16-epilogue-warp gather kernel of the 7x7/2 stem is paced by its cp.async
+// loader warps and measurably loses (476 -> 506 us) when the epilogue warps issue in denser bursts.
+template <bool FULL, bool MM, bool PRE, int FOLD>
 __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
                                                const float* bias, uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol,
                                                uint32_t N, int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
   const uint64_t inner = PRE ? 0ull : (uint64_t)pix * N + col;   // multiple of 4 (N % 4 == 0, col % 16 == 0)
   const QC& c = st.qc;
-  // one multiply when no bias sits between the two scalings and neither product can leave the normal range
-  const bool fold = bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(c.m)) < 60.0f;
+  // one multiply instead of two (decided by the caller, see bnq_chunk_sel)
+  const bool fold = FOLD == 2 ? (bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(c.m)) < 60.0f) : (FOLD == 1);
   const float sm = scale * c.m;
   float tm[16];
 #pragma unroll
@@ -296,18 +301,25 @@ __device__ __forceinline__ void bnq_chunk_impl(const BnqParams& b, BnqState& st,
 }
 
 // `bias`: this chunk's 16 bias values (NULL: none); `u4`: the chunk's noise from bnq_load_noise.
-template <bool PRE>
+template <bool PRE, bool UNSWITCH = true>
 __device__ __forceinline__ void bnq_chunk_sel(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
                                               const float* bias, uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N,
                                               int* s_stat, uint32_t bn, uint32_t tcol, int lane) {
   const bool full = ncol == 16 && __all_sync(0xffffffffu, row_ok);
-  if (b.q.minmax) {
-    if (full) bnq_chunk_impl<true, true, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, true, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  // one multiply when no bias sits between the two scalings and neither product can leave the normal range (warp-uniform)
+  const bool fold = bias == nullptr && fabsf(__log2f(scale)) < 60.0f && fabsf(__log2f(st.qc.m)) < 60.0f;
+#define LBT_BNQ_CHUNK(F, M, FO) bnq_chunk_impl<F, M, PRE, FO>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane)
+  if constexpr (!UNSWITCH) {
+    if (b.q.minmax) { if (full) LBT_BNQ_CHUNK(true, true, 2); else LBT_BNQ_CHUNK(false, true, 2); }
+    else { if (full) LBT_BNQ_CHUNK(true, false, 2); else LBT_BNQ_CHUNK(false, false, 2); }
+  } else if (b.q.minmax) {
+    if (full) { if (fold) LBT_BNQ_CHUNK(true, true, 1); else LBT_BNQ_CHUNK(true, true, 0); }
+    else { if (fold) LBT_BNQ_CHUNK(false, true, 1); else LBT_BNQ_CHUNK(false, true, 0); }
   } else {
-    if (full) bnq_chunk_impl<true, false, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
-    else bnq_chunk_impl<false, false, PRE>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+    if (full) { if (fold) LBT_BNQ_CHUNK(true, false, 1); else LBT_BNQ_CHUNK(true, false, 0); }
+    else { if (fold) LBT_BNQ_CHUNK(false, false, 1); else LBT_BNQ_CHUNK(false, false, 0); }
   }
+#undef LBT_BNQ_CHUNK
 }
 __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], const float4 (&u4)[4], float scale,
                                           const float* bias, uint32_t row, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
@@ -315,11 +327,12 @@ __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, cons
   bnq_chunk_sel<true>(b, st, v, u4, scale, bias, row, 0u, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
 }
 // Noise fetched inside the chunk, right before use.
+template <bool UNSWITCH = true>
 __device__ __forceinline__ void bnq_chunk(const BnqParams& b, BnqState& st, const uint32_t (&v)[16], float scale, const float* bias,
                                           uint32_t row, uint32_t pix, bool row_ok, uint32_t col, uint32_t ncol, uint32_t N, int* s_stat,
                                           uint32_t bn, uint32_t tcol, int lane) {
   float4 u4[4];   // not read
-  bnq_chunk_sel<false>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
+  bnq_chunk_sel<false, UNSWITCH>(b, st, v, u4, scale, bias, row, pix, row_ok, col, ncol, N, s_stat, bn, tcol, lane);
 }
 
 // Add the warp's partial sums for the tile columns [col0, col0 + bn) to the global int64 sums and clear them.
