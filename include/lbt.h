@@ -398,6 +398,7 @@ int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, in
  * tf.nn.max_pool 3x3/2 'SAME', dfxp:993-1006): k2 and the statistics / running averages exactly as lbt_bn_fwd_apply; instead
  * of the fp32 module output, pooled[n_outer, POH, POW, C] and idx (winning tap r*k + s of every pooled element) exactly as
  * lbt_maxpool_fwd would produce from it (first maximum in scan order) — the fp32 tensor never exists.  k1[n_outer, H, W, C].
+ * q_next / next_mant / next_kind as in lbt_bn_fwd_apply, applied to the POOLED tensor (the input quantiser of its consumer).
  * Shapes: C == 64, k == 3, s == 2, pad_top == pad_left == 0; else LBT_EUNSUPPORTED (run the two kernels).
  */
 int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, int W, int C, int bits1, const int32_t* ib1,
@@ -405,7 +406,8 @@ int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, int W, int 
                             uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                             const float* gamma_q, const float* beta_q, int relu, int8_t* k2, float* run_mean,
                             float* run_var, double momentum, int stats_minmax, int k, int s, int pad_top, int pad_left,
-                            int POH, int POW, float* pooled, uint8_t* pidx, void* stream);
+                            int POH, int POW, float* pooled, uint8_t* pidx, const lbt_qsite* q_next, void* next_mant,
+                            int next_kind, void* stream);
 /*
  * bwd 1: g (w.r.t. the module output) -> ReLU mask (relu: 0 none, 1 recomputed from k2, 2 from `out`)
  * [-> d_add = masked g] -> kg2 = Q(g) (dfxp:687) -> sums[0..C) = sum kg2 (dbeta, :690),

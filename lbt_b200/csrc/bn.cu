@@ -509,6 +509,8 @@ struct Fwd2PoolParams {
   float momentum, one_minus_momentum;
   float* pooled;           // [N, POH, POW, 64]
   uint8_t* pidx;           // winning tap r * 3 + q
+  QSite q3;                // optional: the input quantiser of the layer that consumes the POOLED tensor (bits == 0: off)
+  uint8_t* next_mant;      // its mantissas [N, POH, POW, 64] (u8 for a 9-bit non-negative tensor, s8 otherwise: same byte)
   uint32_t N, H, W, POH, POW;
   uint32_t tiles_x, tiles_img, rows_per_group, total_tiles;
 };
@@ -555,6 +557,15 @@ __global__ void __launch_bounds__(kPoolThreads, 1) bn_fwd2_pool_kernel(const Fwd
   const uint32_t hly = hp <= (uint32_t)kPoolTW ? (uint32_t)kPoolTH : hp - (kPoolTW + 1), hlx = hp <= (uint32_t)kPoolTW ? hp : (uint32_t)kPoolTW;
   uint32_t n1 = 0, n2 = 0;
   float mx = -INFINITY, mn = INFINITY;
+  const bool nxt = p.q3.bits != 0;
+  QC c3 = c2;
+  uint64_t off3 = 0;
+  if (nxt) {
+    c3 = make_qc(p.q3.bits, __ldg(p.q3.ib));
+    off3 = site_offset(p.q3);
+  }
+  uint32_t m1 = 0, m2 = 0;
+  float mx3 = -INFINITY, mn3 = INFINITY;
   const uint32_t HW = p.H * p.W, PHW = p.POH * p.POW;
   const uint32_t* const k1w = reinterpret_cast<const uint32_t*>(p.k1);
   uint32_t* const k2w = reinterpret_cast<uint32_t*>(p.k2);
@@ -599,6 +610,11 @@ __global__ void __launch_bounds__(kPoolThreads, 1) bn_fwd2_pool_kernel(const Fwd
     // the pooling window of this thread: output (a, b), top-left pixel = the block's
     const uint32_t pa = (y0 >> 1) + by, pb = (x0 >> 1) + bx;
     const bool wv = pa < p.POH && pb < p.POW;
+    float u3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (nxt && wv) {
+      const float4 t = site_noise(p.q3, (pa * p.POW + pb) * kPoolCG + cg, off3);
+      u3[0] = t.x; u3[1] = t.y; u3[2] = t.z; u3[3] = t.w;
+    }
     bool tok[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -652,6 +668,13 @@ __global__ void __launch_bounds__(kPoolThreads, 1) bn_fwd2_pool_kernel(const Fwd
         const uint32_t o = (r * PHW + pa * p.POW + pb) * kPoolCG + cg;
         reinterpret_cast<float4*>(p.pooled)[o] = m;
         reinterpret_cast<uchar4*>(p.pidx)[o] = wt;
+        if (nxt) {                                                                      // the consumer's Xq, dfxp:287
+          const float mm4[4] = {m.x, m.y, m.z, m.w};
+          float t3[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t3[j] = sq_scaled<MM>(__fmul_rn(mm4[j], c3.m), u3[j], c3, mx3, mn3, m1, m2);
+          reinterpret_cast<uint32_t*>(p.next_mant)[o] = tm_pack4(t3);
+        }
       }
       buf ^= 1u;
     }
@@ -666,6 +689,17 @@ __global__ void __launch_bounds__(kPoolThreads, 1) bn_fwd2_pool_kernel(const Fwd
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && p.q2.counters)
     atomicAdd(p.q2.counters + LBT_CNT_NUMEL, (unsigned long long)p.N * p.H * p.W * C);
+  if (nxt) {
+    if (MM) mm_to_counts(c3, mx3, mn3, m1, m2);
+    m1 = warp_sum(m1);
+    m2 = warp_sum(m2);
+    if ((threadIdx.x & 31) == 0 && p.q3.counters) {
+      if (m1) atomicAdd(p.q3.counters + LBT_CNT_OVER, (unsigned long long)m1);
+      if (m2) atomicAdd(p.q3.counters + LBT_CNT_OVER_HALF, (unsigned long long)m2);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.q3.counters)
+      atomicAdd(p.q3.counters + LBT_CNT_NUMEL, (unsigned long long)p.N * p.POH * p.POW * C);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1430,8 +1464,16 @@ extern "C" int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, 
                                        uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
                                        const float* gamma_q, const float* beta_q, int relu, int8_t* k2, float* run_mean,
                                        float* run_var, double momentum, int stats_minmax, int k, int s, int pad_top, int pad_left,
-                                       int POH, int POW, float* pooled, uint8_t* pidx, void* stream) {
+                                       int POH, int POW, float* pooled, uint8_t* pidx, const lbt_qsite* q_next, void* next_mant,
+                                       int next_kind, void* stream) {
   if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2 || !pooled || !pidx) return LBT_EINVAL;
+  if (q_next) {
+    if (!next_mant || !q_next->ib || !al4(next_mant) || (q_next->noise && !al16(q_next->noise))) return LBT_EINVAL;
+    // u8 holds a 9-bit mantissa only when the tensor is non-negative, i.e. the ReLU is fused here
+    if (next_kind == LBT_MANT_U8 ? (q_next->bits < 2 || q_next->bits > 9 || !relu)
+                                 : (next_kind != LBT_MANT_S8 || q_next->bits < 2 || q_next->bits > 8))
+      return LBT_EUNSUPPORTED;
+  }
   if (H <= 0 || W <= 0 || C <= 0 || POH <= 0 || POW <= 0 || k <= 0 || s <= 0 || pad_top < 0 || pad_left < 0) return LBT_EINVAL;
   if ((run_mean == nullptr) != (run_var == nullptr)) return LBT_EINVAL;
   if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
@@ -1459,6 +1501,8 @@ extern "C" int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, 
   p.one_minus_momentum = (float)(1.0 - momentum);
   p.pooled = pooled;
   p.pidx = pidx;
+  p.q3 = site_from_abi(q_next);
+  p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
   p.N = (uint32_t)n_outer;
   p.H = (uint32_t)H;
   p.W = (uint32_t)W;
@@ -1477,7 +1521,7 @@ extern "C" int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, 
   const size_t smem = (size_t)2 * (kPoolTH + 1) * (kPoolTW + 1) * kPoolCG * sizeof(float4);
   const unsigned grid = (unsigned)total;
   int rc;
-  if (stats_minmax) {
+  if (stats_minmax && (!q_next || q_next->stats_minmax)) {   // one statistics flavour per launch (exact counts are always valid)
     if ((rc = set_smem(bn_fwd2_pool_kernel<true>, smem))) return rc;
     launch_pdl(bn_fwd2_pool_kernel<true>, grid, kPoolThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   } else {

@@ -1420,25 +1420,32 @@ class _ConvBNFn(torch.autograd.Function):
         gq, bq = _bn_params(resc, gamma, beta)
         add_ = _to_mem(add) if add is not None else None
         pooled = pidx = None
-        if (pool is not None and FUSE_POOL_FWD and add is None and next_site is None and Cout == 64 and
-                pool[:4] == (3, 2, 0, 0)):
+        if pool is not None and (add is not None or not FUSE_POOL_FWD or Cout != 64 or pool[:4] != (3, 2, 0, 0)):
+            next_site, next_kind = None, Q.MANT_NONE        # next_site quantises the POOLED tensor: only the one-kernel path runs it
+        if pool is not None and FUSE_POOL_FWD and add is None and Cout == 64 and pool[:4] == (3, 2, 0, 0):
             # the ImageNet stem: BN apply + ReLU + 3x3/2 max-pool in ONE kernel, the fp32 module output never exists
             pk, ps, ppt, ppl, POH, POW = pool
             k2 = torch.empty_like(k1)
             pooled = torch.empty(N, POH, POW, Cout, dtype=torch.float32, device=dev)
             pidx = torch.empty(N, POH, POW, Cout, dtype=torch.uint8, device=dev)
             nz2, off2 = _site_args(resc.qX, k1)
+            qn = nmp = None
+            if next_site is not None:
+                qn = next_site.abi(POH * POW * Cout, dev)
+                nmp = torch.empty(N, POH, POW, Cout, dtype=torch.uint8 if next_kind == Q.MANT_U8 else torch.int8, device=dev)
             if _lib.try_call('lbt_bn_fwd_apply_pooled', _lib.ptr(k1), N, OH, OW, Cout, norm.qX.bits, _lib.ptr(norm.qX.range),
                              _lib.ptr(sums), float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
                              _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), 1 if relu else 0,
                              _lib.ptr(k2), _lib.ptr(norm.X_mean_running), _lib.ptr(norm.X_var_running), float(norm.momentum),
-                             int(resc.qX.target == 0), pk, ps, ppt, ppl, POH, POW, _lib.ptr(pooled), _lib.ptr(pidx), _lib.stream(),
-                             meta=dict(bytes=k1.numel() * 2 + pooled.numel() * 5)):
-                out, nm, relu_mode = None, None, (1 if relu else 0)
+                             int(resc.qX.target == 0), pk, ps, ppt, ppl, POH, POW, _lib.ptr(pooled), _lib.ptr(pidx),
+                             ctypes.addressof(qn) if qn is not None else None, _lib.ptr(nmp), int(next_kind), _lib.stream(),
+                             meta=dict(bytes=k1.numel() * 2 + pooled.numel() * (5 + (1 if nmp is not None else 0)))):
+                out, nm, relu_mode = None, nmp, (1 if relu else 0)
             else:
                 pooled = pidx = None
+                next_site, next_kind = None, Q.MANT_NONE
         if pooled is None:
-            k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, want_fp32)
+            k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, True if pool is not None else want_fp32)
         ctx.conv, ctx.bn, ctx.geom, ctx.xkind, ctx.prep = conv, bn, geom, xkind, prep
         ctx.relu_mode, ctx.has_add = relu_mode, add is not None
         ctx.link_in, ctx.link_out = link_in, link_out
@@ -1535,7 +1542,8 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
             return (pool(y[0]), y[1]) if alias else pool(y)
         Hc, Wc = _conv_geom(conv, x, conv.weight)[11:13]
         pgeom = pool.geometry(Hc, Wc)
-        next_conv = None      # the consumer quantises the POOLED tensor
+        if not FUSE_POOL_FWD:
+            next_conv = None  # two kernels: the consumer quantises the POOLED tensor itself
     next_site, next_kind = None, Q.MANT_NONE
     if next_conv is not None and isinstance(next_conv, Conv2d_q) and next_conv.fuse_bn:
         nb = next_conv.qX.bits
@@ -1543,7 +1551,7 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
             next_site, next_kind = next_conv.qX, Q.MANT_S8
         elif nb == 9 and relu and not next_conv.input_signed:
             next_site, next_kind = next_conv.qX, Q.MANT_U8
-    if next_site is None or add is not None:
+    if next_site is None or add is not None or pool is not None:
         want_fp32 = True
     # measured: folding pays while the dgrad output is narrow (ResNet-18/20 blocks: -1.6 % step time); for the 256..2048-
     # channel block inputs of ResNet-50 the epilogue-bound 1x1 dgrad GEMMs lose more than the coalesced add costs (+3 %)
@@ -1551,7 +1559,7 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     out, nm, xa = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
                                   want_fp32, use_alias, link_in if FUSE_BWD_LINK else None, link_out if FUSE_BWD_LINK else None,
                                   pgeom)
-    if next_site is not None:
+    if next_site is not None and nm.numel():       # (empty: the pooled one-kernel path declined, the consumer quantises itself)
         out._lbt_q = {id(next_site): (nm, next_kind)}
     if not want_fp32:
         out._lbt_hollow = True
@@ -1571,7 +1579,8 @@ def run_layers(layers, x, next_conv=None):
         if isinstance(m, Conv2d_q) and isinstance(nxt, BatchNorm2d_q):
             after = layers[i + 2] if i + 2 < len(layers) else next_conv
             if (FUSE_POOL or FUSE_POOL_FWD) and isinstance(after, MaxPool_q) and i + 2 < len(layers):
-                x = conv_bn_unit(m, nxt, x, pool=after)       # conv -> BN -> ReLU -> max-pool (ImageNet stem)
+                after2 = layers[i + 3] if i + 3 < len(layers) else next_conv
+                x = conv_bn_unit(m, nxt, x, pool=after, next_conv=_first_conv(after2))   # conv -> BN -> ReLU -> max-pool (ImageNet stem)
                 i += 3
                 continue
             x = conv_bn_unit(m, nxt, x, next_conv=_first_conv(after))
