@@ -21,6 +21,13 @@
 namespace lbt {
 namespace {
 
+// resident CTAs per SM the register allocation of the two heaviest kernels is bounded for (A/B builds: -DLBT_BN_BWD1_CTAS=3 ...)
+#ifndef LBT_BN_BWD1_CTAS
+#define LBT_BN_BWD1_CTAS 2
+#endif
+#ifndef LBT_BN_FWD2_CTAS
+#define LBT_BN_FWD2_CTAS 3
+#endif
 constexpr int kThreads = 256;
 constexpr int kRows = 4;  // rows (batch entries) in flight per thread
 
@@ -349,7 +356,7 @@ struct Fwd2Params {
 // per-channel constants where that commutes with the roundings exactly (x * 2^f scalings commute with RN):
 //   y1 * m2 = RN((xq - mean) / den) * m2 = RN((xq - mean) / (den / m2));   RN(xq2 * g) = RN(k2 * (g / m2)).
 template <bool MM>
-__global__ void __launch_bounds__(kThreads, 3) bn_fwd2_kernel(const Fwd2Params p) {
+__global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(const Fwd2Params p) {
   extern __shared__ float s_par[];  // [4*C]: mean, den / m2, gq / m2, bq
   __shared__ uint32_t s_red[16];
   pdl_trigger();
@@ -733,7 +740,7 @@ struct Bwd1Params {
 // RELU: 0 none, 1 mask recomputed from k2, 2 mask from `out`.  ~31 full-rate instructions per element, no conversions;
 // folded constants (exact, powers of two):  RN(xq2 * g) = RN(k2 * (g / m2));  dx2 * mg1 = RN(kg2 * (g * mg1 / mg2)).
 template <bool WIDE, bool MM, int RELU, bool POOL = false>
-__global__ void __launch_bounds__(kThreads, 2) bn_bwd1_kernel(const Bwd1Params p) {
+__global__ void __launch_bounds__(kThreads, LBT_BN_BWD1_CTAS) bn_bwd1_kernel(const Bwd1Params p) {
   extern __shared__ unsigned long long s_acc[];
   __shared__ uint32_t s_red[16];
   pdl_trigger();

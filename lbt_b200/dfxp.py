@@ -54,6 +54,8 @@ class Runtime:
         self._side = None            # side stream: wgrad runs beside dgrad (independent consumers of the same gradient)
         self.overlap = True
         self._prep_pending = False   # begin_step() left the parameter branch running on the side stream
+        self._prep_head_pending = False
+        self._prep_ev = None
         self._noise_req = {}         # (quantiser id, n_inner) wanted by fused tensor-core epilogues
         self._noise_tab = None       # dict(map={key: fp32 view}, jobs=device table, total=groups, keep=[...])
         self._noise_valid = False
@@ -73,7 +75,7 @@ class Runtime:
         key = (site.qid, int(n_inner))
         tab = self._noise_tab
         if tab is not None and self._noise_valid and key in tab['map']:
-            self.join_prep()
+            self.join_prep(head=True)
             return tab['map'][key]
         self._noise_req[key] = True
         return None
@@ -120,21 +122,34 @@ class Runtime:
             main, side = torch.cuda.current_stream(device), self.side_stream(device)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                self.prep.run()
                 self._fill_noise(device)
+                self.prep.run('head')
+                self._prep_ev = torch.cuda.Event()
+                self._prep_ev.record(side)          # noise vectors + the first layer's operands: all the first kernels need
+                self.prep.run('rest')
             self._prep_valid = True
             self._prep_pending = True
+            self._prep_head_pending = True
             return
         if self.prep is not None:
             self.prep.run()
             self._prep_valid = True      # until update_ranges() closes the step
         self._fill_noise(device)
 
-    def join_prep(self):
-        """First consumer of a prepared operand or a noise vector: wait for the parameter branch of begin_step()."""
-        if self._prep_pending:
-            self._prep_pending = False
-            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+    def join_prep(self, layer=None, head=False):
+        """First consumer of a prepared operand or a noise vector: wait for the parameter branch of begin_step() — for its
+        head only (noise vectors and the first layer's operands, an event in the middle of the branch) when that is all the
+        consumer needs."""
+        if not self._prep_pending:
+            return
+        main = torch.cuda.current_stream(self._side.device)
+        if head or (layer is not None and self.prep is not None and layer in self.prep.head):
+            if self._prep_head_pending:
+                self._prep_head_pending = False
+                main.wait_event(self._prep_ev)
+            return
+        self._prep_pending = self._prep_head_pending = False
+        main.wait_stream(self._side)
 
     def zeros_i64(self, n, device):
         """n zeroed int64 slots (16-byte aligned) from the arena; a fresh tensor when the arena is off or full."""
@@ -213,6 +228,8 @@ class ParamPrep:
     def __init__(self, model, runtime, device):
         self.rt = runtime
         self.entries = {}            # module -> dict of prepared tensors
+        self._njobs_of = {}          # module -> number of jobs it contributed (jobs are in module order)
+        self.head, self.head_blocks = set(), 0
         jobs = []
 
         def job(site, x, layout=0, **kw):
@@ -228,6 +245,7 @@ class ParamPrep:
             return out
 
         for m in model.modules():
+            n_before = len(jobs)
             if isinstance(m, Conv2d_q) and m.qW.bits <= 8:
                 kh, kw, Cin, Cout = m.weight.shape
                 e = {}
@@ -260,26 +278,44 @@ class ParamPrep:
                 self.entries[m] = e
             elif isinstance(m, Rescale_q):
                 self.entries[m] = dict(gq=vec(m.qg, m.gamma), bq=vec(m.qb, m.beta))
+            if m in self.entries:
+                self._njobs_of[m] = len(jobs) - n_before
         self.njobs = len(jobs)
         if not jobs:
             return
+        # head: the first weight layer and the batch-norm behind it — what the first kernels of the forward pass need.  Their
+        # jobs come first (module order), so the launch can be cut in two: the step's first convolution waits for the head only
+        # while the rest of the parameters is prepared beside it (Runtime.begin_step / join_prep)
+        ents = list(self.entries)
+        self.head = set(ents[:1])
+        if len(ents) > 1 and isinstance(ents[1], Rescale_q):
+            self.head.add(ents[1])
+        head_jobs = sum(self._njobs_of[m] for m in self.head)
         bj, bc = [], []
+        self.head_blocks = 0
         for i, j in enumerate(jobs):
             n = j.n_outer * j.n_inner
             for c in range(-(-n // self.CHUNK)):
                 bj.append(i)
                 bc.append(c)
+            if i + 1 == head_jobs:
+                self.head_blocks = len(bj)
         self.jobs_dev = _lib.to_device_table(jobs, device)
         self.block_job = torch.tensor(bj, dtype=torch.int32, device=device)
         self.block_chunk = torch.tensor(bc, dtype=torch.int32, device=device)
         self._keep = jobs
 
-    def run(self):
+    def run(self, part=None):
+        """part: None = everything in one launch; 'head' / 'rest' = the two halves of the cut described above."""
         if not self.njobs:
             return
         rt = self.rt
-        _lib.call('lbt_param_prep', _lib.ptr(self.jobs_dev), _lib.ptr(self.block_job), _lib.ptr(self.block_chunk),
-                  self.block_job.numel(), self.CHUNK, rt.seed, _lib.ptr(rt.dev_step), _lib.stream())
+        nb, hb = self.block_job.numel(), self.head_blocks
+        lo, hi = (0, nb) if part is None else ((0, hb) if part == 'head' else (hb, nb))
+        if hi <= lo:
+            return
+        _lib.call('lbt_param_prep', _lib.ptr(self.jobs_dev), self.block_job.data_ptr() + 4 * lo, self.block_chunk.data_ptr() + 4 * lo,
+                  hi - lo, self.CHUNK, rt.seed, _lib.ptr(rt.dev_step), _lib.stream())
 
 
 def _prepared(layer):
@@ -287,7 +323,7 @@ def _prepared(layer):
     rt = layer.qX.runtime
     if rt.prep is None or rt.noise_fn is not None or not getattr(rt, '_prep_valid', False):
         return None
-    rt.join_prep()
+    rt.join_prep(layer)
     return rt.prep.entries.get(layer)
 
 
