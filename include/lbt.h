@@ -393,6 +393,16 @@ int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, in
                      float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
                      double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
                      void* stream);
+/* lbt_bn_fwd_apply with a SECOND consumer quantiser on the module output: a residual block whose first convolution and whose
+ * strided 1x1 shortcut convolution both read the block input quantises it twice (one Conv2d_q `Xq` each, dfxp:287); both run
+ * in the producing kernel.  q_next2 / next_mant2 / next_kind2 as q_next / next_mant / next_kind (q_next must be set too). */
+int lbt_bn_fwd_apply2(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                      const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                      uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                      const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                      float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                      double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                      const lbt_qsite* q_next2, void* next_mant2, int next_kind2, void* stream);
 /*
  * fwd 2 with the stride-2 3x3 max-pool that consumes the module output folded in (the ImageNet stem: conv -> BN -> ReLU ->
  * tf.nn.max_pool 3x3/2 'SAME', dfxp:993-1006): k2 and the statistics / running averages exactly as lbt_bn_fwd_apply; instead

@@ -66,6 +66,10 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_int,
                                  c_void_p, c_void_p, c_int, c_void_p]),
+    'lbt_bn_fwd_apply2': (c_int, [c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p, c_void_p, c_float, c_int,
+                                  c_void_p, c_void_p, c_u64, c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_double, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     # k1, n_outer, H, W, C, bits1, ib1, sums, eps, bits2, ib2, noise2, seed, offset2, dev_step, counters2, gamma_q, beta_q, relu,
     # k2, run_mean, run_var, momentum, stats_minmax, k, s, pad_top, pad_left, POH, POW, pooled, pidx, q_next, next_mant, next_kind, stream
     'lbt_bn_fwd_apply_pooled': (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int,

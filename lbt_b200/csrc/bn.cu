@@ -349,14 +349,17 @@ struct Fwd2Params {
   float momentum, one_minus_momentum;   // the reference's Python constants `momentum` and `(1-momentum)`, each rounded to fp32
   QSite q3;               // optional: the consuming layer's input quantiser (bits == 0: off)
   uint8_t* next_mant;     // its mantissas (u8 for a 9-bit non-negative tensor, s8 otherwise: same byte)
+  QSite q4;               // optional: a SECOND consumer's input quantiser (a block's strided 1x1 shortcut convolution reads the
+  uint8_t* next_mant2;    // same tensor as its first 3x3 through its own quantiser, dfxp:287 in both Conv2d_q)
 };
 
 // MM: every quantiser of the launch keeps min/max statistics (LBT_STATS_MINMAX).  Per element: ~28 full-rate instructions,
 // no conversion-pipe instruction (see "conversion-free arithmetic" above); power-of-two scale factors are folded into the
 // per-channel constants where that commutes with the roundings exactly (x * 2^f scalings commute with RN):
 //   y1 * m2 = RN((xq - mean) / den) * m2 = RN((xq - mean) / (den / m2));   RN(xq2 * g) = RN(k2 * (g / m2)).
-template <bool MM>
-__global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(const Fwd2Params p) {
+// Q4: the second-consumer instantiation (its own registers: only the HBM-bound add + out launches in front of a strided block use it)
+template <bool MM, bool Q4 = false>
+__global__ void __launch_bounds__(kThreads, Q4 ? 2 : LBT_BN_FWD2_CTAS) bn_fwd2_kernel(const Fwd2Params p) {
   extern __shared__ float s_par[];  // [4*C]: mean, den / m2, gq / m2, bq
   __shared__ uint32_t s_red[16];
   pdl_trigger();
@@ -408,6 +411,14 @@ __global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(con
   }
   uint32_t m1 = 0, m2 = 0;
   float mx3 = -INFINITY, mn3 = INFINITY;
+  QC c4 = c2;
+  uint64_t off4 = 0;
+  if (Q4) {
+    c4 = make_qc(p.q4.bits, __ldg(p.q4.ib));
+    off4 = site_offset(p.q4);
+  }
+  uint32_t l1 = 0, l2 = 0;
+  float mx4 = -INFINITY, mn4 = INFINITY;
   const bool has_add = p.add != nullptr, relu = p.relu != 0, has_out = p.out != nullptr;
   for (uint64_t tile = blockIdx.x; tile < p.t.total_tiles; tile += gridDim.x) {
     const uint32_t rg = (uint32_t)(tile / p.t.chunks), chk = (uint32_t)(tile % p.t.chunks);
@@ -420,6 +431,11 @@ __global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(con
     if (nxt) {
       const float4 t = site_noise(p.q3, v, off3);
       u3[0] = t.x; u3[1] = t.y; u3[2] = t.z; u3[3] = t.w;
+    }
+    float u4n[4] = {0.f, 0.f, 0.f, 0.f};
+    if (Q4) {
+      const float4 t = site_noise(p.q4, v, off4);
+      u4n[0] = t.x; u4n[1] = t.y; u4n[2] = t.z; u4n[3] = t.w;
     }
     float nmean[4], den[4], rden[4], g[4], b[4];
 #pragma unroll
@@ -474,6 +490,12 @@ __global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(con
             for (int j = 0; j < 4; ++j) t3[j] = sq_scaled<MM>(__fmul_rn(o[j], c3.m), u3[j], c3, mx3, mn3, m1, m2);
             *reinterpret_cast<uint32_t*>(p.next_mant + idx) = tm_pack4(t3);
           }
+          if (Q4) {                                                                     // the second consumer's Xq
+            float t4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t4[j] = sq_scaled<MM>(__fmul_rn(o[j], c4.m), u4n[j], c4, mx4, mn4, l1, l2);
+            *reinterpret_cast<uint32_t*>(p.next_mant2 + idx) = tm_pack4(t4);
+          }
         }
     }
   }
@@ -482,6 +504,10 @@ __global__ void __launch_bounds__(kThreads, LBT_BN_FWD2_CTAS) bn_fwd2_kernel(con
   if (nxt) {
     if (MM) mm_to_counts(c3, mx3, mn3, m1, m2);
     publish_counters(p.q3.counters, m1, m2, p.t.n_outer * p.t.n_inner, s_red);
+  }
+  if (Q4) {
+    if (MM) mm_to_counts(c4, mx4, mn4, l1, l2);
+    publish_counters(p.q4.counters, l1, l2, p.t.n_outer * p.t.n_inner, s_red);
   }
 }
 
@@ -1407,14 +1433,20 @@ extern "C" int lbt_bn_fwd_quant_stats(const float* x, size_t n_outer, size_t n_i
   return check_launch("lbt_bn_fwd_quant_stats");
 }
 
-extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
-                                const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
-                                uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
-                                const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
-                                float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
-                                double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
-                                void* stream) {
+static int bn_fwd_apply_run(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                            const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                            uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                            const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                            float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                            double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                            const lbt_qsite* q_next2, void* next_mant2, int next_kind2, void* stream) {
   if (!k1 || !ib1 || !sums || !ib2 || !gamma_q || !beta_q || !k2) return LBT_EINVAL;
+  if (q_next2) {
+    if (!q_next || !next_mant2 || !q_next2->ib || !al4(next_mant2) || (q_next2->noise && !al16(q_next2->noise))) return LBT_EINVAL;
+    if (next_kind2 == LBT_MANT_U8 ? (q_next2->bits < 2 || q_next2->bits > 9 || !relu)
+                                  : (next_kind2 != LBT_MANT_S8 || q_next2->bits < 2 || q_next2->bits > 8))
+      return LBT_EUNSUPPORTED;
+  }
   if (!out && !q_next) return LBT_EINVAL;
   if (bits1 < 2 || bits1 > 8 || bits2 < 2 || bits2 > 8) return LBT_EUNSUPPORTED;
   if (q_next) {
@@ -1431,9 +1463,10 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   Fwd2Params p{};
   unsigned grid;
   // one statistics flavour per launch: min/max only when EVERY site of the launch asked for it (exact counts are always valid)
-  const bool mm = stats_minmax && (!q_next || q_next->stats_minmax);
-  int rc = mm ? make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel<true>, (size_t)4 * C * 4))
-              : make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(bn_fwd2_kernel<false>, (size_t)4 * C * 4));
+  const bool mm = stats_minmax && (!q_next || q_next->stats_minmax) && (!q_next2 || q_next2->stats_minmax);
+  void (*kern)(const Fwd2Params) = q_next2 ? (mm ? bn_fwd2_kernel<true, true> : bn_fwd2_kernel<false, true>)
+                                           : (mm ? bn_fwd2_kernel<true, false> : bn_fwd2_kernel<false, false>);
+  int rc = make_tiling(p.t, n_outer, n_inner, C, grid, ctas_per_sm(kern, (size_t)4 * C * 4));
   if (rc) return rc;
   p.k1 = k1;
   p.bits1 = bits1;
@@ -1455,15 +1488,37 @@ extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner
   p.one_minus_momentum = (float)(1.0 - momentum);   // dfxp:606: `(1-momentum)` is evaluated in Python (double), THEN becomes an fp32 constant
   p.q3 = site_from_abi(q_next);
   p.next_mant = reinterpret_cast<uint8_t*>(next_mant);
+  p.q4 = site_from_abi(q_next2);
+  p.next_mant2 = reinterpret_cast<uint8_t*>(next_mant2);
   const size_t smem = (size_t)4 * C * 4;
-  if (mm) {
-    if ((rc = set_smem(bn_fwd2_kernel<true>, smem))) return rc;
-    launch_pdl(bn_fwd2_kernel<true>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  } else {
-    if ((rc = set_smem(bn_fwd2_kernel<false>, smem))) return rc;
-    launch_pdl(bn_fwd2_kernel<false>, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
-  }
+  if ((rc = set_smem(kern, smem))) return rc;
+  launch_pdl(kern, grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream), p);
   return check_launch("lbt_bn_fwd_apply");
+}
+
+extern "C" int lbt_bn_fwd_apply(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                                const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                                uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                                const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                                float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                                double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                                void* stream) {
+  return bn_fwd_apply_run(k1, n_outer, n_inner, C, bits1, ib1, sums, eps, bits2, ib2, noise2, seed, offset2, dev_step, counters2,
+                          gamma_q, beta_q, add, relu, k2, out, batch_mean, batch_var, run_mean, run_var, momentum, stats_minmax,
+                          q_next, next_mant, next_kind, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int lbt_bn_fwd_apply2(const int8_t* k1, size_t n_outer, size_t n_inner, int C, int bits1, const int32_t* ib1,
+                                 const int64_t* sums, float eps, int bits2, const int32_t* ib2, const float* noise2,
+                                 uint64_t seed, uint64_t offset2, const uint64_t* dev_step, uint64_t* counters2,
+                                 const float* gamma_q, const float* beta_q, const float* add, int relu, int8_t* k2,
+                                 float* out, float* batch_mean, float* batch_var, float* run_mean, float* run_var,
+                                 double momentum, int stats_minmax, const lbt_qsite* q_next, void* next_mant, int next_kind,
+                                 const lbt_qsite* q_next2, void* next_mant2, int next_kind2, void* stream) {
+  if (!q_next2) return LBT_EINVAL;
+  return bn_fwd_apply_run(k1, n_outer, n_inner, C, bits1, ib1, sums, eps, bits2, ib2, noise2, seed, offset2, dev_step, counters2,
+                          gamma_q, beta_q, add, relu, k2, out, batch_mean, batch_var, run_mean, run_var, momentum, stats_minmax,
+                          q_next, next_mant, next_kind, q_next2, next_mant2, next_kind2, stream);
 }
 
 extern "C" int lbt_bn_fwd_apply_pooled(const int8_t* k1, size_t n_outer, int H, int W, int C, int bits1, const int32_t* ib1,

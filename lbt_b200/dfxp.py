@@ -1267,9 +1267,10 @@ def _bn_fwd1(bn, xm_):
     return k1, sums
 
 
-def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_NONE, want_fp32=True):
+def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_NONE, want_fp32=True, next2=None):
     """BN forward pass 2 (+ residual add, ReLU, the consumer's input quantiser): (k2, out or None, next mantissas or None,
-    relu_mode)."""
+    relu_mode).  next2 = (site, kind): a second consumer's input quantiser; its mantissas come back as ``next2[2]`` (a list
+    cell the caller passes in)."""
     norm, resc = bn[0], bn[1]
     rt = norm.qX.runtime
     N, C = k1.shape[0], k1.shape[-1]
@@ -1283,14 +1284,22 @@ def _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site=None, next_kind=Q.MANT_
     if next_site is not None:
         qn = next_site.abi(n_inner, dev)
         nm = torch.empty(k1.shape, dtype=torch.uint8 if next_kind == Q.MANT_U8 else torch.int8, device=dev)
-    _lib.call('lbt_bn_fwd_apply', _lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range), _lib.ptr(sums),
-              float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
-              _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add_),
-              1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
-              _lib.ptr(norm.X_var_running), float(norm.momentum), int(resc.qX.target == 0),
-              ctypes.addressof(qn) if qn is not None else None, _lib.ptr(nm), int(next_kind), _lib.stream(),
-              meta=dict(bytes=k1.numel() * (2 + (4 if want_fp32 else 0) + (4 if add_ is not None else 0) +
-                                            (1 if nm is not None else 0))))
+    args = (_lib.ptr(k1), N, n_inner, C, norm.qX.bits, _lib.ptr(norm.qX.range), _lib.ptr(sums),
+            float(norm.eps), resc.qX.bits, _lib.ptr(resc.qX.range), _lib.ptr(nz2), rt.seed, off2,
+            _lib.ptr(rt.dev_step), _lib.ptr(resc.qX.counters), _lib.ptr(gq), _lib.ptr(bq), _lib.ptr(add_),
+            1 if relu else 0, _lib.ptr(k2), _lib.ptr(out), None, None, _lib.ptr(norm.X_mean_running),
+            _lib.ptr(norm.X_var_running), float(norm.momentum), int(resc.qX.target == 0),
+            ctypes.addressof(qn) if qn is not None else None, _lib.ptr(nm), int(next_kind))
+    nbytes = k1.numel() * (2 + (4 if want_fp32 else 0) + (4 if add_ is not None else 0) + (1 if nm is not None else 0))
+    if next2 is not None and qn is not None:
+        site2, kind2 = next2[0], next2[1]
+        qn2 = site2.abi(n_inner, dev)
+        nm2 = torch.empty(k1.shape, dtype=torch.uint8 if kind2 == Q.MANT_U8 else torch.int8, device=dev)
+        _lib.call('lbt_bn_fwd_apply2', *args, ctypes.addressof(qn2), _lib.ptr(nm2), int(kind2), _lib.stream(),
+                  meta=dict(bytes=nbytes + k1.numel()))
+        next2[2] = nm2
+    else:
+        _lib.call('lbt_bn_fwd_apply', *args, _lib.stream(), meta=dict(bytes=nbytes))
     return k2, out, nm, relu_mode
 
 
@@ -1440,7 +1449,8 @@ class _ConvBNFn(torch.autograd.Function):
     the results are bit-identical (tests/test_fused_gpu.py)."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias, link_in, link_out, pool=None):
+    def forward(ctx, x, weight, gamma, beta, add, conv, bn, relu, next_site, next_kind, want_fp32, alias, link_in, link_out, pool=None,
+                next2=None):
         geom = _conv_geom(conv, x, weight)
         N, H, W, Cin, Cout, kh, kw, sh, sw, pt, pl, OH, OW = geom
         norm, resc = bn[0], bn[1]
@@ -1481,7 +1491,8 @@ class _ConvBNFn(torch.autograd.Function):
                 pooled = pidx = None
                 next_site, next_kind = None, Q.MANT_NONE
         if pooled is None:
-            k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, True if pool is not None else want_fp32)
+            k2, out, nm, relu_mode = _bn_fwd2(bn, k1, sums, gq, bq, add_, relu, next_site, next_kind, True if pool is not None else want_fp32,
+                                              next2=next2 if pool is None else None)
         ctx.conv, ctx.bn, ctx.geom, ctx.xkind, ctx.prep = conv, bn, geom, xkind, prep
         ctx.relu_mode, ctx.has_add = relu_mode, add is not None
         ctx.link_in, ctx.link_out = link_in, link_out
@@ -1539,7 +1550,7 @@ class _ConvBNFn(torch.autograd.Function):
         else:
             dx, dW, _ = _conv_backward(conv, ctx.geom, xm, ctx.xkind, wm, ctx.prep, gm, need_dx, need_dw, False, addend=addend, link=li)
         return ((_from_mem(dx) if dx is not None else None), dW, dgamma, dbeta,
-                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None, None)
+                (_from_mem(d_add) if d_add is not None else None), None, None, None, None, None, None, None, None, None, None, None)
 
 
 FUSE_POOL = os.environ.get('LBT_FUSE_POOL', '0') == '1'   # module switch: a MaxPool_q right behind a fused unit runs its backward inside the
@@ -1550,6 +1561,8 @@ FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lb
                       # tensor is one wave of CTAs.  Bit-identical; measured no faster on B200 (1.77 vs 1.75 ms ResNet-20
                       # step: the barrier + second fp64 prologue cost what the saved launch gains), so off by default
 FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused units (tests compare both settings)
+FUSE_NEXT2 = os.environ.get('LBT_FUSE_NEXT2', '1') != '0'   # a strided block's shortcut convolution gets its input mantissas from the
+                      # kernel that produced the block input too (lbt_bn_fwd_apply2) instead of a separate lbt_quantize
 
 
 def _unit_fusable(conv, bn, x):
@@ -1580,13 +1593,25 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
         pgeom = pool.geometry(Hc, Wc)
         if not FUSE_POOL_FWD:
             next_conv = None  # two kernels: the consumer quantises the POOLED tensor itself
-    next_site, next_kind = None, Q.MANT_NONE
-    if next_conv is not None and isinstance(next_conv, Conv2d_q) and next_conv.fuse_bn:
-        nb = next_conv.qX.bits
-        if nb <= 8:
-            next_site, next_kind = next_conv.qX, Q.MANT_S8
-        elif nb == 9 and relu and not next_conv.input_signed:
-            next_site, next_kind = next_conv.qX, Q.MANT_U8
+    next_conv2 = None
+    if isinstance(next_conv, (tuple, list)):      # two consumers of the result (a block's first 3x3 and its 1x1 shortcut convolution)
+        next_conv, next_conv2 = (tuple(next_conv) + (None, None))[:2]
+
+    def _site_of(nc):
+        if nc is not None and isinstance(nc, Conv2d_q) and nc.fuse_bn:
+            nb = nc.qX.bits
+            if nb <= 8:
+                return nc.qX, Q.MANT_S8
+            if nb == 9 and relu and not nc.input_signed:
+                return nc.qX, Q.MANT_U8
+        return None, Q.MANT_NONE
+
+    next_site, next_kind = _site_of(next_conv)
+    next2 = None
+    if next_site is not None and next_conv2 is not None and pool is None and FUSE_NEXT2:
+        s2, k2_ = _site_of(next_conv2)
+        if s2 is not None and s2 is not next_site:
+            next2 = [s2, k2_, None]
     if next_site is None or add is not None or pool is not None:
         want_fp32 = True
     # measured: folding pays while the dgrad output is narrow (ResNet-18/20 blocks: -1.6 % step time); for the 256..2048-
@@ -1594,9 +1619,11 @@ def conv_bn_unit(conv, bn, x, add=None, relu=False, next_conv=None, want_fp32=Tr
     use_alias = bool(alias and x.requires_grad and not getattr(x, '_lbt_hollow', False) and conv.weight.shape[2] <= 128)
     out, nm, xa = _ConvBNFn.apply(x, conv.weight, bn[1].gamma, bn[1].beta, add, conv, bn, relu, next_site, next_kind,
                                   want_fp32, use_alias, link_in if FUSE_BWD_LINK else None, link_out if FUSE_BWD_LINK else None,
-                                  pgeom)
+                                  pgeom, next2)
     if next_site is not None and nm.numel():       # (empty: the pooled one-kernel path declined, the consumer quantises itself)
         out._lbt_q = {id(next_site): (nm, next_kind)}
+        if next2 is not None and next2[2] is not None:
+            out._lbt_q[id(next2[0])] = (next2[2], next2[1])
     if not want_fp32:
         out._lbt_hollow = True
     if alias:
@@ -1635,7 +1662,11 @@ def _first_conv(m):
     if isinstance(m, Conv2d_q):
         return m
     if isinstance(m, ResidualBlock_q):
-        return m.residual[0] if isinstance(m.residual[0], Conv2d_q) else None
+        first = m.residual[0] if isinstance(m.residual[0], Conv2d_q) else None
+        sc = list(m.shortcut) if isinstance(m.shortcut, nn.Sequential) else []
+        if first is not None and sc and isinstance(sc[0], Conv2d_q):
+            return (first, sc[0])          # both read the block input, each through its own quantiser
+        return first
     return None
 
 
@@ -2008,6 +2039,8 @@ class ResidualBlock_q(nn.Module):
             # unit's BN backward pass 1 in its epilogue (_BwdLink)
             link = _BwdLink()
             r, xs = conv_bn_unit(res[0], res[1], x, next_conv=res[2], want_fp32=False, alias=True, link_out=link)
+            if xs is not x and getattr(x, '_lbt_q', None) is not None:
+                xs._lbt_q = x._lbt_q       # mantissas made for the shortcut convolution's quantiser travel with the alias
             for i in range(2, len(res) - 2, 2):
                 nxt = _BwdLink()
                 r = conv_bn_unit(res[i], res[i + 1], r, next_conv=res[i + 2], want_fp32=False, link_in=link, link_out=nxt)
