@@ -23,7 +23,8 @@ from ncu_summary import METRICS  # noqa: E402
 CLASSES = [
     ('stem_wgrad', 'lbt_conv_i8_wgrad_c3'), ('conv_wgrad', 'lbt_conv_i8_wgrad'), ('conv_ldg_wgrad', 'lbt_conv_i8_wgrad'),
     ('conv_fprop', 'lbt_conv_i8_fprop'), ('conv_ldg_kernel', 'lbt_conv_i8_fprop'), ('conv_halo', 'lbt_conv_i8_fprop'),
-    ('gemm_i8', 'lbt_gemm_i8'), ('bn_fwd2', 'lbt_bn_fwd_apply'), ('bn_fwd1', 'lbt_bn_fwd_quant_stats'),
+    ('gemm_i8', 'lbt_gemm_i8'), ('bn_fwd2_pool', 'lbt_bn_fwd_apply_pooled'), ('bn_fwd2_kernel<(bool)1, (bool)1>', 'lbt_bn_fwd_apply2'),
+    ('bn_fwd2_kernel<(bool)0, (bool)1>', 'lbt_bn_fwd_apply2'), ('bn_fwd2', 'lbt_bn_fwd_apply'), ('bn_fwd1', 'lbt_bn_fwd_quant_stats'),
     ('bn_bwd1', 'lbt_bn_bwd_quant_stats'), ('bn_bwd2', 'lbt_bn_bwd_apply'), ('quantize_', 'lbt_quantize'),
     ('maxpool_fwd', 'lbt_maxpool_fwd'), ('maxpool_bwd', 'lbt_maxpool_bwd'), ('param_prep', 'lbt_param_prep'),
     ('finalize_multi', 'lbt_finalize_multi'), ('dp_step', 'lbt_dp_step'),
