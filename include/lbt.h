@@ -233,6 +233,20 @@ int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C,
                       void* stream);
 
 /*
+ * Stride-1 convolution of a 9..16-bit source given as its two byte planes k = 256 * hi + lo (hi s8, lo u8 — what
+ * lbt_bn_bwd_apply emits for a 16-bit gradient quantiser, BASELINE config 5) with an 8-bit filter, as ONE implicit GEMM with two
+ * accumulators in tensor memory: out[(n,oh,ow), co] = fp32(256 * (hi * W) + (lo * W)) * 2^e (+ addend), one rounding — the
+ * arithmetic of lbt_gemm_i8_dual without the im2col matrices of the two planes.  With the rotated filter this is the stride-1
+ * input gradient tf.gradients(y, X, gradq) (dynamic_fixed_point.py:305).  Shapes of the TMA halo kernel with a filter bank and
+ * two patches per ring slot in shared memory (C == 64, 3x3 ... 5x5, Cout <= 128); else LBT_EUNSUPPORTED: lbt_im2col_i8 +
+ * lbt_gemm_i8_dual.  e = exp_const + *ib_src + *ib_w.
+ */
+int lbt_conv_i8_fprop_dual(const int8_t* src_hi, const uint8_t* src_lo, int N, int H, int W, int C, const void* wp, int w_kind,
+                           size_t ldw, int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW,
+                           const int32_t* ib_src, const int32_t* ib_w, int exp_const, float* out, size_t ldc,
+                           const float* addend, void* stream);
+
+/*
  * Input gradient of a convolution of ANY stride as an implicit GEMM (no im2col matrix in HBM), the transposed
  * gather of lbt_im2col_i8(transposed = 1) done by the kernel's loader warps: dx[(n,h,w), ci] = 2^e * sum over taps
  * (r,s) and co of g[n, (h + pad_top - r)/sh, (w + pad_left - s)/sw, co] * wp[ci, (r*kw + s)*Cout + co] where

@@ -59,6 +59,7 @@ struct HaloParams {
   BnqParams bnq;
   int remap;                     // fp32 rows go to out + img * rs_n + oy * rs_y + ox * rs_x (OutRemap) instead of row * ldc
   int sector_f32;                // fp32 epilogue through the .16x256b load shape (full-sector stores): N % 16 == 0, 8-byte aligned rows
+  uint32_t idesc2;               // DUAL: instruction descriptor of the low-plane MMAs (A = u8)
   long long rs_n, rs_y, rs_x;
 };
 
@@ -78,12 +79,19 @@ __device__ __forceinline__ uint64_t make_desc_halo(uint32_t smem_addr, int m, ui
 
 // EPI epilogue warps (a multiple of 4: EPI / 4 per TMEM lane quadrant, interleaved over the 16-column chunks).
 // FUSED: the re-quantising epilogue (two instantiations per shape: either epilogue compiles without the other's registers).
-template <int BN, int EPI, bool FUSED>
+// DUAL: the source is a 9..16-bit mantissa split into byte planes k = 256 * hi + lo (hi s8 through tmA, lo u8 through tmA2: the
+// 16-bit gradients of BASELINE config 5).  Both planes' patches arrive per tile, both are multiplied with the SAME resident filter
+// bank into two accumulators (BN columns apart), and the fp32 epilogue rounds 256 * acc_hi + acc_lo ONCE — lbt_gemm_i8_dual's
+// arithmetic without the two im2col matrices it needed for a 3x3 layer.  fp32 sector epilogue only (host-checked).
+template <int BN, int EPI, bool FUSED, bool DUAL = false>
 __global__ void __launch_bounds__(32 * (2 + EPI), EPI == 8 ? 2 : 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                 const HaloParams p) {
   constexpr int kThreadsH = 32 * (2 + EPI);
-  constexpr int kAccStages = EPI == 8 ? (BN <= 64 ? 4 : 2) : (512 / BN > 4 ? 4 : 512 / BN);
-  constexpr int kTmemCols = kAccStages * BN;
+  constexpr int kAccW = (DUAL ? 2 : 1) * BN;   // tensor-memory columns of one accumulator stage
+  constexpr int kAccStages = DUAL ? (EPI == 8 ? 256 / kAccW : 512 / kAccW) : (EPI == 8 ? (BN <= 64 ? 4 : 2) : (512 / BN > 4 ? 4 : 512 / BN));
+  constexpr int kTmemCols = kAccStages * kAccW;
+  static_assert(kAccStages >= 1, "tensor memory budget");
   constexpr int kSub = EPI / 4;   // epilogue warps per quadrant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -116,6 +124,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     s_abort = 0;
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
+    if (DUAL) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, kTmemCols);
@@ -144,9 +153,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t img = fastdiv(tile, p.d_tiles_img), t2 = tile - img * p.d_tiles_img.d;
         const uint32_t ty = fastdiv(t2, p.d_tiles_x), tx = t2 - ty * p.d_tiles_x.d;
         if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_halo_error))) break;
-        mbar_expect_tx(&full_bar[stage], p.patch_bytes);
+        mbar_expect_tx(&full_bar[stage], (DUAL ? 2u : 1u) * p.patch_bytes);
         tma_load_tiled_4d(&tmA, &full_bar[stage], sA + (size_t)stage * p.stage_bytes, 0, (int)(tx * kPatchW) - p.pl,
                           (int)(ty * kPatchH) - p.pt, (int)img);
+        if (DUAL)   // the low plane's patch: second half of the stage
+          tma_load_tiled_4d(&tmA2, &full_bar[stage], sA + (size_t)stage * p.stage_bytes + p.stage_bytes / 2, 0, (int)(tx * kPatchW) - p.pl,
+                            (int)(ty * kPatchH) - p.pt, (int)img);
         if (++stage == p.nstages) {
           stage = 0;
           phase ^= 1;
@@ -162,11 +174,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag, &g_halo_error))) break;
         if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_halo_error))) break;
         fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * kAccW;
         const uint32_t sa = smem_u32(sA + (size_t)stage * p.stage_bytes);
         const uint64_t da0 = make_desc_halo(sa, (int)p.mode, sbo);   // + offset >> 4: the start-address field cannot carry out
 #pragma unroll 4
         for (uint32_t j = 0; j < n_mma; ++j) umma_i8(d_tmem, da0 + s_aoff[j], s_bdesc[j], p.idesc, j ? 1u : 0u);
+        if (DUAL) {   // the low plane against the same filter bank, into the second accumulator
+          const uint64_t db0 = make_desc_halo(sa + p.stage_bytes / 2, (int)p.mode, sbo);
+#pragma unroll 4
+          for (uint32_t j = 0; j < n_mma; ++j) umma_i8(d_tmem + BN, db0 + s_aoff[j], s_bdesc[j], p.idesc2, j ? 1u : 0u);
+        }
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full_bar[acc]);
         if (++stage == p.nstages) {
@@ -225,7 +242,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      const uint32_t taddr = tmem_base + acc * kAccW + ((quad * 32u) << 16);
       if (fused && bst.tiles >= (uint32_t)kBnqFlushTiles) {
         bnq_flush(p.bnq, my_stat, 0, BN, p.N, lane);
         bst.tiles = 0;
@@ -253,9 +270,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int n = 0; n < 2; ++n)
                 if (rv[j]) ad[2 * j + n] = __ldcs(reinterpret_cast<const float2*>(p.addend + ob2 + j * ystep + c + 8 * n));
           }
-          uint32_t va[8], vb[8];
+          uint32_t va[8], vb[8], wa[8], wb[8];
           tmem_ld_16x256b_x2(taddr + c, va);                 // lanes 0..15 of the quadrant: patch rows 4 * quad + {0, 1}
           tmem_ld_16x256b_x2(taddr + c + (16u << 16), vb);   // lanes 16..31:                             + {2, 3}
+          if (DUAL) {
+            tmem_ld_16x256b_x2(taddr + BN + c, wa);
+            tmem_ld_16x256b_x2(taddr + BN + c + (16u << 16), wb);
+          }
           tmem_ld_wait();
           float2 bs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
           if (p.bias) {
@@ -268,7 +289,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int n = 0; n < 2; ++n) {
               const uint32_t* src = j < 2 ? va : vb;
-              float f0 = __int2float_rn((int)src[4 * n + 2 * (j & 1)]) * scale, f1 = __int2float_rn((int)src[4 * n + 2 * (j & 1) + 1]) * scale;
+              float f0, f1;
+              if (DUAL) {   // 256 * (hi . W) + (lo . W): exact in 64 bits, ONE rounding to fp32 (lbt_gemm_i8_dual's arithmetic)
+                const uint32_t* slo = j < 2 ? wa : wb;
+                f0 = __ll2float_rn((long long)(int)src[4 * n + 2 * (j & 1)] * 256ll + (long long)(int)slo[4 * n + 2 * (j & 1)]) * scale;
+                f1 = __ll2float_rn((long long)(int)src[4 * n + 2 * (j & 1) + 1] * 256ll + (long long)(int)slo[4 * n + 2 * (j & 1) + 1]) * scale;
+              } else {
+                f0 = __int2float_rn((int)src[4 * n + 2 * (j & 1)]) * scale;
+                f1 = __int2float_rn((int)src[4 * n + 2 * (j & 1) + 1]) * scale;
+              }
               if (p.bias) {
                 f0 = __fadd_rn(f0, n ? bs[1].x : bs[0].x);
                 f1 = __fadd_rn(f1, n ? bs[1].y : bs[0].y);
@@ -368,26 +397,30 @@ void* driver_fn(const char* name) {
   return f;
 }
 
-template <int BN, int EPI, bool FUSED>
-int launch_halo_impl(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+template <int BN, int EPI, bool FUSED, bool DUAL = false>
+int launch_halo_impl(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem,
+                     cudaStream_t st) {
   static size_t attr_done[16] = {};
   const int dev = device_info().device;
   if (attr_done[dev] < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, EPI, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, EPI, FUSED, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_kernel)");
       return LBT_ECUDA;
     }
     attr_done[dev] = smem;
   }
-  launch_pdl(conv_halo_kernel<BN, EPI, FUSED>, grid, 32 * (2 + EPI), smem, st, ta, tb, p);
+  launch_pdl(conv_halo_kernel<BN, EPI, FUSED, DUAL>, grid, 32 * (2 + EPI), smem, st, ta, ta2, tb, p);
   g_halo_launches.fetch_add(1, std::memory_order_relaxed);
-  return check_launch("lbt_conv_i8_fprop");
+  return check_launch(DUAL ? "lbt_conv_i8_fprop_dual" : "lbt_conv_i8_fprop");
 }
 
 template <int BN, int EPI>
-int launch_halo(const CUtensorMap& ta, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem, cudaStream_t st) {
-  return p.bnq.q.bits != 0 ? launch_halo_impl<BN, EPI, true>(ta, tb, p, grid, smem, st) : launch_halo_impl<BN, EPI, false>(ta, tb, p, grid, smem, st);
+int launch_halo(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const HaloParams& p, unsigned grid, size_t smem,
+                cudaStream_t st, bool dual) {
+  if (dual) return launch_halo_impl<BN, EPI, false, true>(ta, ta2, tb, p, grid, smem, st);
+  return p.bnq.q.bits != 0 ? launch_halo_impl<BN, EPI, true>(ta, ta2, tb, p, grid, smem, st)
+                           : launch_halo_impl<BN, EPI, false>(ta, ta2, tb, p, grid, smem, st);
 }
 
 std::atomic<int> g_use_tma_halo{1};   // bit 0: on; bit 1 (tests): take ragged images whatever the patch fill ratio
@@ -414,7 +447,9 @@ bool conv_halo_applies(int N, int OH, int OW, int C, int Cout, int kh, int kw, i
 int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                   int kw, int pt, int pl, int OH, int OW, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
                   float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream,
-                  const OutRemap* remap) {
+                  const OutRemap* remap, const void* src_lo) {
+  const bool dual = src_lo != nullptr;   // src = high byte plane (s8), src_lo = low byte plane (u8): k = 256 * hi + lo
+  if (dual && (q_out || !out)) return LBT_EINVAL;
   const DeviceInfo& di = device_info();
   static EncodeTiledFn enc_tiled = reinterpret_cast<EncodeTiledFn>(driver_fn("cuTensorMapEncodeTiled"));
   if (!enc_tiled) return LBT_ECUDA;
@@ -451,6 +486,7 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
   p.out = out;
   p.ldc = ldc;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
+  p.idesc2 = tc::make_idesc_i8(false, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
   p.bnq.q = site_from_abi(q_out);
   p.bnq.k = k_out;
   p.bnq.sums = reinterpret_cast<long long*>(sums);
@@ -474,6 +510,10 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
     p.sector_f32 = !q_out && out && Cout % 16 == 0 && al &&
                    (p.remap ? even(p.rs_n) && even(p.rs_y) && even(p.rs_x) : even((long long)ldc)) &&
                    sector_on;
+  }
+  if (dual) {
+    if (!p.sector_f32) return LBT_EUNSUPPORTED;   // the dual mode lives in the sector epilogue only
+    p.stage_bytes *= 2;                           // both planes' patches per ring slot
   }
   const size_t b_bytes = (size_t)kh * kw * p.b_block;
   // two CTAs per SM (8 epilogue warps each) when two filter banks + rings fit; else one CTA with 16 epilogue warps
@@ -513,11 +553,24 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
       return LBT_ECUDA;
     }
   }
+  CUtensorMap ta2 = ta;
+  if (dual) {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
+    cuuint32_t box[4] = {(cuuint32_t)C, p.halo_w, halo_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc_tiled(&ta2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(src_lo), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(halo patch, low plane)");
+      return LBT_ECUDA;
+    }
+  }
   const uint64_t cap = (uint64_t)di.sm_count * (two ? 2 : 1);
   const unsigned grid = (unsigned)(p.m_tiles < cap ? p.m_tiles : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (two) return bn == 64 ? launch_halo<64, 8>(ta, tb, p, grid, smem, st) : launch_halo<128, 8>(ta, tb, p, grid, smem, st);
-  return bn == 64 ? launch_halo<64, 16>(ta, tb, p, grid, smem, st) : launch_halo<128, 16>(ta, tb, p, grid, smem, st);
+  if (two) return bn == 64 ? launch_halo<64, 8>(ta, ta2, tb, p, grid, smem, st, dual) : launch_halo<128, 8>(ta, ta2, tb, p, grid, smem, st, dual);
+  return bn == 64 ? launch_halo<64, 16>(ta, ta2, tb, p, grid, smem, st, dual) : launch_halo<128, 16>(ta, ta2, tb, p, grid, smem, st, dual);
 }
 
 int conv_halo_debug_error() {
@@ -528,6 +581,24 @@ int conv_halo_debug_error() {
 }
 
 }  // namespace lbt
+
+extern "C" int lbt_conv_i8_fprop_dual(const int8_t* src_hi, const uint8_t* src_lo, int N, int H, int W, int C, const void* wp, int w_kind,
+                                      size_t ldw, int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW,
+                                      const int32_t* ib_src, const int32_t* ib_w, int exp_const, float* out, size_t ldc,
+                                      const float* addend, void* stream) {
+  if (!src_hi || !src_lo || !wp || !out) return LBT_EINVAL;
+  if (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8) return LBT_EINVAL;
+  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || OH <= 0 || OW <= 0 || pad_top < 0 || pad_left < 0)
+    return LBT_EINVAL;
+  if (ldc < (size_t)Cout || ldw < (size_t)kh * kw * C) return LBT_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(src_hi) & 15) || (reinterpret_cast<uintptr_t>(src_lo) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15) ||
+      (ldw & 15))
+    return LBT_EUNSUPPORTED;
+  if (!lbt::conv_halo_applies(N, OH, OW, C, Cout, kh, kw, 1, 1)) return LBT_EUNSUPPORTED;
+  LBT_REQUIRE_ARCH();
+  return lbt::conv_halo_run(src_hi, LBT_MANT_S8, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w,
+                            exp_const, nullptr, out, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr, src_lo);
+}
 
 // Test probe (not in lbt.h): launches of the halo kernel so far — lets a test assert which kernel a shape was routed to.
 extern "C" long long lbt_conv_halo_launches(void) { return lbt::g_halo_launches.load(std::memory_order_relaxed); }

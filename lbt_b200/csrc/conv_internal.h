@@ -34,7 +34,7 @@ int conv_stem_debug_error();   // conv_stem.cu (first-layer weight gradient)
 int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                   int kw, int pt, int pl, int OH, int OW, const int32_t* ibA, const int32_t* ibB, int exp_const, const float* bias,
                   float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums, const float* addend, void* stream,
-                  const OutRemap* remap = nullptr);
+                  const OutRemap* remap = nullptr, const void* src_lo = nullptr);   // src_lo: low byte plane (u8) of a 16-bit source
 // lbt_conv_i8_fprop's body; remap != NULL: fp32 epilogue only, the im2col-TMA or halo kernels only
 int conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                    int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_src, const int32_t* ib_w,

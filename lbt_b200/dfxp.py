@@ -947,18 +947,28 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw,
         ad2 = addend.reshape(N * H * W, Cin) if addend is not None else None
         one_by_one = kh == 1 and kw == 1 and sh == 1 and sw == 1 and Cout % 16 == 0 and pt == 0 and pl == 0
         rot = bool(prep is not None and prep.get('rot180'))
+        done = False
         if one_by_one:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(Cin, Cout))
             a_hi, a_lo = hi.view(M, Cout), lo.view(M, Cout)
         elif rot:
             w2 = pw2                                      # rot180-packed: dX = conv(G, rot180 W), padding k - 1 - pad
-            a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
-            a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
+            # both byte planes through the TMA halo kernel with two accumulators in tensor memory (no im2col matrices) where
+            # the filter bank and two patches per ring slot fit (64 gathered channels); else im2col of both planes + dual GEMM
+            done = DUAL_HALO and _lib.try_call(
+                'lbt_conv_i8_fprop_dual', _lib.ptr(hi), _lib.ptr(lo), N, OH, OW, Cout, _lib.ptr(w2),
+                Q.MANT_S8, w2.stride(0), Cin, kh, kw, kh - 1 - pt, kw - 1 - pl, H, W, _lib.ptr(layer.qG.range),
+                _lib.ptr(layer.qW.range), int(e), _lib.ptr(dx), Cin, _lib.ptr(ad2), _lib.stream(),
+                meta=dict(ops=2 * 2 * N * H * W * Cin * K2, bytes=2 * N * OH * OW * Cout + Cin * K2 + N * H * W * Cin * 4))
+            if not done:
+                a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
+                a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
             a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, sh, sw, pt, pl, True)
-        G.gemm_i8_dual(a_hi, a_lo, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin), addend=ad2)
+        if not done:
+            G.gemm_i8_dual(a_hi, a_lo, w2, ibA=layer.qG.range, ibB=layer.qW.range, exp_const=e, out=dx.view(N * H * W, Cin), addend=ad2)
     if fork:
         for t in (xm, hi, lo):
             t.record_stream(side)
@@ -1561,6 +1571,7 @@ FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lb
                       # tensor is one wave of CTAs.  Bit-identical; measured no faster on B200 (1.77 vs 1.75 ms ResNet-20
                       # step: the barrier + second fp64 prologue cost what the saved launch gains), so off by default
 FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused units (tests compare both settings)
+DUAL_HALO = os.environ.get('LBT_DUAL_HALO', '1') != '0'     # 16-bit gradients: stride-1 3x3 input gradients through lbt_conv_i8_fprop_dual
 FUSE_NEXT2 = os.environ.get('LBT_FUSE_NEXT2', '1') != '0'   # a strided block's shortcut convolution gets its input mantissas from the
                       # kernel that produced the block input too (lbt_bn_fwd_apply2) instead of a separate lbt_quantize
 

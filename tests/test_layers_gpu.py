@@ -547,3 +547,34 @@ def test_stem_wgrad_c3_equals_general_kernel_and_exact_sum(N, H, W, k):
         cols = cols.view(N, 3, k, k, -1, Lw)[:, :, :, :, :OH, :OW]                 # [N, c, r, s, oh, ow]
         ref = torch.einsum('ncrsyx,nkyx->rsck', cols, gg).reshape(k * k * 3, Cout)
         assert torch.equal(got.cpu().double(), ref)
+
+
+@pytest.mark.parametrize('N,H,W,Cout,k', [(2, 16, 16, 64, 3), (3, 30, 23, 64, 3), (1, 32, 40, 128, 3), (2, 16, 24, 32, 5)])
+def test_conv_dual_planes_equals_exact_sum(N, H, W, Cout, k):
+    """lbt_conv_i8_fprop_dual (16-bit source as hi / lo byte planes, two accumulators in tensor memory, one rounding) against
+    the exact integer convolution in fp64: out = RN_fp32((256 * conv(hi, W) + conv(lo, W)) * 2^e) + addend, stride 1 'SAME',
+    ragged patches included — the arithmetic of lbt_gemm_i8_dual on im2col matrices, which it replaces for 64-channel 3x3 layers."""
+    from lbt_b200 import _lib, quantizer as Q
+    C, pad = 64, k // 2
+    gen = torch.Generator().manual_seed(N * 100 + H + Cout)
+    hi = torch.randint(-128, 128, (N, H, W, C), generator=gen, dtype=torch.int32)
+    lo = torch.randint(0, 256, (N, H, W, C), generator=gen, dtype=torch.int32)
+    wt = torch.randint(-128, 128, (Cout, k, k, C), generator=gen, dtype=torch.int32)
+    addend = torch.randn(N * H * W, Cout, generator=gen)
+    ib_s = torch.tensor(2, dtype=torch.int32, device='cuda')
+    ib_w = torch.tensor(-1, dtype=torch.int32, device='cuda')
+    e = -20
+    out = torch.empty(N * H * W, Cout, dtype=torch.float32, device='cuda')
+    wp = wt.reshape(Cout, k * k * C).to(torch.int8).cuda().contiguous()
+    before = _lib.lib().lbt_conv_halo_launches()
+    hi_d, lo_d, ad_d = hi.to(torch.int8).cuda(), lo.to(torch.uint8).cuda(), addend.cuda()     # (kept alive across the call)
+    ok = _lib.try_call('lbt_conv_i8_fprop_dual', _lib.ptr(hi_d), _lib.ptr(lo_d), N, H, W, C,
+                       _lib.ptr(wp), Q.MANT_S8, wp.stride(0), Cout, k, k, pad, pad, H, W, _lib.ptr(ib_s), _lib.ptr(ib_w), e,
+                       _lib.ptr(out), Cout, _lib.ptr(ad_d), _lib.stream())
+    assert ok and _lib.lib().lbt_conv_halo_launches() == before + 1
+    torch.cuda.synchronize()
+    assert _lib.lib().lbt_conv_debug_error() == 0
+    src = (256 * hi + lo).permute(0, 3, 1, 2).double()
+    ref = F.conv2d(src, wt.permute(0, 3, 1, 2).double(), padding=pad).permute(0, 2, 3, 1).reshape(N * H * W, Cout)
+    want = (ref * 2.0 ** (e + 2 - 1)).float() + addend
+    assert torch.equal(out.cpu(), want)
