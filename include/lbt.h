@@ -270,6 +270,13 @@ int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C,
                       int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
                       int alpha, int k_splits, void* stream);
 
+/* lbt_conv_i8_wgrad for a 9..16-bit gradient given as its byte planes k = 256 * hi + lo (g_hi s8, g_lo u8; BASELINE config 5):
+ * ONE launch with two accumulators in tensor memory — the input blocks are loaded once and every element costs one int64
+ * atomic, acc64 += alpha * (256 * sum(src * hi) + sum(src * lo)) — instead of two lbt_conv_i8_wgrad passes (alpha = 256 | 1). */
+int lbt_conv_i8_wgrad_dual(const void* src, int src_kind, int N, int H, int W, int C, const int8_t* g_hi, const uint8_t* g_lo,
+                           int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW,
+                           int64_t* acc64, int alpha, int k_splits, void* stream);
+
 /*
  * Weight gradient of a FIRST convolution (3-channel 9-bit image, LBT_MANT_S9C3 pixels x16[N,H,W,16]) of stride 2 with
  * <= 8 x 8 taps and 64 output channels (the 7x7/2 ImageNet stem; tf.gradients(y, W, gradq), dynamic_fixed_point.py:207,

@@ -42,6 +42,8 @@ SIGNATURES = {
                           [c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     'lbt_conv_i8_wgrad': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int] + [c_int] * 9 +
                           [c_void_p, c_int, c_int, c_void_p]),
+    'lbt_conv_i8_wgrad_dual': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p] + [c_int] * 9 +
+                               [c_void_p, c_int, c_int, c_void_p]),
     'lbt_stem_pack8_bytes': (c_size_t, [c_int, c_int, c_int]),
     'lbt_stem_pack8': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'lbt_conv_i8_wgrad_c3': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p] + [c_int] * 8 + [c_void_p, c_int, c_void_p, c_int, c_void_p]),

@@ -76,6 +76,26 @@ struct Cfg {
 
 inline int ctas_per_sm(int bn) { return bn <= 16 ? 3 : (bn <= 128 ? 2 : 1); }
 
+// wgrad configuration.  DUAL: the gradient is a 9..16-bit mantissa as two byte planes (k = 256 * hi + lo, BASELINE config 5): both
+// planes' blocks ride in one ring slot and are multiplied with the SAME input block into two accumulators, so the input
+// operand is loaded once and every element costs ONE int64 atomic (256 * acc_hi + acc_lo) instead of two passes' two.
+template <int BN, bool DUAL>
+struct WCfg {
+  static constexpr int kStageA = Cfg<BN>::kStageA;
+  static constexpr int kStageB1 = Cfg<BN>::kStageB;                    // one plane
+  static constexpr int kStageBytes = kStageA + (DUAL ? 2 : 1) * kStageB1;
+  static constexpr int kCtasPerSm = Cfg<BN>::kCtasPerSm;
+  static constexpr int kBudget = (227 * 1024) / kCtasPerSm - 1024;
+  static constexpr int kStages = !DUAL ? Cfg<BN>::kStages : (kBudget / kStageBytes > 4 ? 4 : kBudget / kStageBytes);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kAccW = (DUAL ? 2 : 1) * BN;                     // tensor-memory columns of one accumulator stage
+  static constexpr int kAccStages = !DUAL ? Cfg<BN>::kAccStages : ((512 / kCtasPerSm) / kAccW > 4 ? 4 : (512 / kCtasPerSm) / kAccW);
+  static constexpr int kTmemCols = (kAccStages * kAccW) < 32 ? 32 : (kAccStages * kAccW);
+  static_assert(kStages >= 2 && kAccStages >= 1, "wgrad ring");
+  static_assert(kCtasPerSm * kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kCtasPerSm * kTmemCols <= 512, "tensor memory budget");
+};
+
 template <int BN>
 __global__ void __launch_bounds__(kThreadsF, Cfg<BN>::kCtasPerSm)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
@@ -350,12 +370,14 @@ struct WgradParams {
   long long* acc64;
   int alpha;
   uint32_t idesc;
+  uint32_t idesc2;               // DUAL: the low plane's MMAs (B = u8)
 };
 
-template <int BN>
+template <int BN, bool DUAL = false>
 __global__ void __launch_bounds__(kThreads, Cfg<BN>::kCtasPerSm)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgradParams p) {
-  using C = Cfg<BN>;
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmG2,
+                  const WgradParams p) {
+  using C = WCfg<BN, DUAL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
@@ -379,6 +401,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmG);
+    if (DUAL) tma_prefetch_desc(&tmG2);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
   pdl_trigger();
@@ -424,13 +447,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t ohu = fastdiv(rem, p.d_OW);
           const int oh = (int)ohu, ow = (int)(rem - ohu * p.OW);
           const int base_w = p.lower_w + ow * p.sw, base_h = p.lower_h + oh * p.sh;
-          mbar_expect_tx(&full_bar[stage], nblk * a_block + p.nchunks * b_block);
+          mbar_expect_tx(&full_bar[stage], nblk * a_block + (DUAL ? 2u : 1u) * p.nchunks * b_block);
 #pragma unroll
           for (uint32_t j = 0; j < 8; ++j)
             if (j < nblk)
               tma_load_im2col_4d(&tmX, &full_bar[stage], sa + j * a_block, jc[j], base_w, base_h, (int)img, js[j], jr[j]);
           for (uint32_t j = 0; j < p.nchunks; ++j)
             tma_load_2d(&tmG, &full_bar[stage], sb + j * b_block, (int)(n_tile * BN + j * p.cbn), (int)m0);
+          if (DUAL)
+            for (uint32_t j = 0; j < p.nchunks; ++j)
+              tma_load_2d(&tmG2, &full_bar[stage], sb + C::kStageB1 + j * b_block, (int)(n_tile * BN + j * p.cbn), (int)m0);
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1;
@@ -447,7 +473,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t pb0 = ks * p.blocks_per_split, pb1 = min(pb0 + p.blocks_per_split, p.pix_blocks);
         if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag, &g_conv_error))) break;
         fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * C::kAccW;
         for (uint32_t pb = pb0; pb < pb1; ++pb) {
           if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_conv_error))) break;
           fence_after();
@@ -456,8 +482,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (uint32_t kk = 0; kk < kBlockM / 32; ++kk) {
             // 32 pixels (K) per instruction: advance by 32 rows of the block
-            umma_i8(d_tmem, make_desc_mnmajor(sa + kk * 32 * p.cb, (int)p.mode_a, a_block),
-                    make_desc_mnmajor(sb + kk * 32 * p.cbn, (int)p.mode_b, b_block), p.idesc, (pb > pb0 || kk > 0) ? 1u : 0u);
+            const uint64_t da = make_desc_mnmajor(sa + kk * 32 * p.cb, (int)p.mode_a, a_block);
+            umma_i8(d_tmem, da, make_desc_mnmajor(sb + kk * 32 * p.cbn, (int)p.mode_b, b_block), p.idesc, (pb > pb0 || kk > 0) ? 1u : 0u);
+            if (DUAL)   // the low plane against the same input block, into the second accumulator
+              umma_i8(d_tmem + BN, da, make_desc_mnmajor(sb + C::kStageB1 + kk * 32 * p.cbn, (int)p.mode_b, b_block), p.idesc2,
+                      (pb > pb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == C::kStages) {
@@ -486,11 +515,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       fence_after();
       const uint32_t row = m_tile * kBlockM + quad * 32 + lane;   // (tap, channel) index kf
       const uint32_t col0 = n_tile * BN;
-      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      const uint32_t taddr = tmem_base + acc * C::kAccW + ((quad * 32u) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 16) {
-        uint32_t v[16];
+        uint32_t v[16], w[DUAL ? 16 : 1];
         tmem_ld16(taddr + c, v);
+        if constexpr (DUAL) tmem_ld16(taddr + BN + c, w);
         tmem_ld_wait();
         if (row < p.Kf && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));
@@ -498,7 +528,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             if (j < (int)ncol) {
-              const long long a = (long long)(int)v[j] * (long long)p.alpha;
+              long long a = (long long)(int)v[j];
+              if constexpr (DUAL) a = a * 256ll + (long long)(int)w[j];   // k = 256 * hi + lo
+              a *= (long long)p.alpha;
               if (a != 0) atomicAdd(o + j, (unsigned long long)a);
             }
         }
@@ -719,28 +751,31 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
 
 namespace lbt {
 namespace {
-template <int BN>
-int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tg, const WgradParams& p, unsigned grid, cudaStream_t st) {
+template <int BN, bool DUAL = false>
+int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tg, const CUtensorMap& tg2, const WgradParams& p, unsigned grid, cudaStream_t st) {
   static bool attr_done[16] = {};
   const int dev = device_info().device;
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, WCfg<BN, DUAL>::kSmemBytes);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_kernel)");
       return LBT_ECUDA;
     }
     attr_done[dev] = true;
   }
-  launch_pdl(conv_wgrad_kernel<BN>, grid, kThreads, Cfg<BN>::kSmemBytes, st, tx, tg, p);
-  return check_launch("lbt_conv_i8_wgrad");
+  launch_pdl(conv_wgrad_kernel<BN, DUAL>, grid, kThreads, WCfg<BN, DUAL>::kSmemBytes, st, tx, tg, tg2, p);
+  return check_launch(DUAL ? "lbt_conv_i8_wgrad_dual" : "lbt_conv_i8_wgrad");
 }
 }  // namespace
 }  // namespace lbt
 
-extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout,
-                                 int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
-                                 int alpha, int k_splits, void* stream) {
+// g_lo != NULL: g is the high byte plane (s8) and g_lo the low one (u8) of a 16-bit gradient: one dual-accumulator launch
+static int conv_wgrad_run(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, const void* g_lo, int Cout,
+                          int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
+                          int alpha, int k_splits, void* stream) {
+  const bool dual = g_lo != nullptr;
   if (!src || !g || !acc64) return LBT_EINVAL;
+  if (dual && (g_kind != LBT_MANT_S8 || (reinterpret_cast<uintptr_t>(g_lo) & 15))) return LBT_EUNSUPPORTED;
   if ((src_kind != LBT_MANT_S8 && src_kind != LBT_MANT_U8) || (g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8)) return LBT_EINVAL;
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
     return LBT_EINVAL;
@@ -752,7 +787,7 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
   LBT_REQUIRE_ARCH();
   // the gather wgrad only pays off for 16-byte pixel rows (elsewhere both kernels are bound by the int64 atomics)
-  if (conv_ldg_enabled() && k_splits <= 0 && C == 16 && Cout <= 16 && conv_wgrad_ldg_ok(C, Cout, kh, kw)) {
+  if (!dual && conv_ldg_enabled() && k_splits <= 0 && C == 16 && Cout <= 16 && conv_wgrad_ldg_ok(C, Cout, kh, kw)) {
     const int rc = conv_wgrad_ldg_run(src, src_kind, N, H, W, C, g, g_kind, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, acc64,
                                       alpha, stream);
     if (rc != LBT_EUNSUPPORTED) return rc;
@@ -764,6 +799,7 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
 
   int bn = Cout >= 256 ? 256 : Cout;  // 16, 32, 64, 128 or 256 (Cout is a multiple of cbn)
   if (Cout > 128 && Cout % 256) bn = 128;
+  if (dual && bn > 128) bn = 128;     // two accumulators of bn columns each per stage
   uint32_t mode_a = 0, mode_b = 0;
   while ((16u << mode_a) < cb) ++mode_a;
   while ((16u << mode_b) < cbn) ++mode_b;
@@ -809,8 +845,9 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
   p.acc64 = reinterpret_cast<long long*>(acc64);
   p.alpha = alpha;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, g_kind == LBT_MANT_S8, true, true, bn, kBlockM);
+  p.idesc2 = tc::make_idesc_i8(src_kind == LBT_MANT_S8, false, true, true, bn, kBlockM);
 
-  CUtensorMap tx, tg;
+  CUtensorMap tx, tg, tg2;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
@@ -837,18 +874,51 @@ extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, in
       set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(grad)");
       return LBT_ECUDA;
     }
+    tg2 = tg;
+    if (dual) {
+      r = enc_tiled(&tg2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(g_lo), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode_b), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(grad, low plane)");
+        return LBT_ECUDA;
+      }
+    }
   }
   const uint64_t items = (uint64_t)p.m_tiles * p.n_tiles * p.k_splits;
   const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm(bn);
   const unsigned grid = (unsigned)(items < cap ? items : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (bn) {
-    case 16: return launch_wgrad<16>(tx, tg, p, grid, st);
-    case 32: return launch_wgrad<32>(tx, tg, p, grid, st);
-    case 64: return launch_wgrad<64>(tx, tg, p, grid, st);
-    case 128: return launch_wgrad<128>(tx, tg, p, grid, st);
-    default: return launch_wgrad<256>(tx, tg, p, grid, st);
+  if (dual) {
+    switch (bn) {
+      case 16: return launch_wgrad<16, true>(tx, tg, tg2, p, grid, st);
+      case 32: return launch_wgrad<32, true>(tx, tg, tg2, p, grid, st);
+      case 64: return launch_wgrad<64, true>(tx, tg, tg2, p, grid, st);
+      default: return launch_wgrad<128, true>(tx, tg, tg2, p, grid, st);
+    }
   }
+  switch (bn) {
+    case 16: return launch_wgrad<16>(tx, tg, tg2, p, grid, st);
+    case 32: return launch_wgrad<32>(tx, tg, tg2, p, grid, st);
+    case 64: return launch_wgrad<64>(tx, tg, tg2, p, grid, st);
+    case 128: return launch_wgrad<128>(tx, tg, tg2, p, grid, st);
+    default: return launch_wgrad<256>(tx, tg, tg2, p, grid, st);
+  }
+}
+
+extern "C" int lbt_conv_i8_wgrad(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout,
+                                 int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, int64_t* acc64,
+                                 int alpha, int k_splits, void* stream) {
+  return conv_wgrad_run(src, src_kind, N, H, W, C, g, g_kind, nullptr, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, acc64, alpha,
+                        k_splits, stream);
+}
+
+extern "C" int lbt_conv_i8_wgrad_dual(const void* src, int src_kind, int N, int H, int W, int C, const int8_t* g_hi, const uint8_t* g_lo,
+                                      int Cout, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW,
+                                      int64_t* acc64, int alpha, int k_splits, void* stream) {
+  if (!g_lo) return LBT_EINVAL;
+  return conv_wgrad_run(src, src_kind, N, H, W, C, g_hi, LBT_MANT_S8, g_lo, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, acc64,
+                        alpha, k_splits, stream);
 }
 
 extern "C" int lbt_conv_debug_error(void) {

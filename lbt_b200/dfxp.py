@@ -917,7 +917,11 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw,
                 a = acc16.view(kh * kw, 16, Cout)
                 acc = (a[:, 0:3] + a[:, 3:6] + a[:, 6:9]).reshape(Kf, Cout).contiguous()
         elif layer.implicit and xkind != Q.MANT_S16 and _implicit_ok(Cin, kh, kw) and _implicit_ok(Cout, 1, 1):
-            for g_, kind, alpha in halves:
+            # both byte planes in ONE launch (two accumulators, the input blocks loaded once, one atomic per element) ...
+            done = DUAL_WGRAD and _lib.try_call('lbt_conv_i8_wgrad_dual', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(hi), _lib.ptr(lo),
+                                                Cout, kh, kw, sh, sw, pt, pl, OH, OW, _lib.ptr(acc), 1, 0, _lib.stream(),
+                                                meta=dict(ops=2 * M * Cout * Kf, bytes=N * H * W * Cin + 2 * M * Cout + 8 * Kf * Cout))
+            for g_, kind, alpha in (() if done else halves):      # ... else one pass per plane (alpha = 256 | 1)
                 _lib.call('lbt_conv_i8_wgrad', _lib.ptr(xm), xkind, N, H, W, Cin, _lib.ptr(g_), kind, Cout, kh, kw, sh, sw,
                           pt, pl, OH, OW, _lib.ptr(acc), alpha, 0, _lib.stream(),
                           meta=dict(ops=M * Cout * Kf, bytes=N * H * W * Cin + M * Cout + 8 * Kf * Cout))
@@ -1571,6 +1575,7 @@ FUSE_BN_BWD = False   # module switch: both BN backward passes in ONE launch (lb
                       # tensor is one wave of CTAs.  Bit-identical; measured no faster on B200 (1.77 vs 1.75 ms ResNet-20
                       # step: the barrier + second fp64 prologue cost what the saved launch gains), so off by default
 FUSE_UNITS = True     # module switch for the Conv2d_q + BatchNorm2d_q fused units (tests compare both settings)
+DUAL_WGRAD = os.environ.get('LBT_DUAL_WGRAD', '1') != '0'   # 16-bit gradients: weight gradient of both byte planes in one launch
 DUAL_HALO = os.environ.get('LBT_DUAL_HALO', '1') != '0'     # 16-bit gradients: stride-1 3x3 input gradients through lbt_conv_i8_fprop_dual
 FUSE_NEXT2 = os.environ.get('LBT_FUSE_NEXT2', '1') != '0'   # a strided block's shortcut convolution gets its input mantissas from the
                       # kernel that produced the block input too (lbt_bn_fwd_apply2) instead of a separate lbt_quantize
