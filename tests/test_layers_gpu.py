@@ -578,3 +578,28 @@ def test_conv_dual_planes_equals_exact_sum(N, H, W, Cout, k):
     ref = F.conv2d(src, wt.permute(0, 3, 1, 2).double(), padding=pad).permute(0, 2, 3, 1).reshape(N * H * W, Cout)
     want = (ref * 2.0 ** (e + 2 - 1)).float() + addend
     assert torch.equal(out.cpu(), want)
+
+
+@pytest.mark.parametrize('N,H,W,C,Cout,k,s', [(2, 16, 16, 64, 64, 3, 1), (3, 14, 14, 128, 256, 1, 1), (2, 17, 15, 16, 16, 3, 1),
+                                                (2, 16, 16, 64, 128, 3, 2), (1, 8, 8, 256, 512, 3, 1)])
+def test_wgrad_dual_planes_equals_two_passes(N, H, W, C, Cout, k, s):
+    """lbt_conv_i8_wgrad_dual (both byte planes of a 16-bit gradient, two accumulators, one atomic per element) against two
+    lbt_conv_i8_wgrad passes with alpha = 256 | 1: the int64 sums are equal."""
+    from lbt_b200 import _lib, quantizer as Q
+    OH, pt, _ = D.same_pad(H, k, s)
+    OW, pl, _ = D.same_pad(W, k, s)
+    gen = torch.Generator().manual_seed(N * 100 + C + Cout)
+    x = torch.randint(0, 256, (N, H, W, C), generator=gen, dtype=torch.int32).to(torch.uint8).cuda()
+    hi = torch.randint(-128, 128, (N * OH * OW, Cout), generator=gen, dtype=torch.int32).to(torch.int8).cuda()
+    lo = torch.randint(0, 256, (N * OH * OW, Cout), generator=gen, dtype=torch.int32).to(torch.uint8).cuda()
+    Kf = k * k * C
+    a = torch.zeros(Kf, Cout, dtype=torch.int64, device='cuda')
+    b = torch.zeros(Kf, Cout, dtype=torch.int64, device='cuda')
+    _lib.call('lbt_conv_i8_wgrad_dual', _lib.ptr(x), Q.MANT_U8, N, H, W, C, _lib.ptr(hi), _lib.ptr(lo), Cout, k, k, s, s, pt, pl, OH, OW,
+              _lib.ptr(a), 1, 0, _lib.stream())
+    for g_, kind, alpha in ((hi, Q.MANT_S8, 256), (lo, Q.MANT_U8, 1)):
+        _lib.call('lbt_conv_i8_wgrad', _lib.ptr(x), Q.MANT_U8, N, H, W, C, _lib.ptr(g_), kind, Cout, k, k, s, s, pt, pl, OH, OW,
+                  _lib.ptr(b), alpha, 0, _lib.stream())
+    torch.cuda.synchronize()
+    assert _lib.lib().lbt_conv_debug_error() == 0
+    assert torch.equal(a, b)
