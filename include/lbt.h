@@ -237,9 +237,9 @@ int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, int W, int C,
  * lbt_bn_bwd_apply emits for a 16-bit gradient quantiser, BASELINE config 5) with an 8-bit filter, as ONE implicit GEMM with two
  * accumulators in tensor memory: out[(n,oh,ow), co] = fp32(256 * (hi * W) + (lo * W)) * 2^e (+ addend), one rounding — the
  * arithmetic of lbt_gemm_i8_dual without the im2col matrices of the two planes.  With the rotated filter this is the stride-1
- * input gradient tf.gradients(y, X, gradq) (dynamic_fixed_point.py:305).  Shapes of the TMA halo kernel with a filter bank and
- * two patches per ring slot in shared memory (C == 64, 3x3 ... 5x5, Cout <= 128); else LBT_EUNSUPPORTED: lbt_im2col_i8 +
- * lbt_gemm_i8_dual.  e = exp_const + *ib_src + *ib_w.
+ * input gradient tf.gradients(y, X, gradq) (dynamic_fixed_point.py:305).  The TMA halo kernel (two patches per ring slot) where
+ * its filter bank fits beside them (C == 64), the im2col-TMA kernel (both planes' blocks per ring slot) for C >= 64 otherwise;
+ * LBT_EUNSUPPORTED for narrower sources or Cout < 64: lbt_im2col_i8 + lbt_gemm_i8_dual.  e = exp_const + *ib_src + *ib_w.
  */
 int lbt_conv_i8_fprop_dual(const int8_t* src_hi, const uint8_t* src_lo, int N, int H, int W, int C, const void* wp, int w_kind,
                            size_t ldw, int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW,

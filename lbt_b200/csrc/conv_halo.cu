@@ -582,23 +582,5 @@ int conv_halo_debug_error() {
 
 }  // namespace lbt
 
-extern "C" int lbt_conv_i8_fprop_dual(const int8_t* src_hi, const uint8_t* src_lo, int N, int H, int W, int C, const void* wp, int w_kind,
-                                      size_t ldw, int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW,
-                                      const int32_t* ib_src, const int32_t* ib_w, int exp_const, float* out, size_t ldc,
-                                      const float* addend, void* stream) {
-  if (!src_hi || !src_lo || !wp || !out) return LBT_EINVAL;
-  if (w_kind != LBT_MANT_S8 && w_kind != LBT_MANT_U8) return LBT_EINVAL;
-  if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || OH <= 0 || OW <= 0 || pad_top < 0 || pad_left < 0)
-    return LBT_EINVAL;
-  if (ldc < (size_t)Cout || ldw < (size_t)kh * kw * C) return LBT_EINVAL;
-  if ((reinterpret_cast<uintptr_t>(src_hi) & 15) || (reinterpret_cast<uintptr_t>(src_lo) & 15) || (reinterpret_cast<uintptr_t>(wp) & 15) ||
-      (ldw & 15))
-    return LBT_EUNSUPPORTED;
-  if (!lbt::conv_halo_applies(N, OH, OW, C, Cout, kh, kw, 1, 1)) return LBT_EUNSUPPORTED;
-  LBT_REQUIRE_ARCH();
-  return lbt::conv_halo_run(src_hi, LBT_MANT_S8, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w,
-                            exp_const, nullptr, out, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr, src_lo);
-}
-
 // Test probe (not in lbt.h): launches of the halo kernel so far — lets a test assert which kernel a shape was routed to.
 extern "C" long long lbt_conv_halo_launches(void) { return lbt::g_halo_launches.load(std::memory_order_relaxed); }

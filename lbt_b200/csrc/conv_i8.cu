@@ -53,6 +53,7 @@ struct ConvParams {
   float* out;
   size_t ldc;
   uint32_t idesc;
+  uint32_t idesc2;               // DUAL: the low plane's MMAs (A = u8)
   BnqParams bnq;                 // fused re-quantising epilogue (bnq.q.bits == 0: off)
   int remap;                     // fp32 rows go to out + img * rs_n + oh * rs_y + ow * rs_x (OutRemap) instead of row * ldc
   long long rs_n, rs_y, rs_x;
@@ -76,6 +77,25 @@ struct Cfg {
 
 inline int ctas_per_sm(int bn) { return bn <= 16 ? 3 : (bn <= 128 ? 2 : 1); }
 
+// fprop configuration.  DUAL: the SOURCE is a 9..16-bit mantissa as two byte planes (k = 256 * hi + lo: a 16-bit gradient on its
+// way to the input gradient, BASELINE config 5): both planes' im2col blocks ride in one ring slot and meet the same filter tile in
+// two accumulators; the fp32 epilogue rounds 256 * acc_hi + acc_lo once.  One CTA per SM (it owns all of tensor memory).
+template <int BN, bool DUAL>
+struct FCfg {
+  static constexpr int kStageA = Cfg<BN>::kStageA;
+  static constexpr int kStageB = Cfg<BN>::kStageB;
+  static constexpr int kStageBytes = (DUAL ? 2 : 1) * kStageA + kStageB;
+  static constexpr int kCtasPerSm = DUAL ? 1 : Cfg<BN>::kCtasPerSm;
+  static constexpr int kStages = DUAL ? ((226 * 1024) / kStageBytes > 4 ? 4 : (226 * 1024) / kStageBytes) : Cfg<BN>::kStages;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kAccW = (DUAL ? 2 : 1) * BN;
+  static constexpr int kAccStages = DUAL ? (512 / kAccW > 4 ? 4 : 512 / kAccW) : Cfg<BN>::kAccStages;
+  static constexpr int kTmemCols = (kAccStages * kAccW) < 32 ? 32 : (kAccStages * kAccW);
+  static_assert(kStages >= 2 && kAccStages >= 1, "fprop ring");
+  static_assert(kCtasPerSm * kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kCtasPerSm * kTmemCols <= 512, "tensor memory budget");
+};
+
 // wgrad configuration.  DUAL: the gradient is a 9..16-bit mantissa as two byte planes (k = 256 * hi + lo, BASELINE config 5): both
 // planes' blocks ride in one ring slot and are multiplied with the SAME input block into two accumulators, so the input
 // operand is loaded once and every element costs ONE int64 atomic (256 * acc_hi + acc_lo) instead of two passes' two.
@@ -96,10 +116,11 @@ struct WCfg {
   static_assert(kCtasPerSm * kTmemCols <= 512, "tensor memory budget");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreadsF, Cfg<BN>::kCtasPerSm)
-conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  using C = Cfg<BN>;
+template <int BN, bool DUAL = false>
+__global__ void __launch_bounds__(kThreadsF, FCfg<BN, DUAL>::kCtasPerSm)
+conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
+                  const ConvParams p) {
+  using C = FCfg<BN, DUAL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
@@ -124,6 +145,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     s_abort = 0;
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
+    if (DUAL) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_slot, C::kTmemCols);
@@ -156,15 +178,18 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (uint32_t ks = 0; ks < nstages_k; ++ks) {
           if (!(ok = mbar_wait(&empty_bar[stage], phase ^ 1, abort_flag, &g_conv_error))) break;
           uint8_t* sa = smem + stage * C::kStageBytes;
-          uint8_t* sb = sa + C::kStageA;
+          uint8_t* sb = sa + (DUAL ? 2 : 1) * C::kStageA;
           const uint32_t k0 = ks * spb;
           const uint32_t nblk = min(spb, p.ksteps - k0);
-          mbar_expect_tx(&full_bar[stage], nblk * (a_block + b_block));
+          mbar_expect_tx(&full_bar[stage], nblk * ((DUAL ? 2u : 1u) * a_block + b_block));
           for (uint32_t j = 0; j < nblk; ++j) {
             const uint32_t kstep = k0 + j;
             const bool pad = kstep >= p.ksteps_real;        // Cb == 16 pairing pad: B is OOB-zero, A is any tap
             tma_load_im2col_4d(&tmA, &full_bar[stage], sa + j * a_block, pad ? 0 : (int)(cc * p.cb), base_w, base_h, (int)img,
                                (uint16_t)(pad ? 0u : s), (uint16_t)(pad ? 0u : r));
+            if (DUAL)   // the low plane's block of the same tap / channel chunk
+              tma_load_im2col_4d(&tmA2, &full_bar[stage], sa + C::kStageA + j * a_block, pad ? 0 : (int)(cc * p.cb), base_w, base_h,
+                                 (int)img, (uint16_t)(pad ? 0u : s), (uint16_t)(pad ? 0u : r));
             tma_load_2d(&tmB, &full_bar[stage], sb + j * b_block, (int)(kstep * p.cb), (int)(n_tile * BN));
             if (++cc == p.cchunks) {
               cc = 0;
@@ -188,27 +213,31 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (uint32_t tile = blockIdx.x; tile < total_tiles && ok; tile += gridDim.x) {
         if (!(ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, abort_flag, &g_conv_error))) break;
         fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * C::kAccW;
         uint32_t first = 1;
         for (uint32_t ks = 0; ks < nstages_k; ++ks) {
           if (!(ok = mbar_wait(&full_bar[stage], phase, abort_flag, &g_conv_error))) break;
           fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + C::kStageA;
+          const uint32_t sb = sa + (DUAL ? 2 : 1) * C::kStageA;
           const uint32_t nblk = min(spb, p.ksteps - ks * spb);
           if (p.mode == 0) {
             // 16-byte rows: one K=32 instruction spans two consecutive tap-blocks (leading byte offset = block size)
             for (uint32_t j = 0; j < nblk; j += 2) {  // nblk is even: ksteps is padded to an even count
-              umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block, 0, a_block), make_desc_kmajor(sb + j * b_block, 0, b_block),
-                      p.idesc, first ? 0u : 1u);
+              const uint64_t db = make_desc_kmajor(sb + j * b_block, 0, b_block);
+              umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block, 0, a_block), db, p.idesc, first ? 0u : 1u);
+              if (DUAL) umma_i8(d_tmem + BN, make_desc_kmajor(sa + C::kStageA + j * a_block, 0, a_block), db, p.idesc2, first ? 0u : 1u);
               first = 0;
             }
           } else {
             const uint32_t per_block = p.cb / 32;
             for (uint32_t j = 0; j < nblk; ++j)
               for (uint32_t kk = 0; kk < per_block; ++kk) {
-                umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block + kk * 32, (int)p.mode, 16),
-                        make_desc_kmajor(sb + j * b_block + kk * 32, (int)p.mode, 16), p.idesc, first ? 0u : 1u);
+                const uint64_t db = make_desc_kmajor(sb + j * b_block + kk * 32, (int)p.mode, 16);
+                umma_i8(d_tmem, make_desc_kmajor(sa + j * a_block + kk * 32, (int)p.mode, 16), db, p.idesc, first ? 0u : 1u);
+                if (DUAL)   // the low plane against the same filter tile, into the second accumulator
+                  umma_i8(d_tmem + BN, make_desc_kmajor(sa + C::kStageA + j * a_block + kk * 32, (int)p.mode, 16), db, p.idesc2,
+                          first ? 0u : 1u);
                 first = 0;
               }
           }
@@ -259,7 +288,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
       fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((quad * 32u) << 16);
+      const uint32_t taddr = tmem_base + acc * C::kAccW + ((quad * 32u) << 16);
       if (fused && (n_tile != stat_ntile || bst.tiles >= (uint32_t)kBnqFlushTiles)) {
         bnq_flush(p.bnq, my_stat, stat_ntile * BN, BN, p.N, lane);
         stat_ntile = n_tile;
@@ -273,6 +302,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool fchunk = fused && col0 + c < p.N;   // warp-uniform
         if (BN > 16 && fchunk) bnq_load_noise(p.bnq, bst, pix, row < p.M, col0 + c, min(16u, p.N - (col0 + c)), p.N, u4);
         tmem_ld16(taddr + c, v);
+        uint32_t w[DUAL ? 16 : 1];
+        if constexpr (DUAL) tmem_ld16(taddr + BN + c, w);
         tmem_ld_wait();
         if (BN <= 16 && fchunk)   // the 16-column instantiation runs three CTAs per SM at 64 registers: no room for early loads
           bnq_load_noise(p.bnq, bst, pix, row < p.M, col0 + c, min(16u, p.N - (col0 + c)), p.N, u4);
@@ -295,7 +326,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            f[j] = __int2float_rn((int)v[j]) * scale;
+            if constexpr (DUAL) f[j] = __ll2float_rn((long long)(int)v[j] * 256ll + (long long)(int)w[j]) * scale;   // one rounding
+            else f[j] = __int2float_rn((int)v[j]) * scale;
             if (p.bias && j < (int)ncol) f[j] = __fadd_rn(f[j], __ldg(p.bias + col0 + c + j));
           }
           if (p.addend) {   // + an fp32 tensor of the output's shape (the other branch of a gradient sum)
@@ -575,20 +607,20 @@ CUtensorMapSwizzle swizzle_of(uint32_t mode) {
   }
 }
 
-template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, unsigned grid, cudaStream_t st) {
+template <int BN, bool DUAL = false>
+int launch(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tb, const ConvParams& p, unsigned grid, cudaStream_t st) {
   static bool attr_done[16] = {};
   const int dev = device_info().device;
   if (!attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_fprop_kernel<BN, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, FCfg<BN, DUAL>::kSmemBytes);
     if (e != cudaSuccess) {
       set_cuda_error(e, "cudaFuncSetAttribute(conv_fprop_kernel)");
       return LBT_ECUDA;
     }
     attr_done[dev] = true;
   }
-  launch_pdl(conv_fprop_kernel<BN>, grid, kThreadsF, Cfg<BN>::kSmemBytes, st, ta, tb, p);
-  return check_launch("lbt_conv_i8_fprop");
+  launch_pdl(conv_fprop_kernel<BN, DUAL>, grid, kThreadsF, FCfg<BN, DUAL>::kSmemBytes, st, ta, ta2, tb, p);
+  return check_launch(DUAL ? "lbt_conv_i8_fprop_dual" : "lbt_conv_i8_fprop");
 }
 
 }  // namespace
@@ -602,16 +634,28 @@ extern "C" int lbt_conv_i8_fprop(const void* src, int src_kind, int N, int H, in
                                  float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
                                  const float* addend, void* stream) {
   return conv_fprop_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, sh, sw, pad_top, pad_left, OH, OW, ib_src, ib_w,
-                        exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream, nullptr);
+                        exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream, nullptr, nullptr);
+}
+
+extern "C" int lbt_conv_i8_fprop_dual(const int8_t* src_hi, const uint8_t* src_lo, int N, int H, int W, int C, const void* wp, int w_kind,
+                                      size_t ldw, int Cout, int kh, int kw, int pad_top, int pad_left, int OH, int OW,
+                                      const int32_t* ib_src, const int32_t* ib_w, int exp_const, float* out, size_t ldc,
+                                      const float* addend, void* stream) {
+  if (!src_hi || !src_lo || !wp || !out) return LBT_EINVAL;
+  if (ldc < (size_t)Cout) return LBT_EINVAL;
+  return conv_fprop_run(src_hi, LBT_MANT_S8, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, 1, 1, pad_top, pad_left, OH, OW, ib_src, ib_w,
+                        exp_const, nullptr, out, ldc, nullptr, nullptr, nullptr, addend, stream, nullptr, src_lo);
 }
 
 int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout,
                         int kh, int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_src,
                         const int32_t* ib_w, int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out,
-                        int8_t* k_out, int64_t* sums, const float* addend, void* stream, const OutRemap* remap) {
+                        int8_t* k_out, int64_t* sums, const float* addend, void* stream, const OutRemap* remap, const void* src_lo) {
   const bool w_prepared = (w_kind & LBT_MANT_PREPARED) != 0;
   w_kind &= ~LBT_MANT_PREPARED;
+  const bool dual = src_lo != nullptr;   // src = high byte plane (s8), src_lo = low byte plane (u8) of a 16-bit source
   if (!src || !wp) return LBT_EINVAL;
+  if (dual && (q_out || bias || remap || !out || src_kind != LBT_MANT_S8 || (reinterpret_cast<uintptr_t>(src_lo) & 15))) return LBT_EUNSUPPORTED;
   if (q_out) {
     if (!k_out || !sums || !q_out->ib) return LBT_EINVAL;
     if (q_out->bits < 2 || q_out->bits > 8 || (Cout & 3)) return LBT_EUNSUPPORTED;
@@ -625,7 +669,7 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
   // measured (benchmarks/gemm_bench.py --path 0|1): the cp.async gather wins for 16- and 32-byte pixel rows (3.1x / 1.1x),
   // the TMA im2col kernel for 64 bytes and more
   if (remap && q_out) return LBT_EINVAL;
-  if (!remap && conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C))) &&
+  if (!dual && !remap && conv_ldg_enabled() && (C <= 32 || (C == 64 && conv_ldg_c64_halo() && conv_ldg_halo_applies(N, OH, OW, kh, kw, sh, sw, C))) &&
       conv_ldg_ok(C, Cout, kh, kw) && !(reinterpret_cast<uintptr_t>(src) & 15) &&
       !(reinterpret_cast<uintptr_t>(wp) & 15) && !(ldw & 15) && ldw >= (size_t)kh * kw * C && (q_out || ldc >= (size_t)Cout)) {
     LBT_REQUIRE_ARCH();   // narrow channels: the cp.async-gather kernel (conv_ldg.cu)
@@ -642,8 +686,9 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
   // stride-1 filters on 64- / 128-channel images that fill 8 x 16 patches: halo patches through the TMA engine (conv_halo.cu)
   if (conv_halo_applies(N, OH, OW, C, Cout, kh, kw, sh, sw)) {
     LBT_REQUIRE_ARCH();
-    return conv_halo_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w, exp_const,
-                         bias, out, ldc, q_out, k_out, sums, addend, stream, remap);
+    const int rc = conv_halo_run(src, src_kind, N, H, W, C, wp, w_kind, ldw, Cout, kh, kw, pad_top, pad_left, OH, OW, ib_src, ib_w,
+                                 exp_const, bias, out, ldc, q_out, k_out, sums, addend, stream, remap, src_lo);
+    if (!(dual && rc == LBT_EUNSUPPORTED)) return rc;   // two planes: the filter bank + two patches may not fit; im2col-TMA kernel below
   }
   if (Ktot > 65536) return LBT_EUNSUPPORTED;  // exactness bound of one s32 accumulator
   if (kh > 255 || kw > 255) return LBT_EUNSUPPORTED;
@@ -659,6 +704,8 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
       bn = c;
       break;
     }
+  if (dual && bn > 128) bn = 128;   // two accumulators of bn columns per stage
+  if (dual && bn < 64) return LBT_EUNSUPPORTED;
   uint32_t mode = 0;
   while ((16u << mode) < cb) ++mode;
 
@@ -692,6 +739,7 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
   p.out = out;
   p.ldc = ldc;
   p.idesc = tc::make_idesc_i8(src_kind == LBT_MANT_S8, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
+  p.idesc2 = tc::make_idesc_i8(false, w_kind == LBT_MANT_S8, false, false, bn, kBlockM);
   p.bnq.q = site_from_abi(q_out);
   p.bnq.k = k_out;
   p.bnq.sums = reinterpret_cast<long long*>(sums);
@@ -705,7 +753,7 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
 
   // A: im2col map over (C, W, H, N).  The bounding box of base pixels is [lower, dim + upper): with
   // lower = -pad_before and upper = pad_after - (k - 1) it has exactly (out - 1) * stride + 1 positions.
-  CUtensorMap ta, tb;
+  CUtensorMap ta, ta2, tb;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t gstr[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)H * W * C};
@@ -722,6 +770,16 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
       set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeIm2col");
       return LBT_ECUDA;
     }
+    ta2 = ta;
+    if (dual) {
+      r = enc_im2col(&ta2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(src_lo), gdim, gstr, lower, upper, cb, kBlockM,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(mode), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeIm2col(low plane)");
+        return LBT_ECUDA;
+      }
+    }
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
@@ -737,15 +795,16 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
     }
   }
   const uint64_t tiles = (uint64_t)p.m_tiles * p.n_tiles;
-  const uint64_t cap = (uint64_t)di.sm_count * ctas_per_sm(bn);
+  const uint64_t cap = (uint64_t)di.sm_count * (dual ? 1 : ctas_per_sm(bn));
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dual) return bn == 64 ? launch<64, true>(ta, ta2, tb, p, grid, st) : launch<128, true>(ta, ta2, tb, p, grid, st);
   switch (bn) {
-    case 16: return launch<16>(ta, tb, p, grid, st);
-    case 32: return launch<32>(ta, tb, p, grid, st);
-    case 64: return launch<64>(ta, tb, p, grid, st);
-    case 128: return launch<128>(ta, tb, p, grid, st);
-    default: return launch<256>(ta, tb, p, grid, st);
+    case 16: return launch<16>(ta, ta2, tb, p, grid, st);
+    case 32: return launch<32>(ta, ta2, tb, p, grid, st);
+    case 64: return launch<64>(ta, ta2, tb, p, grid, st);
+    case 128: return launch<128>(ta, ta2, tb, p, grid, st);
+    default: return launch<256>(ta, ta2, tb, p, grid, st);
   }
 }
 

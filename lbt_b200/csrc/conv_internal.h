@@ -39,7 +39,7 @@ int conv_halo_run(const void* src, int src_kind, int N, int H, int W, int C, con
 int conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int C, const void* wp, int w_kind, size_t ldw, int Cout, int kh,
                    int kw, int sh, int sw, int pad_top, int pad_left, int OH, int OW, const int32_t* ib_src, const int32_t* ib_w,
                    int exp_const, const float* bias, float* out, size_t ldc, const lbt_qsite* q_out, int8_t* k_out, int64_t* sums,
-                   const float* addend, void* stream, const OutRemap* remap);
+                   const float* addend, void* stream, const OutRemap* remap, const void* src_lo = nullptr);   // src_lo: see conv_halo_run
 
 bool conv_wgrad_ldg_ok(int C, int Cout, int kh, int kw);
 int conv_wgrad_ldg_run(const void* src, int src_kind, int N, int H, int W, int C, const void* g, int g_kind, int Cout, int kh, int kw,

@@ -549,13 +549,17 @@ def test_stem_wgrad_c3_equals_general_kernel_and_exact_sum(N, H, W, k):
         assert torch.equal(got.cpu().double(), ref)
 
 
-@pytest.mark.parametrize('N,H,W,Cout,k', [(2, 16, 16, 64, 3), (3, 30, 23, 64, 3), (1, 32, 40, 128, 3), (2, 16, 24, 32, 5)])
-def test_conv_dual_planes_equals_exact_sum(N, H, W, Cout, k):
+@pytest.mark.parametrize('N,H,W,C,Cout,k,halo', [(2, 16, 16, 64, 64, 3, True), (3, 30, 23, 64, 64, 3, True), (1, 32, 40, 64, 128, 3, True),
+                                                   (3, 20, 13, 64, 64, 3, False),      # ragged: the halo kernel declines, im2col-TMA kernel
+                                                   (2, 14, 14, 128, 128, 3, False),    # filter bank + two patches do not fit: im2col-TMA
+                                                   (2, 14, 14, 256, 256, 3, False), (1, 7, 7, 512, 512, 3, False)])
+def test_conv_dual_planes_equals_exact_sum(N, H, W, C, Cout, k, halo):
     """lbt_conv_i8_fprop_dual (16-bit source as hi / lo byte planes, two accumulators in tensor memory, one rounding) against
     the exact integer convolution in fp64: out = RN_fp32((256 * conv(hi, W) + conv(lo, W)) * 2^e) + addend, stride 1 'SAME',
-    ragged patches included — the arithmetic of lbt_gemm_i8_dual on im2col matrices, which it replaces for 64-channel 3x3 layers."""
+    on the TMA halo kernel and on the im2col-TMA kernel — the arithmetic of lbt_gemm_i8_dual on im2col matrices, which it
+    replaces for the 3x3 input gradients of BASELINE config 5."""
     from lbt_b200 import _lib, quantizer as Q
-    C, pad = 64, k // 2
+    pad = k // 2
     gen = torch.Generator().manual_seed(N * 100 + H + Cout)
     hi = torch.randint(-128, 128, (N, H, W, C), generator=gen, dtype=torch.int32)
     lo = torch.randint(0, 256, (N, H, W, C), generator=gen, dtype=torch.int32)
@@ -563,7 +567,7 @@ def test_conv_dual_planes_equals_exact_sum(N, H, W, Cout, k):
     addend = torch.randn(N * H * W, Cout, generator=gen)
     ib_s = torch.tensor(2, dtype=torch.int32, device='cuda')
     ib_w = torch.tensor(-1, dtype=torch.int32, device='cuda')
-    e = -20
+    e = -24
     out = torch.empty(N * H * W, Cout, dtype=torch.float32, device='cuda')
     wp = wt.reshape(Cout, k * k * C).to(torch.int8).cuda().contiguous()
     before = _lib.lib().lbt_conv_halo_launches()
@@ -571,7 +575,7 @@ def test_conv_dual_planes_equals_exact_sum(N, H, W, Cout, k):
     ok = _lib.try_call('lbt_conv_i8_fprop_dual', _lib.ptr(hi_d), _lib.ptr(lo_d), N, H, W, C,
                        _lib.ptr(wp), Q.MANT_S8, wp.stride(0), Cout, k, k, pad, pad, H, W, _lib.ptr(ib_s), _lib.ptr(ib_w), e,
                        _lib.ptr(out), Cout, _lib.ptr(ad_d), _lib.stream())
-    assert ok and _lib.lib().lbt_conv_halo_launches() == before + 1
+    assert ok and _lib.lib().lbt_conv_halo_launches() == before + (1 if halo else 0)
     torch.cuda.synchronize()
     assert _lib.lib().lbt_conv_debug_error() == 0
     src = (256 * hi + lo).permute(0, 3, 1, 2).double()
