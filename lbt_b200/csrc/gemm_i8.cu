@@ -337,6 +337,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = (BN > 16 ? 16 * (int)half : 0); c < BN; c += (BN > 16 ? 32 : 16)) {
         if (BN == 16 && half) break;  // a single chunk: the second warp of the quadrant has nothing to do
         uint32_t v[16];
+        float4 u4[4];   // fused: the chunk's noise, requested before the accumulator wait (bnq_load_noise; not in the 64-register BN = 16 build)
+        const bool fchunk = !DUAL && BN > 16 && fused && col0 + c < p.N;   // warp-uniform
+        if (fchunk) bnq_load_noise(p.bnq, bst, pix, row < p.M, col0 + c, min(16u, p.N - (col0 + c)), p.N, u4);
         tmem_ld16(taddr + c, v);
         if (DUAL) {   // host guarantees LBT_EPI_F32, no fused quantiser, k_splits == 1
           uint32_t w[16];
@@ -370,8 +373,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (fused) {
           if (col0 + c < p.N) {  // warp-uniform
             const uint32_t ncol = min(16u, p.N - (col0 + c));
-            bnq_chunk(p.bnq, bst, v, scale, p.bias ? p.bias + col0 + c : nullptr, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
-                      (uint32_t)c, lane);
+            if (fchunk)
+              bnq_chunk(p.bnq, bst, v, u4, scale, p.bias ? p.bias + col0 + c : nullptr, row, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
+                        (uint32_t)c, lane);
+            else
+              bnq_chunk(p.bnq, bst, v, scale, p.bias ? p.bias + col0 + c : nullptr, row, pix, row < p.M, col0 + c, ncol, p.N, my_stat, BN,
+                        (uint32_t)c, lane);
           }
         } else if (row < p.M && col0 + c < p.N) {
           const uint32_t ncol = min(16u, p.N - (col0 + c));
