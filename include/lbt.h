@@ -661,6 +661,12 @@ int lbt_conv_i8_dgrad_strided(const void* g, int g_kind, int N, int OH, int OW, 
                               int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
                               const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
                               const float* addend, void* stream);
+/* The same for a 9..16-bit gradient given as its byte planes k = 256 * hi + lo (g_hi s8, g_lo u8; BASELINE config 5): every class is
+ * a dual-accumulator convolution (lbt_conv_i8_fprop_dual's kernels), one rounding.  Cin >= 64, Cout == 64 or a multiple of 128. */
+int lbt_conv_i8_dgrad_strided_dual(const int8_t* g_hi, const uint8_t* g_lo, int N, int OH, int OW, int Cout, const void* w2,
+                                   int w_kind, size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left,
+                                   int H, int W, const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
+                                   const float* addend, void* stream);
 
 #ifdef __cplusplus
 }

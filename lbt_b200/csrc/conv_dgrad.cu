@@ -39,12 +39,15 @@ __global__ void __launch_bounds__(256) dgrad_fill_kernel(float* __restrict__ out
 
 using namespace lbt;
 
-extern "C" int lbt_conv_i8_dgrad_strided(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* w2, int w_kind,
-                                         size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
-                                         const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
-                                         const float* addend, void* stream) {
+// g_lo != NULL: g is the high byte plane (s8) and g_lo the low one (u8) of a 16-bit gradient (k = 256 * hi + lo): every class runs
+// as a dual-accumulator convolution (lbt_conv_i8_fprop_dual's kernels, one rounding)
+static int dgrad_strided_run(const void* g, int g_kind, const void* g_lo, int N, int OH, int OW, int Cout, const void* w2, int w_kind,
+                             size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
+                             const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
+                             const float* addend, void* stream) {
   if (!g || !w2 || !dx) return LBT_EINVAL;
   if ((g_kind != LBT_MANT_S8 && g_kind != LBT_MANT_U8)) return LBT_EINVAL;
+  if (g_lo && (g_kind != LBT_MANT_S8 || Cin < 64 || (Cout != 64 && Cout % 128))) return LBT_EUNSUPPORTED;
   if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || OH <= 0 || OW <= 0)
     return LBT_EINVAL;
   if (pad_top < 0 || pad_left < 0 || ldc < (size_t)Cin || ldw < (size_t)kh * kw * Cout) return LBT_EINVAL;
@@ -82,8 +85,25 @@ extern "C" int lbt_conv_i8_dgrad_strided(const void* g, int g_kind, int N, int O
       const int pt2 = nr - 1 - (a + pad_top) / sh, pl2 = nc - 1 - (b + pad_left) / sw;
       const uint8_t* wp = reinterpret_cast<const uint8_t*>(w2) + (size_t)class_group_offset(r0, s0, kh, kw, sh, sw) * Cout;
       const int rc = conv_fprop_run(g, g_kind, N, OH, OW, Cout, wp, w_kind, ldw, Cin, nr, nc, 1, 1, pt2, pl2, Hc, Wc, ib_g, ib_w,
-                                    exp_const, nullptr, out, ldc, nullptr, nullptr, nullptr, ad, stream, &rm);
+                                    exp_const, nullptr, out, ldc, nullptr, nullptr, nullptr, ad, stream, &rm, g_lo);
       if (rc) return rc;
     }
   return LBT_OK;
+}
+
+extern "C" int lbt_conv_i8_dgrad_strided(const void* g, int g_kind, int N, int OH, int OW, int Cout, const void* w2, int w_kind,
+                                         size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left, int H, int W,
+                                         const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
+                                         const float* addend, void* stream) {
+  return dgrad_strided_run(g, g_kind, nullptr, N, OH, OW, Cout, w2, w_kind, ldw, Cin, kh, kw, sh, sw, pad_top, pad_left, H, W, ib_g, ib_w,
+                           exp_const, dx, ldc, addend, stream);
+}
+
+extern "C" int lbt_conv_i8_dgrad_strided_dual(const int8_t* g_hi, const uint8_t* g_lo, int N, int OH, int OW, int Cout, const void* w2,
+                                              int w_kind, size_t ldw, int Cin, int kh, int kw, int sh, int sw, int pad_top, int pad_left,
+                                              int H, int W, const int32_t* ib_g, const int32_t* ib_w, int exp_const, float* dx, size_t ldc,
+                                              const float* addend, void* stream) {
+  if (!g_lo) return LBT_EINVAL;
+  return dgrad_strided_run(g_hi, LBT_MANT_S8, g_lo, N, OH, OW, Cout, w2, w_kind, ldw, Cin, kh, kw, sh, sw, pad_top, pad_left, H, W, ib_g,
+                           ib_w, exp_const, dx, ldc, addend, stream);
 }

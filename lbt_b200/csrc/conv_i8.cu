@@ -655,7 +655,7 @@ int lbt::conv_fprop_run(const void* src, int src_kind, int N, int H, int W, int 
   w_kind &= ~LBT_MANT_PREPARED;
   const bool dual = src_lo != nullptr;   // src = high byte plane (s8), src_lo = low byte plane (u8) of a 16-bit source
   if (!src || !wp) return LBT_EINVAL;
-  if (dual && (q_out || bias || remap || !out || src_kind != LBT_MANT_S8 || (reinterpret_cast<uintptr_t>(src_lo) & 15))) return LBT_EUNSUPPORTED;
+  if (dual && (q_out || bias || !out || src_kind != LBT_MANT_S8 || (reinterpret_cast<uintptr_t>(src_lo) & 15))) return LBT_EUNSUPPORTED;
   if (q_out) {
     if (!k_out || !sums || !q_out->ib) return LBT_EINVAL;
     if (q_out->bits < 2 || q_out->bits > 8 || (Cout & 3)) return LBT_EUNSUPPORTED;

@@ -520,6 +520,9 @@ DGRAD_CLASSES = True      # module switch (tests): strided input gradients with 
 def _dgrad_classes_ok(layer, Cin, Cout, kh, kw, sh, sw):
     """Strided input gradients that run as stride-1 sub-convolutions per parity class (lbt_conv_i8_dgrad_strided) instead of
     a transposed im2col matrix + GEMM: everything the gather kernel does not take."""
+    if layer.qG.bits > 8:      # 16-bit gradients: the classes run on the dual-accumulator kernels (lbt_conv_i8_dgrad_strided_dual)
+        return (DGRAD_CLASSES and DUAL_HALO and layer.implicit and (sh, sw) != (1, 1) and sh <= 4 and sw <= 4 and layer.qG.bits <= 16 and
+                layer.qW.bits <= 8 and (Cout == 64 or Cout % 128 == 0) and Cin >= 64 and Cin % 4 == 0)
     return (DGRAD_CLASSES and layer.implicit and (sh, sw) != (1, 1) and sh <= 4 and sw <= 4 and layer.qG.bits <= 8 and
             layer.qW.bits <= 8 and (Cout in (16, 32, 64) or Cout % 128 == 0) and Cin % 4 == 0 and
             not _gather_ok(Cout, Cin, kh, kw))
@@ -967,6 +970,13 @@ def _conv_backward16(layer, geom, xm, xkind, wm, prep, hi, lo, need_dx, need_dw,
             if not done:
                 a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
                 a_lo = _im2col(lo, Q.MANT_U8, H, W, kh, kw, 1, 1, kh - 1 - pt, kw - 1 - pl, False)
+        elif prep is not None and prep.get('classes'):
+            # strided layer: one dual-accumulator stride-1 sub-convolution per parity class (class-ordered filter from lbt_param_prep)
+            _lib.call('lbt_conv_i8_dgrad_strided_dual', _lib.ptr(hi), _lib.ptr(lo), N, OH, OW, Cout, _lib.ptr(pw2), Q.MANT_S8,
+                      pw2.stride(0), Cin, kh, kw, sh, sw, pt, pl, H, W, _lib.ptr(layer.qG.range), _lib.ptr(layer.qW.range), int(e),
+                      _lib.ptr(dx), Cin, _lib.ptr(ad2), _lib.stream(),
+                      meta=dict(ops=2 * 2 * N * OH * OW * Cin * K2, bytes=2 * N * OH * OW * Cout * min(sh * sw, kh * kw) + Cin * K2 + N * H * W * Cin * 4))
+            done = True
         else:
             w2 = pw2 if pw2 is not None else _as_operand(wm.view(kh * kw, Cin, Cout).permute(1, 0, 2).reshape(Cin, K2))
             a_hi = _im2col(hi, Q.MANT_S8, H, W, kh, kw, sh, sw, pt, pl, True)
